@@ -1,0 +1,56 @@
+/*
+ * mtgl_context.h -- context management of the B200-native MyTinyGL.
+ *
+ * Mirrors the context API of the reference (src/mytinygl.h:228-233: gl_create_context,
+ * gl_destroy_context, gl_make_current, gl_get_current_context).  GLState is opaque here; the one
+ * thing applications reach into it for in the reference -- ctx->framebuffer.color, read by
+ * mtgl_swap (include/mytinygl/sdl.h:76-81) -- is exposed through mtgl_map_framebuffer(), which
+ * first makes the host mirror of the device planes current.
+ */
+#ifndef MTGL_CONTEXT_H
+#define MTGL_CONTEXT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct GLState GLState;
+
+/* NULL on failure (bad size, no CUDA device, out of memory) exactly like gl_api.c:81-90.
+ * There is no CPU fallback: without a usable sm_100a device the call fails. */
+GLState *gl_create_context(int32_t width, int32_t height);
+void gl_destroy_context(GLState *ctx);
+void gl_make_current(GLState *ctx);
+GLState *gl_get_current_context(void);
+
+/* framebuffer_t (src/framebuffer.h:19-25): row 0 = top, pitch = width */
+typedef struct mtgl_framebuffer {
+    int32_t width;
+    int32_t height;
+    uint32_t *color;    /* a<<24 | b<<16 | g<<8 | r */
+    float *depth;
+    uint8_t *stencil;
+} mtgl_framebuffer;
+
+#define MTGL_PLANE_COLOR   1u
+#define MTGL_PLANE_DEPTH   2u
+#define MTGL_PLANE_STENCIL 4u
+
+/* Flush queued work, wait for the GPU and copy the selected planes into the context's host
+ * mirror; returns the mirror (valid until the next gl* call on the context) or NULL on error. */
+const mtgl_framebuffer *mtgl_map_framebuffer(GLState *ctx, unsigned planes);
+
+/* Back-end handle of a context (struct mtgl_dev*, include/mtgl_dev.h) for tools that need device
+ * plane pointers, band ownership or timing counters. */
+struct mtgl_dev *mtgl_context_device(GLState *ctx);
+
+/* Select the CUDA ordinal used by contexts created afterwards on this thread (-1 = current). */
+void mtgl_set_device(int ordinal);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MTGL_CONTEXT_H */

@@ -1,0 +1,914 @@
+/*
+ * scenes.c -- headless scene recipes shared by the parity tests and the benchmark.
+ *
+ * Uses ONLY the public gl* API (GL/gl.h), so the very same translation unit is compiled twice:
+ * into oracle/_ref/libref_*.so together with the unmodified reference sources, and into the
+ * product library.  The recipes restate the reference's interactive testbed programs without
+ * SDL (testbed/1.0-7, 1.0-9, 1.0-14, 1.0-15, 1.0-17, 1.0-18, 1.5-0 ...) plus the five BASELINE.json
+ * configurations as fixed by SURVEY.md section 8(d).
+ *
+ * The Suzanne mesh is not stored here: the harness passes it in (tests/golden/suzanne.npz,
+ * extracted from the reference's testbed/suzanne_data.h by tests/golden/make_fixtures.py).
+ */
+#include <GL/gl.h>
+
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------------------------------------------------------------- mesh supplied by the harness */
+static float *g_mesh_pos;   /* nv * 3 */
+static float *g_mesh_nrm;   /* nv * 3 */
+static int *g_mesh_faces;   /* nf * 3 vertex indices (normal index == vertex index) */
+static int g_mesh_nv, g_mesh_nf;
+
+void scene_set_mesh(const float *pos, const float *nrm, const int *faces, int nv, int nf)
+{
+    free(g_mesh_pos); free(g_mesh_nrm); free(g_mesh_faces);
+    g_mesh_pos = (float *)malloc(sizeof(float) * 3 * (size_t)nv);
+    g_mesh_nrm = (float *)malloc(sizeof(float) * 3 * (size_t)nv);
+    g_mesh_faces = (int *)malloc(sizeof(int) * 3 * (size_t)nf);
+    memcpy(g_mesh_pos, pos, sizeof(float) * 3 * (size_t)nv);
+    memcpy(g_mesh_nrm, nrm, sizeof(float) * 3 * (size_t)nv);
+    memcpy(g_mesh_faces, faces, sizeof(int) * 3 * (size_t)nf);
+    g_mesh_nv = nv; g_mesh_nf = nf;
+}
+
+/* ---------------------------------------------------------------- procedural textures */
+static GLuint make_checker_rgb(int size, int cell, int white_first) /* 1.0-7:25-42 / 1.0-14:50-64 */
+{
+    uint8_t *px = (uint8_t *)malloc((size_t)size * size * 3);
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            int on = ((x / cell) + (y / cell)) % 2;
+            if (white_first) on = !on;
+            uint8_t *p = px + ((size_t)y * size + x) * 3;
+            if (on) { p[0] = 255; p[1] = 255; p[2] = 255; } else { p[0] = 50; p[1] = 50; p[2] = 200; }
+        }
+    GLuint id;
+    glGenTextures(1, &id);
+    glBindTexture(GL_TEXTURE_2D, id);
+    glTexImage2D(GL_TEXTURE_2D, 0, GL_RGB, size, size, 0, GL_RGB, GL_UNSIGNED_BYTE, px);
+    free(px);
+    return id;
+}
+
+static GLuint make_radial_rgba(int size) /* 1.0-15:40-73 */
+{
+    uint8_t *px = (uint8_t *)malloc((size_t)size * size * 4);
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            uint8_t *p = px + ((size_t)y * size + x) * 4;
+            float cx = (x - size / 2.0f) / (size / 2.0f);
+            float cy = (y - size / 2.0f) / (size / 2.0f);
+            float dist = sqrtf(cx * cx + cy * cy);
+            if (dist < 0.8f) {
+                float alpha = 1.0f - (dist / 0.8f);
+                p[0] = 255; p[1] = 255; p[2] = 0; p[3] = (uint8_t)(alpha * 255);
+            } else { p[0] = p[1] = p[2] = p[3] = 0; }
+        }
+    GLuint id;
+    glGenTextures(1, &id);
+    glBindTexture(GL_TEXTURE_2D, id);
+    glTexImage2D(GL_TEXTURE_2D, 0, GL_RGBA, size, size, 0, GL_RGBA, GL_UNSIGNED_BYTE, px);
+    free(px);
+    return id;
+}
+
+static GLuint make_gradient_la(int w, int h) /* luminance+alpha ramp: exercises the LA upload and non-square sizes */
+{
+    uint8_t *px = (uint8_t *)malloc((size_t)w * h * 2);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            px[((size_t)y * w + x) * 2] = (uint8_t)((x * 255) / (w > 1 ? w - 1 : 1));
+            px[((size_t)y * w + x) * 2 + 1] = (uint8_t)(255 - (y * 200) / (h > 1 ? h - 1 : 1));
+        }
+    GLuint id;
+    glGenTextures(1, &id);
+    glBindTexture(GL_TEXTURE_2D, id);
+    glTexImage2D(GL_TEXTURE_2D, 0, GL_LUMINANCE_ALPHA, w, h, 0, GL_LUMINANCE_ALPHA, GL_UNSIGNED_BYTE, px);
+    free(px);
+    return id;
+}
+
+/* ---------------------------------------------------------------- helpers */
+static void frustum_like_testbed(int w, int h, double zfar) /* 1.0-18:95-101 */
+{
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    float aspect = (float)w / (float)h;
+    glFrustum(-aspect * 0.1, aspect * 0.1, -0.1, 0.1, 0.1, zfar);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+}
+
+static void suzanne_immediate(void) /* 1.0-18:25-41 */
+{
+    glBegin(GL_TRIANGLES);
+    for (int i = 0; i < g_mesh_nf; i++)
+        for (int j = 0; j < 3; j++) {
+            int vi = g_mesh_faces[i * 3 + j];
+            glNormal3f(g_mesh_nrm[vi * 3], g_mesh_nrm[vi * 3 + 1], g_mesh_nrm[vi * 3 + 2]);
+            glVertex3f(g_mesh_pos[vi * 3], g_mesh_pos[vi * 3 + 1], g_mesh_pos[vi * 3 + 2]);
+        }
+    glEnd();
+}
+
+static void suzanne_lights_and_material(void) /* 1.0-18:107-138 */
+{
+    glEnable(GL_LIGHTING);
+    glEnable(GL_LIGHT0);
+    glEnable(GL_LIGHT1);
+    GLfloat l0p[] = { 3.0f, 3.0f, 3.0f, 0.0f }, l0d[] = { 1.0f, 0.95f, 0.9f, 1.0f }, l0s[] = { 1, 1, 1, 1 };
+    glLightfv(GL_LIGHT0, GL_POSITION, l0p);
+    glLightfv(GL_LIGHT0, GL_DIFFUSE, l0d);
+    glLightfv(GL_LIGHT0, GL_SPECULAR, l0s);
+    GLfloat l1p[] = { -2.0f, -1.0f, 2.0f, 0.0f }, l1d[] = { 0.3f, 0.4f, 0.5f, 1.0f };
+    glLightfv(GL_LIGHT1, GL_POSITION, l1p);
+    glLightfv(GL_LIGHT1, GL_DIFFUSE, l1d);
+    GLfloat amb[] = { 0.15f, 0.15f, 0.2f, 1.0f };
+    glLightModelfv(GL_LIGHT_MODEL_AMBIENT, amb);
+    GLfloat ma[] = { 0.3f, 0.2f, 0.1f, 1.0f }, md[] = { 0.8f, 0.5f, 0.3f, 1.0f }, ms[] = { 0.4f, 0.4f, 0.4f, 1.0f };
+    glMaterialfv(GL_FRONT_AND_BACK, GL_AMBIENT, ma);
+    glMaterialfv(GL_FRONT_AND_BACK, GL_DIFFUSE, md);
+    glMaterialfv(GL_FRONT_AND_BACK, GL_SPECULAR, ms);
+    glMaterialf(GL_FRONT_AND_BACK, GL_SHININESS, 32.0f);
+}
+
+static void cube_quads(float size, float uvs) /* geometry of 1.0-7:45-102, texture coordinates scaled by uvs */
+{
+    float s = size / 2.0f;
+    static const float f[6][4][5] = {
+        { { -1, -1, 1, 0, 0 }, { 1, -1, 1, 1, 0 }, { 1, 1, 1, 1, 1 }, { -1, 1, 1, 0, 1 } },
+        { { -1, -1, -1, 1, 0 }, { -1, 1, -1, 1, 1 }, { 1, 1, -1, 0, 1 }, { 1, -1, -1, 0, 0 } },
+        { { -1, 1, -1, 0, 1 }, { -1, 1, 1, 0, 0 }, { 1, 1, 1, 1, 0 }, { 1, 1, -1, 1, 1 } },
+        { { -1, -1, -1, 1, 1 }, { 1, -1, -1, 0, 1 }, { 1, -1, 1, 0, 0 }, { -1, -1, 1, 1, 0 } },
+        { { 1, -1, -1, 1, 0 }, { 1, 1, -1, 1, 1 }, { 1, 1, 1, 0, 1 }, { 1, -1, 1, 0, 0 } },
+        { { -1, -1, -1, 0, 0 }, { -1, -1, 1, 1, 0 }, { -1, 1, 1, 1, 1 }, { -1, 1, -1, 0, 1 } },
+    };
+    for (int face = 0; face < 6; face++) {
+        glBegin(GL_QUADS);
+        glColor3f(1.0f, 1.0f, 1.0f);
+        for (int k = 0; k < 4; k++) {
+            glTexCoord2f(f[face][k][3] * uvs, f[face][k][4] * uvs);
+            glVertex3f(f[face][k][0] * s, f[face][k][1] * s, f[face][k][2] * s);
+        }
+        glEnd();
+    }
+}
+
+/* ---------------------------------------------------------------- BASELINE configurations */
+
+/* C1: Suzanne, immediate mode, depth test + lighting.  variant: 0 smooth, 1 phong, 2 flat,
+ * 3 smooth + two-sided lighting with a distinct back material, 4 smooth + local viewer */
+static void scene_c1(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glDepthFunc(GL_LESS);
+    glClearColor(0.2f, 0.2f, 0.3f, 1.0f);
+    suzanne_lights_and_material();
+    glShadeModel(variant == 1 ? GL_PHONG : variant == 2 ? GL_FLAT : GL_SMOOTH);
+    if (variant == 3) {
+        GLfloat bd[] = { 0.1f, 0.6f, 0.9f, 1.0f };
+        glMaterialfv(GL_BACK, GL_DIFFUSE, bd);
+        glLightModeli(GL_LIGHT_MODEL_TWO_SIDE, 1);
+    }
+    if (variant == 4) glLightModeli(GL_LIGHT_MODEL_LOCAL_VIEWER, 1);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -2.2f);
+    glRotatef(20.0f, 1.0f, 0.0f, 0.0f);
+    glRotatef(30.0f, 0.0f, 1.0f, 0.0f);
+    suzanne_immediate();
+}
+
+/* C2: textured cube, trilinear + GL_MODULATE + linear fog, back-face culling */
+static void scene_c2_cube(int w, int h, int variant)
+{
+    (void)variant;
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glEnable(GL_CULL_FACE);
+    glCullFace(GL_BACK);
+    glClearColor(0.5f, 0.5f, 0.5f, 1.0f);
+    glEnable(GL_TEXTURE_2D);
+    make_checker_rgb(64, 4, 1);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_REPEAT);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_REPEAT);
+    glTexEnvi(GL_TEXTURE_ENV, GL_TEXTURE_ENV_MODE, GL_MODULATE);
+    GLfloat fog[] = { 0.5f, 0.5f, 0.5f, 1.0f };
+    glEnable(GL_FOG);
+    glFogi(GL_FOG_MODE, GL_LINEAR);
+    glFogf(GL_FOG_START, 2.0f);
+    glFogf(GL_FOG_END, 8.0f);
+    glFogfv(GL_FOG_COLOR, fog);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -3.0f);
+    glRotatef(30.0f, 1.0f, 0.0f, 0.0f);
+    glRotatef(40.0f, 0.0f, 1.0f, 0.0f);
+    cube_quads(1.5f, 4.0f);
+}
+
+/* C2 sub-scene: the 1.0-14 floor (212-228), real minification and heavy frustum clipping.
+ * variant 0..5 = the six minification filters */
+static void scene_c2_floor(int w, int h, int variant)
+{
+    static const GLint filt[6] = { GL_NEAREST, GL_LINEAR, GL_NEAREST_MIPMAP_NEAREST, GL_LINEAR_MIPMAP_NEAREST,
+                                   GL_NEAREST_MIPMAP_LINEAR, GL_LINEAR_MIPMAP_LINEAR };
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.1f, 0.1f, 0.2f, 1.0f);
+    glEnable(GL_TEXTURE_2D);
+    make_checker_rgb(64, 4, 1);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_REPEAT);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_REPEAT);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, filt[variant % 6]);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glLoadIdentity();
+    glRotatef(60.0f, 1.0f, 0.0f, 0.0f);
+    glTranslatef(0.0f, -2.0f, 0.0f);
+    glColor3f(1.0f, 1.0f, 1.0f);
+    glBegin(GL_QUADS);
+    glTexCoord2f(0.0f, 0.0f);   glVertex3f(-20.0f, 0.0f, -20.0f);
+    glTexCoord2f(20.0f, 0.0f);  glVertex3f(20.0f, 0.0f, -20.0f);
+    glTexCoord2f(20.0f, 20.0f); glVertex3f(20.0f, 0.0f, 20.0f);
+    glTexCoord2f(0.0f, 20.0f);  glVertex3f(-20.0f, 0.0f, 20.0f);
+    glEnd();
+}
+
+/* C2 sub-scene: the 1.0-15 quad (186-209), one texenv mode per variant (0..4), rotated 17 degrees */
+static void scene_c2_texenv(int w, int h, int variant)
+{
+    static const GLint modes[5] = { GL_MODULATE, GL_DECAL, GL_REPLACE, GL_BLEND, GL_ADD };
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(-2.0, 2.0, -1.5, 1.5, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glClearColor(0.2f, 0.2f, 0.3f, 1.0f);
+    glEnable(GL_TEXTURE_2D);
+    make_radial_rgba(64);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_CLAMP);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_CLAMP);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    glTexEnvi(GL_TEXTURE_ENV, GL_TEXTURE_ENV_MODE, modes[variant % 5]);
+    GLfloat env[] = { 0.0f, 1.0f, 1.0f, 1.0f };
+    glTexEnvfv(GL_TEXTURE_ENV, GL_TEXTURE_ENV_COLOR, env);
+    glClear(GL_COLOR_BUFFER_BIT);
+    glLoadIdentity();
+    glRotatef(17.0f, 0.0f, 0.0f, 1.0f);
+    glBegin(GL_QUADS);
+    glColor3f(1.0f, 0.0f, 0.0f); glTexCoord2f(0.0f, 0.0f); glVertex2f(-1.0f, -1.0f);
+    glColor3f(0.0f, 1.0f, 0.0f); glTexCoord2f(1.0f, 0.0f); glVertex2f(1.0f, -1.0f);
+    glColor3f(0.0f, 0.0f, 1.0f); glTexCoord2f(1.0f, 1.0f); glVertex2f(1.0f, 1.0f);
+    glColor3f(1.0f, 1.0f, 0.0f); glTexCoord2f(0.0f, 1.0f); glVertex2f(-1.0f, 1.0f);
+    glEnd();
+}
+
+/* C3: fill-rate stress.  variant = number of full-screen quads (0 -> 64). */
+static void scene_c3(int w, int h, int variant)
+{
+    int nq = variant > 0 ? variant : 64;
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
+    glClearStencil(0);
+    glEnable(GL_TEXTURE_2D);
+    make_radial_rgba(64);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_CLAMP);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_CLAMP);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    glEnable(GL_ALPHA_TEST);
+    glAlphaFunc(GL_GREATER, 0.1f);
+    glEnable(GL_STENCIL_TEST);
+    glStencilFunc(GL_ALWAYS, 0, 0xFF);
+    glStencilOp(GL_KEEP, GL_KEEP, GL_INCR_WRAP);
+    glEnable(GL_BLEND);
+    glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA);
+    glClear(GL_COLOR_BUFFER_BIT | GL_STENCIL_BUFFER_BIT);
+    glBegin(GL_QUADS);
+    for (int q = 0; q < nq; q++) {
+        glColor4f((float)((q * 37) % 64) / 63.0f, (float)((q * 11) % 64) / 63.0f, (float)((q * 5) % 64) / 63.0f,
+                  (q & 1) ? 0.75f : 0.25f);
+        glTexCoord2f(0.0f, 0.0f); glVertex2f(-1.0f, -1.0f);
+        glTexCoord2f(1.0f, 0.0f); glVertex2f(1.0f, -1.0f);
+        glTexCoord2f(1.0f, 1.0f); glVertex2f(1.0f, 1.0f);
+        glTexCoord2f(0.0f, 1.0f); glVertex2f(-1.0f, 1.0f);
+    }
+    glEnd();
+}
+
+/* C4 / C5: grid of Suzannes through one interleaved VBO (pos3 normal3 uv2 = 32 B / vertex).
+ * The VBO and texture are built once per context by scene_c4_setup; scene_c4_draw issues the frame. */
+static struct {
+    GLuint vbo, tex;
+    int gx, gy, nverts;
+    float *host;    /* retained so the end-to-end benchmark can re-upload it every frame */
+} g_c4;
+
+static void c4_build(int gx, int gy)
+{
+    size_t nv = (size_t)gx * gy * g_mesh_nf * 3;
+    free(g_c4.host);
+    g_c4.host = (float *)malloc(nv * 8 * sizeof(float));
+    float *o = g_c4.host;
+    for (int iy = 0; iy < gy; iy++)
+        for (int ix = 0; ix < gx; ix++) {
+            float ox = ((float)ix - (float)(gx - 1) * 0.5f) * 2.1f;
+            float oy = ((float)iy - (float)(gy - 1) * 0.5f) * 1.5f;
+            for (int f = 0; f < g_mesh_nf; f++)
+                for (int j = 0; j < 3; j++) {
+                    int vi = g_mesh_faces[f * 3 + j];
+                    float x = g_mesh_pos[vi * 3], y = g_mesh_pos[vi * 3 + 1], z = g_mesh_pos[vi * 3 + 2];
+                    o[0] = x + ox; o[1] = y + oy; o[2] = z;
+                    o[3] = g_mesh_nrm[vi * 3]; o[4] = g_mesh_nrm[vi * 3 + 1]; o[5] = g_mesh_nrm[vi * 3 + 2];
+                    o[6] = (x + 0.7f) * 4.0f; o[7] = (y + 0.5f) * 4.0f;
+                    o += 8;
+                }
+        }
+    g_c4.gx = gx; g_c4.gy = gy; g_c4.nverts = (int)nv;
+}
+
+void scene_c4_upload(void) /* the per-frame host->device part of the end-to-end measurement */
+{
+    glBindBuffer(GL_ARRAY_BUFFER, g_c4.vbo);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr)((size_t)g_c4.nverts * 32), g_c4.host, GL_STATIC_DRAW);
+}
+
+/* variant: bits 0-7 grid columns (0 -> 38), bits 8-15 grid rows (0 -> 28), bit 16 GL_PHONG */
+void scene_c4_setup(int w, int h, int variant)
+{
+    int gx = variant & 0xFF, gy = (variant >> 8) & 0xFF;
+    if (gx == 0) gx = 38;
+    if (gy == 0) gy = 28;
+    c4_build(gx, gy);
+    glGenBuffers(1, &g_c4.vbo);
+    scene_c4_upload();
+    g_c4.tex = make_checker_rgb(64, 4, 1);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_REPEAT);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_REPEAT);
+
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glDepthFunc(GL_LESS);
+    glEnable(GL_TEXTURE_2D);
+    glClearColor(0.2f, 0.2f, 0.3f, 1.0f);
+    glEnable(GL_LIGHTING);
+    GLfloat amb[] = { 0.15f, 0.15f, 0.2f, 1.0f };
+    glLightModelfv(GL_LIGHT_MODEL_AMBIENT, amb);
+    for (int l = 0; l < 8; l++) {   /* even = directional, odd = positional with linear attenuation 0.05 */
+        GLfloat pos[4] = { (float)((37 * l) % 7) - 3.0f, (float)((53 * l) % 5) - 2.0f, 3.0f, (l & 1) ? 1.0f : 0.0f };
+        GLfloat dif[4] = { 0.10f + 0.05f * (float)(l % 3), 0.12f + 0.04f * (float)((l + 1) % 3), 0.10f + 0.06f * (float)((l + 2) % 3), 1.0f };
+        GLfloat spc[4] = { 0.4f, 0.4f, 0.4f, 1.0f };
+        glEnable(GL_LIGHT0 + l);
+        glLightfv(GL_LIGHT0 + l, GL_POSITION, pos);
+        glLightfv(GL_LIGHT0 + l, GL_DIFFUSE, dif);
+        glLightfv(GL_LIGHT0 + l, GL_SPECULAR, spc);
+        if (l & 1) glLightf(GL_LIGHT0 + l, GL_LINEAR_ATTENUATION, 0.05f);
+    }
+    GLfloat ma[] = { 0.3f, 0.2f, 0.1f, 1.0f }, md[] = { 0.8f, 0.5f, 0.3f, 1.0f }, ms[] = { 0.4f, 0.4f, 0.4f, 1.0f };
+    glMaterialfv(GL_FRONT_AND_BACK, GL_AMBIENT, ma);
+    glMaterialfv(GL_FRONT_AND_BACK, GL_DIFFUSE, md);
+    glMaterialfv(GL_FRONT_AND_BACK, GL_SPECULAR, ms);
+    glMaterialf(GL_FRONT_AND_BACK, GL_SHININESS, 32.0f);
+    glShadeModel((variant & (1 << 16)) ? GL_PHONG : GL_SMOOTH);
+
+    glBindBuffer(GL_ARRAY_BUFFER, g_c4.vbo);
+    glEnableClientState(GL_VERTEX_ARRAY);
+    glEnableClientState(GL_NORMAL_ARRAY);
+    glEnableClientState(GL_TEXTURE_COORD_ARRAY);
+    glVertexPointer(3, GL_FLOAT, 32, (const void *)0);
+    glNormalPointer(GL_FLOAT, 32, (const void *)12);
+    glTexCoordPointer(2, GL_FLOAT, 32, (const void *)24);
+    glLoadIdentity();
+    /* the camera distance of the official layout is 24 for the 38x28 grid; smaller grids move closer
+     * so that the per-triangle footprint stays comparable */
+    float cz = 24.0f * (float)(gx > gy * 38 / 28 ? gx : gy * 38 / 28) / 38.0f;
+    if (cz < 2.5f) cz = 2.5f;
+    glTranslatef(0.0f, 0.0f, -cz);
+}
+
+void scene_c4_draw(void)
+{
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glDrawArrays(GL_TRIANGLES, 0, g_c4.nverts);
+}
+
+static void scene_c4(int w, int h, int variant)
+{
+    scene_c4_setup(w, h, variant);
+    scene_c4_draw();
+}
+
+int scene_c4_vertex_count(void) { return g_c4.nverts; }
+
+/* ---------------------------------------------------------------- testbed-derived feature scenes */
+
+/* 1.0-3: oversize triangle crossing every frustum plane, plus a quad poking through the near plane */
+static void scene_clipping(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 20.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glShadeModel(variant ? GL_FLAT : GL_SMOOTH);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -3.0f);
+    glRotatef(25.0f, 0.3f, 1.0f, 0.1f);
+    glBegin(GL_TRIANGLES);
+    glColor3f(1, 0, 0); glVertex3f(-9.0f, -4.0f, 0.5f);
+    glColor3f(0, 1, 0); glVertex3f(9.0f, -5.0f, -1.0f);
+    glColor3f(0, 0, 1); glVertex3f(0.5f, 8.0f, 2.9f);
+    glColor3f(1, 1, 0); glVertex3f(-1.0f, -1.0f, 4.0f);
+    glColor3f(0, 1, 1); glVertex3f(1.0f, -1.0f, -30.0f);
+    glColor3f(1, 0, 1); glVertex3f(0.0f, 1.5f, 1.0f);
+    glEnd();
+    glBegin(GL_QUADS);
+    glColor4f(1, 1, 1, 1);
+    glVertex3f(-0.5f, -0.5f, 3.5f); glVertex3f(0.5f, -0.5f, 3.5f);
+    glVertex3f(0.5f, 0.5f, -2.0f); glVertex3f(-0.5f, 0.5f, -2.0f);
+    glEnd();
+}
+
+/* 1.0-8 / 1.0-4: every filled primitive mode, with and without back-face culling (1.0-5) */
+static void scene_primitives(int w, int h, int variant)
+{
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(-4.0, 4.0, -3.0, 3.0, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glClearColor(0.1f, 0.1f, 0.1f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT);
+    if (variant & 1) { glEnable(GL_CULL_FACE); glCullFace((variant & 2) ? GL_FRONT : GL_BACK); }
+    if (variant & 4) glFrontFace(GL_CW);
+    if (variant & 8) glShadeModel(GL_FLAT);
+    static const GLenum modes[6] = { GL_TRIANGLES, GL_TRIANGLE_STRIP, GL_TRIANGLE_FAN, GL_QUADS, GL_QUAD_STRIP, GL_POLYGON };
+    for (int m = 0; m < 6; m++) {
+        glLoadIdentity();
+        glTranslatef(-2.6f + 2.6f * (float)(m % 3), 1.4f - 2.8f * (float)(m / 3), 0.0f);
+        glBegin(modes[m]);
+        int n = (modes[m] == GL_TRIANGLES) ? 9 : (modes[m] == GL_QUADS) ? 8 : 7;
+        for (int i = 0; i < n; i++) {
+            float a = (float)i * 0.9f;
+            glColor3f(0.5f + 0.5f * sinf(a), 0.5f + 0.5f * cosf(a * 1.3f), 0.5f + 0.5f * sinf(a * 0.7f + 1.0f));
+            if (modes[m] == GL_TRIANGLE_STRIP || modes[m] == GL_QUAD_STRIP)
+                glVertex2f(-1.0f + 0.33f * (float)i, (i & 1) ? 0.8f : -0.8f);
+            else if (modes[m] == GL_TRIANGLE_FAN || modes[m] == GL_POLYGON)
+                glVertex2f(i == 0 && modes[m] == GL_TRIANGLE_FAN ? 0.0f : 0.9f * cosf(a), i == 0 && modes[m] == GL_TRIANGLE_FAN ? 0.0f : 0.9f * sinf(a));
+            else
+                glVertex2f(-1.0f + 0.7f * (float)(i % 4) + 0.2f * (float)(i / 4), -0.8f + 0.55f * (float)((i * 5) % 4));
+        }
+        glEnd();
+    }
+}
+
+/* 1.0-6 + depth-function sweep: two interpenetrating quads; variant = depth func index 0..7, bit 3 = no depth write,
+ * bit 4 = shifted glDepthRange (exercises the double-precision depth expression) */
+static void scene_zbuffer(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
+    glClearDepth((variant & 7) >= 4 ? 0.0 : 1.0);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glDepthFunc(GL_NEVER + (variant & 7));
+    if (variant & 8) glDepthMask(GL_FALSE);
+    if (variant & 16) glDepthRange(0.25, 0.8);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -4.0f);
+    for (int k = 0; k < 3; k++) {
+        glPushMatrix();
+        glRotatef(35.0f + 50.0f * (float)k, 0.2f, 1.0f, 0.1f * (float)k);
+        glBegin(GL_QUADS);
+        glColor3f(k == 0, k == 1, k == 2);
+        glVertex3f(-1.2f, -1.0f, 0.0f); glVertex3f(1.2f, -1.0f, 0.0f);
+        glColor3f(1.0f, 1.0f, k == 2);
+        glVertex3f(1.2f, 1.0f, 0.0f); glVertex3f(-1.2f, 1.0f, 0.0f);
+        glEnd();
+        glPopMatrix();
+    }
+}
+
+/* 1.0-9: rows of cubes in fog; variant 0 LINEAR, 1 EXP, 2 EXP2 */
+static void scene_fog(int w, int h, int variant)
+{
+    static const GLint modes[3] = { GL_LINEAR, GL_EXP, GL_EXP2 };
+    frustum_like_testbed(w, h, 50.0);
+    GLfloat fog[] = { 0.5f, 0.5f, 0.5f, 0.3f };
+    glClearColor(0.5f, 0.5f, 0.5f, 1.0f);
+    glEnable(GL_DEPTH_TEST);
+    glEnable(GL_FOG);
+    glFogi(GL_FOG_MODE, modes[variant % 3]);
+    glFogf(GL_FOG_START, 2.0f);
+    glFogf(GL_FOG_END, 25.0f);
+    glFogf(GL_FOG_DENSITY, 0.1f);
+    glFogfv(GL_FOG_COLOR, fog);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    for (int row = 0; row < 5; row++)
+        for (int col = -2; col <= 2; col++) {
+            glLoadIdentity();
+            glTranslatef(2.2f * (float)col, -1.0f, -4.0f - 4.5f * (float)row);
+            glRotatef(20.0f * (float)(row + col), 0.0f, 1.0f, 0.0f);
+            glBegin(GL_QUADS);
+            glColor3f(0.9f, 0.3f + 0.1f * (float)row, 0.2f);
+            glVertex3f(-0.7f, -0.7f, 0.7f); glVertex3f(0.7f, -0.7f, 0.7f); glVertex3f(0.7f, 0.7f, 0.7f); glVertex3f(-0.7f, 0.7f, 0.7f);
+            glColor3f(0.2f, 0.8f, 0.3f);
+            glVertex3f(0.7f, -0.7f, 0.7f); glVertex3f(0.7f, -0.7f, -0.7f); glVertex3f(0.7f, 0.7f, -0.7f); glVertex3f(0.7f, 0.7f, 0.7f);
+            glColor3f(0.2f, 0.3f, 0.9f);
+            glVertex3f(-0.7f, 0.7f, 0.7f); glVertex3f(0.7f, 0.7f, 0.7f); glVertex3f(0.7f, 0.7f, -0.7f); glVertex3f(-0.7f, 0.7f, -0.7f);
+            glEnd();
+        }
+}
+
+/* 1.0-11: overlapping translucent quads; variant selects the blend function pair */
+static void scene_blend(int w, int h, int variant)
+{
+    static const GLenum src[8] = { GL_SRC_ALPHA, GL_SRC_ALPHA, GL_ONE, GL_DST_COLOR, GL_ONE_MINUS_DST_ALPHA, GL_SRC_ALPHA_SATURATE, GL_ONE_MINUS_SRC_COLOR, GL_ZERO };
+    static const GLenum dst[8] = { GL_ONE_MINUS_SRC_ALPHA, GL_ONE, GL_ONE, GL_ZERO, GL_DST_ALPHA, GL_ONE, GL_SRC_COLOR, GL_ONE_MINUS_DST_COLOR };
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(-2.0, 2.0, -1.5, 1.5, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glClearColor(0.3f, 0.3f, 0.3f, 0.5f);
+    glClear(GL_COLOR_BUFFER_BIT);
+    glEnable(GL_BLEND);
+    glBlendFunc(src[variant & 7], dst[variant & 7]);
+    for (int k = 0; k < 4; k++) {
+        glLoadIdentity();
+        glTranslatef(-0.9f + 0.6f * (float)k, -0.3f + 0.2f * (float)k, 0.0f);
+        glRotatef(13.0f * (float)k, 0, 0, 1);
+        glBegin(GL_QUADS);
+        glColor4f(k == 0 || k == 3, k == 1 || k == 3, k == 2, 0.35f + 0.15f * (float)k);
+        glVertex2f(-0.8f, -0.8f); glVertex2f(0.8f, -0.8f); glVertex2f(0.8f, 0.8f); glVertex2f(-0.8f, 0.8f);
+        glEnd();
+    }
+}
+
+/* 1.0-17: stencil mask pass then GL_EQUAL pass; variant perturbs ops / masks */
+static void scene_stencil(int w, int h, int variant)
+{
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(-1.5, 1.5, -1.0, 1.0, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glClearColor(0.2f, 0.2f, 0.3f, 1.0f);
+    glClearStencil(variant == 3 ? 200 : 0);
+    glClear(GL_COLOR_BUFFER_BIT | GL_STENCIL_BUFFER_BIT);
+    glEnable(GL_STENCIL_TEST);
+    glStencilFunc(GL_ALWAYS, 1, 0xFF);
+    glStencilOp(GL_KEEP, GL_KEEP, variant == 1 ? GL_INCR : variant == 2 ? GL_INVERT : variant == 3 ? GL_DECR_WRAP : GL_REPLACE);
+    if (variant == 2) glStencilMask(0x0F);
+    glColorMask(GL_FALSE, GL_FALSE, GL_FALSE, GL_FALSE);
+    glBegin(GL_TRIANGLE_FAN);
+    glVertex2f(0.0f, 0.0f);
+    for (int i = 0; i <= 32; i++) {
+        float a = (float)i * 2.0f * 3.14159f / 32.0f;
+        glVertex2f(0.5f * cosf(a), 0.5f * sinf(a));
+    }
+    glEnd();
+    glStencilFunc(variant == 1 ? GL_LEQUAL : GL_EQUAL, variant == 2 ? 0x0F : variant == 3 ? 199 : 1, variant == 2 ? 0x0F : 0xFF);
+    glStencilOp(variant == 1 ? GL_ZERO : GL_KEEP, GL_KEEP, variant == 1 ? GL_DECR : GL_KEEP);
+    glColorMask(GL_TRUE, GL_TRUE, variant == 3 ? GL_FALSE : GL_TRUE, GL_TRUE);
+    glLoadIdentity();
+    glRotatef(31.0f, 0.0f, 0.0f, 1.0f);
+    glBegin(GL_QUADS);
+    glColor3f(1.0f, 0.0f, 0.0f); glVertex2f(-0.8f, -0.8f);
+    glColor3f(0.0f, 1.0f, 0.0f); glVertex2f(0.8f, -0.8f);
+    glColor3f(0.0f, 0.0f, 1.0f); glVertex2f(0.8f, 0.8f);
+    glColor3f(1.0f, 1.0f, 0.0f); glVertex2f(-0.8f, 0.8f);
+    glEnd();
+    glDisable(GL_STENCIL_TEST);
+}
+
+/* 1.0-10: lit sphere from triangle strips with GL_NORMALIZE; variant 0 flat, 1 smooth, 2 phong,
+ * 3 smooth + spotlight + attenuation, 4 smooth + COLOR_MATERIAL, 5 phong + spotlight */
+static void scene_lighting(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glEnable(GL_NORMALIZE);
+    glClearColor(0.05f, 0.05f, 0.1f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glEnable(GL_LIGHTING);
+    glEnable(GL_LIGHT0);
+    GLfloat pos[] = { 1.5f, 2.0f, 1.0f, 1.0f }, dif[] = { 1.0f, 0.9f, 0.8f, 1.0f }, spc[] = { 1, 1, 1, 1 }, la[] = { 0.1f, 0.1f, 0.1f, 1 };
+    glLightfv(GL_LIGHT0, GL_DIFFUSE, dif);
+    glLightfv(GL_LIGHT0, GL_SPECULAR, spc);
+    glLightfv(GL_LIGHT0, GL_AMBIENT, la);
+    GLfloat md[] = { 0.2f, 0.5f, 0.9f, 1.0f }, ms[] = { 0.8f, 0.8f, 0.8f, 1.0f };
+    glMaterialfv(GL_FRONT, GL_DIFFUSE, md);
+    glMaterialfv(GL_FRONT, GL_SPECULAR, ms);
+    glMaterialf(GL_FRONT, GL_SHININESS, 48.0f);
+    glShadeModel(variant == 0 ? GL_FLAT : (variant == 2 || variant == 5) ? GL_PHONG : GL_SMOOTH);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -3.0f);
+    glLightfv(GL_LIGHT0, GL_POSITION, pos);
+    if (variant == 3 || variant == 5) {
+        GLfloat dir[] = { -0.45f, -0.6f, -0.66f };
+        glLightfv(GL_LIGHT0, GL_SPOT_DIRECTION, dir);
+        glLightf(GL_LIGHT0, GL_SPOT_CUTOFF, 25.0f);
+        glLightf(GL_LIGHT0, GL_SPOT_EXPONENT, 6.0f);
+        glLightf(GL_LIGHT0, GL_CONSTANT_ATTENUATION, 0.5f);
+        glLightf(GL_LIGHT0, GL_LINEAR_ATTENUATION, 0.1f);
+        glLightf(GL_LIGHT0, GL_QUADRATIC_ATTENUATION, 0.02f);
+    }
+    if (variant == 4) { glEnable(GL_COLOR_MATERIAL); glColorMaterial(GL_FRONT, GL_DIFFUSE); }
+    glScalef(1.0f, 1.2f, 0.9f);
+    const int stacks = 18, slices = 24;
+    for (int i = 0; i < stacks; i++) {
+        float t0 = 3.14159265f * (float)i / stacks, t1 = 3.14159265f * (float)(i + 1) / stacks;
+        glBegin(GL_TRIANGLE_STRIP);
+        for (int j = 0; j <= slices; j++) {
+            float p = 2.0f * 3.14159265f * (float)j / slices;
+            float x0 = sinf(t0) * cosf(p), y0 = cosf(t0), z0 = sinf(t0) * sinf(p);
+            float x1 = sinf(t1) * cosf(p), y1 = cosf(t1), z1 = sinf(t1) * sinf(p);
+            if (variant == 4) glColor3f(0.5f + 0.5f * x0, 0.5f + 0.5f * y0, 0.5f + 0.5f * z0);
+            glNormal3f(2.0f * x0, 2.0f * y0, 2.0f * z0); glVertex3f(x0, y0, z0);
+            glNormal3f(2.0f * x1, 2.0f * y1, 2.0f * z1); glVertex3f(x1, y1, z1);
+        }
+        glEnd();
+    }
+}
+
+/* 1.0-13: the same geometry through a compiled display list, called with different matrices;
+ * variant 1 uses GL_COMPILE_AND_EXECUTE and a nested list */
+static void scene_displaylist(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -6.0f);
+    GLuint base = glGenLists(2);
+    glNewList(base + 1, GL_COMPILE);
+    glBegin(GL_TRIANGLES);
+    glColor3f(1, 0, 0); glVertex3f(-0.5f, -0.5f, 0.0f);
+    glColor3f(0, 1, 0); glVertex3f(0.5f, -0.5f, 0.0f);
+    glColor3f(0, 0, 1); glVertex3f(0.0f, 0.6f, 0.0f);
+    glEnd();
+    glEndList();
+    glNewList(base, variant ? GL_COMPILE_AND_EXECUTE : GL_COMPILE);
+    glPushMatrix();
+    glRotatef(30.0f, 0, 0, 1);
+    glCallList(base + 1);
+    glTranslatef(0.0f, 0.0f, 0.5f);
+    glScalef(0.5f, 0.5f, 1.0f);
+    glCallList(base + 1);
+    glPopMatrix();
+    glEndList();
+    for (int k = 0; k < 5; k++) {
+        glPushMatrix();
+        glTranslatef(-2.4f + 1.2f * (float)k, 0.3f * (float)(k % 2), -0.4f * (float)k);
+        glCallList(base);
+        glPopMatrix();
+    }
+    glDeleteLists(base, 2);
+}
+
+/* 1.5-0: interleaved position+colour VBO drawn as quads (stride 24), plus an indexed draw with
+ * ubyte colours, a client-memory array draw and an element-buffer draw */
+static void scene_vbo(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.1f, 0.1f, 0.15f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    static const float cube[24][6] = {
+        { -1, -1, 1, 1, 0, 0 }, { 1, -1, 1, 1, 0, 0 }, { 1, 1, 1, 1, 0.5f, 0 }, { -1, 1, 1, 1, 0.5f, 0 },
+        { -1, -1, -1, 0, 1, 0 }, { -1, 1, -1, 0, 1, 0 }, { 1, 1, -1, 0, 1, 0.5f }, { 1, -1, -1, 0, 1, 0.5f },
+        { -1, 1, -1, 0, 0, 1 }, { -1, 1, 1, 0, 0, 1 }, { 1, 1, 1, 0.5f, 0, 1 }, { 1, 1, -1, 0.5f, 0, 1 },
+        { -1, -1, -1, 1, 1, 0 }, { 1, -1, -1, 1, 1, 0 }, { 1, -1, 1, 1, 1, 0.5f }, { -1, -1, 1, 1, 1, 0.5f },
+        { 1, -1, -1, 1, 0, 1 }, { 1, 1, -1, 1, 0, 1 }, { 1, 1, 1, 1, 0.5f, 1 }, { 1, -1, 1, 1, 0.5f, 1 },
+        { -1, -1, -1, 0, 1, 1 }, { -1, -1, 1, 0, 1, 1 }, { -1, 1, 1, 0.5f, 1, 1 }, { -1, 1, -1, 0.5f, 1, 1 },
+    };
+    GLuint vbo[3];
+    glGenBuffers(3, vbo);
+    glBindBuffer(GL_ARRAY_BUFFER, vbo[0]);
+    glBufferData(GL_ARRAY_BUFFER, sizeof cube, cube, GL_STATIC_DRAW);
+    glEnableClientState(GL_VERTEX_ARRAY);
+    glEnableClientState(GL_COLOR_ARRAY);
+    glVertexPointer(3, GL_FLOAT, 24, (const void *)0);
+    glColorPointer(3, GL_FLOAT, 24, (const void *)12);
+    glLoadIdentity();
+    glTranslatef(-1.6f, 0.0f, -6.0f);
+    glRotatef(35.0f, 1.0f, 1.0f, 0.0f);
+    glDrawArrays(GL_QUADS, 0, 24);
+
+    /* indexed, ubyte colours with 4 components, positions of size 2, element buffer with ushort indices */
+    struct { float x, y; uint8_t c[4]; } flat[5] = {
+        { -0.8f, -0.8f, { 255, 0, 0, 255 } }, { 0.8f, -0.8f, { 0, 255, 0, 255 } }, { 0.8f, 0.8f, { 0, 0, 255, 128 } },
+        { -0.8f, 0.8f, { 255, 255, 0, 255 } }, { 0.0f, 1.4f, { 255, 255, 255, 64 } } };
+    uint16_t idx[9] = { 0, 1, 2, 0, 2, 3, 3, 2, 4 };
+    glBindBuffer(GL_ARRAY_BUFFER, vbo[1]);
+    glBufferData(GL_ARRAY_BUFFER, sizeof flat, flat, GL_STATIC_DRAW);
+    glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, vbo[2]);
+    glBufferData(GL_ELEMENT_ARRAY_BUFFER, sizeof idx, idx, GL_STATIC_DRAW);
+    glVertexPointer(2, GL_FLOAT, 12, (const void *)0);
+    glColorPointer(4, GL_UNSIGNED_BYTE, 12, (const void *)8);
+    glLoadIdentity();
+    glTranslatef(1.5f, -0.3f, -5.0f);
+    if (variant & 1) glEnable(GL_BLEND), glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA);
+    glDrawElements(GL_TRIANGLES, 9, GL_UNSIGNED_SHORT, (const void *)0);
+    glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, 0);
+    /* client-memory indices against the bound array buffer */
+    uint8_t idx8[3] = { 4, 3, 0 };
+    glLoadIdentity();
+    glTranslatef(1.5f, 0.9f, -5.5f);
+    glDrawElements(GL_TRIANGLES, 3, GL_UNSIGNED_BYTE, idx8);
+
+    /* client-memory arrays (no buffer bound): snapshotted at call time */
+    glBindBuffer(GL_ARRAY_BUFFER, 0);
+    float tri[3][7] = { { 0, 0, 0, 1, 0, 1, 1 }, { 1, 0, 0, 0, 1, 1, 1 }, { 0, 1, 0, 1, 1, 0, 1 } };
+    glVertexPointer(3, GL_FLOAT, 28, &tri[0][0]);
+    glColorPointer(4, GL_FLOAT, 28, &tri[0][3]);
+    glLoadIdentity();
+    glTranslatef(-0.4f, -1.7f, -4.0f);
+    glDrawArrays(GL_TRIANGLES, 0, 3);
+    tri[0][0] = 99.0f; /* must not affect the draw above */
+    glDisableClientState(GL_COLOR_ARRAY);
+    glDisableClientState(GL_VERTEX_ARRAY);
+    glDeleteBuffers(3, vbo);
+}
+
+/* 1.0-16: hostile input must not crash and must match the reference: NaN/Inf colours,
+ * huge coordinates, degenerate triangles */
+static void scene_validation(int w, int h, int variant)
+{
+    (void)variant;
+    frustum_like_testbed(w, h, 100.0);
+    glClearColor(0.0f, 0.0f, 0.0f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glEnable(GL_DEPTH_TEST);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -3.0f);
+    float inf = 1.0f / 0.0f * 1.0f, nanv = inf - inf;
+    glBegin(GL_TRIANGLES);
+    glColor3f(nanv, 0.5f, inf); glVertex3f(-1.0f, -1.0f, 0.0f);
+    glColor4f(2.0f, -1.0f, 0.5f, nanv); glVertex3f(1.0f, -1.0f, 0.0f);
+    glColor3f(0.2f, 0.9f, 0.4f); glVertex3f(0.0f, 1.0f, 0.0f);
+    /* far outside the frustum */
+    glColor3f(1, 1, 1);
+    glVertex3f(-1e10f, -1e10f, -5.0f); glVertex3f(1e10f, -1e10f, -5.0f); glVertex3f(0.0f, 1e10f, -5.0f);
+    /* degenerate: zero area, repeated vertices */
+    glVertex3f(0.3f, 0.3f, 0.0f); glVertex3f(0.3f, 0.3f, 0.0f); glVertex3f(0.3f, 0.3f, 0.0f);
+    glVertex3f(-0.5f, 0.0f, 0.0f); glVertex3f(0.0f, 0.0f, 0.0f); glVertex3f(0.5f, 0.0f, 0.0f);
+    /* crossing w = 0 */
+    glColor3f(0.8f, 0.2f, 0.2f);
+    glVertex3f(-0.5f, -0.5f, 2.0f); glVertex3f(0.5f, -0.5f, 4.0f); glVertex3f(0.0f, 0.5f, 3.0f);
+    glEnd();
+}
+
+/* scissor + partial clears + colour mask + viewport offset (Appendix A.22, A.24) */
+static void scene_scissor(int w, int h, int variant)
+{
+    glClearColor(0.1f, 0.2f, 0.3f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT | GL_STENCIL_BUFFER_BIT);
+    glEnable(GL_SCISSOR_TEST);
+    glScissor(w / 8, h / 6, w / 2, h / 2);
+    glClearColor(0.6f, 0.1f, 0.1f, 1.0f);
+    glColorMask(GL_FALSE, GL_TRUE, GL_TRUE, GL_TRUE); /* glClear ignores the colour mask */
+    glClear(GL_COLOR_BUFFER_BIT);
+    glColorMask(GL_TRUE, GL_TRUE, GL_TRUE, GL_TRUE);
+    glViewport(w / 10, h / 8, (w * 3) / 4, (h * 2) / 3);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    if (variant & 1) glScissor(-5, -7, w / 3, h + 50);
+    if (variant & 2) glColorMask(GL_TRUE, GL_FALSE, GL_TRUE, GL_FALSE);
+    glBegin(GL_TRIANGLES);
+    glColor3f(1, 1, 0); glVertex2f(-1.2f, -1.1f);
+    glColor3f(0, 1, 1); glVertex2f(1.3f, -0.9f);
+    glColor3f(1, 0, 1); glVertex2f(0.1f, 1.4f);
+    glEnd();
+    glDisable(GL_SCISSOR_TEST);
+}
+
+/* textures: non-square LA texture, clamp vs repeat, nearest vs bilinear (1.0-12), texture matrix,
+ * affine hint, alpha test without blending */
+static void scene_texture_misc(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glClearColor(0.0f, 0.1f, 0.0f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glEnable(GL_TEXTURE_2D);
+    make_gradient_la(48, 20);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, (variant & 1) ? GL_LINEAR_MIPMAP_NEAREST : GL_NEAREST_MIPMAP_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, (variant & 1) ? GL_LINEAR : GL_NEAREST);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, (variant & 2) ? GL_CLAMP_TO_EDGE : GL_REPEAT);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, (variant & 4) ? GL_CLAMP : GL_REPEAT);
+    if (variant & 8) glHint(GL_PERSPECTIVE_CORRECTION_HINT, GL_FASTEST);
+    glEnable(GL_ALPHA_TEST);
+    glAlphaFunc(GL_GEQUAL, 0.5f);
+    glMatrixMode(GL_TEXTURE);
+    glLoadIdentity();
+    glTranslatef(0.25f, -0.1f, 0.0f);
+    glRotatef(15.0f, 0, 0, 1);
+    glScalef(1.5f, 0.75f, 1.0f);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -2.5f);
+    glRotatef(-50.0f, 1.0f, 0.2f, 0.0f);
+    glBegin(GL_QUADS);
+    glColor3f(1.0f, 0.8f, 0.8f); glTexCoord2f(-1.0f, -1.0f); glVertex3f(-1.5f, -1.5f, 0.0f);
+    glColor3f(0.8f, 1.0f, 0.8f); glTexCoord2f(2.0f, -1.0f); glVertex3f(1.5f, -1.5f, 0.0f);
+    glColor3f(0.8f, 0.8f, 1.0f); glTexCoord2f(2.0f, 2.0f); glVertex3f(1.5f, 1.5f, 0.0f);
+    glColor3f(1.0f, 1.0f, 1.0f); glTexCoord2f(-1.0f, 2.0f); glVertex3f(-1.5f, 1.5f, 0.0f);
+    glEnd();
+}
+
+/* many small state changes inside one frame: exercises state-block batching and ordering */
+static void scene_state_churn(int w, int h, int variant)
+{
+    (void)variant;
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(0.0, 16.0, 0.0, 12.0, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glClearColor(0, 0, 0, 1);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT | GL_STENCIL_BUFFER_BIT);
+    GLuint tex = make_checker_rgb(16, 2, 0);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST);
+    for (int k = 0; k < 48; k++) {
+        glLoadIdentity();
+        glTranslatef((float)(k % 8) * 1.9f + 0.4f, (float)(k / 8) * 1.9f + 0.3f, 0.0f);
+        if (k % 3 == 0) glEnable(GL_BLEND); else glDisable(GL_BLEND);
+        glBlendFunc(GL_SRC_ALPHA, (k % 2) ? GL_ONE : GL_ONE_MINUS_SRC_ALPHA);
+        if (k % 4 == 1) { glEnable(GL_TEXTURE_2D); glBindTexture(GL_TEXTURE_2D, tex); } else glDisable(GL_TEXTURE_2D);
+        if (k % 5 == 2) glShadeModel(GL_FLAT); else glShadeModel(GL_SMOOTH);
+        if (k == 20) glClear(GL_DEPTH_BUFFER_BIT);     /* a clear in the middle of the frame */
+        glBegin(GL_TRIANGLE_FAN);
+        glColor4f(1.0f, (float)(k % 7) / 6.0f, 0.2f, 0.6f);
+        glTexCoord2f(0.5f, 0.5f); glVertex2f(1.0f, 1.0f);
+        for (int i = 0; i <= 6; i++) {
+            float a = 6.2831853f * (float)i / 6.0f;
+            if (i == 3) glColor4f(0.1f, 0.3f, 1.0f, 0.9f);  /* colour change between vertices */
+            glTexCoord2f(0.5f + 0.5f * cosf(a), 0.5f + 0.5f * sinf(a));
+            glVertex2f(1.0f + 1.3f * cosf(a), 1.0f + 1.3f * sinf(a));
+        }
+        glEnd();
+    }
+}
+
+/* ---------------------------------------------------------------- registry */
+typedef void (*scene_fn)(int, int, int);
+static const struct { const char *name; scene_fn fn; } g_scenes[] = {
+    { "c1_suzanne", scene_c1 },
+    { "c2_cube", scene_c2_cube },
+    { "c2_floor", scene_c2_floor },
+    { "c2_texenv", scene_c2_texenv },
+    { "c3_fill", scene_c3 },
+    { "c4_grid", scene_c4 },
+    { "clipping", scene_clipping },
+    { "primitives", scene_primitives },
+    { "zbuffer", scene_zbuffer },
+    { "fog", scene_fog },
+    { "blend", scene_blend },
+    { "stencil", scene_stencil },
+    { "lighting", scene_lighting },
+    { "displaylist", scene_displaylist },
+    { "vbo", scene_vbo },
+    { "validation", scene_validation },
+    { "scissor", scene_scissor },
+    { "texture_misc", scene_texture_misc },
+    { "state_churn", scene_state_churn },
+};
+
+int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }
+const char *scene_name(int i) { return (i >= 0 && i < scene_count()) ? g_scenes[i].name : NULL; }
+
+/* Issue every GL call of the named scene into the current context.  Returns 0, or -1 for an unknown name. */
+int scene_render(const char *name, int w, int h, int variant)
+{
+    for (int i = 0; i < scene_count(); i++)
+        if (strcmp(g_scenes[i].name, name) == 0) {
+            g_scenes[i].fn(w, h, variant);
+            return 0;
+        }
+    return -1;
+}
