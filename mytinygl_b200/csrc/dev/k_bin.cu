@@ -1,0 +1,178 @@
+/*
+ * k_bin.cu -- K3: sort-middle binning of set-up sub-triangles into 64x64 screen tiles.
+ *
+ * No reference counterpart: the reference walks every triangle's bounding box in submission
+ * order (src/raster.c:532-533).  Here each record is referenced from every tile its clamped
+ * bounding box touches; the per-tile reference lists are built with count -> scan -> fill and
+ * are NOT ordered by the binner -- every reference carries the record's submission-ordered id
+ * and the tile kernel sorts its list, which is what preserves blend / stencil / depth-tie
+ * semantics (hard part 2) without serialising this pass.
+ *
+ * Records whose box spans more than LARGE_TILES tiles (full-screen quads) are deferred to a
+ * cooperative pass: one CTA per record, threads striding over its tiles, with a conservative
+ * corner test of the three edge functions that drops tiles the triangle cannot touch.
+ *
+ * Algorithmic bytes: 8 B (packed bbox) read per record per pass + 4 B written per (record, tile).
+ */
+#include "dev_common.cuh"
+
+namespace mtgl_dev_impl {
+
+void note_launch();
+
+__device__ __forceinline__ float edge_at(float ax, float ay, float bx, float by, float px, float py)   /* raster.c:299-302 */
+{
+    return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
+}
+
+/* Can the triangle cover any pixel of the rectangle [x0,x1]x[y0,y1]?  The rounded float edge
+ * function is monotone in px for fixed py and vice versa, so its extrema over the rectangle are
+ * attained at corners: if one edge is strictly outside at all four corners no pixel passes the
+ * inclusive test of raster.c:539-540. */
+__device__ bool tile_may_overlap(const TriRecord *r, int x0, int y0, int x1, int y1)
+{
+    const float fx0 = (float)r->x0, fy0 = (float)r->y0, fx1 = (float)r->x1, fy1 = (float)r->y1, fx2 = (float)r->x2, fy2 = (float)r->y2;
+    const float ax[3] = { fx1, fx2, fx0 }, ay[3] = { fy1, fy2, fy0 }, bx[3] = { fx2, fx0, fx1 }, by[3] = { fy2, fy0, fy1 };
+    const bool pos = r->area > 0;
+    const float cx[2] = { (float)x0, (float)x1 }, cy[2] = { (float)y0, (float)y1 };
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        bool all_out = true;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float v = edge_at(ax[e], ay[e], bx[e], by[e], cx[k & 1], cy[k >> 1]);
+            bool out = pos ? (v < 0) : (v > 0);
+            all_out = all_out && out;
+        }
+        if (all_out) return false;
+    }
+    return true;
+}
+
+struct TileRange { int tx0, ty0, tx1, ty1; };
+
+__device__ __forceinline__ TileRange tile_range(const TriRecord *r, const FrameTargets &fb)
+{
+    TileRange t;
+    t.tx0 = (int)(r->bbox_min & 0xFFFFu) >> TILE_LOG; t.tx1 = (int)(r->bbox_max & 0xFFFFu) >> TILE_LOG;
+    t.ty0 = ((int)(r->bbox_min >> 16) >> TILE_LOG) - fb.tile_y0; t.ty1 = ((int)(r->bbox_max >> 16) >> TILE_LOG) - fb.tile_y0;
+    return t;
+}
+
+/* pass = 0: count references per tile; pass = 1: write them through the per-tile cursors */
+template <int PASS>
+__global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
+{
+    const uint32_t n = b.counters->records;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const TriRecord *rec = b.records + r;
+        uint2 box = *reinterpret_cast<const uint2 *>(&rec->bbox_min);
+        int tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG, tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
+        int ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0, ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
+        int ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+        if (ntiles > LARGE_TILES) {
+            if (PASS == 0) {
+                uint32_t at = atomicAdd(&b.counters->large_count, 1u);
+                b.large_list[at] = r;
+            }
+            continue;
+        }
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++) {
+                uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
+                if (PASS == 0) atomicAdd(&b.tile_count[tile], 1u);
+                else {
+                    uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
+                    b.tile_list[b.tile_offset[tile] + at] = r;
+                }
+            }
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
+{
+    const uint32_t n = b.counters->large_count;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t r = b.large_list[i];
+        const TriRecord *rec = b.records + r;
+        TileRange tr = tile_range(rec, fb);
+        int w = tr.tx1 - tr.tx0 + 1, cnt = w * (tr.ty1 - tr.ty0 + 1);
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            int tx = tr.tx0 + k % w, ty = tr.ty0 + k / w;
+            int bx0 = (int)(rec->bbox_min & 0xFFFFu), by0 = (int)(rec->bbox_min >> 16);
+            int bx1 = (int)(rec->bbox_max & 0xFFFFu), by1 = (int)(rec->bbox_max >> 16);
+            int px0 = max(tx << TILE_LOG, bx0), px1 = min((tx << TILE_LOG) + TILE_W - 1, bx1);
+            int py0 = max((ty + fb.tile_y0) << TILE_LOG, by0), py1 = min(((ty + fb.tile_y0) << TILE_LOG) + TILE_H - 1, by1);
+            if (!tile_may_overlap(rec, px0, py0, px1, py1)) continue;
+            uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
+            if (PASS == 0) atomicAdd(&b.tile_count[tile], 1u);
+            else {
+                uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
+                b.tile_list[b.tile_offset[tile] + at] = r;
+            }
+        }
+    }
+}
+
+/* exclusive scan of the per-tile counts (one CTA; at most 256x256 tiles for a 16384^2 framebuffer) */
+__global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = (i < ntiles) ? b.tile_count[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += n;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= (uint32_t)o) wi += n;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[warp] + incl - v;
+        if (i < ntiles) { b.tile_offset[i] = excl; b.tile_cursor[i] = 0u; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) b.counters->tile_refs = carry;
+}
+
+static int bin_grid() { return 148 * 8; }
+
+void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
+{
+    k_bin_small<0><<<bin_grid(), 256, 0, s>>>(b, fb);
+    k_bin_large<0><<<148 * 4, 128, 0, s>>>(b, fb);
+    note_launch(); note_launch();
+}
+
+void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
+{
+    k_bin_scan<<<1, 1024, 0, s>>>(b, (uint32_t)(fb.tiles_x * fb.tile_rows));
+    note_launch();
+}
+
+void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
+{
+    k_bin_small<1><<<bin_grid(), 256, 0, s>>>(b, fb);
+    k_bin_large<1><<<148 * 4, 128, 0, s>>>(b, fb);
+    note_launch(); note_launch();
+}
+
+} // namespace mtgl_dev_impl

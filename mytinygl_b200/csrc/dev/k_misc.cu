@@ -1,0 +1,51 @@
+/*
+ * k_misc.cu -- K6 and small utility kernels.
+ *
+ *   k_mip1        texture_generate_mip1 (src/textures.c:311-354): 2x2 box filter, sum of four
+ *                 n/255 floats * 0.25, truncating pack; built eagerly at upload instead of lazily
+ *                 inside the sampler (identical values).
+ *   k_fill_unorm8 the 256 correctly rounded quotients n / 255.0f that color_from_rgba32
+ *                 (src/graphics.h:350-357) produces, computed with the IEEE division itself.
+ */
+#include "dev_common.cuh"
+
+namespace mtgl_dev_impl {
+
+void note_launch();
+
+__global__ void k_fill_unorm8(float *table)
+{
+    int i = threadIdx.x;
+    if (i < 256) table[i] = (float)i / 255.0f;
+}
+
+__global__ void __launch_bounds__(256) k_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8)
+{
+    const int w1 = w / 2, h1 = h / 2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w1 * h1) return;
+    int x = i % w1, y = i / w1;
+    Color4 a = color_unpack(l0[(2 * y) * w + 2 * x], unorm8);
+    Color4 b = color_unpack(l0[(2 * y) * w + 2 * x + 1], unorm8);
+    Color4 c = color_unpack(l0[(2 * y + 1) * w + 2 * x], unorm8);
+    Color4 d = color_unpack(l0[(2 * y + 1) * w + 2 * x + 1], unorm8);
+    Color4 s = { ((a.r + b.r) + c.r) + d.r, ((a.g + b.g) + c.g) + d.g, ((a.b + b.b) + c.b) + d.b, ((a.a + b.a) + c.a) + d.a };
+    s.r *= 0.25f; s.g *= 0.25f; s.b *= 0.25f; s.a *= 0.25f;
+    l1[i] = color_pack(s);
+}
+
+void launch_fill_unorm8(float *table, cudaStream_t s)
+{
+    k_fill_unorm8<<<1, 256, 0, s>>>(table);
+    note_launch();
+}
+
+void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s)
+{
+    int n = (w / 2) * (h / 2);
+    if (n <= 0) return;
+    k_mip1<<<(n + 255) / 256, 256, 0, s>>>(l0, w, h, l1, unorm8);
+    note_launch();
+}
+
+} // namespace mtgl_dev_impl

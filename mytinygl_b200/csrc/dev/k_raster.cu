@@ -1,0 +1,621 @@
+/*
+ * k_raster.cu -- K4: fine rasterisation, texture sampling and per-fragment operations on
+ * tile-resident colour / depth / stencil, plus the fused glClear and the tile write-back (K5).
+ *
+ * Replaces the scan loop and fragment block of rasterize_triangle_smooth (src/raster.c:532-724),
+ * edge_function (299-302), depth_test / alpha_test / stencil_test / stencil_op /
+ * write_stencil_masked (344-448), get_blend_factor / blend_colors (360-387), write_pixel_masked
+ * (20-45), texture_sample_lod and helpers (src/textures.c:272-557), the per-fragment
+ * compute_lighting calls (raster.c:593-614) and glClear (src/gl_api.c:409-457).
+ *
+ * One CTA per 64x64 tile.  The three planes of the tile live in shared memory for the whole
+ * batch: loaded once with 128-bit loads (or initialised from the clear values when the batch
+ * starts with a clear that covers the tile -- a cleared tile is never read from HBM), updated in
+ * place by every fragment, written back once with 128-bit stores.  The tile's triangle references
+ * are sorted by submission id first.  Each of the 8 warps owns a fixed 32x16 pixel region, walks
+ * the sorted list 32 references at a time (one bounding-box test per lane, warp ballot), and
+ * rasterises the hits in order over 8x4-pixel blocks -- so every pixel sees its fragments in
+ * exactly the reference's order (blending, stencil counting, depth ties, double-shaded shared
+ * edges) without atomics or inter-warp synchronisation.
+ *
+ * Shared-memory rows are padded (72 words / 80 bytes) so that the 32 lanes of an 8x4 block hit
+ * 32 distinct banks.
+ *
+ * Roofline: algorithmically HBM-bound (2-18 B of framebuffer traffic per covered
+ * fragment in the reference's immediate-mode formulation); in this tile-resident formulation the
+ * real DRAM traffic is one load + one store per touched tile and the kernel is issue-bound.
+ */
+#include "dev_common.cuh"
+
+namespace mtgl_dev_impl {
+
+void note_launch();
+
+struct RasterSmem {
+    uint32_t color[TILE_H * COLOR_PITCH];
+    float depth[TILE_H * COLOR_PITCH];
+    uint8_t stencil[TILE_H * STENCIL_PITCH];
+    uint32_t key[LIST_WINDOW];
+    uint32_t rec[LIST_WINDOW];
+    uint32_t box[LIST_WINDOW];
+    float unorm8[256];
+    uint32_t count;
+    uint32_t scratch[RASTER_THREADS / 32];
+};
+
+/* ---------------------------------------------------------------- texture sampling (textures.c) */
+__device__ __forceinline__ uint32_t texel_wrapped(const uint32_t *px, int w, int h, uint32_t ws, uint32_t wt, int x, int y)
+{   /* get_texel_wrapped / get_mip1_texel_wrapped, textures.c:272-291, 357-376 */
+    if (ws == G_REPEAT) x = ((x % w) + w) % w; else { if (x < 0) x = 0; else if (x >= w) x = w - 1; }
+    if (wt == G_REPEAT) y = ((y % h) + h) % h; else { if (y < 0) y = 0; else if (y >= h) y = h - 1; }
+    return __ldg(px + y * w + x);
+}
+
+__device__ __forceinline__ uint32_t bilinear(uint32_t c00, uint32_t c10, uint32_t c01, uint32_t c11, float fx, float fy,
+                                             const float *un)
+{   /* bilinear_filter, textures.c:294-307: every stage result is truncated back to RGBA8 */
+    Color4 top = color_lerp(color_unpack(c00, un), color_unpack(c10, un), fx);
+    Color4 bot = color_lerp(color_unpack(c01, un), color_unpack(c11, un), fx);
+    return color_pack(color_lerp(top, bot, fy));
+}
+
+__device__ uint32_t sample_level(const uint32_t *px, int w, int h, uint32_t ws, uint32_t wt, float u, float v, bool linear,
+                                 const float *un)
+{   /* texture_sample_base / _mip1 / tail of texture_sample_lod, textures.c:379-451, 524-556 */
+    float tx = u * (float)w - 0.5f;
+    float ty = v * (float)h - 0.5f;
+    if (linear) {
+        int x0 = f2i_x86(floorf(tx)), y0 = f2i_x86(floorf(ty));
+        float fx = tx - (float)x0, fy = ty - (float)y0;
+        return bilinear(texel_wrapped(px, w, h, ws, wt, x0, y0), texel_wrapped(px, w, h, ws, wt, x0 + 1, y0),
+                        texel_wrapped(px, w, h, ws, wt, x0, y0 + 1), texel_wrapped(px, w, h, ws, wt, x0 + 1, y0 + 1), fx, fy, un);
+    }
+    int x = f2i_x86(floorf(tx + 0.5f)), y = f2i_x86(floorf(ty + 0.5f));
+    if (x < 0) x = 0;
+    if (x >= w) x = w - 1;
+    if (y < 0) y = 0;
+    if (y >= h) y = h - 1;
+    return __ldg(px + y * w + x);
+}
+
+__device__ __forceinline__ uint32_t sample_mip1(const RasterCfg *c, float u, float v, uint32_t filter, const float *un)
+{   /* texture_sample_mip1, textures.c:413-451: a level that cannot exist samples as opaque white */
+    if (!c->tex_l1) return 0xFFFFFFFFu;
+    bool linear = (filter == G_LINEAR || filter == G_LINEAR_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_LINEAR);
+    return sample_level(c->tex_l1, c->tex_w1, c->tex_h1, c->tex_wrap_s, c->tex_wrap_t, u, v, linear, un);
+}
+
+__device__ uint32_t sample_lod(const RasterCfg *c, float u, float v, float lod, const float *un)
+{   /* texture_sample_lod, textures.c:457-557 */
+    if (c->tex_wrap_s == G_REPEAT) { u = u - (float)f2i_x86(u); if (u < 0) u += 1.0f; }
+    else { if (u < 0.0f) u = 0.0f; if (u > 1.0f) u = 1.0f; }
+    if (c->tex_wrap_t == G_REPEAT) { v = v - (float)f2i_x86(v); if (v < 0) v += 1.0f; }
+    else { if (v < 0.0f) v = 0.0f; if (v > 1.0f) v = 1.0f; }
+
+    uint32_t filter = (lod > 0.0f) ? c->tex_min : c->tex_mag;
+    if (filter == G_NEAREST_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_NEAREST) {
+        if (lod >= 0.5f) return sample_mip1(c, u, v, filter, un);
+        filter = (filter == G_NEAREST_MIPMAP_NEAREST) ? G_NEAREST : G_LINEAR;
+    } else if (filter == G_NEAREST_MIPMAP_LINEAR || filter == G_LINEAR_MIPMAP_LINEAR) {
+        if (lod > 0.0f) {
+            float cl = (lod > 1.0f) ? 1.0f : lod;
+            bool base_linear = (filter != G_NEAREST_MIPMAP_LINEAR);
+            uint32_t c0 = sample_level(c->tex_l0, c->tex_w, c->tex_h, c->tex_wrap_s, c->tex_wrap_t, u, v, base_linear, un);
+            uint32_t c1 = sample_mip1(c, u, v, filter, un);
+            return color_pack(color_lerp(color_unpack(c0, un), color_unpack(c1, un), cl));
+        }
+        filter = (filter == G_NEAREST_MIPMAP_LINEAR) ? G_NEAREST : G_LINEAR;
+    }
+    return sample_level(c->tex_l0, c->tex_w, c->tex_h, c->tex_wrap_s, c->tex_wrap_t, u, v, filter == G_LINEAR, un);
+}
+
+/* ---------------------------------------------------------------- per-fragment helpers */
+__device__ __forceinline__ uint8_t stencil_apply(uint32_t op, uint8_t v, int32_t ref)   /* raster.c:425-438 */
+{
+    switch (op) {
+    case G_KEEP: return v;
+    case G_ZERO: return 0;
+    case G_REPLACE: return (uint8_t)(ref & 0xFF);
+    case G_INCR: return v < 255 ? (uint8_t)(v + 1) : (uint8_t)255;
+    case G_INCR_WRAP: return (uint8_t)(v + 1);
+    case G_DECR: return v > 0 ? (uint8_t)(v - 1) : (uint8_t)0;
+    case G_DECR_WRAP: return (uint8_t)(v - 1);
+    case G_INVERT: return (uint8_t)~v;
+    default: return v;
+    }
+}
+
+__device__ __forceinline__ Color4 blend_factor(uint32_t f, Color4 s, Color4 d)   /* raster.c:360-379 */
+{
+    switch (f) {
+    case G_ZERO: return { 0.0f, 0.0f, 0.0f, 0.0f };
+    case G_SRC_COLOR: return s;
+    case G_ONE_MINUS_SRC_COLOR: return { 1 - s.r, 1 - s.g, 1 - s.b, 1 - s.a };
+    case G_DST_COLOR: return d;
+    case G_ONE_MINUS_DST_COLOR: return { 1 - d.r, 1 - d.g, 1 - d.b, 1 - d.a };
+    case G_SRC_ALPHA: return { s.a, s.a, s.a, s.a };
+    case G_ONE_MINUS_SRC_ALPHA: return { 1 - s.a, 1 - s.a, 1 - s.a, 1 - s.a };
+    case G_DST_ALPHA: return { d.a, d.a, d.a, d.a };
+    case G_ONE_MINUS_DST_ALPHA: return { 1 - d.a, 1 - d.a, 1 - d.a, 1 - d.a };
+    case G_SRC_ALPHA_SATURATE: { float k = (s.a < (1 - d.a)) ? s.a : (1 - d.a); return { k, k, k, 1.0f }; }
+    default: return { 1.0f, 1.0f, 1.0f, 1.0f };     /* GL_ONE and the accepted-but-unimplemented GL_CONSTANT_* */
+    }
+}
+
+__device__ __forceinline__ float fog_factor(const RasterCfg *c, float coord)   /* raster.c:677-701 */
+{
+    float f;
+    switch (c->fog_mode) {
+    case G_LINEAR: f = (c->fog_end != c->fog_start) ? (c->fog_end - coord) / (c->fog_end - c->fog_start) : 1.0f; break;
+    case G_EXP: f = expf(-c->fog_density * coord); break;
+    case G_EXP2: { float d = c->fog_density * coord; f = expf(-d * d); break; }
+    default: f = 1.0f; break;
+    }
+    if (f < 0.0f) f = 0.0f;
+    if (f > 1.0f) f = 1.0f;
+    return f;
+}
+
+__device__ __forceinline__ float edge_at(float ax, float ay, float bx, float by, float px, float py)   /* raster.c:299-302 */
+{
+    return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
+}
+
+/* ---------------------------------------------------------------- one triangle over one warp region */
+__device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, int tile_px, int tile_py,
+                                int X0, int Y0, int X1, int Y1)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const TriRecord *rec = b.records + r;
+    const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+    const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+    const uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(rec) + 2);
+    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
+    const float4 row4 = __ldg(reinterpret_cast<const float4 *>(rec) + 4);
+    const float4 col0 = __ldg(reinterpret_cast<const float4 *>(rec) + 5);
+    const float4 col1 = __ldg(reinterpret_cast<const float4 *>(rec) + 6);
+    const float4 col2 = __ldg(reinterpret_cast<const float4 *>(rec) + 7);
+    const float4 row8 = __ldg(reinterpret_cast<const float4 *>(rec) + 8);
+    const float4 row9 = __ldg(reinterpret_cast<const float4 *>(rec) + 9);
+
+    const float fx0 = (float)row0.x, fy0 = (float)row0.y, fx1 = (float)row0.z, fy1 = (float)row0.w;
+    const float fx2 = (float)row1.x, fy2 = (float)row1.y;
+    const float area = __int_as_float(row1.z), inv_area = __int_as_float(row1.w);
+    const uint32_t state_index = row2.z & 0x7FFFFFFFu;
+    const bool back_facing = (row2.z >> 31) != 0;
+    const RasterCfg *cfg = b.cfgs + state_index;
+    const uint32_t flags = cfg->flags;
+    const float z0 = row3.x, z1 = row3.y, z2 = row3.z, lod = row3.w;
+    const float w0 = row4.x, w1 = row4.y, w2 = row4.z;
+    const float ez0 = row4.w, ez1 = row9.z, ez2 = row9.w;
+    const float u0 = row8.x, v0 = row8.y, u1 = row8.z, v1 = row8.w, u2 = row9.x, v2 = row9.y;
+    /* u/w, v/w per vertex (raster.c:501-503) */
+    const float u0w = u0 * w0, v0w = v0 * w0, u1w = u1 * w1, v1w = v1 * w1, u2w = u2 * w2, v2w = v2 * w2;
+    const bool area_pos = area > 0;
+    const float *un = sm.unorm8;
+
+    const bool relight = (flags & RC_LIGHTING) && ((flags & RC_PHONG) || (back_facing && (flags & RC_TWO_SIDE)));
+
+    for (int by = Y0; by <= Y1; by += 4) {
+        for (int bx = X0; bx <= X1; bx += 8) {
+            const int x = bx + (int)(lane & 7), y = by + (int)(lane >> 3);
+            bool active = (x <= X1) && (y <= Y1);
+            const float px = (float)(tile_px + x), py = (float)(tile_py + y);
+            const float e0 = edge_at(fx1, fy1, fx2, fy2, px, py);
+            const float e1 = edge_at(fx2, fy2, fx0, fy0, px, py);
+            const float e2 = edge_at(fx0, fy0, fx1, fy1, px, py);
+            /* inclusive on all three edges, no fill rule (raster.c:539-540) */
+            active = active && (area_pos ? (e0 >= 0 && e1 >= 0 && e2 >= 0) : (e0 <= 0 && e1 <= 0 && e2 <= 0));
+            if (!active) continue;
+
+            const float b0 = e0 * inv_area, b1 = e1 * inv_area, b2 = e2 * inv_area;
+            const float z = b0 * z0 + b1 * z1 + b2 * z2;
+            float depth;
+            if (flags & RC_DEPTH_RANGE_01) depth = (z + 1.0f) * 0.5f;
+            else depth = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
+
+            const int ci = y * COLOR_PITCH + x;
+            const int si = y * STENCIL_PITCH + x;
+
+            uint8_t sval = 0;
+            if (flags & RC_STENCIL) {                       /* raster.c:550-579 */
+                sval = sm.stencil[si];
+                const int32_t mref = (int32_t)((uint32_t)cfg->stencil_ref & cfg->stencil_mask);
+                const int32_t mval = (int32_t)((uint32_t)sval & cfg->stencil_mask);
+                const uint8_t wm = (uint8_t)(cfg->stencil_writemask & 0xFF);
+                if (!compare_i(cfg->stencil_func, mref, mval)) {
+                    uint8_t nv = stencil_apply(cfg->stencil_fail, sval, cfg->stencil_ref);
+                    sm.stencil[si] = (uint8_t)((sval & ~wm) | (nv & wm));
+                    continue;
+                }
+                if ((flags & RC_DEPTH_TEST) && !compare_f(cfg->depth_func, depth, sm.depth[ci])) {
+                    uint8_t nv = stencil_apply(cfg->stencil_zfail, sval, cfg->stencil_ref);
+                    sm.stencil[si] = (uint8_t)((sval & ~wm) | (nv & wm));
+                    continue;
+                }
+                uint8_t nv = stencil_apply(cfg->stencil_zpass, sval, cfg->stencil_ref);
+                sm.stencil[si] = (uint8_t)((sval & ~wm) | (nv & wm));
+            } else if (flags & RC_DEPTH_TEST) {
+                if (!compare_f(cfg->depth_func, depth, sm.depth[ci])) continue;
+            }
+
+            Color4 c;
+            if (flags & RC_FLAT) c = { col2.x, col2.y, col2.z, col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
+            else {
+                c.r = col0.x * b0 + col1.x * b1 + col2.x * b2;
+                c.g = col0.y * b0 + col1.y * b1 + col2.y * b2;
+                c.b = col0.z * b0 + col1.z * b1 + col2.z * b2;
+                c.a = col0.w * b0 + col1.w * b1 + col2.w * b2;
+            }
+
+            if (relight) {                                  /* raster.c:592-615 */
+                const TriEye *eye = b.rec_eye + r;
+                float ep[3], en[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    ep[k] = eye->ep0[k] * b0 + eye->ep1[k] * b1 + eye->ep2[k] * b2;
+                    en[k] = eye->en0[k] * b0 + eye->en1[k] * b1 + eye->en2[k] * b2;
+                }
+                const mtgl_state *st = b.states + state_index;
+                MaterialRegs mat;
+                if (back_facing && (flags & RC_TWO_SIDE)) {
+                    en[0] *= -1.0f; en[1] *= -1.0f; en[2] *= -1.0f;
+                    load_material(mat, &st->material_back);
+                } else load_material(mat, &st->material_front);
+                c = compute_lighting(st, ep[0], ep[1], ep[2], en[0], en[1], en[2], mat);
+            }
+
+            if (flags & RC_TEXTURED) {                      /* raster.c:618-669 */
+                float u, v;
+                if (flags & RC_PERSPECTIVE) {
+                    float uw = b0 * u0w + b1 * u1w + b2 * u2w;
+                    float vw = b0 * v0w + b1 * v1w + b2 * v2w;
+                    float ow = b0 * w0 + b1 * w1 + b2 * w2;
+                    float w = 1.0f / ow;
+                    u = uw * w;
+                    v = vw * w;
+                } else {
+                    u = b0 * u0 + b1 * u1 + b2 * u2;
+                    v = b0 * v0 + b1 * v1 + b2 * v2;
+                }
+                Color4 t = color_unpack(sample_lod(cfg, u, v, lod, un), un);
+                /* alpha test exists only here and tests the TEXEL alpha (raster.c:640-643) */
+                if ((flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, t.a, cfg->alpha_ref)) continue;
+                switch (cfg->tex_env_mode) {
+                case G_REPLACE: c = t; break;
+                case G_DECAL: c = color_lerp_rgb(c, t, t.a); break;
+                case G_BLEND: {
+                    const float *e = cfg->tex_env_color;
+                    c = { c.r * (1.0f - t.r) + e[0] * t.r, c.g * (1.0f - t.g) + e[1] * t.g, c.b * (1.0f - t.b) + e[2] * t.b, c.a * t.a };
+                    break;
+                }
+                case G_ADD: c = { c.r + t.r, c.g + t.g, c.b + t.b, c.a * t.a }; break;
+                default: c = { c.r * t.r, c.g * t.g, c.b * t.b, c.a * t.a }; break;
+                }
+            }
+
+            if (flags & RC_FOG) {                           /* raster.c:672-705; result alpha = fog colour alpha */
+                float fc = b0 * ez0 + b1 * ez1 + b2 * ez2;
+                Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
+                c = color_lerp_rgb(fogc, c, fog_factor(cfg, fc));
+            }
+
+            if ((flags & (RC_DEPTH_TEST | RC_DEPTH_WRITE)) == (RC_DEPTH_TEST | RC_DEPTH_WRITE)) sm.depth[ci] = depth;
+
+            if (flags & RC_BLEND) {                         /* raster.c:712-717 */
+                Color4 d = color_unpack(sm.color[ci], un);
+                Color4 sf = blend_factor(cfg->blend_src, c, d), df = blend_factor(cfg->blend_dst, c, d);
+                c = color_clamp({ c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a });
+            }
+            c = color_clamp(c);
+
+            const uint32_t cm = cfg->color_mask;            /* write_pixel_masked, raster.c:20-45 */
+            if (cm == 0xFu) sm.color[ci] = color_pack(c);
+            else if (cm != 0u) {
+                Color4 d = color_unpack(sm.color[ci], un);
+                if (cm & 1u) d.r = c.r;
+                if (cm & 2u) d.g = c.g;
+                if (cm & 4u) d.b = c.b;
+                if (cm & 8u) d.a = c.a;
+                sm.color[ci] = color_pack(d);
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- tile load / clear / store */
+__device__ void tile_init(RasterSmem &sm, const FrameTargets &fb, const ClearOp &clr, uint32_t planes, int px0, int py0,
+                          int vw, int vh)
+{
+    /* clear rectangle relative to the tile */
+    const int cx0 = max(clr.x0 - px0, 0), cy0 = max(clr.y0 - py0, 0);
+    const int cx1 = min(clr.x1 - px0, vw), cy1 = min(clr.y1 - py0, vh);
+    const bool clr_any = clr.mask && cx0 < cx1 && cy0 < cy1;
+    const bool clr_full = clr_any && cx0 == 0 && cy0 == 0 && cx1 == vw && cy1 == vh;
+    const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
+
+    if (planes & 1u) {
+        const bool cl = clr_any && (clr.mask & G_COLOR_BUFFER_BIT);
+        if (!(cl && clr_full)) {
+            if (vec) {
+                for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+                    int y = i >> 4, q = i & 15;
+                    uint4 v = *reinterpret_cast<const uint4 *>(fb.color + (size_t)(py0 + y) * fb.width + px0 + q * 4);
+                    *reinterpret_cast<uint4 *>(&sm.color[y * COLOR_PITCH + q * 4]) = v;
+                }
+            } else {
+                for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                    int y = i >> 6, x = i & 63;
+                    if (x < vw) sm.color[y * COLOR_PITCH + x] = fb.color[(size_t)(py0 + y) * fb.width + px0 + x];
+                }
+            }
+        }
+        if (cl) {
+            if (!clr_full) __syncthreads();
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) sm.color[y * COLOR_PITCH + x] = clr.color;
+            }
+        }
+    }
+    if (planes & 2u) {
+        const bool cl = clr_any && (clr.mask & G_DEPTH_BUFFER_BIT);
+        if (!(cl && clr_full)) {
+            if (vec) {
+                for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+                    int y = i >> 4, q = i & 15;
+                    float4 v = *reinterpret_cast<const float4 *>(fb.depth + (size_t)(py0 + y) * fb.width + px0 + q * 4);
+                    *reinterpret_cast<float4 *>(&sm.depth[y * COLOR_PITCH + q * 4]) = v;
+                }
+            } else {
+                for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                    int y = i >> 6, x = i & 63;
+                    if (x < vw) sm.depth[y * COLOR_PITCH + x] = fb.depth[(size_t)(py0 + y) * fb.width + px0 + x];
+                }
+            }
+        }
+        if (cl) {
+            if (!clr_full) __syncthreads();
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) sm.depth[y * COLOR_PITCH + x] = clr.depth;
+            }
+        }
+    }
+    if (planes & 4u) {
+        const bool cl = clr_any && (clr.mask & G_STENCIL_BUFFER_BIT);
+        if (!(cl && clr_full)) {
+            if (vec && (fb.width & 15) == 0) {
+                for (int i = threadIdx.x; i < vh * 4; i += RASTER_THREADS) {
+                    int y = i >> 2, q = i & 3;
+                    uint4 v = *reinterpret_cast<const uint4 *>(fb.stencil + (size_t)(py0 + y) * fb.width + px0 + q * 16);
+                    *reinterpret_cast<uint4 *>(&sm.stencil[y * STENCIL_PITCH + q * 16]) = v;
+                }
+            } else {
+                for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                    int y = i >> 6, x = i & 63;
+                    if (x < vw) sm.stencil[y * STENCIL_PITCH + x] = fb.stencil[(size_t)(py0 + y) * fb.width + px0 + x];
+                }
+            }
+        }
+        if (cl) {
+            if (!clr_full) __syncthreads();
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) sm.stencil[y * STENCIL_PITCH + x] = (uint8_t)clr.stencil;
+            }
+        }
+    }
+}
+
+__device__ void tile_store(RasterSmem &sm, const FrameTargets &fb, uint32_t planes, int px0, int py0, int vw, int vh)
+{
+    const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
+    if (planes & 1u) {
+        if (vec) {
+            for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+                int y = i >> 4, q = i & 15;
+                *reinterpret_cast<uint4 *>(fb.color + (size_t)(py0 + y) * fb.width + px0 + q * 4) =
+                    *reinterpret_cast<const uint4 *>(&sm.color[y * COLOR_PITCH + q * 4]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x < vw) fb.color[(size_t)(py0 + y) * fb.width + px0 + x] = sm.color[y * COLOR_PITCH + x];
+            }
+        }
+    }
+    if (planes & 2u) {
+        if (vec) {
+            for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+                int y = i >> 4, q = i & 15;
+                *reinterpret_cast<float4 *>(fb.depth + (size_t)(py0 + y) * fb.width + px0 + q * 4) =
+                    *reinterpret_cast<const float4 *>(&sm.depth[y * COLOR_PITCH + q * 4]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x < vw) fb.depth[(size_t)(py0 + y) * fb.width + px0 + x] = sm.depth[y * COLOR_PITCH + x];
+            }
+        }
+    }
+    if (planes & 4u) {
+        if (vec && (fb.width & 15) == 0) {
+            for (int i = threadIdx.x; i < vh * 4; i += RASTER_THREADS) {
+                int y = i >> 2, q = i & 3;
+                *reinterpret_cast<uint4 *>(fb.stencil + (size_t)(py0 + y) * fb.width + px0 + q * 16) =
+                    *reinterpret_cast<const uint4 *>(&sm.stencil[y * STENCIL_PITCH + q * 16]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x < vw) fb.stencil[(size_t)(py0 + y) * fb.width + px0 + x] = sm.stencil[y * STENCIL_PITCH + x];
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- list staging */
+__device__ __forceinline__ uint32_t pack_box(uint2 bb, int px0, int py0)
+{
+    int x0 = max((int)(bb.x & 0xFFFFu) - px0, 0), y0 = max((int)(bb.x >> 16) - py0, 0);
+    int x1 = min((int)(bb.y & 0xFFFFu) - px0, TILE_W - 1), y1 = min((int)(bb.y >> 16) - py0, TILE_H - 1);
+    return (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+}
+
+/* bitonic sort of (key, rec, box) triples by key; n padded to a power of two with key = ~0 */
+__device__ void sort_window(RasterSmem &sm, uint32_t n)
+{
+    uint32_t p = 32;
+    while (p < n) p <<= 1;
+    for (uint32_t i = n + threadIdx.x; i < p; i += RASTER_THREADS) sm.key[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint32_t k = 2; k <= p; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < p; i += RASTER_THREADS) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t a = sm.key[i], c = sm.key[ixj];
+                    bool up = ((i & k) == 0);
+                    if ((a > c) == up) {
+                        sm.key[i] = c; sm.key[ixj] = a;
+                        uint32_t t = sm.rec[i]; sm.rec[i] = sm.rec[ixj]; sm.rec[ixj] = t;
+                        t = sm.box[i]; sm.box[i] = sm.box[ixj]; sm.box[ixj] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+/* rasterise the n staged (sorted) references: every warp walks the whole window for its region */
+__device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, int px0, int py0)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rx0 = (int)(warp & 1) * REGION_W, ry0 = (int)(warp >> 1) * REGION_H;
+    const int rx1 = rx0 + REGION_W - 1, ry1 = ry0 + REGION_H - 1;
+    for (uint32_t base = 0; base < n; base += 32) {
+        uint32_t e = base + lane;
+        uint32_t box = 0;
+        bool hit = false;
+        if (e < n) {
+            box = sm.box[e];
+            int x0 = box & 0xFF, y0 = (box >> 8) & 0xFF, x1 = (box >> 16) & 0xFF, y1 = box >> 24;
+            hit = !(x1 < rx0 || x0 > rx1 || y1 < ry0 || y0 > ry1);
+        }
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+        while (mask) {
+            int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            uint32_t bx = __shfl_sync(0xFFFFFFFFu, box, k);
+            uint32_t r = sm.rec[base + k];
+            int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
+            int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
+            raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1);
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RasterSmem &sm = *reinterpret_cast<RasterSmem *>(smem_raw);
+
+    const uint32_t tile = blockIdx.x;
+    const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
+    const int px0 = tx << TILE_LOG, py0t = ty << TILE_LOG;
+    /* rows of this tile owned by the band, columns inside the framebuffer */
+    const int py0 = max(py0t, fb.band_y0);
+    const int vw = min(TILE_W, fb.width - px0);
+    const int vh = min(py0t + TILE_H, fb.band_y1) - py0;
+    if (vw <= 0 || vh <= 0) return;
+
+    const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
+    const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
+    if (L == 0 && !clr_here) return;
+
+    for (int i = threadIdx.x; i < 256; i += RASTER_THREADS) sm.unorm8[i] = b.unorm8[i];
+    /* shared-memory row 0 is framebuffer row py0 (the first row of the tile inside the band) */
+    tile_init(sm, fb, clr, planes, px0, py0, vw, vh);
+    __syncthreads();
+
+    if (L > 0) {
+        const uint32_t *list = b.tile_list + b.tile_offset[tile];
+        if (L <= (uint32_t)LIST_WINDOW) {
+            for (uint32_t i = threadIdx.x; i < L; i += RASTER_THREADS) {
+                uint32_t r = list[i];
+                uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(b.records + r) + 2);
+                sm.key[i] = row2.w;
+                sm.rec[i] = r;
+                sm.box[i] = pack_box(make_uint2(row2.x, row2.y), px0, py0);
+            }
+            __syncthreads();
+            sort_window(sm, L);
+            process_window(b, sm, L, px0, py0);
+        } else {
+            /* Long list: take the references in windows of increasing id.  The upper id bound of a
+             * window is found by bisection on the id value, counting with the whole CTA. */
+            unsigned long long lo = 0;
+            uint32_t done = 0;
+            while (done < L) {
+                unsigned long long a = lo + 1, z = 0x100000000ull;     /* answer in [a, z]: largest hi with count(lo<=id<hi) <= WINDOW */
+                while (a < z) {
+                    unsigned long long mid = (a + z + 1) >> 1;
+                    uint32_t cnt = 0;
+                    for (uint32_t i = threadIdx.x; i < L; i += RASTER_THREADS) {
+                        uint32_t id = __ldg(&b.records[list[i]].id);
+                        cnt += (id >= lo && id < mid) ? 1u : 0u;
+                    }
+                    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+                    if ((threadIdx.x & 31) == 0) sm.scratch[threadIdx.x >> 5] = cnt;
+                    __syncthreads();
+                    uint32_t total = 0;
+                    for (int w = 0; w < RASTER_THREADS / 32; w++) total += sm.scratch[w];
+                    __syncthreads();
+                    if (total <= (uint32_t)LIST_WINDOW) a = mid; else z = mid - 1;
+                }
+                const unsigned long long hi = a;
+                if (threadIdx.x == 0) sm.count = 0;
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < L; i += RASTER_THREADS) {
+                    uint32_t r = list[i];
+                    uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(b.records + r) + 2);
+                    if (row2.w >= lo && row2.w < hi) {
+                        uint32_t at = atomicAdd(&sm.count, 1u);
+                        sm.key[at] = row2.w;
+                        sm.rec[at] = r;
+                        sm.box[at] = pack_box(make_uint2(row2.x, row2.y), px0, py0);
+                    }
+                }
+                __syncthreads();
+                const uint32_t n = sm.count;
+                __syncthreads();
+                sort_window(sm, n);
+                process_window(b, sm, n, px0, py0);
+                __syncthreads();
+                done += n;
+                lo = hi;
+            }
+        }
+    }
+    __syncthreads();
+    tile_store(sm, fb, planes, px0, py0, vw, vh);
+}
+
+void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, cudaStream_t s)
+{
+    static bool configured[64] = { false };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {      /* the opt-in is per device */
+        cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
+        configured[dev] = true;
+    }
+    uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
+    if (tiles == 0 || planes == 0) return;
+    k_raster<<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes);
+    note_launch();
+}
+
+} // namespace mtgl_dev_impl

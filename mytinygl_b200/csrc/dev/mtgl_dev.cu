@@ -1,0 +1,598 @@
+/*
+ * mtgl_dev.cu -- host side of the C ABI (include/mtgl_dev.h): device memory management, object
+ * mirrors (buffer objects, textures + mip level 1), batch upload and kernel orchestration.
+ *
+ * HBM layout per context:
+ *   framebuffer planes   colour u32 / depth f32 / stencil u8, row 0 = top, pitch = width -- the
+ *                        reference's framebuffer_t (src/framebuffer.h:19-25), so read-back is a memcpy
+ *   object mirrors       one allocation per buffer object; per texture level 0 and level 1 (RGBA8 words)
+ *   batch arena          states | raster cfgs | staged vertices | draw records | prefix tables | index blob
+ *                        (one pinned-host -> device copy per batch)
+ *   vertex streams       3 (5 with per-fragment lighting) float4 SoA arrays, one slot per vertex
+ *   triangle records     160 B per surviving sub-triangle, worst case 7 per input triangle
+ *   tile tables          count / offset / cursor per 64x64 tile, and the reference lists
+ * All of it is grow-only and reused across batches; nothing is allocated per frame in steady state.
+ *
+ * There is no CPU path in this file: every entry point either runs CUDA work or fails.
+ */
+#include "dev_common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace mtgl_dev_impl;
+
+namespace {
+
+constexpr uint32_t kMaxObjects = 257;
+constexpr uint32_t kMaxTrisPerPass = 4u << 20;
+
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct TexObj { uint32_t *l0 = nullptr, *l1 = nullptr; int w = 0, h = 0, w1 = 0, h1 = 0; };
+struct BufObj { uint8_t *ptr = nullptr; uint64_t size = 0; };
+
+} // namespace
+
+struct mtgl_dev {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int32_t width = 0, height = 0, band_y0 = 0, band_y1 = 0;
+    uint32_t *color = nullptr;
+    float *depth = nullptr;
+    uint8_t *stencil = nullptr;
+    TexObj tex[kMaxObjects];
+    BufObj buf[kMaxObjects];
+    float *unorm8 = nullptr;
+
+    DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list;
+    DevBuf tile_count, tile_offset, tile_cursor, tile_list;
+    DevCounters *counters = nullptr;
+    DevCounters *h_counters = nullptr;      /* pinned */
+
+    uint8_t *pinned[2] = { nullptr, nullptr };
+    size_t pinned_cap[2] = { 0, 0 };
+    cudaEvent_t pinned_ev[2] = { nullptr, nullptr };
+    int pinned_next = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timed = false;
+
+    mtgl_dev_stats stats{};
+    char err[256] = { 0 };
+};
+
+namespace {
+
+int fail(mtgl_dev *d, int code, const char *what, cudaError_t ce = cudaSuccess)
+{
+    if (d) std::snprintf(d->err, sizeof d->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
+    return code;
+}
+
+#define CU(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t ce_ = (call);                                                            \
+        if (ce_ != cudaSuccess) return fail(d, ce_ == cudaErrorMemoryAllocation ? MTGL_E_OOM : MTGL_E_CUDA, #call, ce_); \
+    } while (0)
+
+int reserve(mtgl_dev *d, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return MTGL_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    /* queued kernels may still use the old allocation */
+    CU(cudaStreamSynchronize(d->stream));
+    if (b.ptr) CU(cudaFree(b.ptr));
+    b.ptr = nullptr; b.cap = 0;
+    CU(cudaMalloc(&b.ptr, want));
+    b.cap = want;
+    return MTGL_OK;
+}
+
+void release(DevBuf &b)
+{
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr; b.cap = 0;
+}
+
+uint32_t triangles_of(uint32_t mode, uint32_t n)   /* loop bounds of flush_* (raster.c:961-1017, 1199-1231) */
+{
+    switch (mode) {
+    case G_TRIANGLES: return n / 3;
+    case G_QUADS: return (n / 4) * 2;
+    case G_TRIANGLE_STRIP: case G_TRIANGLE_FAN: case G_POLYGON: return n >= 3 ? n - 2 : 0;
+    case G_QUAD_STRIP: return n >= 4 ? ((n - 2) / 2) * 2 : 0;
+    default: return 0;      /* points and lines: TODO(next) */
+    }
+}
+
+void build_cfg(const mtgl_dev *d, const mtgl_state &s, RasterCfg &c)
+{
+    std::memset(&c, 0, sizeof c);
+    uint32_t f = 0;
+    if (s.caps & MTGL_CAP_DEPTH_TEST) f |= RC_DEPTH_TEST;
+    if (s.depth_mask) f |= RC_DEPTH_WRITE;
+    if (s.caps & MTGL_CAP_STENCIL_TEST) f |= RC_STENCIL;
+    if (s.caps & MTGL_CAP_BLEND) f |= RC_BLEND;
+    if (s.caps & MTGL_CAP_ALPHA_TEST) f |= RC_ALPHA_TEST;
+    if (s.caps & MTGL_CAP_FOG) f |= RC_FOG;
+    if (s.caps & MTGL_CAP_LIGHTING) f |= RC_LIGHTING;
+    if (s.shade_model == G_FLAT) f |= RC_FLAT;
+    if (s.shade_model == G_PHONG) f |= RC_PHONG;
+    if (s.light_model_two_side) f |= RC_TWO_SIDE;
+    if (s.perspective_hint != G_FASTEST) f |= RC_PERSPECTIVE;
+    if (s.depth_near == 0.0 && s.depth_far == 1.0) f |= RC_DEPTH_RANGE_01;
+    /* raster.c:495-498, 618: texturing needs the cap, a bound texture and an uploaded image */
+    if ((s.caps & MTGL_CAP_TEXTURE_2D) && s.texture_id != 0 && s.texture_id < kMaxObjects && d->tex[s.texture_id].l0) {
+        const TexObj &t = d->tex[s.texture_id];
+        f |= RC_TEXTURED;
+        c.tex_l0 = t.l0; c.tex_l1 = t.l1;
+        c.tex_w = t.w; c.tex_h = t.h; c.tex_w1 = t.w1; c.tex_h1 = t.h1;
+        c.tex_min = s.tex_min_filter; c.tex_mag = s.tex_mag_filter;
+        c.tex_wrap_s = s.tex_wrap_s; c.tex_wrap_t = s.tex_wrap_t;
+    }
+    c.flags = f;
+    c.depth_func = s.depth_func - G_NEVER; c.alpha_func = s.alpha_func - G_NEVER; c.stencil_func = s.stencil_func - G_NEVER;
+    c.stencil_fail = s.stencil_fail; c.stencil_zfail = s.stencil_zfail; c.stencil_zpass = s.stencil_zpass;
+    c.stencil_ref = s.stencil_ref; c.stencil_mask = s.stencil_mask; c.stencil_writemask = s.stencil_writemask;
+    c.blend_src = s.blend_src; c.blend_dst = s.blend_dst;
+    c.color_mask = s.color_mask & 0xFu;
+    c.tex_env_mode = s.tex_env_mode; c.fog_mode = s.fog_mode;
+    c.alpha_ref = s.alpha_ref;
+    c.fog_density = s.fog_density; c.fog_start = s.fog_start; c.fog_end = s.fog_end;
+    std::memcpy(c.fog_color, s.fog_color, 16);
+    std::memcpy(c.tex_env_color, s.tex_env_color, 16);
+    c.depth_near = s.depth_near; c.depth_far = s.depth_far;
+}
+
+void describe(const mtgl_dev *d, const mtgl_attrib &a, DevAttrib &o)
+{
+    std::memset(&o, 0, sizeof o);
+    o.enabled = a.enabled;
+    if (!a.enabled) return;
+    o.stride = a.stride; o.size = a.size; o.type = a.type;
+    if (a.buffer != 0 && a.buffer < kMaxObjects && d->buf[a.buffer].ptr && a.offset <= d->buf[a.buffer].size) {
+        o.ptr = d->buf[a.buffer].ptr + a.offset;
+        o.avail = d->buf[a.buffer].size - a.offset;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+FrameTargets frame_targets(const mtgl_dev *d)
+{
+    FrameTargets fb;
+    fb.color = d->color; fb.depth = d->depth; fb.stencil = d->stencil;
+    fb.width = d->width; fb.height = d->height;
+    fb.band_y0 = d->band_y0; fb.band_y1 = d->band_y1;
+    fb.tiles_x = (d->width + TILE_W - 1) / TILE_W;
+    fb.tile_y0 = d->band_y0 >> TILE_LOG;
+    fb.tile_rows = (d->band_y1 > d->band_y0) ? (((d->band_y1 - 1) >> TILE_LOG) - fb.tile_y0 + 1) : 0;
+    return fb;
+}
+
+struct PassDraw { uint32_t draw; uint32_t tri_first, tri_count; };
+
+} // namespace
+
+extern "C" {
+
+int mtgl_dev_abi_version(void) { return MTGL_DEV_ABI_VERSION; }
+
+int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **out)
+{
+    if (!out || width <= 0 || height <= 0 || width > 16384 || height > 16384) return MTGL_E_INVALID;   /* framebuffer.h:30-36 */
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return MTGL_E_NO_DEVICE;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MTGL_E_NO_DEVICE;
+    if (device >= count) return MTGL_E_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MTGL_E_NO_DEVICE;
+    if (prop.major < 10) return MTGL_E_NO_DEVICE;    /* the kernels are built for sm_100a only */
+
+    mtgl_dev *d = new (std::nothrow) mtgl_dev();
+    if (!d) return MTGL_E_OOM;
+    d->device = device;
+    d->width = width; d->height = height; d->band_y0 = 0; d->band_y1 = height;
+    size_t n = (size_t)width * (size_t)height;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d->color, n * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d->depth, n * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d->stencil, n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d->unorm8, 256 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d->counters, sizeof(DevCounters));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&d->h_counters, sizeof(DevCounters));
+    for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&d->pinned_ev[i], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_start);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_stop);
+    if (ce != cudaSuccess) {
+        mtgl_dev_destroy(d);
+        return ce == cudaErrorMemoryAllocation ? MTGL_E_OOM : MTGL_E_CUDA;
+    }
+    launch_fill_unorm8(d->unorm8, d->stream);
+    *out = d;
+    return MTGL_OK;
+}
+
+void mtgl_dev_destroy(mtgl_dev *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (uint32_t i = 0; i < kMaxObjects; i++) {
+        if (d->tex[i].l0) cudaFree(d->tex[i].l0);
+        if (d->tex[i].l1) cudaFree(d->tex[i].l1);
+        if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
+    }
+    DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
+                       &d->chunk_base, &d->large_list, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_list };
+    for (DevBuf *b : bufs) release(*b);
+    if (d->color) cudaFree(d->color);
+    if (d->depth) cudaFree(d->depth);
+    if (d->stencil) cudaFree(d->stencil);
+    if (d->unorm8) cudaFree(d->unorm8);
+    if (d->counters) cudaFree(d->counters);
+    if (d->h_counters) cudaFreeHost(d->h_counters);
+    for (int i = 0; i < 2; i++) {
+        if (d->pinned[i]) cudaFreeHost(d->pinned[i]);
+        if (d->pinned_ev[i]) cudaEventDestroy(d->pinned_ev[i]);
+    }
+    if (d->ev_start) cudaEventDestroy(d->ev_start);
+    if (d->ev_stop) cudaEventDestroy(d->ev_stop);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int mtgl_dev_set_band(mtgl_dev *d, int32_t y0, int32_t y1)
+{
+    if (!d || y0 < 0 || y1 > d->height || y0 > y1) return MTGL_E_INVALID;
+    d->band_y0 = y0; d->band_y1 = y1;
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *data)
+{
+    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    BufObj &b = d->buf[id];
+    if (b.size != size || !b.ptr) {
+        CU(cudaStreamSynchronize(d->stream));
+        if (b.ptr) CU(cudaFree(b.ptr));
+        b.ptr = nullptr; b.size = 0;
+        if (size == 0) return MTGL_OK;
+        CU(cudaMalloc(&b.ptr, size));
+        b.size = size;
+    }
+    if (size && data) {
+        CU(cudaMemcpyAsync(b.ptr, data, size, cudaMemcpyHostToDevice, d->stream));
+        /* the caller may reuse 'data' immediately (glBufferData copies at call time, vbo.c:120-145) */
+        CU(cudaStreamSynchronize(d->stream));
+    }
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, const void *data)
+{
+    if (!d || id == 0 || id >= kMaxObjects || !data) return MTGL_E_INVALID;
+    BufObj &b = d->buf[id];
+    if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    if (size) {
+        CU(cudaMemcpyAsync(b.ptr + offset, data, size, cudaMemcpyHostToDevice, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+    }
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
+{
+    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    BufObj &b = d->buf[id];
+    if (b.ptr) {
+        CU(cudaStreamSynchronize(d->stream));
+        CU(cudaFree(b.ptr));
+    }
+    b.ptr = nullptr; b.size = 0;
+    return MTGL_OK;
+}
+
+int mtgl_dev_texture_image(mtgl_dev *d, uint32_t id, int32_t w, int32_t h, const uint32_t *rgba8)
+{
+    if (!d || id == 0 || id >= kMaxObjects || w <= 0 || h <= 0 || w > 2048 || h > 2048 || !rgba8) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    TexObj &t = d->tex[id];
+    CU(cudaStreamSynchronize(d->stream));
+    if (t.l0) CU(cudaFree(t.l0));
+    if (t.l1) CU(cudaFree(t.l1));
+    t = TexObj();
+    size_t n = (size_t)w * (size_t)h;
+    CU(cudaMalloc(&t.l0, n * 4));
+    t.w = w; t.h = h;
+    CU(cudaMemcpyAsync(t.l0, rgba8, n * 4, cudaMemcpyHostToDevice, d->stream));
+    if (w >= 2 && h >= 2) {      /* textures.c:317: level 1 needs both dimensions >= 2 */
+        t.w1 = w / 2; t.h1 = h / 2;
+        CU(cudaMalloc(&t.l1, (size_t)t.w1 * t.h1 * 4));
+        launch_mip1(t.l0, w, h, t.l1, d->unorm8, d->stream);
+    }
+    CU(cudaStreamSynchronize(d->stream));
+    return MTGL_OK;
+}
+
+int mtgl_dev_texture_delete(mtgl_dev *d, uint32_t id)
+{
+    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    TexObj &t = d->tex[id];
+    if (t.l0 || t.l1) CU(cudaStreamSynchronize(d->stream));
+    if (t.l0) CU(cudaFree(t.l0));
+    if (t.l1) CU(cudaFree(t.l1));
+    t = TexObj();
+    return MTGL_OK;
+}
+
+int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
+{
+    if (!d || !bt) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    const FrameTargets fb = frame_targets(d);
+    const uint32_t ntiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
+
+    /* ---- validate + per-draw prefix tables ---- */
+    std::vector<DevDraw> draws;
+    draws.reserve(bt->n_draws);
+    uint32_t planes = 0;
+    bool need_eye = false;
+    for (uint32_t i = 0; i < bt->n_draws; i++) {
+        const mtgl_draw &s = bt->draws[i];
+        if (s.raster_state >= bt->n_states) return fail(d, MTGL_E_INVALID, "draw refers to a missing state block");
+        if (s.source == MTGL_SRC_STAGED && (uint64_t)s.first_staged + s.count > bt->n_vertices) return fail(d, MTGL_E_INVALID, "draw exceeds the staged vertices");
+        if (s.source == MTGL_SRC_ARRAYS && s.vertex_state >= bt->n_states) return fail(d, MTGL_E_INVALID, "draw refers to a missing vertex state");
+        DevDraw o;
+        std::memset(&o, 0, sizeof o);
+        o.mode = s.mode; o.count = s.count; o.raster_state = s.raster_state; o.source = s.source;
+        o.first_staged = s.first_staged; o.vertex_state = s.vertex_state; o.first = s.first; o.index_type = s.index_type;
+        std::memcpy(o.cur_color, s.cur_color, 16); std::memcpy(o.cur_texcoord, s.cur_texcoord, 8); std::memcpy(o.cur_normal, s.cur_normal, 12);
+        describe(d, s.position, o.position); describe(d, s.color, o.color);
+        describe(d, s.texcoord, o.texcoord); describe(d, s.normal, o.normal);
+        o.ntris = triangles_of(s.mode, s.count);
+        draws.push_back(o);
+        const mtgl_state &rs = bt->states[s.raster_state];
+        planes |= 1u;
+        if (rs.caps & MTGL_CAP_DEPTH_TEST) planes |= 2u;
+        if (rs.caps & MTGL_CAP_STENCIL_TEST) planes |= 4u;
+        if ((rs.caps & MTGL_CAP_LIGHTING) && (rs.shade_model == G_PHONG || rs.light_model_two_side)) need_eye = true;
+    }
+    if (bt->clear_mask & G_COLOR_BUFFER_BIT) planes |= 1u;
+    if (bt->clear_mask & G_DEPTH_BUFFER_BIT) planes |= 2u;
+    if (bt->clear_mask & G_STENCIL_BUFFER_BIT) planes |= 4u;
+    if (planes == 0) return MTGL_OK;
+
+    /* ---- split into passes that fit the worst-case record storage ---- */
+    std::vector<std::vector<PassDraw>> passes(1);
+    {
+        uint32_t room = kMaxTrisPerPass;
+        for (uint32_t i = 0; i < draws.size(); i++) {
+            uint32_t left = draws[i].ntris, first = 0;
+            while (left) {
+                if (room == 0) { passes.emplace_back(); room = kMaxTrisPerPass; }
+                uint32_t take = std::min(left, room);
+                passes.back().push_back({ i, first, take });
+                first += take; left -= take; room -= take;
+            }
+        }
+    }
+
+    /* ---- batch arena: states | cfgs | staged | blob (shared by all passes) ---- */
+    std::vector<RasterCfg> cfgs(bt->n_states);
+    for (uint32_t i = 0; i < bt->n_states; i++) build_cfg(d, bt->states[i], cfgs[i]);
+    const size_t sz_states = align_up((size_t)bt->n_states * sizeof(mtgl_state), 256);
+    const size_t sz_cfgs = align_up((size_t)bt->n_states * sizeof(RasterCfg), 256);
+    const size_t sz_staged = align_up((size_t)bt->n_vertices * sizeof(mtgl_in_vertex), 256);
+    const size_t sz_blob = align_up((size_t)bt->blob_size, 256);
+    size_t max_pass_draws = 0;
+    for (auto &p : passes) max_pass_draws = std::max(max_pass_draws, p.size());
+    const size_t sz_draws = align_up(max_pass_draws * sizeof(DevDraw), 256);
+    const size_t sz_prefix = align_up((max_pass_draws + 1) * sizeof(uint32_t), 256);
+    const size_t arena_fixed = sz_states + sz_cfgs + sz_staged + sz_blob;
+    const size_t arena_pass = sz_draws + 2 * sz_prefix;
+    const size_t arena_total = arena_fixed + arena_pass * passes.size();
+
+    int rc = reserve(d, d->arena, arena_total);
+    if (rc != MTGL_OK) return rc;
+    const int slot = d->pinned_next;
+    d->pinned_next ^= 1;
+    CU(cudaEventSynchronize(d->pinned_ev[slot]));       /* the previous copy out of this staging buffer is done */
+    if (d->pinned_cap[slot] < arena_total) {
+        if (d->pinned[slot]) CU(cudaFreeHost(d->pinned[slot]));
+        d->pinned[slot] = nullptr; d->pinned_cap[slot] = 0;
+        size_t want = align_up(arena_total + arena_total / 2, 4096);
+        CU(cudaMallocHost(&d->pinned[slot], want));
+        d->pinned_cap[slot] = want;
+    }
+    uint8_t *hp = d->pinned[slot];
+    uint8_t *dp = (uint8_t *)d->arena.ptr;
+    size_t off = 0;
+    const size_t o_states = off; if (bt->n_states) std::memcpy(hp + off, bt->states, (size_t)bt->n_states * sizeof(mtgl_state)); off += sz_states;
+    const size_t o_cfgs = off; if (bt->n_states) std::memcpy(hp + off, cfgs.data(), (size_t)bt->n_states * sizeof(RasterCfg)); off += sz_cfgs;
+    const size_t o_staged = off; if (bt->n_vertices) std::memcpy(hp + off, bt->vertices, (size_t)bt->n_vertices * sizeof(mtgl_in_vertex)); off += sz_staged;
+    const size_t o_blob = off; if (bt->blob_size) std::memcpy(hp + off, bt->blob, (size_t)bt->blob_size); off += sz_blob;
+
+    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles; };
+    std::vector<PassInfo> infos;
+    for (auto &p : passes) {
+        PassInfo pi{};
+        pi.o_draws = off; off += sz_draws;
+        pi.o_vbase = off; off += sz_prefix;
+        pi.o_tbase = off; off += sz_prefix;
+        DevDraw *pd = reinterpret_cast<DevDraw *>(hp + pi.o_draws);
+        uint32_t *vb = reinterpret_cast<uint32_t *>(hp + pi.o_vbase), *tb = reinterpret_cast<uint32_t *>(hp + pi.o_tbase);
+        uint32_t v = 0, t = 0, k = 0;
+        for (const PassDraw &q : p) {
+            DevDraw o = draws[q.draw];
+            const mtgl_draw &s = bt->draws[q.draw];
+            if (o.index_type) {
+                if (s.index_buffer) {
+                    if (s.index_buffer < kMaxObjects && d->buf[s.index_buffer].ptr && s.index_offset <= d->buf[s.index_buffer].size) {
+                        o.index_ptr = d->buf[s.index_buffer].ptr + s.index_offset;
+                        o.index_avail = d->buf[s.index_buffer].size - s.index_offset;
+                    }
+                } else if (s.index_offset <= bt->blob_size) {
+                    o.index_ptr = dp + o_blob + s.index_offset;
+                    o.index_avail = bt->blob_size - s.index_offset;
+                }
+            }
+            o.vbase = v;
+            o.tbase = t - q.tri_first;      /* triangle k of the draw has global index tbase + k */
+            o.ntris = q.tri_count;
+            vb[k] = v; tb[k] = t;
+            pd[k++] = o;
+            v += o.count; t += q.tri_count;
+        }
+        vb[k] = v; tb[k] = t;
+        pi.n_draws = k; pi.n_vertices = v; pi.n_triangles = t;
+        infos.push_back(pi);
+    }
+    CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaEventRecord(d->pinned_ev[slot], d->stream));
+
+    CU(cudaEventRecord(d->ev_start, d->stream));
+    d->timed = true;
+    uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0;
+
+    for (size_t pidx = 0; pidx < passes.size(); pidx++) {
+        const PassInfo &pi = infos[pidx];
+        BatchDev b;
+        std::memset(&b, 0, sizeof b);
+        b.states = reinterpret_cast<const mtgl_state *>(dp + o_states);
+        b.cfgs = reinterpret_cast<const RasterCfg *>(dp + o_cfgs);
+        b.staged = reinterpret_cast<const mtgl_in_vertex *>(dp + o_staged);
+        b.draws = reinterpret_cast<const DevDraw *>(dp + pi.o_draws);
+        b.draw_vbase = reinterpret_cast<const uint32_t *>(dp + pi.o_vbase);
+        b.draw_tbase = reinterpret_cast<const uint32_t *>(dp + pi.o_tbase);
+        b.n_draws = pi.n_draws; b.n_vertices = pi.n_vertices; b.n_triangles = pi.n_triangles;
+        b.need_eye = need_eye ? 1u : 0u;
+        b.unorm8 = d->unorm8;
+        b.counters = d->counters;
+
+        ClearOp clr;
+        std::memset(&clr, 0, sizeof clr);
+        if (pidx == 0 && bt->clear_mask) {
+            clr.mask = bt->clear_mask;
+            clr.x0 = bt->clear_rect[0]; clr.y0 = bt->clear_rect[1]; clr.x1 = bt->clear_rect[2]; clr.y1 = bt->clear_rect[3];
+            clr.color = bt->clear_color; clr.depth = bt->clear_depth; clr.stencil = bt->clear_stencil;
+        }
+
+        if (pi.n_triangles > 0 && ntiles > 0) {
+            const size_t nv = pi.n_vertices;
+            const uint32_t chunks = (pi.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS;
+            const size_t rec_cap = (size_t)pi.n_triangles * 7;
+            if ((rc = reserve(d, d->v_clip, nv * 16)) || (rc = reserve(d, d->v_color, nv * 16)) || (rc = reserve(d, d->v_tex, nv * 16))) return rc;
+            if (need_eye && ((rc = reserve(d, d->v_epos, nv * 16)) || (rc = reserve(d, d->v_enrm, nv * 16)))) return rc;
+            if ((rc = reserve(d, d->records, rec_cap * sizeof(TriRecord)))) return rc;
+            if (need_eye && (rc = reserve(d, d->rec_eye, rec_cap * sizeof(TriEye)))) return rc;
+            if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4))) return rc;
+            if ((rc = reserve(d, d->tile_count, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_offset, (size_t)ntiles * 4)) ||
+                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4))) return rc;
+            b.v_clip = (float4 *)d->v_clip.ptr; b.v_color = (float4 *)d->v_color.ptr; b.v_tex = (float4 *)d->v_tex.ptr;
+            b.v_epos = (float4 *)d->v_epos.ptr; b.v_enrm = (float4 *)d->v_enrm.ptr;
+            b.records = (TriRecord *)d->records.ptr; b.rec_eye = (TriEye *)d->rec_eye.ptr;
+            b.record_capacity = (uint32_t)std::min<size_t>(rec_cap, 0xFFFFFFFFu);
+            b.chunk_base = (uint32_t *)d->chunk_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
+            b.tile_count = (uint32_t *)d->tile_count.ptr; b.tile_offset = (uint32_t *)d->tile_offset.ptr;
+            b.tile_cursor = (uint32_t *)d->tile_cursor.ptr;
+
+            CU(cudaMemsetAsync(d->counters, 0, sizeof(DevCounters), d->stream));
+            CU(cudaMemsetAsync(b.tile_count, 0, (size_t)ntiles * 4, d->stream));
+            launch_vertex_stage(b, d->stream);
+            launch_setup(b, fb, d->stream);
+            launch_bin_count(b, fb, d->stream);
+            launch_bin_scan(b, fb, d->stream);
+            /* the list length is only known on the device: one small read-back sizes the list buffer */
+            CU(cudaMemcpyAsync(d->h_counters, d->counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, d->stream));
+            CU(cudaStreamSynchronize(d->stream));
+            if (d->h_counters->overflow) return fail(d, MTGL_E_OOM, "triangle record storage overflow");
+            const uint32_t refs = d->h_counters->tile_refs;
+            if ((rc = reserve(d, d->tile_list, std::max<size_t>((size_t)refs * 4, 1024)))) return rc;
+            b.tile_list = (uint32_t *)d->tile_list.ptr;
+            b.list_capacity = (uint32_t)(d->tile_list.cap / 4);
+            if (refs) launch_bin_fill(b, fb, d->stream);
+            tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += refs;
+        }
+        launch_raster(b, fb, clr, planes, d->stream);
+    }
+    CU(cudaEventRecord(d->ev_stop, d->stream));
+    CU(cudaGetLastError());
+    d->stats.vertices = tot_v; d->stats.triangles_in = tot_t; d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs;
+    return MTGL_OK;
+}
+
+int mtgl_dev_finish(mtgl_dev *d)
+{
+    if (!d) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    CU(cudaStreamSynchronize(d->stream));
+    return MTGL_OK;
+}
+
+int mtgl_dev_read_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *color, float *depth, uint8_t *stencil)
+{
+    if (!d || y0 < 0 || y1 > d->height || y0 > y1) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
+    if (n == 0) return MTGL_OK;
+    if (color) CU(cudaMemcpyAsync(color + o, d->color + o, n * 4, cudaMemcpyDeviceToHost, d->stream));
+    if (depth) CU(cudaMemcpyAsync(depth + o, d->depth + o, n * 4, cudaMemcpyDeviceToHost, d->stream));
+    if (stencil) CU(cudaMemcpyAsync(stencil + o, d->stencil + o, n, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return MTGL_OK;
+}
+
+int mtgl_dev_write_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, const uint32_t *color, const float *depth, const uint8_t *stencil)
+{
+    if (!d || y0 < 0 || y1 > d->height || y0 > y1) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
+    if (n == 0) return MTGL_OK;
+    if (color) CU(cudaMemcpyAsync(d->color + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
+    if (depth) CU(cudaMemcpyAsync(d->depth + o, depth + o, n * 4, cudaMemcpyHostToDevice, d->stream));
+    if (stencil) CU(cudaMemcpyAsync(d->stencil + o, stencil + o, n, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return MTGL_OK;
+}
+
+int mtgl_dev_plane_pointers(mtgl_dev *d, void **color, void **depth, void **stencil)
+{
+    if (!d) return MTGL_E_INVALID;
+    if (color) *color = d->color;
+    if (depth) *depth = d->depth;
+    if (stencil) *stencil = d->stencil;
+    return MTGL_OK;
+}
+
+int mtgl_dev_get_stats(mtgl_dev *d, mtgl_dev_stats *out)
+{
+    if (!d || !out) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    if (d->timed) {
+        CU(cudaEventSynchronize(d->ev_stop));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, d->ev_start, d->ev_stop));
+        d->stats.last_batch_ms = ms;
+    }
+    d->stats.kernel_launches = kernel_launch_count();
+    *out = d->stats;
+    return MTGL_OK;
+}
+
+const char *mtgl_dev_last_error(mtgl_dev *d) { return d ? d->err : "no device"; }
+
+} // extern "C"

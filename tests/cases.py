@@ -1,0 +1,35 @@
+"""Scene cases shared by the CPU (oracle vs reference) and GPU (CUDA vs oracle/reference) parity tests.
+
+Each case is (scene, width, height, variant); see tests/scenes/scenes.c for what the variants select.
+Sizes are chosen so that the CPU oracle finishes each case in well under a second.
+"""
+
+C4_SMALL = 3 | (2 << 8)          # 3x2 Suzannes
+C4_SMALL_PHONG = C4_SMALL | (1 << 16)
+
+CASES = (
+    [("c1_suzanne", 800, 600, v) for v in range(5)]
+    + [("c1_suzanne", 333, 211, 0)]                       # framebuffer not a multiple of the tile / vector width
+    + [("c2_cube", 480, 270, 0), ("c2_cube", 1920, 1080, 0)]
+    + [("c2_floor", 400, 300, v) for v in range(6)]
+    + [("c2_texenv", 320, 240, v) for v in range(5)]
+    + [("c3_fill", 256, 144, 4), ("c3_fill", 640, 360, 9)]
+    + [("c4_grid", 480, 270, C4_SMALL), ("c4_grid", 480, 270, C4_SMALL_PHONG), ("c4_grid", 960, 540, 6 | (4 << 8))]
+    + [("clipping", 320, 240, v) for v in range(2)]
+    + [("primitives", 320, 240, v) for v in (0, 1, 3, 5, 7, 8)]
+    + [("zbuffer", 320, 240, v) for v in list(range(8)) + [9, 17]]
+    + [("fog", 320, 240, v) for v in range(3)]
+    + [("blend", 320, 240, v) for v in range(8)]
+    + [("stencil", 300, 200, v) for v in range(4)]
+    + [("lighting", 320, 240, v) for v in range(6)]
+    + [("displaylist", 320, 240, v) for v in range(2)]
+    + [("vbo", 320, 240, v) for v in range(2)]
+    + [("validation", 320, 240, 0)]
+    + [("scissor", 320, 240, v) for v in range(4)]
+    + [("texture_misc", 320, 240, v) for v in range(16)]
+    + [("state_churn", 320, 240, 0), ("state_churn", 517, 389, 0)]
+)
+
+
+def case_id(c):
+    return f"{c[0]}-{c[1]}x{c[2]}-v{c[3]}"
