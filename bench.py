@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native MyTinyGL back end.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c3|c5]
+
+A "step" is one frame of the workload: glClear + the draw calls + whatever makes the result observable.
+Default workload: C4 of BASELINE.json -- 38x28 Suzannes (1 029 952 triangles, 3 089 856 vertices), 8 lights,
+trilinear 64x64 texture, one glDrawArrays from a VBO, 3840x2160.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  value        covered fragments/s with the VBO and texture resident in HBM (device-timed, K frames)
+  e2e          the same metric with the per-frame host->device upload of the 98.9 MB vertex buffer from pinned
+               host memory and the device->host read-back of the colour plane inside the timed region,
+               through the public gl* API + the C ABI
+  roofline     the tile raster kernel (K4/K5): algorithmic framebuffer bytes per launch (SURVEY.md 8d:
+               4 B per covered + 8 B per depth-passing fragment + cleared bytes) / its CUDA-event duration,
+               against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline the unmodified reference (as-shipped flags, 1 thread) on this box's host CPU
+  stages_ms    CUDA-event time per pipeline stage, mean over the timed steps
+
+Multi-GPU (torchrun, one rank per GPU): sort-first bands of framebuffer rows; every rank runs the vertex and
+set-up stages on the whole scene and bins / rasterises only its band; the colour bands are gathered into
+rank 0's framebuffer with NCCL point-to-point over NVLink.  Total work is fixed: "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from mytinygl_b200 import load_b200, load_reference  # noqa: E402
+
+GL_ARRAY_BUFFER = 0x8892
+GL_STATIC_DRAW = 0x88E4
+
+WORKLOADS = {
+    # name: (counts key, width, height, c4 variant / c3 quads)
+    "c4": ("c4_grid_3840x2160", 3840, 2160, 0),
+    "c5": ("c5_grid_7680x4320", 7680, 4320, 0),
+    "c3": ("c3_fill_3840x2160", 3840, 2160, 64),
+}
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("vertices", ctypes.c_uint64), ("triangles_in", ctypes.c_uint64), ("triangles_setup", ctypes.c_uint64),
+                ("tile_refs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("last_batch_ms", ctypes.c_float),
+                ("stage_ms", ctypes.c_float * 5)]
+
+
+def counts_for(key):
+    return json.loads((ROOT / "tests" / "golden" / "workload_counts.json").read_text())[key]
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, workload):
+    """The reference's own CPU implementation, unmodified, as-shipped flags, one thread (it has no threading)."""
+    key, w, h, variant = WORKLOADS[workload]
+    cnt = counts_for(key)
+    lib = load_reference("shipped")
+    lib.create(w, h)
+    steps = max(1, min(args.steps, 3))           # a C4 frame takes ~3 s on one host core
+    warm = 1 if args.warmup > 0 else 0
+    times = []
+    if workload == "c3":
+        for i in range(warm + 1):                # ~40 s per frame: a single timed frame is the bounded sample
+            t0 = time.perf_counter()
+            lib.lib.scene_render(b"c3_fill", w, h, variant)
+            times.append(time.perf_counter() - t0)
+        times = times[-1:]
+        sample = "1 full C3 frame (64 full-screen quads)"
+    else:
+        lib.lib.scene_c4_setup(w, h, variant)
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            lib.lib.scene_c4_draw()
+            lib.lib.glFinish()
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+        sample = f"{len(times)} full frames of the workload, VBO resident in host memory"
+    lib.destroy()
+    t = float(np.mean(times))
+    value = cnt["covered"] / t
+    return {
+        "impl": "reference", "metric": "covered_fragments_per_s", "value": value, "unit": "fragments/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_s": 1.0 / t,
+        "config": {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3},
+        "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": 1, "kind": "reference", "sample": sample,
+                         "build": lib.kind, "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def band_rows(height, rank, world):
+    """Contiguous bands of 64-row tile rows, as even as possible."""
+    tile_rows = (height + 63) // 64
+    lo = (tile_rows * rank) // world
+    hi = (tile_rows * (rank + 1)) // world
+    return min(lo * 64, height), min(hi * 64, height)
+
+
+class DevTensor:
+    """Zero-copy torch view of a device allocation owned by the C library."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+def run_b200(args, workload):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    key, w, h, variant = WORKLOADS[workload]
+    cnt = counts_for(key)
+    lib = load_b200()
+    L = lib.lib
+    L.mtgl_set_device(local)
+    lib.create(w, h)
+    dev = lib.device()
+    L.mtgl_dev_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+    L.mtgl_dev_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.mtgl_dev_timer_elapsed_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    L.mtgl_dev_set_band.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.mtgl_dev_plane_pointers.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 3
+    L.mtgl_dev_read_framebuffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+    L.glBindBuffer.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    L.glBufferData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
+    L.scene_c4_host_data.restype = ctypes.c_void_p
+    L.scene_c4_vbo.restype = ctypes.c_uint
+
+    y0, y1 = band_rows(h, rank, world)
+    if world > 1:
+        assert L.mtgl_dev_set_band(dev, y0, y1) == 0
+
+    is_c3 = workload == "c3"
+    if not is_c3:
+        L.scene_c4_setup(w, h, variant)
+
+    def frame():
+        if is_c3:
+            L.scene_render(b"c3_fill", w, h, variant)
+        else:
+            L.scene_c4_draw()
+
+    # colour plane as a torch tensor for the band gather
+    cptr = ctypes.c_void_p()
+    L.mtgl_dev_plane_pointers(dev, ctypes.byref(cptr), None, None)
+    color_dev = torch.as_tensor(DevTensor(cptr.value, w * h * 4), device=f"cuda:{local}") if world > 1 else None
+
+    def gather():
+        """colour rows of every band -> rank 0's framebuffer (NCCL send/recv over NVLink)"""
+        if world == 1:
+            return
+        L.glFinish()
+        ops = []
+        if rank == 0:
+            for r in range(1, world):
+                a, b = band_rows(h, r, world)
+                if b > a:
+                    ops.append(dist.P2POp(dist.irecv, color_dev[a * w * 4:b * w * 4], r))
+        elif y1 > y0:
+            ops.append(dist.P2POp(dist.isend, color_dev[y0 * w * 4:y1 * w * 4], 0))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def sync_all():
+        L.glFinish()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # L2 hygiene: C4/C5 stream > 126 MB per frame (98.9 MB of vertices, 165 MB of triangle records, 74 MB of planes),
+    # i.e. inputs larger than L2; the C3 working set is small, so flush L2 between its frames.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if is_c3 else None
+
+    for _ in range(max(args.warmup, 3)):
+        frame(); gather()
+    sync_all()
+
+    st = Stats()
+    L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+    launches0 = st.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    stage = np.zeros(5)
+    batch_ms = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ms_total = 0.0
+    sync_all()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1); torch.cuda.synchronize()
+        L.mtgl_dev_timer_mark(dev, 0)
+        frame()
+        gather()
+        L.glFinish()
+        L.mtgl_dev_timer_mark(dev, 1)
+        ms = ctypes.c_float()
+        L.mtgl_dev_timer_elapsed_ms(dev, ctypes.byref(ms))
+        dev_ms_total += ms.value
+        L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+        stage += np.array(list(st.stage_ms))
+        batch_ms += st.last_batch_ms
+    ev1.record()
+    sync_all()
+    wall_s = time.perf_counter() - t_wall0
+    # device time of the K steps: CUDA events on the library's stream around each step (flushes excluded);
+    # for N > 1 the NCCL gather runs on torch's stream, so the bracketing torch events are used instead
+    elapsed_ms = dev_ms_total if world == 1 else ev0.elapsed_time(ev1)
+    if dist:
+        tt = torch.tensor([elapsed_ms], device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+    launches = int(st.kernel_launches - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the public API with host buffers (C4/C5: VBO re-upload + read-back) ----
+    e2e = None
+    h2d = d2h = 0
+    pinned_out = torch.empty((y1 - y0) * w, dtype=torch.int32).pin_memory() if y1 > y0 else None
+    if not is_c3:
+        nbytes = cnt["vertices"] * 32
+        pinned_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        ctypes.memmove(pinned_in.data_ptr(), L.scene_c4_host_data(), nbytes)
+        vbo = L.scene_c4_vbo()
+        h2d = nbytes
+    d2h = (y1 - y0) * w * 4
+
+    def e2e_step():
+        if not is_c3:
+            L.glBindBuffer(GL_ARRAY_BUFFER, vbo)
+            L.glBufferData(GL_ARRAY_BUFFER, nbytes, pinned_in.data_ptr(), GL_STATIC_DRAW)
+        frame()
+        if pinned_out is not None:      # glFinish + read this rank's colour rows into pinned host memory
+            base = pinned_out.data_ptr() - y0 * w * 4
+            assert L.mtgl_dev_read_framebuffer(dev, y0, y1, base, None, None) == 0
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        tt = torch.tensor([e2e_s], device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = cnt["covered"] * args.steps / e2e_s
+
+    # ---- CPU baseline on this box (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            a2 = argparse.Namespace(**vars(args)); a2.steps = 2 if not is_c3 else 1; a2.warmup = 1 if not is_c3 else 0
+            cpu = run_reference(a2, workload)["cpu_baseline"]
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": "fragments/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    lib.destroy()
+    if dist:
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+
+    ms_per_step = elapsed_ms / args.steps
+    value = cnt["covered"] * args.steps / (elapsed_ms * 1e-3)
+    bw, bw_src = peaks()
+    px = w * h
+    if is_c3:       # stencil R+W on every covered fragment, blend read + colour write on shaded ones; clear colour+stencil
+        frag_bytes = cnt["covered"] * 2 + cnt["shaded"] * 8
+        clear_bytes = px * (4 + 1)
+        vertex_bytes = 0
+    else:           # depth read on every covered fragment, depth + colour write on passing ones; clear colour+depth
+        frag_bytes = cnt["covered"] * 4 + cnt["tested"] * 8
+        clear_bytes = px * (4 + 4)
+        vertex_bytes = cnt["vertices"] * 32
+    raster_ms = stage[4] / args.steps
+    raster_bytes = (frag_bytes + clear_bytes) / world          # one launch per rank covers 1/N of the frame
+    achieved = raster_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+    frame_bytes = frag_bytes + clear_bytes + vertex_bytes
+    out = {
+        "metric": "covered_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_s": 1e3 / ms_per_step, "triangles_per_s": cnt["vertices"] / 3 * 1e3 / ms_per_step,
+        "config": {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3,
+                   "covered_fragments": cnt["covered"], "depth_passing_fragments": cnt["tested"], "shaded_fragments": cnt["shaded"],
+                   "partition": f"sort-first bands x{world}",
+                   "l2": "flushed between frames (256 MiB fill)" if is_c3 else "inputs larger than L2 (>330 MB streamed per frame)"},
+        "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3 / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "k_raster", "bound": "hbm", "achieved": achieved, "peak": bw, "unit": "GB/s",
+                     "frac": achieved / bw, "traffic": None, "peak_source": bw_src,
+                     "algorithmic_bytes_per_launch": raster_bytes, "kernel_ms": raster_ms,
+                     "frame_bytes": frame_bytes, "frame_frac": frame_bytes / (bw * 1e9) / (ms_per_step * 1e-3)},
+        "stages_ms": {k: float(v / args.steps) for k, v in zip(["vertex", "setup", "bin_count_scan", "bin_fill", "raster"], stage)},
+        "batch_ms": batch_ms / args.steps, "wall_ms_per_step": wall_s * 1e3 / args.steps,
+        "cpu_baseline": cpu,
+    }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args, args.workload)), flush=True)
+        return
+    out = run_b200(args, args.workload)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -217,8 +217,9 @@ typedef struct mtgl_dev_stats {
     uint64_t triangles_setup;   /* sub-triangles that survived clip / cull / degenerate tests */
     uint64_t tile_refs;         /* (sub-triangle, tile) pairs binned */
     uint64_t kernel_launches;   /* CUDA kernels launched by this library since creation */
-    float    last_batch_ms;     /* CUDA-event time of the last batch (all kernels) */
-    float    pad_;
+    float    last_batch_ms;     /* CUDA-event time of the last batch (upload + all kernels) */
+    float    stage_ms[5];       /* CUDA-event time per stage of the last batch, summed over passes:
+                                   0 vertex (K1), 1 set-up (K2), 2 bin count + scan, 3 bin fill, 4 tile raster (K4/K5) */
 } mtgl_dev_stats;
 
 typedef struct mtgl_dev mtgl_dev;
@@ -239,6 +240,8 @@ int mtgl_dev_set_band(mtgl_dev *dev, int32_t y0, int32_t y1);
 int mtgl_dev_buffer_data(mtgl_dev *dev, uint32_t id, uint64_t size, const void *data);
 int mtgl_dev_buffer_sub_data(mtgl_dev *dev, uint32_t id, uint64_t offset, uint64_t size, const void *data);
 int mtgl_dev_buffer_delete(mtgl_dev *dev, uint32_t id);
+/* read back part of a buffer-object mirror (the front end keeps no host copy of large buffers) */
+int mtgl_dev_buffer_read(mtgl_dev *dev, uint32_t id, uint64_t offset, uint64_t size, void *out);
 
 /* texture_upload_* (textures.c:141-269) after conversion to RGBA8 words (a<<24|b<<16|g<<8|r);
  * also builds mip level 1 the way texture_generate_mip1 does (textures.c:311-354). */
@@ -265,6 +268,11 @@ int mtgl_dev_write_framebuffer(mtgl_dev *dev, int32_t y0, int32_t y1,
 int mtgl_dev_plane_pointers(mtgl_dev *dev, void **color, void **depth, void **stencil);
 
 int mtgl_dev_get_stats(mtgl_dev *dev, mtgl_dev_stats *out);
+
+/* Device-side stopwatch on the context's stream: mark(0) ... mark(1), then elapsed = CUDA-event time
+ * between the two marks (waits for mark 1).  Used by bench.py to time K steps on the device. */
+int mtgl_dev_timer_mark(mtgl_dev *dev, int which);
+int mtgl_dev_timer_elapsed_ms(mtgl_dev *dev, float *ms);
 const char *mtgl_dev_last_error(mtgl_dev *dev);
 int mtgl_dev_abi_version(void);
 

@@ -62,6 +62,9 @@ struct mtgl_dev {
     int pinned_next = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
+    std::vector<cudaEvent_t> stage_ev;      /* 6 per pass of the last batch: K1 | K2 | count+scan | fill | raster */
+    size_t stage_passes = 0;
+    cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
     mtgl_dev_stats stats{};
     char err[256] = { 0 };
@@ -213,6 +216,7 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&d->pinned_ev[i], cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_start);
     if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_stop);
+    for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreate(&d->mark_ev[i]);
     if (ce != cudaSuccess) {
         mtgl_dev_destroy(d);
         return ce == cudaErrorMemoryAllocation ? MTGL_E_OOM : MTGL_E_CUDA;
@@ -247,6 +251,8 @@ void mtgl_dev_destroy(mtgl_dev *d)
     }
     if (d->ev_start) cudaEventDestroy(d->ev_start);
     if (d->ev_stop) cudaEventDestroy(d->ev_stop);
+    for (cudaEvent_t e : d->stage_ev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) if (d->mark_ev[i]) cudaEventDestroy(d->mark_ev[i]);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -302,6 +308,19 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
         CU(cudaFree(b.ptr));
     }
     b.ptr = nullptr; b.size = 0;
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_read(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, void *out)
+{
+    if (!d || id == 0 || id >= kMaxObjects || !out) return MTGL_E_INVALID;
+    BufObj &b = d->buf[id];
+    if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    if (size) {
+        CU(cudaMemcpyAsync(out, b.ptr + offset, size, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+    }
     return MTGL_OK;
 }
 
@@ -467,6 +486,12 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     CU(cudaEventRecord(d->ev_start, d->stream));
     d->timed = true;
     uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0;
+    while (d->stage_ev.size() < passes.size() * 6) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        d->stage_ev.push_back(e);
+    }
+    d->stage_passes = passes.size();
 
     for (size_t pidx = 0; pidx < passes.size(); pidx++) {
         const PassInfo &pi = infos[pidx];
@@ -483,6 +508,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         b.unorm8 = d->unorm8;
         b.counters = d->counters;
 
+        cudaEvent_t *sev = &d->stage_ev[pidx * 6];
+        CU(cudaEventRecord(sev[0], d->stream));
         ClearOp clr;
         std::memset(&clr, 0, sizeof clr);
         if (pidx == 0 && bt->clear_mask) {
@@ -513,9 +540,12 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             CU(cudaMemsetAsync(d->counters, 0, sizeof(DevCounters), d->stream));
             CU(cudaMemsetAsync(b.tile_count, 0, (size_t)ntiles * 4, d->stream));
             launch_vertex_stage(b, d->stream);
+            CU(cudaEventRecord(sev[1], d->stream));
             launch_setup(b, fb, d->stream);
+            CU(cudaEventRecord(sev[2], d->stream));
             launch_bin_count(b, fb, d->stream);
             launch_bin_scan(b, fb, d->stream);
+            CU(cudaEventRecord(sev[3], d->stream));
             /* the list length is only known on the device: one small read-back sizes the list buffer */
             CU(cudaMemcpyAsync(d->h_counters, d->counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, d->stream));
             CU(cudaStreamSynchronize(d->stream));
@@ -526,8 +556,14 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.list_capacity = (uint32_t)(d->tile_list.cap / 4);
             if (refs) launch_bin_fill(b, fb, d->stream);
             tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += refs;
+        } else {
+            CU(cudaEventRecord(sev[1], d->stream));
+            CU(cudaEventRecord(sev[2], d->stream));
+            CU(cudaEventRecord(sev[3], d->stream));
         }
+        CU(cudaEventRecord(sev[4], d->stream));
         launch_raster(b, fb, clr, planes, d->stream);
+        CU(cudaEventRecord(sev[5], d->stream));
     }
     CU(cudaEventRecord(d->ev_stop, d->stream));
     CU(cudaGetLastError());
@@ -587,9 +623,32 @@ int mtgl_dev_get_stats(mtgl_dev *d, mtgl_dev_stats *out)
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, d->ev_start, d->ev_stop));
         d->stats.last_batch_ms = ms;
+        for (int k = 0; k < 5; k++) d->stats.stage_ms[k] = 0.0f;
+        for (size_t p = 0; p < d->stage_passes; p++)
+            for (int k = 0; k < 5; k++) {
+                CU(cudaEventElapsedTime(&ms, d->stage_ev[p * 6 + k], d->stage_ev[p * 6 + k + 1]));
+                d->stats.stage_ms[k] += ms;
+            }
     }
     d->stats.kernel_launches = kernel_launch_count();
     *out = d->stats;
+    return MTGL_OK;
+}
+
+int mtgl_dev_timer_mark(mtgl_dev *d, int which)
+{
+    if (!d || which < 0 || which > 1) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    CU(cudaEventRecord(d->mark_ev[which], d->stream));
+    return MTGL_OK;
+}
+
+int mtgl_dev_timer_elapsed_ms(mtgl_dev *d, float *ms)
+{
+    if (!d || !ms) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    CU(cudaEventSynchronize(d->mark_ev[1]));
+    CU(cudaEventElapsedTime(ms, d->mark_ev[0], d->mark_ev[1]));
     return MTGL_OK;
 }
 

@@ -32,6 +32,10 @@ GLint *current_depth(GLState *c);
 Texture *get_texture(GLState *c, GLuint id);
 Buffer *get_buffer(GLState *c, GLuint id);
 DisplayList *get_list(GLState *c, GLuint id);
+/* host view of a buffer object: materialises the mirror of an HBM-only buffer on demand */
+const uint8_t *buffer_host_data(GLState *c, GLuint id);
+/* copy n bytes at 'offset' out of a buffer object (small device read-back when there is no host mirror) */
+bool buffer_read(GLState *c, GLuint id, uint64_t offset, uint64_t n, void *out);
 
 uint32_t pack_rgba(Rgba c);                                   /* graphics.h:337-348 */
 inline Rgba rgba(float r, float g, float b, float a) { Rgba c = { r, g, b, a }; return c; }

@@ -454,15 +454,27 @@ void glBufferData(GLenum target, GLsizeiptr size, const GLvoid *data, GLenum usa
     flush_batch(c);                           /* queued draws read the previous contents */
     b->usage = usage;
     if (size <= 0) {                          /* vbo.c:126-134 */
-        b->data.clear(); b->has_data = false;
+        b->data.clear(); b->data.shrink_to_fit();
+        b->has_data = false; b->host_valid = false; b->size = 0;
         mtgl_dev_buffer_data(c->dev, id, 0, nullptr);
         return;
     }
-    b->data.resize((size_t)size);             /* fresh storage; contents undefined when data == NULL */
+    /* fresh storage; contents undefined when data == NULL.  The HBM mirror is filled straight from the
+     * caller's memory (a pinned pointer is DMA'd without a bounce); only small buffers also keep a host copy. */
     b->has_data = true;
-    if (data) std::memcpy(b->data.data(), data, (size_t)size);
-    if (mtgl_dev_buffer_data(c->dev, id, (uint64_t)size, data ? b->data.data() : nullptr) != MTGL_OK)
+    b->size = (uint64_t)size;
+    if ((uint64_t)size <= kHostMirrorLimit) {
+        b->data.resize((size_t)size);
+        if (data) std::memcpy(b->data.data(), data, (size_t)size);
+        b->host_valid = true;
+    } else {
+        b->data.clear(); b->data.shrink_to_fit();
+        b->host_valid = false;
+    }
+    if (mtgl_dev_buffer_data(c->dev, id, (uint64_t)size, data) != MTGL_OK) {
         set_error(c, GL_OUT_OF_MEMORY);
+        b->has_data = false; b->host_valid = false; b->size = 0;
+    }
 }
 
 void glBufferSubData(GLenum target, GLintptr offset, GLsizeiptr size, const GLvoid *data)
@@ -474,9 +486,9 @@ void glBufferSubData(GLenum target, GLintptr offset, GLsizeiptr size, const GLvo
     if (!ok) { set_error(c, GL_INVALID_ENUM); return; }
     Buffer *b = get_buffer(c, id);
     if (!b) { set_error(c, GL_INVALID_OPERATION); return; }
-    if (!b->has_data || !data || (size_t)offset + (size_t)size > b->data.size()) { set_error(c, GL_INVALID_VALUE); return; }
+    if (!b->has_data || !data || (uint64_t)offset + (uint64_t)size > b->size) { set_error(c, GL_INVALID_VALUE); return; }
     flush_batch(c);
-    std::memcpy(b->data.data() + offset, data, (size_t)size);
+    if (b->host_valid) std::memcpy(b->data.data() + offset, data, (size_t)size);
     if (mtgl_dev_buffer_sub_data(c->dev, id, (uint64_t)offset, (uint64_t)size, data) != MTGL_OK)
         set_error(c, GL_INVALID_VALUE);
 }

@@ -133,6 +133,26 @@ Buffer *get_buffer(GLState *c, GLuint id)
     return b->allocated ? b : nullptr;
 }
 
+const uint8_t *buffer_host_data(GLState *c, GLuint id)
+{
+    Buffer *b = get_buffer(c, id);
+    if (!b || !b->has_data) return nullptr;
+    if (!b->host_valid) {
+        b->data.resize((size_t)b->size);
+        if (mtgl_dev_buffer_read(c->dev, id, 0, b->size, b->data.data()) != MTGL_OK) return nullptr;
+        b->host_valid = true;
+    }
+    return b->data.data();
+}
+
+bool buffer_read(GLState *c, GLuint id, uint64_t offset, uint64_t n, void *out)
+{
+    Buffer *b = get_buffer(c, id);
+    if (!b || !b->has_data || offset + n > b->size) return false;
+    if (b->host_valid) { std::memcpy(out, b->data.data() + offset, (size_t)n); return true; }
+    return mtgl_dev_buffer_read(c->dev, id, offset, n, out) == MTGL_OK;
+}
+
 DisplayList *get_list(GLState *c, GLuint id)
 {
     if (id == 0 || id > c->lists.size()) return nullptr;
@@ -599,9 +619,8 @@ void glNormal3f(GLfloat nx, GLfloat ny, GLfloat nz)
 static const uint8_t *array_base(GLState *c, const ArrayPointer &a) /* get_array_pointer, gl_api.c:1745-1755 */
 {
     if (c->bound_array_buffer) {
-        Buffer *b = get_buffer(c, c->bound_array_buffer);
-        if (b && b->has_data) return b->data.data() + (size_t)a.pointer;
-        return nullptr;
+        const uint8_t *base = buffer_host_data(c, c->bound_array_buffer);
+        return base ? base + (size_t)a.pointer : nullptr;
     }
     return (const uint8_t *)a.pointer;
 }
@@ -668,14 +687,16 @@ static void describe_attrib(GLState *c, const ArrayPointer &a, bool enabled, mtg
 }
 
 /* host-side read of one element with a bounds check (the device does the same check) */
-static bool host_element(const Buffer *b, const ArrayPointer &a, GLint idx, float *out, int want)
+static bool host_element(GLState *c, GLuint buffer, const ArrayPointer &a, GLint idx, float *out, int want)
 {
     GLsizei stride = resolved_stride(a);
     if (idx < 0 || stride <= 0) return false;
     size_t comp = (a.type == GL_FLOAT) ? 4 : 1;
-    size_t off = (size_t)a.pointer + (size_t)idx * (size_t)stride;
-    if (off + comp * (size_t)a.size > b->data.size()) return false;
-    array_element(a, b->data.data() + (size_t)a.pointer, idx, out, want);
+    uint64_t off = (uint64_t)(size_t)a.pointer + (uint64_t)idx * (uint64_t)stride;
+    uint8_t raw[16];
+    if (!buffer_read(c, buffer, off, comp * (size_t)a.size, raw)) return false;
+    ArrayPointer one = a;
+    array_element(one, raw, 0, out, want);
     return true;
 }
 
@@ -689,9 +710,15 @@ static void draw_arrays_common(GLState *c, GLenum mode, GLsizei count, GLint fir
     bool fast = vbuf && vbuf->has_data && !compiling(c) && !c->inside_begin_end && mode <= GL_POLYGON &&
                 c->staged.size() == c->prim_first && resolved_stride(c->vertex_pointer) > 0;
     if (!fast) {
+        if (indices_in_buffer) {
+            const uint8_t *ib = buffer_host_data(c, c->bound_element_buffer);
+            indices = ib ? ib + index_offset : nullptr;
+        }
+        if (index_type && !indices) return;
         draw_expanded(c, mode, count, first, index_type, indices);
         return;
     }
+    const GLuint vbo = c->bound_array_buffer;
     c->primitive_mode = mode;
     if (count == 0) return;
 
@@ -726,9 +753,16 @@ static void draw_arrays_common(GLState *c, GLenum mode, GLsizei count, GLint fir
 
     /* host-visible side effects of the per-element glColor4f/glTexCoord2f/glNormal3f calls:
      * the "current" attributes end up holding the last element's values (gl_api.c:1826-1842) */
-    GLint last = index_type ? (GLint)fetch_index(index_type, indices, count - 1) : first + (count - 1);
+    GLint last = first + (count - 1);
+    if (index_type) {
+        size_t isz = (index_type == GL_UNSIGNED_INT) ? 4 : (index_type == GL_UNSIGNED_SHORT ? 2 : 1);
+        uint32_t raw = 0;
+        if (indices_in_buffer) buffer_read(c, c->bound_element_buffer, index_offset + isz * (size_t)(count - 1), isz, &raw);
+        else std::memcpy(&raw, (const uint8_t *)indices + isz * (size_t)(count - 1), isz);
+        last = (GLint)raw;
+    }
     float tmp[4];
-    if (d.color.enabled && host_element(vbuf, c->color_pointer, last, tmp, 4)) {
+    if (d.color.enabled && host_element(c, vbo, c->color_pointer, last, tmp, 4)) {
         float r = tmp[0], g = tmp[1], b = tmp[2], a = tmp[3];
         if (!finite_f(r)) r = 0.0f;
         if (!finite_f(g)) g = 0.0f;
@@ -736,10 +770,10 @@ static void draw_arrays_common(GLState *c, GLenum mode, GLsizei count, GLint fir
         if (!finite_f(a)) a = 1.0f;
         c->current_color = rgba(sat(r), sat(g), sat(b), sat(a));
     }
-    if (d.texcoord.enabled && host_element(vbuf, c->texcoord_pointer, last, tmp, 2)) {
+    if (d.texcoord.enabled && host_element(c, vbo, c->texcoord_pointer, last, tmp, 2)) {
         c->current_texcoord[0] = tmp[0]; c->current_texcoord[1] = tmp[1];
     }
-    if (d.normal.enabled && host_element(vbuf, c->normal_pointer, last, tmp, 3)) {
+    if (d.normal.enabled && host_element(c, vbo, c->normal_pointer, last, tmp, 3)) {
         c->current_normal[0] = tmp[0]; c->current_normal[1] = tmp[1]; c->current_normal[2] = tmp[2];
     }
     apply_color_material(c, c->current_color);
@@ -753,7 +787,11 @@ void glDrawArrays(GLenum mode, GLint first, GLsizei count) /* gl_api.c:1799-1852
 {
     MTGL_CTX();
     if (count < 0) { set_error(c, GL_INVALID_VALUE); return; }
-    if (!(c->client_state & 1u) || !array_base(c, c->vertex_pointer)) return;
+    if (!(c->client_state & 1u)) return;
+    if (c->bound_array_buffer) {          /* get_array_pointer: a bound buffer without storage draws nothing */
+        Buffer *b = get_buffer(c, c->bound_array_buffer);
+        if (!b || !b->has_data) return;
+    } else if (!c->vertex_pointer.pointer) return;
     draw_arrays_common(c, mode, count, first, 0, nullptr, false, 0);
 }
 
@@ -765,7 +803,11 @@ void glDrawElements(GLenum mode, GLsizei count, GLenum type, const GLvoid *indic
         set_error(c, GL_INVALID_ENUM);
         return;
     }
-    const uint8_t *vb = array_base(c, c->vertex_pointer);
+    bool have_vertices;
+    if (c->bound_array_buffer) {
+        Buffer *b = get_buffer(c, c->bound_array_buffer);
+        have_vertices = b && b->has_data;
+    } else have_vertices = c->vertex_pointer.pointer != nullptr;
     const void *index_data = indices;
     bool in_buffer = false;
     uint64_t offset = 0;
@@ -773,11 +815,11 @@ void glDrawElements(GLenum mode, GLsizei count, GLenum type, const GLvoid *indic
         Buffer *b = get_buffer(c, c->bound_element_buffer);
         if (!b || !b->has_data) return;
         offset = (uint64_t)(uintptr_t)indices;
-        if (offset >= b->data.size()) { set_error(c, GL_INVALID_VALUE); return; }
-        index_data = b->data.data() + offset;
+        if (offset >= b->size) { set_error(c, GL_INVALID_VALUE); return; }
+        index_data = nullptr;               /* resolved lazily: the indices live in the element buffer */
         in_buffer = true;
     }
-    if (!(c->client_state & 1u) || !vb || !index_data) return;
+    if (!(c->client_state & 1u) || !have_vertices || (!in_buffer && !index_data)) return;
     draw_arrays_common(c, mode, count, 0, type, index_data, in_buffer, offset);
 }
 

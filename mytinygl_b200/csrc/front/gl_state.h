@@ -58,10 +58,14 @@ struct Texture {                        /* texture_t, textures.h:21-39 (level 1 
 
 struct Buffer {                         /* buffer_t, vbo.h */
     bool allocated = false;
+    bool has_data = false;              /* storage exists (glBufferData with size > 0) */
+    bool host_valid = false;            /* 'data' mirrors the contents; large buffers live in HBM only */
+    uint64_t size = 0;
     std::vector<uint8_t> data;
-    bool has_data = false;
     GLenum usage = 0;
 };
+
+constexpr uint64_t kHostMirrorLimit = 8u << 20;   /* buffers above this keep no host copy */
 
 enum ListOp : uint8_t {                 /* the 31 opcodes of lists.h:21-53 */
     OP_END, OP_BEGIN, OP_VERTEX, OP_COLOR, OP_TEXCOORD, OP_NORMAL, OP_TRANSLATE, OP_ROTATE, OP_SCALE,

@@ -81,6 +81,8 @@ struct mtgl_dev {
     otex tex[O_MAX_OBJECTS];
     obuf buf[O_MAX_OBJECTS];
     mtgl_dev_stats stats;
+    uint64_t frag_covered, frag_tested, frag_shaded;   /* cumulative: inside test / past stencil+depth / colour write */
+    double t_mark[2];
     char err[128];
 };
 
@@ -561,6 +563,7 @@ static void raster_triangle(mtgl_dev *dev, const mtgl_state *st, const overt *v0
             float e2 = edge_fn((float)x0, (float)y0, (float)x1, (float)y1, (float)x, (float)y);
             if (!((area > 0 && e0 >= 0 && e1 >= 0 && e2 >= 0) || (area < 0 && e0 <= 0 && e1 <= 0 && e2 <= 0))) continue;
 
+            dev->frag_covered++;
             float b0 = e0 * inv_area, b1 = e1 * inv_area, b2 = e2 * inv_area;
             float z = b0 * z0 + b1 * z1 + b2 * z2;
             float depth = (float)((z + 1.0f) * 0.5f * (st->depth_far - st->depth_near) + st->depth_near);
@@ -583,6 +586,7 @@ static void raster_triangle(mtgl_dev *dev, const mtgl_state *st, const overt *v0
                 }
             }
             if (stencil_on) put_stencil_masked(dev, st, idx, stencil_apply(st->stencil_zpass, sval, st->stencil_ref));
+            dev->frag_tested++;
 
             col4 c;
             if (st->shade_model == T_FLAT) c = v2->color;
@@ -655,6 +659,7 @@ static void raster_triangle(mtgl_dev *dev, const mtgl_state *st, const overt *v0
                 c = col_clamp(o);
             }
             c = col_clamp(c);
+            dev->frag_shaded++;
             put_color_masked(dev, st, x, y, c);
         }
     }
@@ -886,6 +891,14 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
     return MTGL_OK;
 }
 
+int mtgl_dev_buffer_read(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, void *out)
+{
+    if (!d || id == 0 || id >= O_MAX_OBJECTS || !d->buf[id].data || !out) return MTGL_E_INVALID;
+    if (offset + size > d->buf[id].size) return MTGL_E_INVALID;
+    memcpy(out, d->buf[id].data + offset, size);
+    return MTGL_OK;
+}
+
 int mtgl_dev_texture_image(mtgl_dev *d, uint32_t id, int32_t w, int32_t h, const uint32_t *rgba8)
 {
     if (!d || id == 0 || id >= O_MAX_OBJECTS || w <= 0 || h <= 0 || w > 2048 || h > 2048 || !rgba8) return MTGL_E_INVALID;
@@ -1018,6 +1031,35 @@ int mtgl_dev_get_stats(mtgl_dev *d, mtgl_dev_stats *out)
     if (!d || !out) return MTGL_E_INVALID;
     *out = d->stats;
     return MTGL_OK;
+}
+
+#include <time.h>
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+int mtgl_dev_timer_mark(mtgl_dev *d, int which)
+{
+    if (!d || which < 0 || which > 1) return MTGL_E_INVALID;
+    d->t_mark[which] = now_s();
+    return MTGL_OK;
+}
+
+int mtgl_dev_timer_elapsed_ms(mtgl_dev *d, float *ms)
+{
+    if (!d || !ms) return MTGL_E_INVALID;
+    *ms = (float)((d->t_mark[1] - d->t_mark[0]) * 1e3);
+    return MTGL_OK;
+}
+
+/* Oracle-only: exact fragment counters -- fragments passing the inclusive inside
+ * test, fragments past the stencil + depth tests, fragments reaching the colour write.  Cumulative. */
+void mtgl_oracle_fragment_counts(mtgl_dev *d, uint64_t out[3])
+{
+    out[0] = d->frag_covered; out[1] = d->frag_tested; out[2] = d->frag_shaded;
 }
 
 const char *mtgl_dev_last_error(mtgl_dev *d) { return d ? d->err : "no device"; }

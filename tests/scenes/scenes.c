@@ -417,6 +417,8 @@ static void scene_c4(int w, int h, int variant)
 }
 
 int scene_c4_vertex_count(void) { return g_c4.nverts; }
+const void *scene_c4_host_data(void) { return g_c4.host; }
+unsigned scene_c4_vbo(void) { return g_c4.vbo; }
 
 /* ---------------------------------------------------------------- testbed-derived feature scenes */
 
