@@ -31,6 +31,8 @@ namespace mtgl_dev_impl {
 
 void note_launch();
 
+constexpr int FRAG_QUEUE = 64;               /* per-warp deferred-shading queue (two batches of 32) */
+
 struct RasterSmem {
     uint32_t color[TILE_H * COLOR_PITCH];
     float depth[TILE_H * COLOR_PITCH];
@@ -39,74 +41,121 @@ struct RasterSmem {
     uint32_t rec[LIST_WINDOW];
     uint32_t box[LIST_WINDOW];
     float unorm8[256];
+    /* fragments that passed the stencil/depth tests and wait for shading: record, pixel, barycentrics */
+    uint32_t fq_rec[RASTER_THREADS / 32][FRAG_QUEUE];
+    uint32_t fq_pix[RASTER_THREADS / 32][FRAG_QUEUE];
+    float fq_b0[RASTER_THREADS / 32][FRAG_QUEUE];
+    float fq_b1[RASTER_THREADS / 32][FRAG_QUEUE];
+    float fq_b2[RASTER_THREADS / 32][FRAG_QUEUE];
     uint32_t count;
     uint32_t scratch[RASTER_THREADS / 32];
 };
 
-/* ---------------------------------------------------------------- texture sampling (textures.c) */
-__device__ __forceinline__ uint32_t texel_wrapped(const uint32_t *px, int w, int h, uint32_t ws, uint32_t wt, int x, int y)
+/* ---------------------------------------------------------------- texture sampling (textures.c)
+ * The sampler is split in two: tex_taps() resolves the filter, wraps the coordinates and fetches the (up to 8)
+ * texels once; tex_channel() then filters ONE 8-bit channel.  Every stage of the reference works per channel
+ * (bilinear_filter textures.c:294-307, the trilinear blend 512-515, all truncating to 8 bits), so evaluating
+ * alpha first and the colour channels only for fragments that survive the alpha test is bit-identical. */
+struct LevelTaps {
+    uint32_t t00, t10, t01, t11;
+    float fx, fy;
+    uint32_t mode;          /* 0 = single texel in t00, 1 = bilinear, 2 = opaque white (missing level 1) */
+};
+
+struct TexTaps {
+    LevelTaps a, b;
+    float cl;               /* trilinear weight min(lod, 1) */
+    bool tri;
+};
+
+__device__ __forceinline__ int wrap_coord(int x, int n, bool repeat)
 {   /* get_texel_wrapped / get_mip1_texel_wrapped, textures.c:272-291, 357-376 */
-    if (ws == G_REPEAT) x = ((x % w) + w) % w; else { if (x < 0) x = 0; else if (x >= w) x = w - 1; }
-    if (wt == G_REPEAT) y = ((y % h) + h) % h; else { if (y < 0) y = 0; else if (y >= h) y = h - 1; }
-    return __ldg(px + y * w + x);
+    if (repeat) {
+        if ((unsigned)(x + n) < (unsigned)(3 * n)) {            /* x in [-n, 2n): one conditional add == the euclidean modulo */
+            if (x < 0) x += n; else if (x >= n) x -= n;
+        } else x = ((x % n) + n) % n;
+    } else { if (x < 0) x = 0; else if (x >= n) x = n - 1; }
+    return x;
 }
 
-__device__ __forceinline__ uint32_t bilinear(uint32_t c00, uint32_t c10, uint32_t c01, uint32_t c11, float fx, float fy,
-                                             const float *un)
-{   /* bilinear_filter, textures.c:294-307: every stage result is truncated back to RGBA8 */
-    Color4 top = color_lerp(color_unpack(c00, un), color_unpack(c10, un), fx);
-    Color4 bot = color_lerp(color_unpack(c01, un), color_unpack(c11, un), fx);
-    return color_pack(color_lerp(top, bot, fy));
-}
-
-__device__ uint32_t sample_level(const uint32_t *px, int w, int h, uint32_t ws, uint32_t wt, float u, float v, bool linear,
-                                 const float *un)
+__device__ __forceinline__ void level_taps(LevelTaps &L, const uint32_t *px, int w, int h, bool rep_s, bool rep_t,
+                                           float u, float v, bool linear)
 {   /* texture_sample_base / _mip1 / tail of texture_sample_lod, textures.c:379-451, 524-556 */
     float tx = u * (float)w - 0.5f;
     float ty = v * (float)h - 0.5f;
     if (linear) {
         int x0 = f2i_x86(floorf(tx)), y0 = f2i_x86(floorf(ty));
-        float fx = tx - (float)x0, fy = ty - (float)y0;
-        return bilinear(texel_wrapped(px, w, h, ws, wt, x0, y0), texel_wrapped(px, w, h, ws, wt, x0 + 1, y0),
-                        texel_wrapped(px, w, h, ws, wt, x0, y0 + 1), texel_wrapped(px, w, h, ws, wt, x0 + 1, y0 + 1), fx, fy, un);
+        L.fx = tx - (float)x0; L.fy = ty - (float)y0;
+        int xa = wrap_coord(x0, w, rep_s), xb = wrap_coord(x0 + 1, w, rep_s);
+        int ya = wrap_coord(y0, h, rep_t), yb = wrap_coord(y0 + 1, h, rep_t);
+        L.t00 = __ldg(px + ya * w + xa); L.t10 = __ldg(px + ya * w + xb);
+        L.t01 = __ldg(px + yb * w + xa); L.t11 = __ldg(px + yb * w + xb);
+        L.mode = 1;
+    } else {
+        int x = f2i_x86(floorf(tx + 0.5f)), y = f2i_x86(floorf(ty + 0.5f));
+        if (x < 0) x = 0;
+        if (x >= w) x = w - 1;
+        if (y < 0) y = 0;
+        if (y >= h) y = h - 1;
+        L.t00 = __ldg(px + y * w + x);
+        L.mode = 0;
     }
-    int x = f2i_x86(floorf(tx + 0.5f)), y = f2i_x86(floorf(ty + 0.5f));
-    if (x < 0) x = 0;
-    if (x >= w) x = w - 1;
-    if (y < 0) y = 0;
-    if (y >= h) y = h - 1;
-    return __ldg(px + y * w + x);
 }
 
-__device__ __forceinline__ uint32_t sample_mip1(const RasterCfg *c, float u, float v, uint32_t filter, const float *un)
+__device__ __forceinline__ void mip1_taps(LevelTaps &L, const RasterCfg *c, float u, float v, uint32_t filter)
 {   /* texture_sample_mip1, textures.c:413-451: a level that cannot exist samples as opaque white */
-    if (!c->tex_l1) return 0xFFFFFFFFu;
+    if (!c->tex_l1) { L.mode = 2; return; }
     bool linear = (filter == G_LINEAR || filter == G_LINEAR_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_LINEAR);
-    return sample_level(c->tex_l1, c->tex_w1, c->tex_h1, c->tex_wrap_s, c->tex_wrap_t, u, v, linear, un);
+    level_taps(L, c->tex_l1, c->tex_w1, c->tex_h1, c->tex_wrap_s == G_REPEAT, c->tex_wrap_t == G_REPEAT, u, v, linear);
 }
 
-__device__ uint32_t sample_lod(const RasterCfg *c, float u, float v, float lod, const float *un)
+__device__ __forceinline__ void tex_taps(TexTaps &T, const RasterCfg *c, float u, float v, float lod)
 {   /* texture_sample_lod, textures.c:457-557 */
-    if (c->tex_wrap_s == G_REPEAT) { u = u - (float)f2i_x86(u); if (u < 0) u += 1.0f; }
+    const bool rep_s = c->tex_wrap_s == G_REPEAT, rep_t = c->tex_wrap_t == G_REPEAT;
+    if (rep_s) { u = u - (float)f2i_x86(u); if (u < 0) u += 1.0f; }
     else { if (u < 0.0f) u = 0.0f; if (u > 1.0f) u = 1.0f; }
-    if (c->tex_wrap_t == G_REPEAT) { v = v - (float)f2i_x86(v); if (v < 0) v += 1.0f; }
+    if (rep_t) { v = v - (float)f2i_x86(v); if (v < 0) v += 1.0f; }
     else { if (v < 0.0f) v = 0.0f; if (v > 1.0f) v = 1.0f; }
 
+    T.tri = false;
     uint32_t filter = (lod > 0.0f) ? c->tex_min : c->tex_mag;
     if (filter == G_NEAREST_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_NEAREST) {
-        if (lod >= 0.5f) return sample_mip1(c, u, v, filter, un);
+        if (lod >= 0.5f) { mip1_taps(T.a, c, u, v, filter); return; }
         filter = (filter == G_NEAREST_MIPMAP_NEAREST) ? G_NEAREST : G_LINEAR;
     } else if (filter == G_NEAREST_MIPMAP_LINEAR || filter == G_LINEAR_MIPMAP_LINEAR) {
         if (lod > 0.0f) {
-            float cl = (lod > 1.0f) ? 1.0f : lod;
-            bool base_linear = (filter != G_NEAREST_MIPMAP_LINEAR);
-            uint32_t c0 = sample_level(c->tex_l0, c->tex_w, c->tex_h, c->tex_wrap_s, c->tex_wrap_t, u, v, base_linear, un);
-            uint32_t c1 = sample_mip1(c, u, v, filter, un);
-            return color_pack(color_lerp(color_unpack(c0, un), color_unpack(c1, un), cl));
+            T.cl = (lod > 1.0f) ? 1.0f : lod;
+            T.tri = true;
+            level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter != G_NEAREST_MIPMAP_LINEAR);
+            mip1_taps(T.b, c, u, v, filter);
+            return;
         }
         filter = (filter == G_NEAREST_MIPMAP_LINEAR) ? G_NEAREST : G_LINEAR;
     }
-    return sample_level(c->tex_l0, c->tex_w, c->tex_h, c->tex_wrap_s, c->tex_wrap_t, u, v, filter == G_LINEAR, un);
+    level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter == G_LINEAR);
+}
+
+__device__ __forceinline__ uint32_t pack1(float x) { return __float2uint_rz(sat01(x) * 255.0f) & 0xFFu; }   /* one channel of color_to_rgba32 */
+
+__device__ __forceinline__ uint32_t level_channel(const LevelTaps &L, int sh, const float *un)
+{   /* bilinear_filter, textures.c:294-307: lerp horizontally, then vertically, truncate to 8 bits */
+    if (L.mode == 0) return (L.t00 >> sh) & 0xFFu;
+    if (L.mode == 2) return 0xFFu;
+    float c00 = un[(L.t00 >> sh) & 0xFFu], c10 = un[(L.t10 >> sh) & 0xFFu];
+    float c01 = un[(L.t01 >> sh) & 0xFFu], c11 = un[(L.t11 >> sh) & 0xFFu];
+    float sx = 1.0f - L.fx, sy = 1.0f - L.fy;
+    float top = c00 * sx + c10 * L.fx;
+    float bot = c01 * sx + c11 * L.fx;
+    return pack1(top * sy + bot * L.fy);
+}
+
+__device__ __forceinline__ float tex_channel(const TexTaps &T, int sh, const float *un)
+{   /* one channel of color_from_rgba32(texture_sample_lod(...)) */
+    uint32_t v0 = level_channel(T.a, sh, un);
+    if (!T.tri) return un[v0];
+    uint32_t v1 = level_channel(T.b, sh, un);
+    float s = 1.0f - T.cl;
+    return un[pack1(un[v0] * s + un[v1] * T.cl)];      /* textures.c:512-515 */
 }
 
 /* ---------------------------------------------------------------- per-fragment helpers */
@@ -161,40 +210,196 @@ __device__ __forceinline__ float edge_at(float ax, float ay, float bx, float by,
     return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
 }
 
+/* the interpolants of one record (rows 3-9), loaded uniformly per triangle or per lane when shading is deferred */
+struct TriAttr {
+    float4 col0, col1, col2;
+    float u0, v0, u1, v1, u2, v2;
+    float w0, w1, w2;
+    float ez0, ez1, ez2;
+    float lod;
+};
+
+__device__ __forceinline__ void load_attr(TriAttr &A, const TriRecord *rec)
+{
+    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
+    const float4 row4 = __ldg(reinterpret_cast<const float4 *>(rec) + 4);
+    A.col0 = __ldg(reinterpret_cast<const float4 *>(rec) + 5);
+    A.col1 = __ldg(reinterpret_cast<const float4 *>(rec) + 6);
+    A.col2 = __ldg(reinterpret_cast<const float4 *>(rec) + 7);
+    const float4 row8 = __ldg(reinterpret_cast<const float4 *>(rec) + 8);
+    const float4 row9 = __ldg(reinterpret_cast<const float4 *>(rec) + 9);
+    A.lod = row3.w;
+    A.w0 = row4.x; A.w1 = row4.y; A.w2 = row4.z; A.ez0 = row4.w;
+    A.u0 = row8.x; A.v0 = row8.y; A.u1 = row8.z; A.v1 = row8.w;
+    A.u2 = row9.x; A.v2 = row9.y; A.ez1 = row9.z; A.ez2 = row9.w;
+}
+
+/* Colour of one fragment: interpolation, per-fragment lighting, texturing, alpha test, texenv, fog
+ * (raster.c:581-705).  Returns false when the alpha test discards the fragment. */
+__device__ __forceinline__ bool shade_color(const BatchDev &b, const float *un, uint32_t r, uint32_t state_flags,
+                                            const TriAttr &A, const RasterCfg *cfg, float b0, float b1, float b2, Color4 &c)
+{
+    const uint32_t flags = cfg->flags;
+    if (flags & RC_FLAT) c = { A.col2.x, A.col2.y, A.col2.z, A.col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
+    else {
+        c.r = A.col0.x * b0 + A.col1.x * b1 + A.col2.x * b2;
+        c.g = A.col0.y * b0 + A.col1.y * b1 + A.col2.y * b2;
+        c.b = A.col0.z * b0 + A.col1.z * b1 + A.col2.z * b2;
+        c.a = A.col0.w * b0 + A.col1.w * b1 + A.col2.w * b2;
+    }
+
+    if (flags & RC_LIGHTING) {                              /* raster.c:592-615 */
+        const bool back_facing = (state_flags >> 31) != 0;
+        const bool flip = back_facing && (flags & RC_TWO_SIDE);
+        if ((flags & RC_PHONG) || flip) {
+            const TriEye *eye = b.rec_eye + r;
+            float ep[3], en[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                ep[k] = eye->ep0[k] * b0 + eye->ep1[k] * b1 + eye->ep2[k] * b2;
+                en[k] = eye->en0[k] * b0 + eye->en1[k] * b1 + eye->en2[k] * b2;
+            }
+            const mtgl_state *st = b.states + (state_flags & 0x7FFFFFFFu);
+            MaterialRegs mat;
+            if (flip) {
+                en[0] *= -1.0f; en[1] *= -1.0f; en[2] *= -1.0f;
+                load_material(mat, &st->material_back);
+            } else load_material(mat, &st->material_front);
+            c = compute_lighting(st, ep[0], ep[1], ep[2], en[0], en[1], en[2], mat);
+        }
+    }
+
+    if (flags & RC_TEXTURED) {                              /* raster.c:618-669 */
+        float u, v;
+        if (flags & RC_PERSPECTIVE) {
+            /* u/w, v/w per vertex (raster.c:501-503) */
+            const float u0w = A.u0 * A.w0, v0w = A.v0 * A.w0, u1w = A.u1 * A.w1, v1w = A.v1 * A.w1, u2w = A.u2 * A.w2, v2w = A.v2 * A.w2;
+            float uw = b0 * u0w + b1 * u1w + b2 * u2w;
+            float vw = b0 * v0w + b1 * v1w + b2 * v2w;
+            float ow = b0 * A.w0 + b1 * A.w1 + b2 * A.w2;
+            float w = 1.0f / ow;
+            u = uw * w;
+            v = vw * w;
+        } else {
+            u = b0 * A.u0 + b1 * A.u1 + b2 * A.u2;
+            v = b0 * A.v0 + b1 * A.v1 + b2 * A.v2;
+        }
+        TexTaps T;
+        tex_taps(T, cfg, u, v, A.lod);
+        Color4 t;
+        t.a = tex_channel(T, 24, un);
+        /* alpha test exists only here and tests the TEXEL alpha (raster.c:640-643) */
+        if ((flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, t.a, cfg->alpha_ref)) return false;
+        t.r = tex_channel(T, 0, un); t.g = tex_channel(T, 8, un); t.b = tex_channel(T, 16, un);
+        switch (cfg->tex_env_mode) {
+        case G_REPLACE: c = t; break;
+        case G_DECAL: c = color_lerp_rgb(c, t, t.a); break;
+        case G_BLEND: {
+            const float *e = cfg->tex_env_color;
+            c = { c.r * (1.0f - t.r) + e[0] * t.r, c.g * (1.0f - t.g) + e[1] * t.g, c.b * (1.0f - t.b) + e[2] * t.b, c.a * t.a };
+            break;
+        }
+        case G_ADD: c = { c.r + t.r, c.g + t.g, c.b + t.b, c.a * t.a }; break;
+        default: c = { c.r * t.r, c.g * t.g, c.b * t.b, c.a * t.a }; break;
+        }
+    }
+
+    if (flags & RC_FOG) {                                   /* raster.c:672-705; result alpha = fog colour alpha */
+        float fc = b0 * A.ez0 + b1 * A.ez1 + b2 * A.ez2;
+        Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
+        c = color_lerp_rgb(fogc, c, fog_factor(cfg, fc));
+    }
+    return true;
+}
+
+/* Shade up to 32 queued fragments, one per lane (lane < n).  Only fragments whose state neither blends nor
+ * alpha-tests nor masks colour channels are queued, so the last fragment of a pixel in submission order wins:
+ * inside a batch that is the highest lane addressing the pixel. */
+__device__ __noinline__ void drain_queue(const BatchDev &b, RasterSmem &sm, uint32_t warp, uint32_t lane, uint32_t &qhead, uint32_t &qcount)
+{
+    const uint32_t n = min(qcount, 32u);
+    const bool valid = lane < n;
+    uint32_t pix = 0;
+    Color4 c = { 0.0f, 0.0f, 0.0f, 0.0f };
+    if (valid) {
+        const uint32_t e = (qhead + lane) & (FRAG_QUEUE - 1);
+        const uint32_t r = sm.fq_rec[warp][e];
+        pix = sm.fq_pix[warp][e];
+        const float b0 = sm.fq_b0[warp][e], b1 = sm.fq_b1[warp][e], b2 = sm.fq_b2[warp][e];
+        const TriRecord *rec = b.records + r;
+        const uint32_t state_flags = __ldg(&rec->state_flags);
+        const RasterCfg *cfg = b.cfgs + (state_flags & 0x7FFFFFFFu);
+        TriAttr A;
+        load_attr(A, rec);
+        shade_color(b, sm.unorm8, r, state_flags, A, cfg, b0, b1, b2, c);
+    }
+    const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+    if (valid) {
+        const uint32_t peers = __match_any_sync(vmask, pix);
+        if ((peers >> lane) == 1u) sm.color[pix] = color_pack(color_clamp(c));      /* raster.c:719-721 */
+    }
+    qhead = (qhead + n) & (FRAG_QUEUE - 1);
+    qcount -= n;
+    __syncwarp();
+}
+
+/* Immediate (in-order) shading of one fragment for states that blend, alpha-test or mask channels:
+ * colour, then the late depth write (raster.c:707-710), blending and the masked write (712-721). */
+__device__ __noinline__ void shade_now(const BatchDev &b, RasterSmem &sm, uint32_t r, uint32_t state_flags, const RasterCfg *cfg,
+                                       float b0, float b1, float b2, int ci, float depth, bool depth_write)
+{
+    const float *un = sm.unorm8;
+    const uint32_t flags = cfg->flags, cm = cfg->color_mask;
+    TriAttr A;
+    load_attr(A, b.records + r);
+    Color4 c;
+    if (!shade_color(b, un, r, state_flags, A, cfg, b0, b1, b2, c)) return;
+    if (depth_write) sm.depth[ci] = depth;
+    if (flags & RC_BLEND) {                     /* raster.c:712-717 */
+        Color4 d = color_unpack(sm.color[ci], un);
+        Color4 sf = blend_factor(cfg->blend_src, c, d), df = blend_factor(cfg->blend_dst, c, d);
+        c = color_clamp({ c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a });
+    }
+    c = color_clamp(c);
+    if (cm == 0xFu) sm.color[ci] = color_pack(c);       /* write_pixel_masked, raster.c:20-45 */
+    else if (cm != 0u) {
+        Color4 d = color_unpack(sm.color[ci], un);
+        if (cm & 1u) d.r = c.r;
+        if (cm & 2u) d.g = c.g;
+        if (cm & 4u) d.b = c.b;
+        if (cm & 8u) d.a = c.a;
+        sm.color[ci] = color_pack(d);
+    }
+}
+
 /* ---------------------------------------------------------------- one triangle over one warp region */
 __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, int tile_px, int tile_py,
-                                int X0, int Y0, int X1, int Y1)
+                                int X0, int Y0, int X1, int Y1, uint32_t &qhead, uint32_t &qcount)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TriRecord *rec = b.records + r;
     const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
     const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
     const uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(rec) + 2);
     const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
-    const float4 row4 = __ldg(reinterpret_cast<const float4 *>(rec) + 4);
-    const float4 col0 = __ldg(reinterpret_cast<const float4 *>(rec) + 5);
-    const float4 col1 = __ldg(reinterpret_cast<const float4 *>(rec) + 6);
-    const float4 col2 = __ldg(reinterpret_cast<const float4 *>(rec) + 7);
-    const float4 row8 = __ldg(reinterpret_cast<const float4 *>(rec) + 8);
-    const float4 row9 = __ldg(reinterpret_cast<const float4 *>(rec) + 9);
 
     const float fx0 = (float)row0.x, fy0 = (float)row0.y, fx1 = (float)row0.z, fy1 = (float)row0.w;
     const float fx2 = (float)row1.x, fy2 = (float)row1.y;
     const float area = __int_as_float(row1.z), inv_area = __int_as_float(row1.w);
-    const uint32_t state_index = row2.z & 0x7FFFFFFFu;
-    const bool back_facing = (row2.z >> 31) != 0;
-    const RasterCfg *cfg = b.cfgs + state_index;
+    const uint32_t state_flags = row2.z;
+    const RasterCfg *cfg = b.cfgs + (state_flags & 0x7FFFFFFFu);
     const uint32_t flags = cfg->flags;
-    const float z0 = row3.x, z1 = row3.y, z2 = row3.z, lod = row3.w;
-    const float w0 = row4.x, w1 = row4.y, w2 = row4.z;
-    const float ez0 = row4.w, ez1 = row9.z, ez2 = row9.w;
-    const float u0 = row8.x, v0 = row8.y, u1 = row8.z, v1 = row8.w, u2 = row9.x, v2 = row9.y;
-    /* u/w, v/w per vertex (raster.c:501-503) */
-    const float u0w = u0 * w0, v0w = v0 * w0, u1w = u1 * w1, v1w = v1 * w1, u2w = u2 * w2, v2w = v2 * w2;
+    const float z0 = row3.x, z1 = row3.y, z2 = row3.z;
     const bool area_pos = area > 0;
-    const float *un = sm.unorm8;
+    const uint32_t cm = cfg->color_mask;
+    /* shading can be deferred (and compacted across triangles) when nothing between the depth test and the
+     * colour write depends on or discards per fragment state: no blending, no alpha test, full colour mask */
+    const bool defer = !(flags & RC_BLEND) && !((flags & RC_ALPHA_TEST) && (flags & RC_TEXTURED)) && cm == 0xFu;
 
-    const bool relight = (flags & RC_LIGHTING) && ((flags & RC_PHONG) || (back_facing && (flags & RC_TWO_SIDE)));
+    if (!defer) {       /* queued colour writes of earlier triangles must land before an in-order triangle reads them */
+        while (qcount) drain_queue(b, sm, warp, lane, qhead, qcount);
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int by = Y0; by <= Y1; by += 4) {
         for (int bx = X0; bx <= X1; bx += 8) {
@@ -206,119 +411,50 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, i
             const float e2 = edge_at(fx0, fy0, fx1, fy1, px, py);
             /* inclusive on all three edges, no fill rule (raster.c:539-540) */
             active = active && (area_pos ? (e0 >= 0 && e1 >= 0 && e2 >= 0) : (e0 <= 0 && e1 <= 0 && e2 <= 0));
-            if (!active) continue;
 
             const float b0 = e0 * inv_area, b1 = e1 * inv_area, b2 = e2 * inv_area;
-            const float z = b0 * z0 + b1 * z1 + b2 * z2;
-            float depth;
-            if (flags & RC_DEPTH_RANGE_01) depth = (z + 1.0f) * 0.5f;
-            else depth = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
-
             const int ci = y * COLOR_PITCH + x;
-            const int si = y * STENCIL_PITCH + x;
+            float depth = 0.0f;
+            if (active) {
+                const float z = b0 * z0 + b1 * z1 + b2 * z2;
+                if (flags & RC_DEPTH_RANGE_01) depth = (z + 1.0f) * 0.5f;
+                else depth = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
 
-            uint8_t sval = 0;
-            if (flags & RC_STENCIL) {                       /* raster.c:550-579 */
-                sval = sm.stencil[si];
-                const int32_t mref = (int32_t)((uint32_t)cfg->stencil_ref & cfg->stencil_mask);
-                const int32_t mval = (int32_t)((uint32_t)sval & cfg->stencil_mask);
-                const uint8_t wm = (uint8_t)(cfg->stencil_writemask & 0xFF);
-                if (!compare_i(cfg->stencil_func, mref, mval)) {
-                    uint8_t nv = stencil_apply(cfg->stencil_fail, sval, cfg->stencil_ref);
+                if (flags & RC_STENCIL) {                       /* raster.c:550-579 */
+                    const int si = y * STENCIL_PITCH + x;
+                    const uint8_t sval = sm.stencil[si];
+                    const int32_t mref = (int32_t)((uint32_t)cfg->stencil_ref & cfg->stencil_mask);
+                    const int32_t mval = (int32_t)((uint32_t)sval & cfg->stencil_mask);
+                    const uint8_t wm = (uint8_t)(cfg->stencil_writemask & 0xFF);
+                    uint32_t op;
+                    if (!compare_i(cfg->stencil_func, mref, mval)) { op = cfg->stencil_fail; active = false; }
+                    else if ((flags & RC_DEPTH_TEST) && !compare_f(cfg->depth_func, depth, sm.depth[ci])) { op = cfg->stencil_zfail; active = false; }
+                    else op = cfg->stencil_zpass;
+                    const uint8_t nv = stencil_apply(op, sval, cfg->stencil_ref);
                     sm.stencil[si] = (uint8_t)((sval & ~wm) | (nv & wm));
-                    continue;
-                }
-                if ((flags & RC_DEPTH_TEST) && !compare_f(cfg->depth_func, depth, sm.depth[ci])) {
-                    uint8_t nv = stencil_apply(cfg->stencil_zfail, sval, cfg->stencil_ref);
-                    sm.stencil[si] = (uint8_t)((sval & ~wm) | (nv & wm));
-                    continue;
-                }
-                uint8_t nv = stencil_apply(cfg->stencil_zpass, sval, cfg->stencil_ref);
-                sm.stencil[si] = (uint8_t)((sval & ~wm) | (nv & wm));
-            } else if (flags & RC_DEPTH_TEST) {
-                if (!compare_f(cfg->depth_func, depth, sm.depth[ci])) continue;
-            }
-
-            Color4 c;
-            if (flags & RC_FLAT) c = { col2.x, col2.y, col2.z, col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
-            else {
-                c.r = col0.x * b0 + col1.x * b1 + col2.x * b2;
-                c.g = col0.y * b0 + col1.y * b1 + col2.y * b2;
-                c.b = col0.z * b0 + col1.z * b1 + col2.z * b2;
-                c.a = col0.w * b0 + col1.w * b1 + col2.w * b2;
-            }
-
-            if (relight) {                                  /* raster.c:592-615 */
-                const TriEye *eye = b.rec_eye + r;
-                float ep[3], en[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    ep[k] = eye->ep0[k] * b0 + eye->ep1[k] * b1 + eye->ep2[k] * b2;
-                    en[k] = eye->en0[k] * b0 + eye->en1[k] * b1 + eye->en2[k] * b2;
-                }
-                const mtgl_state *st = b.states + state_index;
-                MaterialRegs mat;
-                if (back_facing && (flags & RC_TWO_SIDE)) {
-                    en[0] *= -1.0f; en[1] *= -1.0f; en[2] *= -1.0f;
-                    load_material(mat, &st->material_back);
-                } else load_material(mat, &st->material_front);
-                c = compute_lighting(st, ep[0], ep[1], ep[2], en[0], en[1], en[2], mat);
-            }
-
-            if (flags & RC_TEXTURED) {                      /* raster.c:618-669 */
-                float u, v;
-                if (flags & RC_PERSPECTIVE) {
-                    float uw = b0 * u0w + b1 * u1w + b2 * u2w;
-                    float vw = b0 * v0w + b1 * v1w + b2 * v2w;
-                    float ow = b0 * w0 + b1 * w1 + b2 * w2;
-                    float w = 1.0f / ow;
-                    u = uw * w;
-                    v = vw * w;
-                } else {
-                    u = b0 * u0 + b1 * u1 + b2 * u2;
-                    v = b0 * v0 + b1 * v1 + b2 * v2;
-                }
-                Color4 t = color_unpack(sample_lod(cfg, u, v, lod, un), un);
-                /* alpha test exists only here and tests the TEXEL alpha (raster.c:640-643) */
-                if ((flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, t.a, cfg->alpha_ref)) continue;
-                switch (cfg->tex_env_mode) {
-                case G_REPLACE: c = t; break;
-                case G_DECAL: c = color_lerp_rgb(c, t, t.a); break;
-                case G_BLEND: {
-                    const float *e = cfg->tex_env_color;
-                    c = { c.r * (1.0f - t.r) + e[0] * t.r, c.g * (1.0f - t.g) + e[1] * t.g, c.b * (1.0f - t.b) + e[2] * t.b, c.a * t.a };
-                    break;
-                }
-                case G_ADD: c = { c.r + t.r, c.g + t.g, c.b + t.b, c.a * t.a }; break;
-                default: c = { c.r * t.r, c.g * t.g, c.b * t.b, c.a * t.a }; break;
+                } else if (flags & RC_DEPTH_TEST) {
+                    if (!compare_f(cfg->depth_func, depth, sm.depth[ci])) active = false;
                 }
             }
+            const bool depth_write = (flags & (RC_DEPTH_TEST | RC_DEPTH_WRITE)) == (RC_DEPTH_TEST | RC_DEPTH_WRITE);
 
-            if (flags & RC_FOG) {                           /* raster.c:672-705; result alpha = fog colour alpha */
-                float fc = b0 * ez0 + b1 * ez1 + b2 * ez2;
-                Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
-                c = color_lerp_rgb(fogc, c, fog_factor(cfg, fc));
-            }
-
-            if ((flags & (RC_DEPTH_TEST | RC_DEPTH_WRITE)) == (RC_DEPTH_TEST | RC_DEPTH_WRITE)) sm.depth[ci] = depth;
-
-            if (flags & RC_BLEND) {                         /* raster.c:712-717 */
-                Color4 d = color_unpack(sm.color[ci], un);
-                Color4 sf = blend_factor(cfg->blend_src, c, d), df = blend_factor(cfg->blend_dst, c, d);
-                c = color_clamp({ c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a });
-            }
-            c = color_clamp(c);
-
-            const uint32_t cm = cfg->color_mask;            /* write_pixel_masked, raster.c:20-45 */
-            if (cm == 0xFu) sm.color[ci] = color_pack(c);
-            else if (cm != 0u) {
-                Color4 d = color_unpack(sm.color[ci], un);
-                if (cm & 1u) d.r = c.r;
-                if (cm & 2u) d.g = c.g;
-                if (cm & 4u) d.b = c.b;
-                if (cm & 8u) d.a = c.a;
-                sm.color[ci] = color_pack(d);
-            }
+            if (defer) {
+                /* nothing can discard the fragment any more: the depth write of raster.c:707-710 happens now,
+                 * the colour work is queued and later executed with full warps */
+                if (active && depth_write) sm.depth[ci] = depth;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, active);
+                if (m) {
+                    if (active) {
+                        const uint32_t e = (qhead + qcount + __popc(m & lt_mask)) & (FRAG_QUEUE - 1);
+                        sm.fq_rec[warp][e] = r;
+                        sm.fq_pix[warp][e] = (uint32_t)ci;
+                        sm.fq_b0[warp][e] = b0; sm.fq_b1[warp][e] = b1; sm.fq_b2[warp][e] = b2;
+                    }
+                    qcount += __popc(m);
+                    __syncwarp();
+                    if (qcount >= 32) drain_queue(b, sm, warp, lane, qhead, qcount);
+                }
+            } else if (active) shade_now(b, sm, r, state_flags, cfg, b0, b1, b2, ci, depth, depth_write);
         }
     }
 }
@@ -494,6 +630,7 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rx0 = (int)(warp & 1) * REGION_W, ry0 = (int)(warp >> 1) * REGION_H;
     const int rx1 = rx0 + REGION_W - 1, ry1 = ry0 + REGION_H - 1;
+    uint32_t qhead = 0, qcount = 0;
     for (uint32_t base = 0; base < n; base += 32) {
         uint32_t e = base + lane;
         uint32_t box = 0;
@@ -511,13 +648,14 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
             uint32_t r = sm.rec[base + k];
             int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
             int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
-            raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1);
+            raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1, qhead, qcount);
             __syncwarp();
         }
     }
+    while (qcount) drain_queue(b, sm, warp, lane, qhead, qcount);
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes)
+__global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem &sm = *reinterpret_cast<RasterSmem *>(smem_raw);
