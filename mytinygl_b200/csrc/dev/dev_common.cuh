@@ -45,9 +45,11 @@ enum : uint32_t {
 constexpr int TILE_W = 64;
 constexpr int TILE_H = 64;
 constexpr int TILE_LOG = 6;
-constexpr int RASTER_THREADS = 256;           /* 8 warps, each owning a 32x16 pixel region of the tile */
-constexpr int REGION_W = 32;
+constexpr int RASTER_THREADS = 256;           /* 8 warps; each takes one 16x16 pixel region of the tile at a time */
+constexpr int REGION_W = 16;
 constexpr int REGION_H = 16;
+constexpr int REGIONS_X = TILE_W / REGION_W;
+constexpr int NUM_REGIONS = (TILE_W / REGION_W) * (TILE_H / REGION_H);
 constexpr int COLOR_PITCH = 72;               /* words per tile row in shared memory: an 8x4 pixel block */
 constexpr int STENCIL_PITCH = 80;             /* (the fragment quantum) hits 32 distinct banks            */
 constexpr int LIST_WINDOW = 2048;             /* triangle references sorted + staged per pass             */

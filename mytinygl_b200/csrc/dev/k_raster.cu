@@ -12,11 +12,13 @@
  * batch: loaded once with 128-bit loads (or initialised from the clear values when the batch
  * starts with a clear that covers the tile -- a cleared tile is never read from HBM), updated in
  * place by every fragment, written back once with 128-bit stores.  The tile's triangle references
- * are sorted by submission id first.  Each of the 8 warps owns a fixed 32x16 pixel region, walks
- * the sorted list 32 references at a time (one bounding-box test per lane, warp ballot), and
- * rasterises the hits in order over 8x4-pixel blocks -- so every pixel sees its fragments in
- * exactly the reference's order (blending, stencil counting, depth ties, double-shaded shared
- * edges) without atomics or inter-warp synchronisation.
+ * are sorted by submission id first.  The tile is cut into 16 regions of 16x16 pixels; each of the 8
+ * warps repeatedly takes the next region, walks the sorted list 32 references at a time (one
+ * bounding-box test per lane, warp ballot), and rasterises the hits in order over 8x4-pixel
+ * blocks -- so every pixel sees its fragments in exactly the reference's order (blending, stencil
+ * counting, depth ties, double-shaded shared edges) without per-pixel atomics, and the regions
+ * balance the load between warps.  Fragments of states that neither blend nor alpha-test are
+ * queued per warp and shaded 32 at a time with full lanes (deferred shading across triangles).
  *
  * Shared-memory rows are padded (72 words / 80 bytes) so that the 32 lanes of an 8x4 block hit
  * 32 distinct banks.
@@ -37,19 +39,29 @@ struct RasterSmem {
     uint32_t color[TILE_H * COLOR_PITCH];
     float depth[TILE_H * COLOR_PITCH];
     uint8_t stencil[TILE_H * STENCIL_PITCH];
-    uint32_t key[LIST_WINDOW];
+    union {
+        uint32_t key[LIST_WINDOW];      /* sort keys: dead once the window is sorted ... */
+        struct {                        /* ... so the per-warp fragment queues reuse the space while it is rasterised */
+            uint32_t fq_rec[RASTER_THREADS / 32][FRAG_QUEUE];
+            uint32_t fq_pix[RASTER_THREADS / 32][FRAG_QUEUE];
+            float fq_b0[RASTER_THREADS / 32][FRAG_QUEUE];
+            float fq_b1[RASTER_THREADS / 32][FRAG_QUEUE];
+        };
+    };
     uint32_t rec[LIST_WINDOW];
     uint32_t box[LIST_WINDOW];
     float unorm8[256];
-    /* fragments that passed the stencil/depth tests and wait for shading: record, pixel, barycentrics */
-    uint32_t fq_rec[RASTER_THREADS / 32][FRAG_QUEUE];
-    uint32_t fq_pix[RASTER_THREADS / 32][FRAG_QUEUE];
-    float fq_b0[RASTER_THREADS / 32][FRAG_QUEUE];
-    float fq_b1[RASTER_THREADS / 32][FRAG_QUEUE];
+    /* queued fragments (passed the stencil/depth tests, wait for shading): record, pixel, barycentrics */
     float fq_b2[RASTER_THREADS / 32][FRAG_QUEUE];
     uint32_t count;
+    uint32_t next_region;       /* dynamic region scheduler of the current window */
+    uint32_t region_work[NUM_REGIONS];      /* estimated work per region (8x4 blocks touched + visits) */
+    uint32_t region_order[NUM_REGIONS];     /* regions sorted by decreasing work: heaviest first */
     uint32_t scratch[RASTER_THREADS / 32];
 };
+
+static_assert(4 * (RASTER_THREADS / 32) * FRAG_QUEUE <= LIST_WINDOW, "fragment queues must fit in the key array");
+static_assert((LIST_WINDOW & (LIST_WINDOW - 1)) == 0, "the bitonic sort pads to a power of two");
 
 /* ---------------------------------------------------------------- texture sampling (textures.c)
  * The sampler is split in two: tex_taps() resolves the filter, wraps the coordinates and fetches the (up to 8)
@@ -416,9 +428,11 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, i
             const int ci = y * COLOR_PITCH + x;
             float depth = 0.0f;
             if (active) {
-                const float z = b0 * z0 + b1 * z1 + b2 * z2;
-                if (flags & RC_DEPTH_RANGE_01) depth = (z + 1.0f) * 0.5f;
-                else depth = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
+                if (flags & RC_DEPTH_TEST) {                    /* the value is only consumed by the depth test / write */
+                    const float z = b0 * z0 + b1 * z1 + b2 * z2;
+                    if (flags & RC_DEPTH_RANGE_01) depth = (z + 1.0f) * 0.5f;
+                    else depth = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
+                }
 
                 if (flags & RC_STENCIL) {                       /* raster.c:550-579 */
                     const int si = y * STENCIL_PITCH + x;
@@ -599,13 +613,36 @@ __device__ __forceinline__ uint32_t pack_box(uint2 bb, int px0, int py0)
     return (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
 }
 
+/* add one reference's estimated cost to every region its (tile-relative) box overlaps */
+__device__ __forceinline__ void account_regions(RasterSmem &sm, uint32_t box)
+{
+    const int x0 = box & 0xFF, y0 = (box >> 8) & 0xFF, x1 = (box >> 16) & 0xFF, y1 = box >> 24;
+    for (int ry = y0 / REGION_H; ry <= y1 / REGION_H; ry++)
+        for (int rx = x0 / REGION_W; rx <= x1 / REGION_W; rx++) {
+            const int w = min(x1, rx * REGION_W + REGION_W - 1) - max(x0, rx * REGION_W) + 1;
+            const int h = min(y1, ry * REGION_H + REGION_H - 1) - max(y0, ry * REGION_H) + 1;
+            atomicAdd(&sm.region_work[ry * REGIONS_X + rx], 2u + (uint32_t)(((w + 7) >> 3) * ((h + 3) >> 2)));
+        }
+}
+
 /* bitonic sort of (key, rec, box) triples by key; n padded to a power of two with key = ~0 */
 __device__ void sort_window(RasterSmem &sm, uint32_t n)
 {
     uint32_t p = 32;
     while (p < n) p <<= 1;
     for (uint32_t i = n + threadIdx.x; i < p; i += RASTER_THREADS) sm.key[i] = 0xFFFFFFFFu;
+    if (threadIdx.x == 0) sm.next_region = 0;
+    if (threadIdx.x < NUM_REGIONS) {        /* longest-processing-time-first order of the regions */
+        const uint32_t mine = sm.region_work[threadIdx.x];
+        uint32_t rank = 0;
+        for (int k = 0; k < NUM_REGIONS; k++) {
+            const uint32_t other = sm.region_work[k];
+            rank += (other > mine || (other == mine && k < (int)threadIdx.x)) ? 1u : 0u;
+        }
+        sm.region_order[rank] = threadIdx.x;
+    }
     __syncthreads();
+    if (threadIdx.x < NUM_REGIONS) sm.region_work[threadIdx.x] = 0;
     for (uint32_t k = 2; k <= p; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t i = threadIdx.x; i < p; i += RASTER_THREADS) {
@@ -624,32 +661,46 @@ __device__ void sort_window(RasterSmem &sm, uint32_t n)
         }
 }
 
-/* rasterise the n staged (sorted) references: every warp walks the whole window for its region */
+/* Rasterise the n staged (sorted) references.  The tile is cut into 16 regions of 16x16 pixels; a warp takes
+ * the next unprocessed region from a shared counter and walks the whole window for it, so all fragments of a
+ * pixel are produced by one warp in submission order while the regions balance the load between warps. */
 __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, int px0, int py0)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rx0 = (int)(warp & 1) * REGION_W, ry0 = (int)(warp >> 1) * REGION_H;
-    const int rx1 = rx0 + REGION_W - 1, ry1 = ry0 + REGION_H - 1;
     uint32_t qhead = 0, qcount = 0;
-    for (uint32_t base = 0; base < n; base += 32) {
-        uint32_t e = base + lane;
-        uint32_t box = 0;
-        bool hit = false;
-        if (e < n) {
-            box = sm.box[e];
-            int x0 = box & 0xFF, y0 = (box >> 8) & 0xFF, x1 = (box >> 16) & 0xFF, y1 = box >> 24;
-            hit = !(x1 < rx0 || x0 > rx1 || y1 < ry0 || y0 > ry1);
-        }
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
-        while (mask) {
-            int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            uint32_t bx = __shfl_sync(0xFFFFFFFFu, box, k);
-            uint32_t r = sm.rec[base + k];
-            int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
-            int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
-            raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1, qhead, qcount);
-            __syncwarp();
+    for (;;) {
+        uint32_t region = 0;
+        if (lane == 0) region = atomicAdd(&sm.next_region, 1u);
+        region = __shfl_sync(0xFFFFFFFFu, region, 0);
+        if (region >= (uint32_t)NUM_REGIONS) break;
+        region = sm.region_order[region];
+        const int rx0 = (int)(region % REGIONS_X) * REGION_W, ry0 = (int)(region / REGIONS_X) * REGION_H;
+        const int rx1 = rx0 + REGION_W - 1, ry1 = ry0 + REGION_H - 1;
+        for (uint32_t base = 0; base < n; base += 32) {
+            uint32_t e = base + lane;
+            uint32_t box = 0;
+            bool hit = false;
+            if (e < n) {
+                box = sm.box[e];
+                int x0 = box & 0xFF, y0 = (box >> 8) & 0xFF, x1 = (box >> 16) & 0xFF, y1 = box >> 24;
+                hit = !(x1 < rx0 || x0 > rx1 || y1 < ry0 || y0 > ry1);
+                if (hit) {      /* pull the record towards this SM while earlier hits are being rasterised */
+                    const char *p = reinterpret_cast<const char *>(b.records + sm.rec[e]);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 128));
+                }
+            }
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+            while (mask) {
+                int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                uint32_t bx = __shfl_sync(0xFFFFFFFFu, box, k);
+                uint32_t r = sm.rec[base + k];
+                int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
+                int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
+                raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1, qhead, qcount);
+                __syncwarp();
+            }
         }
     }
     while (qcount) drain_queue(b, sm, warp, lane, qhead, qcount);
@@ -674,6 +725,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
     if (L == 0 && !clr_here) return;
 
     for (int i = threadIdx.x; i < 256; i += RASTER_THREADS) sm.unorm8[i] = b.unorm8[i];
+    if (threadIdx.x < NUM_REGIONS) sm.region_work[threadIdx.x] = 0;
     /* shared-memory row 0 is framebuffer row py0 (the first row of the tile inside the band) */
     tile_init(sm, fb, clr, planes, px0, py0, vw, vh);
     __syncthreads();
@@ -686,7 +738,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
                 uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(b.records + r) + 2);
                 sm.key[i] = row2.w;
                 sm.rec[i] = r;
-                sm.box[i] = pack_box(make_uint2(row2.x, row2.y), px0, py0);
+                const uint32_t bx = pack_box(make_uint2(row2.x, row2.y), px0, py0);
+                sm.box[i] = bx;
+                account_regions(sm, bx);
             }
             __syncthreads();
             sort_window(sm, L);
@@ -723,7 +777,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
                         uint32_t at = atomicAdd(&sm.count, 1u);
                         sm.key[at] = row2.w;
                         sm.rec[at] = r;
-                        sm.box[at] = pack_box(make_uint2(row2.x, row2.y), px0, py0);
+                        const uint32_t bx = pack_box(make_uint2(row2.x, row2.y), px0, py0);
+                        sm.box[at] = bx;
+                        account_regions(sm, bx);
                     }
                 }
                 __syncthreads();
