@@ -37,3 +37,25 @@ def test_exactness_report(b200, front_oracle):
         exact += int(s["color_diff_pixels"] == 0 and s["depth_diff_pixels"] == 0)
     print(f"bit-identical cases: {exact}/{len(CASES)}")
     assert exact >= len(CASES) // 2
+
+
+@pytest.mark.parametrize("case,split", [(("c1_suzanne", 800, 600, 0), 320), (("c4_grid", 480, 270, 3 | (2 << 8)), 100),
+                                        (("stencil", 300, 200, 0), 64), (("state_churn", 517, 389, 0), 200)])
+def test_cuda_bands_stitch_to_full_frame(b200, front_oracle, case, split):
+    """mtgl_dev_set_band: two contexts owning complementary (not tile-aligned) bands reproduce the full frame."""
+    import ctypes
+    name, w, h, variant = case
+    b200.lib.mtgl_dev_set_band.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    bands = []
+    for y0, y1 in ((0, split), (split, h)):
+        b200.create(w, h)
+        assert b200.lib.mtgl_dev_set_band(b200.device(), y0, y1) == 0
+        b200.lib.glClearColor(ctypes.c_float(0.25), ctypes.c_float(0.5), ctypes.c_float(0.75), ctypes.c_float(1.0))
+        b200.lib.glClear(0x4000 | 0x0100 | 0x0400)
+        b200.lib.glClearColor(ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(1))
+        assert b200.lib.scene_render(name.encode(), w, h, variant) == 0
+        planes = b200.read()
+        b200.destroy()
+        bands.append([p[y0:y1] for p in planes])
+    got = tuple(np.concatenate([bands[0][i], bands[1][i]]) for i in range(3))
+    assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
