@@ -17,8 +17,9 @@
  * bounding-box test per lane, warp ballot), and rasterises the hits in order over 8x4-pixel
  * blocks -- so every pixel sees its fragments in exactly the reference's order (blending, stencil
  * counting, depth ties, double-shaded shared edges) without per-pixel atomics, and the regions
- * balance the load between warps.  Fragments of states that neither blend nor alpha-test are
- * queued per warp and shaded 32 at a time with full lanes (deferred shading across triangles).
+ * balance the load between warps.  Fragments of states that neither blend nor alpha-test only
+ * update depth/stencil and a per-pixel visibility entry; their colour is computed once per pixel,
+ * with full warps, when the region is resolved (deferred shading).
  *
  * Shared-memory rows are padded (72 words / 80 bytes) so that the 32 lanes of an 8x4 block hit
  * 32 distinct banks.
@@ -33,34 +34,29 @@ namespace mtgl_dev_impl {
 
 void note_launch();
 
-constexpr int FRAG_QUEUE = 64;               /* per-warp deferred-shading queue (two batches of 32) */
+constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 
 struct RasterSmem {
     uint32_t color[TILE_H * COLOR_PITCH];
     float depth[TILE_H * COLOR_PITCH];
+    /* visibility buffer: record of the last fragment that passed the stencil/depth tests and whose colour has
+     * not been computed yet (deferred shading), VIS_NONE otherwise */
+    uint32_t vis[TILE_H * COLOR_PITCH];
     uint8_t stencil[TILE_H * STENCIL_PITCH];
     union {
         uint32_t key[LIST_WINDOW];      /* sort keys: dead once the window is sorted ... */
-        struct {                        /* ... so the per-warp fragment queues reuse the space while it is rasterised */
-            uint32_t fq_rec[RASTER_THREADS / 32][FRAG_QUEUE];
-            uint32_t fq_pix[RASTER_THREADS / 32][FRAG_QUEUE];
-            float fq_b0[RASTER_THREADS / 32][FRAG_QUEUE];
-            float fq_b1[RASTER_THREADS / 32][FRAG_QUEUE];
-        };
+        uint16_t pend[RASTER_THREADS / 32][REGION_W * REGION_H];   /* ... reused for the per-warp lists of pixels to shade */
     };
     uint32_t rec[LIST_WINDOW];
     uint32_t box[LIST_WINDOW];
     float unorm8[256];
-    /* queued fragments (passed the stencil/depth tests, wait for shading): record, pixel, barycentrics */
-    float fq_b2[RASTER_THREADS / 32][FRAG_QUEUE];
     uint32_t count;
     uint32_t next_region;       /* dynamic region scheduler of the current window */
     uint32_t region_work[NUM_REGIONS];      /* estimated work per region (8x4 blocks touched + visits) */
     uint32_t region_order[NUM_REGIONS];     /* regions sorted by decreasing work: heaviest first */
     uint32_t scratch[RASTER_THREADS / 32];
 };
-
-static_assert(4 * (RASTER_THREADS / 32) * FRAG_QUEUE <= LIST_WINDOW, "fragment queues must fit in the key array");
+static_assert(sizeof(uint16_t) * (RASTER_THREADS / 32) * REGION_W * REGION_H <= sizeof(uint32_t) * LIST_WINDOW, "pending lists must fit in the key array");
 static_assert((LIST_WINDOW & (LIST_WINDOW - 1)) == 0, "the bitonic sort pads to a power of two");
 
 /* ---------------------------------------------------------------- texture sampling (textures.c)
@@ -324,34 +320,52 @@ __device__ __forceinline__ bool shade_color(const BatchDev &b, const float *un, 
     return true;
 }
 
-/* Shade up to 32 queued fragments, one per lane (lane < n).  Only fragments whose state neither blends nor
- * alpha-tests nor masks colour channels are queued, so the last fragment of a pixel in submission order wins:
- * inside a batch that is the highest lane addressing the pixel. */
-__device__ __noinline__ void drain_queue(const BatchDev &b, RasterSmem &sm, uint32_t warp, uint32_t lane, uint32_t &qhead, uint32_t &qcount)
+/* Deferred shading of one 16x16 region: every pixel whose visibility entry is set gets the colour of that
+ * (last, in submission order) fragment.  Only fragments of states that neither blend nor alpha-test nor mask
+ * colour channels are deferred, so earlier fragments of the pixel would have been overwritten anyway: the work
+ * is done once per covered pixel instead of once per passing fragment, and with full warps -- the pixels to
+ * shade are first compacted into a per-warp list.  Barycentrics are recomputed from the record with the
+ * reference's expressions (raster.c:534-544), which is deterministic. */
+__device__ __noinline__ void resolve_region(const BatchDev &b, RasterSmem &sm, int rx0, int ry0, int tile_px, int tile_py)
 {
-    const uint32_t n = min(qcount, 32u);
-    const bool valid = lane < n;
-    uint32_t pix = 0;
-    Color4 c = { 0.0f, 0.0f, 0.0f, 0.0f };
-    if (valid) {
-        const uint32_t e = (qhead + lane) & (FRAG_QUEUE - 1);
-        const uint32_t r = sm.fq_rec[warp][e];
-        pix = sm.fq_pix[warp][e];
-        const float b0 = sm.fq_b0[warp][e], b1 = sm.fq_b1[warp][e], b2 = sm.fq_b2[warp][e];
-        const TriRecord *rec = b.records + r;
-        const uint32_t state_flags = __ldg(&rec->state_flags);
-        const RasterCfg *cfg = b.cfgs + (state_flags & 0x7FFFFFFFu);
-        TriAttr A;
-        load_attr(A, rec);
-        shade_color(b, sm.unorm8, r, state_flags, A, cfg, b0, b1, b2, c);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t count = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < (REGION_W / 8) * (REGION_H / 4); blk++) {
+        const int x = rx0 + (blk % (REGION_W / 8)) * 8 + (int)(lane & 7), y = ry0 + (blk / (REGION_W / 8)) * 4 + (int)(lane >> 3);
+        const int ci = y * COLOR_PITCH + x;
+        const bool has = sm.vis[ci] != VIS_NONE;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+        if (has) sm.pend[warp][count + __popc(m & lt_mask)] = (uint16_t)ci;
+        count += __popc(m);
     }
-    const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-    if (valid) {
-        const uint32_t peers = __match_any_sync(vmask, pix);
-        if ((peers >> lane) == 1u) sm.color[pix] = color_pack(color_clamp(c));      /* raster.c:719-721 */
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t base = 0; base < count; base += 32) {
+        if (base + lane < count) {
+            const int ci = sm.pend[warp][base + lane];
+            const uint32_t r = sm.vis[ci];
+            sm.vis[ci] = VIS_NONE;
+            const TriRecord *rec = b.records + r;
+            const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+            const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+            const uint32_t state_flags = __ldg(&rec->state_flags);
+            const float fx0 = (float)row0.x, fy0 = (float)row0.y, fx1 = (float)row0.z, fy1 = (float)row0.w;
+            const float fx2 = (float)row1.x, fy2 = (float)row1.y;
+            const float inv_area = __int_as_float(row1.w);
+            const float px = (float)(tile_px + ci % COLOR_PITCH), py = (float)(tile_py + ci / COLOR_PITCH);
+            const float b0 = edge_at(fx1, fy1, fx2, fy2, px, py) * inv_area;
+            const float b1 = edge_at(fx2, fy2, fx0, fy0, px, py) * inv_area;
+            const float b2 = edge_at(fx0, fy0, fx1, fy1, px, py) * inv_area;
+            const RasterCfg *cfg = b.cfgs + (state_flags & 0x7FFFFFFFu);
+            TriAttr A;
+            load_attr(A, rec);
+            Color4 c;
+            shade_color(b, sm.unorm8, r, state_flags, A, cfg, b0, b1, b2, c);
+            sm.color[ci] = color_pack(color_clamp(c));      /* raster.c:719-721 */
+        }
     }
-    qhead = (qhead + n) & (FRAG_QUEUE - 1);
-    qcount -= n;
     __syncwarp();
 }
 
@@ -386,9 +400,9 @@ __device__ __noinline__ void shade_now(const BatchDev &b, RasterSmem &sm, uint32
 
 /* ---------------------------------------------------------------- one triangle over one warp region */
 __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, int tile_px, int tile_py,
-                                int X0, int Y0, int X1, int Y1, uint32_t &qhead, uint32_t &qcount)
+                                int X0, int Y0, int X1, int Y1, int rx0, int ry0, bool &pending)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     const TriRecord *rec = b.records + r;
     const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
     const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
@@ -404,14 +418,15 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, i
     const float z0 = row3.x, z1 = row3.y, z2 = row3.z;
     const bool area_pos = area > 0;
     const uint32_t cm = cfg->color_mask;
-    /* shading can be deferred (and compacted across triangles) when nothing between the depth test and the
-     * colour write depends on or discards per fragment state: no blending, no alpha test, full colour mask */
+    /* shading can be deferred when nothing between the depth test and the colour write depends on or discards
+     * per fragment state: no blending, no alpha test, full colour mask */
     const bool defer = !(flags & RC_BLEND) && !((flags & RC_ALPHA_TEST) && (flags & RC_TEXTURED)) && cm == 0xFu;
 
-    if (!defer) {       /* queued colour writes of earlier triangles must land before an in-order triangle reads them */
-        while (qcount) drain_queue(b, sm, warp, lane, qhead, qcount);
+    if (defer) pending = true;
+    else if (pending) {     /* deferred colours of earlier triangles must land before an in-order triangle reads them */
+        resolve_region(b, sm, rx0, ry0, tile_px, tile_py);
+        pending = false;
     }
-    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int by = Y0; by <= Y1; by += 4) {
         for (int bx = X0; bx <= X1; bx += 8) {
@@ -453,20 +468,11 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, i
             const bool depth_write = (flags & (RC_DEPTH_TEST | RC_DEPTH_WRITE)) == (RC_DEPTH_TEST | RC_DEPTH_WRITE);
 
             if (defer) {
-                /* nothing can discard the fragment any more: the depth write of raster.c:707-710 happens now,
-                 * the colour work is queued and later executed with full warps */
-                if (active && depth_write) sm.depth[ci] = depth;
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, active);
-                if (m) {
-                    if (active) {
-                        const uint32_t e = (qhead + qcount + __popc(m & lt_mask)) & (FRAG_QUEUE - 1);
-                        sm.fq_rec[warp][e] = r;
-                        sm.fq_pix[warp][e] = (uint32_t)ci;
-                        sm.fq_b0[warp][e] = b0; sm.fq_b1[warp][e] = b1; sm.fq_b2[warp][e] = b2;
-                    }
-                    qcount += __popc(m);
-                    __syncwarp();
-                    if (qcount >= 32) drain_queue(b, sm, warp, lane, qhead, qcount);
+                /* nothing can discard the fragment any more: the depth write of raster.c:707-710 happens now and
+                 * the fragment becomes the pixel's visible one; its colour is computed by resolve_region */
+                if (active) {
+                    if (depth_write) sm.depth[ci] = depth;
+                    sm.vis[ci] = r;
                 }
             } else if (active) shade_now(b, sm, r, state_flags, cfg, b0, b1, b2, ci, depth, depth_write);
         }
@@ -666,8 +672,7 @@ __device__ void sort_window(RasterSmem &sm, uint32_t n)
  * pixel are produced by one warp in submission order while the regions balance the load between warps. */
 __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, int px0, int py0)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t qhead = 0, qcount = 0;
+    const uint32_t lane = threadIdx.x & 31;
     for (;;) {
         uint32_t region = 0;
         if (lane == 0) region = atomicAdd(&sm.next_region, 1u);
@@ -676,6 +681,7 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
         region = sm.region_order[region];
         const int rx0 = (int)(region % REGIONS_X) * REGION_W, ry0 = (int)(region / REGIONS_X) * REGION_H;
         const int rx1 = rx0 + REGION_W - 1, ry1 = ry0 + REGION_H - 1;
+        bool pending = false;
         for (uint32_t base = 0; base < n; base += 32) {
             uint32_t e = base + lane;
             uint32_t box = 0;
@@ -698,12 +704,12 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 uint32_t r = sm.rec[base + k];
                 int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
                 int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
-                raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1, qhead, qcount);
+                raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
                 __syncwarp();
             }
         }
+        if (pending) resolve_region(b, sm, rx0, ry0, px0, py0);
     }
-    while (qcount) drain_queue(b, sm, warp, lane, qhead, qcount);
 }
 
 __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes)
@@ -726,6 +732,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
 
     for (int i = threadIdx.x; i < 256; i += RASTER_THREADS) sm.unorm8[i] = b.unorm8[i];
     if (threadIdx.x < NUM_REGIONS) sm.region_work[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < TILE_H * COLOR_PITCH; i += RASTER_THREADS) sm.vis[i] = VIS_NONE;
     /* shared-memory row 0 is framebuffer row py0 (the first row of the tile inside the band) */
     tile_init(sm, fb, clr, planes, px0, py0, vw, vh);
     __syncthreads();
