@@ -64,28 +64,47 @@ template <int PASS>
 __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
 {
     const uint32_t n = b.counters->records;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const TriRecord *rec = b.records + r;
-        uint2 box = *reinterpret_cast<const uint2 *>(&rec->bbox_min);
-        int tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG, tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
-        int ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0, ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
-        int ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    /* whole warps iterate together so that the warp-level aggregation below sees a full mask */
+    for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; r0 < n; r0 += gridDim.x * blockDim.x) {
+        const uint32_t r = r0 + lane;
+        int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, ntiles = 0;
+        if (r < n) {
+            const TriRecord *rec = b.records + r;
+            uint2 box = *reinterpret_cast<const uint2 *>(&rec->bbox_min);
+            tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG; tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
+            ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0; ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
+            ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+        }
         if (ntiles > LARGE_TILES) {
             if (PASS == 0) {
                 uint32_t at = atomicAdd(&b.counters->large_count, 1u);
                 b.large_list[at] = r;
             }
-            continue;
+            ntiles = 0;
         }
-        for (int ty = ty0; ty <= ty1; ty++)
-            for (int tx = tx0; tx <= tx1; tx++) {
-                uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
-                if (PASS == 0) atomicAdd(&b.tile_count[tile], 1u);
-                else {
-                    uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
-                    b.tile_list[b.tile_offset[tile] + at] = r;
+        /* mesh-ordered records of one warp mostly fall into the same tile: one atomic per distinct tile */
+        const uint32_t single = __ballot_sync(0xFFFFFFFFu, ntiles == 1);
+        if (ntiles == 1) {
+            const uint32_t tile = (uint32_t)(ty0 * fb.tiles_x + tx0);
+            const uint32_t peers = __match_any_sync(single, tile);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(PASS == 0 ? &b.tile_count[tile] : &b.tile_cursor[tile], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            if (PASS == 1) b.tile_list[b.tile_offset[tile] + base + __popc(peers & lt_mask)] = r;
+        } else if (ntiles > 1) {
+            for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++) {
+                    uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
+                    if (PASS == 0) atomicAdd(&b.tile_count[tile], 1u);
+                    else {
+                        uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
+                        b.tile_list[b.tile_offset[tile] + at] = r;
+                    }
                 }
-            }
+        }
     }
 }
 
