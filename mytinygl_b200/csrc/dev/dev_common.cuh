@@ -108,8 +108,14 @@ enum : uint32_t {
     RC_DEPTH_TEST = 1u << 0, RC_DEPTH_WRITE = 1u << 1, RC_STENCIL = 1u << 2, RC_BLEND = 1u << 3,
     RC_TEXTURED = 1u << 4, RC_ALPHA_TEST = 1u << 5, RC_FOG = 1u << 6, RC_FLAT = 1u << 7,
     RC_PHONG = 1u << 8, RC_LIGHTING = 1u << 9, RC_TWO_SIDE = 1u << 10, RC_PERSPECTIVE = 1u << 11,
-    RC_DEPTH_RANGE_01 = 1u << 12    /* depth range is exactly [0,1]: the double expression of raster.c:548 is the float one */
+    RC_DEPTH_RANGE_01 = 1u << 12,   /* depth range is exactly [0,1]: the double expression of raster.c:548 is the float one */
+    RC_DEFER = 1u << 13             /* no blending, no alpha test, full colour mask: the colour work can be deferred */
 };
+
+/* TriRecord.state_flags: state block index | deferrable << 30 | back-facing << 31 */
+constexpr uint32_t STATE_INDEX_MASK = 0x3FFFFFFFu;
+constexpr uint32_t STATE_DEFER_BIT = 1u << 30;
+constexpr uint32_t STATE_BACK_BIT = 1u << 31;
 
 /* One set-up sub-triangle: 10 x 16 B.  Row 2 (clamped bounding box, state, ordered id) is all the
  * binner and the tile kernel's list builder read. */
@@ -117,7 +123,7 @@ struct __align__(16) TriRecord {
     int32_t x0, y0, x1, y1;                 /* row 0: integer-snapped vertices (raster.c:59-63) */
     int32_t x2, y2; float area, inv_area;   /* row 1: signed doubled area (raster.c:483) and its reciprocal */
     uint32_t bbox_min, bbox_max;            /* row 2: inclusive bbox after viewport/scissor/framebuffer/band clamps, x | y << 16 */
-    uint32_t state_flags, id;               /*        state index | back-facing << 31 ; submission-ordered id */
+    uint32_t state_flags, id;               /*        state index | deferrable << 30 | back-facing << 31 ; submission-ordered id */
     float z0, z1, z2, lod;                  /* row 3 */
     float w0, w1, w2, ez0;                  /* row 4: 1/w per vertex */
     float c0[4], c1[4], c2[4];              /* rows 5-7 */
@@ -338,7 +344,9 @@ struct BatchDev {
     DevCounters *counters;
     /* binning */
     uint32_t *tile_count, *tile_offset, *tile_cursor;
+    uint32_t *tile_flags;           /* != 0: the tile references a record whose colour work cannot be deferred */
     uint32_t *tile_list; uint32_t list_capacity;
+    uint32_t *vis_plane;            /* visibility buffer in HBM (record index per pixel) between K4a and K4b */
     const float *unorm8;
 };
 
@@ -347,7 +355,9 @@ void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
-void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask, cudaStream_t s);
+/* any_deferrable / any_in_order: whether some draw of the pass has a deferrable / a non-deferrable raster state */
+void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,
+                   bool any_deferrable, bool any_in_order, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);
 uint64_t kernel_launch_count();

@@ -70,12 +70,14 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
     for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; r0 < n; r0 += gridDim.x * blockDim.x) {
         const uint32_t r = r0 + lane;
         int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, ntiles = 0;
+        bool in_order = false;
         if (r < n) {
             const TriRecord *rec = b.records + r;
-            uint2 box = *reinterpret_cast<const uint2 *>(&rec->bbox_min);
+            uint4 box = *reinterpret_cast<const uint4 *>(&rec->bbox_min);     /* bbox_min, bbox_max, state_flags, id */
             tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG; tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
             ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0; ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
             ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+            in_order = !(box.z & STATE_DEFER_BIT);
         }
         if (ntiles > LARGE_TILES) {
             if (PASS == 0) {
@@ -92,14 +94,17 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
             if ((int)lane == leader) base = atomicAdd(PASS == 0 ? &b.tile_count[tile] : &b.tile_cursor[tile], (uint32_t)__popc(peers));
+            if (PASS == 0 && in_order) atomicOr(&b.tile_flags[tile], 1u);
             base = __shfl_sync(peers, base, leader);
             if (PASS == 1) b.tile_list[b.tile_offset[tile] + base + __popc(peers & lt_mask)] = r;
         } else if (ntiles > 1) {
             for (int ty = ty0; ty <= ty1; ty++)
                 for (int tx = tx0; tx <= tx1; tx++) {
                     uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
-                    if (PASS == 0) atomicAdd(&b.tile_count[tile], 1u);
-                    else {
+                    if (PASS == 0) {
+                        atomicAdd(&b.tile_count[tile], 1u);
+                        if (in_order) atomicOr(&b.tile_flags[tile], 1u);
+                    } else {
                         uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
                         b.tile_list[b.tile_offset[tile] + at] = r;
                     }
@@ -125,8 +130,10 @@ __global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
             int py0 = max((ty + fb.tile_y0) << TILE_LOG, by0), py1 = min(((ty + fb.tile_y0) << TILE_LOG) + TILE_H - 1, by1);
             if (!tile_may_overlap(rec, px0, py0, px1, py1)) continue;
             uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
-            if (PASS == 0) atomicAdd(&b.tile_count[tile], 1u);
-            else {
+            if (PASS == 0) {
+                atomicAdd(&b.tile_count[tile], 1u);
+                if (!(rec->state_flags & STATE_DEFER_BIT)) atomicOr(&b.tile_flags[tile], 1u);
+            } else {
                 uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
                 b.tile_list[b.tile_offset[tile] + at] = r;
             }

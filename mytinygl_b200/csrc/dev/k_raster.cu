@@ -37,7 +37,6 @@ void note_launch();
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 
 struct RasterSmem {
-    uint32_t color[TILE_H * COLOR_PITCH];
     float depth[TILE_H * COLOR_PITCH];
     /* visibility buffer: record of the last fragment that passed the stencil/depth tests and whose colour has
      * not been computed yet (deferred shading), VIS_NONE otherwise */
@@ -55,6 +54,8 @@ struct RasterSmem {
     uint32_t region_work[NUM_REGIONS];      /* estimated work per region (8x4 blocks touched + visits) */
     uint32_t region_order[NUM_REGIONS];     /* regions sorted by decreasing work: heaviest first */
     uint32_t scratch[RASTER_THREADS / 32];
+    /* last: the visibility-only variant of the kernel (K4a) does not allocate the colour plane */
+    __align__(16) uint32_t color[TILE_H * COLOR_PITCH];
 };
 static_assert(sizeof(uint16_t) * (RASTER_THREADS / 32) * REGION_W * REGION_H <= sizeof(uint32_t) * LIST_WINDOW, "pending lists must fit in the key array");
 static_assert((LIST_WINDOW & (LIST_WINDOW - 1)) == 0, "the bitonic sort pads to a power of two");
@@ -267,7 +268,7 @@ __device__ __forceinline__ bool shade_color(const BatchDev &b, const float *un, 
                 ep[k] = eye->ep0[k] * b0 + eye->ep1[k] * b1 + eye->ep2[k] * b2;
                 en[k] = eye->en0[k] * b0 + eye->en1[k] * b1 + eye->en2[k] * b2;
             }
-            const mtgl_state *st = b.states + (state_flags & 0x7FFFFFFFu);
+            const mtgl_state *st = b.states + (state_flags & STATE_INDEX_MASK);
             MaterialRegs mat;
             if (flip) {
                 en[0] *= -1.0f; en[1] *= -1.0f; en[2] *= -1.0f;
@@ -358,7 +359,7 @@ __device__ __noinline__ void resolve_region(const BatchDev &b, RasterSmem &sm, i
             const float b0 = edge_at(fx1, fy1, fx2, fy2, px, py) * inv_area;
             const float b1 = edge_at(fx2, fy2, fx0, fy0, px, py) * inv_area;
             const float b2 = edge_at(fx0, fy0, fx1, fy1, px, py) * inv_area;
-            const RasterCfg *cfg = b.cfgs + (state_flags & 0x7FFFFFFFu);
+            const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
             TriAttr A;
             load_attr(A, rec);
             Color4 c;
@@ -399,6 +400,7 @@ __device__ __noinline__ void shade_now(const BatchDev &b, RasterSmem &sm, uint32
 }
 
 /* ---------------------------------------------------------------- one triangle over one warp region */
+template <bool VIS>
 __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, int tile_px, int tile_py,
                                 int X0, int Y0, int X1, int Y1, int rx0, int ry0, bool &pending)
 {
@@ -413,19 +415,21 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, i
     const float fx2 = (float)row1.x, fy2 = (float)row1.y;
     const float area = __int_as_float(row1.z), inv_area = __int_as_float(row1.w);
     const uint32_t state_flags = row2.z;
-    const RasterCfg *cfg = b.cfgs + (state_flags & 0x7FFFFFFFu);
+    const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
     const uint32_t flags = cfg->flags;
     const float z0 = row3.x, z1 = row3.y, z2 = row3.z;
     const bool area_pos = area > 0;
-    const uint32_t cm = cfg->color_mask;
     /* shading can be deferred when nothing between the depth test and the colour write depends on or discards
-     * per fragment state: no blending, no alpha test, full colour mask */
-    const bool defer = !(flags & RC_BLEND) && !((flags & RC_ALPHA_TEST) && (flags & RC_TEXTURED)) && cm == 0xFu;
+     * per fragment state: no blending, no alpha test, full colour mask (RC_DEFER, mirrored in the record).
+     * The visibility-only kernel only ever sees such records. */
+    const bool defer = VIS || (state_flags & STATE_DEFER_BIT) != 0;
 
-    if (defer) pending = true;
-    else if (pending) {     /* deferred colours of earlier triangles must land before an in-order triangle reads them */
-        resolve_region(b, sm, rx0, ry0, tile_px, tile_py);
-        pending = false;
+    if (!VIS) {
+        if (defer) pending = true;
+        else if (pending) {     /* deferred colours of earlier triangles must land before an in-order triangle reads them */
+            resolve_region(b, sm, rx0, ry0, tile_px, tile_py);
+            pending = false;
+        }
     }
 
     for (int by = Y0; by <= Y1; by += 4) {
@@ -474,15 +478,17 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, i
                     if (depth_write) sm.depth[ci] = depth;
                     sm.vis[ci] = r;
                 }
-            } else if (active) shade_now(b, sm, r, state_flags, cfg, b0, b1, b2, ci, depth, depth_write);
+            } else if (!VIS && active) shade_now(b, sm, r, state_flags, cfg, b0, b1, b2, ci, depth, depth_write);
         }
     }
 }
 
 /* ---------------------------------------------------------------- tile load / clear / store */
+template <bool VIS>
 __device__ void tile_init(RasterSmem &sm, const FrameTargets &fb, const ClearOp &clr, uint32_t planes, int px0, int py0,
                           int vw, int vh)
 {
+    if (VIS) planes &= ~1u;         /* the colour plane is produced by the shade pass */
     /* clear rectangle relative to the tile */
     const int cx0 = max(clr.x0 - px0, 0), cy0 = max(clr.y0 - py0, 0);
     const int cx1 = min(clr.x1 - px0, vw), cy1 = min(clr.y1 - py0, vh);
@@ -564,9 +570,26 @@ __device__ void tile_init(RasterSmem &sm, const FrameTargets &fb, const ClearOp 
     }
 }
 
-__device__ void tile_store(RasterSmem &sm, const FrameTargets &fb, uint32_t planes, int px0, int py0, int vw, int vh)
+template <bool VIS>
+__device__ void tile_store(RasterSmem &sm, const FrameTargets &fb, uint32_t planes, int px0, int py0, int vw, int vh, uint32_t *vis_plane)
 {
     const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
+    if (VIS) {
+        planes &= ~1u;
+        /* visibility entries of the tile -> HBM for the shade pass (every pixel, including "none") */
+        if (vec) {
+            for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+                int y = i >> 4, q = i & 15;
+                *reinterpret_cast<uint4 *>(vis_plane + (size_t)(py0 + y) * fb.width + px0 + q * 4) =
+                    *reinterpret_cast<const uint4 *>(&sm.vis[y * COLOR_PITCH + q * 4]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                int y = i >> 6, x = i & 63;
+                if (x < vw) vis_plane[(size_t)(py0 + y) * fb.width + px0 + x] = sm.vis[y * COLOR_PITCH + x];
+            }
+        }
+    }
     if (planes & 1u) {
         if (vec) {
             for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
@@ -670,6 +693,7 @@ __device__ void sort_window(RasterSmem &sm, uint32_t n)
 /* Rasterise the n staged (sorted) references.  The tile is cut into 16 regions of 16x16 pixels; a warp takes
  * the next unprocessed region from a shared counter and walks the whole window for it, so all fragments of a
  * pixel are produced by one warp in submission order while the regions balance the load between warps. */
+template <bool VIS>
 __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, int px0, int py0)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -704,15 +728,21 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 uint32_t r = sm.rec[base + k];
                 int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
                 int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
-                raster_triangle(b, sm, r, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
+                raster_triangle<VIS>(b, sm, r, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
                 __syncwarp();
             }
         }
-        if (pending) resolve_region(b, sm, rx0, ry0, px0, py0);
+        if (!VIS && pending) resolve_region(b, sm, rx0, ry0, px0, py0);
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes)
+/* VIS = true : K4a, the visibility pass.  Handles the tiles all of whose records are deferrable: resolves coverage,
+ *              stencil and depth in shared memory and leaves one record index per pixel for k_shade (K4b).  No colour
+ *              plane, no shading code: half the registers and less shared memory than the general kernel.
+ * VIS = false: the general kernel (in-order shading, blending, alpha test).  With only_flagged it handles just
+ *              the tiles that reference at least one non-deferrable record. */
+template <bool VIS>
+__global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t only_flagged)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem &sm = *reinterpret_cast<RasterSmem *>(smem_raw);
@@ -727,6 +757,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
     if (vw <= 0 || vh <= 0) return;
 
     const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
+    const uint32_t flagged = (b.tile_count && L) ? b.tile_flags[tile] : 0u;
+    if (VIS ? (flagged != 0) : (only_flagged && flagged == 0)) return;
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
     if (L == 0 && !clr_here) return;
 
@@ -734,7 +766,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
     if (threadIdx.x < NUM_REGIONS) sm.region_work[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < TILE_H * COLOR_PITCH; i += RASTER_THREADS) sm.vis[i] = VIS_NONE;
     /* shared-memory row 0 is framebuffer row py0 (the first row of the tile inside the band) */
-    tile_init(sm, fb, clr, planes, px0, py0, vw, vh);
+    tile_init<VIS>(sm, fb, clr, planes, px0, py0, vw, vh);
     __syncthreads();
 
     if (L > 0) {
@@ -751,7 +783,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
             }
             __syncthreads();
             sort_window(sm, L);
-            process_window(b, sm, L, px0, py0);
+            process_window<VIS>(b, sm, L, px0, py0);
         } else {
             /* Long list: take the references in windows of increasing id.  The upper id bound of a
              * window is found by bisection on the id value, counting with the whole CTA. */
@@ -793,7 +825,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
                 const uint32_t n = sm.count;
                 __syncthreads();
                 sort_window(sm, n);
-                process_window(b, sm, n, px0, py0);
+                process_window<VIS>(b, sm, n, px0, py0);
                 __syncthreads();
                 done += n;
                 lo = hi;
@@ -801,22 +833,92 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(BatchDev b, FrameT
         }
     }
     __syncthreads();
-    tile_store(sm, fb, planes, px0, py0, vw, vh);
+    tile_store<VIS>(sm, fb, planes, px0, py0, vw, vh, b.vis_plane);
 }
 
-void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, cudaStream_t s)
+/* K4b, the shade pass: one thread per pixel of the tiles handled by K4a.  A pixel with a visibility entry gets the
+ * colour of that fragment (same code as resolve_region); the colour part of the batch's leading clear is applied
+ * here as well.  Full occupancy, coalesced plane accesses, no ordering constraints left. */
+__global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
+{
+    __shared__ float un[256];
+    un[threadIdx.x] = b.unorm8[threadIdx.x];
+    __syncthreads();
+    const uint32_t band_px = (uint32_t)(fb.band_y1 - fb.band_y0) * (uint32_t)fb.width;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= band_px) return;
+    const int x = (int)(idx % (uint32_t)fb.width), y = fb.band_y0 + (int)(idx / (uint32_t)fb.width);
+    const int tx = x >> TILE_LOG, ty = y >> TILE_LOG;
+    const uint32_t tile = (uint32_t)((ty - fb.tile_y0) * fb.tiles_x + tx);
+    const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
+    if (L && b.tile_flags[tile]) return;                    /* the general kernel owns this tile */
+    /* same "does this tile have work" predicate as k_raster */
+    const int px0 = tx << TILE_LOG, py0 = max(ty << TILE_LOG, fb.band_y0);
+    const int vw = min(TILE_W, fb.width - px0), vh = min((ty << TILE_LOG) + TILE_H, fb.band_y1) - py0;
+    const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
+    if (L == 0 && !clr_here) return;
+    const size_t p = (size_t)y * fb.width + x;
+    bool write = false;
+    uint32_t out = 0;
+    if ((clr.mask & G_COLOR_BUFFER_BIT) && x >= clr.x0 && x < clr.x1 && y >= clr.y0 && y < clr.y1) { out = clr.color; write = true; }
+    const uint32_t r = L ? b.vis_plane[p] : VIS_NONE;
+    if (r != VIS_NONE) {
+        const TriRecord *rec = b.records + r;
+        const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+        const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+        const uint32_t state_flags = __ldg(&rec->state_flags);
+        const float fx0 = (float)row0.x, fy0 = (float)row0.y, fx1 = (float)row0.z, fy1 = (float)row0.w;
+        const float fx2 = (float)row1.x, fy2 = (float)row1.y;
+        const float inv_area = __int_as_float(row1.w);
+        const float px = (float)x, py = (float)y;
+        const float b0 = edge_at(fx1, fy1, fx2, fy2, px, py) * inv_area;
+        const float b1 = edge_at(fx2, fy2, fx0, fy0, px, py) * inv_area;
+        const float b2 = edge_at(fx0, fy0, fx1, fy1, px, py) * inv_area;
+        const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
+        TriAttr A;
+        load_attr(A, rec);
+        Color4 c;
+        shade_color(b, un, r, state_flags, A, cfg, b0, b1, b2, c);
+        out = color_pack(color_clamp(c));       /* raster.c:719-721 */
+        write = true;
+    }
+    if (write) fb.color[p] = out;
+}
+
+void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes,
+                   bool any_deferrable, bool any_in_order, cudaStream_t s)
 {
     static bool configured[64] = { false };
     int dev = 0;
     cudaGetDevice(&dev);
+    const size_t smem_vis = offsetof(RasterSmem, color);
     if (dev >= 0 && dev < 64 && !configured[dev]) {      /* the opt-in is per device */
-        cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
+        cudaFuncSetAttribute(k_raster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
+        cudaFuncSetAttribute(k_raster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vis);
         configured[dev] = true;
     }
     uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0 || planes == 0) return;
-    k_raster<<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes);
-    note_launch();
+    /* Split path: tiles whose records are all deferrable go through K4a (visibility) + K4b (shade); tiles with an
+     * in-order record go through the general kernel.  A pass without deferrable draws uses the general kernel alone
+     * (it then also owns the tiles that only need clearing). */
+    const bool split = any_deferrable && b.tile_count != nullptr && b.vis_plane != nullptr;
+    if (split) {
+        k_raster<true><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
+        note_launch();
+        if (planes & 1u) {
+            const uint32_t band_px = (uint32_t)(fb.band_y1 - fb.band_y0) * (uint32_t)fb.width;
+            k_shade<<<(band_px + 255) / 256, 256, 0, s>>>(b, fb, clear);
+            note_launch();
+        }
+        if (any_in_order) {
+            k_raster<false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u);
+            note_launch();
+        }
+    } else {
+        k_raster<false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
+        note_launch();
+    }
 }
 
 } // namespace mtgl_dev_impl

@@ -183,7 +183,7 @@ __device__ bool setup_subtri(const mtgl_state *st, const RasterCfg *cfg, const F
     if (!rec) return true;
 
     rec->x0 = x0; rec->y0 = y0; rec->x1 = x1; rec->y1 = y1; rec->x2 = x2; rec->y2 = y2;
-    rec->state_flags = state_index | (back ? 0x80000000u : 0u);
+    rec->state_flags = state_index | (back ? STATE_BACK_BIT : 0u) | ((cfg->flags & RC_DEFER) ? STATE_DEFER_BIT : 0u);
     rec->bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
     rec->bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
     rec->z0 = a.z; rec->z1 = b.z; rec->z2 = c.z;

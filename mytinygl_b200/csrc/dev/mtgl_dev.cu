@@ -52,7 +52,7 @@ struct mtgl_dev {
     float *unorm8 = nullptr;
 
     DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list;
-    DevBuf tile_count, tile_offset, tile_cursor, tile_list;
+    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_list, vis_plane;
     DevCounters *counters = nullptr;
     DevCounters *h_counters = nullptr;      /* pinned */
 
@@ -131,15 +131,19 @@ void build_cfg(const mtgl_dev *d, const mtgl_state &s, RasterCfg &c)
     if (s.light_model_two_side) f |= RC_TWO_SIDE;
     if (s.perspective_hint != G_FASTEST) f |= RC_PERSPECTIVE;
     if (s.depth_near == 0.0 && s.depth_far == 1.0) f |= RC_DEPTH_RANGE_01;
+    bool textured = false;
     /* raster.c:495-498, 618: texturing needs the cap, a bound texture and an uploaded image */
     if ((s.caps & MTGL_CAP_TEXTURE_2D) && s.texture_id != 0 && s.texture_id < kMaxObjects && d->tex[s.texture_id].l0) {
         const TexObj &t = d->tex[s.texture_id];
         f |= RC_TEXTURED;
+        textured = true;
         c.tex_l0 = t.l0; c.tex_l1 = t.l1;
         c.tex_w = t.w; c.tex_h = t.h; c.tex_w1 = t.w1; c.tex_h1 = t.h1;
         c.tex_min = s.tex_min_filter; c.tex_mag = s.tex_mag_filter;
         c.tex_wrap_s = s.tex_wrap_s; c.tex_wrap_t = s.tex_wrap_t;
     }
+    /* raster.c:640-643 / 712-721: the alpha test (textured only), blending and partial colour masks need in-order shading */
+    if (!(s.caps & MTGL_CAP_BLEND) && !((s.caps & MTGL_CAP_ALPHA_TEST) && textured) && (s.color_mask & 0xFu) == 0xFu) f |= RC_DEFER;
     c.flags = f;
     c.depth_func = s.depth_func - G_NEVER; c.alpha_func = s.alpha_func - G_NEVER; c.stencil_func = s.stencil_func - G_NEVER;
     c.stencil_fail = s.stencil_fail; c.stencil_zfail = s.stencil_zfail; c.stencil_zpass = s.stencil_zpass;
@@ -237,7 +241,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     }
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
-                       &d->chunk_base, &d->large_list, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_list };
+                       &d->chunk_base, &d->large_list, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_list, &d->vis_plane };
     for (DevBuf *b : bufs) release(*b);
     if (d->color) cudaFree(d->color);
     if (d->depth) cudaFree(d->depth);
@@ -528,7 +532,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if (need_eye && (rc = reserve(d, d->rec_eye, rec_cap * sizeof(TriEye)))) return rc;
             if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4))) return rc;
             if ((rc = reserve(d, d->tile_count, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_offset, (size_t)ntiles * 4)) ||
-                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4))) return rc;
+                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_flags, (size_t)ntiles * 4))) return rc;
+            if ((rc = reserve(d, d->vis_plane, (size_t)d->width * d->height * 4))) return rc;
             b.v_clip = (float4 *)d->v_clip.ptr; b.v_color = (float4 *)d->v_color.ptr; b.v_tex = (float4 *)d->v_tex.ptr;
             b.v_epos = (float4 *)d->v_epos.ptr; b.v_enrm = (float4 *)d->v_enrm.ptr;
             b.records = (TriRecord *)d->records.ptr; b.rec_eye = (TriEye *)d->rec_eye.ptr;
@@ -536,9 +541,12 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.chunk_base = (uint32_t *)d->chunk_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
             b.tile_count = (uint32_t *)d->tile_count.ptr; b.tile_offset = (uint32_t *)d->tile_offset.ptr;
             b.tile_cursor = (uint32_t *)d->tile_cursor.ptr;
+            b.tile_flags = (uint32_t *)d->tile_flags.ptr;
+            b.vis_plane = (uint32_t *)d->vis_plane.ptr;
 
             CU(cudaMemsetAsync(d->counters, 0, sizeof(DevCounters), d->stream));
             CU(cudaMemsetAsync(b.tile_count, 0, (size_t)ntiles * 4, d->stream));
+            CU(cudaMemsetAsync(b.tile_flags, 0, (size_t)ntiles * 4, d->stream));
             launch_vertex_stage(b, d->stream);
             CU(cudaEventRecord(sev[1], d->stream));
             launch_setup(b, fb, d->stream);
@@ -562,7 +570,11 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             CU(cudaEventRecord(sev[3], d->stream));
         }
         CU(cudaEventRecord(sev[4], d->stream));
-        launch_raster(b, fb, clr, planes, d->stream);
+        bool any_defer = false, any_in_order = false;
+        for (const PassDraw &q : passes[pidx]) {
+            if (cfgs[bt->draws[q.draw].raster_state].flags & RC_DEFER) any_defer = true; else any_in_order = true;
+        }
+        launch_raster(b, fb, clr, planes, any_defer && pi.n_triangles > 0, any_in_order, d->stream);
         CU(cudaEventRecord(sev[5], d->stream));
     }
     CU(cudaEventRecord(d->ev_stop, d->stream));
