@@ -400,24 +400,46 @@ __device__ __noinline__ void shade_now(const BatchDev &b, RasterSmem &sm, uint32
 }
 
 /* ---------------------------------------------------------------- one triangle over one warp region */
+/* the part of a record the coverage / depth stage needs (rows 0, 1, state word of row 2, z of row 3) */
+struct TriHead {
+    int4 row0, row1;
+    uint32_t state_flags;
+    float z0, z1, z2;
+};
+
+__device__ __forceinline__ void load_head(TriHead &h, const TriRecord *rec)
+{
+    h.row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+    h.row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+    h.state_flags = __ldg(&rec->state_flags);
+    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
+    h.z0 = row3.x; h.z1 = row3.y; h.z2 = row3.z;
+}
+
+__device__ __forceinline__ TriHead broadcast_head(const TriHead &h, int src)
+{
+    TriHead o;
+    o.row0.x = __shfl_sync(0xFFFFFFFFu, h.row0.x, src); o.row0.y = __shfl_sync(0xFFFFFFFFu, h.row0.y, src);
+    o.row0.z = __shfl_sync(0xFFFFFFFFu, h.row0.z, src); o.row0.w = __shfl_sync(0xFFFFFFFFu, h.row0.w, src);
+    o.row1.x = __shfl_sync(0xFFFFFFFFu, h.row1.x, src); o.row1.y = __shfl_sync(0xFFFFFFFFu, h.row1.y, src);
+    o.row1.z = __shfl_sync(0xFFFFFFFFu, h.row1.z, src); o.row1.w = __shfl_sync(0xFFFFFFFFu, h.row1.w, src);
+    o.state_flags = __shfl_sync(0xFFFFFFFFu, h.state_flags, src);
+    o.z0 = __shfl_sync(0xFFFFFFFFu, h.z0, src); o.z1 = __shfl_sync(0xFFFFFFFFu, h.z1, src); o.z2 = __shfl_sync(0xFFFFFFFFu, h.z2, src);
+    return o;
+}
+
 template <bool VIS>
-__device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, int tile_px, int tile_py,
+__device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, const TriHead &h, int tile_px, int tile_py,
                                 int X0, int Y0, int X1, int Y1, int rx0, int ry0, bool &pending)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const TriRecord *rec = b.records + r;
-    const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
-    const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
-    const uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(rec) + 2);
-    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
-
-    const float fx0 = (float)row0.x, fy0 = (float)row0.y, fx1 = (float)row0.z, fy1 = (float)row0.w;
-    const float fx2 = (float)row1.x, fy2 = (float)row1.y;
-    const float area = __int_as_float(row1.z), inv_area = __int_as_float(row1.w);
-    const uint32_t state_flags = row2.z;
+    const float fx0 = (float)h.row0.x, fy0 = (float)h.row0.y, fx1 = (float)h.row0.z, fy1 = (float)h.row0.w;
+    const float fx2 = (float)h.row1.x, fy2 = (float)h.row1.y;
+    const float area = __int_as_float(h.row1.z), inv_area = __int_as_float(h.row1.w);
+    const uint32_t state_flags = h.state_flags;
     const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
     const uint32_t flags = cfg->flags;
-    const float z0 = row3.x, z1 = row3.y, z2 = row3.z;
+    const float z0 = h.z0, z1 = h.z1, z2 = h.z2;
     const bool area_pos = area > 0;
     /* shading can be deferred when nothing between the depth test and the colour write depends on or discards
      * per fragment state: no blending, no alpha test, full colour mask (RC_DEFER, mirrored in the record).
@@ -714,12 +736,12 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 box = sm.box[e];
                 int x0 = box & 0xFF, y0 = (box >> 8) & 0xFF, x1 = (box >> 16) & 0xFF, y1 = box >> 24;
                 hit = !(x1 < rx0 || x0 > rx1 || y1 < ry0 || y0 > ry1);
-                if (hit) {      /* pull the record towards this SM while earlier hits are being rasterised */
-                    const char *p = reinterpret_cast<const char *>(b.records + sm.rec[e]);
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 128));
-                }
             }
+            /* every lane with a hit fetches the head of its own record: up to 32 record fetches in flight at once,
+             * handed to the whole warp by shuffles when the hit's turn comes */
+            TriHead mine;
+            if (hit) load_head(mine, b.records + sm.rec[e]);
+            else { mine.row0 = make_int4(0, 0, 0, 0); mine.row1 = make_int4(0, 0, 0, 0); mine.state_flags = 0; mine.z0 = mine.z1 = mine.z2 = 0.0f; }
             uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
             while (mask) {
                 int k = __ffs(mask) - 1;
@@ -728,7 +750,8 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 uint32_t r = sm.rec[base + k];
                 int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
                 int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
-                raster_triangle<VIS>(b, sm, r, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
+                const TriHead h = broadcast_head(mine, k);
+                raster_triangle<VIS>(b, sm, r, h, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
                 __syncwarp();
             }
         }
@@ -836,33 +859,63 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
     tile_store<VIS>(sm, fb, planes, px0, py0, vw, vh, b.vis_plane);
 }
 
-/* K4b, the shade pass: one thread per pixel of the tiles handled by K4a.  A pixel with a visibility entry gets the
- * colour of that fragment (same code as resolve_region); the colour part of the batch's leading clear is applied
- * here as well.  Full occupancy, coalesced plane accesses, no ordering constraints left. */
+/* K4b, the shade pass: one CTA per tile handled by K4a.  The tile's pixels that carry a visibility entry are
+ * first compacted into a list (ballot + prefix), then shaded 256 at a time with every lane busy -- same colour
+ * code as resolve_region.  The colour part of the batch's leading clear is applied here as well.  Full occupancy,
+ * coalesced plane accesses, no ordering constraints left. */
 __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
 {
     __shared__ float un[256];
+    __shared__ uint16_t list[TILE_W * TILE_H];
+    __shared__ uint32_t warp_total[8];
+    __shared__ uint32_t list_n;
     un[threadIdx.x] = b.unorm8[threadIdx.x];
-    __syncthreads();
-    const uint32_t band_px = (uint32_t)(fb.band_y1 - fb.band_y0) * (uint32_t)fb.width;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= band_px) return;
-    const int x = (int)(idx % (uint32_t)fb.width), y = fb.band_y0 + (int)(idx / (uint32_t)fb.width);
-    const int tx = x >> TILE_LOG, ty = y >> TILE_LOG;
-    const uint32_t tile = (uint32_t)((ty - fb.tile_y0) * fb.tiles_x + tx);
-    const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
-    if (L && b.tile_flags[tile]) return;                    /* the general kernel owns this tile */
-    /* same "does this tile have work" predicate as k_raster */
+
+    const uint32_t tile = blockIdx.x;
+    const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
     const int px0 = tx << TILE_LOG, py0 = max(ty << TILE_LOG, fb.band_y0);
     const int vw = min(TILE_W, fb.width - px0), vh = min((ty << TILE_LOG) + TILE_H, fb.band_y1) - py0;
-    const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
+    if (vw <= 0 || vh <= 0) return;
+    const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
+    if (L && b.tile_flags[tile]) return;                    /* the general kernel owns this tile */
+    const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
-    const size_t p = (size_t)y * fb.width + x;
-    bool write = false;
-    uint32_t out = 0;
-    if ((clr.mask & G_COLOR_BUFFER_BIT) && x >= clr.x0 && x < clr.x1 && y >= clr.y0 && y < clr.y1) { out = clr.color; write = true; }
-    const uint32_t r = L ? b.vis_plane[p] : VIS_NONE;
-    if (r != VIS_NONE) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    /* pass 1: colour clear + compaction of the pixels to shade (64 pixels x 4 rows per iteration, coalesced) */
+    uint32_t n_before = 0;
+    if (threadIdx.x == 0) list_n = 0;
+    __syncthreads();
+    for (int row0 = 0; row0 < vh; row0 += 4) {
+        const int x = (int)(threadIdx.x & 63), y = row0 + (int)(threadIdx.x >> 6);
+        const bool in = x < vw && y < vh;
+        const size_t p = (size_t)(py0 + y) * fb.width + px0 + x;
+        bool has = false;
+        if (in) {
+            has = L && b.vis_plane[p] != VIS_NONE;
+            if (!has && (clr.mask & G_COLOR_BUFFER_BIT) && px0 + x >= clr.x0 && px0 + x < clr.x1 && py0 + y >= clr.y0 && py0 + y < clr.y1)
+                fb.color[p] = clr.color;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+        if (lane == 0) warp_total[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = n_before;
+        for (uint32_t w = 0; w < warp; w++) before += warp_total[w];
+        if (has) list[before + __popc(m & lt_mask)] = (uint16_t)(y * TILE_W + x);
+        uint32_t total = 0;
+        for (int w = 0; w < 8; w++) total += warp_total[w];
+        n_before += total;
+        __syncthreads();
+    }
+    const uint32_t n = n_before;
+
+    /* pass 2: shade the compacted pixels */
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        const int lx = list[i] % TILE_W, ly = list[i] / TILE_W;
+        const int x = px0 + lx, y = py0 + ly;
+        const size_t p = (size_t)y * fb.width + x;
+        const uint32_t r = b.vis_plane[p];
         const TriRecord *rec = b.records + r;
         const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
         const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
@@ -879,10 +932,8 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
         load_attr(A, rec);
         Color4 c;
         shade_color(b, un, r, state_flags, A, cfg, b0, b1, b2, c);
-        out = color_pack(color_clamp(c));       /* raster.c:719-721 */
-        write = true;
+        fb.color[p] = color_pack(color_clamp(c));       /* raster.c:719-721 */
     }
-    if (write) fb.color[p] = out;
 }
 
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes,
@@ -907,8 +958,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         k_raster<true><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
         note_launch();
         if (planes & 1u) {
-            const uint32_t band_px = (uint32_t)(fb.band_y1 - fb.band_y0) * (uint32_t)fb.width;
-            k_shade<<<(band_px + 255) / 256, 256, 0, s>>>(b, fb, clear);
+            k_shade<<<tiles, 256, 0, s>>>(b, fb, clear);
             note_launch();
         }
         if (any_in_order) {
