@@ -48,6 +48,7 @@ struct RasterSmem {
     };
     uint32_t rec[LIST_WINDOW];
     uint32_t box[LIST_WINDOW];
+    uint16_t pos[LIST_WINDOW];          /* sort payload: original position of the key */
     float unorm8[256];
     uint32_t count;
     uint32_t next_region;       /* dynamic region scheduler of the current window */
@@ -676,12 +677,13 @@ __device__ __forceinline__ void account_regions(RasterSmem &sm, uint32_t box)
         }
 }
 
-/* bitonic sort of (key, rec, box) triples by key; n padded to a power of two with key = ~0 */
+/* sort the staged (key, rec, box) triples by key; n is padded to a power of two with key = ~0 */
 __device__ void sort_window(RasterSmem &sm, uint32_t n)
 {
     uint32_t p = 32;
     while (p < n) p <<= 1;
     for (uint32_t i = n + threadIdx.x; i < p; i += RASTER_THREADS) sm.key[i] = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < p; i += RASTER_THREADS) sm.pos[i] = (uint16_t)i;
     if (threadIdx.x == 0) sm.next_region = 0;
     if (threadIdx.x < NUM_REGIONS) {        /* longest-processing-time-first order of the regions */
         const uint32_t mine = sm.region_work[threadIdx.x];
@@ -694,22 +696,48 @@ __device__ void sort_window(RasterSmem &sm, uint32_t n)
     }
     __syncthreads();
     if (threadIdx.x < NUM_REGIONS) sm.region_work[threadIdx.x] = 0;
-    for (uint32_t k = 2; k <= p; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < p; i += RASTER_THREADS) {
-                uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    uint32_t a = sm.key[i], c = sm.key[ixj];
-                    bool up = ((i & k) == 0);
-                    if ((a > c) == up) {
-                        sm.key[i] = c; sm.key[ixj] = a;
-                        uint32_t t = sm.rec[i]; sm.rec[i] = sm.rec[ixj]; sm.rec[ixj] = t;
-                        t = sm.box[i]; sm.box[i] = sm.box[ixj]; sm.box[ixj] = t;
-                    }
-                }
+    /* Bitonic sort of (key, original position).  Exchanges at distance >= 32 use the whole CTA and a barrier;
+     * the runs of exchanges at distance 16..1 stay inside one aligned group of 32 elements, which a single warp
+     * owns, so they only need warp-level synchronisation.  rec/box are permuted once at the end. */
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto exchange = [&](uint32_t i, uint32_t j, uint32_t k) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+            const uint32_t a = sm.key[i], c = sm.key[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > c) == up) {
+                sm.key[i] = c; sm.key[ixj] = a;
+                const uint16_t t = sm.pos[i]; sm.pos[i] = sm.pos[ixj]; sm.pos[ixj] = t;
             }
+        }
+    };
+    for (uint32_t k = 2; k <= p; k <<= 1) {
+        uint32_t j = k >> 1;
+        for (; j >= 32; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < p; i += RASTER_THREADS) exchange(i, j, k);
             __syncthreads();
         }
+        for (uint32_t base = warp * 32; base < p; base += RASTER_THREADS) {
+            for (uint32_t jj = j; jj > 0; jj >>= 1) {
+                exchange(base + lane, jj, k);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    uint32_t tr[LIST_WINDOW / RASTER_THREADS], tb[LIST_WINDOW / RASTER_THREADS];
+#pragma unroll
+    for (int q = 0; q < LIST_WINDOW / RASTER_THREADS; q++) {
+        const uint32_t i = threadIdx.x + (uint32_t)q * RASTER_THREADS;
+        if (i < n) { const uint32_t from = sm.pos[i]; tr[q] = sm.rec[from]; tb[q] = sm.box[from]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < LIST_WINDOW / RASTER_THREADS; q++) {
+        const uint32_t i = threadIdx.x + (uint32_t)q * RASTER_THREADS;
+        if (i < n) { sm.rec[i] = tr[q]; sm.box[i] = tb[q]; }
+    }
+    __syncthreads();
 }
 
 /* Rasterise the n staged (sorted) references.  The tile is cut into 16 regions of 16x16 pixels; a warp takes
@@ -740,8 +768,10 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
             /* every lane with a hit fetches the head of its own record: up to 32 record fetches in flight at once,
              * handed to the whole warp by shuffles when the hit's turn comes */
             TriHead mine;
-            if (hit) load_head(mine, b.records + sm.rec[e]);
-            else { mine.row0 = make_int4(0, 0, 0, 0); mine.row1 = make_int4(0, 0, 0, 0); mine.state_flags = 0; mine.z0 = mine.z1 = mine.z2 = 0.0f; }
+            if (VIS) {      /* (the general kernel is register-bound: it loads the head uniformly when the hit's turn comes) */
+                if (hit) load_head(mine, b.records + sm.rec[e]);
+                else { mine.row0 = make_int4(0, 0, 0, 0); mine.row1 = make_int4(0, 0, 0, 0); mine.state_flags = 0; mine.z0 = mine.z1 = mine.z2 = 0.0f; }
+            }
             uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
             while (mask) {
                 int k = __ffs(mask) - 1;
@@ -750,7 +780,9 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 uint32_t r = sm.rec[base + k];
                 int X0 = max((int)(bx & 0xFF), rx0), Y0 = max((int)((bx >> 8) & 0xFF), ry0);
                 int X1 = min((int)((bx >> 16) & 0xFF), rx1), Y1 = min((int)(bx >> 24), ry1);
-                const TriHead h = broadcast_head(mine, k);
+                TriHead h;
+                if (VIS) h = broadcast_head(mine, k);
+                else load_head(h, b.records + r);
                 raster_triangle<VIS>(b, sm, r, h, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
                 __syncwarp();
             }
