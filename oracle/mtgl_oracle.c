@@ -751,6 +751,217 @@ static void to_screen(const mtgl_state *st, float x, float y, int32_t *sx, int32
     *sy = (int32_t)((1.0f - y) * 0.5f * st->viewport[3] + st->viewport[1]);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* points and lines (raster.c:65-296, 776-898, 1019-1196; clipping.h:128-229)                  */
+/* ------------------------------------------------------------------------------------------ */
+static sampler bound_sampler(const mtgl_dev *dev, const mtgl_state *st, int *textured)
+{
+    sampler smp;
+    memset(&smp, 0, sizeof smp);
+    *textured = 0;
+    if ((st->caps & MTGL_CAP_TEXTURE_2D) && st->texture_id != 0 && st->texture_id < O_MAX_OBJECTS && dev->tex[st->texture_id].px) {
+        const otex *t = &dev->tex[st->texture_id];
+        smp.px = t->px; smp.w = t->w; smp.h = t->h; smp.px1 = t->px1; smp.w1 = t->w1; smp.h1 = t->h1;
+        smp.min_f = st->tex_min_filter; smp.mag_f = st->tex_mag_filter; smp.wrap_s = st->tex_wrap_s; smp.wrap_t = st->tex_wrap_t;
+        *textured = 1;
+    }
+    return smp;
+}
+
+/* depth test, blend, depth write, masked colour write of one line / point pixel: write_line_pixel (raster.c:66-104)
+ * and the pixel loops of flush_points (1123-1161) / draw_point_at_screen (795-843).  No stencil on these paths. */
+static void put_simple_pixel(mtgl_dev *dev, const mtgl_state *st, int32_t px, int32_t py, float depth, col4 c)
+{
+    if (px < 0 || px >= dev->width || py < 0 || py >= dev->height) return;
+    if (py < dev->band_y0 || py >= dev->band_y1) return;
+    if (st->caps & MTGL_CAP_SCISSOR_TEST) {
+        if (px < st->scissor[0] || px >= st->scissor[0] + st->scissor[2] || py < st->scissor[1] || py >= st->scissor[1] + st->scissor[3]) return;
+    }
+    size_t idx = (size_t)py * dev->width + px;
+    int depth_on = (st->caps & MTGL_CAP_DEPTH_TEST) != 0;
+    if (depth_on && !cmp_f(st->depth_func, depth, dev->depth[idx])) return;
+    dev->frag_tested++;
+    if (st->caps & MTGL_CAP_BLEND) {
+        col4 d = col_unpack(dev->color[idx]);
+        col4 sf = blend_factor(st->blend_src, c, d), df = blend_factor(st->blend_dst, c, d);
+        col4 o = { c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a };
+        c = col_clamp(o);
+    }
+    if (depth_on && st->depth_mask) dev->depth[idx] = depth;
+    dev->frag_shaded++;
+    put_color_masked(dev, st, px, py, c);
+}
+
+static float simple_depth(const mtgl_state *st, float z) /* raster.c:161, 793, 1065 */
+{
+    return (float)((z + 1.0f) * 0.5f * (st->depth_far - st->depth_near) + st->depth_near);
+}
+
+/* fog for lines and points: the coordinate is NEGATED once more (raster.c:189, 809, 1093) */
+static col4 simple_fog(const mtgl_state *st, col4 c, float eye_z)
+{
+    if (!(st->caps & MTGL_CAP_FOG)) return c;
+    float fc = -eye_z, f = 1.0f;
+    switch (st->fog_mode) {
+    case T_LINEAR_FOG: if (st->fog_end != st->fog_start) f = (st->fog_end - fc) / (st->fog_end - st->fog_start); break;
+    case T_EXP: f = expf(-st->fog_density * fc); break;
+    case T_EXP2: { float d = st->fog_density * fc; f = expf(-d * d); break; }
+    default: break;
+    }
+    if (f < 0.0f) f = 0.0f;
+    if (f > 1.0f) f = 1.0f;
+    return col_lerp_rgb(col_from(st->fog_color), c, f);
+}
+
+/* draw_line_full (raster.c:107-241).  One deliberate deviation: when the alpha test rejects a pixel the reference
+ * executes `continue` inside `for (;;)` and never advances (an infinite loop); here the pixel is
+ * skipped and the walk goes on. */
+static void draw_line(mtgl_dev *dev, const mtgl_state *st, int32_t x0, int32_t y0, float z0, int32_t x1, int32_t y1, float z1,
+                      col4 c0, col4 c1, float ez0, float ez1, const float *uv0, const float *uv1)
+{
+    int32_t dx = x1 - x0, dy = y1 - y0;
+    int32_t adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+    int32_t sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+    int32_t err = adx - ady;
+    int32_t total = (adx > ady) ? adx : ady;
+    if (total == 0) total = 1;
+    int32_t step = 0;
+    int lw = (int)(st->line_width + 0.5f);
+    if (lw < 1) lw = 1;
+    int half = lw / 2;
+    int ex = (adx > ady) ? 0 : 1, ey = (adx > ady) ? 1 : 0;
+    int textured;
+    sampler smp = bound_sampler(dev, st, &textured);
+    int32_t cx = x0, cy = y0;
+    for (;;) {
+        float t = (float)step / (float)total;
+        float z = z0 + t * (z1 - z0);
+        float depth = simple_depth(st, z);
+        col4 c = col_lerp(c0, c1, t);
+        int keep = 1;
+        if (textured) {
+            float u = uv0[0] + t * (uv1[0] - uv0[0]), v = uv0[1] + t * (uv1[1] - uv0[1]);
+            col4 tc = col_unpack(sample_lod(&smp, u, v, 0.0f));
+            if ((st->caps & MTGL_CAP_ALPHA_TEST) && !cmp_f(st->alpha_func, tc.a, st->alpha_ref)) keep = 0;
+            else { col4 o = { c.r * tc.r, c.g * tc.g, c.b * tc.b, c.a * tc.a }; c = o; }
+        } else if ((st->caps & MTGL_CAP_ALPHA_TEST) && !cmp_f(st->alpha_func, c.a, st->alpha_ref)) keep = 0;
+        if (keep) {
+            c = simple_fog(st, c, ez0 + t * (ez1 - ez0));
+            dev->frag_covered += (uint64_t)lw;
+            if (lw == 1) put_simple_pixel(dev, st, cx, cy, depth, c);
+            else for (int w = -half; w < lw - half; w++) put_simple_pixel(dev, st, cx + w * ex, cy + w * ey, depth, c);
+        }
+        if (cx == x1 && cy == y1) break;
+        int32_t e2 = err * 2;
+        if (e2 > -ady) { err -= ady; cx += sx; }
+        if (e2 < adx) { err += adx; cy += sy; }
+        step++;
+    }
+}
+
+static int outcode(const float *p) /* clipping.h:138-148 */
+{
+    int c = 0;
+    if (p[0] < -p[3]) c |= 1; else if (p[0] > p[3]) c |= 2;
+    if (p[1] < -p[3]) c |= 4; else if (p[1] > p[3]) c |= 8;
+    if (p[2] < -p[3]) c |= 16; else if (p[2] > p[3]) c |= 32;
+    return c;
+}
+
+static int clip_segment(overt *v0, overt *v1) /* clip_line, clipping.h:152-229 (Cohen-Sutherland with snap) */
+{
+    int c0 = outcode(v0->pos), c1 = outcode(v1->pos);
+    for (;;) {
+        if (!(c0 | c1)) return 1;
+        if (c0 & c1) return 0;
+        int co = c0 ? c0 : c1;
+        const float *p0 = v0->pos, *p1 = v1->pos;
+        float d0, d1;
+        int plane;
+        if (co & 1) { d0 = p0[0] + p0[3]; d1 = p1[0] + p1[3]; plane = 2; }
+        else if (co & 2) { d0 = p0[3] - p0[0]; d1 = p1[3] - p1[0]; plane = 3; }
+        else if (co & 4) { d0 = p0[1] + p0[3]; d1 = p1[1] + p1[3]; plane = 4; }
+        else if (co & 8) { d0 = p0[3] - p0[1]; d1 = p1[3] - p1[1]; plane = 5; }
+        else if (co & 16) { d0 = p0[2] + p0[3]; d1 = p1[2] + p1[3]; plane = 0; }
+        else { d0 = p0[3] - p0[2]; d1 = p1[3] - p1[2]; plane = 1; }
+        float den = d0 - d1;
+        if (fabsf(den) < 1e-10f) return 0;
+        overt cl = vert_lerp(v0, v1, d0 / den);
+        plane_snap(cl.pos, plane);
+        if (co == c0) { *v0 = cl; c0 = outcode(v0->pos); }
+        else { *v1 = cl; c1 = outcode(v1->pos); }
+    }
+}
+
+static void line_segment(mtgl_dev *dev, const mtgl_state *st, const overt *a, const overt *b) /* draw_line_segment, raster.c:244-285 */
+{
+    overt v0 = *a, v1 = *b;
+    if (!clip_segment(&v0, &v1)) return;
+    float z0, z1;
+    if (fabsf(v0.pos[3]) >= 1e-6f) { float iw = 1.0f / v0.pos[3]; v0.pos[0] *= iw; v0.pos[1] *= iw; z0 = v0.pos[2] * iw; }
+    else { v0.pos[0] = 0.0f; v0.pos[1] = 0.0f; z0 = 0.0f; }
+    if (fabsf(v1.pos[3]) >= 1e-6f) { float iw = 1.0f / v1.pos[3]; v1.pos[0] *= iw; v1.pos[1] *= iw; z1 = v1.pos[2] * iw; }
+    else { v1.pos[0] = 0.0f; v1.pos[1] = 0.0f; z1 = 0.0f; }
+    int32_t x0, y0, x1, y1;
+    to_screen(st, v0.pos[0], v0.pos[1], &x0, &y0);
+    to_screen(st, v1.pos[0], v1.pos[1], &x1, &y1);
+    draw_line(dev, st, x0, y0, z0, x1, y1, z1, v0.color, v1.color, v0.eye_z, v1.eye_z, v0.uv, v1.uv);
+}
+
+static void points(mtgl_dev *dev, const mtgl_state *st, const overt *v, uint32_t n) /* flush_points, raster.c:1020-1164 */
+{
+    int ps = (int)(st->point_size + 0.5f);
+    if (ps < 1) ps = 1;
+    int half = ps / 2;
+    int textured;
+    sampler smp = bound_sampler(dev, st, &textured);
+    for (uint32_t i = 0; i < n; i++) {
+        const float *p = v[i].pos;
+        if (p[0] < -p[3] || p[0] > p[3] || p[1] < -p[3] || p[1] > p[3] || p[2] < -p[3] || p[2] > p[3] || p[3] <= 0.0f) continue;
+        float nx = p[0] / p[3], ny = p[1] / p[3], nz = p[2] / p[3];
+        int32_t cx, cy;
+        to_screen(st, nx, ny, &cx, &cy);
+        float depth = simple_depth(st, nz);
+        col4 c = v[i].color;
+        if (textured) {
+            col4 tc = col_unpack(sample_lod(&smp, v[i].uv[0], v[i].uv[1], 0.0f));
+            if ((st->caps & MTGL_CAP_ALPHA_TEST) && !cmp_f(st->alpha_func, tc.a, st->alpha_ref)) continue;
+            col4 o = { c.r * tc.r, c.g * tc.g, c.b * tc.b, c.a * tc.a };
+            c = o;
+        } else if ((st->caps & MTGL_CAP_ALPHA_TEST) && !cmp_f(st->alpha_func, c.a, st->alpha_ref)) continue;
+        c = simple_fog(st, c, v[i].eye_z);
+        dev->frag_covered += (uint64_t)ps * ps;
+        for (int py = cy - half; py < cy - half + ps; py++)
+            for (int px = cx - half; px < cx - half + ps; px++) put_simple_pixel(dev, st, px, py, depth, c);
+    }
+}
+
+/* polygon modes GL_LINE / GL_POINT (draw_triangle_wireframe / draw_triangle_points, raster.c:847-898) */
+static void triangle_outline(mtgl_dev *dev, const mtgl_state *st, const overt *c0, const overt *c1, const overt *c2,
+                             const int32_t *sx, const int32_t *sy, int as_points)
+{
+    col4 col[3] = { c0->color, c1->color, c2->color };
+    const overt *cv[3] = { c0, c1, c2 };
+    if ((st->caps & MTGL_CAP_LIGHTING) && st->shade_model == T_PHONG)
+        for (int k = 0; k < 3; k++) col[k] = light_vertex(st, cv[k]->eye_pos, cv[k]->eye_nrm, &st->material_front);
+    if (as_points) {
+        for (int k = 0; k < 3; k++) {   /* draw_point_at_screen, raster.c:777-844: depth test before the alpha test, vertex alpha */
+            if ((st->caps & MTGL_CAP_ALPHA_TEST) && !cmp_f(st->alpha_func, col[k].a, st->alpha_ref)) {
+                /* the reference tests depth first, but neither test has side effects before the writes */
+                continue;
+            }
+            dev->frag_covered++;
+            put_simple_pixel(dev, st, sx[k], sy[k], simple_depth(st, cv[k]->pos[2]), simple_fog(st, col[k], cv[k]->eye_z));
+        }
+        return;
+    }
+    for (int k = 0; k < 3; k++) {
+        int n = (k + 1) % 3;
+        draw_line(dev, st, sx[k], sy[k], cv[k]->pos[2], sx[n], sy[n], cv[n]->pos[2], col[k], col[n], cv[k]->eye_z, cv[n]->eye_z,
+                  cv[k]->uv, cv[n]->uv);
+    }
+}
+
 static void render_triangle(mtgl_dev *dev, const mtgl_state *st, const overt *a, const overt *b, const overt *c)
 {
     overt t1[O_MAX_CLIP], t2[O_MAX_CLIP];
@@ -785,7 +996,7 @@ static void render_triangle(mtgl_dev *dev, const mtgl_state *st, const overt *a,
         }
         int back = (st->front_face == T_CCW) ? (sa >= 0) : (sa < 0);
         uint32_t pm = back ? st->polygon_mode_back : st->polygon_mode_front;
-        if (pm == T_POINT || pm == T_LINE) continue; /* TODO(next): wireframe / point polygon modes */
+        if (pm == T_POINT || pm == T_LINE) { triangle_outline(dev, st, &cl[0], &cl[j], &cl[j + 1], sx, sy, pm == T_POINT); continue; }
         dev->stats.triangles_setup++;
         raster_triangle(dev, st, &cl[0], &cl[j], &cl[j + 1], sx, sy, back);
     }
@@ -821,7 +1032,19 @@ static void assemble(mtgl_dev *dev, const mtgl_state *st, uint32_t mode, const o
             render_triangle(dev, st, &v[i], &v[i + 3], &v[i + 2]);
         }
         break;
-    default: /* TODO(next): points and lines */
+    case T_POINTS:
+        points(dev, st, v, n);
+        break;
+    case T_LINES:                               /* raster.c:288-296 */
+        for (uint32_t i = 0; i + 1 < n; i += 2) line_segment(dev, st, &v[i], &v[i + 1]);
+        break;
+    case T_LINE_STRIP:                          /* raster.c:1167-1177 */
+    case T_LINE_LOOP:                           /* raster.c:1180-1196 */
+        if (n < 2) break;
+        for (uint32_t i = 0; i + 1 < n; i++) line_segment(dev, st, &v[i], &v[i + 1]);
+        if (mode == T_LINE_LOOP) line_segment(dev, st, &v[n - 1], &v[0]);
+        break;
+    default:
         break;
     }
 }

@@ -28,6 +28,8 @@ CASES = (
     + [("scissor", 320, 240, v) for v in range(4)]
     + [("texture_misc", 320, 240, v) for v in range(16)]
     + [("state_churn", 320, 240, 0), ("state_churn", 517, 389, 0)]
+    + [("lines", 320, 240, v) for v in (0, 1, 2, 6, 9, 16, 19, 32, 63)]
+    + [("wireframe", 400, 300, v) for v in (0, 1, 2, 3, 4, 5, 8)]
 )
 
 

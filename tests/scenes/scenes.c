@@ -877,6 +877,101 @@ static void scene_state_churn(int w, int h, int variant)
     }
 }
 
+/* 1.0-1 / 1.0-8: points, lines, line strips and loops; variant bit0 wide lines + big points, bit1 depth test,
+ * bit2 blending, bit3 fog (EXP2: the only mode that visibly fogs lines), bit4 textured (no alpha test:
+ * the reference's line loop never terminates when the alpha test rejects a pixel), bit5 scissor */
+static void scene_lines(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 50.0);
+    glClearColor(0.05f, 0.05f, 0.08f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    if (variant & 1) { glLineWidth(3.0f); glPointSize(5.0f); }
+    if (variant & 2) glEnable(GL_DEPTH_TEST);
+    if (variant & 4) { glEnable(GL_BLEND); glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA); }
+    if (variant & 8) {
+        GLfloat fog[] = { 0.4f, 0.1f, 0.1f, 0.6f };
+        glEnable(GL_FOG); glFogi(GL_FOG_MODE, GL_EXP2); glFogf(GL_FOG_DENSITY, 0.25f); glFogfv(GL_FOG_COLOR, fog);
+    }
+    if (variant & 16) {
+        glEnable(GL_TEXTURE_2D);
+        make_checker_rgb(16, 2, 1);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    }
+    if (variant & 32) { glEnable(GL_SCISSOR_TEST); glScissor(w / 5, h / 7, w / 2, (h * 2) / 3); }
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -3.0f);
+    glRotatef(25.0f, 0.0f, 0.0f, 1.0f);
+    glRotatef(35.0f, 1.0f, 0.0f, 0.0f);
+    glBegin(GL_LINES);
+    for (int i = 0; i < 24; i++) {
+        float a = 6.2831853f * (float)i / 24.0f;
+        glColor4f(0.5f + 0.5f * cosf(a), 0.5f + 0.5f * sinf(a), 0.6f, 0.7f);
+        glTexCoord2f(0.0f, 0.0f); glVertex3f(0.1f * cosf(a), 0.1f * sinf(a), 0.0f);
+        glColor4f(1.0f, 1.0f, 0.2f, 0.4f);
+        glTexCoord2f(3.0f, 1.0f); glVertex3f(2.6f * cosf(a), 2.6f * sinf(a), (float)(i % 5) * 0.6f - 1.0f);    /* some leave the frustum */
+    }
+    glEnd();
+    glBegin(GL_LINE_STRIP);
+    for (int i = 0; i < 40; i++) {
+        float a = (float)i * 0.37f;
+        glColor3f(0.2f, 0.9f, 0.5f + 0.5f * sinf(a));
+        glTexCoord2f((float)i * 0.1f, 0.5f);
+        glVertex3f(-1.5f + 0.075f * (float)i, 0.8f * sinf(a), 0.5f * cosf(a));
+    }
+    glEnd();
+    glBegin(GL_LINE_LOOP);
+    for (int i = 0; i < 7; i++) {
+        float a = 6.2831853f * (float)i / 7.0f;
+        glColor3f(1.0f, 0.3f, 0.3f);
+        glVertex3f(1.1f * cosf(a), 1.1f * sinf(a), -0.4f);
+    }
+    glEnd();
+    glBegin(GL_POINTS);
+    for (int i = 0; i < 150; i++) {
+        float a = (float)i * 0.61f;
+        glColor4f(0.3f + 0.7f * fabsf(sinf(a)), 0.8f, 0.3f + 0.7f * fabsf(cosf(a)), 0.8f);
+        glTexCoord2f(a, a * 0.3f);
+        glVertex3f(1.9f * cosf(a) * (float)(i % 10) / 9.0f, 1.4f * sinf(a * 1.7f), 1.5f * sinf(a * 0.3f));
+    }
+    glEnd();
+    /* degenerate and axis-aligned segments */
+    glBegin(GL_LINES);
+    glColor3f(1, 1, 1);
+    glVertex3f(0.5f, 0.5f, 0.0f); glVertex3f(0.5f, 0.5f, 0.0f);
+    glVertex3f(-1.0f, -0.9f, 0.0f); glVertex3f(1.0f, -0.9f, 0.0f);
+    glVertex3f(-1.2f, -1.0f, 0.0f); glVertex3f(-1.2f, 1.0f, 0.0f);
+    glEnd();
+}
+
+/* polygon modes: Suzanne as wireframe (the testbed's SPACE toggle, 1.0-18) or points; variant bit0 GL_POINT instead of
+ * GL_LINE, bit1 GL_PHONG (colours re-lit per vertex, raster.c:864-868), bit2 back faces filled / front outlined,
+ * bit3 cull back faces */
+static void scene_wireframe(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.2f, 0.2f, 0.3f, 1.0f);
+    suzanne_lights_and_material();
+    glShadeModel((variant & 2) ? GL_PHONG : GL_SMOOTH);
+    GLenum mode = (variant & 1) ? GL_POINT : GL_LINE;
+    if (variant & 4) { glPolygonMode(GL_FRONT, mode); glPolygonMode(GL_BACK, GL_FILL); }
+    else glPolygonMode(GL_FRONT_AND_BACK, mode);
+    if (variant & 8) glEnable(GL_CULL_FACE);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -2.2f);
+    glRotatef(20.0f, 1.0f, 0.0f, 0.0f);
+    glRotatef(30.0f, 0.0f, 1.0f, 0.0f);
+    suzanne_immediate();
+    /* an oversize outlined triangle: the outline follows the CLIPPED polygon's fan (raster.c:916-945) */
+    glDisable(GL_LIGHTING);
+    glBegin(GL_TRIANGLES);
+    glColor3f(1, 0, 0); glVertex3f(-6.0f, -2.0f, 1.0f);
+    glColor3f(0, 1, 0); glVertex3f(6.0f, -2.5f, 0.0f);
+    glColor3f(0, 0, 1); glVertex3f(0.3f, 5.0f, 1.9f);
+    glEnd();
+}
+
 /* ---------------------------------------------------------------- registry */
 typedef void (*scene_fn)(int, int, int);
 static const struct { const char *name; scene_fn fn; } g_scenes[] = {
@@ -899,6 +994,8 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "scissor", scene_scissor },
     { "texture_misc", scene_texture_misc },
     { "state_churn", scene_state_churn },
+    { "lines", scene_lines },
+    { "wireframe", scene_wireframe },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }
