@@ -54,7 +54,7 @@ constexpr int COLOR_PITCH = 72;               /* words per tile row in shared me
 constexpr int STENCIL_PITCH = 80;             /* (the fragment quantum) hits 32 distinct banks            */
 constexpr int LIST_WINDOW = 2048;             /* triangle references sorted + staged per pass             */
 constexpr int SETUP_THREADS = 256;            /* one chunk = 256 input triangles                          */
-constexpr int CHUNK_SHIFT = 11;               /* record id = chunk << 11 | index-in-chunk (<= 7*256)      */
+constexpr int CHUNK_SHIFT = 13;               /* record id = chunk << 13 | index-in-chunk (<= 21*256)     */
 constexpr int LARGE_TILES = 16;               /* records overlapping more tiles are binned cooperatively  */
 
 /* ---- device views of objects ---- */
@@ -79,8 +79,8 @@ struct DevDraw {
     float cur_texcoord[2];
     float cur_normal[3];
     uint32_t vbase;          /* index of this draw's first post-transform vertex */
-    uint32_t tbase;          /* index of this draw's first assembled triangle */
-    uint32_t ntris;
+    uint32_t tbase;          /* index of this draw's first assembled primitive (triangle, line segment or point) */
+    uint32_t ntris;          /* primitives of this draw in the pass */
 };
 
 /* Raster-stage view of one mtgl_state: enums folded to small integers, texture resolved to
@@ -112,12 +112,20 @@ enum : uint32_t {
     RC_DEFER = 1u << 13             /* no blending, no alpha test, full colour mask: the colour work can be deferred */
 };
 
-/* TriRecord.state_flags: state block index | deferrable << 30 | back-facing << 31 */
-constexpr uint32_t STATE_INDEX_MASK = 0x3FFFFFFFu;
+/* TriRecord.state_flags: state block index | record kind << 28 | deferrable << 30 | back-facing << 31 */
+constexpr uint32_t STATE_INDEX_MASK = 0x0FFFFFFFu;
+constexpr uint32_t STATE_KIND_SHIFT = 28;
+constexpr uint32_t STATE_KIND_MASK = 3u << STATE_KIND_SHIFT;
+constexpr uint32_t KIND_TRIANGLE = 0u, KIND_LINE = 1u, KIND_POINT = 2u;
 constexpr uint32_t STATE_DEFER_BIT = 1u << 30;
 constexpr uint32_t STATE_BACK_BIT = 1u << 31;
 
-/* One set-up sub-triangle: 10 x 16 B.  Row 2 (clamped bounding box, state, ordered id) is all the
+/* One set-up primitive: 10 x 16 B.  For a sub-triangle the fields mean what their names say.  A LINE record
+ * (draw_line_full, raster.c:107-241) stores its end points in (x0,y0)-(x1,y1), the line width in x2, NDC z in z0/z1,
+ * end colours in c0/c1, texture coordinates in (u0,v0)/(u1,v1) and eye z in ez0/ez1.  A POINT record (flush_points
+ * 1020-1164, draw_point_at_screen 777-844) stores the top-left corner of its square in (x0,y0), the size in x1, its
+ * final depth in z0 and its final colour (after texture, alpha test and fog, all per vertex) in c0.
+ * One set-up sub-triangle: 10 x 16 B.  Row 2 (clamped bounding box, state, ordered id) is all the
  * binner and the tile kernel's list builder read. */
 struct __align__(16) TriRecord {
     int32_t x0, y0, x1, y1;                 /* row 0: integer-snapped vertices (raster.c:59-63) */

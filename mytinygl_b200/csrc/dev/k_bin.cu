@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
             int bx1 = (int)(rec->bbox_max & 0xFFFFu), by1 = (int)(rec->bbox_max >> 16);
             int px0 = max(tx << TILE_LOG, bx0), px1 = min((tx << TILE_LOG) + TILE_W - 1, bx1);
             int py0 = max((ty + fb.tile_y0) << TILE_LOG, by0), py1 = min(((ty + fb.tile_y0) << TILE_LOG) + TILE_H - 1, by1);
-            if (!tile_may_overlap(rec, px0, py0, px1, py1)) continue;
+            /* the exact-coverage corner test only knows triangles; lines and points are binned by their box */
+            if ((rec->state_flags & STATE_KIND_MASK) == (KIND_TRIANGLE << STATE_KIND_SHIFT) && !tile_may_overlap(rec, px0, py0, px1, py1)) continue;
             uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
             if (PASS == 0) {
                 atomicAdd(&b.tile_count[tile], 1u);

@@ -29,6 +29,7 @@
  * real DRAM traffic is one load + one store per touched tile and the kernel is issue-bound.
  */
 #include "dev_common.cuh"
+#include "dev_texture.cuh"
 
 namespace mtgl_dev_impl {
 
@@ -60,113 +61,6 @@ struct RasterSmem {
 };
 static_assert(sizeof(uint16_t) * (RASTER_THREADS / 32) * REGION_W * REGION_H <= sizeof(uint32_t) * LIST_WINDOW, "pending lists must fit in the key array");
 static_assert((LIST_WINDOW & (LIST_WINDOW - 1)) == 0, "the bitonic sort pads to a power of two");
-
-/* ---------------------------------------------------------------- texture sampling (textures.c)
- * The sampler is split in two: tex_taps() resolves the filter, wraps the coordinates and fetches the (up to 8)
- * texels once; tex_channel() then filters ONE 8-bit channel.  Every stage of the reference works per channel
- * (bilinear_filter textures.c:294-307, the trilinear blend 512-515, all truncating to 8 bits), so evaluating
- * alpha first and the colour channels only for fragments that survive the alpha test is bit-identical. */
-struct LevelTaps {
-    uint32_t t00, t10, t01, t11;
-    float fx, fy;
-    uint32_t mode;          /* 0 = single texel in t00, 1 = bilinear, 2 = opaque white (missing level 1) */
-};
-
-struct TexTaps {
-    LevelTaps a, b;
-    float cl;               /* trilinear weight min(lod, 1) */
-    bool tri;
-};
-
-__device__ __forceinline__ int wrap_coord(int x, int n, bool repeat)
-{   /* get_texel_wrapped / get_mip1_texel_wrapped, textures.c:272-291, 357-376 */
-    if (repeat) {
-        if ((unsigned)(x + n) < (unsigned)(3 * n)) {            /* x in [-n, 2n): one conditional add == the euclidean modulo */
-            if (x < 0) x += n; else if (x >= n) x -= n;
-        } else x = ((x % n) + n) % n;
-    } else { if (x < 0) x = 0; else if (x >= n) x = n - 1; }
-    return x;
-}
-
-__device__ __forceinline__ void level_taps(LevelTaps &L, const uint32_t *px, int w, int h, bool rep_s, bool rep_t,
-                                           float u, float v, bool linear)
-{   /* texture_sample_base / _mip1 / tail of texture_sample_lod, textures.c:379-451, 524-556 */
-    float tx = u * (float)w - 0.5f;
-    float ty = v * (float)h - 0.5f;
-    if (linear) {
-        int x0 = f2i_x86(floorf(tx)), y0 = f2i_x86(floorf(ty));
-        L.fx = tx - (float)x0; L.fy = ty - (float)y0;
-        int xa = wrap_coord(x0, w, rep_s), xb = wrap_coord(x0 + 1, w, rep_s);
-        int ya = wrap_coord(y0, h, rep_t), yb = wrap_coord(y0 + 1, h, rep_t);
-        L.t00 = __ldg(px + ya * w + xa); L.t10 = __ldg(px + ya * w + xb);
-        L.t01 = __ldg(px + yb * w + xa); L.t11 = __ldg(px + yb * w + xb);
-        L.mode = 1;
-    } else {
-        int x = f2i_x86(floorf(tx + 0.5f)), y = f2i_x86(floorf(ty + 0.5f));
-        if (x < 0) x = 0;
-        if (x >= w) x = w - 1;
-        if (y < 0) y = 0;
-        if (y >= h) y = h - 1;
-        L.t00 = __ldg(px + y * w + x);
-        L.mode = 0;
-    }
-}
-
-__device__ __forceinline__ void mip1_taps(LevelTaps &L, const RasterCfg *c, float u, float v, uint32_t filter)
-{   /* texture_sample_mip1, textures.c:413-451: a level that cannot exist samples as opaque white */
-    if (!c->tex_l1) { L.mode = 2; return; }
-    bool linear = (filter == G_LINEAR || filter == G_LINEAR_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_LINEAR);
-    level_taps(L, c->tex_l1, c->tex_w1, c->tex_h1, c->tex_wrap_s == G_REPEAT, c->tex_wrap_t == G_REPEAT, u, v, linear);
-}
-
-__device__ __forceinline__ void tex_taps(TexTaps &T, const RasterCfg *c, float u, float v, float lod)
-{   /* texture_sample_lod, textures.c:457-557 */
-    const bool rep_s = c->tex_wrap_s == G_REPEAT, rep_t = c->tex_wrap_t == G_REPEAT;
-    if (rep_s) { u = u - (float)f2i_x86(u); if (u < 0) u += 1.0f; }
-    else { if (u < 0.0f) u = 0.0f; if (u > 1.0f) u = 1.0f; }
-    if (rep_t) { v = v - (float)f2i_x86(v); if (v < 0) v += 1.0f; }
-    else { if (v < 0.0f) v = 0.0f; if (v > 1.0f) v = 1.0f; }
-
-    T.tri = false;
-    uint32_t filter = (lod > 0.0f) ? c->tex_min : c->tex_mag;
-    if (filter == G_NEAREST_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_NEAREST) {
-        if (lod >= 0.5f) { mip1_taps(T.a, c, u, v, filter); return; }
-        filter = (filter == G_NEAREST_MIPMAP_NEAREST) ? G_NEAREST : G_LINEAR;
-    } else if (filter == G_NEAREST_MIPMAP_LINEAR || filter == G_LINEAR_MIPMAP_LINEAR) {
-        if (lod > 0.0f) {
-            T.cl = (lod > 1.0f) ? 1.0f : lod;
-            T.tri = true;
-            level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter != G_NEAREST_MIPMAP_LINEAR);
-            mip1_taps(T.b, c, u, v, filter);
-            return;
-        }
-        filter = (filter == G_NEAREST_MIPMAP_LINEAR) ? G_NEAREST : G_LINEAR;
-    }
-    level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter == G_LINEAR);
-}
-
-__device__ __forceinline__ uint32_t pack1(float x) { return __float2uint_rz(sat01(x) * 255.0f) & 0xFFu; }   /* one channel of color_to_rgba32 */
-
-__device__ __forceinline__ uint32_t level_channel(const LevelTaps &L, int sh, const float *un)
-{   /* bilinear_filter, textures.c:294-307: lerp horizontally, then vertically, truncate to 8 bits */
-    if (L.mode == 0) return (L.t00 >> sh) & 0xFFu;
-    if (L.mode == 2) return 0xFFu;
-    float c00 = un[(L.t00 >> sh) & 0xFFu], c10 = un[(L.t10 >> sh) & 0xFFu];
-    float c01 = un[(L.t01 >> sh) & 0xFFu], c11 = un[(L.t11 >> sh) & 0xFFu];
-    float sx = 1.0f - L.fx, sy = 1.0f - L.fy;
-    float top = c00 * sx + c10 * L.fx;
-    float bot = c01 * sx + c11 * L.fx;
-    return pack1(top * sy + bot * L.fy);
-}
-
-__device__ __forceinline__ float tex_channel(const TexTaps &T, int sh, const float *un)
-{   /* one channel of color_from_rgba32(texture_sample_lod(...)) */
-    uint32_t v0 = level_channel(T.a, sh, un);
-    if (!T.tri) return un[v0];
-    uint32_t v1 = level_channel(T.b, sh, un);
-    float s = 1.0f - T.cl;
-    return un[pack1(un[v0] * s + un[v1] * T.cl)];      /* textures.c:512-515 */
-}
 
 /* ---------------------------------------------------------------- per-fragment helpers */
 __device__ __forceinline__ uint8_t stencil_apply(uint32_t op, uint8_t v, int32_t ref)   /* raster.c:425-438 */
@@ -397,6 +291,122 @@ __device__ __noinline__ void shade_now(const BatchDev &b, RasterSmem &sm, uint32
         if (cm & 4u) d.b = c.b;
         if (cm & 8u) d.a = c.a;
         sm.color[ci] = color_pack(d);
+    }
+}
+
+/* ---------------------------------------------------------------- points and lines (general kernel only) */
+/* depth test, blend, depth write, masked colour write of one line / point pixel: write_line_pixel (raster.c:66-104)
+ * and the pixel loops of flush_points (1123-1161) / draw_point_at_screen (795-843).  These paths have no stencil. */
+__device__ __forceinline__ void simple_pixel(RasterSmem &sm, const RasterCfg *cfg, int ci, float depth, Color4 c)
+{
+    const float *un = sm.unorm8;
+    const uint32_t flags = cfg->flags, cm = cfg->color_mask;
+    if ((flags & RC_DEPTH_TEST) && !compare_f(cfg->depth_func, depth, sm.depth[ci])) return;
+    if (flags & RC_BLEND) {
+        Color4 d = color_unpack(sm.color[ci], un);
+        Color4 sf = blend_factor(cfg->blend_src, c, d), df = blend_factor(cfg->blend_dst, c, d);
+        c = color_clamp({ c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a });
+    }
+    if ((flags & (RC_DEPTH_TEST | RC_DEPTH_WRITE)) == (RC_DEPTH_TEST | RC_DEPTH_WRITE)) sm.depth[ci] = depth;
+    if (cm == 0xFu) sm.color[ci] = color_pack(c);
+    else if (cm != 0u) {
+        Color4 d = color_unpack(sm.color[ci], un);
+        if (cm & 1u) d.r = c.r;
+        if (cm & 2u) d.g = c.g;
+        if (cm & 4u) d.b = c.b;
+        if (cm & 8u) d.a = c.a;
+        sm.color[ci] = color_pack(d);
+    }
+}
+
+/* a POINT record over the part [X0,X1]x[Y0,Y1] (tile-relative, already clamped to the record's box) of a region */
+__device__ __noinline__ void raster_point(const BatchDev &b, RasterSmem &sm, uint32_t r, int X0, int Y0, int X1, int Y1)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const TriRecord *rec = b.records + r;
+    const uint32_t state_flags = __ldg(&rec->state_flags);
+    const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
+    const float depth = __ldg(&rec->z0);
+    const float4 col = __ldg(reinterpret_cast<const float4 *>(rec) + 5);
+    for (int by = Y0; by <= Y1; by += 4)
+        for (int bx = X0; bx <= X1; bx += 8) {
+            const int x = bx + (int)(lane & 7), y = by + (int)(lane >> 3);
+            if (x <= X1 && y <= Y1) simple_pixel(sm, cfg, y * COLOR_PITCH + x, depth, { col.x, col.y, col.z, col.w });
+        }
+}
+
+/* A LINE record: the pixels of the reference's Bresenham walk (raster.c:154-240) in closed form.  Step k of the walk
+ * (k = 0 .. max(|dx|,|dy|)) sits at major = start + k * sign and minor = start + sign * floor((2 k a_minor + a_major - 1)
+ * / (2 a_major)) (verified exhaustively against the loop); the width replicates perpendicular to the major axis, so
+ * all pixels of one line are distinct and the steps can be processed in parallel, 32 per warp iteration. */
+__device__ __noinline__ void raster_line(const BatchDev &b, RasterSmem &sm, uint32_t r, int tile_px, int tile_py,
+                                         int X0, int Y0, int X1, int Y1)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const float *un = sm.unorm8;
+    const TriRecord *rec = b.records + r;
+    const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+    const int lw = __ldg(&rec->x2);
+    const uint32_t state_flags = __ldg(&rec->state_flags);
+    const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
+    const uint32_t flags = cfg->flags;
+    const int x0 = row0.x, y0 = row0.y, x1 = row0.z, y1 = row0.w;
+    const long long dx = (long long)x1 - x0, dy = (long long)y1 - y0;
+    const long long adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+    const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1;
+    const long long total = adx > ady ? adx : ady;
+    const float total_steps = (float)(total == 0 ? 1 : (int)total);
+    const bool x_major = adx > ady;                 /* also the replication axis: vertical when mostly horizontal */
+    const int half = lw / 2;
+    /* steps whose major coordinate falls into the rectangle (absolute pixel coordinates) */
+    const int lo = x_major ? tile_px + X0 : tile_py + Y0, hi = x_major ? tile_px + X1 : tile_py + Y1;
+    const int start = x_major ? x0 : y0, sgn = x_major ? sx : sy;
+    long long k0, k1;                               /* inclusive step range with lo <= start + sgn * k <= hi */
+    if (sgn > 0) { k0 = (long long)lo - start; k1 = (long long)hi - start; } else { k0 = (long long)start - hi; k1 = (long long)start - lo; }
+    if (k0 < 0) k0 = 0;
+    if (k1 > total) k1 = total;
+    const float z0 = __ldg(&rec->z0), z1 = __ldg(&rec->z1);
+    const float4 c0 = __ldg(reinterpret_cast<const float4 *>(rec) + 5), c1 = __ldg(reinterpret_cast<const float4 *>(rec) + 6);
+    const float4 uv = __ldg(reinterpret_cast<const float4 *>(rec) + 8);
+    const float ez0 = __ldg(&rec->ez0), ez1 = __ldg(&rec->ez1);
+
+    for (long long kb = k0; kb <= k1; kb += 32) {
+        const long long k = kb + lane;
+        if (k > k1) continue;
+        int px, py;
+        if (adx >= ady) {
+            px = x0 + sx * (int)k;
+            py = y0 + (adx ? sy * (int)((2 * k * ady + adx - 1) / (2 * adx)) : 0);
+        } else {
+            px = x0 + sx * (int)((2 * k * adx + ady - 1) / (2 * ady));
+            py = y0 + sy * (int)k;
+        }
+        const float t = (float)(int)k / total_steps;            /* raster.c:157 */
+        const float z = z0 + t * (z1 - z0);
+        float depth;
+        if (flags & RC_DEPTH_RANGE_01) depth = (z + 1.0f) * 0.5f;
+        else depth = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);
+        Color4 c = color_lerp({ c0.x, c0.y, c0.z, c0.w }, { c1.x, c1.y, c1.z, c1.w }, t);
+        if (flags & RC_TEXTURED) {                              /* raster.c:167-179: lod 0, GL_MODULATE only */
+            const float u = uv.x + t * (uv.z - uv.x), v = uv.y + t * (uv.w - uv.y);
+            TexTaps T;
+            tex_taps(T, cfg, u, v, 0.0f);
+            Color4 tc;
+            tc.a = tex_channel(T, 24, un);
+            /* the reference never terminates when this test fails (`continue` without stepping); skip the pixel instead */
+            if ((flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, tc.a, cfg->alpha_ref)) continue;
+            tc.r = tex_channel(T, 0, un); tc.g = tex_channel(T, 8, un); tc.b = tex_channel(T, 16, un);
+            c = { c.r * tc.r, c.g * tc.g, c.b * tc.b, c.a * tc.a };
+        } else if ((flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, c.a, cfg->alpha_ref)) continue;
+        if (flags & RC_FOG) {                                   /* raster.c:188-211: negated coordinate */
+            const float fc = -(ez0 + t * (ez1 - ez0));
+            Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
+            c = color_lerp_rgb(fogc, c, fog_factor(cfg, fc));
+        }
+        for (int w = -half; w < lw - half; w++) {               /* raster.c:214-226 */
+            const int qx = (x_major ? px : px + w) - tile_px, qy = (x_major ? py + w : py) - tile_py;
+            if (qx >= X0 && qx <= X1 && qy >= Y0 && qy <= Y1) simple_pixel(sm, cfg, qy * COLOR_PITCH + qx, depth, c);
+        }
     }
 }
 
@@ -783,7 +793,16 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 TriHead h;
                 if (VIS) h = broadcast_head(mine, k);
                 else load_head(h, b.records + r);
-                raster_triangle<VIS>(b, sm, r, h, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
+                const uint32_t kind = VIS ? KIND_TRIANGLE : (h.state_flags & STATE_KIND_MASK) >> STATE_KIND_SHIFT;
+                if (kind == KIND_TRIANGLE) raster_triangle<VIS>(b, sm, r, h, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
+                else {
+                    if (pending) {      /* lines and points are drawn in order on top of whatever was deferred */
+                        resolve_region(b, sm, rx0, ry0, px0, py0);
+                        pending = false;
+                    }
+                    if (kind == KIND_POINT) raster_point(b, sm, r, X0, Y0, X1, Y1);
+                    else raster_line(b, sm, r, px0, py0, X0, Y0, X1, Y1);
+                }
                 __syncwarp();
             }
         }

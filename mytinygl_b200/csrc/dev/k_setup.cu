@@ -18,6 +18,9 @@
  * 160 B written per surviving sub-triangle.
  */
 #include "dev_common.cuh"
+#include "dev_texture.cuh"
+
+#include <climits>
 
 namespace mtgl_dev_impl {
 
@@ -90,7 +93,7 @@ __device__ __forceinline__ void snap(SVert &v, int plane)   /* clipping.h:37-47 
 
 #define MAX_CLIP 12
 
-__device__ int clip_plane(const SVert *in, int n, SVert *out, int plane)   /* clipping.h:50-99 */
+__device__ __noinline__ int clip_plane(const SVert *in, int n, SVert *out, int plane)   /* clipping.h:50-99 */
 {
     if (n == 0) return 0;
     int m = 0;
@@ -133,45 +136,211 @@ __device__ __forceinline__ void persp_divide(SVert &v)   /* raster.c:729-746: w 
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(a, max(b, c)); }
 
-/* One fan sub-triangle after the divide: snap, cull, set up.  Returns false when nothing is to be
- * rasterised; otherwise fills *rec (and *eye).  Mirrors raster.c:916-956 and 458-529. */
-__device__ bool setup_subtri(const mtgl_state *st, const RasterCfg *cfg, const FrameTargets &fb, const SVert &a,
-                             const SVert &b, const SVert &c, uint32_t state_index, TriRecord *rec, TriEye *eye)
+/* ---------------------------------------------------------------- record emission */
+struct Emitter {
+    bool write;             /* false: counting pass */
+    uint32_t n;             /* records emitted so far by this thread */
+    TriRecord *dst;         /* first slot of this thread (write pass) */
+    TriEye *eye_dst;
+    uint32_t id0;           /* ordered id of the first slot */
+};
+
+__device__ __forceinline__ void store_record(TriRecord *dst, const TriRecord &r)
 {
-    const float vw = (float)st->viewport[2], vh = (float)st->viewport[3];
-    const float vx = (float)st->viewport[0], vy = (float)st->viewport[1];
-    int32_t x0 = f2i_x86((a.x + 1.0f) * 0.5f * vw + vx), y0 = f2i_x86((1.0f - a.y) * 0.5f * vh + vy);
-    int32_t x1 = f2i_x86((b.x + 1.0f) * 0.5f * vw + vx), y1 = f2i_x86((1.0f - b.y) * 0.5f * vh + vy);
-    int32_t x2 = f2i_x86((c.x + 1.0f) * 0.5f * vw + vx), y2 = f2i_x86((1.0f - c.y) * 0.5f * vh + vy);
+    const int4 *s = reinterpret_cast<const int4 *>(&r);
+    int4 *d = reinterpret_cast<int4 *>(dst);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(TriRecord) / 16); k++) d[k] = s[k];
+}
+
+__device__ __forceinline__ void emit(Emitter &em, TriRecord &rec, const TriEye *eye)
+{
+    if (em.write) {
+        rec.id = em.id0 + em.n;
+        store_record(em.dst + em.n, rec);
+        if (eye && em.eye_dst) em.eye_dst[em.n] = *eye;
+    }
+    em.n++;
+}
+
+/* clamp an inclusive pixel box to framebuffer, scissor and band; false when empty */
+__device__ __forceinline__ bool clamp_box(const mtgl_state *st, const FrameTargets &fb, int &minX, int &minY, int &maxX, int &maxY)
+{
+    if (st->caps & MTGL_CAP_SCISSOR_TEST) {
+        const int32_t *sc = st->scissor;
+        if (minX < sc[0]) minX = sc[0];
+        if (minY < sc[1]) minY = sc[1];
+        if (maxX >= sc[0] + sc[2]) maxX = sc[0] + sc[2] - 1;
+        if (maxY >= sc[1] + sc[3]) maxY = sc[1] + sc[3] - 1;
+    }
+    if (minX < 0) minX = 0;
+    if (maxX >= fb.width) maxX = fb.width - 1;
+    if (minY < fb.band_y0) minY = fb.band_y0;
+    if (maxY >= fb.band_y1) maxY = fb.band_y1 - 1;
+    return minX <= maxX && minY <= maxY;
+}
+
+/* depth of a line / point pixel (raster.c:161, 793, 1065) */
+__device__ __forceinline__ float simple_depth(const RasterCfg *cfg, float z)
+{
+    if (cfg->flags & RC_DEPTH_RANGE_01) return (z + 1.0f) * 0.5f;
+    return (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);
+}
+
+/* fog of lines and points: the coordinate is negated once more (raster.c:189, 809, 1093) */
+__device__ __forceinline__ Color4 simple_fog(const RasterCfg *cfg, Color4 c, float eye_z)
+{
+    if (!(cfg->flags & RC_FOG)) return c;
+    float fc = -eye_z, f = 1.0f;
+    switch (cfg->fog_mode) {
+    case G_LINEAR: if (cfg->fog_end != cfg->fog_start) f = (cfg->fog_end - fc) / (cfg->fog_end - cfg->fog_start); break;
+    case G_EXP: f = expf(-cfg->fog_density * fc); break;
+    case G_EXP2: { float d = cfg->fog_density * fc; f = expf(-d * d); break; }
+    default: break;
+    }
+    if (f < 0.0f) f = 0.0f;
+    if (f > 1.0f) f = 1.0f;
+    Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
+    return color_lerp_rgb(fogc, c, f);
+}
+
+/* a LINE record for draw_line_full(x0, y0, z0, x1, y1, z1, c0, c1, ez0, ez1, uv0, uv1) (raster.c:107-241) */
+__device__ __noinline__ void emit_line(Emitter &em, const mtgl_state *st, const FrameTargets fb, uint32_t state_index, int32_t x0, int32_t y0, float z0,
+                          int32_t x1, int32_t y1, float z1, Color4 c0, Color4 c1, float ez0, float ez1, float u0, float v0, float u1, float v1)
+{
+    int lw = f2i_x86(st->line_width + 0.5f);
+    if (lw < 1) lw = 1;
+    const int half = lw / 2;
+    const long long adx = llabs((long long)x1 - x0), ady = llabs((long long)y1 - y0);
+    int minX = min(x0, x1), maxX = max(x0, x1), minY = min(y0, y1), maxY = max(y0, y1);
+    if (lw > 1) {               /* perpendicular replication: vertical for mostly-horizontal lines (raster.c:136-146, 219-226) */
+        if (adx > ady) { minY -= half; maxY += lw - half - 1; } else { minX -= half; maxX += lw - half - 1; }
+    }
+    if (!clamp_box(st, fb, minX, minY, maxX, maxY)) return;
+    TriRecord rec;
+    rec.x0 = x0; rec.y0 = y0; rec.x1 = x1; rec.y1 = y1; rec.x2 = lw; rec.y2 = 0;
+    rec.area = 0.0f; rec.inv_area = 0.0f;
+    rec.bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
+    rec.bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
+    rec.state_flags = state_index | (KIND_LINE << STATE_KIND_SHIFT);
+    rec.id = 0;
+    rec.z0 = z0; rec.z1 = z1; rec.z2 = 0.0f; rec.lod = 0.0f;
+    rec.w0 = rec.w1 = rec.w2 = 0.0f; rec.ez0 = ez0;
+    rec.c0[0] = c0.r; rec.c0[1] = c0.g; rec.c0[2] = c0.b; rec.c0[3] = c0.a;
+    rec.c1[0] = c1.r; rec.c1[1] = c1.g; rec.c1[2] = c1.b; rec.c1[3] = c1.a;
+    rec.c2[0] = rec.c2[1] = rec.c2[2] = rec.c2[3] = 0.0f;
+    rec.u0 = u0; rec.v0 = v0; rec.u1 = u1; rec.v1 = v1; rec.u2 = 0.0f; rec.v2 = 0.0f;
+    rec.ez1 = ez1; rec.ez2 = 0.0f;
+    emit(em, rec, nullptr);
+}
+
+/* a POINT record: a ps x ps square with constant depth and colour (raster.c:1117-1162, 777-844) */
+__device__ __noinline__ void emit_point(Emitter &em, const mtgl_state *st, const FrameTargets fb, uint32_t state_index, int32_t left, int32_t top, int ps,
+                           float depth, Color4 c)
+{
+    long long r = (long long)left + ps - 1, bt = (long long)top + ps - 1;
+    int minX = left, minY = top;
+    int maxX = (int)min(r, (long long)INT_MAX), maxY = (int)min(bt, (long long)INT_MAX);
+    if (!clamp_box(st, fb, minX, minY, maxX, maxY)) return;
+    TriRecord rec;
+    rec.x0 = left; rec.y0 = top; rec.x1 = ps; rec.y1 = 0; rec.x2 = 0; rec.y2 = 0;
+    rec.area = 0.0f; rec.inv_area = 0.0f;
+    rec.bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
+    rec.bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
+    rec.state_flags = state_index | (KIND_POINT << STATE_KIND_SHIFT);
+    rec.id = 0;
+    rec.z0 = depth; rec.z1 = rec.z2 = 0.0f; rec.lod = 0.0f;
+    rec.w0 = rec.w1 = rec.w2 = 0.0f; rec.ez0 = 0.0f;
+    rec.c0[0] = c.r; rec.c0[1] = c.g; rec.c0[2] = c.b; rec.c0[3] = c.a;
+    rec.c1[0] = rec.c1[1] = rec.c1[2] = rec.c1[3] = 0.0f;
+    rec.c2[0] = rec.c2[1] = rec.c2[2] = rec.c2[3] = 0.0f;
+    rec.u0 = rec.v0 = rec.u1 = rec.v1 = rec.u2 = rec.v2 = 0.0f;
+    rec.ez1 = rec.ez2 = 0.0f;
+    emit(em, rec, nullptr);
+}
+
+__device__ __forceinline__ void to_screen(const mtgl_state *st, float x, float y, int32_t &sx, int32_t &sy)   /* raster.c:59-63 */
+{
+    sx = f2i_x86((x + 1.0f) * 0.5f * (float)st->viewport[2] + (float)st->viewport[0]);
+    sy = f2i_x86((1.0f - y) * 0.5f * (float)st->viewport[3] + (float)st->viewport[1]);
+}
+
+/* polygon modes GL_LINE / GL_POINT: draw_triangle_wireframe / draw_triangle_points (raster.c:847-898) */
+__device__ __noinline__ void setup_outline(Emitter &em, const mtgl_state *st, const RasterCfg *cfg, const FrameTargets fb, const SVert &a,
+                                           const SVert &b, const SVert &c, const int32_t *sx, const int32_t *sy, uint32_t state_index, bool as_points)
+{
+    const SVert *v[3] = { &a, &b, &c };
+    Color4 col[3];
+    for (int k = 0; k < 3; k++) {
+        col[k] = { v[k]->r, v[k]->g, v[k]->b, v[k]->a };
+        if ((st->caps & MTGL_CAP_LIGHTING) && st->shade_model == G_PHONG) {
+            MaterialRegs mat;
+            load_material(mat, &st->material_front);
+            col[k] = compute_lighting(st, v[k]->epx, v[k]->epy, v[k]->epz, v[k]->enx, v[k]->eny, v[k]->enz, mat);
+        }
+    }
+    if (as_points) {
+        for (int k = 0; k < 3; k++) {           /* draw_point_at_screen, raster.c:777-844: vertex alpha, no texture */
+            if ((cfg->flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, col[k].a, cfg->alpha_ref)) continue;
+            emit_point(em, st, fb, state_index, sx[k], sy[k], 1, simple_depth(cfg, v[k]->z), simple_fog(cfg, col[k], v[k]->ez));
+        }
+    } else {
+        for (int k = 0; k < 3; k++) {
+            const int n = (k + 1) % 3;
+            emit_line(em, st, fb, state_index, sx[k], sy[k], v[k]->z, sx[n], sy[n], v[n]->z, col[k], col[n], v[k]->ez, v[n]->ez,
+                      v[k]->u, v[k]->v, v[n]->u, v[n]->v);
+        }
+    }
+}
+
+/* One fan sub-triangle after the divide: snap, cull, then either set it up for filling or turn it into its
+ * outline (3 LINE records) / corners (3 POINT records).  Mirrors raster.c:916-956, 847-898 and 458-529. */
+__device__ __forceinline__ void setup_subtri(const bool write, uint32_t &n_emitted, TriRecord *const dst, TriEye *const eye_dst, const uint32_t id0,
+                                             const BatchDev &bd, const mtgl_state *st, const RasterCfg *cfg, const FrameTargets &fb,
+                                             const SVert &a, const SVert &b, const SVert &c, uint32_t state_index)
+{
+    int32_t x0, y0, x1, y1, x2, y2;
+    to_screen(st, a.x, a.y, x0, y0);
+    to_screen(st, b.x, b.y, x1, y1);
+    to_screen(st, c.x, c.y, x2, y2);
 
     /* signed area of the snapped triangle decides culling and facing (raster.c:923-935) */
     float sa = (float)(x1 - x0) * (float)(y2 - y0) - (float)(x2 - x0) * (float)(y1 - y0);
     if (st->caps & MTGL_CAP_CULL_FACE) {
         bool front = (st->front_face == G_CCW) ? (sa < 0) : (sa > 0);
         bool cull = (st->cull_face_mode == G_FRONT) ? front : (st->cull_face_mode == G_BACK) ? !front : true;
-        if (cull) return false;
+        if (cull) return;
     }
     bool back = (st->front_face == G_CCW) ? (sa >= 0) : (sa < 0);
     uint32_t pm = back ? st->polygon_mode_back : st->polygon_mode_front;
-    if (pm != G_FILL) return false;     /* TODO(next): GL_LINE / GL_POINT polygon modes */
+
+    if (pm == G_POINT || pm == G_LINE) {
+        const int32_t sx[3] = { x0, x1, x2 }, sy[3] = { y0, y1, y2 };
+        Emitter em = { write, n_emitted, dst, eye_dst, id0 };       /* the rare paths are out of line and take the emitter by reference */
+        const SVert ca = a, cb = b, cc = c;         /* copies: the caller's vertices must stay in registers */
+        setup_outline(em, st, cfg, fb, ca, cb, cc, sx, sy, state_index, pm == G_POINT);
+        n_emitted = em.n;
+        return;
+    }
 
     int32_t minX = imin3(x0, x1, x2), minY = imin3(y0, y1, y2), maxX = imax3(x0, x1, x2), maxY = imax3(y0, y1, y2);
-    const int32_t *vp = st->viewport, *sc = st->scissor;
+    const int32_t *vp = st->viewport;
     if (minX < vp[0]) minX = vp[0];
     if (minY < vp[1]) minY = vp[1];
     if (maxX >= vp[0] + vp[2]) maxX = vp[0] + vp[2] - 1;
     if (maxY >= vp[1] + vp[3]) maxY = vp[1] + vp[3] - 1;
     if (st->caps & MTGL_CAP_SCISSOR_TEST) {
+        const int32_t *sc = st->scissor;
         if (minX < sc[0]) minX = sc[0];
         if (minY < sc[1]) minY = sc[1];
         if (maxX >= sc[0] + sc[2]) maxX = sc[0] + sc[2] - 1;
         if (maxY >= sc[1] + sc[3]) maxY = sc[1] + sc[3] - 1;
     }
-    if (minX > maxX || minY > maxY) return false;
+    if (minX > maxX || minY > maxY) return;
 
     /* edge_function(x0,y0,x1,y1,x2,y2) (raster.c:483, 299-302) */
     float area = ((float)x2 - (float)x0) * ((float)y1 - (float)y0) - ((float)y2 - (float)y0) * ((float)x1 - (float)x0);
-    if (fabsf(area) < 0.5f) return false;
+    if (fabsf(area) < 0.5f) return;
 
     /* pixels outside the framebuffer are dropped by the bounds-checked accessors (framebuffer.h:92-134);
      * rows outside this device's band belong to another GPU */
@@ -179,22 +348,24 @@ __device__ bool setup_subtri(const mtgl_state *st, const RasterCfg *cfg, const F
     if (maxX >= fb.width) maxX = fb.width - 1;
     if (minY < fb.band_y0) minY = fb.band_y0;
     if (maxY >= fb.band_y1) maxY = fb.band_y1 - 1;
-    if (minX > maxX || minY > maxY) return false;
-    if (!rec) return true;
+    if (minX > maxX || minY > maxY) return;
+    if (!write) { n_emitted++; return; }
 
-    rec->x0 = x0; rec->y0 = y0; rec->x1 = x1; rec->y1 = y1; rec->x2 = x2; rec->y2 = y2;
-    rec->state_flags = state_index | (back ? STATE_BACK_BIT : 0u) | ((cfg->flags & RC_DEFER) ? STATE_DEFER_BIT : 0u);
-    rec->bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
-    rec->bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
-    rec->z0 = a.z; rec->z1 = b.z; rec->z2 = c.z;
-    rec->w0 = a.w; rec->w1 = b.w; rec->w2 = c.w;
-    rec->area = area;
-    rec->inv_area = 1.0f / area;
-    rec->c0[0] = a.r; rec->c0[1] = a.g; rec->c0[2] = a.b; rec->c0[3] = a.a;
-    rec->c1[0] = b.r; rec->c1[1] = b.g; rec->c1[2] = b.b; rec->c1[3] = b.a;
-    rec->c2[0] = c.r; rec->c2[1] = c.g; rec->c2[2] = c.b; rec->c2[3] = c.a;
-    rec->u0 = a.u; rec->v0 = a.v; rec->u1 = b.u; rec->v1 = b.v; rec->u2 = c.u; rec->v2 = c.v;
-    rec->ez0 = a.ez; rec->ez1 = b.ez; rec->ez2 = c.ez;
+    TriRecord rec;
+    rec.x0 = x0; rec.y0 = y0; rec.x1 = x1; rec.y1 = y1; rec.x2 = x2; rec.y2 = y2;
+    rec.state_flags = state_index | (back ? STATE_BACK_BIT : 0u) | ((cfg->flags & RC_DEFER) ? STATE_DEFER_BIT : 0u);
+    rec.id = 0;
+    rec.bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
+    rec.bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
+    rec.z0 = a.z; rec.z1 = b.z; rec.z2 = c.z;
+    rec.w0 = a.w; rec.w1 = b.w; rec.w2 = c.w;
+    rec.area = area;
+    rec.inv_area = 1.0f / area;
+    rec.c0[0] = a.r; rec.c0[1] = a.g; rec.c0[2] = a.b; rec.c0[3] = a.a;
+    rec.c1[0] = b.r; rec.c1[1] = b.g; rec.c1[2] = b.b; rec.c1[3] = b.a;
+    rec.c2[0] = c.r; rec.c2[1] = c.g; rec.c2[2] = c.b; rec.c2[3] = c.a;
+    rec.u0 = a.u; rec.v0 = a.v; rec.u1 = b.u; rec.v1 = b.v; rec.u2 = c.u; rec.v2 = c.v;
+    rec.ez0 = a.ez; rec.ez1 = b.ez; rec.ez2 = c.ez;
 
     float lod = 0.0f;                   /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
     if (cfg->flags & RC_TEXTURED) {
@@ -211,24 +382,93 @@ __device__ bool setup_subtri(const mtgl_state *st, const RasterCfg *cfg, const F
             }
         }
     }
-    rec->lod = lod;
-    if (eye) {
-        eye->ep0[0] = a.epx; eye->ep0[1] = a.epy; eye->ep0[2] = a.epz; eye->ep0[3] = 0.0f;
-        eye->ep1[0] = b.epx; eye->ep1[1] = b.epy; eye->ep1[2] = b.epz; eye->ep1[3] = 0.0f;
-        eye->ep2[0] = c.epx; eye->ep2[1] = c.epy; eye->ep2[2] = c.epz; eye->ep2[3] = 0.0f;
-        eye->en0[0] = a.enx; eye->en0[1] = a.eny; eye->en0[2] = a.enz; eye->en0[3] = 0.0f;
-        eye->en1[0] = b.enx; eye->en1[1] = b.eny; eye->en1[2] = b.enz; eye->en1[3] = 0.0f;
-        eye->en2[0] = c.enx; eye->en2[1] = c.eny; eye->en2[2] = c.enz; eye->en2[3] = 0.0f;
+    rec.lod = lod;
+    TriEye eye;
+    if (bd.need_eye) {
+        eye.ep0[0] = a.epx; eye.ep0[1] = a.epy; eye.ep0[2] = a.epz; eye.ep0[3] = 0.0f;
+        eye.ep1[0] = b.epx; eye.ep1[1] = b.epy; eye.ep1[2] = b.epz; eye.ep1[3] = 0.0f;
+        eye.ep2[0] = c.epx; eye.ep2[1] = c.epy; eye.ep2[2] = c.epz; eye.ep2[3] = 0.0f;
+        eye.en0[0] = a.enx; eye.en0[1] = a.eny; eye.en0[2] = a.enz; eye.en0[3] = 0.0f;
+        eye.en1[0] = b.enx; eye.en1[1] = b.eny; eye.en1[2] = b.enz; eye.en1[3] = 0.0f;
+        eye.en2[0] = c.enx; eye.en2[1] = c.eny; eye.en2[2] = c.enz; eye.en2[3] = 0.0f;
     }
-    return true;
+    rec.id = id0 + n_emitted;
+    store_record(dst + n_emitted, rec);
+    if (bd.need_eye) eye_dst[n_emitted] = eye;
+    n_emitted++;
 }
 
-__device__ __forceinline__ void store_record(TriRecord *dst, const TriRecord &r)
+/* ---------------------------------------------------------------- line segments and points as primitives */
+__device__ __forceinline__ int outcode(const SVert &v)   /* clipping.h:138-148 */
 {
-    const int4 *s = reinterpret_cast<const int4 *>(&r);
-    int4 *d = reinterpret_cast<int4 *>(dst);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(TriRecord) / 16); k++) d[k] = s[k];
+    int c = 0;
+    if (v.x < -v.w) c |= 1; else if (v.x > v.w) c |= 2;
+    if (v.y < -v.w) c |= 4; else if (v.y > v.w) c |= 8;
+    if (v.z < -v.w) c |= 16; else if (v.z > v.w) c |= 32;
+    return c;
+}
+
+__device__ bool clip_segment(SVert &v0, SVert &v1)   /* clip_line, clipping.h:152-229 */
+{
+    int c0 = outcode(v0), c1 = outcode(v1);
+    for (int guard = 0; guard < 64; guard++) {      /* (the reference loops unboundedly; it converges in <= 6 rounds per end) */
+        if (!(c0 | c1)) return true;
+        if (c0 & c1) return false;
+        const int co = c0 ? c0 : c1;
+        float d0, d1;
+        int plane;
+        if (co & 1) { d0 = v0.x + v0.w; d1 = v1.x + v1.w; plane = 2; }
+        else if (co & 2) { d0 = v0.w - v0.x; d1 = v1.w - v1.x; plane = 3; }
+        else if (co & 4) { d0 = v0.y + v0.w; d1 = v1.y + v1.w; plane = 4; }
+        else if (co & 8) { d0 = v0.w - v0.y; d1 = v1.w - v1.y; plane = 5; }
+        else if (co & 16) { d0 = v0.z + v0.w; d1 = v1.z + v1.w; plane = 0; }
+        else { d0 = v0.w - v0.z; d1 = v1.w - v1.z; plane = 1; }
+        const float den = d0 - d1;
+        if (fabsf(den) < 1e-10f) return false;
+        SVert cl = vertex_lerp(v0, v1, d0 / den);
+        snap(cl, plane);
+        if (co == c0) { v0 = cl; c0 = outcode(v0); } else { v1 = cl; c1 = outcode(v1); }
+    }
+    return false;
+}
+
+/* draw_line_segment (raster.c:244-285) up to the call of draw_line_full */
+__device__ __noinline__ void setup_segment(Emitter &em, const mtgl_state *st, const FrameTargets fb, uint32_t state_index, SVert v0, SVert v1)
+{
+    if (!clip_segment(v0, v1)) return;
+    float z0, z1;
+    if (fabsf(v0.w) >= 1e-6f) { float iw = 1.0f / v0.w; v0.x *= iw; v0.y *= iw; z0 = v0.z * iw; } else { v0.x = 0.0f; v0.y = 0.0f; z0 = 0.0f; }
+    if (fabsf(v1.w) >= 1e-6f) { float iw = 1.0f / v1.w; v1.x *= iw; v1.y *= iw; z1 = v1.z * iw; } else { v1.x = 0.0f; v1.y = 0.0f; z1 = 0.0f; }
+    int32_t x0, y0, x1, y1;
+    to_screen(st, v0.x, v0.y, x0, y0);
+    to_screen(st, v1.x, v1.y, x1, y1);
+    emit_line(em, st, fb, state_index, x0, y0, z0, x1, y1, z1, { v0.r, v0.g, v0.b, v0.a }, { v1.r, v1.g, v1.b, v1.a }, v0.ez, v1.ez,
+              v0.u, v0.v, v1.u, v1.v);
+}
+
+/* one vertex of flush_points (raster.c:1044-1163): everything but the per-pixel tests happens here */
+__device__ __noinline__ void setup_point(Emitter &em, const float *unorm8, const mtgl_state *st, const RasterCfg *cfg, const FrameTargets fb,
+                            uint32_t state_index, SVert v)
+{
+    if (v.x < -v.w || v.x > v.w || v.y < -v.w || v.y > v.w || v.z < -v.w || v.z > v.w || v.w <= 0.0f) return;
+    const float nx = v.x / v.w, ny = v.y / v.w, nz = v.z / v.w;
+    int32_t cx, cy;
+    to_screen(st, nx, ny, cx, cy);
+    const float depth = simple_depth(cfg, nz);
+    Color4 c = { v.r, v.g, v.b, v.a };
+    if (cfg->flags & RC_TEXTURED) {
+        TexTaps T;
+        tex_taps(T, cfg, v.u, v.v, 0.0f);               /* texture_sample(): magnification filter */
+        Color4 t;
+        t.a = tex_channel(T, 24, unorm8);
+        if ((cfg->flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, t.a, cfg->alpha_ref)) return;
+        t.r = tex_channel(T, 0, unorm8); t.g = tex_channel(T, 8, unorm8); t.b = tex_channel(T, 16, unorm8);
+        c = { c.r * t.r, c.g * t.g, c.b * t.b, c.a * t.a };
+    } else if ((cfg->flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, c.a, cfg->alpha_ref)) return;
+    c = simple_fog(cfg, c, v.ez);
+    int ps = f2i_x86(st->point_size + 0.5f);
+    if (ps < 1) ps = 1;
+    emit_point(em, st, fb, state_index, cx - ps / 2, cy - ps / 2, ps, depth, c);
 }
 
 __device__ __forceinline__ uint32_t find_draw_tri(const uint32_t *base, uint32_t n, uint32_t g)
@@ -254,50 +494,67 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(BatchDev b, FrameTarget
     SVert poly_a[MAX_CLIP], poly_b[MAX_CLIP];
     SVert *poly = nullptr;
     int npoly = 0;
-    bool clipped = false;
+    int shape = 0;          /* 0 nothing, 1 unclipped triangle, 2 clipped polygon, 3 line segment, 4 point */
     const mtgl_state *st = nullptr;
     const RasterCfg *cfg = nullptr;
     uint32_t state_index = 0;
-    uint32_t count = 0;
 
     if (valid) {
         uint32_t d = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t);
         const DevDraw &dr = b.draws[d];
-        uint32_t k = t - dr.tbase, i0, i1, i2;
-        switch (dr.mode) {                                  /* raster.c:961-1017, 1199-1231 */
-        case G_TRIANGLES: i0 = 3 * k; i1 = i0 + 1; i2 = i0 + 2; break;
-        case G_QUADS: { uint32_t q = 4 * (k >> 1); i0 = q; if (k & 1) { i1 = q + 2; i2 = q + 3; } else { i1 = q + 1; i2 = q + 2; } break; }
-        case G_TRIANGLE_STRIP: if (k & 1) { i0 = k + 1; i1 = k; } else { i0 = k; i1 = k + 1; } i2 = k + 2; break;
-        case G_QUAD_STRIP: { uint32_t q = 2 * (k >> 1); i0 = q; if (k & 1) { i1 = q + 3; i2 = q + 2; } else { i1 = q + 1; i2 = q + 3; } break; }
-        default: i0 = 0; i1 = k + 1; i2 = k + 2; break;     /* fan, polygon */
-        }
+        const uint32_t k = t - dr.tbase, n = dr.count;
+        uint32_t i0 = 0, i1 = 0, i2 = 0;
         state_index = dr.raster_state;
         st = b.states + state_index;
         cfg = b.cfgs + state_index;
+        switch (dr.mode) {                                  /* raster.c:961-1017, 1020-1044, 288-296, 1167-1231 */
+        case G_POINTS: i0 = k; shape = 4; break;
+        case G_LINES: i0 = 2 * k; i1 = i0 + 1; shape = 3; break;
+        case G_LINE_STRIP: i0 = k; i1 = k + 1; shape = 3; break;
+        case G_LINE_LOOP: if (k + 1 < n) { i0 = k; i1 = k + 1; } else { i0 = n - 1; i1 = 0; } shape = 3; break;
+        case G_TRIANGLES: i0 = 3 * k; i1 = i0 + 1; i2 = i0 + 2; shape = 1; break;
+        case G_QUADS: { uint32_t q = 4 * (k >> 1); i0 = q; if (k & 1) { i1 = q + 2; i2 = q + 3; } else { i1 = q + 1; i2 = q + 2; } shape = 1; break; }
+        case G_TRIANGLE_STRIP: if (k & 1) { i0 = k + 1; i1 = k; } else { i0 = k; i1 = k + 1; } i2 = k + 2; shape = 1; break;
+        case G_QUAD_STRIP: { uint32_t q = 2 * (k >> 1); i0 = q; if (k & 1) { i1 = q + 3; i2 = q + 2; } else { i1 = q + 1; i2 = q + 3; } shape = 1; break; }
+        default: i0 = 0; i1 = k + 1; i2 = k + 2; shape = 1; break;     /* fan, polygon */
+        }
         v0 = load_vertex(b, dr.vbase + i0);
-        v1 = load_vertex(b, dr.vbase + i1);
-        v2 = load_vertex(b, dr.vbase + i2);
-
-        if (inside_all(v0) && inside_all(v1) && inside_all(v2)) {
-            /* Sutherland-Hodgman returns its input unchanged when every vertex passes every plane */
-            persp_divide(v0); persp_divide(v1); persp_divide(v2);
-            count = setup_subtri(st, cfg, fb, v0, v1, v2, state_index, nullptr, nullptr) ? 1u : 0u;
-        } else {
-            clipped = true;
-            poly_a[0] = v0; poly_a[1] = v1; poly_a[2] = v2;
-            int n = clip_plane(poly_a, 3, poly_b, 0);       /* clipping.h:106-126 */
-            if (n) n = clip_plane(poly_b, n, poly_a, 1);
-            if (n) n = clip_plane(poly_a, n, poly_b, 2);
-            if (n) n = clip_plane(poly_b, n, poly_a, 3);
-            if (n) n = clip_plane(poly_a, n, poly_b, 4);
-            if (n) n = clip_plane(poly_b, n, poly_a, 5);
-            poly = poly_a;
-            npoly = (n >= 3) ? n : 0;
-            for (int j = 0; j < npoly; j++) persp_divide(poly[j]);
-            for (int j = 1; j + 1 < npoly; j++)
-                if (setup_subtri(st, cfg, fb, poly[0], poly[j], poly[j + 1], state_index, nullptr, nullptr)) count++;
+        if (shape != 4) v1 = load_vertex(b, dr.vbase + i1);
+        if (shape == 1) {
+            v2 = load_vertex(b, dr.vbase + i2);
+            if (inside_all(v0) && inside_all(v1) && inside_all(v2)) {
+                /* Sutherland-Hodgman returns its input unchanged when every vertex passes every plane */
+                persp_divide(v0); persp_divide(v1); persp_divide(v2);
+            } else {
+                shape = 2;
+                poly_a[0] = v0; poly_a[1] = v1; poly_a[2] = v2;
+                int m = clip_plane(poly_a, 3, poly_b, 0);       /* clipping.h:106-126 */
+                if (m) m = clip_plane(poly_b, m, poly_a, 1);
+                if (m) m = clip_plane(poly_a, m, poly_b, 2);
+                if (m) m = clip_plane(poly_b, m, poly_a, 3);
+                if (m) m = clip_plane(poly_a, m, poly_b, 4);
+                if (m) m = clip_plane(poly_b, m, poly_a, 5);
+                poly = poly_a;
+                npoly = (m >= 3) ? m : 0;
+                for (int j = 0; j < npoly; j++) persp_divide(poly[j]);
+            }
         }
     }
+
+    /* everything this thread's primitive turns into, in submission order; run once to count, once to write */
+#define MTGL_RUN_PRIMITIVE(WR_, CNT_, DST_, EYE_, ID0_)                                                                         \
+    switch (shape) {                                                                                                             \
+    case 1: setup_subtri(WR_, CNT_, DST_, EYE_, ID0_, b, st, cfg, fb, v0, v1, v2, state_index); break;                           \
+    case 2:                                                                                                                      \
+        for (int j = 1; j + 1 < npoly; j++)                                                                                      \
+            setup_subtri(WR_, CNT_, DST_, EYE_, ID0_, b, st, cfg, fb, poly[0], poly[j], poly[j + 1], state_index);               \
+        break;                                                                                                                   \
+    case 3: { Emitter em = { WR_, CNT_, DST_, EYE_, ID0_ }; setup_segment(em, st, fb, state_index, v0, v1); CNT_ = em.n; break; }   \
+    case 4: { Emitter em = { WR_, CNT_, DST_, EYE_, ID0_ }; setup_point(em, b.unorm8, st, cfg, fb, state_index, v0); CNT_ = em.n; break; } \
+    default: break;                                                                                                              \
+    }
+    uint32_t count = 0;
+    MTGL_RUN_PRIMITIVE(false, count, nullptr, nullptr, 0u)
 
     /* block-wide exclusive scan of the survivor counts -> submission-ordered slots */
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -328,25 +585,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(BatchDev b, FrameTarget
     }
     __syncthreads();
     if (count == 0 || chunk_slot0 == 0xFFFFFFFFu) return;
-    uint32_t slot = warp_sums[warp] + incl - count;         /* index inside the chunk */
-
-    TriRecord rec;
-    TriEye eye;
-    TriEye *eyep = b.need_eye ? &eye : nullptr;
-    if (!clipped) {
-        setup_subtri(st, cfg, fb, v0, v1, v2, state_index, &rec, eyep);
-        rec.id = (chunk << CHUNK_SHIFT) | slot;
-        store_record(b.records + chunk_slot0 + slot, rec);
-        if (eyep) b.rec_eye[chunk_slot0 + slot] = eye;
-    } else {
-        for (int j = 1; j + 1 < npoly; j++) {
-            if (!setup_subtri(st, cfg, fb, poly[0], poly[j], poly[j + 1], state_index, &rec, eyep)) continue;
-            rec.id = (chunk << CHUNK_SHIFT) | slot;
-            store_record(b.records + chunk_slot0 + slot, rec);
-            if (eyep) b.rec_eye[chunk_slot0 + slot] = eye;
-            slot++;
-        }
-    }
+    const uint32_t slot = warp_sums[warp] + incl - count;       /* index inside the chunk */
+    uint32_t written = 0;
+    TriRecord *const dst = b.records + chunk_slot0 + slot;
+    TriEye *const eye_dst = b.need_eye ? b.rec_eye + chunk_slot0 + slot : nullptr;
+    const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
+    MTGL_RUN_PRIMITIVE(true, written, dst, eye_dst, id0)
+#undef MTGL_RUN_PRIMITIVE
 }
 
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)

@@ -104,14 +104,18 @@ void release(DevBuf &b)
     b.ptr = nullptr; b.cap = 0;
 }
 
-uint32_t triangles_of(uint32_t mode, uint32_t n)   /* loop bounds of flush_* (raster.c:961-1017, 1199-1231) */
+uint32_t triangles_of(uint32_t mode, uint32_t n)   /* primitives per draw: loop bounds of flush_* (raster.c:288-296, 961-1231) */
 {
     switch (mode) {
     case G_TRIANGLES: return n / 3;
     case G_QUADS: return (n / 4) * 2;
     case G_TRIANGLE_STRIP: case G_TRIANGLE_FAN: case G_POLYGON: return n >= 3 ? n - 2 : 0;
     case G_QUAD_STRIP: return n >= 4 ? ((n - 2) / 2) * 2 : 0;
-    default: return 0;      /* points and lines: TODO(next) */
+    case G_POINTS: return n;                                /* raster.c:1044 */
+    case G_LINES: return n / 2;                             /* raster.c:293 */
+    case G_LINE_STRIP: return n >= 2 ? n - 1 : 0;           /* raster.c:1172-1176 */
+    case G_LINE_LOOP: return n >= 2 ? n : 0;                /* raster.c:1185-1195: n - 1 segments + the closing one */
+    default: return 0;
     }
 }
 
@@ -394,6 +398,9 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         if (rs.caps & MTGL_CAP_STENCIL_TEST) planes |= 4u;
         if ((rs.caps & MTGL_CAP_LIGHTING) && (rs.shade_model == G_PHONG || rs.light_model_two_side)) need_eye = true;
     }
+    bool outline_modes = false;
+    for (uint32_t i = 0; i < bt->n_states; i++)
+        if (bt->states[i].polygon_mode_front != G_FILL || bt->states[i].polygon_mode_back != G_FILL) outline_modes = true;
     if (bt->clear_mask & G_COLOR_BUFFER_BIT) planes |= 1u;
     if (bt->clear_mask & G_DEPTH_BUFFER_BIT) planes |= 2u;
     if (bt->clear_mask & G_STENCIL_BUFFER_BIT) planes |= 4u;
@@ -525,7 +532,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         if (pi.n_triangles > 0 && ntiles > 0) {
             const size_t nv = pi.n_vertices;
             const uint32_t chunks = (pi.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS;
-            const size_t rec_cap = (size_t)pi.n_triangles * 7;
+            /* worst case per primitive: 7 fan sub-triangles of a clipped triangle, each 3 outline records in GL_LINE/GL_POINT mode */
+            const size_t rec_cap = (size_t)pi.n_triangles * (outline_modes ? 21 : 7);
             if ((rc = reserve(d, d->v_clip, nv * 16)) || (rc = reserve(d, d->v_color, nv * 16)) || (rc = reserve(d, d->v_tex, nv * 16))) return rc;
             if (need_eye && ((rc = reserve(d, d->v_epos, nv * 16)) || (rc = reserve(d, d->v_enrm, nv * 16)))) return rc;
             if ((rc = reserve(d, d->records, rec_cap * sizeof(TriRecord)))) return rc;
@@ -572,7 +580,11 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         CU(cudaEventRecord(sev[4], d->stream));
         bool any_defer = false, any_in_order = false;
         for (const PassDraw &q : passes[pidx]) {
-            if (cfgs[bt->draws[q.draw].raster_state].flags & RC_DEFER) any_defer = true; else any_in_order = true;
+            const mtgl_draw &dq = bt->draws[q.draw];
+            const mtgl_state &sq = bt->states[dq.raster_state];
+            const bool filled = dq.mode >= G_TRIANGLES && sq.polygon_mode_front == G_FILL && sq.polygon_mode_back == G_FILL;
+            if ((cfgs[dq.raster_state].flags & RC_DEFER) && filled) any_defer = true; else any_in_order = true;
+            if ((cfgs[dq.raster_state].flags & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */
         }
         launch_raster(b, fb, clr, planes, any_defer && pi.n_triangles > 0, any_in_order, d->stream);
         CU(cudaEventRecord(sev[5], d->stream));
