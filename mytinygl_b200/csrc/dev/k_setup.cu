@@ -33,20 +33,6 @@ struct SVert {              /* vertex_t (graphics.h:438-446) minus the unused ob
     float epx, epy, epz, enx, eny, enz;
 };
 
-__device__ __forceinline__ SVert load_vertex(const BatchDev &b, uint32_t i)
-{
-    SVert o;
-    float4 p = b.v_clip[i], c = b.v_color[i], t = b.v_tex[i];
-    o.x = p.x; o.y = p.y; o.z = p.z; o.w = p.w;
-    o.r = c.x; o.g = c.y; o.b = c.z; o.a = c.w;
-    o.u = t.x; o.v = t.y; o.ez = t.z;
-    if (b.need_eye) {
-        float4 e = b.v_epos[i], n = b.v_enrm[i];
-        o.epx = e.x; o.epy = e.y; o.epz = e.z; o.enx = n.x; o.eny = n.y; o.enz = n.z;
-    } else { o.epx = o.epy = o.epz = 0.0f; o.enx = o.eny = 0.0f; o.enz = 1.0f; }
-    return o;
-}
-
 __device__ __forceinline__ float plane_dist(const SVert &v, int plane)   /* clipping.h:27-32: near far left right bottom top */
 {
     switch (plane) {
@@ -293,35 +279,36 @@ __device__ __noinline__ void setup_outline(Emitter &em, const mtgl_state *st, co
     }
 }
 
-/* One fan sub-triangle after the divide: snap, cull, then either set it up for filling or turn it into its
- * outline (3 LINE records) / corners (3 POINT records).  Mirrors raster.c:916-956, 847-898 and 458-529. */
-__device__ __forceinline__ void setup_subtri(const bool write, uint32_t &n_emitted, TriRecord *const dst, TriEye *const eye_dst, const uint32_t id0,
-                                             const BatchDev &bd, const mtgl_state *st, const RasterCfg *cfg, const FrameTargets &fb,
-                                             const SVert &a, const SVert &b, const SVert &c, uint32_t state_index)
+/* ---------------------------------------------------------------- filled triangles */
+struct ScreenTri {
+    int32_t x0, y0, x1, y1, x2, y2;     /* snapped corners */
+    float area;
+    uint32_t bbox_min, bbox_max;        /* x | y << 16, inclusive, clamped */
+    uint32_t mode;                      /* polygon mode of the facing side */
+    bool back;
+};
+enum { TRI_REJECT = 0, TRI_FILL = 1, TRI_OUTLINE = 2 };
+
+/* Everything render_triangle / rasterize_triangle_smooth decide from the three NDC positions alone
+ * (raster.c:916-956, 458-499): snap, cull, facing, polygon mode, bounding box, degenerate-area reject. */
+__device__ __forceinline__ int screen_setup(const mtgl_state *st, const FrameTargets &fb, float ax, float ay, float bx, float by, float cx, float cy,
+                                            ScreenTri &s)
 {
-    int32_t x0, y0, x1, y1, x2, y2;
-    to_screen(st, a.x, a.y, x0, y0);
-    to_screen(st, b.x, b.y, x1, y1);
-    to_screen(st, c.x, c.y, x2, y2);
+    to_screen(st, ax, ay, s.x0, s.y0);
+    to_screen(st, bx, by, s.x1, s.y1);
+    to_screen(st, cx, cy, s.x2, s.y2);
+    const int32_t x0 = s.x0, y0 = s.y0, x1 = s.x1, y1 = s.y1, x2 = s.x2, y2 = s.y2;
 
     /* signed area of the snapped triangle decides culling and facing (raster.c:923-935) */
     float sa = (float)(x1 - x0) * (float)(y2 - y0) - (float)(x2 - x0) * (float)(y1 - y0);
     if (st->caps & MTGL_CAP_CULL_FACE) {
         bool front = (st->front_face == G_CCW) ? (sa < 0) : (sa > 0);
         bool cull = (st->cull_face_mode == G_FRONT) ? front : (st->cull_face_mode == G_BACK) ? !front : true;
-        if (cull) return;
+        if (cull) return TRI_REJECT;
     }
-    bool back = (st->front_face == G_CCW) ? (sa >= 0) : (sa < 0);
-    uint32_t pm = back ? st->polygon_mode_back : st->polygon_mode_front;
-
-    if (pm == G_POINT || pm == G_LINE) {
-        const int32_t sx[3] = { x0, x1, x2 }, sy[3] = { y0, y1, y2 };
-        Emitter em = { write, n_emitted, dst, eye_dst, id0 };       /* the rare paths are out of line and take the emitter by reference */
-        const SVert ca = a, cb = b, cc = c;         /* copies: the caller's vertices must stay in registers */
-        setup_outline(em, st, cfg, fb, ca, cb, cc, sx, sy, state_index, pm == G_POINT);
-        n_emitted = em.n;
-        return;
-    }
+    s.back = (st->front_face == G_CCW) ? (sa >= 0) : (sa < 0);
+    s.mode = s.back ? st->polygon_mode_back : st->polygon_mode_front;
+    if (s.mode == G_POINT || s.mode == G_LINE) return TRI_OUTLINE;
 
     int32_t minX = imin3(x0, x1, x2), minY = imin3(y0, y1, y2), maxX = imax3(x0, x1, x2), maxY = imax3(y0, y1, y2);
     const int32_t *vp = st->viewport;
@@ -336,11 +323,11 @@ __device__ __forceinline__ void setup_subtri(const bool write, uint32_t &n_emitt
         if (maxX >= sc[0] + sc[2]) maxX = sc[0] + sc[2] - 1;
         if (maxY >= sc[1] + sc[3]) maxY = sc[1] + sc[3] - 1;
     }
-    if (minX > maxX || minY > maxY) return;
+    if (minX > maxX || minY > maxY) return TRI_REJECT;
 
     /* edge_function(x0,y0,x1,y1,x2,y2) (raster.c:483, 299-302) */
-    float area = ((float)x2 - (float)x0) * ((float)y1 - (float)y0) - ((float)y2 - (float)y0) * ((float)x1 - (float)x0);
-    if (fabsf(area) < 0.5f) return;
+    s.area = ((float)x2 - (float)x0) * ((float)y1 - (float)y0) - ((float)y2 - (float)y0) * ((float)x1 - (float)x0);
+    if (fabsf(s.area) < 0.5f) return TRI_REJECT;
 
     /* pixels outside the framebuffer are dropped by the bounds-checked accessors (framebuffer.h:92-134);
      * rows outside this device's band belong to another GPU */
@@ -348,19 +335,26 @@ __device__ __forceinline__ void setup_subtri(const bool write, uint32_t &n_emitt
     if (maxX >= fb.width) maxX = fb.width - 1;
     if (minY < fb.band_y0) minY = fb.band_y0;
     if (maxY >= fb.band_y1) maxY = fb.band_y1 - 1;
-    if (minX > maxX || minY > maxY) return;
-    if (!write) { n_emitted++; return; }
+    if (minX > maxX || minY > maxY) return TRI_REJECT;
+    s.bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
+    s.bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
+    return TRI_FILL;
+}
 
+/* the 160-byte record of a filled triangle (+ the eye-space side record for per-fragment lighting) */
+__device__ __forceinline__ void write_fill(TriRecord *dst, TriEye *eye_dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index, const ScreenTri &s,
+                                           const SVert &a, const SVert &b, const SVert &c)
+{
     TriRecord rec;
-    rec.x0 = x0; rec.y0 = y0; rec.x1 = x1; rec.y1 = y1; rec.x2 = x2; rec.y2 = y2;
-    rec.state_flags = state_index | (back ? STATE_BACK_BIT : 0u) | ((cfg->flags & RC_DEFER) ? STATE_DEFER_BIT : 0u);
-    rec.id = 0;
-    rec.bbox_min = (uint32_t)minX | ((uint32_t)minY << 16);
-    rec.bbox_max = (uint32_t)maxX | ((uint32_t)maxY << 16);
+    rec.x0 = s.x0; rec.y0 = s.y0; rec.x1 = s.x1; rec.y1 = s.y1; rec.x2 = s.x2; rec.y2 = s.y2;
+    rec.state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cfg->flags & RC_DEFER) ? STATE_DEFER_BIT : 0u);
+    rec.id = id;
+    rec.bbox_min = s.bbox_min;
+    rec.bbox_max = s.bbox_max;
     rec.z0 = a.z; rec.z1 = b.z; rec.z2 = c.z;
     rec.w0 = a.w; rec.w1 = b.w; rec.w2 = c.w;
-    rec.area = area;
-    rec.inv_area = 1.0f / area;
+    rec.area = s.area;
+    rec.inv_area = 1.0f / s.area;
     rec.c0[0] = a.r; rec.c0[1] = a.g; rec.c0[2] = a.b; rec.c0[3] = a.a;
     rec.c1[0] = b.r; rec.c1[1] = b.g; rec.c1[2] = b.b; rec.c1[3] = b.a;
     rec.c2[0] = c.r; rec.c2[1] = c.g; rec.c2[2] = c.b; rec.c2[3] = c.a;
@@ -369,7 +363,7 @@ __device__ __forceinline__ void setup_subtri(const bool write, uint32_t &n_emitt
 
     float lod = 0.0f;                   /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
     if (cfg->flags & RC_TEXTURED) {
-        float screen_area = fabsf(area) * 0.5f;
+        float screen_area = fabsf(s.area) * 0.5f;
         float tw = (float)cfg->tex_w, th = (float)cfg->tex_h;
         float du1 = (b.u - a.u) * tw, dv1 = (b.v - a.v) * th;
         float du2 = (c.u - a.u) * tw, dv2 = (c.v - a.v) * th;
@@ -383,19 +377,34 @@ __device__ __forceinline__ void setup_subtri(const bool write, uint32_t &n_emitt
         }
     }
     rec.lod = lod;
-    TriEye eye;
-    if (bd.need_eye) {
+    store_record(dst, rec);
+    if (eye_dst) {
+        TriEye eye;
         eye.ep0[0] = a.epx; eye.ep0[1] = a.epy; eye.ep0[2] = a.epz; eye.ep0[3] = 0.0f;
         eye.ep1[0] = b.epx; eye.ep1[1] = b.epy; eye.ep1[2] = b.epz; eye.ep1[3] = 0.0f;
         eye.ep2[0] = c.epx; eye.ep2[1] = c.epy; eye.ep2[2] = c.epz; eye.ep2[3] = 0.0f;
         eye.en0[0] = a.enx; eye.en0[1] = a.eny; eye.en0[2] = a.enz; eye.en0[3] = 0.0f;
         eye.en1[0] = b.enx; eye.en1[1] = b.eny; eye.en1[2] = b.enz; eye.en1[3] = 0.0f;
         eye.en2[0] = c.enx; eye.en2[1] = c.eny; eye.en2[2] = c.enz; eye.en2[3] = 0.0f;
+        *eye_dst = eye;
     }
-    rec.id = id0 + n_emitted;
-    store_record(dst + n_emitted, rec);
-    if (bd.need_eye) eye_dst[n_emitted] = eye;
-    n_emitted++;
+}
+
+/* One fan sub-triangle after the divide, general form (used by the out-of-line path): fill it, or turn it into its
+ * outline (3 LINE records) / corners (3 POINT records).  Mirrors raster.c:916-956, 847-898 and 458-529. */
+__device__ void setup_subtri(Emitter &em, const mtgl_state *st, const RasterCfg *cfg, const FrameTargets &fb,
+                             const SVert &a, const SVert &b, const SVert &c, uint32_t state_index)
+{
+    ScreenTri s;
+    const int kind = screen_setup(st, fb, a.x, a.y, b.x, b.y, c.x, c.y, s);
+    if (kind == TRI_REJECT) return;
+    if (kind == TRI_OUTLINE) {
+        const int32_t sx[3] = { s.x0, s.x1, s.x2 }, sy[3] = { s.y0, s.y1, s.y2 };
+        setup_outline(em, st, cfg, fb, a, b, c, sx, sy, state_index, s.mode == G_POINT);
+        return;
+    }
+    if (em.write) write_fill(em.dst + em.n, em.eye_dst ? em.eye_dst + em.n : nullptr, em.id0 + em.n, cfg, state_index, s, a, b, c);
+    em.n++;
 }
 
 /* ---------------------------------------------------------------- line segments and points as primitives */
@@ -481,7 +490,79 @@ __device__ __forceinline__ uint32_t find_draw_tri(const uint32_t *base, uint32_t
     return lo;
 }
 
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(BatchDev b, FrameTargets fb)
+/* where a thread finds its vertices; passed by value to the out-of-line path so that the kernel's parameter
+ * block never has its address taken (that would copy it to local memory at entry) */
+struct VertexSrc {
+    const float4 *clip, *color, *tex, *epos, *enrm;
+    const float *unorm8;
+    int need_eye;
+};
+
+__device__ __forceinline__ SVert load_vertex(const VertexSrc &b, uint32_t i)
+{
+    SVert o;
+    float4 p = b.clip[i], c = b.color[i], t = b.tex[i];
+    o.x = p.x; o.y = p.y; o.z = p.z; o.w = p.w;
+    o.r = c.x; o.g = c.y; o.b = c.z; o.a = c.w;
+    o.u = t.x; o.v = t.y; o.ez = t.z;
+    if (b.need_eye) {
+        float4 e = b.epos[i], n = b.enrm[i];
+        o.epx = e.x; o.epy = e.y; o.epz = e.z; o.enx = n.x; o.eny = n.y; o.enz = n.z;
+    } else { o.epx = o.epy = o.epz = 0.0f; o.enx = o.eny = 0.0f; o.enz = 1.0f; }
+    return o;
+}
+
+/* Everything that is not an unclipped filled triangle: clipped polygons (a fan of up to 7 sub-triangles), outlines,
+ * line segments and points.  Out of line and self-contained (it reloads its vertices) so that the common path
+ * stays in registers.  Returns the number of records emitted. */
+__device__ __noinline__ uint32_t setup_rare(const bool write, TriRecord *const dst, TriEye *const eye_dst, const uint32_t id0, const VertexSrc src,
+                                            const mtgl_state *st, const RasterCfg *cfg, const FrameTargets fb, const uint32_t state_index,
+                                            const int shape, const uint32_t i0, const uint32_t i1, const uint32_t i2)
+{
+    Emitter em = { write, 0u, dst, eye_dst, id0 };
+    if (shape == 4) {
+        setup_point(em, src.unorm8, st, cfg, fb, state_index, load_vertex(src, i0));
+    } else if (shape == 3) {
+        setup_segment(em, st, fb, state_index, load_vertex(src, i0), load_vertex(src, i1));
+    } else if (shape == 5) {        /* unclipped triangle with polygon mode GL_LINE / GL_POINT */
+        SVert a = load_vertex(src, i0), b = load_vertex(src, i1), c = load_vertex(src, i2);
+        persp_divide(a); persp_divide(b); persp_divide(c);
+        setup_subtri(em, st, cfg, fb, a, b, c, state_index);
+    } else {
+        SVert poly_a[MAX_CLIP], poly_b[MAX_CLIP];
+        poly_a[0] = load_vertex(src, i0); poly_a[1] = load_vertex(src, i1); poly_a[2] = load_vertex(src, i2);
+        int m = clip_plane(poly_a, 3, poly_b, 0);       /* clipping.h:106-126 */
+        if (m) m = clip_plane(poly_b, m, poly_a, 1);
+        if (m) m = clip_plane(poly_a, m, poly_b, 2);
+        if (m) m = clip_plane(poly_b, m, poly_a, 3);
+        if (m) m = clip_plane(poly_a, m, poly_b, 4);
+        if (m) m = clip_plane(poly_b, m, poly_a, 5);
+        if (m < 3) return 0u;
+        for (int j = 0; j < m; j++) persp_divide(poly_a[j]);
+        for (int j = 1; j + 1 < m; j++) setup_subtri(em, st, cfg, fb, poly_a[0], poly_a[j], poly_a[j + 1], state_index);
+    }
+    return em.n;
+}
+
+__device__ __forceinline__ bool inside_all(const float4 &v)
+{
+    return (v.z + v.w) >= 0 && (v.w - v.z) >= 0 && (v.x + v.w) >= 0 && (v.w - v.x) >= 0 && (v.y + v.w) >= 0 && (v.w - v.y) >= 0;
+}
+
+__device__ __forceinline__ void persp_divide_xy(const float4 &v, float &x, float &y)   /* the x, y half of persp_divide */
+{
+    if (fabsf(v.w) < 1e-6f) { x = 0.0f; y = 0.0f; return; }
+    float iw = 1.0f / v.w;
+    x = v.x * iw; y = v.y * iw;
+}
+
+/*
+ * The common case -- a triangle with all three vertices inside the frustum and polygon mode GL_FILL -- is decided
+ * from the three clip-space positions alone (48 B); colours, texture coordinates and eye-space attributes are only
+ * fetched for survivors, after the scan, so culled triangles cost a third of the traffic and nothing but the
+ * screen-space result (10 registers) lives across the barrier.
+ */
+__global__ void __launch_bounds__(SETUP_THREADS, 2) k_setup(BatchDev b, FrameTargets fb)
 {
     __shared__ uint32_t warp_sums[SETUP_THREADS / 32];
     __shared__ uint32_t chunk_slot0;
@@ -490,20 +571,19 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(BatchDev b, FrameTarget
     const uint32_t t = chunk * SETUP_THREADS + threadIdx.x;
     const bool valid = t < b.n_triangles;
 
-    SVert v0, v1, v2;
-    SVert poly_a[MAX_CLIP], poly_b[MAX_CLIP];
-    SVert *poly = nullptr;
-    int npoly = 0;
-    int shape = 0;          /* 0 nothing, 1 unclipped triangle, 2 clipped polygon, 3 line segment, 4 point */
+    int shape = 0;          /* 0 nothing, 1 unclipped filled triangle, 2 clipped polygon, 3 line segment, 4 point, 5 unclipped outline */
     const mtgl_state *st = nullptr;
     const RasterCfg *cfg = nullptr;
     uint32_t state_index = 0;
+    uint32_t i0 = 0, i1 = 0, i2 = 0;
+    uint32_t count = 0;
+    ScreenTri s;
+    const VertexSrc src = { b.v_clip, b.v_color, b.v_tex, b.v_epos, b.v_enrm, b.unorm8, b.need_eye ? 1 : 0 };
 
     if (valid) {
         uint32_t d = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t);
         const DevDraw &dr = b.draws[d];
         const uint32_t k = t - dr.tbase, n = dr.count;
-        uint32_t i0 = 0, i1 = 0, i2 = 0;
         state_index = dr.raster_state;
         st = b.states + state_index;
         cfg = b.cfgs + state_index;
@@ -518,43 +598,19 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(BatchDev b, FrameTarget
         case G_QUAD_STRIP: { uint32_t q = 2 * (k >> 1); i0 = q; if (k & 1) { i1 = q + 3; i2 = q + 2; } else { i1 = q + 1; i2 = q + 3; } shape = 1; break; }
         default: i0 = 0; i1 = k + 1; i2 = k + 2; shape = 1; break;     /* fan, polygon */
         }
-        v0 = load_vertex(b, dr.vbase + i0);
-        if (shape != 4) v1 = load_vertex(b, dr.vbase + i1);
+        i0 += dr.vbase; i1 += dr.vbase; i2 += dr.vbase;
         if (shape == 1) {
-            v2 = load_vertex(b, dr.vbase + i2);
-            if (inside_all(v0) && inside_all(v1) && inside_all(v2)) {
+            const float4 p0 = src.clip[i0], p1 = src.clip[i1], p2 = src.clip[i2];
+            if (inside_all(p0) && inside_all(p1) && inside_all(p2)) {
                 /* Sutherland-Hodgman returns its input unchanged when every vertex passes every plane */
-                persp_divide(v0); persp_divide(v1); persp_divide(v2);
-            } else {
-                shape = 2;
-                poly_a[0] = v0; poly_a[1] = v1; poly_a[2] = v2;
-                int m = clip_plane(poly_a, 3, poly_b, 0);       /* clipping.h:106-126 */
-                if (m) m = clip_plane(poly_b, m, poly_a, 1);
-                if (m) m = clip_plane(poly_a, m, poly_b, 2);
-                if (m) m = clip_plane(poly_b, m, poly_a, 3);
-                if (m) m = clip_plane(poly_a, m, poly_b, 4);
-                if (m) m = clip_plane(poly_b, m, poly_a, 5);
-                poly = poly_a;
-                npoly = (m >= 3) ? m : 0;
-                for (int j = 0; j < npoly; j++) persp_divide(poly[j]);
-            }
+                float ax, ay, bx, by, cx, cy;
+                persp_divide_xy(p0, ax, ay); persp_divide_xy(p1, bx, by); persp_divide_xy(p2, cx, cy);
+                const int kind = screen_setup(st, fb, ax, ay, bx, by, cx, cy, s);
+                if (kind == TRI_OUTLINE) shape = 5; else count = (uint32_t)kind;
+            } else shape = 2;
         }
+        if (shape > 1) count = setup_rare(false, nullptr, nullptr, 0u, src, st, cfg, fb, state_index, shape, i0, i1, i2);
     }
-
-    /* everything this thread's primitive turns into, in submission order; run once to count, once to write */
-#define MTGL_RUN_PRIMITIVE(WR_, CNT_, DST_, EYE_, ID0_)                                                                         \
-    switch (shape) {                                                                                                             \
-    case 1: setup_subtri(WR_, CNT_, DST_, EYE_, ID0_, b, st, cfg, fb, v0, v1, v2, state_index); break;                           \
-    case 2:                                                                                                                      \
-        for (int j = 1; j + 1 < npoly; j++)                                                                                      \
-            setup_subtri(WR_, CNT_, DST_, EYE_, ID0_, b, st, cfg, fb, poly[0], poly[j], poly[j + 1], state_index);               \
-        break;                                                                                                                   \
-    case 3: { Emitter em = { WR_, CNT_, DST_, EYE_, ID0_ }; setup_segment(em, st, fb, state_index, v0, v1); CNT_ = em.n; break; }   \
-    case 4: { Emitter em = { WR_, CNT_, DST_, EYE_, ID0_ }; setup_point(em, b.unorm8, st, cfg, fb, state_index, v0); CNT_ = em.n; break; } \
-    default: break;                                                                                                              \
-    }
-    uint32_t count = 0;
-    MTGL_RUN_PRIMITIVE(false, count, nullptr, nullptr, 0u)
 
     /* block-wide exclusive scan of the survivor counts -> submission-ordered slots */
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -586,12 +642,16 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(BatchDev b, FrameTarget
     __syncthreads();
     if (count == 0 || chunk_slot0 == 0xFFFFFFFFu) return;
     const uint32_t slot = warp_sums[warp] + incl - count;       /* index inside the chunk */
-    uint32_t written = 0;
     TriRecord *const dst = b.records + chunk_slot0 + slot;
     TriEye *const eye_dst = b.need_eye ? b.rec_eye + chunk_slot0 + slot : nullptr;
     const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
-    MTGL_RUN_PRIMITIVE(true, written, dst, eye_dst, id0)
-#undef MTGL_RUN_PRIMITIVE
+    if (shape == 1) {
+        SVert v0 = load_vertex(src, i0), v1 = load_vertex(src, i1), v2 = load_vertex(src, i2);
+        persp_divide(v0); persp_divide(v1); persp_divide(v2);
+        write_fill(dst, eye_dst, id0, cfg, state_index, s, v0, v1, v2);
+    } else {
+        setup_rare(true, dst, eye_dst, id0, src, st, cfg, fb, state_index, shape, i0, i1, i2);
+    }
 }
 
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
