@@ -109,11 +109,14 @@ enum : uint32_t {
     RC_TEXTURED = 1u << 4, RC_ALPHA_TEST = 1u << 5, RC_FOG = 1u << 6, RC_FLAT = 1u << 7,
     RC_PHONG = 1u << 8, RC_LIGHTING = 1u << 9, RC_TWO_SIDE = 1u << 10, RC_PERSPECTIVE = 1u << 11,
     RC_DEPTH_RANGE_01 = 1u << 12,   /* depth range is exactly [0,1]: the double expression of raster.c:548 is the float one */
-    RC_DEFER = 1u << 13             /* no blending, no alpha test, full colour mask: the colour work can be deferred */
+    RC_DEFER = 1u << 13,            /* no blending, no alpha test, full colour mask: the colour work can be deferred */
+    RC_UNORDERED = 1u << 14         /* RC_DEFER + depth test and write, no stencil, the batch's common LESS/LEQUAL/GREATER/GEQUAL
+                                     * function: the surviving fragment of a pixel does not depend on submission order (k_vis.cu) */
 };
 
-/* TriRecord.state_flags: state block index | record kind << 28 | deferrable << 30 | back-facing << 31 */
-constexpr uint32_t STATE_INDEX_MASK = 0x0FFFFFFFu;
+/* TriRecord.state_flags: state block index | unordered << 27 | record kind << 28 | deferrable << 30 | back-facing << 31 */
+constexpr uint32_t STATE_INDEX_MASK = 0x07FFFFFFu;
+constexpr uint32_t STATE_UNORD_BIT = 1u << 27;
 constexpr uint32_t STATE_KIND_SHIFT = 28;
 constexpr uint32_t STATE_KIND_MASK = 3u << STATE_KIND_SHIFT;
 constexpr uint32_t KIND_TRIANGLE = 0u, KIND_LINE = 1u, KIND_POINT = 2u;
@@ -352,7 +355,8 @@ struct BatchDev {
     DevCounters *counters;
     /* binning */
     uint32_t *tile_count, *tile_offset, *tile_cursor;
-    uint32_t *tile_flags;           /* != 0: the tile references a record whose colour work cannot be deferred */
+    uint32_t *tile_flags;           /* bit 0: the tile references a record whose colour work cannot be deferred (general kernel);
+                                     * bit 1: it references a record outside the unordered class (sorted visibility kernel) */
     uint32_t *tile_list; uint32_t list_capacity;
     uint32_t *vis_plane;            /* visibility buffer in HBM (record index per pixel) between K4a and K4b */
     const float *unorm8;
@@ -363,9 +367,18 @@ void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
-/* any_deferrable / any_in_order: whether some draw of the pass has a deferrable / a non-deferrable raster state */
+/* which raster kernels a pass needs, decided on the host from the raster states its draws use */
+struct RasterPlan {
+    bool any_deferrable;        /* some draw has a deferrable state (K4a + K4b) */
+    bool any_ordered_vis;       /* ... that is not in the unordered class (sorted K4a) */
+    bool any_in_order;          /* some draw needs in-order shading (general kernel) */
+    uint32_t unordered_func;    /* depth function (0..7) of the unordered class, 0 when the class is empty */
+    bool unordered_range01;     /* every unordered state has depth range [0,1] */
+};
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,
-                   bool any_deferrable, bool any_in_order, cudaStream_t s);
+                   const RasterPlan &plan, cudaStream_t s);
+void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
+                          bool all_range01, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);
 uint64_t kernel_launch_count();

@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
     for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; r0 < n; r0 += gridDim.x * blockDim.x) {
         const uint32_t r = r0 + lane;
         int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, ntiles = 0;
-        bool in_order = false;
+        uint32_t tflags = 0;      /* bit 0: needs in-order shading, bit 1: not in the unordered class */
         if (r < n) {
             const TriRecord *rec = b.records + r;
             uint4 box = *reinterpret_cast<const uint4 *>(&rec->bbox_min);     /* bbox_min, bbox_max, state_flags, id */
             tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG; tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
             ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0; ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
             ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-            in_order = !(box.z & STATE_DEFER_BIT);
+            tflags = ((box.z & STATE_DEFER_BIT) ? 0u : 1u) | ((box.z & STATE_UNORD_BIT) ? 0u : 2u);
         }
         if (ntiles > LARGE_TILES) {
             if (PASS == 0) {
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
             if ((int)lane == leader) base = atomicAdd(PASS == 0 ? &b.tile_count[tile] : &b.tile_cursor[tile], (uint32_t)__popc(peers));
-            if (PASS == 0 && in_order) atomicOr(&b.tile_flags[tile], 1u);
+            if (PASS == 0 && tflags) atomicOr(&b.tile_flags[tile], tflags);
             base = __shfl_sync(peers, base, leader);
             if (PASS == 1) b.tile_list[b.tile_offset[tile] + base + __popc(peers & lt_mask)] = r;
         } else if (ntiles > 1) {
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
                     uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
                     if (PASS == 0) {
                         atomicAdd(&b.tile_count[tile], 1u);
-                        if (in_order) atomicOr(&b.tile_flags[tile], 1u);
+                        if (tflags) atomicOr(&b.tile_flags[tile], tflags);
                     } else {
                         uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
                         b.tile_list[b.tile_offset[tile] + at] = r;
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
             uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
             if (PASS == 0) {
                 atomicAdd(&b.tile_count[tile], 1u);
-                if (!(rec->state_flags & STATE_DEFER_BIT)) atomicOr(&b.tile_flags[tile], 1u);
+                const uint32_t tflags = ((rec->state_flags & STATE_DEFER_BIT) ? 0u : 1u) | ((rec->state_flags & STATE_UNORD_BIT) ? 0u : 2u);
+                if (tflags) atomicOr(&b.tile_flags[tile], tflags);
             } else {
                 uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
                 b.tile_list[b.tile_offset[tile] + at] = r;

@@ -832,7 +832,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
 
     const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
     const uint32_t flagged = (b.tile_count && L) ? b.tile_flags[tile] : 0u;
-    if (VIS ? (flagged != 0) : (only_flagged && flagged == 0)) return;
+    /* flags 0: the order-independent kernel (k_vis.cu) owns the tile, also when it only needs clearing; 2: sorted
+     * visibility kernel; bit 0 set: general kernel */
+    if (VIS ? (flagged != 2u) : (only_flagged && !(flagged & 1u))) return;
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
     if (L == 0 && !clr_here) return;
 
@@ -928,7 +930,7 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
     const int vw = min(TILE_W, fb.width - px0), vh = min((ty << TILE_LOG) + TILE_H, fb.band_y1) - py0;
     if (vw <= 0 || vh <= 0) return;
     const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
-    if (L && b.tile_flags[tile]) return;                    /* the general kernel owns this tile */
+    if (L && (b.tile_flags[tile] & 1u)) return;             /* the general kernel owns this tile */
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -988,8 +990,9 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
 }
 
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes,
-                   bool any_deferrable, bool any_in_order, cudaStream_t s)
+                   const RasterPlan &plan, cudaStream_t s)
 {
+    const bool any_deferrable = plan.any_deferrable, any_in_order = plan.any_in_order;
     static bool configured[64] = { false };
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1006,8 +1009,12 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
      * (it then also owns the tiles that only need clearing). */
     const bool split = any_deferrable && b.tile_count != nullptr && b.vis_plane != nullptr;
     if (split) {
-        k_raster<true><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
-        note_launch();
+        /* tiles whose records are all order-independent (and the tiles that only need clearing) */
+        launch_vis_unordered(b, fb, clear, planes, plan.unordered_func ? plan.unordered_func : 1u, plan.unordered_range01, s);
+        if (plan.any_ordered_vis) {
+            k_raster<true><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
+            note_launch();
+        }
         if (planes & 1u) {
             k_shade<<<tiles, 256, 0, s>>>(b, fb, clear);
             note_launch();

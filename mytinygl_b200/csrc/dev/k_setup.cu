@@ -347,7 +347,9 @@ __device__ __forceinline__ void write_fill(TriRecord *dst, TriEye *eye_dst, uint
 {
     TriRecord rec;
     rec.x0 = s.x0; rec.y0 = s.y0; rec.x1 = s.x1; rec.y1 = s.y1; rec.x2 = s.x2; rec.y2 = s.y2;
-    rec.state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cfg->flags & RC_DEFER) ? STATE_DEFER_BIT : 0u);
+    const uint32_t cflags = cfg->flags;
+    rec.state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
+                      ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
     rec.id = id;
     rec.bbox_min = s.bbox_min;
     rec.bbox_max = s.bbox_max;
@@ -362,7 +364,7 @@ __device__ __forceinline__ void write_fill(TriRecord *dst, TriEye *eye_dst, uint
     rec.ez0 = a.ez; rec.ez1 = b.ez; rec.ez2 = c.ez;
 
     float lod = 0.0f;                   /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
-    if (cfg->flags & RC_TEXTURED) {
+    if (cflags & RC_TEXTURED) {
         float screen_area = fabsf(s.area) * 0.5f;
         float tw = (float)cfg->tex_w, th = (float)cfg->tex_h;
         float du1 = (b.u - a.u) * tw, dv1 = (b.v - a.v) * th;

@@ -1,0 +1,356 @@
+/*
+ * k_vis.cu -- K4a, order-independent form: coverage + depth resolution of the tiles whose records all belong to
+ * the batch's "unordered class" (RC_UNORDERED: deferrable colour work, depth test and depth write on, no stencil
+ * test, one common depth function out of GL_LESS / GL_LEQUAL / GL_GREATER / GL_GEQUAL).
+ *
+ * Replaces the scan loop, edge test and depth test/write of rasterize_triangle_smooth (src/raster.c:532-548,
+ * 582-587, 707-710) for those tiles.  The reference draws fragments in submission order; for this class the final
+ * depth and the surviving fragment of a pixel are a pure function of the SET of fragments:
+ *
+ *     GL_LESS    : smallest depth, ties -> earliest submission (the later equal depth fails `<`), the value already
+ *                  in the depth plane wins ties;
+ *     GL_LEQUAL  : smallest depth, ties -> latest submission, a fragment beats an equal value in the plane;
+ *     GL_GREATER / GL_GEQUAL : the same with the largest depth.
+ *
+ * So each pixel holds one 64-bit key  (order-preserving image of the depth) << 32 | tie-break word  in shared
+ * memory, every fragment does an atomicMin on it in whatever order the hardware gets to it, and the result is
+ * bit-identical to the in-order loop.  What that buys: no per-tile sort, no pixel ownership, no window limit, and
+ * freedom to map work to lanes by triangle size --
+ *
+ *   small triangles (clamped box <= 256 pixels, the C4 case: ~14 covered pixels each): a warp fetches 32 record
+ *     heads, one per lane, then works on four triangles at a time, 8 lanes each; a lane owns one column of the box
+ *     and walks its rows with the column part of the three edge functions hoisted;
+ *   large triangles: queued, then rasterised by all 8 warps together over 8x4 pixel blocks.
+ *
+ * The arithmetic is the reference's, operation for operation (edge_function raster.c:299-302, barycentrics 541-543,
+ * depth 546-548); the only liberty is algebraically exact: for clockwise triangles all three edge values and
+ * 1/area are negated together (IEEE negation is exact), which turns the two inclusive tests of raster.c:539-540
+ * into one.
+ *
+ * The kernel leaves the depth plane and, per pixel, the record index of the surviving fragment (or VIS_NONE) in the
+ * visibility plane for k_shade (K4b).  The depth / stencil part of the batch's leading glClear is fused here.
+ *
+ * Algorithmic bytes per tile: 64 B head per referenced record + 4 B list entry, 4 B/pixel depth in (unless
+ * cleared), 4 B/pixel depth out, 4 B/pixel visibility out.
+ */
+#include "dev_common.cuh"
+
+namespace mtgl_dev_impl {
+
+void note_launch();
+
+constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
+constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start 4 banks apart, 16-byte aligned */
+constexpr int VIS_WINDOW = 1024;        /* list entries per round = capacity of the large-triangle queue */
+constexpr int VIS_SMALL_AREA = 256;     /* clamped box area up to which 8 lanes handle a triangle */
+constexpr int VIS_COORD_LIMIT = 1 << 22;    /* |snapped coordinate| below which pixel - vertex differences are exact integers in float */
+
+struct VisSmem {
+    unsigned long long key[TILE_H * VIS_PITCH];
+    uint32_t large_rec[VIS_WINDOW];
+    uint32_t next_chunk;
+    uint32_t large_n;
+};
+
+/* monotone map float -> uint32 (total order of the reals, -0 < +0) and back */
+__device__ __forceinline__ uint32_t ord_bits(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord_float(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+struct VisMode {
+    uint32_t inv;           /* 0xFFFFFFFF for GL_GREATER / GL_GEQUAL: the key holds the complement, so min = largest depth */
+    bool first_wins;        /* GL_LESS / GL_GREATER: equal depths keep the earliest fragment and the plane's value */
+    bool all_range01;       /* every unordered state has depth range [0,1] */
+};
+
+__device__ __forceinline__ unsigned long long make_key(const VisMode &m, float depth, uint32_t id)
+{
+    const uint32_t hi = ord_bits(depth) ^ m.inv;
+    const uint32_t lo = m.first_wins ? id + 1u : 0xFFFFFFFEu - id;
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void key_min(unsigned long long *addr, unsigned long long key)
+{
+    /* keys only ever decrease, so a fragment that loses against a (possibly stale) read loses for good */
+    if (key < *reinterpret_cast<volatile unsigned long long *>(addr)) atomicMin(addr, key);
+}
+
+/* window-space depth of raster.c:546-548 */
+__device__ __forceinline__ float depth_of(float z, bool range01, double dnear, double dfar)
+{
+    const float d = (z + 1.0f) * 0.5f;
+    if (range01) return d;
+    return (float)((double)d * (dfar - dnear) + dnear);
+}
+
+__device__ __forceinline__ bool coord_small(int32_t v)      /* |v| < VIS_COORD_LIMIT without overflowing on INT32_MIN */
+{
+    return (uint32_t)v + (uint32_t)VIS_COORD_LIMIT < 2u * (uint32_t)VIS_COORD_LIMIT;
+}
+
+struct VisHead {                /* the 64 leading bytes of a record: rows 0-3 */
+    int4 row0, row1;            /* x0 y0 x1 y1 | x2 y2 area inv_area */
+    uint4 row2;                 /* bbox_min bbox_max state_flags id */
+    float z0, z1, z2;
+};
+
+__device__ __forceinline__ void load_vis_head(VisHead &h, const TriRecord *rec)
+{
+    h.row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+    h.row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+    h.row2 = __ldg(reinterpret_cast<const uint4 *>(rec) + 2);
+    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
+    h.z0 = row3.x; h.z1 = row3.y; h.z2 = row3.z;
+}
+
+/* the three edge functions of a triangle prepared for evaluation at (px, py):
+ * e_k = (px - ax[k]) * dy[k] - (py - ay[k]) * dx[k], with all of them and inv_area negated for negative areas */
+struct EdgeSet {
+    float ax[3], ay[3], dx[3], dy[3];
+    float inv_area;
+};
+
+__device__ __forceinline__ void prepare_edges(EdgeSet &E, int x0, int y0, int x1, int y1, int x2, int y2, float area, float inv_area)
+{
+    const float fx0 = (float)x0, fy0 = (float)y0, fx1 = (float)x1, fy1 = (float)y1, fx2 = (float)x2, fy2 = (float)y2;
+    /* raster.c:536-538: w0 = edge(v1, v2, p), w1 = edge(v2, v0, p), w2 = edge(v0, v1, p) */
+    E.ax[0] = fx1; E.ay[0] = fy1; E.dx[0] = fx2 - fx1; E.dy[0] = fy2 - fy1;
+    E.ax[1] = fx2; E.ay[1] = fy2; E.dx[1] = fx0 - fx2; E.dy[1] = fy0 - fy2;
+    E.ax[2] = fx0; E.ay[2] = fy0; E.dx[2] = fx1 - fx0; E.dy[2] = fy1 - fy0;
+    E.inv_area = inv_area;
+    if (!(area > 0)) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { E.dx[k] = -E.dx[k]; E.dy[k] = -E.dy[k]; }
+        E.inv_area = -inv_area;
+    }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS, 4)
+k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_func, uint32_t all_range01)
+{
+    __shared__ VisSmem sm;
+
+    const uint32_t tile = blockIdx.x;
+    const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
+    const int px0 = tx << TILE_LOG, py0t = ty << TILE_LOG;
+    const int py0 = max(py0t, fb.band_y0);          /* shared-memory row 0 is framebuffer row py0 */
+    const int vw = min(TILE_W, fb.width - px0);
+    const int vh = min(py0t + TILE_H, fb.band_y1) - py0;
+    if (vw <= 0 || vh <= 0) return;
+
+    const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
+    if (L && b.tile_flags[tile] != 0u) return;      /* an ordered kernel owns this tile */
+    const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
+    if (L == 0 && !clr_here) return;
+
+    VisMode mode;
+    mode.inv = (depth_func == 4u || depth_func == 6u) ? 0xFFFFFFFFu : 0u;
+    mode.first_wins = (depth_func == 1u || depth_func == 4u);
+    mode.all_range01 = all_range01 != 0u;
+    const uint32_t none_lo = mode.first_wins ? 0u : 0xFFFFFFFFu;
+
+    /* ---- fused glClear (gl_api.c:409-457): stencil goes straight to HBM, depth becomes the initial keys ---- */
+    const int cx0 = max(clr.x0 - px0, 0), cy0 = max(clr.y0 - py0, 0);
+    const int cx1 = min(clr.x1 - px0, vw), cy1 = min(clr.y1 - py0, vh);
+    const bool clr_depth = clr_here && (clr.mask & G_DEPTH_BUFFER_BIT) && (planes & 2u);
+    if (clr_here && (clr.mask & G_STENCIL_BUFFER_BIT) && (planes & 4u)) {
+        for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+            const int y = i >> 6, x = i & 63;
+            if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) fb.stencil[(size_t)(py0 + y) * fb.width + px0 + x] = (uint8_t)clr.stencil;
+        }
+    }
+    if (L == 0) {
+        if (clr_depth)
+            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+                const int y = i >> 6, x = i & 63;
+                if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) fb.depth[(size_t)(py0 + y) * fb.width + px0 + x] = clr.depth;
+            }
+        return;
+    }
+    const bool clr_full = clr_depth && cx0 == 0 && cy0 == 0 && cx1 == vw && cy1 == vh;
+    for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+        const int y = i >> 6, x = i & 63;
+        float d = 0.0f;
+        if (x < vw) {
+            if (clr_full || (clr_depth && x >= cx0 && x < cx1 && y >= cy0 && y < cy1)) d = clr.depth;
+            else d = fb.depth[(size_t)(py0 + y) * fb.width + px0 + x];
+        }
+        sm.key[y * VIS_PITCH + x] = ((unsigned long long)(ord_bits(d) ^ mode.inv) << 32) | none_lo;
+    }
+    if (threadIdx.x == 0) { sm.next_chunk = 0; sm.large_n = 0; }
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = (int)(lane >> 3), col = (int)(lane & 7);
+    const uint32_t *list = b.tile_list + b.tile_offset[tile];
+
+    for (uint32_t ws = 0; ws < L; ws += VIS_WINDOW) {
+        const uint32_t wn = min((uint32_t)VIS_WINDOW, L - ws);
+
+        /* ---- phase 1: warps take 32 list entries at a time; small triangles are finished on the spot ---- */
+        for (;;) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(&sm.next_chunk, 32u);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            if (c >= wn) break;
+            const uint32_t e = c + lane;
+            VisHead h;
+            uint32_t r = 0, box = 0;
+            bool small = false;
+            if (e < wn) {
+                r = list[ws + e];
+                load_vis_head(h, b.records + r);
+                /* the record's box is already clamped to viewport, scissor, framebuffer and band: clamp to the tile */
+                const int X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0), Y0 = max((int)(h.row2.x >> 16) - py0, 0);
+                const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
+                box = (uint32_t)X0 | ((uint32_t)Y0 << 8) | ((uint32_t)X1 << 16) | ((uint32_t)Y1 << 24);
+                small = (X1 - X0 + 1) * (Y1 - Y0 + 1) <= VIS_SMALL_AREA && coord_small(h.row0.x) && coord_small(h.row0.y) &&
+                        coord_small(h.row0.z) && coord_small(h.row0.w) && coord_small(h.row1.x) && coord_small(h.row1.y);
+                if (!small) sm.large_rec[atomicAdd(&sm.large_n, 1u)] = r;
+            } else {
+                h.row0 = make_int4(0, 0, 0, 0); h.row1 = make_int4(0, 0, 0, 0); h.row2 = make_uint4(0, 0, 0, 0); h.z0 = h.z1 = h.z2 = 0.0f;
+            }
+            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, small);
+#pragma unroll 1
+            for (int it = 0; it < 8; it++) {
+                const uint32_t quad = (smask >> (it * 4)) & 0xFu;
+                if (!quad) continue;
+                const int src = it * 4 + grp;
+                /* each group of 8 lanes receives the head of its triangle */
+                const int x0 = __shfl_sync(0xFFFFFFFFu, h.row0.x, src), y0 = __shfl_sync(0xFFFFFFFFu, h.row0.y, src);
+                const int x1 = __shfl_sync(0xFFFFFFFFu, h.row0.z, src), y1 = __shfl_sync(0xFFFFFFFFu, h.row0.w, src);
+                const int x2 = __shfl_sync(0xFFFFFFFFu, h.row1.x, src), y2 = __shfl_sync(0xFFFFFFFFu, h.row1.y, src);
+                const float area = __int_as_float(__shfl_sync(0xFFFFFFFFu, h.row1.z, src));
+                const float inv_area = __int_as_float(__shfl_sync(0xFFFFFFFFu, h.row1.w, src));
+                const uint32_t state = __shfl_sync(0xFFFFFFFFu, h.row2.z, src);
+                const uint32_t id = __shfl_sync(0xFFFFFFFFu, h.row2.w, src);
+                const float z0 = __shfl_sync(0xFFFFFFFFu, h.z0, src), z1 = __shfl_sync(0xFFFFFFFFu, h.z1, src), z2 = __shfl_sync(0xFFFFFFFFu, h.z2, src);
+                const uint32_t bx = __shfl_sync(0xFFFFFFFFu, box, src);
+                if (!((quad >> grp) & 1u)) continue;
+
+                const int X0 = (int)(bx & 0xFFu), Y0 = (int)((bx >> 8) & 0xFFu), X1 = (int)((bx >> 16) & 0xFFu), Y1 = (int)(bx >> 24);
+                bool range01 = true;
+                double dnear = 0.0, dfar = 1.0;
+                if (!mode.all_range01) {
+                    const RasterCfg *cfg = b.cfgs + (state & STATE_INDEX_MASK);
+                    range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
+                    dnear = cfg->depth_near; dfar = cfg->depth_far;
+                }
+                EdgeSet E;
+                prepare_edges(E, x0, y0, x1, y1, x2, y2, area, inv_area);
+                const float fy = (float)(py0 + Y0);
+                for (int cx = X0 + col; cx <= X1; cx += 8) {
+                    const float fx = (float)(px0 + cx);
+                    /* column part of the edge functions; the row part advances by exact integer steps */
+                    const float t0 = (fx - E.ax[0]) * E.dy[0], t1 = (fx - E.ax[1]) * E.dy[1], t2 = (fx - E.ax[2]) * E.dy[2];
+                    float q0 = fy - E.ay[0], q1 = fy - E.ay[1], q2 = fy - E.ay[2];
+                    unsigned long long *kp = &sm.key[Y0 * VIS_PITCH + cx];
+                    for (int y = Y0; y <= Y1; y++, kp += VIS_PITCH, q0 += 1.0f, q1 += 1.0f, q2 += 1.0f) {
+                        const float e0 = t0 - q0 * E.dx[0], e1 = t1 - q1 * E.dx[1], e2 = t2 - q2 * E.dx[2];
+                        if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
+                            const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
+                            const float z = b0 * z0 + b1 * z1 + b2 * z2;
+                            key_min(kp, make_key(mode, depth_of(z, range01, dnear, dfar), id));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- phase 2: the queued large triangles, all warps on each, 8x4 pixel blocks dealt round-robin ---- */
+        const uint32_t nl = sm.large_n;
+        for (uint32_t q = 0; q < nl; q++) {
+            VisHead h;
+            load_vis_head(h, b.records + sm.large_rec[q]);
+            const int X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0), Y0 = max((int)(h.row2.x >> 16) - py0, 0);
+            const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
+            bool range01 = true;
+            double dnear = 0.0, dfar = 1.0;
+            if (!mode.all_range01) {
+                const RasterCfg *cfg = b.cfgs + (h.row2.z & STATE_INDEX_MASK);
+                range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
+                dnear = cfg->depth_near; dfar = cfg->depth_far;
+            }
+            EdgeSet E;
+            prepare_edges(E, h.row0.x, h.row0.y, h.row0.z, h.row0.w, h.row1.x, h.row1.y, __int_as_float(h.row1.z), __int_as_float(h.row1.w));
+            const int nbx = (X1 - X0 + 8) >> 3, nby = (Y1 - Y0 + 4) >> 2;
+            const int nblk = nbx * nby;
+            /* rotate the first warp with the queue position so that one-block triangles do not all land on warp 0 */
+            for (int blk = (int)((warp + 8u - (q & 7u)) & 7u); blk < nblk; blk += RASTER_THREADS / 32) {
+                const int byi = blk / nbx, bxi = blk - byi * nbx;
+                const int x = X0 + bxi * 8 + (int)(lane & 7), y = Y0 + byi * 4 + (int)(lane >> 3);
+                if (x > X1 || y > Y1) continue;
+                const float fx = (float)(px0 + x), fy = (float)(py0 + y);
+                const float e0 = (fx - E.ax[0]) * E.dy[0] - (fy - E.ay[0]) * E.dx[0];
+                const float e1 = (fx - E.ax[1]) * E.dy[1] - (fy - E.ay[1]) * E.dx[1];
+                const float e2 = (fx - E.ax[2]) * E.dy[2] - (fy - E.ay[2]) * E.dx[2];
+                if (fminf(fminf(e0, e1), e2) >= 0.0f) {
+                    const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
+                    const float z = b0 * h.z0 + b1 * h.z1 + b2 * h.z2;
+                    key_min(&sm.key[y * VIS_PITCH + x], make_key(mode, depth_of(z, range01, dnear, dfar), h.row2.w));
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { sm.next_chunk = 0; sm.large_n = 0; }
+        __syncthreads();
+    }
+
+    /* ---- write-back: depth plane + visibility plane (record index of the surviving fragment) ---- */
+    const uint32_t slot_mask = (1u << CHUNK_SHIFT) - 1u;
+    const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
+    if (vec) {
+        for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+            const int y = i >> 4, q4 = (i & 15) * 4;
+            float dv[4];
+            uint32_t rv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned long long key = sm.key[y * VIS_PITCH + q4 + k];
+                const uint32_t lo = (uint32_t)key;
+                dv[k] = ord_float((uint32_t)(key >> 32) ^ mode.inv);
+                if (lo == none_lo) rv[k] = VIS_NONE;
+                else {
+                    const uint32_t id = mode.first_wins ? lo - 1u : 0xFFFFFFFEu - lo;
+                    rv[k] = __ldg(&b.chunk_base[id >> CHUNK_SHIFT]) + (id & slot_mask);
+                }
+            }
+            const size_t p = (size_t)(py0 + y) * fb.width + px0 + q4;
+            if (planes & 2u) *reinterpret_cast<float4 *>(fb.depth + p) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            *reinterpret_cast<uint4 *>(b.vis_plane + p) = make_uint4(rv[0], rv[1], rv[2], rv[3]);
+        }
+    } else {
+        for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+            const int y = i >> 6, x = i & 63;
+            if (x >= vw) continue;
+            const unsigned long long key = sm.key[y * VIS_PITCH + x];
+            const uint32_t lo = (uint32_t)key;
+            uint32_t rv = VIS_NONE;
+            if (lo != none_lo) {
+                const uint32_t id = mode.first_wins ? lo - 1u : 0xFFFFFFFEu - lo;
+                rv = __ldg(&b.chunk_base[id >> CHUNK_SHIFT]) + (id & slot_mask);
+            }
+            const size_t p = (size_t)(py0 + y) * fb.width + px0 + x;
+            if (planes & 2u) fb.depth[p] = ord_float((uint32_t)(key >> 32) ^ mode.inv);
+            b.vis_plane[p] = rv;
+        }
+    }
+}
+
+void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
+                          bool all_range01, cudaStream_t s)
+{
+    const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
+    k_vis<<<tiles, RASTER_THREADS, 0, s>>>(b, fb, clear, planes, depth_func, all_range01 ? 1u : 0u);
+    note_launch();
+}
+
+} // namespace mtgl_dev_impl

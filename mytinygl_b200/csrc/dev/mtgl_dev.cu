@@ -424,6 +424,21 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     /* ---- batch arena: states | cfgs | staged | blob (shared by all passes) ---- */
     std::vector<RasterCfg> cfgs(bt->n_states);
     for (uint32_t i = 0; i < bt->n_states; i++) build_cfg(d, bt->states[i], cfgs[i]);
+    /* The unordered class (k_vis.cu): deferrable states with depth test + write, no stencil test and the depth
+     * function of the first such state, when that is one of LESS / LEQUAL / GREATER / GEQUAL. */
+    uint32_t unordered_func = 0;
+    bool unordered_range01 = true;
+    for (uint32_t i = 0; i < bt->n_states; i++) {
+        RasterCfg &c = cfgs[i];
+        const uint32_t need = RC_DEFER | RC_DEPTH_TEST | RC_DEPTH_WRITE;
+        if ((c.flags & need) != need || (c.flags & RC_STENCIL)) continue;
+        const uint32_t fn = c.depth_func;
+        if (fn != 1u && fn != 3u && fn != 4u && fn != 6u) continue;
+        if (!unordered_func) unordered_func = fn;
+        if (fn != unordered_func) continue;
+        c.flags |= RC_UNORDERED;
+        if (!(c.flags & RC_DEPTH_RANGE_01)) unordered_range01 = false;
+    }
     const size_t sz_states = align_up((size_t)bt->n_states * sizeof(mtgl_state), 256);
     const size_t sz_cfgs = align_up((size_t)bt->n_states * sizeof(RasterCfg), 256);
     const size_t sz_staged = align_up((size_t)bt->n_vertices * sizeof(mtgl_in_vertex), 256);
@@ -578,15 +593,23 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             CU(cudaEventRecord(sev[3], d->stream));
         }
         CU(cudaEventRecord(sev[4], d->stream));
-        bool any_defer = false, any_in_order = false;
+        bool any_defer = false, any_in_order = false, any_ordered_vis = false;
         for (const PassDraw &q : passes[pidx]) {
             const mtgl_draw &dq = bt->draws[q.draw];
             const mtgl_state &sq = bt->states[dq.raster_state];
+            const uint32_t cf = cfgs[dq.raster_state].flags;
             const bool filled = dq.mode >= G_TRIANGLES && sq.polygon_mode_front == G_FILL && sq.polygon_mode_back == G_FILL;
-            if ((cfgs[dq.raster_state].flags & RC_DEFER) && filled) any_defer = true; else any_in_order = true;
-            if ((cfgs[dq.raster_state].flags & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */
+            if ((cf & RC_DEFER) && filled) any_defer = true; else any_in_order = true;
+            if ((cf & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */
+            if ((cf & RC_DEFER) && !(cf & RC_UNORDERED) && dq.mode >= G_TRIANGLES) any_ordered_vis = true;
         }
-        launch_raster(b, fb, clr, planes, any_defer && pi.n_triangles > 0, any_in_order, d->stream);
+        RasterPlan plan;
+        plan.any_deferrable = any_defer && pi.n_triangles > 0;
+        plan.any_ordered_vis = any_ordered_vis;
+        plan.any_in_order = any_in_order;
+        plan.unordered_func = unordered_func;
+        plan.unordered_range01 = unordered_range01;
+        launch_raster(b, fb, clr, planes, plan, d->stream);
         CU(cudaEventRecord(sev[5], d->stream));
     }
     CU(cudaEventRecord(d->ev_stop, d->stream));

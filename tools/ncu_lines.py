@@ -16,13 +16,23 @@ import tempfile
 from pathlib import Path
 
 
-def sass_rows(rep):
+def sass_rows(rep, want=""):
+    """rows of the first kernel section whose name contains `want` (a report may hold several kernels)"""
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[1]
-    ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) == len(hdr)]
-    return ix, data
+    sections, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "hdr": None, "data": []}
+            sections.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None and len(r) == len(cur["hdr"]):
+            cur["data"].append(r)
+    sec = next((x for x in sections if want in x["name"]), sections[0])
+    print(f"# kernel: {sec['name']}")
+    ix = {h: i for i, h in enumerate(sec["hdr"])}
+    return ix, sec["data"]
 
 
 def disasm_functions(lib):
@@ -49,7 +59,7 @@ def disasm_functions(lib):
 def main():
     rep, lib = sys.argv[1], sys.argv[2]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    ix, data = sass_rows(rep)
+    ix, data = sass_rows(rep, sys.argv[3] if len(sys.argv) > 3 else "")
     funcs = disasm_functions(lib)
 
     def f(r, k):
