@@ -254,7 +254,26 @@ __device__ __forceinline__ void load_material(MaterialRegs &m, const mtgl_materi
     m.shininess = s->shininess;
 }
 
-static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, float px, float py, float pz,
+/* powf(x, y) for x > 0 as the lighting equations use it (lighting.h:103, 132).  glibc's powf is correctly rounded in
+ * all but a vanishing fraction of cases; for the integral exponents that shininess and spot exponents usually are,
+ * binary powering in double (<= 13 roundings of 2^-53, then one rounding to float) has the same property and costs a
+ * dozen FP64 multiplies instead of CUDA's ~100-instruction powf, which is kept for every other exponent. */
+__device__ __forceinline__ int integral_exponent(float y)
+{
+    return (y >= 1.0f && y <= 128.0f && y == truncf(y)) ? (int)y : 0;
+}
+__device__ __forceinline__ float pow_pos(float x, float y, int iy)
+{
+    if (iy == 0) return powf(x, y);
+    double r = 1.0, b = (double)x;
+    for (int n = iy; n; n >>= 1) {
+        if (n & 1) r *= b;
+        b *= b;
+    }
+    return (float)r;
+}
+
+__device__ __forceinline__ Color4 lighting_body(const mtgl_state *st, float px, float py, float pz,
                                                 float nx, float ny, float nz, const MaterialRegs &mat)
 {
     Color4 res;
@@ -264,6 +283,7 @@ static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, flo
     res.a = mat.diffuse[3];
     if (st->caps & MTGL_CAP_NORMALIZE) normalize3(nx, ny, nz);
     const uint32_t local_viewer = st->light_model_local_viewer;
+    const int ishine = integral_exponent(mat.shininess);
 
     for (int i = 0; i < MTGL_MAX_LIGHTS; i++) {
         const mtgl_light *l = &st->lights[i];
@@ -283,7 +303,7 @@ static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, flo
             if (l->spot_cutoff < 180.0f) {
                 float cos_angle = -(Lx * l->spot_dir_unit[0] + Ly * l->spot_dir_unit[1] + Lz * l->spot_dir_unit[2]);
                 if (cos_angle < l->cos_cutoff) att = 0.0f;
-                else att *= powf(cos_angle, l->spot_exponent);
+                else att *= (cos_angle > 0.0f) ? pow_pos(cos_angle, l->spot_exponent, integral_exponent(l->spot_exponent)) : powf(cos_angle, l->spot_exponent);
             }
         }
         if (att <= 0.0f) continue;
@@ -310,7 +330,7 @@ static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, flo
                 normalize3(Hx, Hy, Hz);
                 float NdotH = nx * Hx + ny * Hy + nz * Hz;
                 if (NdotH > 0.0f) {
-                    float spec = powf(NdotH, mat.shininess) * att;
+                    float spec = pow_pos(NdotH, mat.shininess, ishine) * att;
                     res.r = res.r + (mat.specular[0] * l->specular[0]) * spec;
                     res.g = res.g + (mat.specular[1] * l->specular[1]) * spec;
                     res.b = res.b + (mat.specular[2] * l->specular[2]) * spec;
@@ -320,6 +340,13 @@ static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, flo
         }
     }
     return color_clamp(res);
+}
+
+/* out-of-line copy for the register-bound raster / set-up kernels */
+static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, float px, float py, float pz,
+                                                float nx, float ny, float nz, const MaterialRegs &mat)
+{
+    return lighting_body(st, px, py, pz, nx, ny, nz, mat);
 }
 
 /* ---------------------------------------------------------------- launch wrappers (defined in the .cu files) */
@@ -352,6 +379,7 @@ struct BatchDev {
     TriRecord *records; TriEye *rec_eye; uint32_t record_capacity;
     uint32_t *chunk_base;           /* first record slot of every 256-triangle chunk */
     uint32_t *large_list;
+    uint4 *bin_rows;                /* copy of every record's row 2 (bbox_min, bbox_max, state_flags, id): all the binner reads */
     DevCounters *counters;
     /* binning */
     uint32_t *tile_count, *tile_offset, *tile_cursor;

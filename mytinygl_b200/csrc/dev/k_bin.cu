@@ -72,8 +72,7 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
         int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, ntiles = 0;
         uint32_t tflags = 0;      /* bit 0: needs in-order shading, bit 1: not in the unordered class */
         if (r < n) {
-            const TriRecord *rec = b.records + r;
-            uint4 box = *reinterpret_cast<const uint4 *>(&rec->bbox_min);     /* bbox_min, bbox_max, state_flags, id */
+            const uint4 box = b.bin_rows[r];        /* bbox_min, bbox_max, state_flags, id */
             tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG; tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
             ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0; ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
             ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
@@ -185,9 +184,9 @@ static int bin_grid() { return 148 * 8; }
 
 void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 {
-    k_bin_small<0><<<bin_grid(), 256, 0, s>>>(b, fb);
+    /* the count pass of the small records is fused into k_setup; only the cooperative binner remains */
     k_bin_large<0><<<148 * 4, 128, 0, s>>>(b, fb);
-    note_launch(); note_launch();
+    note_launch();
 }
 
 void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)

@@ -921,7 +921,6 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
     __shared__ float un[256];
     __shared__ uint16_t list[TILE_W * TILE_H];
     __shared__ uint32_t warp_total[8];
-    __shared__ uint32_t list_n;
     un[threadIdx.x] = b.unorm8[threadIdx.x];
 
     const uint32_t tile = blockIdx.x;
@@ -934,34 +933,43 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-
-    /* pass 1: colour clear + compaction of the pixels to shade (64 pixels x 4 rows per iteration, coalesced) */
-    uint32_t n_before = 0;
-    if (threadIdx.x == 0) list_n = 0;
-    __syncthreads();
-    for (int row0 = 0; row0 < vh; row0 += 4) {
-        const int x = (int)(threadIdx.x & 63), y = row0 + (int)(threadIdx.x >> 6);
-        const bool in = x < vw && y < vh;
-        const size_t p = (size_t)(py0 + y) * fb.width + px0 + x;
-        bool has = false;
-        if (in) {
-            has = L && b.vis_plane[p] != VIS_NONE;
-            if (!has && (clr.mask & G_COLOR_BUFFER_BIT) && px0 + x >= clr.x0 && px0 + x < clr.x1 && py0 + y >= clr.y0 && py0 + y < clr.y1)
-                fb.color[p] = clr.color;
+    /* pass 1: colour clear + compaction of the pixels to shade.  A thread owns column (tid & 63) of rows
+     * (tid >> 6) + 4k: its 16 visibility loads are issued back to back, then one block scan places its survivors. */
+    const int x = (int)(threadIdx.x & 63), yb = (int)(threadIdx.x >> 6);
+    uint32_t has_mask = 0;
+    {
+        uint32_t v[TILE_H / 4];
+#pragma unroll
+        for (int k = 0; k < TILE_H / 4; k++) {
+            const int y = yb + 4 * k;
+            v[k] = (L && x < vw && y < vh) ? b.vis_plane[(size_t)(py0 + y) * fb.width + px0 + x] : VIS_NONE;
         }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-        if (lane == 0) warp_total[warp] = __popc(m);
-        __syncthreads();
-        uint32_t before = n_before;
-        for (uint32_t w = 0; w < warp; w++) before += warp_total[w];
-        if (has) list[before + __popc(m & lt_mask)] = (uint16_t)(y * TILE_W + x);
-        uint32_t total = 0;
-        for (int w = 0; w < 8; w++) total += warp_total[w];
-        n_before += total;
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TILE_H / 4; k++) {
+            const int y = yb + 4 * k;
+            if (v[k] != VIS_NONE) has_mask |= 1u << k;
+            else if (x < vw && y < vh && (clr.mask & G_COLOR_BUFFER_BIT) && px0 + x >= clr.x0 && px0 + x < clr.x1 && py0 + y >= clr.y0 && py0 + y < clr.y1)
+                fb.color[(size_t)(py0 + y) * fb.width + px0 + x] = clr.color;
+        }
     }
-    const uint32_t n = n_before;
+    const uint32_t mine = (uint32_t)__popc(has_mask);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += up;
+    }
+    if (lane == 31) warp_total[warp] = incl;
+    __syncthreads();
+    uint32_t at = incl - mine, n = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) {
+        const uint32_t wt = warp_total[w];
+        if (w < warp) at += wt;
+        n += wt;
+    }
+    for (uint32_t m = has_mask; m; m &= m - 1) list[at++] = (uint16_t)((yb + 4 * (__ffs(m) - 1)) * TILE_W + x);
+    __syncthreads();
 
     /* pass 2: shade the compacted pixels */
     for (uint32_t i = threadIdx.x; i < n; i += 256) {

@@ -123,12 +123,40 @@ __device__ __forceinline__ int imin3(int a, int b, int c) { return min(a, min(b,
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(a, max(b, c)); }
 
 /* ---------------------------------------------------------------- record emission */
+/* where the binner's first pass (count references per tile, k_bin.cu) is fused into set-up */
+struct BinOut {
+    TriRecord *records;
+    uint4 *bin_rows;
+    uint32_t *tile_count, *tile_flags, *large_list;
+    DevCounters *counters;
+    int32_t tiles_x, tile_y0;
+};
+
+/* one record's contribution to the per-tile reference counts; records spanning many tiles go to the cooperative binner */
+__device__ __forceinline__ void count_tiles_single(const BinOut &bo, uint32_t r, uint32_t bbox_min, uint32_t bbox_max, uint32_t state_flags)
+{
+    const int tx0 = (int)(bbox_min & 0xFFFFu) >> TILE_LOG, tx1 = (int)(bbox_max & 0xFFFFu) >> TILE_LOG;
+    const int ty0 = ((int)(bbox_min >> 16) >> TILE_LOG) - bo.tile_y0, ty1 = ((int)(bbox_max >> 16) >> TILE_LOG) - bo.tile_y0;
+    if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > LARGE_TILES) {
+        bo.large_list[atomicAdd(&bo.counters->large_count, 1u)] = r;
+        return;
+    }
+    const uint32_t tflags = ((state_flags & STATE_DEFER_BIT) ? 0u : 1u) | ((state_flags & STATE_UNORD_BIT) ? 0u : 2u);
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+            const uint32_t tile = (uint32_t)(ty * bo.tiles_x + tx);
+            atomicAdd(&bo.tile_count[tile], 1u);
+            if (tflags) atomicOr(&bo.tile_flags[tile], tflags);
+        }
+}
+
 struct Emitter {
     bool write;             /* false: counting pass */
     uint32_t n;             /* records emitted so far by this thread */
     TriRecord *dst;         /* first slot of this thread (write pass) */
     TriEye *eye_dst;
     uint32_t id0;           /* ordered id of the first slot */
+    const BinOut *bin;
 };
 
 __device__ __forceinline__ void store_record(TriRecord *dst, const TriRecord &r)
@@ -145,6 +173,9 @@ __device__ __forceinline__ void emit(Emitter &em, TriRecord &rec, const TriEye *
         rec.id = em.id0 + em.n;
         store_record(em.dst + em.n, rec);
         if (eye && em.eye_dst) em.eye_dst[em.n] = *eye;
+        const uint32_t r = (uint32_t)(em.dst + em.n - em.bin->records);
+        em.bin->bin_rows[r] = make_uint4(rec.bbox_min, rec.bbox_max, rec.state_flags, rec.id);
+        count_tiles_single(*em.bin, r, rec.bbox_min, rec.bbox_max, rec.state_flags);
     }
     em.n++;
 }
@@ -342,8 +373,8 @@ __device__ __forceinline__ int screen_setup(const mtgl_state *st, const FrameTar
 }
 
 /* the 160-byte record of a filled triangle (+ the eye-space side record for per-fragment lighting) */
-__device__ __forceinline__ void write_fill(TriRecord *dst, TriEye *eye_dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index, const ScreenTri &s,
-                                           const SVert &a, const SVert &b, const SVert &c)
+__device__ __forceinline__ uint4 write_fill(TriRecord *dst, TriEye *eye_dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index, const ScreenTri &s,
+                                            const SVert &a, const SVert &b, const SVert &c)
 {
     TriRecord rec;
     rec.x0 = s.x0; rec.y0 = s.y0; rec.x1 = s.x1; rec.y1 = s.y1; rec.x2 = s.x2; rec.y2 = s.y2;
@@ -390,6 +421,7 @@ __device__ __forceinline__ void write_fill(TriRecord *dst, TriEye *eye_dst, uint
         eye.en2[0] = c.enx; eye.en2[1] = c.eny; eye.en2[2] = c.enz; eye.en2[3] = 0.0f;
         *eye_dst = eye;
     }
+    return make_uint4(rec.bbox_min, rec.bbox_max, rec.state_flags, rec.id);
 }
 
 /* One fan sub-triangle after the divide, general form (used by the out-of-line path): fill it, or turn it into its
@@ -405,7 +437,12 @@ __device__ void setup_subtri(Emitter &em, const mtgl_state *st, const RasterCfg 
         setup_outline(em, st, cfg, fb, a, b, c, sx, sy, state_index, s.mode == G_POINT);
         return;
     }
-    if (em.write) write_fill(em.dst + em.n, em.eye_dst ? em.eye_dst + em.n : nullptr, em.id0 + em.n, cfg, state_index, s, a, b, c);
+    if (em.write) {
+        const uint4 row = write_fill(em.dst + em.n, em.eye_dst ? em.eye_dst + em.n : nullptr, em.id0 + em.n, cfg, state_index, s, a, b, c);
+        const uint32_t r = (uint32_t)(em.dst + em.n - em.bin->records);
+        em.bin->bin_rows[r] = row;
+        count_tiles_single(*em.bin, r, row.x, row.y, row.z);
+    }
     em.n++;
 }
 
@@ -517,11 +554,11 @@ __device__ __forceinline__ SVert load_vertex(const VertexSrc &b, uint32_t i)
 /* Everything that is not an unclipped filled triangle: clipped polygons (a fan of up to 7 sub-triangles), outlines,
  * line segments and points.  Out of line and self-contained (it reloads its vertices) so that the common path
  * stays in registers.  Returns the number of records emitted. */
-__device__ __noinline__ uint32_t setup_rare(const bool write, TriRecord *const dst, TriEye *const eye_dst, const uint32_t id0, const VertexSrc src,
+__device__ __noinline__ uint32_t setup_rare(const bool write, TriRecord *const dst, TriEye *const eye_dst, const uint32_t id0, const BinOut bin, const VertexSrc src,
                                             const mtgl_state *st, const RasterCfg *cfg, const FrameTargets fb, const uint32_t state_index,
                                             const int shape, const uint32_t i0, const uint32_t i1, const uint32_t i2)
 {
-    Emitter em = { write, 0u, dst, eye_dst, id0 };
+    Emitter em = { write, 0u, dst, eye_dst, id0, &bin };
     if (shape == 4) {
         setup_point(em, src.unorm8, st, cfg, fb, state_index, load_vertex(src, i0));
     } else if (shape == 3) {
@@ -581,6 +618,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 2) k_setup(BatchDev b, FrameTar
     uint32_t count = 0;
     ScreenTri s;
     const VertexSrc src = { b.v_clip, b.v_color, b.v_tex, b.v_epos, b.v_enrm, b.unorm8, b.need_eye ? 1 : 0 };
+    const BinOut bin = { b.records, b.bin_rows, b.tile_count, b.tile_flags, b.large_list, b.counters, fb.tiles_x, fb.tile_y0 };
 
     if (valid) {
         uint32_t d = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t);
@@ -611,7 +649,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 2) k_setup(BatchDev b, FrameTar
                 if (kind == TRI_OUTLINE) shape = 5; else count = (uint32_t)kind;
             } else shape = 2;
         }
-        if (shape > 1) count = setup_rare(false, nullptr, nullptr, 0u, src, st, cfg, fb, state_index, shape, i0, i1, i2);
+        if (shape > 1) count = setup_rare(false, nullptr, nullptr, 0u, bin, src, st, cfg, fb, state_index, shape, i0, i1, i2);
     }
 
     /* block-wide exclusive scan of the survivor counts -> submission-ordered slots */
@@ -642,18 +680,43 @@ __global__ void __launch_bounds__(SETUP_THREADS, 2) k_setup(BatchDev b, FrameTar
         }
     }
     __syncthreads();
-    if (count == 0 || chunk_slot0 == 0xFFFFFFFFu) return;
-    const uint32_t slot = warp_sums[warp] + incl - count;       /* index inside the chunk */
-    TriRecord *const dst = b.records + chunk_slot0 + slot;
-    TriEye *const eye_dst = b.need_eye ? b.rec_eye + chunk_slot0 + slot : nullptr;
-    const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
-    if (shape == 1) {
-        SVert v0 = load_vertex(src, i0), v1 = load_vertex(src, i1), v2 = load_vertex(src, i2);
-        persp_divide(v0); persp_divide(v1); persp_divide(v2);
-        write_fill(dst, eye_dst, id0, cfg, state_index, s, v0, v1, v2);
-    } else {
-        setup_rare(true, dst, eye_dst, id0, src, st, cfg, fb, state_index, shape, i0, i1, i2);
+    /* no early exit: the whole warp stays for the aggregated tile counting below */
+    bool counted = false;
+    uint32_t r = 0;
+    uint4 row = make_uint4(0u, 0u, 0u, 0u);
+    if (count != 0 && chunk_slot0 != 0xFFFFFFFFu) {
+        const uint32_t slot = warp_sums[warp] + incl - count;       /* index inside the chunk */
+        r = chunk_slot0 + slot;
+        TriRecord *const dst = b.records + r;
+        TriEye *const eye_dst = b.need_eye ? b.rec_eye + r : nullptr;
+        const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
+        if (shape == 1) {
+            SVert v0 = load_vertex(src, i0), v1 = load_vertex(src, i1), v2 = load_vertex(src, i2);
+            persp_divide(v0); persp_divide(v1); persp_divide(v2);
+            row = write_fill(dst, eye_dst, id0, cfg, state_index, s, v0, v1, v2);
+            b.bin_rows[r] = row;
+            counted = true;
+        } else {
+            setup_rare(true, dst, eye_dst, id0, bin, src, st, cfg, fb, state_index, shape, i0, i1, i2);   /* counts its own records */
+        }
     }
+
+    /* ---- fused first pass of the binner (k_bin.cu): references per tile.  Mesh-ordered triangles of one warp mostly
+     * fall into the same tile, so single-tile records are counted with one atomic per distinct tile. ---- */
+    int tx0 = 0, ty0 = 0, ntiles = 0;
+    if (counted) {
+        tx0 = (int)(row.x & 0xFFFFu) >> TILE_LOG; ty0 = ((int)(row.x >> 16) >> TILE_LOG) - fb.tile_y0;
+        const int tx1 = (int)(row.y & 0xFFFFu) >> TILE_LOG, ty1 = ((int)(row.y >> 16) >> TILE_LOG) - fb.tile_y0;
+        ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+    }
+    const uint32_t single = __ballot_sync(0xFFFFFFFFu, ntiles == 1);
+    if (ntiles == 1) {
+        const uint32_t tile = (uint32_t)(ty0 * fb.tiles_x + tx0);
+        const uint32_t tflags = ((row.z & STATE_DEFER_BIT) ? 0u : 1u) | ((row.z & STATE_UNORD_BIT) ? 0u : 2u);
+        const uint32_t peers = __match_any_sync(single, tile);
+        if ((int)lane == __ffs(peers) - 1) atomicAdd(&b.tile_count[tile], (uint32_t)__popc(peers));
+        if (tflags) atomicOr(&b.tile_flags[tile], tflags);
+    } else if (ntiles > 1) count_tiles_single(bin, r, row.x, row.y, row.z);
 }
 
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)

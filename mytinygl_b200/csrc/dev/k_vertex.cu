@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_vertex(BatchDev b)
                 }
             }
         }
-        vc = compute_lighting(st, ex, ey, ez, enx, eny, enz, mat);
+        vc = lighting_body(st, ex, ey, ez, enx, eny, enz, mat);
     }
 
     /* clip = P * eye   (raster.c:48-56) */

@@ -51,7 +51,7 @@ struct mtgl_dev {
     BufObj buf[kMaxObjects];
     float *unorm8 = nullptr;
 
-    DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list;
+    DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list, bin_rows;
     DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_list, vis_plane;
     DevCounters *counters = nullptr;
     DevCounters *h_counters = nullptr;      /* pinned */
@@ -245,7 +245,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     }
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
-                       &d->chunk_base, &d->large_list, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_list, &d->vis_plane };
+                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_list, &d->vis_plane };
     for (DevBuf *b : bufs) release(*b);
     if (d->color) cudaFree(d->color);
     if (d->depth) cudaFree(d->depth);
@@ -553,7 +553,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if (need_eye && ((rc = reserve(d, d->v_epos, nv * 16)) || (rc = reserve(d, d->v_enrm, nv * 16)))) return rc;
             if ((rc = reserve(d, d->records, rec_cap * sizeof(TriRecord)))) return rc;
             if (need_eye && (rc = reserve(d, d->rec_eye, rec_cap * sizeof(TriEye)))) return rc;
-            if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4))) return rc;
+            if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4)) ||
+                (rc = reserve(d, d->bin_rows, rec_cap * 16))) return rc;
             if ((rc = reserve(d, d->tile_count, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_offset, (size_t)ntiles * 4)) ||
                 (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_flags, (size_t)ntiles * 4))) return rc;
             if ((rc = reserve(d, d->vis_plane, (size_t)d->width * d->height * 4))) return rc;
@@ -562,6 +563,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.records = (TriRecord *)d->records.ptr; b.rec_eye = (TriEye *)d->rec_eye.ptr;
             b.record_capacity = (uint32_t)std::min<size_t>(rec_cap, 0xFFFFFFFFu);
             b.chunk_base = (uint32_t *)d->chunk_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
+            b.bin_rows = (uint4 *)d->bin_rows.ptr;
             b.tile_count = (uint32_t *)d->tile_count.ptr; b.tile_offset = (uint32_t *)d->tile_offset.ptr;
             b.tile_cursor = (uint32_t *)d->tile_cursor.ptr;
             b.tile_flags = (uint32_t *)d->tile_flags.ptr;
