@@ -933,23 +933,32 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    /* pass 1: colour clear + compaction of the pixels to shade.  A thread owns column (tid & 63) of rows
-     * (tid >> 6) + 4k: its 16 visibility loads are issued back to back, then one block scan places its survivors. */
-    const int x = (int)(threadIdx.x & 63), yb = (int)(threadIdx.x >> 6);
+    /* pass 1: colour clear + compaction of the pixels to shade.  A thread owns 16 consecutive pixels of one row
+     * (row = tid / 4), so its visibility loads are four 16-byte loads issued back to back and thread order is
+     * row-major pixel order: the compacted list keeps neighbouring pixels next to each other for pass 2. */
+    const int y = (int)(threadIdx.x >> 2), xq = (int)(threadIdx.x & 3) * 16;
     uint32_t has_mask = 0;
-    {
-        uint32_t v[TILE_H / 4];
+    if (y < vh) {
+        uint32_t v[16];
+        const size_t p0 = (size_t)(py0 + y) * fb.width + px0 + xq;
+        if (!L) {
 #pragma unroll
-        for (int k = 0; k < TILE_H / 4; k++) {
-            const int y = yb + 4 * k;
-            v[k] = (L && x < vw && y < vh) ? b.vis_plane[(size_t)(py0 + y) * fb.width + px0 + x] : VIS_NONE;
+            for (int k = 0; k < 16; k++) v[k] = VIS_NONE;
+        } else if (vw == TILE_W && (fb.width & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(b.vis_plane + p0 + q * 4);
+                v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = (xq + k < vw) ? b.vis_plane[p0 + k] : VIS_NONE;
         }
+        const bool clr_row = (clr.mask & G_COLOR_BUFFER_BIT) && py0 + y >= clr.y0 && py0 + y < clr.y1;
 #pragma unroll
-        for (int k = 0; k < TILE_H / 4; k++) {
-            const int y = yb + 4 * k;
+        for (int k = 0; k < 16; k++) {
             if (v[k] != VIS_NONE) has_mask |= 1u << k;
-            else if (x < vw && y < vh && (clr.mask & G_COLOR_BUFFER_BIT) && px0 + x >= clr.x0 && px0 + x < clr.x1 && py0 + y >= clr.y0 && py0 + y < clr.y1)
-                fb.color[(size_t)(py0 + y) * fb.width + px0 + x] = clr.color;
+            else if (clr_row && xq + k < vw && px0 + xq + k >= clr.x0 && px0 + xq + k < clr.x1) fb.color[p0 + k] = clr.color;
         }
     }
     const uint32_t mine = (uint32_t)__popc(has_mask);
@@ -968,7 +977,7 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
         if (w < warp) at += wt;
         n += wt;
     }
-    for (uint32_t m = has_mask; m; m &= m - 1) list[at++] = (uint16_t)((yb + 4 * (__ffs(m) - 1)) * TILE_W + x);
+    for (uint32_t m = has_mask; m; m &= m - 1) list[at++] = (uint16_t)(y * TILE_W + xq + __ffs(m) - 1);
     __syncthreads();
 
     /* pass 2: shade the compacted pixels */

@@ -218,11 +218,12 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
                 h.row0 = make_int4(0, 0, 0, 0); h.row1 = make_int4(0, 0, 0, 0); h.row2 = make_uint4(0, 0, 0, 0); h.z0 = h.z1 = h.z2 = 0.0f;
             }
             const uint32_t smask = __ballot_sync(0xFFFFFFFFu, small);
+            if (!smask) continue;
 #pragma unroll 1
             for (int it = 0; it < 8; it++) {
-                const uint32_t quad = (smask >> (it * 4)) & 0xFu;
-                if (!quad) continue;
+                if (!((smask >> (it * 4)) & 0xFu)) continue;        /* warp-uniform */
                 const int src = it * 4 + grp;
+                const bool has = ((smask >> src) & 1u) != 0u;
                 /* each group of 8 lanes receives the head of its triangle */
                 const int x0 = __shfl_sync(0xFFFFFFFFu, h.row0.x, src), y0 = __shfl_sync(0xFFFFFFFFu, h.row0.y, src);
                 const int x1 = __shfl_sync(0xFFFFFFFFu, h.row0.z, src), y1 = __shfl_sync(0xFFFFFFFFu, h.row0.w, src);
@@ -233,34 +234,38 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
                 const uint32_t id = __shfl_sync(0xFFFFFFFFu, h.row2.w, src);
                 const float z0 = __shfl_sync(0xFFFFFFFFu, h.z0, src), z1 = __shfl_sync(0xFFFFFFFFu, h.z1, src), z2 = __shfl_sync(0xFFFFFFFFu, h.z2, src);
                 const uint32_t bx = __shfl_sync(0xFFFFFFFFu, box, src);
-                if (!((quad >> grp) & 1u)) continue;
-
-                const int X0 = (int)(bx & 0xFFu), Y0 = (int)((bx >> 8) & 0xFFu), X1 = (int)((bx >> 16) & 0xFFu), Y1 = (int)(bx >> 24);
-                bool range01 = true;
-                double dnear = 0.0, dfar = 1.0;
-                if (!mode.all_range01) {
-                    const RasterCfg *cfg = b.cfgs + (state & STATE_INDEX_MASK);
-                    range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
-                    dnear = cfg->depth_near; dfar = cfg->depth_far;
-                }
-                EdgeSet E;
-                prepare_edges(E, x0, y0, x1, y1, x2, y2, area, inv_area);
-                const float fy = (float)(py0 + Y0);
-                for (int cx = X0 + col; cx <= X1; cx += 8) {
-                    const float fx = (float)(px0 + cx);
-                    /* column part of the edge functions; the row part advances by exact integer steps */
-                    const float t0 = (fx - E.ax[0]) * E.dy[0], t1 = (fx - E.ax[1]) * E.dy[1], t2 = (fx - E.ax[2]) * E.dy[2];
-                    float q0 = fy - E.ay[0], q1 = fy - E.ay[1], q2 = fy - E.ay[2];
-                    unsigned long long *kp = &sm.key[Y0 * VIS_PITCH + cx];
-                    for (int y = Y0; y <= Y1; y++, kp += VIS_PITCH, q0 += 1.0f, q1 += 1.0f, q2 += 1.0f) {
-                        const float e0 = t0 - q0 * E.dx[0], e1 = t1 - q1 * E.dx[1], e2 = t2 - q2 * E.dx[2];
-                        if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
-                            const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
-                            const float z = b0 * z0 + b1 * z1 + b2 * z2;
-                            key_min(kp, make_key(mode, depth_of(z, range01, dnear, dfar), id));
+                if (has) {
+                    const int X0 = (int)(bx & 0xFFu), Y0 = (int)((bx >> 8) & 0xFFu), X1 = (int)((bx >> 16) & 0xFFu), Y1 = (int)(bx >> 24);
+                    bool range01 = true;
+                    double dnear = 0.0, dfar = 1.0;
+                    if (!mode.all_range01) {
+                        const RasterCfg *cfg = b.cfgs + (state & STATE_INDEX_MASK);
+                        range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
+                        dnear = cfg->depth_near; dfar = cfg->depth_far;
+                    }
+                    EdgeSet E;
+                    prepare_edges(E, x0, y0, x1, y1, x2, y2, area, inv_area);
+                    const float fy = (float)(py0 + Y0);
+#pragma unroll 1
+                    for (int cx = X0 + col; cx <= X1; cx += 8) {
+                        const float fx = (float)(px0 + cx);
+                        /* column part of the edge functions; the row part advances by exact integer steps */
+                        const float t0 = (fx - E.ax[0]) * E.dy[0], t1 = (fx - E.ax[1]) * E.dy[1], t2 = (fx - E.ax[2]) * E.dy[2];
+                        float q0 = fy - E.ay[0], q1 = fy - E.ay[1], q2 = fy - E.ay[2];
+                        unsigned long long *kp = &sm.key[Y0 * VIS_PITCH + cx];
+                        /* not unrolled: the four groups must stay in one instruction stream whatever their row counts */
+#pragma unroll 1
+                        for (int y = Y0; y <= Y1; y++, kp += VIS_PITCH, q0 += 1.0f, q1 += 1.0f, q2 += 1.0f) {
+                            const float e0 = t0 - q0 * E.dx[0], e1 = t1 - q1 * E.dx[1], e2 = t2 - q2 * E.dx[2];
+                            if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
+                                const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
+                                const float z = b0 * z0 + b1 * z1 + b2 * z2;
+                                key_min(kp, make_key(mode, depth_of(z, range01, dnear, dfar), id));
+                            }
                         }
                     }
                 }
+                __syncwarp();       /* the four groups leave their loops at different times: rejoin before the next shuffles */
             }
         }
         __syncthreads();
