@@ -551,6 +551,65 @@ __device__ __forceinline__ SVert load_vertex(const VertexSrc &b, uint32_t i)
     return o;
 }
 
+/* write_fill for the common path, streaming: each group of record rows is loaded from the post-transform vertex
+ * arrays and stored at once, so no more than three float4 are live at a time (the generic form keeps all three
+ * vertices, 51 values, in registers).  Same values, same operations. */
+__device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, TriEye *__restrict__ eye_dst, uint32_t id, const RasterCfg *cfg,
+                                                   uint32_t state_index, const ScreenTri &s, const VertexSrc &src, uint32_t i0, uint32_t i1, uint32_t i2)
+{
+    float4 *out = reinterpret_cast<float4 *>(dst);
+    const uint32_t cflags = cfg->flags;
+    const uint32_t state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
+                                 ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
+    reinterpret_cast<int4 *>(dst)[0] = make_int4(s.x0, s.y0, s.x1, s.y1);
+    reinterpret_cast<int4 *>(dst)[1] = make_int4(s.x2, s.y2, __float_as_int(s.area), __float_as_int(1.0f / s.area));
+    reinterpret_cast<uint4 *>(dst)[2] = make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
+    {   /* rows 5-7: colours are copied */
+        const float4 c0 = __ldg(src.color + i0), c1 = __ldg(src.color + i1), c2 = __ldg(src.color + i2);
+        out[5] = c0; out[6] = c1; out[7] = c2;
+    }
+    float lod = 0.0f, ez0;
+    {   /* rows 8-9: texture coordinates and eye z; one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
+        const float4 t0 = __ldg(src.tex + i0), t1 = __ldg(src.tex + i1), t2 = __ldg(src.tex + i2);
+        if (cflags & RC_TEXTURED) {
+            float screen_area = fabsf(s.area) * 0.5f;
+            float tw = (float)cfg->tex_w, th = (float)cfg->tex_h;
+            float du1 = (t1.x - t0.x) * tw, dv1 = (t1.y - t0.y) * th;
+            float du2 = (t2.x - t0.x) * tw, dv2 = (t2.y - t0.y) * th;
+            float texel_area = fabsf(du1 * dv2 - du2 * dv1) * 0.5f;
+            if (screen_area > 0.0f) {
+                float tpp = texel_area / screen_area;
+                if (tpp > 0.0f) {
+                    lod = log2f(tpp) * 0.5f;
+                    if (lod < 0.0f) lod = 0.0f;
+                }
+            }
+        }
+        out[8] = make_float4(t0.x, t0.y, t1.x, t1.y);
+        out[9] = make_float4(t2.x, t2.y, t1.z, t2.z);
+        ez0 = t0.z;
+    }
+    {   /* rows 3-4: z / w after the divide (raster.c:729-746) */
+        const float4 p0 = __ldg(src.clip + i0), p1 = __ldg(src.clip + i1), p2 = __ldg(src.clip + i2);
+        float z0, w0, z1, w1, z2, w2;
+        if (fabsf(p0.w) < 1e-6f) { z0 = 0.0f; w0 = 1.0f; } else { w0 = 1.0f / p0.w; z0 = p0.z * w0; }
+        if (fabsf(p1.w) < 1e-6f) { z1 = 0.0f; w1 = 1.0f; } else { w1 = 1.0f / p1.w; z1 = p1.z * w1; }
+        if (fabsf(p2.w) < 1e-6f) { z2 = 0.0f; w2 = 1.0f; } else { w2 = 1.0f / p2.w; z2 = p2.z * w2; }
+        out[3] = make_float4(z0, z1, z2, lod);
+        out[4] = make_float4(w0, w1, w2, ez0);
+    }
+    if (eye_dst) {
+        float4 *eo = reinterpret_cast<float4 *>(eye_dst);
+        float4 e0 = __ldg(src.epos + i0), e1 = __ldg(src.epos + i1), e2 = __ldg(src.epos + i2);
+        e0.w = 0.0f; e1.w = 0.0f; e2.w = 0.0f;
+        eo[0] = e0; eo[1] = e1; eo[2] = e2;
+        float4 n0 = __ldg(src.enrm + i0), n1 = __ldg(src.enrm + i1), n2 = __ldg(src.enrm + i2);
+        n0.w = 0.0f; n1.w = 0.0f; n2.w = 0.0f;
+        eo[3] = n0; eo[4] = n1; eo[5] = n2;
+    }
+    return make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
+}
+
 /* Everything that is not an unclipped filled triangle: clipped polygons (a fan of up to 7 sub-triangles), outlines,
  * line segments and points.  Out of line and self-contained (it reloads its vertices) so that the common path
  * stays in registers.  Returns the number of records emitted. */
@@ -601,7 +660,7 @@ __device__ __forceinline__ void persp_divide_xy(const float4 &v, float &x, float
  * fetched for survivors, after the scan, so culled triangles cost a third of the traffic and nothing but the
  * screen-space result (10 registers) lives across the barrier.
  */
-__global__ void __launch_bounds__(SETUP_THREADS, 2) k_setup(BatchDev b, FrameTargets fb)
+__global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTargets fb)
 {
     __shared__ uint32_t warp_sums[SETUP_THREADS / 32];
     __shared__ uint32_t chunk_slot0;
@@ -691,9 +750,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 2) k_setup(BatchDev b, FrameTar
         TriEye *const eye_dst = b.need_eye ? b.rec_eye + r : nullptr;
         const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
         if (shape == 1) {
-            SVert v0 = load_vertex(src, i0), v1 = load_vertex(src, i1), v2 = load_vertex(src, i2);
-            persp_divide(v0); persp_divide(v1); persp_divide(v2);
-            row = write_fill(dst, eye_dst, id0, cfg, state_index, s, v0, v1, v2);
+            row = write_fill_stream(dst, eye_dst, id0, cfg, state_index, s, src, i0, i1, i2);
             b.bin_rows[r] = row;
             counted = true;
         } else {
