@@ -30,6 +30,8 @@ CASES = (
     + [("state_churn", 320, 240, 0), ("state_churn", 517, 389, 0)]
     + [("lines", 320, 240, v) for v in (0, 1, 2, 6, 9, 16, 19, 32, 63)]
     + [("wireframe", 400, 300, v) for v in (0, 1, 2, 3, 4, 5, 8)]
+    + [("depth_order", 320, 240, v) for v in (0, 1, 2, 3, 5, 6, 8, 9, 10, 11, 12, 16, 31)]
+    + [("depth_order", 517, 389, 1), ("depth_order", 1280, 720, 8)]
 )
 
 

@@ -972,6 +972,86 @@ static void scene_wireframe(int w, int h, int variant)
     glEnd();
 }
 
+/* Depth ordering stress for the order-independent visibility path (k_vis.cu): exact depth ties between coplanar
+ * duplicates, all four ordering depth functions, non-default depth range, a mid-frame change of depth function,
+ * more than a thousand tiny triangles inside one 64x64 tile, large and small triangles mixed, scissor.
+ *   variant & 3   : GL_LESS, GL_LEQUAL, GL_GREATER, GL_GEQUAL
+ *   variant & 4   : glDepthRange(0.3, 0.9)
+ *   variant & 8   : second half of the frame uses the "opposite tie" function (LESS<->LEQUAL, GREATER<->GEQUAL)
+ *   variant & 16  : scissor rectangle */
+static void scene_depth_order(int w, int h, int variant)
+{
+    static const GLenum funcs[4] = { GL_LESS, GL_LEQUAL, GL_GREATER, GL_GEQUAL };
+    const int fi = variant & 3;
+    frustum_like_testbed(w, h, 60.0);
+    glEnable(GL_DEPTH_TEST);
+    glDepthFunc(funcs[fi]);
+    if (variant & 4) glDepthRange(0.3, 0.9);
+    glClearColor(0.1f, 0.1f, 0.15f, 1.0f);
+    glClearDepth(fi >= 2 ? 0.0 : 1.0);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    if (variant & 16) { glEnable(GL_SCISSOR_TEST); glScissor(w / 9, h / 7, (w * 3) / 4, (h * 2) / 3); }
+    glLoadIdentity();
+    glTranslatef(0.0f, 0.0f, -5.0f);
+
+    /* 1. a large tilted background quad and an interpenetrating one */
+    glBegin(GL_QUADS);
+    glColor3f(0.8f, 0.2f, 0.2f);
+    glVertex3f(-4.0f, -3.0f, -2.0f); glVertex3f(4.0f, -3.0f, 1.0f); glVertex3f(4.0f, 3.0f, 1.0f); glVertex3f(-4.0f, 3.0f, -2.0f);
+    glColor3f(0.2f, 0.8f, 0.2f);
+    glVertex3f(-4.0f, -3.0f, 1.0f); glVertex3f(4.0f, -3.0f, -2.0f); glVertex3f(4.0f, 3.0f, -2.0f); glVertex3f(-4.0f, 3.0f, 1.0f);
+    glEnd();
+
+    /* 2. exact ties: the same triangle five times with different colours, then shifted coplanar copies that share
+     *    vertices with it (identical vertex data -> identical interpolated depth on the shared pixels) */
+    static const GLfloat tri[3][3] = { { -1.5f, -1.0f, 1.5f }, { 1.2f, -0.8f, 1.5f }, { 0.1f, 1.4f, 1.5f } };
+    for (int k = 0; k < 5; k++) {
+        glBegin(GL_TRIANGLES);
+        glColor3f(0.2f * (float)k, 1.0f - 0.2f * (float)k, 0.5f);
+        for (int j = 0; j < 3; j++) glVertex3f(tri[j][0], tri[j][1], tri[j][2]);
+        glEnd();
+    }
+    glBegin(GL_TRIANGLES);
+    glColor3f(1.0f, 1.0f, 0.0f);
+    glVertex3f(tri[1][0], tri[1][1], tri[1][2]); glVertex3f(2.6f, 1.3f, 1.5f); glVertex3f(tri[2][0], tri[2][1], tri[2][2]);
+    glColor3f(0.0f, 1.0f, 1.0f);
+    glVertex3f(tri[2][0], tri[2][1], tri[2][2]); glVertex3f(2.6f, 1.3f, 1.5f); glVertex3f(tri[1][0], tri[1][1], tri[1][2]);       /* the same triangle, other winding */
+    glEnd();
+
+    if (variant & 8) glDepthFunc(funcs[fi ^ 1]);
+
+    /* 3. a dense patch: 36 x 36 cells of two tiny triangles each, inside roughly one tile, drawn twice (ties again) */
+    for (int pass = 0; pass < 2; pass++) {
+        glBegin(GL_TRIANGLES);
+        for (int iy = 0; iy < 36; iy++)
+            for (int ix = 0; ix < 36; ix++) {
+                const float x0 = -2.4f + 0.035f * (float)ix, y0 = -1.6f + 0.035f * (float)iy, d = 0.035f;
+                const float z = 1.8f + 0.01f * (float)((ix * 7 + iy * 3) % 5);
+                glColor3f((float)((ix + pass) & 1), (float)(iy & 1), pass ? 0.9f : 0.1f);
+                glVertex3f(x0, y0, z); glVertex3f(x0 + d, y0, z); glVertex3f(x0 + d, y0 + d, z);
+                glVertex3f(x0, y0, z); glVertex3f(x0 + d, y0 + d, z); glVertex3f(x0, y0 + d, z);
+            }
+        glEnd();
+    }
+
+    /* 4. long thin slivers crossing many tiles, and a strip that wraps back over itself */
+    glBegin(GL_TRIANGLES);
+    for (int k = 0; k < 12; k++) {
+        const float y = -2.5f + 0.4f * (float)k;
+        glColor3f(0.3f + 0.05f * (float)k, 0.3f, 1.0f - 0.05f * (float)k);
+        glVertex3f(-3.8f, y, 0.5f + 0.1f * (float)k); glVertex3f(3.8f, y + 0.05f, 2.0f - 0.1f * (float)k); glVertex3f(3.8f, y + 0.12f, 0.7f);
+    }
+    glEnd();
+    glBegin(GL_TRIANGLE_STRIP);
+    for (int k = 0; k < 20; k++) {
+        const float a = 0.45f * (float)k;
+        glColor3f(0.5f + 0.5f * sinf(a), 0.5f + 0.5f * cosf(a), 0.6f);
+        glVertex3f(1.5f + 1.2f * cosf(a), -0.5f + 1.2f * sinf(a), 1.0f + 0.05f * (float)k);
+        glVertex3f(1.5f + 0.6f * cosf(a), -0.5f + 0.6f * sinf(a), 2.2f - 0.05f * (float)k);
+    }
+    glEnd();
+}
+
 /* ---------------------------------------------------------------- registry */
 typedef void (*scene_fn)(int, int, int);
 static const struct { const char *name; scene_fn fn; } g_scenes[] = {
@@ -996,6 +1076,7 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "state_churn", scene_state_churn },
     { "lines", scene_lines },
     { "wireframe", scene_wireframe },
+    { "depth_order", scene_depth_order },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }
