@@ -55,7 +55,7 @@ WORKLOADS = {
 class Stats(ctypes.Structure):
     _fields_ = [("vertices", ctypes.c_uint64), ("triangles_in", ctypes.c_uint64), ("triangles_setup", ctypes.c_uint64),
                 ("tile_refs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("last_batch_ms", ctypes.c_float),
-                ("stage_ms", ctypes.c_float * 5)]
+                ("stage_ms", ctypes.c_float * 5), ("raster_ms", ctypes.c_float * 3)]
 
 
 def counts_for(key):
@@ -254,6 +254,7 @@ def run_b200(args, workload):
 
     # ---- timed region 1: inputs resident in HBM ----
     stage = np.zeros(5)
+    rstage = np.zeros(3)
     batch_ms = 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dev_ms_total = 0.0
@@ -273,6 +274,7 @@ def run_b200(args, workload):
         dev_ms_total += ms.value
         L.mtgl_dev_get_stats(dev, ctypes.byref(st))
         stage += np.array(list(st.stage_ms))
+        rstage += np.array(list(st.raster_ms))
         batch_ms += st.last_batch_ms
     ev1.record()
     sync_all()
@@ -349,9 +351,27 @@ def run_b200(args, workload):
         frag_bytes = cnt["covered"] * 4 + cnt["tested"] * 8
         clear_bytes = px * (4 + 4)
         vertex_bytes = cnt["vertices"] * 32
-    raster_ms = stage[4] / args.steps
-    raster_bytes = (frag_bytes + clear_bytes) / world          # one launch per rank covers 1/N of the frame
+    # the dominant kernel of the step: K4a (visibility: coverage + depth), K4b (shade) or the general in-order kernel,
+    # whichever the live per-group CUDA-event times say; its algorithmic bytes are SURVEY.md 8(d)'s per-fragment
+    # framebuffer traffic of the reference restricted to the planes that kernel owns (DESIGN.md "Roofline")
+    groups = ["k_vis (K4a visibility)", "k_shade (K4b)", "k_raster<false> (general)"]
+    gi = int(np.argmax(rstage))
+    raster_ms = rstage[gi] / args.steps
+    if is_c3:
+        group_bytes = [0, 0, frag_bytes + clear_bytes]
+    else:
+        group_bytes = [cnt["covered"] * 4 + cnt["tested"] * 4 + px * 4, cnt["tested"] * 4 + px * 4, 0]
+        if group_bytes[gi] == 0:        # a state mix that sends C4/C5 through the general kernel
+            group_bytes[gi] = frag_bytes + clear_bytes
+    raster_bytes = group_bytes[gi] / world          # one launch per rank covers 1/N of the frame
     achieved = raster_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text()).get(workload)
+        if tj and tj["kernel"].split("<")[0].split(" ")[0] == groups[gi].split("<")[0].split(" ")[0] and world == 1:
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+    except Exception:
+        traffic = None
     frame_bytes = frag_bytes + clear_bytes + vertex_bytes
     out = {
         "metric": "covered_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
@@ -366,11 +386,13 @@ def run_b200(args, workload):
                 "ms_per_step": e2e_s * 1e3 / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "k_raster", "bound": "hbm", "achieved": achieved, "peak": bw, "unit": "GB/s",
-                     "frac": achieved / bw, "traffic": None, "peak_source": bw_src,
+        "roofline": {"kernel": groups[gi], "bound": "hbm", "achieved": achieved, "peak": bw, "unit": "GB/s",
+                     "frac": achieved / bw, "traffic": traffic, "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, per launch)" if traffic else None,
+                     "peak_source": bw_src,
                      "algorithmic_bytes_per_launch": raster_bytes, "kernel_ms": raster_ms,
                      "frame_bytes": frame_bytes, "frame_frac": frame_bytes / (bw * 1e9) / (ms_per_step * 1e-3)},
         "stages_ms": {k: float(v / args.steps) for k, v in zip(["vertex", "setup", "bin_count_scan", "bin_fill", "raster"], stage)},
+        "raster_ms": {k: float(v / args.steps) for k, v in zip(["visibility", "shade", "general"], rstage)},
         "batch_ms": batch_ms / args.steps, "wall_ms_per_step": wall_s * 1e3 / args.steps,
         "cpu_baseline": cpu,
     }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MTGL_DEV_ABI_VERSION 1
+#define MTGL_DEV_ABI_VERSION 2
 
 /* error codes */
 #define MTGL_OK            0
@@ -220,6 +220,7 @@ typedef struct mtgl_dev_stats {
     float    last_batch_ms;     /* CUDA-event time of the last batch (upload + all kernels) */
     float    stage_ms[5];       /* CUDA-event time per stage of the last batch, summed over passes:
                                    0 vertex (K1), 1 set-up (K2), 2 bin count + scan, 3 bin fill, 4 tile raster (K4/K5) */
+    float    raster_ms[3];      /* stage 4 split by kernel group: 0 visibility (K4a), 1 shade (K4b), 2 general in-order kernel */
 } mtgl_dev_stats;
 
 typedef struct mtgl_dev mtgl_dev;

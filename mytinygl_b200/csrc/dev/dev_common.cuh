@@ -403,8 +403,9 @@ struct RasterPlan {
     uint32_t unordered_func;    /* depth function (0..7) of the unordered class, 0 when the class is empty */
     bool unordered_range01;     /* every unordered state has depth range [0,1] */
 };
+/* ev_vis / ev_shade are recorded after the visibility kernels and after the shade kernel (stage timing) */
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,
-                   const RasterPlan &plan, cudaStream_t s);
+                   const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);

@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
 }
 
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes,
-                   const RasterPlan &plan, cudaStream_t s)
+                   const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade)
 {
     const bool any_deferrable = plan.any_deferrable, any_in_order = plan.any_in_order;
     static bool configured[64] = { false };
@@ -1020,7 +1020,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         configured[dev] = true;
     }
     uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
-    if (tiles == 0 || planes == 0) return;
+    if (tiles == 0 || planes == 0) { cudaEventRecord(ev_vis, s); cudaEventRecord(ev_shade, s); return; }
     /* Split path: tiles whose records are all deferrable go through K4a (visibility) + K4b (shade); tiles with an
      * in-order record go through the general kernel.  A pass without deferrable draws uses the general kernel alone
      * (it then also owns the tiles that only need clearing). */
@@ -1032,15 +1032,19 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
             k_raster<true><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
             note_launch();
         }
+        cudaEventRecord(ev_vis, s);
         if (planes & 1u) {
             k_shade<<<tiles, 256, 0, s>>>(b, fb, clear);
             note_launch();
         }
+        cudaEventRecord(ev_shade, s);
         if (any_in_order) {
             k_raster<false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u);
             note_launch();
         }
     } else {
+        cudaEventRecord(ev_vis, s);
+        cudaEventRecord(ev_shade, s);
         k_raster<false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
         note_launch();
     }

@@ -62,7 +62,7 @@ struct mtgl_dev {
     int pinned_next = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
-    std::vector<cudaEvent_t> stage_ev;      /* 6 per pass of the last batch: K1 | K2 | count+scan | fill | raster */
+    std::vector<cudaEvent_t> stage_ev;      /* 8 per pass of the last batch: K1 | K2 | count+scan | fill | raster, then [6] end of K4a, [7] end of K4b */
     size_t stage_passes = 0;
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
@@ -512,7 +512,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     CU(cudaEventRecord(d->ev_start, d->stream));
     d->timed = true;
     uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0;
-    while (d->stage_ev.size() < passes.size() * 6) {
+    while (d->stage_ev.size() < passes.size() * 8) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         d->stage_ev.push_back(e);
@@ -534,7 +534,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         b.unorm8 = d->unorm8;
         b.counters = d->counters;
 
-        cudaEvent_t *sev = &d->stage_ev[pidx * 6];
+        cudaEvent_t *sev = &d->stage_ev[pidx * 8];
         CU(cudaEventRecord(sev[0], d->stream));
         ClearOp clr;
         std::memset(&clr, 0, sizeof clr);
@@ -611,7 +611,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         plan.any_in_order = any_in_order;
         plan.unordered_func = unordered_func;
         plan.unordered_range01 = unordered_range01;
-        launch_raster(b, fb, clr, planes, plan, d->stream);
+        launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
         CU(cudaEventRecord(sev[5], d->stream));
     }
     CU(cudaEventRecord(d->ev_stop, d->stream));
@@ -673,11 +673,17 @@ int mtgl_dev_get_stats(mtgl_dev *d, mtgl_dev_stats *out)
         CU(cudaEventElapsedTime(&ms, d->ev_start, d->ev_stop));
         d->stats.last_batch_ms = ms;
         for (int k = 0; k < 5; k++) d->stats.stage_ms[k] = 0.0f;
-        for (size_t p = 0; p < d->stage_passes; p++)
+        for (int k = 0; k < 3; k++) d->stats.raster_ms[k] = 0.0f;
+        for (size_t p = 0; p < d->stage_passes; p++) {
+            cudaEvent_t *sev = &d->stage_ev[p * 8];
             for (int k = 0; k < 5; k++) {
-                CU(cudaEventElapsedTime(&ms, d->stage_ev[p * 6 + k], d->stage_ev[p * 6 + k + 1]));
+                CU(cudaEventElapsedTime(&ms, sev[k], sev[k + 1]));
                 d->stats.stage_ms[k] += ms;
             }
+            CU(cudaEventElapsedTime(&ms, sev[4], sev[6])); d->stats.raster_ms[0] += ms;
+            CU(cudaEventElapsedTime(&ms, sev[6], sev[7])); d->stats.raster_ms[1] += ms;
+            CU(cudaEventElapsedTime(&ms, sev[7], sev[5])); d->stats.raster_ms[2] += ms;
+        }
     }
     d->stats.kernel_launches = kernel_launch_count();
     *out = d->stats;
