@@ -81,6 +81,8 @@ struct DevDraw {
     uint32_t vbase;          /* index of this draw's first post-transform vertex */
     uint32_t tbase;          /* index of this draw's first assembled primitive (triangle, line segment or point) */
     uint32_t ntris;          /* primitives of this draw in the pass */
+    uint32_t fused;          /* independent triangles: no vertex-stage launch, k_setup shades the survivors' vertices */
+    uint32_t pad2_;
 };
 
 /* Raster-stage view of one mtgl_state: enums folded to small integers, texture resolved to
@@ -373,6 +375,7 @@ struct BatchDev {
     const uint32_t *draw_tbase;     /* n_draws + 1 */
     uint32_t n_draws, n_vertices, n_triangles;
     uint32_t need_eye;
+    uint32_t n_unfused_draws;       /* draws whose vertices go through k_vertex */
     /* post-transform vertices */
     float4 *v_clip, *v_color, *v_tex, *v_epos, *v_enrm;
     /* set-up output */

@@ -19,6 +19,7 @@
  */
 #include "dev_common.cuh"
 #include "dev_texture.cuh"
+#include "dev_vertex.cuh"
 
 #include <climits>
 
@@ -535,10 +536,35 @@ struct VertexSrc {
     const float4 *clip, *color, *tex, *epos, *enrm;
     const float *unorm8;
     int need_eye;
+    /* fused draws (independent triangles): vertices are shaded here instead of being read from the streams */
+    const mtgl_in_vertex *staged;
+    const mtgl_state *states;
+    const DevDraw *draw;
+    uint32_t fused;
 };
+
+/* the vertex stage for one vertex of a fused draw (dev_vertex.cuh), as the SVert the set-up code works on */
+__device__ __noinline__ SVert compute_vertex(const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw *draw, uint32_t i)
+{
+    VertexIn in;
+    fetch_vertex(staged, states, *draw, i - draw->vbase, in);
+    VertexOut v;
+    shade_vertex(in, v);
+    SVert o;
+    o.x = v.clip.x; o.y = v.clip.y; o.z = v.clip.z; o.w = v.clip.w;
+    o.r = v.color.x; o.g = v.color.y; o.b = v.color.z; o.a = v.color.w;
+    o.u = v.tex.x; o.v = v.tex.y; o.ez = v.tex.z;
+    o.epx = v.epos.x; o.epy = v.epos.y; o.epz = v.epos.z; o.enx = v.enrm.x; o.eny = v.enrm.y; o.enz = v.enrm.z;
+    return o;
+}
 
 __device__ __forceinline__ SVert load_vertex(const VertexSrc &b, uint32_t i)
 {
+    if (b.fused) {
+        SVert o = compute_vertex(b.staged, b.states, b.draw, i);
+        if (!b.need_eye) { o.epx = o.epy = o.epz = 0.0f; o.enx = o.eny = 0.0f; o.enz = 1.0f; }
+        return o;
+    }
     SVert o;
     float4 p = b.clip[i], c = b.color[i], t = b.tex[i];
     o.x = p.x; o.y = p.y; o.z = p.z; o.w = p.w;
@@ -610,6 +636,54 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
     return make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
 }
 
+/* Fused path, triangle part: rows 0-4 and 8-9 of the record (geometry, z / w, texture coordinates, eye z, LOD) from
+ * the attribute arrays.  The colour rows (and the eye-space side record) are filled afterwards by the whole CTA, one
+ * thread per vertex of the survivors (k_setup, phase B). */
+__device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index,
+                                                  const ScreenTri &s, const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw &dr, uint32_t l0)
+{
+    float4 *out = reinterpret_cast<float4 *>(dst);
+    const uint32_t cflags = cfg->flags;
+    const uint32_t state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
+                                 ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
+    reinterpret_cast<int4 *>(dst)[0] = make_int4(s.x0, s.y0, s.x1, s.y1);
+    reinterpret_cast<int4 *>(dst)[1] = make_int4(s.x2, s.y2, __float_as_int(s.area), __float_as_int(1.0f / s.area));
+    reinterpret_cast<uint4 *>(dst)[2] = make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
+    float z[3], w[3], nez[3], tu[3], tv[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float x, y, zz, ex, ey, ez, ew, ts, tt;
+        const mtgl_state *vs;
+        fetch_position(staged, states, dr, l0 + j, x, y, zz, vs);
+        to_eye(vs, x, y, zz, ex, ey, ez, ew);
+        const float4 c = to_clip(vs, ex, ey, ez, ew);
+        if (fabsf(c.w) < 1e-6f) { z[j] = 0.0f; w[j] = 1.0f; } else { w[j] = 1.0f / c.w; z[j] = c.z * w[j]; }   /* raster.c:729-746 */
+        nez[j] = -ez;
+        fetch_texcoord(staged, dr, l0 + j, ts, tt);
+        tex_transform(vs, ts, tt, tu[j], tv[j]);
+    }
+    float lod = 0.0f;       /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
+    if (cflags & RC_TEXTURED) {
+        float screen_area = fabsf(s.area) * 0.5f;
+        float tw = (float)cfg->tex_w, th = (float)cfg->tex_h;
+        float du1 = (tu[1] - tu[0]) * tw, dv1 = (tv[1] - tv[0]) * th;
+        float du2 = (tu[2] - tu[0]) * tw, dv2 = (tv[2] - tv[0]) * th;
+        float texel_area = fabsf(du1 * dv2 - du2 * dv1) * 0.5f;
+        if (screen_area > 0.0f) {
+            float tpp = texel_area / screen_area;
+            if (tpp > 0.0f) {
+                lod = log2f(tpp) * 0.5f;
+                if (lod < 0.0f) lod = 0.0f;
+            }
+        }
+    }
+    out[3] = make_float4(z[0], z[1], z[2], lod);
+    out[4] = make_float4(w[0], w[1], w[2], nez[0]);
+    out[8] = make_float4(tu[0], tv[0], tu[1], tv[1]);
+    out[9] = make_float4(tu[2], tv[2], nez[1], nez[2]);
+    return make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
+}
+
 /* Everything that is not an unclipped filled triangle: clipped polygons (a fan of up to 7 sub-triangles), outlines,
  * line segments and points.  Out of line and self-contained (it reloads its vertices) so that the common path
  * stays in registers.  Returns the number of records emitted. */
@@ -660,10 +734,13 @@ __device__ __forceinline__ void persp_divide_xy(const float4 &v, float &x, float
  * fetched for survivors, after the scan, so culled triangles cost a third of the traffic and nothing but the
  * screen-space result (10 registers) lives across the barrier.
  */
-__global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTargets fb)
+__global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTargets fb)
 {
     __shared__ uint32_t warp_sums[SETUP_THREADS / 32];
     __shared__ uint32_t chunk_slot0;
+    __shared__ uint32_t fused_n;                            /* survivors of this chunk whose colour rows phase B fills */
+    __shared__ uint2 fused_list[SETUP_THREADS];             /* (record index, input triangle) */
+    if (threadIdx.x == 0) fused_n = 0;
 
     const uint32_t chunk = blockIdx.x;
     const uint32_t t = chunk * SETUP_THREADS + threadIdx.x;
@@ -676,7 +753,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTar
     uint32_t i0 = 0, i1 = 0, i2 = 0;
     uint32_t count = 0;
     ScreenTri s;
-    const VertexSrc src = { b.v_clip, b.v_color, b.v_tex, b.v_epos, b.v_enrm, b.unorm8, b.need_eye ? 1 : 0 };
+    VertexSrc src = { b.v_clip, b.v_color, b.v_tex, b.v_epos, b.v_enrm, b.unorm8, b.need_eye ? 1 : 0, b.staged, b.states, nullptr, 0u };
     const BinOut bin = { b.records, b.bin_rows, b.tile_count, b.tile_flags, b.large_list, b.counters, fb.tiles_x, fb.tile_y0 };
 
     if (valid) {
@@ -686,6 +763,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTar
         state_index = dr.raster_state;
         st = b.states + state_index;
         cfg = b.cfgs + state_index;
+        src.draw = &dr;
+        src.fused = dr.fused;
         switch (dr.mode) {                                  /* raster.c:961-1017, 1020-1044, 288-296, 1167-1231 */
         case G_POINTS: i0 = k; shape = 4; break;
         case G_LINES: i0 = 2 * k; i1 = i0 + 1; shape = 3; break;
@@ -699,7 +778,15 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTar
         }
         i0 += dr.vbase; i1 += dr.vbase; i2 += dr.vbase;
         if (shape == 1) {
-            const float4 p0 = src.clip[i0], p1 = src.clip[i1], p2 = src.clip[i2];
+            float4 p0, p1, p2;
+            if (src.fused) {            /* positions straight from the attribute arrays: MV, then P */
+                const uint32_t l0 = i0 - dr.vbase;
+                float x, y, z, ex, ey, ez, ew;
+                const mtgl_state *vs;
+                fetch_position(b.staged, b.states, dr, l0, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
+                fetch_position(b.staged, b.states, dr, l0 + 1, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
+                fetch_position(b.staged, b.states, dr, l0 + 2, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+            } else { p0 = src.clip[i0]; p1 = src.clip[i1]; p2 = src.clip[i2]; }
             if (inside_all(p0) && inside_all(p1) && inside_all(p2)) {
                 /* Sutherland-Hodgman returns its input unchanged when every vertex passes every plane */
                 float ax, ay, bx, by, cx, cy;
@@ -750,7 +837,10 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTar
         TriEye *const eye_dst = b.need_eye ? b.rec_eye + r : nullptr;
         const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
         if (shape == 1) {
-            row = write_fill_stream(dst, eye_dst, id0, cfg, state_index, s, src, i0, i1, i2);
+            if (src.fused) {
+                row = write_fused_head(dst, id0, cfg, state_index, s, b.staged, b.states, *src.draw, i0 - src.draw->vbase);
+                fused_list[atomicAdd(&fused_n, 1u)] = make_uint2(r, t);
+            } else row = write_fill_stream(dst, eye_dst, id0, cfg, state_index, s, src, i0, i1, i2);
             b.bin_rows[r] = row;
             counted = true;
         } else {
@@ -774,6 +864,27 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) k_setup(BatchDev b, FrameTar
         if ((int)lane == __ffs(peers) - 1) atomicAdd(&b.tile_count[tile], (uint32_t)__popc(peers));
         if (tflags) atomicOr(&b.tile_flags[tile], tflags);
     } else if (ntiles > 1) count_tiles_single(bin, r, row.x, row.y, row.z);
+
+    /* ---- phase B of the fused path: the vertex stage for the survivors only, one thread per vertex: attribute fetch,
+     * eye-space transform, lighting (dev_vertex.cuh) -> colour row 5 + j of the record (and the eye-space side record) ---- */
+    __syncthreads();
+    const uint32_t nv = fused_n * 3u;
+    for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {
+        const uint2 e = fused_list[v / 3u];
+        const uint32_t j = v % 3u;
+        const uint32_t dd = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, e.y);
+        const DevDraw &dr = b.draws[dd];
+        VertexIn in;
+        fetch_vertex(b.staged, b.states, dr, 3u * (e.y - dr.tbase) + j, in);
+        VertexOut o;
+        shade_vertex(in, o);
+        reinterpret_cast<float4 *>(b.records + e.x)[5 + j] = o.color;
+        if (b.need_eye) {
+            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + e.x);
+            eo[j] = o.epos;
+            eo[3 + j] = o.enrm;
+        }
+    }
 }
 
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)

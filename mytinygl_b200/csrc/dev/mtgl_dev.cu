@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -471,7 +472,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     const size_t o_staged = off; if (bt->n_vertices) std::memcpy(hp + off, bt->vertices, (size_t)bt->n_vertices * sizeof(mtgl_in_vertex)); off += sz_staged;
     const size_t o_blob = off; if (bt->blob_size) std::memcpy(hp + off, bt->blob, (size_t)bt->blob_size); off += sz_blob;
 
-    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles; };
+    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles, n_unfused; };
+    static const bool fuse_triangles = std::getenv("MTGL_NO_FUSE") == nullptr;     /* A/B switch for profiling */
     std::vector<PassInfo> infos;
     for (auto &p : passes) {
         PassInfo pi{};
@@ -480,7 +482,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         pi.o_tbase = off; off += sz_prefix;
         DevDraw *pd = reinterpret_cast<DevDraw *>(hp + pi.o_draws);
         uint32_t *vb = reinterpret_cast<uint32_t *>(hp + pi.o_vbase), *tb = reinterpret_cast<uint32_t *>(hp + pi.o_tbase);
-        uint32_t v = 0, t = 0, k = 0;
+        uint32_t v = 0, t = 0, k = 0, unfused = 0;
         for (const PassDraw &q : p) {
             DevDraw o = draws[q.draw];
             const mtgl_draw &s = bt->draws[q.draw];
@@ -496,6 +498,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
                 }
             }
             o.vbase = v;
+            o.fused = (fuse_triangles && o.mode == G_TRIANGLES) ? 1u : 0u;
+            if (!o.fused) unfused++;
             o.tbase = t - q.tri_first;      /* triangle k of the draw has global index tbase + k */
             o.ntris = q.tri_count;
             vb[k] = v; tb[k] = t;
@@ -503,7 +507,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             v += o.count; t += q.tri_count;
         }
         vb[k] = v; tb[k] = t;
-        pi.n_draws = k; pi.n_vertices = v; pi.n_triangles = t;
+        pi.n_draws = k; pi.n_vertices = v; pi.n_triangles = t; pi.n_unfused = unfused;
         infos.push_back(pi);
     }
     CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
@@ -530,6 +534,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         b.draw_vbase = reinterpret_cast<const uint32_t *>(dp + pi.o_vbase);
         b.draw_tbase = reinterpret_cast<const uint32_t *>(dp + pi.o_tbase);
         b.n_draws = pi.n_draws; b.n_vertices = pi.n_vertices; b.n_triangles = pi.n_triangles;
+        b.n_unfused_draws = pi.n_unfused;
         b.need_eye = need_eye ? 1u : 0u;
         b.unorm8 = d->unorm8;
         b.counters = d->counters;
