@@ -213,11 +213,32 @@ def run_b200(args, workload):
     L.mtgl_dev_plane_pointers(dev, ctypes.byref(cptr), None, None)
     color_dev = torch.as_tensor(DevTensor(cptr.value, w * h * 4), device=f"cuda:{local}") if world > 1 else None
 
+    # Fused gather (default for N > 1): rank 0 exports its colour plane over CUDA IPC, the other ranks map it and their
+    # raster kernels store every colour of their band straight into it over NVLink (mtgl_dev_set_present_target);
+    # what is left of the gather is one tiny all-reduce as the "all bands have landed" barrier.
+    peer = world > 1 and args.gather == "peer"
+    token = torch.zeros(1, device=f"cuda:{local}") if world > 1 else None
+    if peer:
+        L.mtgl_dev_export_color_plane.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.mtgl_dev_set_present_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        hbuf = (ctypes.c_ubyte * 64)()
+        if rank == 0:
+            assert L.mtgl_dev_export_color_plane(dev, hbuf) == 0
+        ht = torch.tensor(list(hbuf), dtype=torch.uint8, device=f"cuda:{local}")
+        dist.broadcast(ht, 0)
+        if rank != 0:
+            hb = (ctypes.c_ubyte * 64)(*ht.cpu().tolist())
+            rc = L.mtgl_dev_set_present_target(dev, hb)
+            assert rc == 0, f"mtgl_dev_set_present_target failed ({rc})"
+
     def gather():
-        """colour rows of every band -> rank 0's framebuffer (NCCL send/recv over NVLink)"""
+        """colour rows of every band -> rank 0's framebuffer"""
         if world == 1:
             return
         L.glFinish()
+        if peer:        # the stores already went to rank 0's plane; wait until every rank's frame is complete
+            dist.all_reduce(token)
+            return
         ops = []
         if rank == 0:
             for r in range(1, world):
@@ -287,29 +308,53 @@ def run_b200(args, workload):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tt.item())
     L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+    if os.environ.get("MTGL_BENCH_DEBUG"):
+        print(f"[rank {rank}] stages {np.round(stage / args.steps, 4).tolist()} raster {np.round(rstage / args.steps, 4).tolist()} dev_ms {dev_ms_total / args.steps:.4f}", file=sys.stderr, flush=True)
     launches = int(st.kernel_launches - launches0)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end through the public API with host buffers (C4/C5: VBO re-upload + read-back) ----
     e2e = None
     h2d = d2h = 0
-    pinned_out = torch.empty((y1 - y0) * w, dtype=torch.int32).pin_memory() if y1 > y0 else None
+    # N = 1: this rank uploads the whole VBO and reads the whole colour plane back.
+    # N > 1 (peer gather): every rank uploads 1/N of the VBO from its pinned copy, an NCCL all-gather over NVLink
+    # completes the buffer on every GPU (mtgl_dev_buffer_pointer), each rank renders its band into rank 0's plane
+    # and rank 0 alone reads the whole frame back -- the bytes below are per step, summed over ranks.
+    whole_on_rank0 = peer
+    ry0, ry1 = (0, h) if (whole_on_rank0 and rank == 0) else ((y0, y1) if not whole_on_rank0 else (0, 0))
+    pinned_out = torch.empty((ry1 - ry0) * w, dtype=torch.int32).pin_memory() if ry1 > ry0 else None
+    vbo_dev = None
     if not is_c3:
         nbytes = cnt["vertices"] * 32
         pinned_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         ctypes.memmove(pinned_in.data_ptr(), L.scene_c4_host_data(), nbytes)
         vbo = L.scene_c4_vbo()
-        h2d = nbytes
-    d2h = (y1 - y0) * w * 4
+        if peer and nbytes % world == 0:
+            L.mtgl_dev_buffer_pointer.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
+            L.glBufferSubData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_long, ctypes.c_void_p]
+            bp, bs = ctypes.c_void_p(), ctypes.c_uint64()
+            assert L.mtgl_dev_buffer_pointer(dev, vbo, ctypes.byref(bp), ctypes.byref(bs)) == 0 and bs.value == nbytes
+            vbo_dev = torch.as_tensor(DevTensor(bp.value, nbytes), device=f"cuda:{local}")
+        h2d = nbytes if (world == 1 or vbo_dev is not None) else nbytes * world      # bytes per step, summed over ranks
+    d2h = h * w * 4
 
     def e2e_step():
         if not is_c3:
             L.glBindBuffer(GL_ARRAY_BUFFER, vbo)
-            L.glBufferData(GL_ARRAY_BUFFER, nbytes, pinned_in.data_ptr(), GL_STATIC_DRAW)
+            if vbo_dev is not None:
+                part = nbytes // world
+                L.glBufferSubData(GL_ARRAY_BUFFER, rank * part, part, pinned_in.data_ptr() + rank * part)
+                dist.all_gather_into_tensor(vbo_dev, vbo_dev[rank * part:(rank + 1) * part])
+                torch.cuda.current_stream().synchronize()
+            else:
+                L.glBufferData(GL_ARRAY_BUFFER, nbytes, pinned_in.data_ptr(), GL_STATIC_DRAW)
         frame()
-        if pinned_out is not None:      # glFinish + read this rank's colour rows into pinned host memory
-            base = pinned_out.data_ptr() - y0 * w * 4
-            assert L.mtgl_dev_read_framebuffer(dev, y0, y1, base, None, None) == 0
+        if whole_on_rank0:
+            gather()
+            torch.cuda.current_stream().synchronize()
+        if pinned_out is not None:      # glFinish + read the colour rows into pinned host memory
+            base = pinned_out.data_ptr() - ry0 * w * 4
+            assert L.mtgl_dev_read_framebuffer(dev, ry0, ry1, base, None, None) == 0
 
     e2e_step()
     sync_all()
@@ -323,6 +368,20 @@ def run_b200(args, workload):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_value = cnt["covered"] * args.steps / e2e_s
+
+    # ---- N > 1: the frame assembled in rank 0's plane must be bit-identical to a single-GPU render ----
+    gather_check = None
+    if world > 1:
+        frame(); gather(); sync_all()
+        if rank == 0:
+            got = np.empty(h * w, dtype=np.uint32)
+            assert L.mtgl_dev_read_framebuffer(dev, 0, h, got.ctypes.data, None, None) == 0
+            assert L.mtgl_dev_set_band(dev, 0, h) == 0
+            frame(); L.glFinish()
+            want = np.empty(h * w, dtype=np.uint32)
+            assert L.mtgl_dev_read_framebuffer(dev, 0, h, want.ctypes.data, None, None) == 0
+            gather_check = "bit-identical to a single-GPU render" if np.array_equal(got, want) else f"MISMATCH in {int((got != want).sum())} pixels"
+        sync_all()
 
     # ---- CPU baseline on this box (rank 0, N = 1 only) ----
     cpu = None
@@ -380,7 +439,8 @@ def run_b200(args, workload):
         "frames_per_s": 1e3 / ms_per_step, "triangles_per_s": cnt["vertices"] / 3 * 1e3 / ms_per_step,
         "config": {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3,
                    "covered_fragments": cnt["covered"], "depth_passing_fragments": cnt["tested"], "shaded_fragments": cnt["shaded"],
-                   "partition": f"sort-first bands x{world}",
+                   "partition": f"sort-first bands x{world}" + ("" if world == 1 else (", fused NVLink peer-store gather" if peer else ", NCCL send/recv gather")),
+                   "gather_check": gather_check,
                    "l2": "flushed between frames (256 MiB fill)" if is_c3 else "inputs larger than L2 (>330 MB streamed per frame)"},
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3 / args.steps},
@@ -407,6 +467,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'nccl' = send/recv after the frame")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MTGL_DEV_ABI_VERSION 2
+#define MTGL_DEV_ABI_VERSION 3
 
 /* error codes */
 #define MTGL_OK            0
@@ -242,6 +242,9 @@ int mtgl_dev_buffer_data(mtgl_dev *dev, uint32_t id, uint64_t size, const void *
 int mtgl_dev_buffer_sub_data(mtgl_dev *dev, uint32_t id, uint64_t offset, uint64_t size, const void *data);
 int mtgl_dev_buffer_delete(mtgl_dev *dev, uint32_t id);
 /* read back part of a buffer-object mirror (the front end keeps no host copy of large buffers) */
+/* device address and size of a buffer object's storage (NULL / 0 when it has none): lets a multi-GPU application fill
+ * the buffer with a collective (each rank uploads a slice, NCCL all-gather over NVLink) instead of N full uploads */
+int mtgl_dev_buffer_pointer(mtgl_dev *dev, uint32_t id, void **ptr, uint64_t *size);
 int mtgl_dev_buffer_read(mtgl_dev *dev, uint32_t id, uint64_t offset, uint64_t size, void *out);
 
 /* texture_upload_* (textures.c:141-269) after conversion to RGBA8 words (a<<24|b<<16|g<<8|r);
@@ -267,6 +270,16 @@ int mtgl_dev_write_framebuffer(mtgl_dev *dev, int32_t y0, int32_t y1,
 
 /* Device addresses of the planes (for the multi-GPU gather and for zero-copy consumers). */
 int mtgl_dev_plane_pointers(mtgl_dev *dev, void **color, void **depth, void **stencil);
+
+/* Multi-GPU present path (no reference counterpart: the reference has one framebuffer in host memory that mtgl_swap
+ * reads, include/mytinygl/sdl.h:76-81).  The presenting rank exports its colour plane as a CUDA IPC handle
+ * (MTGL_IPC_HANDLE_BYTES opaque bytes, to be carried to the other processes by any means); a rank that is given the
+ * handle maps the plane over NVLink and every colour store of its band -- shade kernel, tile write-back, clears,
+ * mtgl_dev_write_framebuffer -- is mirrored into it, so that after all ranks have finished their frame the presenting
+ * rank's plane is complete without a separate gather.  Passing NULL detaches. */
+#define MTGL_IPC_HANDLE_BYTES 64
+int mtgl_dev_export_color_plane(mtgl_dev *dev, void *handle_out);
+int mtgl_dev_set_present_target(mtgl_dev *dev, const void *handle);
 
 int mtgl_dev_get_stats(mtgl_dev *dev, mtgl_dev_stats *out);
 

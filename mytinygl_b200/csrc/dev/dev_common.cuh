@@ -354,6 +354,7 @@ static __device__ __noinline__ Color4 compute_lighting(const mtgl_state *st, flo
 /* ---------------------------------------------------------------- launch wrappers (defined in the .cu files) */
 struct FrameTargets {
     uint32_t *color; float *depth; uint8_t *stencil;
+    uint32_t *present;              /* peer GPU's colour plane (NVLink-mapped) that colour stores are mirrored into, or NULL */
     int32_t width, height;
     int32_t band_y0, band_y1;       /* rows owned by this device */
     int32_t tiles_x;                /* tiles per row */
@@ -389,9 +390,17 @@ struct BatchDev {
     uint32_t *tile_flags;           /* bit 0: the tile references a record whose colour work cannot be deferred (general kernel);
                                      * bit 1: it references a record outside the unordered class (sorted visibility kernel) */
     uint32_t *tile_list; uint32_t list_capacity;
+    uint32_t guard;                 /* 1: the list buffer was sized by guess -- fill and raster kernels must check lists_fit() */
     uint32_t *vis_plane;            /* visibility buffer in HBM (record index per pixel) between K4a and K4b */
     const float *unorm8;
 };
+
+/* optimistic batches (mtgl_dev.cu): when the scanned reference count does not fit the list buffer, or set-up ran out of
+ * record slots, the fill and raster kernels must not touch anything; the host re-queues them with a larger buffer */
+__device__ __forceinline__ bool lists_fit(const BatchDev &b)
+{
+    return !b.guard || (b.counters->tile_refs <= b.list_capacity && b.counters->overflow == 0u);
+}
 
 void launch_vertex_stage(const BatchDev &b, cudaStream_t s);
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);

@@ -63,6 +63,7 @@ __device__ __forceinline__ TileRange tile_range(const TriRecord *r, const FrameT
 template <int PASS>
 __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
 {
+    if (PASS == 1 && !lists_fit(b)) return;
     const uint32_t n = b.counters->records;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
 template <int PASS>
 __global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
 {
+    if (PASS == 1 && !lists_fit(b)) return;
     const uint32_t n = b.counters->large_count;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
         const uint32_t r = b.large_list[i];

@@ -627,13 +627,17 @@ __device__ void tile_store(RasterSmem &sm, const FrameTargets &fb, uint32_t plan
         if (vec) {
             for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
                 int y = i >> 4, q = i & 15;
-                *reinterpret_cast<uint4 *>(fb.color + (size_t)(py0 + y) * fb.width + px0 + q * 4) =
-                    *reinterpret_cast<const uint4 *>(&sm.color[y * COLOR_PITCH + q * 4]);
+                const uint4 v = *reinterpret_cast<const uint4 *>(&sm.color[y * COLOR_PITCH + q * 4]);
+                *reinterpret_cast<uint4 *>(fb.color + (size_t)(py0 + y) * fb.width + px0 + q * 4) = v;
+                if (fb.present) *reinterpret_cast<uint4 *>(fb.present + (size_t)(py0 + y) * fb.width + px0 + q * 4) = v;
             }
         } else {
             for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
                 int y = i >> 6, x = i & 63;
-                if (x < vw) fb.color[(size_t)(py0 + y) * fb.width + px0 + x] = sm.color[y * COLOR_PITCH + x];
+                if (x < vw) {
+                    fb.color[(size_t)(py0 + y) * fb.width + px0 + x] = sm.color[y * COLOR_PITCH + x];
+                    if (fb.present) fb.present[(size_t)(py0 + y) * fb.width + px0 + x] = sm.color[y * COLOR_PITCH + x];
+                }
             }
         }
     }
@@ -820,6 +824,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem &sm = *reinterpret_cast<RasterSmem *>(smem_raw);
+    if (!lists_fit(b)) return;
 
     const uint32_t tile = blockIdx.x;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
@@ -916,11 +921,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
  * first compacted into a list (ballot + prefix), then shaded 256 at a time with every lane busy -- same colour
  * code as resolve_region.  The colour part of the batch's leading clear is applied here as well.  Full occupancy,
  * coalesced plane accesses, no ordering constraints left. */
-__global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
+__global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
 {
     __shared__ float un[256];
     __shared__ uint16_t list[TILE_W * TILE_H];
     __shared__ uint32_t warp_total[8];
+    if (!lists_fit(b)) return;
     un[threadIdx.x] = b.unorm8[threadIdx.x];
 
     const uint32_t tile = blockIdx.x;
@@ -1003,6 +1009,24 @@ __global__ void __launch_bounds__(256) k_shade(BatchDev b, FrameTargets fb, Clea
         Color4 c;
         shade_color(b, un, r, state_flags, A, cfg, b0, b1, b2, c);
         fb.color[p] = color_pack(color_clamp(c));       /* raster.c:719-721 */
+    }
+
+    /* Fused gather: the finished tile also goes to the presenting GPU's plane over NVLink, as whole rows in 16-byte
+     * stores (per-pixel peer stores cost twice the kernel); other CTAs keep the SMs busy meanwhile. */
+    if (fb.present) {
+        __threadfence();
+        __syncthreads();
+        if (vw == TILE_W && (fb.width & 3) == 0) {
+            for (int i = threadIdx.x; i < vh * 16; i += 256) {
+                const size_t p = (size_t)(py0 + (i >> 4)) * fb.width + px0 + (i & 15) * 4;
+                *reinterpret_cast<uint4 *>(fb.present + p) = __ldcg(reinterpret_cast<const uint4 *>(fb.color + p));
+            }
+        } else {
+            for (int i = threadIdx.x; i < vh * TILE_W; i += 256) {
+                const size_t p = (size_t)(py0 + (i >> 6)) * fb.width + px0 + (i & 63);
+                if ((i & 63) < vw) fb.present[p] = __ldcg(fb.color + p);
+            }
+        }
     }
 }
 

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4)
 k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_func, uint32_t all_range01)
 {
     __shared__ VisSmem sm;
+    if (!lists_fit(b)) return;
 
     const uint32_t tile = blockIdx.x;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;

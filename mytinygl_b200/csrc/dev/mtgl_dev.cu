@@ -62,7 +62,9 @@ struct mtgl_dev {
     cudaEvent_t pinned_ev[2] = { nullptr, nullptr };
     int pinned_next = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t counters_ev = nullptr;      /* the counters of the current pass have reached h_counters */
     bool timed = false;
+    uint32_t *present = nullptr;            /* IPC-mapped colour plane of the presenting GPU (mtgl_dev_set_present_target) */
     std::vector<cudaEvent_t> stage_ev;      /* 8 per pass of the last batch: K1 | K2 | count+scan | fill | raster, then [6] end of K4a, [7] end of K4b */
     size_t stage_passes = 0;
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
@@ -181,6 +183,7 @@ FrameTargets frame_targets(const mtgl_dev *d)
 {
     FrameTargets fb;
     fb.color = d->color; fb.depth = d->depth; fb.stencil = d->stencil;
+    fb.present = d->present;
     fb.width = d->width; fb.height = d->height;
     fb.band_y0 = d->band_y0; fb.band_y1 = d->band_y1;
     fb.tiles_x = (d->width + TILE_W - 1) / TILE_W;
@@ -224,6 +227,7 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
     if (ce == cudaSuccess) ce = cudaMallocHost(&d->h_counters, sizeof(DevCounters));
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&d->pinned_ev[i], cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_start);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->counters_ev, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_stop);
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreate(&d->mark_ev[i]);
     if (ce != cudaSuccess) {
@@ -259,7 +263,9 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->pinned_ev[i]) cudaEventDestroy(d->pinned_ev[i]);
     }
     if (d->ev_start) cudaEventDestroy(d->ev_start);
+    if (d->counters_ev) cudaEventDestroy(d->counters_ev);
     if (d->ev_stop) cudaEventDestroy(d->ev_stop);
+    if (d->present) cudaIpcCloseMemHandle(d->present);
     for (cudaEvent_t e : d->stage_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (d->mark_ev[i]) cudaEventDestroy(d->mark_ev[i]);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -291,6 +297,14 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
         /* the caller may reuse 'data' immediately (glBufferData copies at call time, vbo.c:120-145) */
         CU(cudaStreamSynchronize(d->stream));
     }
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_pointer(mtgl_dev *d, uint32_t id, void **ptr, uint64_t *size)
+{
+    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    if (ptr) *ptr = d->buf[id].ptr;
+    if (size) *size = d->buf[id].size;
     return MTGL_OK;
 }
 
@@ -540,6 +554,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         b.counters = d->counters;
 
         cudaEvent_t *sev = &d->stage_ev[pidx * 8];
+        bool optimistic = false, had_triangles = false;
         CU(cudaEventRecord(sev[0], d->stream));
         ClearOp clr;
         std::memset(&clr, 0, sizeof clr);
@@ -584,16 +599,28 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             launch_bin_count(b, fb, d->stream);
             launch_bin_scan(b, fb, d->stream);
             CU(cudaEventRecord(sev[3], d->stream));
-            /* the list length is only known on the device: one small read-back sizes the list buffer */
+            /* The list length is only known on the device.  Single-pass batches (the normal frame) run optimistically:
+             * the list buffer is sized from a guess that only ever grows, the fill and raster kernels refuse to run
+             * when the scan result does not fit (BatchDev::guard), and the host checks the counters AFTER queueing
+             * everything -- so the GPU never idles waiting for the host; a miss re-queues fill + raster.  Multi-pass
+             * batches read the count back first. */
             CU(cudaMemcpyAsync(d->h_counters, d->counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, d->stream));
-            CU(cudaStreamSynchronize(d->stream));
-            if (d->h_counters->overflow) return fail(d, MTGL_E_OOM, "triangle record storage overflow");
-            const uint32_t refs = d->h_counters->tile_refs;
-            if ((rc = reserve(d, d->tile_list, std::max<size_t>((size_t)refs * 4, 1024)))) return rc;
+            static const bool sync_lists = std::getenv("MTGL_SYNC_LISTS") != nullptr;      /* A/B switch for profiling */
+            optimistic = passes.size() == 1 && !sync_lists;
+            if (optimistic) {
+                CU(cudaEventRecord(d->counters_ev, d->stream));
+                const size_t guess = std::max<size_t>(d->tile_list.cap / 4, (size_t)pi.n_triangles * 2 + 65536);
+                if ((rc = reserve(d, d->tile_list, guess * 4))) return rc;
+                b.guard = 1u;
+            } else {
+                CU(cudaStreamSynchronize(d->stream));
+                if (d->h_counters->overflow) return fail(d, MTGL_E_OOM, "triangle record storage overflow");
+                if ((rc = reserve(d, d->tile_list, std::max<size_t>((size_t)d->h_counters->tile_refs * 4, 1024)))) return rc;
+            }
             b.tile_list = (uint32_t *)d->tile_list.ptr;
             b.list_capacity = (uint32_t)(d->tile_list.cap / 4);
-            if (refs) launch_bin_fill(b, fb, d->stream);
-            tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += refs;
+            if (optimistic || d->h_counters->tile_refs) launch_bin_fill(b, fb, d->stream);
+            had_triangles = true;
         } else {
             CU(cudaEventRecord(sev[1], d->stream));
             CU(cudaEventRecord(sev[2], d->stream));
@@ -618,6 +645,24 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         plan.unordered_range01 = unordered_range01;
         launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
         CU(cudaEventRecord(sev[5], d->stream));
+        if (had_triangles) {
+            if (optimistic) {
+                CU(cudaEventSynchronize(d->counters_ev));       /* the scan finished long ago; the raster kernels are running */
+                if (d->h_counters->overflow) return fail(d, MTGL_E_OOM, "triangle record storage overflow");
+                if (d->h_counters->tile_refs > b.list_capacity) {      /* the guess was too small: nothing ran; size exactly and redo */
+                    CU(cudaStreamSynchronize(d->stream));
+                    if ((rc = reserve(d, d->tile_list, (size_t)d->h_counters->tile_refs * 4))) return rc;
+                    b.tile_list = (uint32_t *)d->tile_list.ptr;
+                    b.list_capacity = (uint32_t)(d->tile_list.cap / 4);
+                    CU(cudaEventRecord(sev[3], d->stream));
+                    launch_bin_fill(b, fb, d->stream);
+                    CU(cudaEventRecord(sev[4], d->stream));
+                    launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
+                    CU(cudaEventRecord(sev[5], d->stream));
+                }
+            }
+            tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs;
+        }
     }
     CU(cudaEventRecord(d->ev_stop, d->stream));
     CU(cudaGetLastError());
@@ -653,6 +698,7 @@ int mtgl_dev_write_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, const uint32
     size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
     if (color) CU(cudaMemcpyAsync(d->color + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
+    if (color && d->present) CU(cudaMemcpyAsync(d->present + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
     if (depth) CU(cudaMemcpyAsync(d->depth + o, depth + o, n * 4, cudaMemcpyHostToDevice, d->stream));
     if (stencil) CU(cudaMemcpyAsync(d->stencil + o, stencil + o, n, cudaMemcpyHostToDevice, d->stream));
     CU(cudaStreamSynchronize(d->stream));
@@ -665,6 +711,33 @@ int mtgl_dev_plane_pointers(mtgl_dev *d, void **color, void **depth, void **sten
     if (color) *color = d->color;
     if (depth) *depth = d->depth;
     if (stencil) *stencil = d->stencil;
+    return MTGL_OK;
+}
+
+int mtgl_dev_export_color_plane(mtgl_dev *d, void *handle_out)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) <= MTGL_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d || !handle_out) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d->color));
+    std::memset(handle_out, 0, MTGL_IPC_HANDLE_BYTES);
+    std::memcpy(handle_out, &h, sizeof h);
+    return MTGL_OK;
+}
+
+int mtgl_dev_set_present_target(mtgl_dev *d, const void *handle)
+{
+    if (!d) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    CU(cudaStreamSynchronize(d->stream));
+    if (d->present) { CU(cudaIpcCloseMemHandle(d->present)); d->present = nullptr; }
+    if (!handle) return MTGL_OK;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    d->present = static_cast<uint32_t *>(p);
     return MTGL_OK;
 }
 
