@@ -352,7 +352,9 @@ def run_b200(args, workload):
         if whole_on_rank0:
             gather()
             torch.cuda.current_stream().synchronize()
-        if pinned_out is not None:      # glFinish + read the colour rows into pinned host memory
+        else:
+            L.glFinish()                # the frame is rendered before it is read
+        if pinned_out is not None:      # read the colour rows into pinned host memory
             base = pinned_out.data_ptr() - ry0 * w * 4
             assert L.mtgl_dev_read_framebuffer(dev, ry0, ry1, base, None, None) == 0
 

@@ -267,7 +267,12 @@ __device__ __forceinline__ int integral_exponent(float y)
 __device__ __forceinline__ float pow_pos(float x, float y, int iy)
 {
     if (iy == 0) return powf(x, y);
-    double r = 1.0, b = (double)x;
+    double b = (double)x;
+    if ((iy & (iy - 1)) == 0) {         /* 1, 2, 4 ... 128: squarings only (the exponent is uniform across the warp) */
+        for (int n = iy; n > 1; n >>= 1) b *= b;
+        return (float)b;
+    }
+    double r = 1.0;
     for (int n = iy; n; n >>= 1) {
         if (n & 1) r *= b;
         b *= b;

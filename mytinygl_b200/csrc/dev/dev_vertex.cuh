@@ -30,15 +30,20 @@ __device__ __forceinline__ void fetch_attrib(const DevAttrib &a, int32_t index, 
         return;
     }
     const uint8_t *p = a.ptr + off;
+    if (a.type == MTGL_TYPE_F32 && (((uintptr_t)p) & 3u) == 0) {       /* the common case: aligned floats, no per-component branching */
+        const float *f = reinterpret_cast<const float *>(p);
+        const int n = (int)a.size;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i < want) out[i] = (i < n) ? __ldg(f + i) : ((i == 3) ? 1.0f : 0.0f);
+        return;
+    }
     for (int i = 0; i < want; i++) {
         if (i < (int)a.size) {
             if (a.type == MTGL_TYPE_F32) {
-                if ((((uintptr_t)p) & 3u) == 0) out[i] = __ldg((const float *)p + i);
-                else {
-                    uint32_t w = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
-                                 ((uint32_t)p[4 * i + 3] << 24);
-                    out[i] = __uint_as_float(w);
-                }
+                uint32_t w = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
+                             ((uint32_t)p[4 * i + 3] << 24);
+                out[i] = __uint_as_float(w);
             } else out[i] = (float)p[i] / 255.0f;
         } else out[i] = (i == 3) ? 1.0f : 0.0f;
     }
