@@ -609,7 +609,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             optimistic = passes.size() == 1 && !sync_lists;
             if (optimistic) {
                 CU(cudaEventRecord(d->counters_ev, d->stream));
-                const size_t guess = std::max<size_t>(d->tile_list.cap / 4, (size_t)pi.n_triangles * 2 + 65536);
+                size_t guess = std::max<size_t>(d->tile_list.cap / 4, (size_t)pi.n_triangles * 2 + 65536);
+                if (const char *e = std::getenv("MTGL_LIST_GUESS")) guess = std::max<size_t>(d->tile_list.cap / 4, (size_t)std::atoll(e));   /* test knob: force the re-queue path */
                 if ((rc = reserve(d, d->tile_list, guess * 4))) return rc;
                 b.guard = 1u;
             } else {

@@ -59,3 +59,72 @@ def test_cuda_bands_stitch_to_full_frame(b200, front_oracle, case, split):
         bands.append([p[y0:y1] for p in planes])
     got = tuple(np.concatenate([bands[0][i], bands[1][i]]) for i in range(3))
     assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
+
+
+@pytest.mark.parametrize("case", [("c1_suzanne", 800, 600, 0), ("depth_order", 320, 240, 8), ("c3_fill", 256, 144, 4),
+                                  ("c4_grid", 480, 270, 3 | (2 << 8))], ids=case_id)
+def test_list_guess_miss_requeues(b200, front_oracle, case, monkeypatch):
+    """Optimistic tile-list sizing (mtgl_dev.cu): when the guessed capacity is too small the fill and raster kernels
+    must leave everything untouched and the host re-queues them; the frame is the same as with a fitting guess."""
+    want = b200.render(*case)
+    monkeypatch.setenv("MTGL_LIST_GUESS", "8")
+    got = b200.render(*case)                     # a fresh context: its list buffer starts empty
+    for a, b in zip(want[:3], got[:3]):
+        assert np.array_equal(a, b)
+    assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
+
+
+def _present_child(conn, case):
+    """second process: renders `case` with its colour stores mirrored into the parent's plane"""
+    import ctypes
+    from mytinygl_b200 import load_b200
+    lib = load_b200()
+    L = lib.lib
+    L.mtgl_dev_set_present_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    name, w, h, variant = case
+    lib.create(w, h)
+    handle = (ctypes.c_ubyte * 64)(*conn.recv())
+    rc = L.mtgl_dev_set_present_target(lib.device(), handle)
+    if rc == 0:
+        L.glClearColor(ctypes.c_float(0.25), ctypes.c_float(0.5), ctypes.c_float(0.75), ctypes.c_float(1.0))
+        L.glClear(0x4000 | 0x0100 | 0x0400)
+        L.glClearColor(ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(1))
+        assert L.scene_render(name.encode(), w, h, variant) == 0
+        color = lib.read()[0]
+        conn.send((0, color))
+    else:
+        conn.send((rc, None))
+    conn.recv()             # keep the mapping alive until the parent has read its plane
+    lib.destroy()
+
+
+@pytest.mark.parametrize("case", [("c4_grid", 517, 389, 3 | (2 << 8)), ("state_churn", 517, 389, 0), ("lines", 320, 240, 19)], ids=case_id)
+def test_present_target_mirrors_color(b200, case):
+    """mtgl_dev_export_color_plane / mtgl_dev_set_present_target: every colour store of a context also lands in the
+    plane it was given.  Two processes on one GPU here (CUDA IPC needs two processes); bench.py --gpus N uses the same
+    calls across GPUs over NVLink and checks the assembled frame against a single-GPU render."""
+    import ctypes
+    import multiprocessing as mp
+    L = b200.lib
+    L.mtgl_dev_export_color_plane.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    name, w, h, variant = case
+    b200.create(w, h)
+    L.glClearColor(ctypes.c_float(1), ctypes.c_float(0), ctypes.c_float(1), ctypes.c_float(0))
+    L.glClear(0x4000)
+    L.glFinish()
+    handle = (ctypes.c_ubyte * 64)()
+    assert L.mtgl_dev_export_color_plane(b200.device(), handle) == 0
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    proc = ctx.Process(target=_present_child, args=(child, case))
+    proc.start()
+    try:
+        parent.send(list(handle))
+        rc, theirs = parent.recv()
+        assert rc == 0, f"mtgl_dev_set_present_target failed ({rc})"
+        mine = b200.read()[0]
+        assert np.array_equal(mine, theirs)
+    finally:
+        parent.send("done")
+        proc.join(60)
+        b200.destroy()
