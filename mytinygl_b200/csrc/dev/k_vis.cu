@@ -43,6 +43,7 @@ constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start 4 banks apart, 16-byte aligned */
 constexpr int VIS_WINDOW = 1024;        /* list entries per round = capacity of the large-triangle queue */
 constexpr int VIS_SMALL_AREA = 256;     /* clamped box area up to which 8 lanes handle a triangle */
+constexpr int VIS_EXACT_EXTENT = 2047;   /* vertex extent up to which a small triangle's edge values are exact integers in float */
 constexpr int VIS_COORD_LIMIT = 1 << 22;    /* |snapped coordinate| below which pixel - vertex differences are exact integers in float */
 
 struct VisSmem {
@@ -213,7 +214,9 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
                 const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
                 box = (uint32_t)X0 | ((uint32_t)Y0 << 8) | ((uint32_t)X1 << 16) | ((uint32_t)Y1 << 24);
                 small = (X1 - X0 + 1) * (Y1 - Y0 + 1) <= VIS_SMALL_AREA && coord_small(h.row0.x) && coord_small(h.row0.y) &&
-                        coord_small(h.row0.z) && coord_small(h.row0.w) && coord_small(h.row1.x) && coord_small(h.row1.y);
+                        coord_small(h.row0.z) && coord_small(h.row0.w) && coord_small(h.row1.x) && coord_small(h.row1.y) &&
+                        max(max(h.row0.x, h.row0.z), h.row1.x) - min(min(h.row0.x, h.row0.z), h.row1.x) <= VIS_EXACT_EXTENT &&
+                        max(max(h.row0.y, h.row0.w), h.row1.y) - min(min(h.row0.y, h.row0.w), h.row1.y) <= VIS_EXACT_EXTENT;
                 if (!small) sm.large_rec[atomicAdd(&sm.large_n, 1u)] = r;
             } else {
                 h.row0 = make_int4(0, 0, 0, 0); h.row1 = make_int4(0, 0, 0, 0); h.row2 = make_uint4(0, 0, 0, 0); h.z0 = h.z1 = h.z2 = 0.0f;
@@ -250,14 +253,18 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
 #pragma unroll 1
                     for (int cx = X0 + col; cx <= X1; cx += 8) {
                         const float fx = (float)(px0 + cx);
-                        /* column part of the edge functions; the row part advances by exact integer steps */
-                        const float t0 = (fx - E.ax[0]) * E.dy[0], t1 = (fx - E.ax[1]) * E.dy[1], t2 = (fx - E.ax[2]) * E.dy[2];
-                        float q0 = fy - E.ay[0], q1 = fy - E.ay[1], q2 = fy - E.ay[2];
+                        /* Edge values at the column's first row, then one subtraction per row: a small triangle's
+                         * vertex and pixel differences are below 2^11 (checked when it was classified), so both
+                         * products of raster.c:299-302 are below 2^22, every edge value is an exactly represented
+                         * integer, and e(x, y + 1) = e(x, y) - dx holds exactly in float. */
+                        const float q0 = fy - E.ay[0], q1 = fy - E.ay[1], q2 = fy - E.ay[2];
+                        float e0 = (fx - E.ax[0]) * E.dy[0] - q0 * E.dx[0];
+                        float e1 = (fx - E.ax[1]) * E.dy[1] - q1 * E.dx[1];
+                        float e2 = (fx - E.ax[2]) * E.dy[2] - q2 * E.dx[2];
                         unsigned long long *kp = &sm.key[Y0 * VIS_PITCH + cx];
                         /* not unrolled: the four groups must stay in one instruction stream whatever their row counts */
 #pragma unroll 1
-                        for (int y = Y0; y <= Y1; y++, kp += VIS_PITCH, q0 += 1.0f, q1 += 1.0f, q2 += 1.0f) {
-                            const float e0 = t0 - q0 * E.dx[0], e1 = t1 - q1 * E.dx[1], e2 = t2 - q2 * E.dx[2];
+                        for (int y = Y0; y <= Y1; y++, kp += VIS_PITCH, e0 -= E.dx[0], e1 -= E.dx[1], e2 -= E.dx[2]) {
                             if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
                                 const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
                                 const float z = b0 * z0 + b1 * z1 + b2 * z2;
