@@ -41,14 +41,18 @@ void note_launch();
 
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start 4 banks apart, 16-byte aligned */
-constexpr int VIS_WINDOW = 1024;        /* list entries per round = capacity of the large-triangle queue */
+constexpr int VIS_LARGE_CAP = 512;      /* capacity of the large-triangle queue (a full queue makes the finding warp do the triangle alone) */
+constexpr int VIS_EXACT_EXTENT = 2047;  /* vertex extent up to which all edge values inside a tile are exactly represented integers */
+constexpr int VIS_COORD_LIMIT = 1 << 22;
 constexpr int VIS_SMALL_AREA = 256;     /* clamped box area up to which 8 lanes handle a triangle */
-constexpr int VIS_EXACT_EXTENT = 2047;   /* vertex extent up to which a small triangle's edge values are exact integers in float */
-constexpr int VIS_COORD_LIMIT = 1 << 22;    /* |snapped coordinate| below which pixel - vertex differences are exact integers in float */
 
 struct VisSmem {
     unsigned long long key[TILE_H * VIS_PITCH];
-    uint32_t large_rec[VIS_WINDOW];
+    uint32_t large_rec[VIS_LARGE_CAP];
+    /* per warp: the prepared small triangles of the current chunk, 16 words each: edge k as e = A*x + B*y + C in
+     * tile-relative pixel coordinates -- row 0 (A0 B0 C0 A1), row 1 (B1 C1 A2 B2), row 2 (C2, 1/area, z0, z1),
+     * row 3 (z2, id, X0 | Y0 << 6 | (width - 1) << 12 | start-in-run << 18, 1/width) */
+    float4 prep[RASTER_THREADS / 32][4][32];
     uint32_t next_chunk;
     uint32_t large_n;
 };
@@ -91,11 +95,6 @@ __device__ __forceinline__ float depth_of(float z, bool range01, double dnear, d
     return (float)((double)d * (dfar - dnear) + dnear);
 }
 
-__device__ __forceinline__ bool coord_small(int32_t v)      /* |v| < VIS_COORD_LIMIT without overflowing on INT32_MIN */
-{
-    return (uint32_t)v + (uint32_t)VIS_COORD_LIMIT < 2u * (uint32_t)VIS_COORD_LIMIT;
-}
-
 struct VisHead {                /* the 64 leading bytes of a record: rows 0-3 */
     int4 row0, row1;            /* x0 y0 x1 y1 | x2 y2 area inv_area */
     uint4 row2;                 /* bbox_min bbox_max state_flags id */
@@ -133,10 +132,52 @@ __device__ __forceinline__ void prepare_edges(EdgeSet &E, int x0, int y0, int x1
     }
 }
 
+__device__ __forceinline__ bool coord_small(int32_t v)      /* |v| < VIS_COORD_LIMIT without overflowing on INT32_MIN */
+{
+    return (uint32_t)v + (uint32_t)VIS_COORD_LIMIT < 2u * (uint32_t)VIS_COORD_LIMIT;
+}
+
+
+/* one triangle over its clamped box in 8x4 pixel blocks, the blocks first, first + stride, ... by the calling warp:
+ * the reference's expressions evaluated directly (any size of triangle, any coordinates) */
+__device__ __forceinline__ void raster_blocks(unsigned long long *keys, const VisMode &mode, const BatchDev &b, const VisHead &h,
+                                              int px0, int py0, int first, int stride)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const int X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0), Y0 = max((int)(h.row2.x >> 16) - py0, 0);
+    const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
+    bool range01 = true;
+    double dnear = 0.0, dfar = 1.0;
+    if (!mode.all_range01) {
+        const RasterCfg *cfg = b.cfgs + (h.row2.z & STATE_INDEX_MASK);
+        range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
+        dnear = cfg->depth_near; dfar = cfg->depth_far;
+    }
+    EdgeSet E;
+    prepare_edges(E, h.row0.x, h.row0.y, h.row0.z, h.row0.w, h.row1.x, h.row1.y, __int_as_float(h.row1.z), __int_as_float(h.row1.w));
+    const int nbx = (X1 - X0 + 8) >> 3, nby = (Y1 - Y0 + 4) >> 2;
+    const int nblk = nbx * nby;
+    for (int blk = first; blk < nblk; blk += stride) {
+        const int byi = blk / nbx, bxi = blk - byi * nbx;
+        const int x = X0 + bxi * 8 + (int)(lane & 7), y = Y0 + byi * 4 + (int)(lane >> 3);
+        if (x > X1 || y > Y1) continue;
+        const float fx = (float)(px0 + x), fy = (float)(py0 + y);
+        const float e0 = (fx - E.ax[0]) * E.dy[0] - (fy - E.ay[0]) * E.dx[0];
+        const float e1 = (fx - E.ax[1]) * E.dy[1] - (fy - E.ay[1]) * E.dx[1];
+        const float e2 = (fx - E.ax[2]) * E.dy[2] - (fy - E.ay[2]) * E.dx[2];
+        if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
+            const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
+            const float z = b0 * h.z0 + b1 * h.z1 + b2 * h.z2;
+            key_min(&keys[y * VIS_PITCH + x], make_key(mode, depth_of(z, range01, dnear, dfar), h.row2.w));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS, 4)
 k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_func, uint32_t all_range01)
 {
-    __shared__ VisSmem sm;
+    extern __shared__ __align__(16) unsigned char vis_smem_raw[];
+    VisSmem &sm = *reinterpret_cast<VisSmem *>(vis_smem_raw);
     if (!lists_fit(b)) return;
 
     const uint32_t tile = blockIdx.x;
@@ -190,132 +231,129 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = (int)(lane >> 3), col = (int)(lane & 7);
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t *list = b.tile_list + b.tile_offset[tile];
 
-    for (uint32_t ws = 0; ws < L; ws += VIS_WINDOW) {
-        const uint32_t wn = min((uint32_t)VIS_WINDOW, L - ws);
-
-        /* ---- phase 1: warps take 32 list entries at a time; small triangles are finished on the spot ---- */
-        for (;;) {
-            uint32_t c = 0;
-            if (lane == 0) c = atomicAdd(&sm.next_chunk, 32u);
-            c = __shfl_sync(0xFFFFFFFFu, c, 0);
-            if (c >= wn) break;
-            const uint32_t e = c + lane;
-            VisHead h;
-            uint32_t r = 0, box = 0;
-            bool small = false;
-            if (e < wn) {
-                r = list[ws + e];
-                load_vis_head(h, b.records + r);
-                /* the record's box is already clamped to viewport, scissor, framebuffer and band: clamp to the tile */
-                const int X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0), Y0 = max((int)(h.row2.x >> 16) - py0, 0);
-                const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
-                box = (uint32_t)X0 | ((uint32_t)Y0 << 8) | ((uint32_t)X1 << 16) | ((uint32_t)Y1 << 24);
-                small = (X1 - X0 + 1) * (Y1 - Y0 + 1) <= VIS_SMALL_AREA && coord_small(h.row0.x) && coord_small(h.row0.y) &&
-                        coord_small(h.row0.z) && coord_small(h.row0.w) && coord_small(h.row1.x) && coord_small(h.row1.y) &&
-                        max(max(h.row0.x, h.row0.z), h.row1.x) - min(min(h.row0.x, h.row0.z), h.row1.x) <= VIS_EXACT_EXTENT &&
-                        max(max(h.row0.y, h.row0.w), h.row1.y) - min(min(h.row0.y, h.row0.w), h.row1.y) <= VIS_EXACT_EXTENT;
-                if (!small) sm.large_rec[atomicAdd(&sm.large_n, 1u)] = r;
-            } else {
-                h.row0 = make_int4(0, 0, 0, 0); h.row1 = make_int4(0, 0, 0, 0); h.row2 = make_uint4(0, 0, 0, 0); h.z0 = h.z1 = h.z2 = 0.0f;
-            }
-            const uint32_t smask = __ballot_sync(0xFFFFFFFFu, small);
-            if (!smask) continue;
-#pragma unroll 1
-            for (int it = 0; it < 8; it++) {
-                if (!((smask >> (it * 4)) & 0xFu)) continue;        /* warp-uniform */
-                const int src = it * 4 + grp;
-                const bool has = ((smask >> src) & 1u) != 0u;
-                /* each group of 8 lanes receives the head of its triangle */
-                const int x0 = __shfl_sync(0xFFFFFFFFu, h.row0.x, src), y0 = __shfl_sync(0xFFFFFFFFu, h.row0.y, src);
-                const int x1 = __shfl_sync(0xFFFFFFFFu, h.row0.z, src), y1 = __shfl_sync(0xFFFFFFFFu, h.row0.w, src);
-                const int x2 = __shfl_sync(0xFFFFFFFFu, h.row1.x, src), y2 = __shfl_sync(0xFFFFFFFFu, h.row1.y, src);
-                const float area = __int_as_float(__shfl_sync(0xFFFFFFFFu, h.row1.z, src));
-                const float inv_area = __int_as_float(__shfl_sync(0xFFFFFFFFu, h.row1.w, src));
-                const uint32_t state = __shfl_sync(0xFFFFFFFFu, h.row2.z, src);
-                const uint32_t id = __shfl_sync(0xFFFFFFFFu, h.row2.w, src);
-                const float z0 = __shfl_sync(0xFFFFFFFFu, h.z0, src), z1 = __shfl_sync(0xFFFFFFFFu, h.z1, src), z2 = __shfl_sync(0xFFFFFFFFu, h.z2, src);
-                const uint32_t bx = __shfl_sync(0xFFFFFFFFu, box, src);
-                if (has) {
-                    const int X0 = (int)(bx & 0xFFu), Y0 = (int)((bx >> 8) & 0xFFu), X1 = (int)((bx >> 16) & 0xFFu), Y1 = (int)(bx >> 24);
-                    bool range01 = true;
-                    double dnear = 0.0, dfar = 1.0;
-                    if (!mode.all_range01) {
-                        const RasterCfg *cfg = b.cfgs + (state & STATE_INDEX_MASK);
-                        range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
-                        dnear = cfg->depth_near; dfar = cfg->depth_far;
-                    }
-                    EdgeSet E;
-                    prepare_edges(E, x0, y0, x1, y1, x2, y2, area, inv_area);
-                    const float fy = (float)(py0 + Y0);
-#pragma unroll 1
-                    for (int cx = X0 + col; cx <= X1; cx += 8) {
-                        const float fx = (float)(px0 + cx);
-                        /* Edge values at the column's first row, then one subtraction per row: a small triangle's
-                         * vertex and pixel differences are below 2^11 (checked when it was classified), so both
-                         * products of raster.c:299-302 are below 2^22, every edge value is an exactly represented
-                         * integer, and e(x, y + 1) = e(x, y) - dx holds exactly in float. */
-                        const float q0 = fy - E.ay[0], q1 = fy - E.ay[1], q2 = fy - E.ay[2];
-                        float e0 = (fx - E.ax[0]) * E.dy[0] - q0 * E.dx[0];
-                        float e1 = (fx - E.ax[1]) * E.dy[1] - q1 * E.dx[1];
-                        float e2 = (fx - E.ax[2]) * E.dy[2] - q2 * E.dx[2];
-                        unsigned long long *kp = &sm.key[Y0 * VIS_PITCH + cx];
-                        /* not unrolled: the four groups must stay in one instruction stream whatever their row counts */
-#pragma unroll 1
-                        for (int y = Y0; y <= Y1; y++, kp += VIS_PITCH, e0 -= E.dx[0], e1 -= E.dx[1], e2 -= E.dx[2]) {
-                            if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
-                                const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
-                                const float z = b0 * z0 + b1 * z1 + b2 * z2;
-                                key_min(kp, make_key(mode, depth_of(z, range01, dnear, dfar), id));
-                            }
-                        }
-                    }
-                }
-                __syncwarp();       /* the four groups leave their loops at different times: rejoin before the next shuffles */
+    /* ---- phase 1: warps take 32 list entries at a time.  The boxes of the chunk's small triangles are laid end to end
+     * into one run of pixels and the warp walks that run 32 pixels per step, one pixel per lane, whatever triangle it
+     * belongs to -- every lane has a box pixel to test in every step.  "Small" also means a vertex extent below 2^11:
+     * then every edge value inside the tile is an integer below 2^24, exactly represented in float, and
+     * e = A*x + B*y + C with tile-relative x, y gives the same bits as the reference's expression (raster.c:299-302)
+     * in two FMAs per edge.  Everything else is queued for phase 2. ---- */
+    const float px0f = (float)px0, py0f = (float)py0;
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(&sm.next_chunk, 32u);
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        if (c >= L) break;
+        const uint32_t e = c + lane;
+        uint32_t area = 0;                      /* box pixels of this lane's triangle; 0 = no small triangle here */
+        bool alone = false;                     /* a large triangle that did not fit the queue */
+        VisHead h;
+        int X0 = 0, Y0 = 0, bw = 1;
+        if (e < L) {
+            const uint32_t r = list[e];
+            load_vis_head(h, b.records + r);
+            /* the record's box is already clamped to viewport, scissor, framebuffer and band: clamp to the tile */
+            X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0); Y0 = max((int)(h.row2.x >> 16) - py0, 0);
+            const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
+            bw = X1 - X0 + 1;
+            area = (uint32_t)(bw * (Y1 - Y0 + 1));
+            const bool small = area <= (uint32_t)VIS_SMALL_AREA && mode.all_range01 &&
+                               coord_small(h.row0.x) && coord_small(h.row0.y) && coord_small(h.row0.z) && coord_small(h.row0.w) &&
+                               coord_small(h.row1.x) && coord_small(h.row1.y) &&
+                               max(max(h.row0.x, h.row0.z), h.row1.x) - min(min(h.row0.x, h.row0.z), h.row1.x) <= VIS_EXACT_EXTENT &&
+                               max(max(h.row0.y, h.row0.w), h.row1.y) - min(min(h.row0.y, h.row0.w), h.row1.y) <= VIS_EXACT_EXTENT;
+            if (!small) {
+                const uint32_t at = atomicAdd(&sm.large_n, 1u);
+                if (at < (uint32_t)VIS_LARGE_CAP) sm.large_rec[at] = r; else alone = true;
+                area = 0;
             }
         }
-        __syncthreads();
-
-        /* ---- phase 2: the queued large triangles, all warps on each, 8x4 pixel blocks dealt round-robin ---- */
-        const uint32_t nl = sm.large_n;
-        for (uint32_t q = 0; q < nl; q++) {
-            VisHead h;
-            load_vis_head(h, b.records + sm.large_rec[q]);
-            const int X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0), Y0 = max((int)(h.row2.x >> 16) - py0, 0);
-            const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
-            bool range01 = true;
-            double dnear = 0.0, dfar = 1.0;
-            if (!mode.all_range01) {
-                const RasterCfg *cfg = b.cfgs + (h.row2.z & STATE_INDEX_MASK);
-                range01 = (cfg->flags & RC_DEPTH_RANGE_01) != 0u;
-                dnear = cfg->depth_near; dfar = cfg->depth_far;
-            }
+        /* (rare) queue full: the warp rasterises those triangles by itself, one after the other */
+        for (uint32_t am = __ballot_sync(0xFFFFFFFFu, alone); am; am &= am - 1) {
+            const int src = __ffs(am) - 1;
+            VisHead g;
+            g.row0.x = __shfl_sync(0xFFFFFFFFu, h.row0.x, src); g.row0.y = __shfl_sync(0xFFFFFFFFu, h.row0.y, src);
+            g.row0.z = __shfl_sync(0xFFFFFFFFu, h.row0.z, src); g.row0.w = __shfl_sync(0xFFFFFFFFu, h.row0.w, src);
+            g.row1.x = __shfl_sync(0xFFFFFFFFu, h.row1.x, src); g.row1.y = __shfl_sync(0xFFFFFFFFu, h.row1.y, src);
+            g.row1.z = __shfl_sync(0xFFFFFFFFu, h.row1.z, src); g.row1.w = __shfl_sync(0xFFFFFFFFu, h.row1.w, src);
+            g.row2.x = __shfl_sync(0xFFFFFFFFu, h.row2.x, src); g.row2.y = __shfl_sync(0xFFFFFFFFu, h.row2.y, src);
+            g.row2.z = __shfl_sync(0xFFFFFFFFu, h.row2.z, src); g.row2.w = __shfl_sync(0xFFFFFFFFu, h.row2.w, src);
+            g.z0 = __shfl_sync(0xFFFFFFFFu, h.z0, src); g.z1 = __shfl_sync(0xFFFFFFFFu, h.z1, src); g.z2 = __shfl_sync(0xFFFFFFFFu, h.z2, src);
+            raster_blocks(sm.key, mode, b, g, px0, py0, 0, 1);
+            __syncwarp();
+        }
+        const uint32_t smask = __ballot_sync(0xFFFFFFFFu, area != 0u);
+        if (!smask) continue;
+        /* start of each small triangle's box in the run (exclusive scan of the areas) */
+        uint32_t incl = area;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t start = incl - area;
+        if (area) {                             /* prepared triangle -> this warp's staging slots, in compacted order */
             EdgeSet E;
             prepare_edges(E, h.row0.x, h.row0.y, h.row0.z, h.row0.w, h.row1.x, h.row1.y, __int_as_float(h.row1.z), __int_as_float(h.row1.w));
-            const int nbx = (X1 - X0 + 8) >> 3, nby = (Y1 - Y0 + 4) >> 2;
-            const int nblk = nbx * nby;
-            /* rotate the first warp with the queue position so that one-block triangles do not all land on warp 0 */
-            for (int blk = (int)((warp + 8u - (q & 7u)) & 7u); blk < nblk; blk += RASTER_THREADS / 32) {
-                const int byi = blk / nbx, bxi = blk - byi * nbx;
-                const int x = X0 + bxi * 8 + (int)(lane & 7), y = Y0 + byi * 4 + (int)(lane >> 3);
-                if (x > X1 || y > Y1) continue;
-                const float fx = (float)(px0 + x), fy = (float)(py0 + y);
-                const float e0 = (fx - E.ax[0]) * E.dy[0] - (fy - E.ay[0]) * E.dx[0];
-                const float e1 = (fx - E.ax[1]) * E.dy[1] - (fy - E.ay[1]) * E.dx[1];
-                const float e2 = (fx - E.ax[2]) * E.dy[2] - (fy - E.ay[2]) * E.dx[2];
-                if (fminf(fminf(e0, e1), e2) >= 0.0f) {
-                    const float b0 = e0 * E.inv_area, b1 = e1 * E.inv_area, b2 = e2 * E.inv_area;
-                    const float z = b0 * h.z0 + b1 * h.z1 + b2 * h.z2;
-                    key_min(&sm.key[y * VIS_PITCH + x], make_key(mode, depth_of(z, range01, dnear, dfar), h.row2.w));
+            float A[3], B[3], C[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {       /* all operands and results are integers below 2^24: exact */
+                A[k] = E.dy[k]; B[k] = -E.dx[k];
+                C[k] = (px0f - E.ax[k]) * E.dy[k] - (py0f - E.ay[k]) * E.dx[k];
+            }
+            const uint32_t ci = (uint32_t)__popc(smask & lt_mask);
+            float4 *slot = &sm.prep[warp][0][ci];
+            slot[0 * 32] = make_float4(A[0], B[0], C[0], A[1]);
+            slot[1 * 32] = make_float4(B[1], C[1], A[2], B[2]);
+            slot[2 * 32] = make_float4(C[2], E.inv_area, h.z0, h.z1);
+            slot[3 * 32] = make_float4(h.z2, __uint_as_float(h.row2.w),
+                                       __uint_as_float((uint32_t)X0 | ((uint32_t)Y0 << 6) | ((uint32_t)(bw - 1) << 12) | (start << 18)), 1.0f / (float)bw);
+        }
+        __syncwarp();
+        uint32_t before = 0;                    /* small triangles that start before the current step */
+        for (uint32_t base = 0; base < total; base += 32) {
+            const int rel = (int)start - (int)base;
+            const uint32_t marks = __reduce_or_sync(0xFFFFFFFFu, (area != 0u && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+            const uint32_t p = base + lane;
+            if (p < total) {
+                const uint32_t ci = before + (uint32_t)__popc(marks & (0xFFFFFFFFu >> (31u - lane))) - 1u;   /* the triangle whose box holds pixel p */
+                const float4 *slot = &sm.prep[warp][0][ci];
+                const float4 r3 = slot[3 * 32];
+                const uint32_t bs = __float_as_uint(r3.z), q = p - (bs >> 18);
+                const int w = (int)((bs >> 12) & 63u) + 1;
+                /* row inside the box: (q + 1/2) / w is at least 1/(2w) >= 1/128 away from an integer, the product with the
+                 * rounded reciprocal is off by less than 2^-14, so the truncation is the exact quotient */
+                const int yy = __float2int_rz(((float)q + 0.5f) * r3.w);
+                const int x = (int)(bs & 63u) + ((int)q - yy * w), y = (int)((bs >> 6) & 63u) + yy;
+                const float fx = (float)x, fy = (float)y;
+                const float4 r0 = slot[0 * 32], r1 = slot[1 * 32], r2 = slot[2 * 32];
+                const float e0 = __fmaf_rn(r0.x, fx, __fmaf_rn(r0.y, fy, r0.z));
+                const float e1 = __fmaf_rn(r0.w, fx, __fmaf_rn(r1.x, fy, r1.y));
+                const float e2 = __fmaf_rn(r1.z, fx, __fmaf_rn(r1.w, fy, r2.x));
+                if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
+                    const float b0 = e0 * r2.y, b1 = e1 * r2.y, b2 = e2 * r2.y;
+                    const float z = b0 * r2.z + b1 * r2.w + b2 * r3.x;
+                    key_min(&sm.key[y * VIS_PITCH + x], make_key(mode, depth_of(z, true, 0.0, 1.0), __float_as_uint(r3.y)));
                 }
             }
+            before += (uint32_t)__popc(marks);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { sm.next_chunk = 0; sm.large_n = 0; }
-        __syncthreads();
+        __syncwarp();       /* the staging slots are rewritten by the next chunk */
     }
+    __syncthreads();
+
+    /* ---- phase 2: the queued triangles, all warps on each, 8x4 pixel blocks dealt round-robin (the first warp rotates
+     * with the queue position so that one-block triangles do not all land on warp 0) ---- */
+    const uint32_t nl = min(sm.large_n, (uint32_t)VIS_LARGE_CAP);
+    for (uint32_t q = 0; q < nl; q++) {
+        VisHead h;
+        load_vis_head(h, b.records + sm.large_rec[q]);
+        raster_blocks(sm.key, mode, b, h, px0, py0, (int)((warp + 8u - (q & 7u)) & 7u), RASTER_THREADS / 32);
+    }
+    __syncthreads();
 
     /* ---- write-back: depth plane + visibility plane (record index of the surviving fragment) ---- */
     const uint32_t slot_mask = (1u << CHUNK_SHIFT) - 1u;
@@ -362,7 +400,14 @@ void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const Clear
                           bool all_range01, cudaStream_t s)
 {
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
-    k_vis<<<tiles, RASTER_THREADS, 0, s>>>(b, fb, clear, planes, depth_func, all_range01 ? 1u : 0u);
+    static bool configured[64] = { false };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {      /* more than 48 KB of shared memory is a per-device opt-in */
+        cudaFuncSetAttribute(k_vis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisSmem));
+        configured[dev] = true;
+    }
+    k_vis<<<tiles, RASTER_THREADS, sizeof(VisSmem), s>>>(b, fb, clear, planes, depth_func, all_range01 ? 1u : 0u);
     note_launch();
 }
 
