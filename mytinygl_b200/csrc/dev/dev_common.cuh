@@ -417,6 +417,7 @@ struct RasterPlan {
     bool any_deferrable;        /* some draw has a deferrable state (K4a + K4b) */
     bool any_ordered_vis;       /* ... that is not in the unordered class (sorted K4a) */
     bool any_in_order;          /* some draw needs in-order shading (general kernel) */
+    bool plain_in_order;        /* ... and the pass holds nothing but in-order filled triangles */
     uint32_t unordered_func;    /* depth function (0..7) of the unordered class, 0 when the class is empty */
     bool unordered_range01;     /* every unordered state has depth range [0,1] */
 };

@@ -439,7 +439,7 @@ __device__ __forceinline__ TriHead broadcast_head(const TriHead &h, int src)
     return o;
 }
 
-template <bool VIS>
+template <bool VIS, bool PLAIN>
 __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, const TriHead &h, int tile_px, int tile_py,
                                 int X0, int Y0, int X1, int Y1, int rx0, int ry0, bool &pending)
 {
@@ -455,9 +455,9 @@ __device__ void raster_triangle(const BatchDev &b, RasterSmem &sm, uint32_t r, c
     /* shading can be deferred when nothing between the depth test and the colour write depends on or discards
      * per fragment state: no blending, no alpha test, full colour mask (RC_DEFER, mirrored in the record).
      * The visibility-only kernel only ever sees such records. */
-    const bool defer = VIS || (state_flags & STATE_DEFER_BIT) != 0;
+    const bool defer = VIS || (!PLAIN && (state_flags & STATE_DEFER_BIT) != 0);
 
-    if (!VIS) {
+    if (!VIS && !PLAIN) {
         if (defer) pending = true;
         else if (pending) {     /* deferred colours of earlier triangles must land before an in-order triangle reads them */
             resolve_region(b, sm, rx0, ry0, tile_px, tile_py);
@@ -757,7 +757,7 @@ __device__ void sort_window(RasterSmem &sm, uint32_t n)
 /* Rasterise the n staged (sorted) references.  The tile is cut into 16 regions of 16x16 pixels; a warp takes
  * the next unprocessed region from a shared counter and walks the whole window for it, so all fragments of a
  * pixel are produced by one warp in submission order while the regions balance the load between warps. */
-template <bool VIS>
+template <bool VIS, bool PLAIN>
 __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, int px0, int py0)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -797,8 +797,8 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 TriHead h;
                 if (VIS) h = broadcast_head(mine, k);
                 else load_head(h, b.records + r);
-                const uint32_t kind = VIS ? KIND_TRIANGLE : (h.state_flags & STATE_KIND_MASK) >> STATE_KIND_SHIFT;
-                if (kind == KIND_TRIANGLE) raster_triangle<VIS>(b, sm, r, h, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
+                const uint32_t kind = (VIS || PLAIN) ? KIND_TRIANGLE : (h.state_flags & STATE_KIND_MASK) >> STATE_KIND_SHIFT;
+                if (kind == KIND_TRIANGLE) raster_triangle<VIS, PLAIN>(b, sm, r, h, px0, py0, X0, Y0, X1, Y1, rx0, ry0, pending);
                 else {
                     if (pending) {      /* lines and points are drawn in order on top of whatever was deferred */
                         resolve_region(b, sm, rx0, ry0, px0, py0);
@@ -810,7 +810,7 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
                 __syncwarp();
             }
         }
-        if (!VIS && pending) resolve_region(b, sm, rx0, ry0, px0, py0);
+        if (!VIS && !PLAIN && pending) resolve_region(b, sm, rx0, ry0, px0, py0);
     }
 }
 
@@ -819,7 +819,10 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
  *              plane, no shading code: half the registers and less shared memory than the general kernel.
  * VIS = false: the general kernel (in-order shading, blending, alpha test).  With only_flagged it handles just
  *              the tiles that reference at least one non-deferrable record. */
-template <bool VIS>
+/* PLAIN (general kernel only): the pass has nothing but in-order filled triangles -- no deferrable record can reach a
+ * general tile, no lines, no points -- so the deferred-shading bookkeeping and the kind dispatch are compiled out
+ * (the fill-rate case C3: fewer live registers in the block loop). */
+template <bool VIS, bool PLAIN>
 __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t only_flagged)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
             }
             __syncthreads();
             sort_window(sm, L);
-            process_window<VIS>(b, sm, L, px0, py0);
+            process_window<VIS, PLAIN>(b, sm, L, px0, py0);
         } else {
             /* Long list: take the references in windows of increasing id.  The upper id bound of a
              * window is found by bisection on the id value, counting with the whole CTA. */
@@ -906,7 +909,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
                 const uint32_t n = sm.count;
                 __syncthreads();
                 sort_window(sm, n);
-                process_window<VIS>(b, sm, n, px0, py0);
+                process_window<VIS, PLAIN>(b, sm, n, px0, py0);
                 __syncthreads();
                 done += n;
                 lo = hi;
@@ -1039,8 +1042,9 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
     cudaGetDevice(&dev);
     const size_t smem_vis = offsetof(RasterSmem, color);
     if (dev >= 0 && dev < 64 && !configured[dev]) {      /* the opt-in is per device */
-        cudaFuncSetAttribute(k_raster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
-        cudaFuncSetAttribute(k_raster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vis);
+        cudaFuncSetAttribute(k_raster<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
+        cudaFuncSetAttribute(k_raster<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
+        cudaFuncSetAttribute(k_raster<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vis);
         configured[dev] = true;
     }
     uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
@@ -1053,7 +1057,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         /* tiles whose records are all order-independent (and the tiles that only need clearing) */
         launch_vis_unordered(b, fb, clear, planes, plan.unordered_func ? plan.unordered_func : 1u, plan.unordered_range01, s);
         if (plan.any_ordered_vis) {
-            k_raster<true><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
+            k_raster<true, false><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
             note_launch();
         }
         cudaEventRecord(ev_vis, s);
@@ -1063,13 +1067,14 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         }
         cudaEventRecord(ev_shade, s);
         if (any_in_order) {
-            k_raster<false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u);
+            k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u);
             note_launch();
         }
     } else {
         cudaEventRecord(ev_vis, s);
         cudaEventRecord(ev_shade, s);
-        k_raster<false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
+        if (plan.plain_in_order) k_raster<false, true><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
+        else k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
         note_launch();
     }
 }

@@ -41,6 +41,7 @@ void note_launch();
 
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start 4 banks apart, 16-byte aligned */
+constexpr int VIS_CHUNK = 32;           /* list entries a warp takes at a time (<= 32): smaller = better balance between the warps of a tile */
 constexpr int VIS_LARGE_CAP = 512;      /* capacity of the large-triangle queue (a full queue makes the finding warp do the triangle alone) */
 constexpr int VIS_EXACT_EXTENT = 2047;  /* vertex extent up to which all edge values inside a tile are exactly represented integers */
 constexpr int VIS_COORD_LIMIT = 1 << 22;
@@ -243,10 +244,10 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     const float px0f = (float)px0, py0f = (float)py0;
     for (;;) {
         uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(&sm.next_chunk, 32u);
+        if (lane == 0) c = atomicAdd(&sm.next_chunk, (uint32_t)VIS_CHUNK);
         c = __shfl_sync(0xFFFFFFFFu, c, 0);
         if (c >= L) break;
-        const uint32_t e = c + lane;
+        const uint32_t e = (lane < (uint32_t)VIS_CHUNK) ? c + lane : L;
         uint32_t area = 0;                      /* box pixels of this lane's triangle; 0 = no small triangle here */
         bool alone = false;                     /* a large triangle that did not fit the queue */
         VisHead h;

@@ -628,7 +628,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             CU(cudaEventRecord(sev[3], d->stream));
         }
         CU(cudaEventRecord(sev[4], d->stream));
-        bool any_defer = false, any_in_order = false, any_ordered_vis = false;
+        bool any_defer = false, any_in_order = false, any_ordered_vis = false, any_not_plain = false;
         for (const PassDraw &q : passes[pidx]) {
             const mtgl_draw &dq = bt->draws[q.draw];
             const mtgl_state &sq = bt->states[dq.raster_state];
@@ -637,11 +637,13 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if ((cf & RC_DEFER) && filled) any_defer = true; else any_in_order = true;
             if ((cf & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */
             if ((cf & RC_DEFER) && !(cf & RC_UNORDERED) && dq.mode >= G_TRIANGLES) any_ordered_vis = true;
+            if ((cf & RC_DEFER) || !filled) any_not_plain = true;
         }
         RasterPlan plan;
         plan.any_deferrable = any_defer && pi.n_triangles > 0;
         plan.any_ordered_vis = any_ordered_vis;
         plan.any_in_order = any_in_order;
+        plan.plain_in_order = any_in_order && !any_not_plain;
         plan.unordered_func = unordered_func;
         plan.unordered_range01 = unordered_range01;
         launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
