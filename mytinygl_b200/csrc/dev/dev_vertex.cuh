@@ -145,6 +145,80 @@ __device__ __forceinline__ void fetch_vertex(const mtgl_in_vertex *staged, const
     }
 }
 
+/* Fast attribute path.  For a non-indexed array draw whose enabled arrays are 4-byte aligned floats and whose whole
+ * element range lies inside the buffers (checked once, attrib_range_ok), element e of an attribute is base + e * stride:
+ * no per-vertex bounds / type / alignment logic.  The values are the same loads fetch_attrib would do. */
+struct FastDraw {
+    const uint8_t *pos, *nrm, *tex;     /* element 0 of each array (NULL: array disabled) */
+    uint32_t pos_stride, nrm_stride, tex_stride;
+    uint32_t pos_size;
+    int32_t first;
+    uint32_t tri_begin, tri_end;        /* global indices of the draw's triangles in this pass */
+    uint32_t tbase;
+    uint32_t draw;                      /* index into BatchDev::draws */
+    uint32_t valid;
+    float cur_color[4], cur_normal[3], cur_texcoord[2];
+    const mtgl_state *st;
+};
+
+__device__ __forceinline__ bool attrib_range_ok(const DevAttrib &a, int32_t first, uint32_t count)
+{
+    if (!a.ptr || a.type != MTGL_TYPE_F32 || (((uintptr_t)a.ptr) & 3u) || (a.stride & 3u) || first < 0 || count == 0) return false;
+    const uint64_t last = (uint64_t)((uint32_t)first + count - 1u) * a.stride + (uint64_t)a.size * 4u;
+    return last <= a.avail;
+}
+
+/* one thread fills the descriptor for draw d; valid = 0 when the draw does not qualify */
+__device__ __forceinline__ void fast_draw_init(FastDraw &f, const mtgl_state *states, const DevDraw &dr, uint32_t d, uint32_t tri_begin, uint32_t tri_end)
+{
+    f.valid = 0;
+    f.draw = d; f.tri_begin = tri_begin; f.tri_end = tri_end; f.tbase = dr.tbase;
+    if (dr.source != MTGL_SRC_ARRAYS || dr.index_type || dr.color.enabled || !dr.fused) return;
+    if (!attrib_range_ok(dr.position, dr.first, dr.count) || dr.position.size < 2) return;
+    if (dr.normal.enabled && (!attrib_range_ok(dr.normal, dr.first, dr.count) || dr.normal.size != 3)) return;
+    if (dr.texcoord.enabled && (!attrib_range_ok(dr.texcoord, dr.first, dr.count) || dr.texcoord.size < 2)) return;
+    f.pos = dr.position.ptr; f.pos_stride = dr.position.stride; f.pos_size = dr.position.size;
+    f.nrm = dr.normal.enabled ? dr.normal.ptr : nullptr; f.nrm_stride = dr.normal.stride;
+    f.tex = dr.texcoord.enabled ? dr.texcoord.ptr : nullptr; f.tex_stride = dr.texcoord.stride;
+    f.first = dr.first;
+#pragma unroll
+    for (int k = 0; k < 4; k++) f.cur_color[k] = dr.cur_color[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) f.cur_normal[k] = dr.cur_normal[k];
+    f.cur_texcoord[0] = dr.cur_texcoord[0]; f.cur_texcoord[1] = dr.cur_texcoord[1];
+    f.st = states + dr.vertex_state;
+    f.valid = 1;
+}
+
+__device__ __forceinline__ void fast_position(const FastDraw &f, uint32_t i, float &px, float &py, float &pz)
+{
+    const float *p = reinterpret_cast<const float *>(f.pos + (uint64_t)((uint32_t)f.first + i) * f.pos_stride);
+    px = __ldg(p); py = __ldg(p + 1);
+    pz = (f.pos_size >= 3) ? __ldg(p + 2) : 0.0f;
+}
+
+__device__ __forceinline__ void fast_texcoord(const FastDraw &f, uint32_t i, float &s, float &t)
+{
+    s = f.cur_texcoord[0]; t = f.cur_texcoord[1];
+    if (f.tex) {
+        const float *p = reinterpret_cast<const float *>(f.tex + (uint64_t)((uint32_t)f.first + i) * f.tex_stride);
+        s = __ldg(p); t = __ldg(p + 1);
+    }
+}
+
+__device__ __forceinline__ void fast_vertex(const FastDraw &f, uint32_t i, VertexIn &v)
+{
+    fast_position(f, i, v.px, v.py, v.pz);
+    fast_texcoord(f, i, v.s, v.t);
+    v.nx = f.cur_normal[0]; v.ny = f.cur_normal[1]; v.nz = f.cur_normal[2];
+    if (f.nrm) {
+        const float *p = reinterpret_cast<const float *>(f.nrm + (uint64_t)((uint32_t)f.first + i) * f.nrm_stride);
+        v.nx = __ldg(p); v.ny = __ldg(p + 1); v.nz = __ldg(p + 2);
+    }
+    v.cur = { f.cur_color[0], f.cur_color[1], f.cur_color[2], f.cur_color[3] };
+    v.st = f.st;
+}
+
 /* eye = MV * (x, y, z, 1)   (graphics.h:131-138: ((m0*x + m4*y) + m8*z) + m12*w), clip = P * eye (raster.c:48-56) */
 __device__ __forceinline__ void to_eye(const mtgl_state *st, float px, float py, float pz, float &ex, float &ey, float &ez, float &ew)
 {

@@ -640,7 +640,8 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
  * the attribute arrays.  The colour rows (and the eye-space side record) are filled afterwards by the whole CTA, one
  * thread per vertex of the survivors (k_setup, phase B). */
 __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index,
-                                                  const ScreenTri &s, const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw &dr, uint32_t l0)
+                                                  const ScreenTri &s, const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw &dr, uint32_t l0,
+                                                  const FastDraw *fast)
 {
     float4 *out = reinterpret_cast<float4 *>(dst);
     const uint32_t cflags = cfg->flags;
@@ -654,12 +655,14 @@ __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, u
     for (int j = 0; j < 3; j++) {
         float x, y, zz, ex, ey, ez, ew, ts, tt;
         const mtgl_state *vs;
-        fetch_position(staged, states, dr, l0 + j, x, y, zz, vs);
+        if (fast) { fast_position(*fast, l0 + j, x, y, zz); vs = fast->st; }
+        else fetch_position(staged, states, dr, l0 + j, x, y, zz, vs);
         to_eye(vs, x, y, zz, ex, ey, ez, ew);
         const float4 c = to_clip(vs, ex, ey, ez, ew);
         if (fabsf(c.w) < 1e-6f) { z[j] = 0.0f; w[j] = 1.0f; } else { w[j] = 1.0f / c.w; z[j] = c.z * w[j]; }   /* raster.c:729-746 */
         nez[j] = -ez;
-        fetch_texcoord(staged, dr, l0 + j, ts, tt);
+        if (fast) fast_texcoord(*fast, l0 + j, ts, tt);
+        else fetch_texcoord(staged, dr, l0 + j, ts, tt);
         tex_transform(vs, ts, tt, tu[j], tv[j]);
     }
     float lod = 0.0f;       /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
@@ -740,7 +743,22 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     __shared__ uint32_t chunk_slot0;
     __shared__ uint32_t fused_n;                            /* survivors of this chunk whose colour rows phase B fills */
     __shared__ uint2 fused_list[SETUP_THREADS];             /* (record index, input triangle) */
-    if (threadIdx.x == 0) fused_n = 0;
+    constexpr uint32_t VCACHE_SLOTS = 2048;
+    __shared__ uint32_t vcache[VCACHE_SLOTS];               /* phase B: hash slot -> first vertex reference that claimed it */
+    __shared__ uint16_t vsame[3 * SETUP_THREADS];           /* vertex reference -> the reference it duplicates (itself if none) */
+    __shared__ uint16_t shade_list[3 * SETUP_THREADS];      /* references to shade */
+    __shared__ uint32_t shade_n;
+    __shared__ FastDraw fastd;                               /* fast attribute path of the draw this chunk starts in */
+    if (threadIdx.x == 0) {
+        fused_n = 0;
+        const uint32_t t0 = blockIdx.x * SETUP_THREADS;
+        fastd.valid = 0;
+        if (t0 < b.n_triangles) {
+            const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
+            fast_draw_init(fastd, b.states, b.draws[d0], d0, b.draw_tbase[d0], b.draw_tbase[d0 + 1]);
+        }
+    }
+    __syncthreads();
 
     const uint32_t chunk = blockIdx.x;
     const uint32_t t = chunk * SETUP_THREADS + threadIdx.x;
@@ -783,9 +801,16 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
                 const uint32_t l0 = i0 - dr.vbase;
                 float x, y, z, ex, ey, ez, ew;
                 const mtgl_state *vs;
-                fetch_position(b.staged, b.states, dr, l0, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
-                fetch_position(b.staged, b.states, dr, l0 + 1, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
-                fetch_position(b.staged, b.states, dr, l0 + 2, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+                if (fastd.valid && t >= fastd.tri_begin && t < fastd.tri_end) {
+                    vs = fastd.st;
+                    fast_position(fastd, l0, x, y, z); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
+                    fast_position(fastd, l0 + 1, x, y, z); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
+                    fast_position(fastd, l0 + 2, x, y, z); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+                } else {
+                    fetch_position(b.staged, b.states, dr, l0, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
+                    fetch_position(b.staged, b.states, dr, l0 + 1, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
+                    fetch_position(b.staged, b.states, dr, l0 + 2, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+                }
             } else { p0 = src.clip[i0]; p1 = src.clip[i1]; p2 = src.clip[i2]; }
             if (inside_all(p0) && inside_all(p1) && inside_all(p2)) {
                 /* Sutherland-Hodgman returns its input unchanged when every vertex passes every plane */
@@ -838,7 +863,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
         if (shape == 1) {
             if (src.fused) {
-                row = write_fused_head(dst, id0, cfg, state_index, s, b.staged, b.states, *src.draw, i0 - src.draw->vbase);
+                const bool use_fast = fastd.valid && t >= fastd.tri_begin && t < fastd.tri_end;
+                row = write_fused_head(dst, id0, cfg, state_index, s, b.staged, b.states, *src.draw, i0 - src.draw->vbase, use_fast ? &fastd : nullptr);
                 fused_list[atomicAdd(&fused_n, 1u)] = make_uint2(r, t);
             } else row = write_fill_stream(dst, eye_dst, id0, cfg, state_index, s, src, i0, i1, i2);
             b.bin_rows[r] = row;
@@ -865,24 +891,83 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         if (tflags) atomicOr(&b.tile_flags[tile], tflags);
     } else if (ntiles > 1) count_tiles_single(bin, r, row.x, row.y, row.z);
 
-    /* ---- phase B of the fused path: the vertex stage for the survivors only, one thread per vertex: attribute fetch,
-     * eye-space transform, lighting (dev_vertex.cuh) -> colour row 5 + j of the record (and the eye-space side record) ---- */
+    /* ---- phase B of the fused path: the vertex stage for the survivors only -- attribute fetch, eye-space transform,
+     * lighting (dev_vertex.cuh) -> colour row 5 + j of the record (and the eye-space side record).
+     *
+     * Independent triangles of a mesh repeat their vertices (C4: 4.3 references per distinct vertex inside a chunk of
+     * 256 triangles).  The vertex stage is a pure function of (attributes, state block), so it runs once per DISTINCT
+     * input of the chunk -- a post-transform vertex cache: B1 every vertex reference hashes its raw attributes and
+     * claims a table slot; a loser compares bit for bit with the slot's owner and, if equal, becomes its duplicate;
+     * B2 the owners (and hash collisions) are shaded, one thread each; B3 duplicates copy the owner's rows. ---- */
     __syncthreads();
     const uint32_t nv = fused_n * 3u;
-    for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {
+    if (nv == 0) return;                                    /* uniform: fused_n is shared */
+    for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) vcache[i] = 0xFFFFFFFFu;
+    if (threadIdx.x == 0) shade_n = 0;
+    __syncthreads();
+    auto vertex_in = [&](uint32_t v, VertexIn &in) {
         const uint2 e = fused_list[v / 3u];
-        const uint32_t j = v % 3u;
+        if (fastd.valid && e.y >= fastd.tri_begin && e.y < fastd.tri_end) {
+            fast_vertex(fastd, 3u * (e.y - fastd.tbase) + v % 3u, in);
+            return;
+        }
         const uint32_t dd = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, e.y);
         const DevDraw &dr = b.draws[dd];
+        fetch_vertex(b.staged, b.states, dr, 3u * (e.y - dr.tbase) + v % 3u, in);
+    };
+    for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {            /* B1 */
         VertexIn in;
-        fetch_vertex(b.staged, b.states, dr, 3u * (e.y - dr.tbase) + j, in);
+        vertex_in(v, in);
+        const uint32_t w[13] = { __float_as_uint(in.px), __float_as_uint(in.py), __float_as_uint(in.pz), __float_as_uint(in.nx),
+                                 __float_as_uint(in.ny), __float_as_uint(in.nz), __float_as_uint(in.s), __float_as_uint(in.t),
+                                 __float_as_uint(in.cur.r), __float_as_uint(in.cur.g), __float_as_uint(in.cur.b), __float_as_uint(in.cur.a),
+                                 (uint32_t)(in.st - b.states) };
+        uint32_t hsh = 0x811C9DC5u;
+#pragma unroll
+        for (int k = 0; k < 13; k++) hsh = (hsh ^ w[k]) * 0x9E3779B1u;
+        hsh ^= hsh >> 15;
+        const uint32_t owner = atomicCAS(&vcache[hsh & (VCACHE_SLOTS - 1)], 0xFFFFFFFFu, v);
+        uint32_t same_as = v;
+        if (owner != 0xFFFFFFFFu) {
+            VertexIn o;
+            vertex_in(owner, o);
+            const bool equal = __float_as_uint(o.px) == w[0] && __float_as_uint(o.py) == w[1] && __float_as_uint(o.pz) == w[2] &&
+                               __float_as_uint(o.nx) == w[3] && __float_as_uint(o.ny) == w[4] && __float_as_uint(o.nz) == w[5] &&
+                               __float_as_uint(o.s) == w[6] && __float_as_uint(o.t) == w[7] && __float_as_uint(o.cur.r) == w[8] &&
+                               __float_as_uint(o.cur.g) == w[9] && __float_as_uint(o.cur.b) == w[10] && __float_as_uint(o.cur.a) == w[11] &&
+                               (uint32_t)(o.st - b.states) == w[12];
+            if (equal) same_as = owner;
+        }
+        vsame[v] = (uint16_t)same_as;
+        if (same_as == v) shade_list[atomicAdd(&shade_n, 1u)] = (uint16_t)v;
+    }
+    __syncthreads();
+    const uint32_t ns = shade_n;
+    for (uint32_t i = threadIdx.x; i < ns; i += SETUP_THREADS) {            /* B2 */
+        const uint32_t v = shade_list[i];
+        VertexIn in;
+        vertex_in(v, in);
         VertexOut o;
         shade_vertex(in, o);
-        reinterpret_cast<float4 *>(b.records + e.x)[5 + j] = o.color;
+        const uint32_t rr = fused_list[v / 3u].x, j = v % 3u;
+        reinterpret_cast<float4 *>(b.records + rr)[5 + j] = o.color;
         if (b.need_eye) {
-            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + e.x);
+            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + rr);
             eo[j] = o.epos;
             eo[3 + j] = o.enrm;
+        }
+    }
+    __syncthreads();                                        /* the owners' rows are visible to the whole CTA */
+    for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {            /* B3 */
+        const uint32_t o = vsame[v];
+        if (o == v) continue;
+        const uint32_t rr = fused_list[v / 3u].x, j = v % 3u, ro = fused_list[o / 3u].x, jo = o % 3u;
+        reinterpret_cast<float4 *>(b.records + rr)[5 + j] = __ldcg(reinterpret_cast<const float4 *>(b.records + ro) + 5 + jo);
+        if (b.need_eye) {
+            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + rr);
+            const float4 *es = reinterpret_cast<const float4 *>(b.rec_eye + ro);
+            eo[j] = __ldcg(es + jo);
+            eo[3 + j] = __ldcg(es + 3 + jo);
         }
     }
 }
