@@ -178,10 +178,12 @@ __device__ __forceinline__ Color4 color_clamp(Color4 c) { return { sat01(c.r), s
 /* color_to_rgba32 (graphics.h:337-348): clamp, truncate, pack */
 __device__ __forceinline__ uint32_t color_pack(Color4 c)
 {
-    uint32_t r = __float2uint_rz(sat01(c.r) * 255.0f) & 0xFFu;
-    uint32_t g = __float2uint_rz(sat01(c.g) * 255.0f) & 0xFFu;
-    uint32_t b = __float2uint_rz(sat01(c.b) * 255.0f) & 0xFFu;
-    uint32_t a = __float2uint_rz(sat01(c.a) * 255.0f) & 0xFFu;
+    /* __saturatef maps NaN to 0 where the reference's ternaries keep it, but NaN * 255 packs to 0 too (cvttss2si: low
+     * byte of 0x80000000), so the bytes are identical for every input */
+    uint32_t r = __float2uint_rz(__saturatef(c.r) * 255.0f);
+    uint32_t g = __float2uint_rz(__saturatef(c.g) * 255.0f);
+    uint32_t b = __float2uint_rz(__saturatef(c.b) * 255.0f);
+    uint32_t a = __float2uint_rz(__saturatef(c.a) * 255.0f);
     return (a << 24) | (b << 16) | (g << 8) | r;
 }
 
@@ -394,6 +396,7 @@ struct BatchDev {
     uint32_t *tile_count, *tile_offset, *tile_cursor;
     uint32_t *tile_flags;           /* bit 0: the tile references a record whose colour work cannot be deferred (general kernel);
                                      * bit 1: it references a record outside the unordered class (sorted visibility kernel) */
+    uint32_t *tile_order;           /* launch order of the tile kernels: blockIdx -> tile, heaviest lists first (k_bin_scan); NULL = identity */
     uint32_t *tile_list; uint32_t list_capacity;
     uint32_t guard;                 /* 1: the list buffer was sized by guess -- fill and raster kernels must check lists_fit() */
     uint32_t *vis_plane;            /* visibility buffer in HBM (record index per pixel) between K4a and K4b */

@@ -29,6 +29,7 @@ struct TexTaps {
 __device__ __forceinline__ int wrap_coord(int x, int n, bool repeat)
 {   /* get_texel_wrapped / get_mip1_texel_wrapped, textures.c:272-291, 357-376 */
     if (repeat) {
+        if ((n & (n - 1)) == 0) return x & (n - 1);                 /* power-of-two size: the euclidean modulo is a mask */
         if ((unsigned)(x + n) < (unsigned)(3 * n)) {            /* x in [-n, 2n): one conditional add == the euclidean modulo */
             if (x < 0) x += n; else if (x >= n) x -= n;
         } else x = ((x % n) + n) % n;
@@ -93,7 +94,10 @@ __device__ __forceinline__ void tex_taps(TexTaps &T, const RasterCfg *c, float u
     level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter == G_LINEAR);
 }
 
-__device__ __forceinline__ uint32_t pack1(float x) { return __float2uint_rz(sat01(x) * 255.0f) & 0xFFu; }   /* one channel of color_to_rgba32 */
+/* one channel of color_to_rgba32 (graphics.h:337-348).  __saturatef differs from the reference's two ternaries only for
+ * NaN (0 instead of NaN), and NaN * 255 converts to 0 as well (x86 cvttss2si yields 0x80000000, low byte 0), so the
+ * packed byte is the same for every input -- in one instruction instead of four. */
+__device__ __forceinline__ uint32_t pack1(float x) { return __float2uint_rz(__saturatef(x) * 255.0f); }
 
 __device__ __forceinline__ uint32_t level_channel(const LevelTaps &L, int sh, const float *un)
 {   /* bilinear_filter, textures.c:294-307: lerp horizontally, then vertically, truncate to 8 bits */

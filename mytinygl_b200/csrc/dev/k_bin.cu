@@ -180,6 +180,73 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
         __syncthreads();
     }
     if (threadIdx.x == 0) b.counters->tile_refs = carry;
+
+    /* Launch order of the tile kernels: tiles by decreasing reference count (longest-processing-time-first), a
+     * STABLE counting sort over 64 linear buckets -- equal loads keep their row-major order, so a uniform frame
+     * launches exactly as before.  The hardware hands CTAs to SMs in blockIdx order, so the heavy tiles start first
+     * and the light ones fill the tail; with plain row-major order the SMs' busy time differed by 14 % on C4.
+     * Every warp owns a contiguous range of tiles; counts per (bucket, warp), scanned bucket-major, give each warp
+     * its first slot in every bucket. */
+    if (!b.tile_order) return;
+    __shared__ uint32_t hist[64 * 32];
+    __shared__ uint32_t maxc;
+    for (uint32_t i = threadIdx.x; i < 64 * 32; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) maxc = 0;
+    __syncthreads();
+    uint32_t m = 0;
+    for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) m = max(m, b.tile_count[i]);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if (lane == 0 && m) atomicMax(&maxc, m);
+    __syncthreads();
+    const unsigned long long span = (unsigned long long)maxc + 1ull;
+    const uint32_t per_warp = ((ntiles + 1023u) >> 10) << 5;           /* tiles per warp, a multiple of 32 */
+    const uint32_t w_begin = min(warp * per_warp, ntiles), w_end = min(w_begin + per_warp, ntiles);
+    for (uint32_t i0 = w_begin; i0 < w_end; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        if (i < w_end) atomicAdd(&hist[(63u - (uint32_t)(((unsigned long long)b.tile_count[i] * 64ull) / span)) * 32u + warp], 1u);
+    }
+    __syncthreads();
+    {   /* exclusive scan of the 2048 counters, two per thread */
+        const uint32_t a0 = hist[2 * threadIdx.x], a1 = hist[2 * threadIdx.x + 1];
+        uint32_t incl = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += n;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= (uint32_t)o) wi += n;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t excl = warp_sums[warp] + incl - a0 - a1;
+        hist[2 * threadIdx.x] = excl;
+        hist[2 * threadIdx.x + 1] = excl + a0;
+    }
+    __syncthreads();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (uint32_t i0 = w_begin; i0 < w_end; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool on = i < w_end;
+        const uint32_t act = __ballot_sync(0xFFFFFFFFu, on);
+        if (on) {
+            const uint32_t bucket = 63u - (uint32_t)(((unsigned long long)b.tile_count[i] * 64ull) / span);
+            const uint32_t peers = __match_any_sync(act, bucket);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) { base = hist[bucket * 32u + warp]; hist[bucket * 32u + warp] = base + (uint32_t)__popc(peers); }
+            base = __shfl_sync(peers, base, leader);
+            b.tile_order[base + (uint32_t)__popc(peers & lt_mask)] = i;
+        }
+        __syncwarp();
+    }
 }
 
 static int bin_grid() { return 148 * 8; }

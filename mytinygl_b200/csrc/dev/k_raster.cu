@@ -259,7 +259,7 @@ __device__ __noinline__ void resolve_region(const BatchDev &b, RasterSmem &sm, i
             load_attr(A, rec);
             Color4 c;
             shade_color(b, sm.unorm8, r, state_flags, A, cfg, b0, b1, b2, c);
-            sm.color[ci] = color_pack(color_clamp(c));      /* raster.c:719-721 */
+            sm.color[ci] = color_pack(c);      /* raster.c:719-721: color_pack clamps */
         }
     }
     __syncwarp();
@@ -282,7 +282,7 @@ __device__ __noinline__ void shade_now(const BatchDev &b, RasterSmem &sm, uint32
         Color4 sf = blend_factor(cfg->blend_src, c, d), df = blend_factor(cfg->blend_dst, c, d);
         c = color_clamp({ c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a });
     }
-    c = color_clamp(c);
+    /* (the clamp of raster.c:719 is part of color_pack) */
     if (cm == 0xFu) sm.color[ci] = color_pack(c);       /* write_pixel_masked, raster.c:20-45 */
     else if (cm != 0u) {
         Color4 d = color_unpack(sm.color[ci], un);
@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
     RasterSmem &sm = *reinterpret_cast<RasterSmem *>(smem_raw);
     if (!lists_fit(b)) return;
 
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
     const int px0 = tx << TILE_LOG, py0t = ty << TILE_LOG;
     /* rows of this tile owned by the band, columns inside the framebuffer */
@@ -928,11 +928,12 @@ __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, C
 {
     __shared__ float un[256];
     __shared__ uint16_t list[TILE_W * TILE_H];
+    __shared__ uint32_t rlist[TILE_W * TILE_H];             /* record index of the compacted pixel: pass 2 does not re-read the plane */
     __shared__ uint32_t warp_total[8];
     if (!lists_fit(b)) return;
     un[threadIdx.x] = b.unorm8[threadIdx.x];
 
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
     const int px0 = tx << TILE_LOG, py0 = max(ty << TILE_LOG, fb.band_y0);
     const int vw = min(TILE_W, fb.width - px0), vh = min((ty << TILE_LOG) + TILE_H, fb.band_y1) - py0;
@@ -947,8 +948,8 @@ __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, C
      * row-major pixel order: the compacted list keeps neighbouring pixels next to each other for pass 2. */
     const int y = (int)(threadIdx.x >> 2), xq = (int)(threadIdx.x & 3) * 16;
     uint32_t has_mask = 0;
+    uint32_t v[16];
     if (y < vh) {
-        uint32_t v[16];
         const size_t p0 = (size_t)(py0 + y) * fb.width + px0 + xq;
         if (!L) {
 #pragma unroll
@@ -986,7 +987,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, C
         if (w < warp) at += wt;
         n += wt;
     }
-    for (uint32_t m = has_mask; m; m &= m - 1) list[at++] = (uint16_t)(y * TILE_W + xq + __ffs(m) - 1);
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        if (has_mask & (1u << k)) { list[at] = (uint16_t)(y * TILE_W + xq + k); rlist[at] = v[k]; at++; }
     __syncthreads();
 
     /* pass 2: shade the compacted pixels */
@@ -994,7 +997,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, C
         const int lx = list[i] % TILE_W, ly = list[i] / TILE_W;
         const int x = px0 + lx, y = py0 + ly;
         const size_t p = (size_t)y * fb.width + x;
-        const uint32_t r = b.vis_plane[p];
+        const uint32_t r = rlist[i];
         const TriRecord *rec = b.records + r;
         const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
         const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
@@ -1011,7 +1014,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, C
         load_attr(A, rec);
         Color4 c;
         shade_color(b, un, r, state_flags, A, cfg, b0, b1, b2, c);
-        fb.color[p] = color_pack(color_clamp(c));       /* raster.c:719-721 */
+        fb.color[p] = color_pack(c);       /* raster.c:719-721: color_pack clamps */
     }
 
     /* Fused gather: the finished tile also goes to the presenting GPU's plane over NVLink, as whole rows in 16-byte

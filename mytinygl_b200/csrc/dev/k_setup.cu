@@ -640,8 +640,8 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
  * the attribute arrays.  The colour rows (and the eye-space side record) are filled afterwards by the whole CTA, one
  * thread per vertex of the survivors (k_setup, phase B). */
 __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index,
-                                                  const ScreenTri &s, const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw &dr, uint32_t l0,
-                                                  const FastDraw *fast)
+                                                  const ScreenTri &s, const mtgl_state *vs, const float (&px)[3], const float (&py)[3],
+                                                  const float (&pz)[3], const float (&ts)[3], const float (&tt)[3])
 {
     float4 *out = reinterpret_cast<float4 *>(dst);
     const uint32_t cflags = cfg->flags;
@@ -653,17 +653,12 @@ __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, u
     float z[3], w[3], nez[3], tu[3], tv[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        float x, y, zz, ex, ey, ez, ew, ts, tt;
-        const mtgl_state *vs;
-        if (fast) { fast_position(*fast, l0 + j, x, y, zz); vs = fast->st; }
-        else fetch_position(staged, states, dr, l0 + j, x, y, zz, vs);
-        to_eye(vs, x, y, zz, ex, ey, ez, ew);
+        float ex, ey, ez, ew;
+        to_eye(vs, px[j], py[j], pz[j], ex, ey, ez, ew);
         const float4 c = to_clip(vs, ex, ey, ez, ew);
         if (fabsf(c.w) < 1e-6f) { z[j] = 0.0f; w[j] = 1.0f; } else { w[j] = 1.0f / c.w; z[j] = c.z * w[j]; }   /* raster.c:729-746 */
         nez[j] = -ez;
-        if (fast) fast_texcoord(*fast, l0 + j, ts, tt);
-        else fetch_texcoord(staged, dr, l0 + j, ts, tt);
-        tex_transform(vs, ts, tt, tu[j], tv[j]);
+        tex_transform(vs, ts[j], tt[j], tu[j], tv[j]);
     }
     float lod = 0.0f;       /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
     if (cflags & RC_TEXTURED) {
@@ -736,33 +731,67 @@ __device__ __forceinline__ void persp_divide_xy(const float4 &v, float &x, float
  * from the three clip-space positions alone (48 B); colours, texture coordinates and eye-space attributes are only
  * fetched for survivors, after the scan, so culled triangles cost a third of the traffic and nothing but the
  * screen-space result (10 registers) lives across the barrier.
+ *
+ * Fused draws on the fast attribute path (FastDraw) stage the chunk's 768 raw vertices (position, normal, texture
+ * coordinate) in shared memory once, structure-of-arrays, with every load of the chunk in flight at the same time;
+ * the decision, the record heads, the vertex-cache hashing and the vertex stage all read them from there, so each
+ * CTA pays one global-memory round trip for its attributes instead of one per phase.
  */
+constexpr uint32_t SETUP_VERTS = 3 * SETUP_THREADS;
+constexpr uint32_t VCACHE_SLOTS = 2048;
+
+struct SetupSmem {
+    /* raw attributes of local vertex lv = 3 * (triangle - first triangle of the chunk) + corner; after phase B2 the first
+     * four arrays of an OWNER vertex hold its shaded colour (r, g, b, a) instead */
+    float a_px[SETUP_VERTS], a_py[SETUP_VERTS], a_pz[SETUP_VERTS], a_nx[SETUP_VERTS];
+    float a_ny[SETUP_VERTS], a_nz[SETUP_VERTS], a_s[SETUP_VERTS], a_t[SETUP_VERTS];
+    uint32_t vcache[VCACHE_SLOTS];              /* phase B: hash slot -> first vertex reference that claimed it */
+    uint2 fused_list[SETUP_THREADS];            /* (record index, input triangle) of the chunk's fused survivors */
+    uint16_t vsame[SETUP_VERTS];                /* vertex reference -> the reference it duplicates (itself if none) */
+    uint16_t shade_list[SETUP_VERTS];           /* references to shade */
+    uint32_t warp_sums[SETUP_THREADS / 32];
+    uint32_t chunk_slot0;
+    uint32_t fused_n;                           /* survivors of this chunk whose colour rows phase B fills */
+    uint32_t shade_n;
+    FastDraw fastd;                             /* fast attribute path of the draw this chunk starts in */
+};
+static_assert(sizeof(SetupSmem) <= 48 * 1024, "k_setup uses static shared memory");
+
 __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTargets fb)
 {
-    __shared__ uint32_t warp_sums[SETUP_THREADS / 32];
-    __shared__ uint32_t chunk_slot0;
-    __shared__ uint32_t fused_n;                            /* survivors of this chunk whose colour rows phase B fills */
-    __shared__ uint2 fused_list[SETUP_THREADS];             /* (record index, input triangle) */
-    constexpr uint32_t VCACHE_SLOTS = 2048;
-    __shared__ uint32_t vcache[VCACHE_SLOTS];               /* phase B: hash slot -> first vertex reference that claimed it */
-    __shared__ uint16_t vsame[3 * SETUP_THREADS];           /* vertex reference -> the reference it duplicates (itself if none) */
-    __shared__ uint16_t shade_list[3 * SETUP_THREADS];      /* references to shade */
-    __shared__ uint32_t shade_n;
-    __shared__ FastDraw fastd;                               /* fast attribute path of the draw this chunk starts in */
+    __shared__ SetupSmem sm;
+    FastDraw &fastd = sm.fastd;
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t t0 = chunk * SETUP_THREADS;
     if (threadIdx.x == 0) {
-        fused_n = 0;
-        const uint32_t t0 = blockIdx.x * SETUP_THREADS;
+        sm.fused_n = 0;
+        sm.shade_n = 0;
         fastd.valid = 0;
         if (t0 < b.n_triangles) {
             const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
             fast_draw_init(fastd, b.states, b.draws[d0], d0, b.draw_tbase[d0], b.draw_tbase[d0 + 1]);
         }
     }
+    for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) sm.vcache[i] = 0xFFFFFFFFu;
     __syncthreads();
 
-    const uint32_t chunk = blockIdx.x;
-    const uint32_t t = chunk * SETUP_THREADS + threadIdx.x;
+    /* ---- phase A0: stage the raw attributes of the chunk's fast-path triangles ---- */
+    const bool any_fast = fastd.valid != 0u;
+    if (any_fast) {
+        const uint32_t tb = max(fastd.tri_begin, t0), te = min(min(fastd.tri_end, t0 + SETUP_THREADS), b.n_triangles);
+        for (uint32_t lv = threadIdx.x + 3u * (tb - t0); lv < 3u * (te - t0); lv += SETUP_THREADS) {
+            VertexIn in;
+            fast_vertex(fastd, 3u * (t0 - fastd.tbase) + lv, in);
+            sm.a_px[lv] = in.px; sm.a_py[lv] = in.py; sm.a_pz[lv] = in.pz;
+            sm.a_nx[lv] = in.nx; sm.a_ny[lv] = in.ny; sm.a_nz[lv] = in.nz;
+            sm.a_s[lv] = in.s; sm.a_t[lv] = in.t;
+        }
+        __syncthreads();
+    }
+
+    const uint32_t t = t0 + threadIdx.x;
     const bool valid = t < b.n_triangles;
+    const bool fast_t = any_fast && t >= fastd.tri_begin && t < fastd.tri_end;     /* this thread's triangle is staged */
 
     int shape = 0;          /* 0 nothing, 1 unclipped filled triangle, 2 clipped polygon, 3 line segment, 4 point, 5 unclipped outline */
     const mtgl_state *st = nullptr;
@@ -775,7 +804,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     const BinOut bin = { b.records, b.bin_rows, b.tile_count, b.tile_flags, b.large_list, b.counters, fb.tiles_x, fb.tile_y0 };
 
     if (valid) {
-        uint32_t d = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t);
+        uint32_t d = (b.n_draws == 1) ? 0u : (fast_t ? fastd.draw : find_draw_tri(b.draw_tbase, b.n_draws, t));
         const DevDraw &dr = b.draws[d];
         const uint32_t k = t - dr.tbase, n = dr.count;
         state_index = dr.raster_state;
@@ -801,11 +830,12 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
                 const uint32_t l0 = i0 - dr.vbase;
                 float x, y, z, ex, ey, ez, ew;
                 const mtgl_state *vs;
-                if (fastd.valid && t >= fastd.tri_begin && t < fastd.tri_end) {
+                if (fast_t) {
                     vs = fastd.st;
-                    fast_position(fastd, l0, x, y, z); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
-                    fast_position(fastd, l0 + 1, x, y, z); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
-                    fast_position(fastd, l0 + 2, x, y, z); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+                    const uint32_t lv = 3u * threadIdx.x;
+                    to_eye(vs, sm.a_px[lv], sm.a_py[lv], sm.a_pz[lv], ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
+                    to_eye(vs, sm.a_px[lv + 1], sm.a_py[lv + 1], sm.a_pz[lv + 1], ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
+                    to_eye(vs, sm.a_px[lv + 2], sm.a_py[lv + 2], sm.a_pz[lv + 2], ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
                 } else {
                     fetch_position(b.staged, b.states, dr, l0, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
                     fetch_position(b.staged, b.states, dr, l0 + 1, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
@@ -831,22 +861,22 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= (uint32_t)o) incl += n;
     }
-    if (lane == 31) warp_sums[warp] = incl;
+    if (lane == 31) sm.warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = (lane < SETUP_THREADS / 32) ? warp_sums[lane] : 0u;
+        uint32_t w = (lane < SETUP_THREADS / 32) ? sm.warp_sums[lane] : 0u;
         uint32_t wi = w;
 #pragma unroll
         for (int o = 1; o < SETUP_THREADS / 32; o <<= 1) {
             uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
             if (lane >= (uint32_t)o) wi += n;
         }
-        if (lane < SETUP_THREADS / 32) warp_sums[lane] = wi - w;
+        if (lane < SETUP_THREADS / 32) sm.warp_sums[lane] = wi - w;
         if (lane == SETUP_THREADS / 32 - 1) {
             uint32_t total = wi;
             uint32_t base = total ? atomicAdd(&b.counters->records, total) : 0u;
             if (base + total > b.record_capacity) { atomicExch(&b.counters->overflow, 1u); base = 0xFFFFFFFFu; }
-            chunk_slot0 = base;
+            sm.chunk_slot0 = base;
             b.chunk_base[chunk] = base;
         }
     }
@@ -855,17 +885,33 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     bool counted = false;
     uint32_t r = 0;
     uint4 row = make_uint4(0u, 0u, 0u, 0u);
-    if (count != 0 && chunk_slot0 != 0xFFFFFFFFu) {
-        const uint32_t slot = warp_sums[warp] + incl - count;       /* index inside the chunk */
-        r = chunk_slot0 + slot;
+    if (count != 0 && sm.chunk_slot0 != 0xFFFFFFFFu) {
+        const uint32_t slot = sm.warp_sums[warp] + incl - count;       /* index inside the chunk */
+        r = sm.chunk_slot0 + slot;
         TriRecord *const dst = b.records + r;
         TriEye *const eye_dst = b.need_eye ? b.rec_eye + r : nullptr;
         const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
         if (shape == 1) {
             if (src.fused) {
-                const bool use_fast = fastd.valid && t >= fastd.tri_begin && t < fastd.tri_end;
-                row = write_fused_head(dst, id0, cfg, state_index, s, b.staged, b.states, *src.draw, i0 - src.draw->vbase, use_fast ? &fastd : nullptr);
-                fused_list[atomicAdd(&fused_n, 1u)] = make_uint2(r, t);
+                float px[3], py[3], pz[3], ts[3], tt[3];
+                const mtgl_state *vs;
+                if (fast_t) {
+                    vs = fastd.st;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const uint32_t lv = 3u * threadIdx.x + j;
+                        px[j] = sm.a_px[lv]; py[j] = sm.a_py[lv]; pz[j] = sm.a_pz[lv]; ts[j] = sm.a_s[lv]; tt[j] = sm.a_t[lv];
+                    }
+                } else {
+                    const uint32_t l0 = i0 - src.draw->vbase;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        fetch_position(b.staged, b.states, *src.draw, l0 + j, px[j], py[j], pz[j], vs);
+                        fetch_texcoord(b.staged, *src.draw, l0 + j, ts[j], tt[j]);
+                    }
+                }
+                row = write_fused_head(dst, id0, cfg, state_index, s, vs, px, py, pz, ts, tt);
+                sm.fused_list[atomicAdd(&sm.fused_n, 1u)] = make_uint2(r, t);
             } else row = write_fill_stream(dst, eye_dst, id0, cfg, state_index, s, src, i0, i1, i2);
             b.bin_rows[r] = row;
             counted = true;
@@ -898,17 +944,21 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
      * 256 triangles).  The vertex stage is a pure function of (attributes, state block), so it runs once per DISTINCT
      * input of the chunk -- a post-transform vertex cache: B1 every vertex reference hashes its raw attributes and
      * claims a table slot; a loser compares bit for bit with the slot's owner and, if equal, becomes its duplicate;
-     * B2 the owners (and hash collisions) are shaded, one thread each; B3 duplicates copy the owner's rows. ---- */
+     * B2 the owners (and hash collisions) are shaded, one thread each, and leave their colour in shared memory;
+     * B3 every reference stores its owner's colour into its record row. ---- */
     __syncthreads();
-    const uint32_t nv = fused_n * 3u;
+    const uint32_t nv = sm.fused_n * 3u;
     if (nv == 0) return;                                    /* uniform: fused_n is shared */
-    for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) vcache[i] = 0xFFFFFFFFu;
-    if (threadIdx.x == 0) shade_n = 0;
-    __syncthreads();
+    auto local_vertex = [&](uint32_t v) { return 3u * (sm.fused_list[v / 3u].y - t0) + v % 3u; };
     auto vertex_in = [&](uint32_t v, VertexIn &in) {
-        const uint2 e = fused_list[v / 3u];
-        if (fastd.valid && e.y >= fastd.tri_begin && e.y < fastd.tri_end) {
-            fast_vertex(fastd, 3u * (e.y - fastd.tbase) + v % 3u, in);
+        const uint2 e = sm.fused_list[v / 3u];
+        if (any_fast && e.y >= fastd.tri_begin && e.y < fastd.tri_end) {
+            const uint32_t lv = 3u * (e.y - t0) + v % 3u;
+            in.px = sm.a_px[lv]; in.py = sm.a_py[lv]; in.pz = sm.a_pz[lv];
+            in.nx = sm.a_nx[lv]; in.ny = sm.a_ny[lv]; in.nz = sm.a_nz[lv];
+            in.s = sm.a_s[lv]; in.t = sm.a_t[lv];
+            in.cur = { fastd.cur_color[0], fastd.cur_color[1], fastd.cur_color[2], fastd.cur_color[3] };
+            in.st = fastd.st;
             return;
         }
         const uint32_t dd = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, e.y);
@@ -926,7 +976,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
 #pragma unroll
         for (int k = 0; k < 13; k++) hsh = (hsh ^ w[k]) * 0x9E3779B1u;
         hsh ^= hsh >> 15;
-        const uint32_t owner = atomicCAS(&vcache[hsh & (VCACHE_SLOTS - 1)], 0xFFFFFFFFu, v);
+        const uint32_t owner = atomicCAS(&sm.vcache[hsh & (VCACHE_SLOTS - 1)], 0xFFFFFFFFu, v);
         uint32_t same_as = v;
         if (owner != 0xFFFFFFFFu) {
             VertexIn o;
@@ -938,32 +988,34 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
                                (uint32_t)(o.st - b.states) == w[12];
             if (equal) same_as = owner;
         }
-        vsame[v] = (uint16_t)same_as;
-        if (same_as == v) shade_list[atomicAdd(&shade_n, 1u)] = (uint16_t)v;
+        sm.vsame[v] = (uint16_t)same_as;
+        if (same_as == v) sm.shade_list[atomicAdd(&sm.shade_n, 1u)] = (uint16_t)v;
     }
     __syncthreads();
-    const uint32_t ns = shade_n;
+    const uint32_t ns = sm.shade_n;
     for (uint32_t i = threadIdx.x; i < ns; i += SETUP_THREADS) {            /* B2 */
-        const uint32_t v = shade_list[i];
+        const uint32_t v = sm.shade_list[i];
         VertexIn in;
         vertex_in(v, in);
         VertexOut o;
         shade_vertex(in, o);
-        const uint32_t rr = fused_list[v / 3u].x, j = v % 3u;
-        reinterpret_cast<float4 *>(b.records + rr)[5 + j] = o.color;
+        /* the owner's raw position / normal.x are dead from here on (only this thread read them): its colour takes their place */
+        const uint32_t lv = local_vertex(v);
+        sm.a_px[lv] = o.color.x; sm.a_py[lv] = o.color.y; sm.a_pz[lv] = o.color.z; sm.a_nx[lv] = o.color.w;
         if (b.need_eye) {
-            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + rr);
-            eo[j] = o.epos;
-            eo[3 + j] = o.enrm;
+            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + sm.fused_list[v / 3u].x);
+            eo[v % 3u] = o.epos;
+            eo[3 + v % 3u] = o.enrm;
         }
     }
-    __syncthreads();                                        /* the owners' rows are visible to the whole CTA */
+    __syncthreads();                                        /* the owners' colours are visible to the whole CTA */
     for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {            /* B3 */
-        const uint32_t o = vsame[v];
-        if (o == v) continue;
-        const uint32_t rr = fused_list[v / 3u].x, j = v % 3u, ro = fused_list[o / 3u].x, jo = o % 3u;
-        reinterpret_cast<float4 *>(b.records + rr)[5 + j] = __ldcg(reinterpret_cast<const float4 *>(b.records + ro) + 5 + jo);
-        if (b.need_eye) {
+        const uint32_t o = sm.vsame[v];
+        const uint32_t lo = local_vertex(o);
+        const uint32_t rr = sm.fused_list[v / 3u].x, j = v % 3u;
+        reinterpret_cast<float4 *>(b.records + rr)[5 + j] = make_float4(sm.a_px[lo], sm.a_py[lo], sm.a_pz[lo], sm.a_nx[lo]);
+        if (b.need_eye && o != v) {
+            const uint32_t ro = sm.fused_list[o / 3u].x, jo = o % 3u;
             float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + rr);
             const float4 *es = reinterpret_cast<const float4 *>(b.rec_eye + ro);
             eo[j] = __ldcg(es + jo);

@@ -41,7 +41,6 @@ void note_launch();
 
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start 4 banks apart, 16-byte aligned */
-constexpr int VIS_CHUNK = 32;           /* list entries a warp takes at a time (<= 32): smaller = better balance between the warps of a tile */
 constexpr int VIS_LARGE_CAP = 512;      /* capacity of the large-triangle queue (a full queue makes the finding warp do the triangle alone) */
 constexpr int VIS_EXACT_EXTENT = 2047;  /* vertex extent up to which all edge values inside a tile are exactly represented integers */
 constexpr int VIS_COORD_LIMIT = 1 << 22;
@@ -181,7 +180,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     VisSmem &sm = *reinterpret_cast<VisSmem *>(vis_smem_raw);
     if (!lists_fit(b)) return;
 
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
     const int px0 = tx << TILE_LOG, py0t = ty << TILE_LOG;
     const int py0 = max(py0t, fb.band_y0);          /* shared-memory row 0 is framebuffer row py0 */
@@ -242,12 +241,23 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
      * e = A*x + B*y + C with tile-relative x, y gives the same bits as the reference's expression (raster.c:299-302)
      * in two FMAs per edge.  Everything else is queued for phase 2. ---- */
     const float px0f = (float)px0, py0f = (float)py0;
+    /* guided self-scheduling: the list is dealt in chunks of 32 entries, then 16, then 8 towards its end, so that the
+     * warps of the tile finish phase 1 within a fraction of a chunk of each other (the barrier before phase 2 was 16 %
+     * of the kernel's stall samples with uniform chunks).  Ticket k -> [c, c_end) is a pure function of L. */
+    const uint32_t tail8 = min(L, 64u);
+    const uint32_t head32 = ((L - tail8) > 128u) ? ((L - tail8 - 128u) & ~31u) : 0u;
+    const uint32_t mid16 = L - tail8 - head32;
+    const uint32_t n1 = head32 >> 5, n2 = (mid16 + 15u) >> 4;
     for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(&sm.next_chunk, (uint32_t)VIS_CHUNK);
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&sm.next_chunk, 1u);
+        k = __shfl_sync(0xFFFFFFFFu, k, 0);
+        uint32_t c, c_end;
+        if (k < n1) { c = k << 5; c_end = c + 32u; }
+        else if (k - n1 < n2) { c = head32 + ((k - n1) << 4); c_end = min(c + 16u, head32 + mid16); }
+        else { c = head32 + mid16 + ((k - n1 - n2) << 3); c_end = min(c + 8u, L); }
         if (c >= L) break;
-        const uint32_t e = (lane < (uint32_t)VIS_CHUNK) ? c + lane : L;
+        const uint32_t e = (c + lane < c_end) ? c + lane : L;
         uint32_t area = 0;                      /* box pixels of this lane's triangle; 0 = no small triangle here */
         bool alone = false;                     /* a large triangle that did not fit the queue */
         VisHead h;

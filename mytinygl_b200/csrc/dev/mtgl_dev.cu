@@ -53,7 +53,7 @@ struct mtgl_dev {
     float *unorm8 = nullptr;
 
     DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list, bin_rows;
-    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_list, vis_plane;
+    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane;
     DevCounters *counters = nullptr;
     DevCounters *h_counters = nullptr;      /* pinned */
 
@@ -250,7 +250,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     }
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
-                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_list, &d->vis_plane };
+                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane };
     for (DevBuf *b : bufs) release(*b);
     if (d->color) cudaFree(d->color);
     if (d->depth) cudaFree(d->depth);
@@ -576,7 +576,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4)) ||
                 (rc = reserve(d, d->bin_rows, rec_cap * 16))) return rc;
             if ((rc = reserve(d, d->tile_count, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_offset, (size_t)ntiles * 4)) ||
-                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_flags, (size_t)ntiles * 4))) return rc;
+                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_flags, (size_t)ntiles * 4)) ||
+                (rc = reserve(d, d->tile_order, (size_t)ntiles * 4))) return rc;
             if ((rc = reserve(d, d->vis_plane, (size_t)d->width * d->height * 4))) return rc;
             b.v_clip = (float4 *)d->v_clip.ptr; b.v_color = (float4 *)d->v_color.ptr; b.v_tex = (float4 *)d->v_tex.ptr;
             b.v_epos = (float4 *)d->v_epos.ptr; b.v_enrm = (float4 *)d->v_enrm.ptr;
@@ -587,6 +588,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.tile_count = (uint32_t *)d->tile_count.ptr; b.tile_offset = (uint32_t *)d->tile_offset.ptr;
             b.tile_cursor = (uint32_t *)d->tile_cursor.ptr;
             b.tile_flags = (uint32_t *)d->tile_flags.ptr;
+            b.tile_order = (uint32_t *)d->tile_order.ptr;
             b.vis_plane = (uint32_t *)d->vis_plane.ptr;
 
             CU(cudaMemsetAsync(d->counters, 0, sizeof(DevCounters), d->stream));
