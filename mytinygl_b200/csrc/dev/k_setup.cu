@@ -754,6 +754,8 @@ struct SetupSmem {
     uint32_t fused_n;                           /* survivors of this chunk whose colour rows phase B fills */
     uint32_t shade_n;
     FastDraw fastd;                             /* fast attribute path of the draw this chunk starts in */
+    mtgl_state vstate;                          /* ... and a copy of its vertex-stage state block: matrices, lights and materials
+                                                 * are read from shared memory, not through L1, by every thread and every light */
 };
 static_assert(sizeof(SetupSmem) <= 48 * 1024, "k_setup uses static shared memory");
 
@@ -777,7 +779,13 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
 
     /* ---- phase A0: stage the raw attributes of the chunk's fast-path triangles ---- */
     const bool any_fast = fastd.valid != 0u;
+    const mtgl_state *const fst = &sm.vstate;
     if (any_fast) {
+        {
+            const uint32_t *srcw = reinterpret_cast<const uint32_t *>(fastd.st);
+            uint32_t *dstw = reinterpret_cast<uint32_t *>(&sm.vstate);
+            for (uint32_t i = threadIdx.x; i < sizeof(mtgl_state) / 4u; i += SETUP_THREADS) dstw[i] = __ldg(srcw + i);
+        }
         const uint32_t tb = max(fastd.tri_begin, t0), te = min(min(fastd.tri_end, t0 + SETUP_THREADS), b.n_triangles);
         for (uint32_t lv = threadIdx.x + 3u * (tb - t0); lv < 3u * (te - t0); lv += SETUP_THREADS) {
             VertexIn in;
@@ -831,7 +839,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
                 float x, y, z, ex, ey, ez, ew;
                 const mtgl_state *vs;
                 if (fast_t) {
-                    vs = fastd.st;
+                    vs = fst;
                     const uint32_t lv = 3u * threadIdx.x;
                     to_eye(vs, sm.a_px[lv], sm.a_py[lv], sm.a_pz[lv], ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
                     to_eye(vs, sm.a_px[lv + 1], sm.a_py[lv + 1], sm.a_pz[lv + 1], ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
@@ -896,7 +904,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
                 float px[3], py[3], pz[3], ts[3], tt[3];
                 const mtgl_state *vs;
                 if (fast_t) {
-                    vs = fastd.st;
+                    vs = fst;
 #pragma unroll
                     for (int j = 0; j < 3; j++) {
                         const uint32_t lv = 3u * threadIdx.x + j;
@@ -950,7 +958,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     const uint32_t nv = sm.fused_n * 3u;
     if (nv == 0) return;                                    /* uniform: fused_n is shared */
     auto local_vertex = [&](uint32_t v) { return 3u * (sm.fused_list[v / 3u].y - t0) + v % 3u; };
-    auto vertex_in = [&](uint32_t v, VertexIn &in) {
+    auto vertex_in = [&](uint32_t v, VertexIn &in, uint32_t &state_id) {
         const uint2 e = sm.fused_list[v / 3u];
         if (any_fast && e.y >= fastd.tri_begin && e.y < fastd.tri_end) {
             const uint32_t lv = 3u * (e.y - t0) + v % 3u;
@@ -958,20 +966,23 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
             in.nx = sm.a_nx[lv]; in.ny = sm.a_ny[lv]; in.nz = sm.a_nz[lv];
             in.s = sm.a_s[lv]; in.t = sm.a_t[lv];
             in.cur = { fastd.cur_color[0], fastd.cur_color[1], fastd.cur_color[2], fastd.cur_color[3] };
-            in.st = fastd.st;
+            in.st = fst;
+            state_id = (uint32_t)(fastd.st - b.states);
             return;
         }
         const uint32_t dd = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, e.y);
         const DevDraw &dr = b.draws[dd];
         fetch_vertex(b.staged, b.states, dr, 3u * (e.y - dr.tbase) + v % 3u, in);
+        state_id = (uint32_t)(in.st - b.states);
     };
     for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {            /* B1 */
         VertexIn in;
-        vertex_in(v, in);
+        uint32_t sid;
+        vertex_in(v, in, sid);
         const uint32_t w[13] = { __float_as_uint(in.px), __float_as_uint(in.py), __float_as_uint(in.pz), __float_as_uint(in.nx),
                                  __float_as_uint(in.ny), __float_as_uint(in.nz), __float_as_uint(in.s), __float_as_uint(in.t),
                                  __float_as_uint(in.cur.r), __float_as_uint(in.cur.g), __float_as_uint(in.cur.b), __float_as_uint(in.cur.a),
-                                 (uint32_t)(in.st - b.states) };
+                                 sid };
         uint32_t hsh = 0x811C9DC5u;
 #pragma unroll
         for (int k = 0; k < 13; k++) hsh = (hsh ^ w[k]) * 0x9E3779B1u;
@@ -980,12 +991,13 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         uint32_t same_as = v;
         if (owner != 0xFFFFFFFFu) {
             VertexIn o;
-            vertex_in(owner, o);
+            uint32_t osid;
+            vertex_in(owner, o, osid);
             const bool equal = __float_as_uint(o.px) == w[0] && __float_as_uint(o.py) == w[1] && __float_as_uint(o.pz) == w[2] &&
                                __float_as_uint(o.nx) == w[3] && __float_as_uint(o.ny) == w[4] && __float_as_uint(o.nz) == w[5] &&
                                __float_as_uint(o.s) == w[6] && __float_as_uint(o.t) == w[7] && __float_as_uint(o.cur.r) == w[8] &&
                                __float_as_uint(o.cur.g) == w[9] && __float_as_uint(o.cur.b) == w[10] && __float_as_uint(o.cur.a) == w[11] &&
-                               (uint32_t)(o.st - b.states) == w[12];
+                               osid == w[12];
             if (equal) same_as = owner;
         }
         sm.vsame[v] = (uint16_t)same_as;
@@ -996,7 +1008,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     for (uint32_t i = threadIdx.x; i < ns; i += SETUP_THREADS) {            /* B2 */
         const uint32_t v = sm.shade_list[i];
         VertexIn in;
-        vertex_in(v, in);
+        uint32_t sid;
+        vertex_in(v, in, sid);
         VertexOut o;
         shade_vertex(in, o);
         /* the owner's raw position / normal.x are dead from here on (only this thread read them): its colour takes their place */

@@ -41,21 +41,31 @@ void note_launch();
 
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start 4 banks apart, 16-byte aligned */
-constexpr int VIS_LARGE_CAP = 512;      /* capacity of the large-triangle queue (a full queue makes the finding warp do the triangle alone) */
+constexpr int VIS_LARGE_CAP = 192;      /* capacity of the large-triangle queue (a full queue makes the finding warp do the triangle alone) */
 constexpr int VIS_EXACT_EXTENT = 2047;  /* vertex extent up to which all edge values inside a tile are exactly represented integers */
 constexpr int VIS_COORD_LIMIT = 1 << 22;
 constexpr int VIS_SMALL_AREA = 256;     /* clamped box area up to which 8 lanes handle a triangle */
 
+/* per warp: the prepared small triangles of the current chunk (slot = compacted position in the chunk) and the
+ * row spans of the current group of 32 rows.  Edge k is e = A*x + B*y + C in tile-relative pixel coordinates. */
+struct VisWarp {
+    float4 T0[32];          /* A0 A1 A2 1/area                                   (pixel stage) */
+    float4 T1[32];          /* z0 z1 z2 id                                       (pixel stage) */
+    float4 T2[32];          /* B0 B1 B2 X0 | Y0 << 6 | (width - 1) << 12 | first-row-in-run << 18   (span stage) */
+    float C[3][32];         /*                                                   (span stage) */
+    float RN[3][32];        /* -1 / A_k, 0 when A_k == 0                         (span stage) */
+    float4 S[32];           /* spans: row terms t_k = B_k*y + C_k, x_left | y << 6 | triangle slot << 12 | first-pixel-in-run << 17 */
+};
+
 struct VisSmem {
     unsigned long long key[TILE_H * VIS_PITCH];
     uint32_t large_rec[VIS_LARGE_CAP];
-    /* per warp: the prepared small triangles of the current chunk, 16 words each: edge k as e = A*x + B*y + C in
-     * tile-relative pixel coordinates -- row 0 (A0 B0 C0 A1), row 1 (B1 C1 A2 B2), row 2 (C2, 1/area, z0, z1),
-     * row 3 (z2, id, X0 | Y0 << 6 | (width - 1) << 12 | start-in-run << 18, 1/width) */
-    float4 prep[RASTER_THREADS / 32][4][32];
+    VisWarp w[RASTER_THREADS / 32];
     uint32_t next_chunk;
     uint32_t large_n;
 };
+/* four CTAs per SM: 4 * (sizeof + 1 KB reserved) must fit the SM's 228 KB */
+static_assert(4 * (sizeof(VisSmem) + 1024) <= 228 * 1024, "k_vis: four tiles per SM");
 
 /* monotone map float -> uint32 (total order of the reals, -0 < +0) and back */
 __device__ __forceinline__ uint32_t ord_bits(float f)
@@ -234,12 +244,14 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t *list = b.tile_list + b.tile_offset[tile];
 
-    /* ---- phase 1: warps take 32 list entries at a time.  The boxes of the chunk's small triangles are laid end to end
-     * into one run of pixels and the warp walks that run 32 pixels per step, one pixel per lane, whatever triangle it
-     * belongs to -- every lane has a box pixel to test in every step.  "Small" also means a vertex extent below 2^11:
-     * then every edge value inside the tile is an integer below 2^24, exactly represented in float, and
-     * e = A*x + B*y + C with tile-relative x, y gives the same bits as the reference's expression (raster.c:299-302)
-     * in two FMAs per edge.  Everything else is queued for phase 2. ---- */
+    /* ---- phase 1: warps take up to 32 list entries at a time.  "Small" triangles have a clamped box of at most 256
+     * pixels and a vertex extent below 2^11: then every edge value inside the tile is an integer below 2^24, exactly
+     * represented in float, and e = A*x + B*y + C with tile-relative x, y gives the same bits as the reference's
+     * expression (raster.c:299-302).  Because the values are exact, the covered pixels of a box row are exactly the
+     * integer solutions of three linear inequalities: the warp first turns (triangle, row) pairs -- 32 at a time, one per
+     * lane -- into spans [x_left, x_right], then lays the spans end to end into one run of pixels and walks it 32 pixels
+     * per step, one COVERED pixel per lane (a box walk tests ~3 pixels per covered one on C4's slivers).  Everything
+     * else is queued for phase 2. ---- */
     const float px0f = (float)px0, py0f = (float)py0;
     /* guided self-scheduling: the list is dealt in chunks of 32 entries, then 16, then 8 towards its end, so that the
      * warps of the tile finish phase 1 within a fraction of a chunk of each other (the barrier before phase 2 was 16 %
@@ -258,7 +270,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
         else { c = head32 + mid16 + ((k - n1 - n2) << 3); c_end = min(c + 8u, L); }
         if (c >= L) break;
         const uint32_t e = (c + lane < c_end) ? c + lane : L;
-        uint32_t area = 0;                      /* box pixels of this lane's triangle; 0 = no small triangle here */
+        uint32_t nrows = 0;                     /* box rows of this lane's triangle; 0 = no small triangle here */
         bool alone = false;                     /* a large triangle that did not fit the queue */
         VisHead h;
         int X0 = 0, Y0 = 0, bw = 1;
@@ -269,8 +281,8 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
             X0 = max((int)(h.row2.x & 0xFFFFu) - px0, 0); Y0 = max((int)(h.row2.x >> 16) - py0, 0);
             const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
             bw = X1 - X0 + 1;
-            area = (uint32_t)(bw * (Y1 - Y0 + 1));
-            const bool small = area <= (uint32_t)VIS_SMALL_AREA && mode.all_range01 &&
+            nrows = (uint32_t)(Y1 - Y0 + 1);
+            const bool small = (uint32_t)bw * nrows <= (uint32_t)VIS_SMALL_AREA && mode.all_range01 &&
                                coord_small(h.row0.x) && coord_small(h.row0.y) && coord_small(h.row0.z) && coord_small(h.row0.w) &&
                                coord_small(h.row1.x) && coord_small(h.row1.y) &&
                                max(max(h.row0.x, h.row0.z), h.row1.x) - min(min(h.row0.x, h.row0.z), h.row1.x) <= VIS_EXACT_EXTENT &&
@@ -278,7 +290,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
             if (!small) {
                 const uint32_t at = atomicAdd(&sm.large_n, 1u);
                 if (at < (uint32_t)VIS_LARGE_CAP) sm.large_rec[at] = r; else alone = true;
-                area = 0;
+                nrows = 0;
             }
         }
         /* (rare) queue full: the warp rasterises those triangles by itself, one after the other */
@@ -295,64 +307,116 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
             raster_blocks(sm.key, mode, b, g, px0, py0, 0, 1);
             __syncwarp();
         }
-        const uint32_t smask = __ballot_sync(0xFFFFFFFFu, area != 0u);
+        const uint32_t smask = __ballot_sync(0xFFFFFFFFu, nrows != 0u);
         if (!smask) continue;
-        /* start of each small triangle's box in the run (exclusive scan of the areas) */
-        uint32_t incl = area;
+        /* first row of each small triangle in the run of rows (exclusive scan of the row counts) */
+        uint32_t incl = nrows;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= (uint32_t)o) incl += up;
         }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const uint32_t start = incl - area;
-        if (area) {                             /* prepared triangle -> this warp's staging slots, in compacted order */
+        const uint32_t total_rows = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t row_start = incl - nrows;
+        VisWarp &vw_ = sm.w[warp];
+        if (nrows) {                            /* prepared triangle -> this warp's staging slots, in compacted order */
             EdgeSet E;
             prepare_edges(E, h.row0.x, h.row0.y, h.row0.z, h.row0.w, h.row1.x, h.row1.y, __int_as_float(h.row1.z), __int_as_float(h.row1.w));
-            float A[3], B[3], C[3];
+            float A[3], B[3], C[3], RN[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {       /* all operands and results are integers below 2^24: exact */
                 A[k] = E.dy[k]; B[k] = -E.dx[k];
                 C[k] = (px0f - E.ax[k]) * E.dy[k] - (py0f - E.ay[k]) * E.dx[k];
+                RN[k] = (A[k] != 0.0f) ? -1.0f / A[k] : 0.0f;
             }
             const uint32_t ci = (uint32_t)__popc(smask & lt_mask);
-            float4 *slot = &sm.prep[warp][0][ci];
-            slot[0 * 32] = make_float4(A[0], B[0], C[0], A[1]);
-            slot[1 * 32] = make_float4(B[1], C[1], A[2], B[2]);
-            slot[2 * 32] = make_float4(C[2], E.inv_area, h.z0, h.z1);
-            slot[3 * 32] = make_float4(h.z2, __uint_as_float(h.row2.w),
-                                       __uint_as_float((uint32_t)X0 | ((uint32_t)Y0 << 6) | ((uint32_t)(bw - 1) << 12) | (start << 18)), 1.0f / (float)bw);
+            vw_.T0[ci] = make_float4(A[0], A[1], A[2], E.inv_area);
+            vw_.T1[ci] = make_float4(h.z0, h.z1, h.z2, __uint_as_float(h.row2.w));
+            vw_.T2[ci] = make_float4(B[0], B[1], B[2],
+                                     __uint_as_float((uint32_t)X0 | ((uint32_t)Y0 << 6) | ((uint32_t)(bw - 1) << 12) | (row_start << 18)));
+#pragma unroll
+            for (int k = 0; k < 3; k++) { vw_.C[k][ci] = C[k]; vw_.RN[k][ci] = RN[k]; }
         }
         __syncwarp();
-        uint32_t before = 0;                    /* small triangles that start before the current step */
-        for (uint32_t base = 0; base < total; base += 32) {
-            const int rel = (int)start - (int)base;
-            const uint32_t marks = __reduce_or_sync(0xFFFFFFFFu, (area != 0u && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
-            const uint32_t p = base + lane;
-            if (p < total) {
-                const uint32_t ci = before + (uint32_t)__popc(marks & (0xFFFFFFFFu >> (31u - lane))) - 1u;   /* the triangle whose box holds pixel p */
-                const float4 *slot = &sm.prep[warp][0][ci];
-                const float4 r3 = slot[3 * 32];
-                const uint32_t bs = __float_as_uint(r3.z), q = p - (bs >> 18);
-                const int w = (int)((bs >> 12) & 63u) + 1;
-                /* row inside the box: (q + 1/2) / w is at least 1/(2w) >= 1/128 away from an integer, the product with the
-                 * rounded reciprocal is off by less than 2^-14, so the truncation is the exact quotient */
-                const int yy = __float2int_rz(((float)q + 0.5f) * r3.w);
-                const int x = (int)(bs & 63u) + ((int)q - yy * w), y = (int)((bs >> 6) & 63u) + yy;
-                const float fx = (float)x, fy = (float)y;
-                const float4 r0 = slot[0 * 32], r1 = slot[1 * 32], r2 = slot[2 * 32];
-                const float e0 = __fmaf_rn(r0.x, fx, __fmaf_rn(r0.y, fy, r0.z));
-                const float e1 = __fmaf_rn(r0.w, fx, __fmaf_rn(r1.x, fy, r1.y));
-                const float e2 = __fmaf_rn(r1.z, fx, __fmaf_rn(r1.w, fy, r2.x));
-                if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
-                    const float b0 = e0 * r2.y, b1 = e1 * r2.y, b2 = e2 * r2.y;
-                    const float z = b0 * r2.z + b1 * r2.w + b2 * r3.x;
-                    key_min(&sm.key[y * VIS_PITCH + x], make_key(mode, depth_of(z, true, 0.0, 1.0), __float_as_uint(r3.y)));
+        uint32_t before_t = 0;                  /* small triangles that start before the current group of rows */
+        for (uint32_t rbase = 0; rbase < total_rows; rbase += 32) {
+            /* ---- span stage: lane = one (triangle, row) pair ---- */
+            const int rel = (int)row_start - (int)rbase;
+            const uint32_t tmarks = __reduce_or_sync(0xFFFFFFFFu, (nrows != 0u && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+            const uint32_t rho = rbase + lane;
+            uint32_t width = 0, sbits = 0;
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+            if (rho < total_rows) {
+                const uint32_t ci = before_t + (uint32_t)__popc(tmarks & (0xFFFFFFFFu >> (31u - lane))) - 1u;   /* the triangle whose box holds row rho */
+                const float4 g2 = vw_.T2[ci];
+                const uint32_t bs = __float_as_uint(g2.w);
+                const int y = (int)((bs >> 6) & 63u) + (int)(rho - (bs >> 18));
+                const float fy = (float)y;
+                t0 = __fmaf_rn(g2.x, fy, vw_.C[0][ci]);
+                t1 = __fmaf_rn(g2.y, fy, vw_.C[1][ci]);
+                t2 = __fmaf_rn(g2.z, fy, vw_.C[2][ci]);
+                /* A*x + t >= 0  <=>  x >= -t/A (A > 0)  or  x <= -t/A (A < 0)  or  t >= 0 (A == 0).  q = t * (-1/A) is within
+                 * 2^-13 of the quotient wherever it matters (|q| < 2^10); a non-integral quotient of integers with |A| < 2^11 is
+                 * at least 2^-11 away from an integer, so rounding q -+ 2^-12 up / down is exact.  The pixel stage re-tests
+                 * every pixel anyway. */
+                float lo = (float)(int)(bs & 63u), hi = lo + (float)(int)((bs >> 12) & 63u);
+                bool ok = true;
+                const float tk[3] = { t0, t1, t2 };
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float rn = vw_.RN[k][ci];
+                    const float q = fminf(fmaxf(tk[k] * rn, -128.0f), 128.0f);
+                    if (rn < 0.0f) lo = fmaxf(lo, ceilf(q - 0.000244140625f));
+                    else if (rn > 0.0f) hi = fminf(hi, floorf(q + 0.000244140625f));
+                    else ok = ok && (tk[k] >= 0.0f);
+                }
+                if (ok && hi >= lo) {
+                    width = (uint32_t)(int)(hi - lo) + 1u;
+                    sbits = (uint32_t)(int)lo | ((uint32_t)y << 6) | (ci << 12);
                 }
             }
-            before += (uint32_t)__popc(marks);
+            before_t += (uint32_t)__popc(tmarks);
+            /* first pixel of each non-empty span in the run of pixels */
+            uint32_t pincl = width;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, pincl, o);
+                if (lane >= (uint32_t)o) pincl += up;
+            }
+            const uint32_t total_px = __shfl_sync(0xFFFFFFFFu, pincl, 31);
+            const uint32_t pstart = pincl - width;
+            const uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, width != 0u);
+            if (width) vw_.S[__popc(nonempty & lt_mask)] = make_float4(t0, t1, t2, __uint_as_float(sbits | (pstart << 17)));
+            __syncwarp();
+            /* ---- pixel stage: lane = one pixel of the run ---- */
+            uint32_t before_s = 0;
+            for (uint32_t pbase = 0; pbase < total_px; pbase += 32) {
+                const int prel = (int)pstart - (int)pbase;
+                const uint32_t smarks = __reduce_or_sync(0xFFFFFFFFu, (width != 0u && prel >= 0 && prel < 32) ? (1u << prel) : 0u);
+                const uint32_t p = pbase + lane;
+                if (p < total_px) {
+                    const uint32_t si = before_s + (uint32_t)__popc(smarks & (0xFFFFFFFFu >> (31u - lane))) - 1u;   /* the span that holds pixel p */
+                    const float4 sp = vw_.S[si];
+                    const uint32_t sb = __float_as_uint(sp.w);
+                    const uint32_t ci = (sb >> 12) & 31u;
+                    const int x = (int)(sb & 63u) + (int)(p - (sb >> 17)), y = (int)((sb >> 6) & 63u);
+                    const float fx = (float)x;
+                    const float4 g0 = vw_.T0[ci];
+                    const float e0 = __fmaf_rn(g0.x, fx, sp.x);
+                    const float e1 = __fmaf_rn(g0.y, fx, sp.y);
+                    const float e2 = __fmaf_rn(g0.z, fx, sp.z);
+                    if (fminf(fminf(e0, e1), e2) >= 0.0f) {         /* inclusive on all three edges (raster.c:539-540) */
+                        const float4 g1 = vw_.T1[ci];
+                        const float b0 = e0 * g0.w, b1 = e1 * g0.w, b2 = e2 * g0.w;
+                        const float z = b0 * g1.x + b1 * g1.y + b2 * g1.z;
+                        key_min(&sm.key[y * VIS_PITCH + x], make_key(mode, depth_of(z, true, 0.0, 1.0), __float_as_uint(g1.w)));
+                    }
+                }
+                before_s += (uint32_t)__popc(smarks);
+            }
+            __syncwarp();       /* the span slots are rewritten by the next group */
         }
-        __syncwarp();       /* the staging slots are rewritten by the next chunk */
+        __syncwarp();           /* the triangle slots are rewritten by the next chunk */
     }
     __syncthreads();
 
