@@ -44,7 +44,9 @@ constexpr int VIS_PITCH = 66;           /* 64-bit words per tile row: rows start
 constexpr int VIS_LARGE_CAP = 192;      /* capacity of the large-triangle queue (a full queue makes the finding warp do the triangle alone) */
 constexpr int VIS_EXACT_EXTENT = 2047;  /* vertex extent up to which all edge values inside a tile are exactly represented integers */
 constexpr int VIS_COORD_LIMIT = 1 << 22;
-constexpr int VIS_SMALL_AREA = 256;     /* clamped box area up to which 8 lanes handle a triangle */
+constexpr int VIS_SMALL_AREA = 1024;    /* clamped box area up to which one warp turns a triangle into spans (phase 1) ... */
+constexpr int VIS_SMALL_AREA_BUSY = 4096;   /* ... any box, when the tile's list is long enough to keep all warps busy with whole triangles */
+constexpr uint32_t VIS_BUSY_LIST = 64;
 
 /* per warp: the prepared small triangles of the current chunk (slot = compacted position in the chunk) and the
  * row spans of the current group of 32 rows.  Edge k is e = A*x + B*y + C in tile-relative pixel coordinates. */
@@ -282,7 +284,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
             const int X1 = min((int)(h.row2.y & 0xFFFFu) - px0, TILE_W - 1), Y1 = min((int)(h.row2.y >> 16) - py0, TILE_H - 1);
             bw = X1 - X0 + 1;
             nrows = (uint32_t)(Y1 - Y0 + 1);
-            const bool small = (uint32_t)bw * nrows <= (uint32_t)VIS_SMALL_AREA && mode.all_range01 &&
+            const bool small = (uint32_t)bw * nrows <= (uint32_t)(L >= VIS_BUSY_LIST ? VIS_SMALL_AREA_BUSY : VIS_SMALL_AREA) && mode.all_range01 &&
                                coord_small(h.row0.x) && coord_small(h.row0.y) && coord_small(h.row0.z) && coord_small(h.row0.w) &&
                                coord_small(h.row1.x) && coord_small(h.row1.y) &&
                                max(max(h.row0.x, h.row0.z), h.row1.x) - min(min(h.row0.x, h.row0.z), h.row1.x) <= VIS_EXACT_EXTENT &&
