@@ -412,24 +412,27 @@ def run_b200(args, workload):
         frag_bytes = cnt["covered"] * 4 + cnt["tested"] * 8
         clear_bytes = px * (4 + 4)
         vertex_bytes = cnt["vertices"] * 32
-    # the dominant kernel of the step: K4a (visibility: coverage + depth), K4b (shade) or the general in-order kernel,
-    # whichever the live per-group CUDA-event times say; its algorithmic bytes are SURVEY.md 8(d)'s per-fragment
-    # framebuffer traffic of the reference restricted to the planes that kernel owns (DESIGN.md "Roofline")
-    groups = ["k_vis (K4a visibility)", "k_shade (K4b)", "k_raster<false> (general)"]
-    gi = int(np.argmax(rstage))
-    raster_ms = rstage[gi] / args.steps
+    # the dominant kernel of the step, whichever the live per-group CUDA-event times say: the fused vertex + set-up
+    # kernel (K1+K2), K4a (visibility: coverage + depth), K4b (shade) or the general in-order kernel.  Its algorithmic
+    # bytes are SURVEY.md 8(d)'s figures restricted to what that kernel owns (DESIGN.md "Rooflines"): the enabled
+    # attribute arrays per input vertex for set-up, the reference's per-fragment framebuffer traffic for the planes a
+    # raster kernel owns.
+    groups = ["k_setup (K1+K2 vertex + set-up)", "k_vis (K4a visibility)", "k_shade (K4b)", "k_raster<false> (general)"]
+    group_ms = [stage[1] / args.steps] + [float(x) / args.steps for x in rstage]
+    gi = int(np.argmax(group_ms))
+    raster_ms = group_ms[gi]
     if is_c3:
-        group_bytes = [0, 0, frag_bytes + clear_bytes]
+        group_bytes = [0, 0, 0, frag_bytes + clear_bytes]
     else:
-        group_bytes = [cnt["covered"] * 4 + cnt["tested"] * 4 + px * 4, cnt["tested"] * 4 + px * 4, 0]
+        group_bytes = [vertex_bytes * world, cnt["covered"] * 4 + cnt["tested"] * 4 + px * 4, cnt["tested"] * 4 + px * 4, 0]
         if group_bytes[gi] == 0:        # a state mix that sends C4/C5 through the general kernel
             group_bytes[gi] = frag_bytes + clear_bytes
-    raster_bytes = group_bytes[gi] / world          # one launch per rank covers 1/N of the frame
+    raster_bytes = group_bytes[gi] / world          # one launch per rank covers 1/N of the frame (set-up: all of it)
     achieved = raster_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
     traffic = None
     try:
-        tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text()).get(workload)
-        if tj and tj["kernel"].split("<")[0].split(" ")[0] == groups[gi].split("<")[0].split(" ")[0] and world == 1:
+        tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text()).get(workload, {}).get(groups[gi].split(" ")[0])
+        if tj and world == 1:
             traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
     except Exception:
         traffic = None
