@@ -197,6 +197,10 @@ def run_b200(args, workload):
     y0, y1 = band_rows(h, rank, world)
     if world > 1:
         assert L.mtgl_dev_set_band(dev, y0, y1) == 0
+    elif os.environ.get("MTGL_BENCH_BAND"):      # diagnostics: one GPU plays rank r of n ("r/n"); the line is not a bench value
+        er, en = (int(x) for x in os.environ["MTGL_BENCH_BAND"].split("/"))
+        y0, y1 = band_rows(h, er, en)
+        assert L.mtgl_dev_set_band(dev, y0, y1) == 0
 
     is_c3 = workload == "c3"
     if not is_c3:

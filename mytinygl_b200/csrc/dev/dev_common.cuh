@@ -83,6 +83,7 @@ struct DevDraw {
     uint32_t ntris;          /* primitives of this draw in the pass */
     uint32_t fused;          /* independent triangles: no vertex-stage launch, k_setup shades the survivors' vertices */
     uint32_t pad2_;
+    const float4 *bounds;    /* object-space boxes of the draw's 256-triangle chunks (k_cull.cu), or NULL */
 };
 
 /* Raster-stage view of one mtgl_state: enums folded to small integers, texture resolved to
@@ -389,6 +390,7 @@ struct BatchDev {
     /* set-up output */
     TriRecord *records; TriEye *rec_eye; uint32_t record_capacity;
     uint32_t *chunk_base;           /* first record slot of every 256-triangle chunk */
+    uint8_t *chunk_cull;            /* 1 = the chunk cannot produce a record on this device (k_cull.cu); NULL = no culling pass */
     uint32_t *large_list;
     uint4 *bin_rows;                /* copy of every record's row 2 (bbox_min, bbox_max, state_flags, id): all the binner reads */
     DevCounters *counters;
@@ -412,6 +414,8 @@ __device__ __forceinline__ bool lists_fit(const BatchDev &b)
 
 void launch_vertex_stage(const BatchDev &b, cudaStream_t s);
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
+void launch_chunk_bounds(const uint8_t *pos, uint32_t stride, uint32_t size, int32_t first, uint32_t nverts, float4 *out, cudaStream_t s);
+void launch_chunk_cull(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
@@ -432,6 +436,10 @@ void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const Clear
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);
 uint64_t kernel_launch_count();
+/* A tile grid well below one wave of 8-warp CTAs (148 SMs x 4 = 592): the band of a multi-GPU frame (measured: the
+ * latency shapes win at 240-300 tiles, lose at 540).  The tile kernels
+ * then run in their latency shapes -- more warps per tile (k_vis<512>), sub-tile CTAs (k_shade<4>). */
+bool small_grid(uint32_t tiles);      /* tiles <= 400, or what MTGL_GRID_SHAPE=small|large forces (tests cover both shapes at any size) */
 
 } // namespace mtgl_dev_impl
 

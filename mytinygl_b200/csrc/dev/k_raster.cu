@@ -924,49 +924,57 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
  * first compacted into a list (ballot + prefix), then shaded 256 at a time with every lane busy -- same colour
  * code as resolve_region.  The colour part of the batch's leading clear is applied here as well.  Full occupancy,
  * coalesced plane accesses, no ordering constraints left. */
+/* SPLIT = 1: one CTA per tile.  SPLIT = 4: four CTAs per tile, 16 rows each -- for grids of at most about one wave
+ * (small_grid(): the band of a multi-GPU frame), where the finer granularity spreads the uneven tiles over the SMs. */
+template <int SPLIT>
 __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
 {
+    constexpr int ROWS = TILE_H / SPLIT;        /* rows of the tile this CTA owns */
+    constexpr int PX = 16 / SPLIT;              /* consecutive pixels per thread in pass 1 */
+    constexpr int TPR = TILE_W / PX;            /* threads per row */
     __shared__ float un[256];
-    __shared__ uint16_t list[TILE_W * TILE_H];
-    __shared__ uint32_t rlist[TILE_W * TILE_H];             /* record index of the compacted pixel: pass 2 does not re-read the plane */
+    __shared__ uint16_t list[TILE_W * ROWS];
+    __shared__ uint32_t rlist[TILE_W * ROWS];               /* record index of the compacted pixel: pass 2 does not re-read the plane */
     __shared__ uint32_t warp_total[8];
     if (!lists_fit(b)) return;
     un[threadIdx.x] = b.unorm8[threadIdx.x];
 
-    const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
+    const uint32_t slot = blockIdx.x / SPLIT, sub = blockIdx.x % SPLIT;
+    const uint32_t tile = b.tile_order ? b.tile_order[slot] : slot;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
-    const int px0 = tx << TILE_LOG, py0 = max(ty << TILE_LOG, fb.band_y0);
-    const int vw = min(TILE_W, fb.width - px0), vh = min((ty << TILE_LOG) + TILE_H, fb.band_y1) - py0;
+    const int row0 = (ty << TILE_LOG) + (int)sub * ROWS;
+    const int px0 = tx << TILE_LOG, py0 = max(row0, fb.band_y0);
+    const int vw = min(TILE_W, fb.width - px0), vh = min(row0 + ROWS, fb.band_y1) - py0;
     if (vw <= 0 || vh <= 0) return;
     const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
     if (L && (b.tile_flags[tile] & 1u)) return;             /* the general kernel owns this tile */
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    /* pass 1: colour clear + compaction of the pixels to shade.  A thread owns 16 consecutive pixels of one row
-     * (row = tid / 4), so its visibility loads are four 16-byte loads issued back to back and thread order is
-     * row-major pixel order: the compacted list keeps neighbouring pixels next to each other for pass 2. */
-    const int y = (int)(threadIdx.x >> 2), xq = (int)(threadIdx.x & 3) * 16;
+    /* pass 1: colour clear + compaction of the pixels to shade.  A thread owns PX consecutive pixels of one row, so
+     * its visibility loads are 16-byte loads issued back to back and thread order is row-major pixel order: the
+     * compacted list keeps neighbouring pixels next to each other for pass 2. */
+    const int y = (int)threadIdx.x / TPR, xq = ((int)threadIdx.x % TPR) * PX;
     uint32_t has_mask = 0;
-    uint32_t v[16];
+    uint32_t v[PX];
     if (y < vh) {
         const size_t p0 = (size_t)(py0 + y) * fb.width + px0 + xq;
         if (!L) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = VIS_NONE;
+            for (int k = 0; k < PX; k++) v[k] = VIS_NONE;
         } else if (vw == TILE_W && (fb.width & 3) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < PX / 4; q++) {
                 const uint4 t = *reinterpret_cast<const uint4 *>(b.vis_plane + p0 + q * 4);
                 v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = (xq + k < vw) ? b.vis_plane[p0 + k] : VIS_NONE;
+            for (int k = 0; k < PX; k++) v[k] = (xq + k < vw) ? b.vis_plane[p0 + k] : VIS_NONE;
         }
         const bool clr_row = (clr.mask & G_COLOR_BUFFER_BIT) && py0 + y >= clr.y0 && py0 + y < clr.y1;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < PX; k++) {
             if (v[k] != VIS_NONE) has_mask |= 1u << k;
             else if (clr_row && xq + k < vw && px0 + xq + k >= clr.x0 && px0 + xq + k < clr.x1) fb.color[p0 + k] = clr.color;
         }
@@ -988,7 +996,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, C
         n += wt;
     }
 #pragma unroll
-    for (int k = 0; k < 16; k++)
+    for (int k = 0; k < PX; k++)
         if (has_mask & (1u << k)) { list[at] = (uint16_t)(y * TILE_W + xq + k); rlist[at] = v[k]; at++; }
     __syncthreads();
 
@@ -1065,7 +1073,8 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         }
         cudaEventRecord(ev_vis, s);
         if (planes & 1u) {
-            k_shade<<<tiles, 256, 0, s>>>(b, fb, clear);
+            if (small_grid(tiles)) k_shade<4><<<tiles * 4u, 256, 0, s>>>(b, fb, clear);
+            else k_shade<1><<<tiles, 256, 0, s>>>(b, fb, clear);
             note_launch();
         }
         cudaEventRecord(ev_shade, s);

@@ -764,6 +764,10 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     __shared__ SetupSmem sm;
     FastDraw &fastd = sm.fastd;
     const uint32_t chunk = blockIdx.x;
+    if (b.chunk_cull && b.chunk_cull[chunk]) {              /* k_cull.cu: nothing of this chunk reaches the device's rows */
+        if (threadIdx.x == 0) b.chunk_base[chunk] = 0u;
+        return;
+    }
     const uint32_t t0 = chunk * SETUP_THREADS;
     if (threadIdx.x == 0) {
         sm.fused_n = 0;

@@ -20,11 +20,22 @@
 #include "dev_common.cuh"
 #include "dev_vertex.cuh"
 
+#include <cstdlib>
+
 namespace mtgl_dev_impl {
 
 static unsigned long long g_launches = 0;
 uint64_t kernel_launch_count() { return g_launches; }
 void note_launch() { g_launches++; }
+
+bool small_grid(uint32_t tiles)
+{
+    if (const char *e = std::getenv("MTGL_GRID_SHAPE")) {
+        if (e[0] == 's') return true;
+        if (e[0] == 'l') return false;
+    }
+    return tiles <= 400u;
+}
 
 __device__ __forceinline__ uint32_t find_draw(const uint32_t *base, uint32_t n, uint32_t g)
 {

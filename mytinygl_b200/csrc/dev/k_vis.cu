@@ -59,15 +59,17 @@ struct VisWarp {
     float4 S[32];           /* spans: row terms t_k = B_k*y + C_k, x_left | y << 6 | triangle slot << 12 | first-pixel-in-run << 17 */
 };
 
+template <int THREADS>
 struct VisSmem {
     unsigned long long key[TILE_H * VIS_PITCH];
     uint32_t large_rec[VIS_LARGE_CAP];
-    VisWarp w[RASTER_THREADS / 32];
+    VisWarp w[THREADS / 32];
     uint32_t next_chunk;
     uint32_t large_n;
 };
-/* four CTAs per SM: 4 * (sizeof + 1 KB reserved) must fit the SM's 228 KB */
-static_assert(4 * (sizeof(VisSmem) + 1024) <= 228 * 1024, "k_vis: four tiles per SM");
+/* four 8-warp CTAs (or two 16-warp CTAs) per SM: n * (sizeof + 1 KB reserved) must fit the SM's 228 KB */
+static_assert(4 * (sizeof(VisSmem<256>) + 1024) <= 228 * 1024, "k_vis: four tiles per SM");
+static_assert(2 * (sizeof(VisSmem<512>) + 1024) <= 228 * 1024, "k_vis<512>: two tiles per SM");
 
 /* monotone map float -> uint32 (total order of the reals, -0 < +0) and back */
 __device__ __forceinline__ uint32_t ord_bits(float f)
@@ -185,11 +187,16 @@ __device__ __forceinline__ void raster_blocks(unsigned long long *keys, const Vi
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 4)
+/* THREADS = 256: four tiles per SM, the throughput shape for grids of several waves.  THREADS = 512: two tiles per SM
+ * with sixteen warps on each tile's list -- for grids of at most about one wave (a band of a multi-GPU frame), where
+ * the kernel's duration is the time of its heaviest tile. */
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_func, uint32_t all_range01)
 {
+    constexpr uint32_t NWARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char vis_smem_raw[];
-    VisSmem &sm = *reinterpret_cast<VisSmem *>(vis_smem_raw);
+    VisSmem<THREADS> &sm = *reinterpret_cast<VisSmem<THREADS> *>(vis_smem_raw);
     if (!lists_fit(b)) return;
 
     const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
@@ -216,21 +223,21 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     const int cx1 = min(clr.x1 - px0, vw), cy1 = min(clr.y1 - py0, vh);
     const bool clr_depth = clr_here && (clr.mask & G_DEPTH_BUFFER_BIT) && (planes & 2u);
     if (clr_here && (clr.mask & G_STENCIL_BUFFER_BIT) && (planes & 4u)) {
-        for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+        for (int i = threadIdx.x; i < vh * TILE_W; i += THREADS) {
             const int y = i >> 6, x = i & 63;
             if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) fb.stencil[(size_t)(py0 + y) * fb.width + px0 + x] = (uint8_t)clr.stencil;
         }
     }
     if (L == 0) {
         if (clr_depth)
-            for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+            for (int i = threadIdx.x; i < vh * TILE_W; i += THREADS) {
                 const int y = i >> 6, x = i & 63;
                 if (x >= cx0 && x < cx1 && y >= cy0 && y < cy1) fb.depth[(size_t)(py0 + y) * fb.width + px0 + x] = clr.depth;
             }
         return;
     }
     const bool clr_full = clr_depth && cx0 == 0 && cy0 == 0 && cx1 == vw && cy1 == vh;
-    for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+    for (int i = threadIdx.x; i < vh * TILE_W; i += THREADS) {
         const int y = i >> 6, x = i & 63;
         float d = 0.0f;
         if (x < vw) {
@@ -428,7 +435,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     for (uint32_t q = 0; q < nl; q++) {
         VisHead h;
         load_vis_head(h, b.records + sm.large_rec[q]);
-        raster_blocks(sm.key, mode, b, h, px0, py0, (int)((warp + 8u - (q & 7u)) & 7u), RASTER_THREADS / 32);
+        raster_blocks(sm.key, mode, b, h, px0, py0, (int)((warp + NWARPS - (q & (NWARPS - 1u))) & (NWARPS - 1u)), (int)NWARPS);
     }
     __syncthreads();
 
@@ -436,7 +443,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     const uint32_t slot_mask = (1u << CHUNK_SHIFT) - 1u;
     const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
     if (vec) {
-        for (int i = threadIdx.x; i < vh * 16; i += RASTER_THREADS) {
+        for (int i = threadIdx.x; i < vh * 16; i += THREADS) {
             const int y = i >> 4, q4 = (i & 15) * 4;
             float dv[4];
             uint32_t rv[4];
@@ -456,7 +463,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
             *reinterpret_cast<uint4 *>(b.vis_plane + p) = make_uint4(rv[0], rv[1], rv[2], rv[3]);
         }
     } else {
-        for (int i = threadIdx.x; i < vh * TILE_W; i += RASTER_THREADS) {
+        for (int i = threadIdx.x; i < vh * TILE_W; i += THREADS) {
             const int y = i >> 6, x = i & 63;
             if (x >= vw) continue;
             const unsigned long long key = sm.key[y * VIS_PITCH + x];
@@ -481,10 +488,12 @@ void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const Clear
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {      /* more than 48 KB of shared memory is a per-device opt-in */
-        cudaFuncSetAttribute(k_vis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisSmem));
+        cudaFuncSetAttribute(k_vis<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisSmem<256>));
+        cudaFuncSetAttribute(k_vis<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisSmem<512>));
         configured[dev] = true;
     }
-    k_vis<<<tiles, RASTER_THREADS, sizeof(VisSmem), s>>>(b, fb, clear, planes, depth_func, all_range01 ? 1u : 0u);
+    if (small_grid(tiles)) k_vis<512><<<tiles, 512, sizeof(VisSmem<512>), s>>>(b, fb, clear, planes, depth_func, all_range01 ? 1u : 0u);
+    else k_vis<256><<<tiles, 256, sizeof(VisSmem<256>), s>>>(b, fb, clear, planes, depth_func, all_range01 ? 1u : 0u);
     note_launch();
 }
 

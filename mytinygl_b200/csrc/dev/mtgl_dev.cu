@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -37,7 +38,19 @@ struct DevBuf {
 };
 
 struct TexObj { uint32_t *l0 = nullptr, *l1 = nullptr; int w = 0, h = 0, w1 = 0, h1 = 0; };
-struct BufObj { uint8_t *ptr = nullptr; uint64_t size = 0; };
+struct BufObj {
+    uint8_t *ptr = nullptr; uint64_t size = 0;
+    uint64_t gen = 0;               /* bumped by every write through the API */
+    uint32_t draws_since_write = 0; /* array draws that sourced positions from the unchanged content */
+    bool exposed = false;           /* mtgl_dev_buffer_pointer handed the storage out: content may change behind the API */
+};
+/* cached object-space boxes of one (buffer content, position layout, element range): k_cull.cu */
+struct BoundsEntry {
+    uint32_t buffer = 0; uint64_t gen = 0, offset = 0; uint32_t stride = 0, size = 0; int32_t first = 0; uint32_t nverts = 0;
+    DevBuf boxes; uint64_t last_use = 0;
+};
+constexpr size_t kBoundsEntries = 8;
+constexpr uint32_t kBoundsMinTriangles = 4 * SETUP_THREADS;    /* smaller draws are not worth a culling pass */
 
 } // namespace
 
@@ -53,7 +66,9 @@ struct mtgl_dev {
     float *unorm8 = nullptr;
 
     DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list, bin_rows;
-    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane;
+    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane, chunk_cull;
+    BoundsEntry bounds[kBoundsEntries];
+    uint64_t bounds_clock = 0;
     DevCounters *counters = nullptr;
     DevCounters *h_counters = nullptr;      /* pinned */
 
@@ -194,6 +209,47 @@ FrameTargets frame_targets(const mtgl_dev *d)
 
 struct PassDraw { uint32_t draw; uint32_t tri_first, tri_count; };
 
+/* Object-space chunk boxes for an array draw (k_cull.cu), or NULL when the draw does not qualify or a culling pass
+ * is not expected to pay: the boxes cost one pass over the positions, so they are computed when this device renders
+ * only a band of the frame, or when the buffer has already been drawn from unchanged (static geometry: computed once,
+ * kept until the buffer is written). */
+int chunk_bounds_for(mtgl_dev *d, const mtgl_draw &s, const float4 **out)
+{
+    *out = nullptr;
+    static const bool disabled = std::getenv("MTGL_NO_CULL") != nullptr;       /* A/B switch for profiling and tests */
+    if (disabled) return MTGL_OK;
+    const mtgl_attrib &a = s.position;
+    if (s.mode != G_TRIANGLES || s.source != MTGL_SRC_ARRAYS || s.index_type || !a.enabled || a.type != MTGL_TYPE_F32) return MTGL_OK;
+    if (a.buffer == 0 || a.buffer >= kMaxObjects || a.size < 2 || (a.stride & 3u) || (a.offset & 3u) || s.first < 0) return MTGL_OK;
+    BufObj &bo = d->buf[a.buffer];
+    const uint32_t ntris = s.count / 3u, nverts = ntris * 3u;
+    if (!bo.ptr || ntris < kBoundsMinTriangles || (((uintptr_t)bo.ptr) & 3u)) return MTGL_OK;
+    const uint64_t last = a.offset + (uint64_t)((uint32_t)s.first + nverts - 1u) * a.stride + (uint64_t)std::min<uint32_t>(a.size, 3u) * 4u;
+    if (last > bo.size) return MTGL_OK;
+    const bool band = d->band_y0 > 0 || d->band_y1 < d->height;
+    BoundsEntry *hit = nullptr, *lru = &d->bounds[0];
+    for (BoundsEntry &e : d->bounds) {
+        if (e.buffer == a.buffer && e.gen == bo.gen && e.offset == a.offset && e.stride == a.stride && e.size == a.size &&
+            e.first == s.first && e.nverts == nverts && e.boxes.ptr && !bo.exposed) hit = &e;
+        if (e.last_use < lru->last_use) lru = &e;
+    }
+    const bool is_static = bo.draws_since_write >= 1 && !bo.exposed;
+    bo.draws_since_write++;
+    if (!hit) {
+        if (!band && !is_static) return MTGL_OK;
+        const uint32_t nchunks = (ntris + SETUP_THREADS - 1) / SETUP_THREADS;
+        int rc = reserve(d, lru->boxes, (size_t)nchunks * 32);
+        if (rc != MTGL_OK) return rc;
+        launch_chunk_bounds(bo.ptr + a.offset, a.stride, a.size, s.first, nverts, (float4 *)lru->boxes.ptr, d->stream);
+        lru->buffer = a.buffer; lru->gen = bo.gen; lru->offset = a.offset; lru->stride = a.stride; lru->size = a.size;
+        lru->first = s.first; lru->nverts = nverts;
+        hit = lru;
+    }
+    hit->last_use = ++d->bounds_clock;
+    *out = (const float4 *)hit->boxes.ptr;
+    return MTGL_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -250,8 +306,9 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     }
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
-                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane };
+                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane, &d->chunk_cull };
     for (DevBuf *b : bufs) release(*b);
+    for (BoundsEntry &e : d->bounds) release(e.boxes);
     if (d->color) cudaFree(d->color);
     if (d->depth) cudaFree(d->depth);
     if (d->stencil) cudaFree(d->stencil);
@@ -284,7 +341,9 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
     if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
     BufObj &b = d->buf[id];
+    b.gen++; b.draws_since_write = 0;
     if (b.size != size || !b.ptr) {
+        b.exposed = false;
         CU(cudaStreamSynchronize(d->stream));
         if (b.ptr) CU(cudaFree(b.ptr));
         b.ptr = nullptr; b.size = 0;
@@ -305,6 +364,8 @@ int mtgl_dev_buffer_pointer(mtgl_dev *d, uint32_t id, void **ptr, uint64_t *size
     if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
     if (ptr) *ptr = d->buf[id].ptr;
     if (size) *size = d->buf[id].size;
+    d->buf[id].exposed = true;          /* the caller may write the storage directly (NCCL all-gather of a sharded upload) */
+    d->buf[id].gen++;
     return MTGL_OK;
 }
 
@@ -314,6 +375,7 @@ int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t
     BufObj &b = d->buf[id];
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    b.gen++; b.draws_since_write = 0;
     if (size) {
         CU(cudaMemcpyAsync(b.ptr + offset, data, size, cudaMemcpyHostToDevice, d->stream));
         CU(cudaStreamSynchronize(d->stream));
@@ -331,6 +393,7 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
         CU(cudaFree(b.ptr));
     }
     b.ptr = nullptr; b.size = 0;
+    b.gen++; b.draws_since_write = 0; b.exposed = false;
     return MTGL_OK;
 }
 
@@ -384,6 +447,19 @@ int mtgl_dev_texture_delete(mtgl_dev *d, uint32_t id)
 int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
 {
     if (!d || !bt) return MTGL_E_INVALID;
+    /* MTGL_TRACE_SUBMIT=1: host microseconds from entry to (a) the arena copy queued, (b) the last launch queued */
+    static const bool trace = std::getenv("MTGL_TRACE_SUBMIT") != nullptr;
+    const auto t_in = std::chrono::steady_clock::now();
+    auto t_copy = t_in;
+    struct TraceOut {
+        const bool on; const std::chrono::steady_clock::time_point &t0, &t1;
+        ~TraceOut() {
+            if (!on) return;
+            const auto t2 = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[mtgl submit] arena queued +%.1f us, all queued +%.1f us\n",
+                         std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t0).count());
+        }
+    } trace_out{ trace, t_in, t_copy };
     CU(cudaSetDevice(d->device));
     const FrameTargets fb = frame_targets(d);
     const uint32_t ntiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
@@ -406,6 +482,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         describe(d, s.position, o.position); describe(d, s.color, o.color);
         describe(d, s.texcoord, o.texcoord); describe(d, s.normal, o.normal);
         o.ntris = triangles_of(s.mode, s.count);
+        if (int brc = chunk_bounds_for(d, s, &o.bounds)) return brc;
         draws.push_back(o);
         const mtgl_state &rs = bt->states[s.raster_state];
         planes |= 1u;
@@ -486,7 +563,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     const size_t o_staged = off; if (bt->n_vertices) std::memcpy(hp + off, bt->vertices, (size_t)bt->n_vertices * sizeof(mtgl_in_vertex)); off += sz_staged;
     const size_t o_blob = off; if (bt->blob_size) std::memcpy(hp + off, bt->blob, (size_t)bt->blob_size); off += sz_blob;
 
-    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles, n_unfused; };
+    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles, n_unfused; bool any_bounds; };
     static const bool fuse_triangles = std::getenv("MTGL_NO_FUSE") == nullptr;     /* A/B switch for profiling */
     std::vector<PassInfo> infos;
     for (auto &p : passes) {
@@ -498,6 +575,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         uint32_t *vb = reinterpret_cast<uint32_t *>(hp + pi.o_vbase), *tb = reinterpret_cast<uint32_t *>(hp + pi.o_tbase);
         uint32_t v = 0, t = 0, k = 0, unfused = 0;
         for (const PassDraw &q : p) {
+            if (draws[q.draw].bounds) pi.any_bounds = true;
             DevDraw o = draws[q.draw];
             const mtgl_draw &s = bt->draws[q.draw];
             if (o.index_type) {
@@ -526,6 +604,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     }
     CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
     CU(cudaEventRecord(d->pinned_ev[slot], d->stream));
+    t_copy = std::chrono::steady_clock::now();
 
     CU(cudaEventRecord(d->ev_start, d->stream));
     d->timed = true;
@@ -575,26 +654,30 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if (need_eye && (rc = reserve(d, d->rec_eye, rec_cap * sizeof(TriEye)))) return rc;
             if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4)) ||
                 (rc = reserve(d, d->bin_rows, rec_cap * 16))) return rc;
-            if ((rc = reserve(d, d->tile_count, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_offset, (size_t)ntiles * 4)) ||
-                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4)) || (rc = reserve(d, d->tile_flags, (size_t)ntiles * 4)) ||
+            /* everything a pass starts from zero lives in one allocation (one memset per frame, not three):
+             * counters (256 B) | tile_count | tile_flags */
+            if ((rc = reserve(d, d->tile_count, 256 + (size_t)ntiles * 8)) || (rc = reserve(d, d->tile_offset, (size_t)ntiles * 4)) ||
+                (rc = reserve(d, d->tile_cursor, (size_t)ntiles * 4)) ||
                 (rc = reserve(d, d->tile_order, (size_t)ntiles * 4))) return rc;
             if ((rc = reserve(d, d->vis_plane, (size_t)d->width * d->height * 4))) return rc;
+            if (pi.any_bounds && (rc = reserve(d, d->chunk_cull, chunks))) return rc;
+            b.chunk_cull = pi.any_bounds ? (uint8_t *)d->chunk_cull.ptr : nullptr;
             b.v_clip = (float4 *)d->v_clip.ptr; b.v_color = (float4 *)d->v_color.ptr; b.v_tex = (float4 *)d->v_tex.ptr;
             b.v_epos = (float4 *)d->v_epos.ptr; b.v_enrm = (float4 *)d->v_enrm.ptr;
             b.records = (TriRecord *)d->records.ptr; b.rec_eye = (TriEye *)d->rec_eye.ptr;
             b.record_capacity = (uint32_t)std::min<size_t>(rec_cap, 0xFFFFFFFFu);
             b.chunk_base = (uint32_t *)d->chunk_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
             b.bin_rows = (uint4 *)d->bin_rows.ptr;
-            b.tile_count = (uint32_t *)d->tile_count.ptr; b.tile_offset = (uint32_t *)d->tile_offset.ptr;
+            b.counters = (DevCounters *)d->tile_count.ptr;
+            b.tile_count = (uint32_t *)((uint8_t *)d->tile_count.ptr + 256); b.tile_offset = (uint32_t *)d->tile_offset.ptr;
             b.tile_cursor = (uint32_t *)d->tile_cursor.ptr;
-            b.tile_flags = (uint32_t *)d->tile_flags.ptr;
+            b.tile_flags = b.tile_count + ntiles;
             b.tile_order = (uint32_t *)d->tile_order.ptr;
             b.vis_plane = (uint32_t *)d->vis_plane.ptr;
 
-            CU(cudaMemsetAsync(d->counters, 0, sizeof(DevCounters), d->stream));
-            CU(cudaMemsetAsync(b.tile_count, 0, (size_t)ntiles * 4, d->stream));
-            CU(cudaMemsetAsync(b.tile_flags, 0, (size_t)ntiles * 4, d->stream));
+            CU(cudaMemsetAsync(d->tile_count.ptr, 0, 256 + (size_t)ntiles * 8, d->stream));
             launch_vertex_stage(b, d->stream);
+            launch_chunk_cull(b, fb, d->stream);
             CU(cudaEventRecord(sev[1], d->stream));
             launch_setup(b, fb, d->stream);
             CU(cudaEventRecord(sev[2], d->stream));
@@ -606,7 +689,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
              * when the scan result does not fit (BatchDev::guard), and the host checks the counters AFTER queueing
              * everything -- so the GPU never idles waiting for the host; a miss re-queues fill + raster.  Multi-pass
              * batches read the count back first. */
-            CU(cudaMemcpyAsync(d->h_counters, d->counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, d->stream));
+            CU(cudaMemcpyAsync(d->h_counters, b.counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, d->stream));
             static const bool sync_lists = std::getenv("MTGL_SYNC_LISTS") != nullptr;      /* A/B switch for profiling */
             optimistic = passes.size() == 1 && !sync_lists;
             if (optimistic) {

@@ -416,6 +416,39 @@ static void scene_c4(int w, int h, int variant)
     scene_c4_draw();
 }
 
+/* Geometry far larger than the view, drawn from a static VBO twice: exercises the hierarchical chunk culling in front of
+ * set-up (k_cull.cu) -- the second frame reuses the cached chunk boxes on a single device, a band-limited device
+ * culls from the first.  The result must not depend on it.
+ * variant 0: camera inside a 8x6 grid, most Suzannes off screen on all four sides
+ *         1: + rotated about Y so that part of the grid is behind the eye (w <= 0: chunks must not be dropped blindly)
+ *         2: + viewport smaller than and offset inside the framebuffer, scissor on
+ *         3: GL_LINE polygon mode with wide lines (a triangle then touches pixels outside its vertex box: no culling)
+ *         4: position-only array (size 2: z = 0), unlit, flat colour */
+static void scene_cull(int w, int h, int variant)
+{
+    scene_c4_setup(w, h, 8 | (6 << 8));
+    glLoadIdentity();
+    if (variant == 1) { glTranslatef(0.4f, -0.2f, -1.5f); glRotatef(50.0f, 0.0f, 1.0f, 0.0f); }
+    else glTranslatef(0.7f, -0.3f, -4.5f);
+    if (variant == 2) {
+        glViewport(w / 8, h / 6, w / 2, h / 2);
+        glEnable(GL_SCISSOR_TEST);
+        glScissor(w / 5, h / 5, w / 3, h / 3);
+    }
+    if (variant == 3) { glPolygonMode(GL_FRONT_AND_BACK, GL_LINE); glLineWidth(5.0f); }
+    if (variant == 4) {
+        glDisable(GL_LIGHTING); glDisable(GL_TEXTURE_2D);
+        glDisableClientState(GL_NORMAL_ARRAY); glDisableClientState(GL_TEXTURE_COORD_ARRAY);
+        glVertexPointer(2, GL_FLOAT, 32, (const void *)0);
+        glColor3f(0.9f, 0.6f, 0.2f);
+    }
+    for (int frame = 0; frame < 2; frame++) {
+        glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+        glDrawArrays(GL_TRIANGLES, 0, g_c4.nverts);
+        if (frame == 0) glTranslatef(-0.25f, 0.1f, 0.0f);      /* the second frame is not the first one again */
+    }
+}
+
 int scene_c4_vertex_count(void) { return g_c4.nverts; }
 const void *scene_c4_host_data(void) { return g_c4.host; }
 unsigned scene_c4_vbo(void) { return g_c4.vbo; }
@@ -1077,6 +1110,7 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "lines", scene_lines },
     { "wireframe", scene_wireframe },
     { "depth_order", scene_depth_order },
+    { "cull", scene_cull },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }

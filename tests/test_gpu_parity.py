@@ -40,7 +40,9 @@ def test_exactness_report(b200, front_oracle):
 
 
 @pytest.mark.parametrize("case,split", [(("c1_suzanne", 800, 600, 0), 320), (("c4_grid", 480, 270, 3 | (2 << 8)), 100),
-                                        (("stencil", 300, 200, 0), 64), (("state_churn", 517, 389, 0), 200)])
+                                        (("stencil", 300, 200, 0), 64), (("state_churn", 517, 389, 0), 200),
+                                        (("cull", 480, 270, 0), 70), (("cull", 480, 270, 1), 135), (("cull", 480, 270, 2), 101),
+                                        (("cull", 480, 270, 3), 64), (("cull", 480, 270, 4), 200)])
 def test_cuda_bands_stitch_to_full_frame(b200, front_oracle, case, split):
     """mtgl_dev_set_band: two contexts owning complementary (not tile-aligned) bands reproduce the full frame."""
     import ctypes
@@ -72,6 +74,21 @@ def test_list_guess_miss_requeues(b200, front_oracle, case, monkeypatch):
     for a, b in zip(want[:3], got[:3]):
         assert np.array_equal(a, b)
     assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
+
+
+@pytest.mark.parametrize("shape", ["small", "large"])
+@pytest.mark.parametrize("case", [("c1_suzanne", 800, 600, 0), ("c4_grid", 960, 540, 6 | (4 << 8)), ("c4_grid", 480, 270, 3 | (2 << 8) | (1 << 16)),
+                                  ("depth_order", 517, 389, 1), ("cull", 480, 270, 1), ("c2_cube", 1920, 1080, 0)], ids=case_id)
+def test_tile_kernel_shapes(b200, front_oracle, case, shape, monkeypatch):
+    """The deferred tile kernels come in a throughput shape (k_vis<256>, k_shade<1>: grids of several waves) and a latency
+    shape (k_vis<512>, k_shade<4>: the band of a multi-GPU frame).  Both must give the same frame at any grid size."""
+    monkeypatch.setenv("MTGL_GRID_SHAPE", shape)
+    got = b200.render(*case)
+    assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
+    monkeypatch.setenv("MTGL_GRID_SHAPE", "large" if shape == "small" else "small")
+    other = b200.render(*case)
+    for a, b in zip(got[:3], other[:3]):
+        assert np.array_equal(a, b)
 
 
 def _present_child(conn, case):
