@@ -55,7 +55,9 @@ WORKLOADS = {
 class Stats(ctypes.Structure):
     _fields_ = [("vertices", ctypes.c_uint64), ("triangles_in", ctypes.c_uint64), ("triangles_setup", ctypes.c_uint64),
                 ("tile_refs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("last_batch_ms", ctypes.c_float),
-                ("stage_ms", ctypes.c_float * 5), ("raster_ms", ctypes.c_float * 3)]
+                ("stage_ms", ctypes.c_float * 5), ("raster_ms", ctypes.c_float * 3),
+                ("batches", ctypes.c_uint64), ("cum_batch_ms", ctypes.c_double), ("cum_stage_ms", ctypes.c_double * 5),
+                ("cum_raster_ms", ctypes.c_double * 3)]
 
 
 def counts_for(key):
@@ -278,39 +280,68 @@ def run_b200(args, workload):
         sampler.start()
 
     # ---- timed region 1: inputs resident in HBM ----
+    # K frames back to back.  C4/C5 are pipelined the way a render loop is: glFlush() hands each frame to the device and
+    # returns (the host prepares frame i+1 while the GPU rasterises frame i), one glFinish() ends the region; the device
+    # time is taken between two CUDA events on the library's stream.  For N > 1 the "every band has landed" all-reduce of
+    # frame i runs on torch's stream, ordered after the frame with an event, and the library's stream waits for it before
+    # frame i+1 starts -- no rank stores into the presenting GPU's plane while a frame is still being assembled there, and
+    # no host synchronisation inside the loop.  C3 flushes L2 between frames and therefore synchronises every step.
     stage = np.zeros(5)
     rstage = np.zeros(3)
     batch_ms = 0.0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dev_ms_total = 0.0
+    L.mtgl_dev_stream.restype = ctypes.c_void_p
+    L.mtgl_dev_stream.argtypes = [ctypes.c_void_p]
+    lib_stream = torch.cuda.ExternalStream(L.mtgl_dev_stream(dev), device=torch.device("cuda", local))
+    pipelined = flush is None and (world == 1 or peer)
     sync_all()
+    L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+    cum0 = (st.batches, st.cum_batch_ms, np.array(list(st.cum_stage_ms)), np.array(list(st.cum_raster_ms)))
+    dev_ms_total = 0.0
     t_wall0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        if flush is not None:
-            flush.fill_(1); torch.cuda.synchronize()
+    if pipelined:
         L.mtgl_dev_timer_mark(dev, 0)
-        frame()
-        gather()
-        L.glFinish()
+        for _ in range(args.steps):
+            frame()
+            L.glFlush()
+            if world > 1:
+                torch.cuda.current_stream().wait_event(lib_stream.record_event())
+                dist.all_reduce(token)
+                lib_stream.wait_event(torch.cuda.current_stream().record_event())
         L.mtgl_dev_timer_mark(dev, 1)
+        L.glFinish()
         ms = ctypes.c_float()
         L.mtgl_dev_timer_elapsed_ms(dev, ctypes.byref(ms))
-        dev_ms_total += ms.value
-        L.mtgl_dev_get_stats(dev, ctypes.byref(st))
-        stage += np.array(list(st.stage_ms))
-        rstage += np.array(list(st.raster_ms))
-        batch_ms += st.last_batch_ms
-    ev1.record()
+        dev_ms_total = ms.value
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            if flush is not None:
+                flush.fill_(1); torch.cuda.synchronize()
+            L.mtgl_dev_timer_mark(dev, 0)
+            frame()
+            gather()
+            L.glFinish()
+            L.mtgl_dev_timer_mark(dev, 1)
+            ms = ctypes.c_float()
+            L.mtgl_dev_timer_elapsed_ms(dev, ctypes.byref(ms))
+            dev_ms_total += ms.value
+        ev1.record()
     sync_all()
     wall_s = time.perf_counter() - t_wall0
-    # device time of the K steps: CUDA events on the library's stream around each step (flushes excluded);
-    # for N > 1 the NCCL gather runs on torch's stream, so the bracketing torch events are used instead
-    elapsed_ms = dev_ms_total if world == 1 else ev0.elapsed_time(ev1)
+    # device time of the K steps: CUDA events on the library's stream (C3: around each step, flushes excluded); the
+    # unfused NCCL gather runs on torch's stream, so the bracketing torch events are used for it instead
+    elapsed_ms = dev_ms_total if (world == 1 or pipelined) else ev0.elapsed_time(ev1)
     if dist:
         tt = torch.tensor([elapsed_ms], device=f"cuda:{local}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tt.item())
+    # per-kernel-group CUDA-event times of exactly these K frames (the library keeps them per batch and sums them up)
+    L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+    assert st.batches - cum0[0] == args.steps, (st.batches, cum0[0])
+    stage = np.array(list(st.cum_stage_ms)) - cum0[2]
+    rstage = np.array(list(st.cum_raster_ms)) - cum0[3]
+    batch_ms = st.cum_batch_ms - cum0[1]
     L.mtgl_dev_get_stats(dev, ctypes.byref(st))
     if os.environ.get("MTGL_BENCH_DEBUG"):
         print(f"[rank {rank}] stages {np.round(stage / args.steps, 4).tolist()} raster {np.round(rstage / args.steps, 4).tolist()} dev_ms {dev_ms_total / args.steps:.4f}", file=sys.stderr, flush=True)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MTGL_DEV_ABI_VERSION 3
+#define MTGL_DEV_ABI_VERSION 4
 
 /* error codes */
 #define MTGL_OK            0
@@ -221,6 +221,12 @@ typedef struct mtgl_dev_stats {
     float    stage_ms[5];       /* CUDA-event time per stage of the last batch, summed over passes:
                                    0 vertex (K1), 1 set-up (K2), 2 bin count + scan, 3 bin fill, 4 tile raster (K4/K5) */
     float    raster_ms[3];      /* stage 4 split by kernel group: 0 visibility (K4a), 1 shade (K4b), 2 general in-order kernel */
+    /* the same times summed over every batch since creation (ABI v4): a caller that pipelines frames (glFlush per frame,
+     * one glFinish at the end) reads these once instead of synchronising after each frame */
+    uint64_t batches;
+    double   cum_batch_ms;
+    double   cum_stage_ms[5];
+    double   cum_raster_ms[3];
 } mtgl_dev_stats;
 
 typedef struct mtgl_dev mtgl_dev;
@@ -286,6 +292,9 @@ int mtgl_dev_get_stats(mtgl_dev *dev, mtgl_dev_stats *out);
 /* Device-side stopwatch on the context's stream: mark(0) ... mark(1), then elapsed = CUDA-event time
  * between the two marks (waits for mark 1).  Used by bench.py to time K steps on the device. */
 int mtgl_dev_timer_mark(mtgl_dev *dev, int which);
+/* the CUDA stream (cudaStream_t) all of this context's work is queued on: lets a multi-GPU application order its own
+ * collectives against the frames with events instead of host synchronisation (bench.py) */
+void *mtgl_dev_stream(mtgl_dev *dev);
 int mtgl_dev_timer_elapsed_ms(mtgl_dev *dev, float *ms);
 const char *mtgl_dev_last_error(mtgl_dev *dev);
 int mtgl_dev_abi_version(void);

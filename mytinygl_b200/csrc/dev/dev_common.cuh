@@ -394,6 +394,7 @@ struct BatchDev {
     uint32_t *large_list;
     uint4 *bin_rows;                /* copy of every record's row 2 (bbox_min, bbox_max, state_flags, id): all the binner reads */
     DevCounters *counters;
+    DevCounters *host_counters;     /* pinned host copy, device-mapped (unified addressing): k_bin_scan publishes the counters there */
     /* binning */
     uint32_t *tile_count, *tile_offset, *tile_cursor;
     uint32_t *tile_flags;           /* bit 0: the tile references a record whose colour work cannot be deferred (general kernel);
@@ -433,6 +434,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
+void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);
 uint64_t kernel_launch_count();

@@ -179,7 +179,17 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
         if (threadIdx.x == blockDim.x - 1) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) b.counters->tile_refs = carry;
+    if (threadIdx.x == 0) {
+        b.counters->tile_refs = carry;
+        /* the host sizes the reference lists from these: written straight into its pinned, device-mapped copy (a
+         * device-to-host memcpy here costs a compute -> copy-engine -> compute round trip of ~17 us in mid-frame) */
+        if (b.host_counters) {
+            DevCounters c = *b.counters;
+            c.tile_refs = carry;
+            *b.host_counters = c;
+            __threadfence_system();
+        }
+    }
 
     /* Launch order of the tile kernels: tiles by decreasing reference count (longest-processing-time-first), a
      * STABLE counting sort over 64 linear buckets -- equal loads keep their row-major order, so a uniform frame

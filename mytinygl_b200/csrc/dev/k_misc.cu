@@ -34,6 +34,22 @@ __global__ void __launch_bounds__(256) k_mip1(const uint32_t *l0, int w, int h, 
     l1[i] = color_pack(s);
 }
 
+/* Small batch arenas (state blocks, draw records: a few KB) are pulled over PCIe by a kernel reading the pinned,
+ * device-mapped staging buffer instead of a DMA: a host-to-device memcpy between two frames' kernels costs a
+ * compute -> copy-engine -> compute round trip, several times the transfer itself. */
+__global__ void __launch_bounds__(256) k_upload(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint32_t n16)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s)
+{
+    const uint32_t n16 = (uint32_t)((bytes + 15) / 16);
+    if (!n16) return;
+    k_upload<<<min((n16 + 255u) / 256u, 148u * 4u), 256, 0, s>>>(static_cast<const uint4 *>(host_mapped), static_cast<uint4 *>(dst), n16);
+    note_launch();
+}
+
 void launch_fill_unorm8(float *table, cudaStream_t s)
 {
     k_fill_unorm8<<<1, 256, 0, s>>>(table);

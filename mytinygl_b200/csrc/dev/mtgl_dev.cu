@@ -31,6 +31,7 @@ namespace {
 
 constexpr uint32_t kMaxObjects = 257;
 constexpr uint32_t kMaxTrisPerPass = 4u << 20;
+constexpr size_t kKernelUploadMax = 1u << 20;   /* batch arenas up to this size are uploaded by k_upload (k_misc.cu) */
 
 struct DevBuf {
     void *ptr = nullptr;
@@ -76,12 +77,21 @@ struct mtgl_dev {
     size_t pinned_cap[2] = { 0, 0 };
     cudaEvent_t pinned_ev[2] = { nullptr, nullptr };
     int pinned_next = 0;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    /* stage timing of the batches in flight: a ring, so that a caller that only glFlush()es (frames pipelined behind each
+     * other, the host one batch ahead) still gets every batch's kernel times -- a set is folded into the cumulative
+     * statistics when its slot comes round again or when the statistics are read */
+    struct EvSet {
+        cudaEvent_t start = nullptr, stop = nullptr;
+        std::vector<cudaEvent_t> stage;     /* 8 per pass: K1 | K2 | count+scan | fill | raster, then [6] end of K4a, [7] end of K4b */
+        size_t passes = 0;
+        bool pending = false;
+    };
+    static constexpr int kEvSets = 4;
+    EvSet evset[kEvSets];
+    int ev_next = 0;
     cudaEvent_t counters_ev = nullptr;      /* the counters of the current pass have reached h_counters */
     bool timed = false;
     uint32_t *present = nullptr;            /* IPC-mapped colour plane of the presenting GPU (mtgl_dev_set_present_target) */
-    std::vector<cudaEvent_t> stage_ev;      /* 8 per pass of the last batch: K1 | K2 | count+scan | fill | raster, then [6] end of K4a, [7] end of K4b */
-    size_t stage_passes = 0;
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
     mtgl_dev_stats stats{};
@@ -209,6 +219,34 @@ FrameTargets frame_targets(const mtgl_dev *d)
 
 struct PassDraw { uint32_t draw; uint32_t tri_first, tri_count; };
 
+/* wait for a batch's events and add its times to the statistics (last batch + cumulative) */
+int fold_timing(mtgl_dev *d, mtgl_dev::EvSet &es)
+{
+    CU(cudaEventSynchronize(es.stop));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, es.start, es.stop));
+    mtgl_dev_stats &st = d->stats;
+    st.last_batch_ms = ms;
+    st.cum_batch_ms += ms;
+    st.batches++;
+    for (int k = 0; k < 5; k++) st.stage_ms[k] = 0.0f;
+    for (int k = 0; k < 3; k++) st.raster_ms[k] = 0.0f;
+    for (size_t p = 0; p < es.passes; p++) {
+        cudaEvent_t *sev = &es.stage[p * 8];
+        for (int k = 0; k < 5; k++) {
+            CU(cudaEventElapsedTime(&ms, sev[k], sev[k + 1]));
+            st.stage_ms[k] += ms;
+        }
+        CU(cudaEventElapsedTime(&ms, sev[4], sev[6])); st.raster_ms[0] += ms;
+        CU(cudaEventElapsedTime(&ms, sev[6], sev[7])); st.raster_ms[1] += ms;
+        CU(cudaEventElapsedTime(&ms, sev[7], sev[5])); st.raster_ms[2] += ms;
+    }
+    for (int k = 0; k < 5; k++) st.cum_stage_ms[k] += st.stage_ms[k];
+    for (int k = 0; k < 3; k++) st.cum_raster_ms[k] += st.raster_ms[k];
+    es.pending = false;
+    return MTGL_OK;
+}
+
 /* Object-space chunk boxes for an array draw (k_cull.cu), or NULL when the draw does not qualify or a culling pass
  * is not expected to pay: the boxes cost one pass over the positions, so they are computed when this device renders
  * only a band of the frame, or when the buffer has already been drawn from unchanged (static geometry: computed once,
@@ -282,9 +320,11 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
     if (ce == cudaSuccess) ce = cudaMalloc(&d->counters, sizeof(DevCounters));
     if (ce == cudaSuccess) ce = cudaMallocHost(&d->h_counters, sizeof(DevCounters));
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&d->pinned_ev[i], cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_start);
+    for (mtgl_dev::EvSet &es : d->evset) {
+        if (ce == cudaSuccess) ce = cudaEventCreate(&es.start);
+        if (ce == cudaSuccess) ce = cudaEventCreate(&es.stop);
+    }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->counters_ev, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev_stop);
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreate(&d->mark_ev[i]);
     if (ce != cudaSuccess) {
         mtgl_dev_destroy(d);
@@ -319,11 +359,13 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->pinned[i]) cudaFreeHost(d->pinned[i]);
         if (d->pinned_ev[i]) cudaEventDestroy(d->pinned_ev[i]);
     }
-    if (d->ev_start) cudaEventDestroy(d->ev_start);
+    for (mtgl_dev::EvSet &es : d->evset) {
+        if (es.start) cudaEventDestroy(es.start);
+        if (es.stop) cudaEventDestroy(es.stop);
+        for (cudaEvent_t e : es.stage) cudaEventDestroy(e);
+    }
     if (d->counters_ev) cudaEventDestroy(d->counters_ev);
-    if (d->ev_stop) cudaEventDestroy(d->ev_stop);
     if (d->present) cudaIpcCloseMemHandle(d->present);
-    for (cudaEvent_t e : d->stage_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (d->mark_ev[i]) cudaEventDestroy(d->mark_ev[i]);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
@@ -450,16 +492,19 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     /* MTGL_TRACE_SUBMIT=1: host microseconds from entry to (a) the arena copy queued, (b) the last launch queued */
     static const bool trace = std::getenv("MTGL_TRACE_SUBMIT") != nullptr;
     const auto t_in = std::chrono::steady_clock::now();
-    auto t_copy = t_in;
+    auto t_copy = t_in, t_launched = t_in;
     struct TraceOut {
-        const bool on; const std::chrono::steady_clock::time_point &t0, &t1;
+        const bool on; const std::chrono::steady_clock::time_point &t0, &t1, &t2;
         ~TraceOut() {
             if (!on) return;
-            const auto t2 = std::chrono::steady_clock::now();
-            std::fprintf(stderr, "[mtgl submit] arena queued +%.1f us, all queued +%.1f us\n",
-                         std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t0).count());
+            const auto t3 = std::chrono::steady_clock::now();
+            auto us = [&](const std::chrono::steady_clock::time_point &t) { return std::chrono::duration<double, std::micro>(t - t0).count(); };
+            static std::chrono::steady_clock::time_point last_out;
+            std::fprintf(stderr, "[mtgl submit] since last return %.1f us | arena queued +%.1f, kernels queued +%.1f, counters read +%.1f us\n",
+                         std::chrono::duration<double, std::micro>(t0 - last_out).count(), us(t1), us(t2), us(t3));
+            last_out = std::chrono::steady_clock::now();
         }
-    } trace_out{ trace, t_in, t_copy };
+    } trace_out{ trace, t_in, t_copy, t_launched };
     CU(cudaSetDevice(d->device));
     const FrameTargets fb = frame_targets(d);
     const uint32_t ntiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
@@ -602,19 +647,26 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         pi.n_draws = k; pi.n_vertices = v; pi.n_triangles = t; pi.n_unfused = unfused;
         infos.push_back(pi);
     }
-    CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
+    /* the pinned staging buffer is device-mapped (unified addressing): small arenas are read by a kernel, large ones
+     * (immediate-mode batches with millions of staged vertices) go through the copy engine.  Sizes are multiples of 256. */
+    if (arena_total <= kKernelUploadMax) launch_upload(hp, dp, arena_total, d->stream);
+    else CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
     CU(cudaEventRecord(d->pinned_ev[slot], d->stream));
     t_copy = std::chrono::steady_clock::now();
 
-    CU(cudaEventRecord(d->ev_start, d->stream));
+    mtgl_dev::EvSet &es = d->evset[d->ev_next];
+    d->ev_next = (d->ev_next + 1) % mtgl_dev::kEvSets;
+    if (es.pending && (rc = fold_timing(d, es))) return rc;     /* four batches ago: long finished */
+    CU(cudaEventRecord(es.start, d->stream));
+    es.pending = true;
     d->timed = true;
     uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0;
-    while (d->stage_ev.size() < passes.size() * 8) {
+    while (es.stage.size() < passes.size() * 8) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
-        d->stage_ev.push_back(e);
+        es.stage.push_back(e);
     }
-    d->stage_passes = passes.size();
+    es.passes = passes.size();
 
     for (size_t pidx = 0; pidx < passes.size(); pidx++) {
         const PassInfo &pi = infos[pidx];
@@ -632,7 +684,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         b.unorm8 = d->unorm8;
         b.counters = d->counters;
 
-        cudaEvent_t *sev = &d->stage_ev[pidx * 8];
+        cudaEvent_t *sev = &es.stage[pidx * 8];
         bool optimistic = false, had_triangles = false;
         CU(cudaEventRecord(sev[0], d->stream));
         ClearOp clr;
@@ -669,6 +721,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.chunk_base = (uint32_t *)d->chunk_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
             b.bin_rows = (uint4 *)d->bin_rows.ptr;
             b.counters = (DevCounters *)d->tile_count.ptr;
+            b.host_counters = d->h_counters;
             b.tile_count = (uint32_t *)((uint8_t *)d->tile_count.ptr + 256); b.tile_offset = (uint32_t *)d->tile_offset.ptr;
             b.tile_cursor = (uint32_t *)d->tile_cursor.ptr;
             b.tile_flags = b.tile_count + ntiles;
@@ -689,7 +742,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
              * when the scan result does not fit (BatchDev::guard), and the host checks the counters AFTER queueing
              * everything -- so the GPU never idles waiting for the host; a miss re-queues fill + raster.  Multi-pass
              * batches read the count back first. */
-            CU(cudaMemcpyAsync(d->h_counters, b.counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, d->stream));
+            /* (k_bin_scan has written the counters into d->h_counters, BatchDev::host_counters) */
             static const bool sync_lists = std::getenv("MTGL_SYNC_LISTS") != nullptr;      /* A/B switch for profiling */
             optimistic = passes.size() == 1 && !sync_lists;
             if (optimistic) {
@@ -733,6 +786,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         plan.unordered_range01 = unordered_range01;
         launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
         CU(cudaEventRecord(sev[5], d->stream));
+        t_launched = std::chrono::steady_clock::now();
         if (had_triangles) {
             if (optimistic) {
                 CU(cudaEventSynchronize(d->counters_ev));       /* the scan finished long ago; the raster kernels are running */
@@ -752,7 +806,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs;
         }
     }
-    CU(cudaEventRecord(d->ev_stop, d->stream));
+    CU(cudaEventRecord(es.stop, d->stream));
     CU(cudaGetLastError());
     d->stats.vertices = tot_v; d->stats.triangles_in = tot_t; d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs;
     return MTGL_OK;
@@ -833,28 +887,16 @@ int mtgl_dev_get_stats(mtgl_dev *d, mtgl_dev_stats *out)
 {
     if (!d || !out) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
-    if (d->timed) {
-        CU(cudaEventSynchronize(d->ev_stop));
-        float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, d->ev_start, d->ev_stop));
-        d->stats.last_batch_ms = ms;
-        for (int k = 0; k < 5; k++) d->stats.stage_ms[k] = 0.0f;
-        for (int k = 0; k < 3; k++) d->stats.raster_ms[k] = 0.0f;
-        for (size_t p = 0; p < d->stage_passes; p++) {
-            cudaEvent_t *sev = &d->stage_ev[p * 8];
-            for (int k = 0; k < 5; k++) {
-                CU(cudaEventElapsedTime(&ms, sev[k], sev[k + 1]));
-                d->stats.stage_ms[k] += ms;
-            }
-            CU(cudaEventElapsedTime(&ms, sev[4], sev[6])); d->stats.raster_ms[0] += ms;
-            CU(cudaEventElapsedTime(&ms, sev[6], sev[7])); d->stats.raster_ms[1] += ms;
-            CU(cudaEventElapsedTime(&ms, sev[7], sev[5])); d->stats.raster_ms[2] += ms;
-        }
+    for (int i = 0; i < mtgl_dev::kEvSets; i++) {           /* oldest first: the last one folded is the last batch */
+        mtgl_dev::EvSet &es = d->evset[(d->ev_next + i) % mtgl_dev::kEvSets];
+        if (es.pending) { int rc = fold_timing(d, es); if (rc != MTGL_OK) return rc; }
     }
     d->stats.kernel_launches = kernel_launch_count();
     *out = d->stats;
     return MTGL_OK;
 }
+
+void *mtgl_dev_stream(mtgl_dev *d) { return d ? (void *)d->stream : nullptr; }
 
 int mtgl_dev_timer_mark(mtgl_dev *d, int which)
 {

@@ -456,8 +456,19 @@ void glBufferData(GLenum target, GLsizeiptr size, const GLvoid *data, GLenum usa
     if (size <= 0) {                          /* vbo.c:126-134 */
         b->data.clear(); b->data.shrink_to_fit();
         b->has_data = false; b->host_valid = false; b->size = 0;
+        b->peeks.clear();
         mtgl_dev_buffer_data(c->dev, id, 0, nullptr);
         return;
+    }
+    if (!data) b->peeks.clear();
+    else {                                    /* the bytes the host has looked at before, from the new contents */
+        size_t keep = 0;
+        for (Buffer::Peek &p : b->peeks)
+            if (p.off + p.n <= (uint64_t)size) {
+                std::memcpy(p.raw, (const uint8_t *)data + p.off, p.n);
+                b->peeks[keep++] = p;
+            }
+        b->peeks.resize(keep);
     }
     /* fresh storage; contents undefined when data == NULL.  The HBM mirror is filled straight from the
      * caller's memory (a pinned pointer is DMA'd without a bounce); only small buffers also keep a host copy. */
@@ -489,6 +500,10 @@ void glBufferSubData(GLenum target, GLintptr offset, GLsizeiptr size, const GLvo
     if (!b->has_data || !data || (uint64_t)offset + (uint64_t)size > b->size) { set_error(c, GL_INVALID_VALUE); return; }
     flush_batch(c);
     if (b->host_valid) std::memcpy(b->data.data() + offset, data, (size_t)size);
+    for (Buffer::Peek &p : b->peeks) {        /* patch the overlapping bytes */
+        const uint64_t lo = std::max<uint64_t>(p.off, (uint64_t)offset), hi = std::min<uint64_t>(p.off + p.n, (uint64_t)offset + (uint64_t)size);
+        if (lo < hi) std::memcpy(p.raw + (lo - p.off), (const uint8_t *)data + (lo - (uint64_t)offset), (size_t)(hi - lo));
+    }
     if (mtgl_dev_buffer_sub_data(c->dev, id, (uint64_t)offset, (uint64_t)size, data) != MTGL_OK)
         set_error(c, GL_INVALID_VALUE);
 }

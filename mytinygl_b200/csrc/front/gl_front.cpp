@@ -150,7 +150,18 @@ bool buffer_read(GLState *c, GLuint id, uint64_t offset, uint64_t n, void *out)
     Buffer *b = get_buffer(c, id);
     if (!b || !b->has_data || offset + n > b->size) return false;
     if (b->host_valid) { std::memcpy(out, b->data.data() + offset, (size_t)n); return true; }
-    return mtgl_dev_buffer_read(c->dev, id, offset, n, out) == MTGL_OK;
+    if (n <= sizeof(Buffer::Peek::raw)) {
+        for (const Buffer::Peek &p : b->peeks)
+            if (p.off == offset && p.n == n) { std::memcpy(out, p.raw, (size_t)n); return true; }
+    }
+    if (mtgl_dev_buffer_read(c->dev, id, offset, n, out) != MTGL_OK) return false;      /* waits for the queued frames */
+    if (n <= sizeof(Buffer::Peek::raw)) {
+        if (b->peeks.size() >= 16) b->peeks.erase(b->peeks.begin());
+        Buffer::Peek p; p.off = offset; p.n = (uint32_t)n;
+        std::memcpy(p.raw, out, (size_t)n);
+        b->peeks.push_back(p);
+    }
+    return true;
 }
 
 DisplayList *get_list(GLState *c, GLuint id)

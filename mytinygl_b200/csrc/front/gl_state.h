@@ -63,6 +63,11 @@ struct Buffer {                         /* buffer_t, vbo.h */
     uint64_t size = 0;
     std::vector<uint8_t> data;
     GLenum usage = 0;
+    /* HBM-only buffers: the few bytes the host has looked at (the last element of an array draw becomes the current
+     * normal / colour / texture coordinate, gl_api.c:1826-1842).  Kept up to date from the caller's memory by
+     * glBufferData / glBufferSubData, so a frame loop never waits for the device to learn them again. */
+    struct Peek { uint64_t off; uint32_t n; uint8_t raw[16]; };
+    std::vector<Peek> peeks;
 };
 
 constexpr uint64_t kHostMirrorLimit = 8u << 20;   /* buffers above this keep no host copy */

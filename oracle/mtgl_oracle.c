@@ -1264,6 +1264,8 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+void *mtgl_dev_stream(mtgl_dev *d) { (void)d; return NULL; }   /* no device, no stream */
+
 int mtgl_dev_timer_mark(mtgl_dev *d, int which)
 {
     if (!d || which < 0 || which > 1) return MTGL_E_INVALID;

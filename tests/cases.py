@@ -33,6 +33,7 @@ CASES = (
     + [("depth_order", 320, 240, v) for v in (0, 1, 2, 3, 5, 6, 8, 9, 10, 11, 12, 16, 31)]
     + [("depth_order", 517, 389, 1), ("depth_order", 1280, 720, 8)]
     + [("cull", 480, 270, v) for v in range(5)]
+    + [("vbo_large", 480, 270, 0)]
 )
 
 

@@ -1085,6 +1085,74 @@ static void scene_depth_order(int w, int h, int variant)
     glEnd();
 }
 
+/* A buffer too large for a host mirror (> 8 MB): the "current" normal / colour an array draw leaves behind is the
+ * last element's (gl_api.c:1826-1842) and must follow glBufferSubData / glBufferData without the host re-reading HBM.
+ * Each step draws the (mostly degenerate) array, then an immediate-mode lit triangle that uses the current normal
+ * and a flat one that uses the current colour. */
+static void scene_vbo_large(int w, int h, int variant)
+{
+    (void)variant;
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.1f, 0.1f, 0.15f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    const int n = 240000;                                      /* 240000 x 40 B = 9.6 MB */
+    float *v = (float *)calloc((size_t)n * 10, sizeof(float)); /* pos3 normal3 colour4 */
+    for (int i = 0; i < n; i++) { v[i * 10 + 5] = 1.0f; v[i * 10 + 6] = 0.5f; v[i * 10 + 7] = 0.5f; v[i * 10 + 8] = 0.5f; v[i * 10 + 9] = 1.0f; }
+    for (int i = 0; i < 300; i++) {                            /* a fan of real triangles in front */
+        float a = 0.0209f * (float)i;
+        v[i * 10] = (i % 3 == 0) ? 0.0f : 1.2f * cosf(a); v[i * 10 + 1] = (i % 3 == 0) ? 0.0f : 1.2f * sinf(a); v[i * 10 + 2] = 0.0f;
+        v[i * 10 + 6] = 0.2f + 0.002f * (float)i;
+    }
+    GLuint vbo;
+    glGenBuffers(1, &vbo);
+    glBindBuffer(GL_ARRAY_BUFFER, vbo);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr)((size_t)n * 40), v, GL_DYNAMIC_DRAW);
+    glEnableClientState(GL_VERTEX_ARRAY);
+    glEnableClientState(GL_NORMAL_ARRAY);
+    glEnableClientState(GL_COLOR_ARRAY);
+    glVertexPointer(3, GL_FLOAT, 40, (const void *)0);
+    glNormalPointer(GL_FLOAT, 40, (const void *)12);
+    glColorPointer(4, GL_FLOAT, 40, (const void *)24);
+    GLfloat lpos[4] = { 0.3f, 0.5f, 1.0f, 0.0f }, ldif[4] = { 0.9f, 0.8f, 0.7f, 1.0f };
+    glLightfv(GL_LIGHT0, GL_POSITION, lpos);
+    glLightfv(GL_LIGHT0, GL_DIFFUSE, ldif);
+    glEnable(GL_LIGHT0);
+    for (int step = 0; step < 4; step++) {
+        float last[7] = { 0.0f, 0.0f, 1.0f, 0.5f, 0.5f, 0.5f, 1.0f };
+        if (step == 1) { last[0] = 0.6f; last[2] = 0.8f; last[3] = 0.9f; last[4] = 0.2f; }
+        if (step == 2) { last[1] = -0.6f; last[2] = 0.8f; last[3] = 0.1f; last[5] = 0.9f; }
+        if (step == 1) glBufferSubData(GL_ARRAY_BUFFER, (GLintptr)((size_t)(n - 1) * 40 + 12), 28, last);
+        if (step == 2) {                                       /* partial overlap: normal.z and the colour only */
+            glBufferSubData(GL_ARRAY_BUFFER, (GLintptr)((size_t)(n - 1) * 40 + 20), 20, last + 2);
+        }
+        if (step == 3) {                                       /* fresh contents through glBufferData */
+            v[(size_t)(n - 1) * 10 + 3] = -0.7f; v[(size_t)(n - 1) * 10 + 4] = 0.1f; v[(size_t)(n - 1) * 10 + 5] = 0.7f;
+            v[(size_t)(n - 1) * 10 + 6] = 0.3f; v[(size_t)(n - 1) * 10 + 7] = 0.9f; v[(size_t)(n - 1) * 10 + 8] = 0.4f;
+            glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr)((size_t)n * 40), v, GL_DYNAMIC_DRAW);
+        }
+        glDisable(GL_LIGHTING);
+        glLoadIdentity();
+        glTranslatef(-2.4f + 1.6f * (float)step, 1.2f, -7.0f);
+        glDrawArrays(GL_TRIANGLES, 0, n);
+        const float x = -2.4f + 1.6f * (float)step;
+        glLoadIdentity();
+        glTranslatef(x, -0.9f, -6.0f);
+        glBegin(GL_TRIANGLES);                                 /* flat: the current colour */
+        glVertex3f(-0.6f, -0.5f, 0.0f); glVertex3f(0.0f, -0.5f, 0.0f); glVertex3f(-0.3f, 0.4f, 0.0f);
+        glEnd();
+        glEnable(GL_LIGHTING);
+        glBegin(GL_TRIANGLES);                                 /* lit: the current normal */
+        glVertex3f(0.1f, -0.5f, 0.0f); glVertex3f(0.7f, -0.5f, 0.0f); glVertex3f(0.4f, 0.4f, 0.0f);
+        glEnd();
+    }
+    glDisableClientState(GL_COLOR_ARRAY);
+    glDisableClientState(GL_NORMAL_ARRAY);
+    glDisableClientState(GL_VERTEX_ARRAY);
+    glDeleteBuffers(1, &vbo);
+    free(v);
+}
+
 /* ---------------------------------------------------------------- registry */
 typedef void (*scene_fn)(int, int, int);
 static const struct { const char *name; scene_fn fn; } g_scenes[] = {
@@ -1111,6 +1179,7 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "wireframe", scene_wireframe },
     { "depth_order", scene_depth_order },
     { "cull", scene_cull },
+    { "vbo_large", scene_vbo_large },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }
