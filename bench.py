@@ -236,15 +236,19 @@ def run_b200(args, workload):
             hb = (ctypes.c_ubyte * 64)(*ht.cpu().tolist())
             rc = L.mtgl_dev_set_present_target(dev, hb)
             assert rc == 0, f"mtgl_dev_set_present_target failed ({rc})"
+        L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        dist.barrier()          # every rank has mapped the plane (and its barrier counter) before the first frame
 
     def gather():
         """colour rows of every band -> rank 0's framebuffer"""
         if world == 1:
             return
-        L.glFinish()
-        if peer:        # the stores already went to rank 0's plane; wait until every rank's frame is complete
-            dist.all_reduce(token)
+        if peer:        # the stores already went to rank 0's plane; wait until every rank's frame is complete:
+            L.glFlush()     # one barrier kernel on the library's stream behind the raster kernels, counter in rank 0's HBM
+            assert L.mtgl_dev_frame_barrier(dev, world) == 0
+            L.glFinish()
             return
+        L.glFinish()
         ops = []
         if rank == 0:
             for r in range(1, world):
@@ -282,10 +286,11 @@ def run_b200(args, workload):
     # ---- timed region 1: inputs resident in HBM ----
     # K frames back to back.  C4/C5 are pipelined the way a render loop is: glFlush() hands each frame to the device and
     # returns (the host prepares frame i+1 while the GPU rasterises frame i), one glFinish() ends the region; the device
-    # time is taken between two CUDA events on the library's stream.  For N > 1 the "every band has landed" all-reduce of
-    # frame i runs on torch's stream, ordered after the frame with an event, and the library's stream waits for it before
-    # frame i+1 starts -- no rank stores into the presenting GPU's plane while a frame is still being assembled there, and
-    # no host synchronisation inside the loop.  C3 flushes L2 between frames and therefore synchronises every step.
+    # time is taken between two CUDA events on the library's stream.  For N > 1 every frame ends with the library's frame
+    # barrier (mtgl_dev_frame_barrier: one tiny kernel per rank on the same stream, counter in the presenting GPU's HBM
+    # over NVLink): frame i+1 starts on no rank before every band of frame i has landed in rank 0's plane, and there is
+    # no host synchronisation and no NCCL call inside the loop.  C3 flushes L2 between frames and therefore synchronises
+    # every step.
     stage = np.zeros(5)
     rstage = np.zeros(3)
     batch_ms = 0.0
@@ -304,9 +309,7 @@ def run_b200(args, workload):
             frame()
             L.glFlush()
             if world > 1:
-                torch.cuda.current_stream().wait_event(lib_stream.record_event())
-                dist.all_reduce(token)
-                lib_stream.wait_event(torch.cuda.current_stream().record_event())
+                L.mtgl_dev_frame_barrier(dev, world)
         L.mtgl_dev_timer_mark(dev, 1)
         L.glFinish()
         ms = ctypes.c_float()
@@ -459,10 +462,10 @@ def run_b200(args, workload):
     if is_c3:
         group_bytes = [0, 0, 0, frag_bytes + clear_bytes]
     else:
-        group_bytes = [vertex_bytes * world, cnt["covered"] * 4 + cnt["tested"] * 4 + px * 4, cnt["tested"] * 4 + px * 4, 0]
+        group_bytes = [vertex_bytes, cnt["covered"] * 4 + cnt["tested"] * 4 + px * 4, cnt["tested"] * 4 + px * 4, 0]
         if group_bytes[gi] == 0:        # a state mix that sends C4/C5 through the general kernel
             group_bytes[gi] = frag_bytes + clear_bytes
-    raster_bytes = group_bytes[gi] / world          # one launch per rank covers 1/N of the frame (set-up: all of it)
+    raster_bytes = group_bytes[gi] / world          # one launch per rank covers 1/N of the frame (set-up: the chunks that reach its band)
     achieved = raster_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
     traffic = None
     try:

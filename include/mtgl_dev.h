@@ -287,6 +287,13 @@ int mtgl_dev_plane_pointers(mtgl_dev *dev, void **color, void **depth, void **st
 int mtgl_dev_export_color_plane(mtgl_dev *dev, void *handle_out);
 int mtgl_dev_set_present_target(mtgl_dev *dev, const void *handle);
 
+/* Frame barrier of a multi-GPU frame, queued on this context's stream behind its raster kernels: returns at once; the
+ * stream continues when all 'participants' contexts (the presenter, i.e. the one that exported its plane, and every
+ * context that mapped it) have queued the same barrier and finished the work in front of it.  The counter lives behind
+ * the presenter's colour plane, so nothing but the exported handle is needed.  Every participant must call it the same
+ * number of times after export / set_present_target; participants == 1 is a no-op.  (No reference counterpart.) */
+int mtgl_dev_frame_barrier(mtgl_dev *dev, uint32_t participants);
+
 int mtgl_dev_get_stats(mtgl_dev *dev, mtgl_dev_stats *out);
 
 /* Device-side stopwatch on the context's stream: mark(0) ... mark(1), then elapsed = CUDA-event time

@@ -434,6 +434,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
+void launch_frame_barrier(unsigned long long *counter, unsigned long long target, cudaStream_t s);
 void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);

@@ -92,6 +92,7 @@ struct mtgl_dev {
     cudaEvent_t counters_ev = nullptr;      /* the counters of the current pass have reached h_counters */
     bool timed = false;
     uint32_t *present = nullptr;            /* IPC-mapped colour plane of the presenting GPU (mtgl_dev_set_present_target) */
+    unsigned long long barrier_epoch = 0;   /* frame barriers this context has taken part in since the plane was exported / mapped */
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
     mtgl_dev_stats stats{};
@@ -203,6 +204,7 @@ void describe(const mtgl_dev *d, const mtgl_attrib &a, DevAttrib &o)
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+size_t barrier_offset(size_t pixels) { return align_up(pixels * 4, 256); }     /* byte offset of the frame-barrier line in the colour allocation */
 
 FrameTargets frame_targets(const mtgl_dev *d)
 {
@@ -313,7 +315,10 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
     size_t n = (size_t)width * (size_t)height;
     cudaError_t ce = cudaSetDevice(device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaMalloc(&d->color, n * 4);
+    /* + one 256-byte line behind the last pixel: the frame-barrier counter of a multi-GPU frame (mtgl_dev_frame_barrier),
+     * inside the allocation that mtgl_dev_export_color_plane shares, so that one IPC mapping covers both */
+    if (ce == cudaSuccess) ce = cudaMalloc(&d->color, barrier_offset(n) + 256);
+    if (ce == cudaSuccess) ce = cudaMemset((uint8_t *)d->color + barrier_offset(n), 0, 256);
     if (ce == cudaSuccess) ce = cudaMalloc(&d->depth, n * 4);
     if (ce == cudaSuccess) ce = cudaMalloc(&d->stencil, n);
     if (ce == cudaSuccess) ce = cudaMalloc(&d->unorm8, 256 * sizeof(float));
@@ -863,6 +868,9 @@ int mtgl_dev_export_color_plane(mtgl_dev *d, void *handle_out)
     CU(cudaSetDevice(d->device));
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, d->color));
+    CU(cudaStreamSynchronize(d->stream));
+    CU(cudaMemset((uint8_t *)d->color + barrier_offset((size_t)d->width * d->height), 0, 256));   /* a fresh barrier counter for the new group */
+    d->barrier_epoch = 0;
     std::memset(handle_out, 0, MTGL_IPC_HANDLE_BYTES);
     std::memcpy(handle_out, &h, sizeof h);
     return MTGL_OK;
@@ -874,12 +882,27 @@ int mtgl_dev_set_present_target(mtgl_dev *d, const void *handle)
     CU(cudaSetDevice(d->device));
     CU(cudaStreamSynchronize(d->stream));
     if (d->present) { CU(cudaIpcCloseMemHandle(d->present)); d->present = nullptr; }
+    d->barrier_epoch = 0;
     if (!handle) return MTGL_OK;
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, sizeof h);
     void *p = nullptr;
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     d->present = static_cast<uint32_t *>(p);
+    return MTGL_OK;
+}
+
+int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants)
+{
+    if (!d || participants == 0) return MTGL_E_INVALID;
+    if (participants == 1) return MTGL_OK;
+    CU(cudaSetDevice(d->device));
+    /* the counter lives behind the presenting GPU's colour plane: local for the presenter, NVLink-mapped for the others */
+    uint32_t *plane = d->present ? d->present : d->color;
+    unsigned long long *ctr = reinterpret_cast<unsigned long long *>((uint8_t *)plane + barrier_offset((size_t)d->width * d->height));
+    d->barrier_epoch++;
+    launch_frame_barrier(ctr, d->barrier_epoch * participants, d->stream);
+    CU(cudaGetLastError());
     return MTGL_OK;
 }
 

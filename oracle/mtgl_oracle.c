@@ -1264,7 +1264,8 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-void *mtgl_dev_stream(mtgl_dev *d) { (void)d; return NULL; }   /* no device, no stream */
+void *mtgl_dev_stream(mtgl_dev *d) { (void)d; return NULL; }
+int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants) { (void)d; return participants == 1 ? MTGL_OK : MTGL_E_INVALID; }   /* no device, no stream */
 
 int mtgl_dev_timer_mark(mtgl_dev *d, int which)
 {

@@ -107,6 +107,9 @@ def _present_child(conn, case):
         L.glClear(0x4000 | 0x0100 | 0x0400)
         L.glClearColor(ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(1))
         assert L.scene_render(name.encode(), w, h, variant) == 0
+        L.glFlush()
+        L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        assert L.mtgl_dev_frame_barrier(lib.device(), 2) == 0      # "my frame has landed", behind the raster kernels
         color = lib.read()[0]
         conn.send((0, color))
     else:
@@ -137,9 +140,12 @@ def test_present_target_mirrors_color(b200, case):
     proc.start()
     try:
         parent.send(list(handle))
+        # the presenter's side of the frame barrier: its stream continues once the other context's frame is complete
+        L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        assert L.mtgl_dev_frame_barrier(b200.device(), 2) == 0
+        mine = b200.read()[0]                   # queued behind the barrier: no other synchronisation with the child
         rc, theirs = parent.recv()
         assert rc == 0, f"mtgl_dev_set_present_target failed ({rc})"
-        mine = b200.read()[0]
         assert np.array_equal(mine, theirs)
     finally:
         parent.send("done")
