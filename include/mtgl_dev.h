@@ -287,6 +287,25 @@ int mtgl_dev_plane_pointers(mtgl_dev *dev, void **color, void **depth, void **st
 int mtgl_dev_export_color_plane(mtgl_dev *dev, void *handle_out);
 int mtgl_dev_set_present_target(mtgl_dev *dev, const void *handle);
 
+/* Pixel rectangles.  mtgl_dev_draw_pixels replaces the loop of glDrawPixels (gl_api.c:1286-1373):
+ * the rectangle is copied at call time and drawn in stream order behind every batch submitted so far -- no host
+ * synchronisation.  'caps' holds MTGL_CAP_ALPHA_TEST / MTGL_CAP_DEPTH_TEST / MTGL_CAP_BLEND as sampled at the call;
+ * formats: GL_RGBA, GL_RGB, GL_LUMINANCE, GL_LUMINANCE_ALPHA of unsigned bytes, rows tightly packed, first row = bottom.
+ * (x, y) is the raster position in GL window coordinates (origin bottom-left).  Rows outside the device's band are
+ * skipped.  mtgl_dev_read_pixels replaces the loop of glReadPixels (1180-1230) for GL_RGBA / GL_RGB: waits for the
+ * device, then returns width x height x bpp bytes (zeros outside the framebuffer rows, (0,0,0,255) outside its columns). */
+typedef struct mtgl_pixel_rect {
+    int32_t  x, y, width, height;
+    uint32_t format;
+    uint32_t caps;
+    uint32_t alpha_func, depth_func;   /* GL tokens */
+    float    alpha_ref;
+    uint32_t depth_mask;
+    uint32_t blend_src, blend_dst;     /* GL tokens */
+} mtgl_pixel_rect;
+int mtgl_dev_draw_pixels(mtgl_dev *dev, const mtgl_pixel_rect *rect, const void *pixels);
+int mtgl_dev_read_pixels(mtgl_dev *dev, int32_t x, int32_t y, int32_t width, int32_t height, uint32_t format, void *out);
+
 /* Frame barrier of a multi-GPU frame, queued on this context's stream behind its raster kernels: returns at once; the
  * stream continues when all 'participants' contexts (the presenter, i.e. the one that exported its plane, and every
  * context that mapped it) have queued the same barrier and finished the work in front of it.  The counter lives behind

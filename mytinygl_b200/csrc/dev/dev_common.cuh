@@ -220,6 +220,23 @@ __device__ __forceinline__ bool compare_f(uint32_t func, float a, float b)   /* 
     }
 }
 
+__device__ __forceinline__ Color4 blend_factor(uint32_t f, Color4 s, Color4 d)   /* raster.c:360-379 == drawpixels_blend_factor, gl_api.c:1266-1284 */
+{
+    switch (f) {
+    case G_ZERO: return { 0.0f, 0.0f, 0.0f, 0.0f };
+    case G_SRC_COLOR: return s;
+    case G_ONE_MINUS_SRC_COLOR: return { 1 - s.r, 1 - s.g, 1 - s.b, 1 - s.a };
+    case G_DST_COLOR: return d;
+    case G_ONE_MINUS_DST_COLOR: return { 1 - d.r, 1 - d.g, 1 - d.b, 1 - d.a };
+    case G_SRC_ALPHA: return { s.a, s.a, s.a, s.a };
+    case G_ONE_MINUS_SRC_ALPHA: return { 1 - s.a, 1 - s.a, 1 - s.a, 1 - s.a };
+    case G_DST_ALPHA: return { d.a, d.a, d.a, d.a };
+    case G_ONE_MINUS_DST_ALPHA: return { 1 - d.a, 1 - d.a, 1 - d.a, 1 - d.a };
+    case G_SRC_ALPHA_SATURATE: { float k = (s.a < (1 - d.a)) ? s.a : (1 - d.a); return { k, k, k, 1.0f }; }
+    default: return { 1.0f, 1.0f, 1.0f, 1.0f };     /* GL_ONE and the accepted-but-unimplemented GL_CONSTANT_* */
+    }
+}
+
 __device__ __forceinline__ bool compare_i(uint32_t func, int32_t a, int32_t b)   /* raster.c:407-422 */
 {
     switch (func) {
@@ -434,6 +451,8 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
+void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);
+void launch_read_pixels(const FrameTargets &fb, int32_t x, int32_t y, int32_t w, int32_t h, uint32_t bpp, uint8_t *dst, cudaStream_t s);
 void launch_frame_barrier(unsigned long long *counter, unsigned long long target, cudaStream_t s);
 void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);

@@ -78,23 +78,6 @@ __device__ __forceinline__ uint8_t stencil_apply(uint32_t op, uint8_t v, int32_t
     }
 }
 
-__device__ __forceinline__ Color4 blend_factor(uint32_t f, Color4 s, Color4 d)   /* raster.c:360-379 */
-{
-    switch (f) {
-    case G_ZERO: return { 0.0f, 0.0f, 0.0f, 0.0f };
-    case G_SRC_COLOR: return s;
-    case G_ONE_MINUS_SRC_COLOR: return { 1 - s.r, 1 - s.g, 1 - s.b, 1 - s.a };
-    case G_DST_COLOR: return d;
-    case G_ONE_MINUS_DST_COLOR: return { 1 - d.r, 1 - d.g, 1 - d.b, 1 - d.a };
-    case G_SRC_ALPHA: return { s.a, s.a, s.a, s.a };
-    case G_ONE_MINUS_SRC_ALPHA: return { 1 - s.a, 1 - s.a, 1 - s.a, 1 - s.a };
-    case G_DST_ALPHA: return { d.a, d.a, d.a, d.a };
-    case G_ONE_MINUS_DST_ALPHA: return { 1 - d.a, 1 - d.a, 1 - d.a, 1 - d.a };
-    case G_SRC_ALPHA_SATURATE: { float k = (s.a < (1 - d.a)) ? s.a : (1 - d.a); return { k, k, k, 1.0f }; }
-    default: return { 1.0f, 1.0f, 1.0f, 1.0f };     /* GL_ONE and the accepted-but-unimplemented GL_CONSTANT_* */
-    }
-}
-
 __device__ __forceinline__ float fog_factor(const RasterCfg *c, float coord)   /* raster.c:677-701 */
 {
     float f;

@@ -67,7 +67,7 @@ struct mtgl_dev {
     float *unorm8 = nullptr;
 
     DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list, bin_rows;
-    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane, chunk_cull;
+    DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane, chunk_cull, pixel_stage;
     BoundsEntry bounds[kBoundsEntries];
     uint64_t bounds_clock = 0;
     DevCounters *counters = nullptr;
@@ -351,7 +351,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     }
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
-                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane, &d->chunk_cull };
+                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane, &d->chunk_cull, &d->pixel_stage };
     for (DevBuf *b : bufs) release(*b);
     for (BoundsEntry &e : d->bounds) release(e.boxes);
     if (d->color) cudaFree(d->color);
@@ -889,6 +889,49 @@ int mtgl_dev_set_present_target(mtgl_dev *d, const void *handle)
     void *p = nullptr;
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     d->present = static_cast<uint32_t *>(p);
+    return MTGL_OK;
+}
+
+static uint32_t pixel_bpp(uint32_t format)
+{
+    switch (format) {
+    case 0x1908: return 4;      /* GL_RGBA */
+    case 0x1907: return 3;      /* GL_RGB */
+    case 0x1909: return 1;      /* GL_LUMINANCE */
+    case 0x190A: return 2;      /* GL_LUMINANCE_ALPHA */
+    default: return 0;
+    }
+}
+
+int mtgl_dev_draw_pixels(mtgl_dev *d, const mtgl_pixel_rect *rect, const void *pixels)
+{
+    if (!d || !rect || !pixels) return MTGL_E_INVALID;
+    const uint32_t bpp = pixel_bpp(rect->format);
+    if (bpp == 0 || rect->width <= 0 || rect->height <= 0) return MTGL_OK;       /* gl_api.c:1336-1338: unknown formats draw nothing */
+    CU(cudaSetDevice(d->device));
+    const size_t bytes = (size_t)rect->width * rect->height * bpp;
+    /* the staging buffer is reused in stream order (copy, kernel, next copy); growing it waits for the stream */
+    int rc = reserve(d, d->pixel_stage, bytes);
+    if (rc != MTGL_OK) return rc;
+    /* from pageable memory this returns once the driver has taken its copy: the caller may reuse 'pixels' */
+    CU(cudaMemcpyAsync(d->pixel_stage.ptr, pixels, bytes, cudaMemcpyHostToDevice, d->stream));
+    launch_draw_pixels(*rect, (const uint8_t *)d->pixel_stage.ptr, frame_targets(d), d->unorm8, d->stream);
+    CU(cudaGetLastError());
+    return MTGL_OK;
+}
+
+int mtgl_dev_read_pixels(mtgl_dev *d, int32_t x, int32_t y, int32_t width, int32_t height, uint32_t format, void *out)
+{
+    if (!d || !out) return MTGL_E_INVALID;
+    const uint32_t bpp = (format == 0x1908) ? 4u : (format == 0x1907 ? 3u : 0u);
+    if (bpp == 0 || width <= 0 || height <= 0) return MTGL_OK;                   /* other formats leave 'out' untouched */
+    CU(cudaSetDevice(d->device));
+    const size_t bytes = (size_t)width * height * bpp;
+    int rc = reserve(d, d->pixel_stage, bytes);
+    if (rc != MTGL_OK) return rc;
+    launch_read_pixels(frame_targets(d), x, y, width, height, bpp, (uint8_t *)d->pixel_stage.ptr, d->stream);
+    CU(cudaMemcpyAsync(out, d->pixel_stage.ptr, bytes, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
     return MTGL_OK;
 }
 

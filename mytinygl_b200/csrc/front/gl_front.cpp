@@ -79,11 +79,6 @@ uint32_t pack_rgba(Rgba c)
     return ((uint32_t)a << 24) | ((uint32_t)b << 16) | ((uint32_t)g << 8) | r;
 }
 
-static Rgba unpack_rgba(uint32_t p)
-{
-    return rgba((p & 0xFF) / 255.0f, ((p >> 8) & 0xFF) / 255.0f, ((p >> 16) & 0xFF) / 255.0f, ((p >> 24) & 0xFF) / 255.0f);
-}
-
 static void unit3(const float *v, float *o) /* vec3_normalize, graphics.h:54-60 */
 {
     float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
@@ -836,106 +831,31 @@ void glDrawElements(GLenum mode, GLsizei count, GLenum type, const GLvoid *indic
 
 /* ================================================================ pixel rectangles */
 void glReadPixels(GLint x, GLint y, GLsizei width, GLsizei height, GLenum format, GLenum type, GLvoid *pixels)
-{ /* gl_api.c:1180-1230 */
+{ /* gl_api.c:1180-1230.  The rectangle is flipped, cropped and repacked on the device (k_pixels.cu); only its bytes
+   * cross PCIe.  Necessarily a synchronisation point. */
     MTGL_CTX();
     if (type != GL_UNSIGNED_BYTE || !pixels) return;
-    const mtgl_framebuffer *fb = mtgl_map_framebuffer(c, MTGL_PLANE_COLOR);
-    if (!fb) return;
-    uint8_t *dst = (uint8_t *)pixels;
-    int bpp = (format == GL_RGBA) ? 4 : (format == GL_RGB ? 3 : 0);
-    for (GLsizei row = 0; row < height; row++) {
-        GLint fy = fb->height - 1 - (y + row);
-        if (fy < 0 || fy >= fb->height) {
-            if (bpp) std::memset(dst + (size_t)row * width * bpp, 0, (size_t)width * bpp);
-            continue;
-        }
-        for (GLsizei col = 0; col < width; col++) {
-            GLint sx = x + col;
-            uint8_t px[4] = { 0, 0, 0, 255 };
-            if (sx >= 0 && sx < fb->width) {
-                uint32_t p = fb->color[(size_t)fy * fb->width + sx];
-                px[0] = p & 0xFF; px[1] = (p >> 8) & 0xFF; px[2] = (p >> 16) & 0xFF; px[3] = (p >> 24) & 0xFF;
-            }
-            if (bpp) std::memcpy(dst + ((size_t)row * width + col) * bpp, px, bpp);
-        }
-    }
+    flush_batch(c);
+    if (mtgl_dev_read_pixels(c->dev, x, y, width, height, format, pixels) != MTGL_OK) set_error(c, GL_INVALID_OPERATION);
 }
 
-static bool compare_f(GLenum func, float a, float b)
-{
-    switch (func) {
-    case GL_NEVER: return false;
-    case GL_LESS: return a < b;
-    case GL_EQUAL: return a == b;
-    case GL_LEQUAL: return a <= b;
-    case GL_GREATER: return a > b;
-    case GL_NOTEQUAL: return a != b;
-    case GL_GEQUAL: return a >= b;
-    default: return true;
-    }
-}
-
-static Rgba blend_factor(GLenum f, const Rgba &s, const Rgba &d)
-{
-    switch (f) {
-    case GL_ZERO: return rgba(0, 0, 0, 0);
-    case GL_SRC_COLOR: return s;
-    case GL_ONE_MINUS_SRC_COLOR: return rgba(1 - s.r, 1 - s.g, 1 - s.b, 1 - s.a);
-    case GL_DST_COLOR: return d;
-    case GL_ONE_MINUS_DST_COLOR: return rgba(1 - d.r, 1 - d.g, 1 - d.b, 1 - d.a);
-    case GL_SRC_ALPHA: return rgba(s.a, s.a, s.a, s.a);
-    case GL_ONE_MINUS_SRC_ALPHA: return rgba(1 - s.a, 1 - s.a, 1 - s.a, 1 - s.a);
-    case GL_DST_ALPHA: return rgba(d.a, d.a, d.a, d.a);
-    case GL_ONE_MINUS_DST_ALPHA: return rgba(1 - d.a, 1 - d.a, 1 - d.a, 1 - d.a);
-    case GL_SRC_ALPHA_SATURATE: { float k = (s.a < (1 - d.a)) ? s.a : (1 - d.a); return rgba(k, k, k, 1); }
-    default: return rgba(1, 1, 1, 1);
-    }
-}
-
-/* Host-side blit (gl_api.c:1286-1373).  Not on the accelerated path: it forces a round trip of
- * the colour and depth planes through the host mirror. */
+/* glDrawPixels (gl_api.c:1286-1373) on the device: the queued draws go first (glFlush, no wait), then the rectangle
+ * with the per-fragment state sampled now; the call returns as soon as the pixels have been handed over. */
 void glDrawPixels(GLsizei width, GLsizei height, GLenum format, GLenum type, const GLvoid *pixels)
 {
     MTGL_CTX();
     if (type != GL_UNSIGNED_BYTE || !pixels || !c->raster_pos_valid) return;
-    const mtgl_framebuffer *fb = mtgl_map_framebuffer(c, MTGL_PLANE_COLOR | MTGL_PLANE_DEPTH);
-    if (!fb) return;
-    const uint8_t *src = (const uint8_t *)pixels;
-    bool alpha_on = c->caps & MTGL_CAP_ALPHA_TEST, depth_on = c->caps & MTGL_CAP_DEPTH_TEST, blend_on = c->caps & MTGL_CAP_BLEND;
-    const float pixel_depth = 0.0f;
-    int32_t ymin = fb->height, ymax = -1;
-    for (GLsizei row = 0; row < height; row++) {
-        GLint fy = fb->height - 1 - (c->raster_pos_y + row);
-        if (fy < 0 || fy >= fb->height) continue;
-        for (GLsizei col = 0; col < width; col++) {
-            GLint dx = c->raster_pos_x + col;
-            if (dx < 0 || dx >= fb->width) continue;
-            uint8_t r, g, b, a = 255;
-            size_t i = (size_t)row * width + col;
-            if (format == GL_RGBA) { r = src[i * 4]; g = src[i * 4 + 1]; b = src[i * 4 + 2]; a = src[i * 4 + 3]; }
-            else if (format == GL_RGB) { r = src[i * 3]; g = src[i * 3 + 1]; b = src[i * 3 + 2]; }
-            else if (format == GL_LUMINANCE) { r = g = b = src[i]; }
-            else if (format == GL_LUMINANCE_ALPHA) { r = g = b = src[i * 2]; a = src[i * 2 + 1]; }
-            else continue;
-            if (alpha_on && !compare_f(c->alpha_func, a / 255.0f, c->alpha_ref)) continue;
-            size_t at = (size_t)fy * fb->width + dx;
-            if (depth_on && !compare_f(c->depth_func, pixel_depth, fb->depth[at])) continue;
-            Rgba s = rgba(r / 255.0f, g / 255.0f, b / 255.0f, a / 255.0f);
-            if (blend_on) {
-                Rgba d = unpack_rgba(fb->color[at]);
-                Rgba sf = blend_factor(c->blend_src, s, d), df = blend_factor(c->blend_dst, s, d);
-                s = rgba(sat(s.r * sf.r + d.r * df.r), sat(s.g * sf.g + d.g * df.g), sat(s.b * sf.b + d.b * df.b),
-                         sat(s.a * sf.a + d.a * df.a));
-            }
-            if (depth_on && c->depth_mask) fb->depth[at] = pixel_depth;
-            fb->color[at] = pack_rgba(s);
-            if (fy < ymin) ymin = fy;
-            if (fy > ymax) ymax = fy;
-        }
-    }
-    if (ymax >= ymin &&
-        mtgl_dev_write_framebuffer(c->dev, ymin, ymax + 1, fb->color, fb->depth, nullptr) != MTGL_OK)
-        set_error(c, GL_INVALID_OPERATION);
+    if (width <= 0 || height <= 0) return;
+    flush_batch(c);
+    mtgl_pixel_rect r;
+    std::memset(&r, 0, sizeof r);
+    r.x = c->raster_pos_x; r.y = c->raster_pos_y; r.width = width; r.height = height;
+    r.format = format;
+    r.caps = c->caps & (MTGL_CAP_ALPHA_TEST | MTGL_CAP_DEPTH_TEST | MTGL_CAP_BLEND);
+    r.alpha_func = c->alpha_func; r.alpha_ref = c->alpha_ref;
+    r.depth_func = c->depth_func; r.depth_mask = c->depth_mask ? 1u : 0u;
+    r.blend_src = c->blend_src; r.blend_dst = c->blend_dst;
+    if (mtgl_dev_draw_pixels(c->dev, &r, pixels) != MTGL_OK) set_error(c, GL_INVALID_OPERATION);
 }
 
 static void raster_pos(GLState *c, float x, float y, float z) /* gl_api.c:1375-1424 */

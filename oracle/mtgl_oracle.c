@@ -1264,6 +1264,69 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* glDrawPixels, gl_api.c:1286-1373: per pixel -- row / column bounds, format expansion, alpha test on a / 255, depth
+ * test of depth 0 against the stored depth, blend with the 8-bit destination, depth write, truncating pack */
+int mtgl_dev_draw_pixels(mtgl_dev *d, const mtgl_pixel_rect *rc, const void *pixels)
+{
+    if (!d || !rc || !pixels) return MTGL_E_INVALID;
+    const uint8_t *src = (const uint8_t *)pixels;
+    const int alpha_on = (rc->caps & MTGL_CAP_ALPHA_TEST) != 0, depth_on = (rc->caps & MTGL_CAP_DEPTH_TEST) != 0;
+    const int blend_on = (rc->caps & MTGL_CAP_BLEND) != 0;
+    const uint32_t afunc = rc->alpha_func, dfunc = rc->depth_func;          /* GL tokens; unknown ones pass (1233-1264) */
+    const float pixel_depth = 0.0f;                                         /* gl_api.c:1297 */
+    for (int32_t row = 0; row < rc->height; row++) {
+        const int32_t fy = d->height - 1 - (rc->y + row);                   /* 1304-1306 */
+        if (fy < 0 || fy >= d->height || fy < d->band_y0 || fy >= d->band_y1) continue;
+        for (int32_t col = 0; col < rc->width; col++) {
+            const int32_t dx = rc->x + col;
+            if (dx < 0 || dx >= d->width) continue;
+            uint8_t r, g, b, a = 255;
+            const size_t i = (size_t)row * (size_t)rc->width + (size_t)col;
+            if (rc->format == 0x1908) { r = src[i * 4]; g = src[i * 4 + 1]; b = src[i * 4 + 2]; a = src[i * 4 + 3]; }
+            else if (rc->format == 0x1907) { r = src[i * 3]; g = src[i * 3 + 1]; b = src[i * 3 + 2]; }
+            else if (rc->format == 0x1909) { r = g = b = src[i]; }
+            else if (rc->format == 0x190A) { r = g = b = src[i * 2]; a = src[i * 2 + 1]; }
+            else continue;
+            if (alpha_on && !cmp_f(afunc, (float)a / 255.0f, rc->alpha_ref)) continue;
+            const size_t at = (size_t)fy * (size_t)d->width + (size_t)dx;
+            if (depth_on && !cmp_f(dfunc, pixel_depth, d->depth[at])) continue;
+            col4 s = { (float)r / 255.0f, (float)g / 255.0f, (float)b / 255.0f, (float)a / 255.0f };
+            if (blend_on) {                                                 /* 1359-1365 */
+                const col4 dc = col_unpack(d->color[at]);
+                const col4 sf = blend_factor(rc->blend_src, s, dc), df = blend_factor(rc->blend_dst, s, dc);
+                const col4 o = { s.r * sf.r + dc.r * df.r, s.g * sf.g + dc.g * df.g, s.b * sf.b + dc.b * df.b, s.a * sf.a + dc.a * df.a };
+                s = col_clamp(o);
+            }
+            if (depth_on && rc->depth_mask) d->depth[at] = pixel_depth;
+            d->color[at] = col_pack(s);
+        }
+    }
+    return MTGL_OK;
+}
+
+/* glReadPixels, gl_api.c:1180-1230 (GL_RGBA / GL_RGB; anything else leaves the destination untouched) */
+int mtgl_dev_read_pixels(mtgl_dev *d, int32_t x, int32_t y, int32_t width, int32_t height, uint32_t format, void *out)
+{
+    if (!d || !out) return MTGL_E_INVALID;
+    const int bpp = (format == 0x1908) ? 4 : (format == 0x1907 ? 3 : 0);
+    uint8_t *dst = (uint8_t *)out;
+    if (!bpp) return MTGL_OK;
+    for (int32_t row = 0; row < height; row++) {
+        const int32_t fy = d->height - 1 - (y + row);
+        if (fy < 0 || fy >= d->height) { memset(dst + (size_t)row * (size_t)width * (size_t)bpp, 0, (size_t)width * (size_t)bpp); continue; }
+        for (int32_t col = 0; col < width; col++) {
+            const int32_t sx = x + col;
+            uint8_t px[4] = { 0, 0, 0, 255 };
+            if (sx >= 0 && sx < d->width) {
+                const uint32_t p = d->color[(size_t)fy * (size_t)d->width + (size_t)sx];
+                px[0] = (uint8_t)(p & 0xFF); px[1] = (uint8_t)((p >> 8) & 0xFF); px[2] = (uint8_t)((p >> 16) & 0xFF); px[3] = (uint8_t)(p >> 24);
+            }
+            memcpy(dst + ((size_t)row * (size_t)width + (size_t)col) * (size_t)bpp, px, (size_t)bpp);
+        }
+    }
+    return MTGL_OK;
+}
+
 void *mtgl_dev_stream(mtgl_dev *d) { (void)d; return NULL; }
 int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants) { (void)d; return participants == 1 ? MTGL_OK : MTGL_E_INVALID; }   /* no device, no stream */
 

@@ -34,6 +34,7 @@ CASES = (
     + [("depth_order", 517, 389, 1), ("depth_order", 1280, 720, 8)]
     + [("cull", 480, 270, v) for v in range(5)]
     + [("vbo_large", 480, 270, 0)]
+    + [("pixels", 320, 240, v) for v in (0, 1, 2, 5, 7)] + [("pixels", 517, 389, 3)]
 )
 
 

@@ -1153,6 +1153,110 @@ static void scene_vbo_large(int w, int h, int variant)
     free(v);
 }
 
+/* Pixel rectangles: glRasterPos*, glDrawPixels (all four formats; alpha test, depth test against depth 0, blending,
+ * depth write) and glReadPixels (RGBA / RGB, partly outside the framebuffer), mixed with geometry before and after
+ * (gl_api.c:1180-1424).  What glReadPixels returns is drawn again elsewhere, so it is part of the image.
+ * variant bit 0: blending on for the RGBA rectangles; bit 1: depth function GL_LEQUAL instead of GL_LESS; bit 2: the
+ * raster position comes through a perspective transform (and once from behind the eye: invalid, nothing drawn) */
+static void scene_pixels(int w, int h, int variant)
+{
+    glViewport(0, 0, w, h);
+    glMatrixMode(GL_PROJECTION);
+    glLoadIdentity();
+    glOrtho(0.0, (double)w, 0.0, (double)h, -1.0, 1.0);
+    glMatrixMode(GL_MODELVIEW);
+    glLoadIdentity();
+    glClearColor(0.15f, 0.2f, 0.1f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    glEnable(GL_DEPTH_TEST);
+    glDepthFunc((variant & 2) ? GL_LEQUAL : GL_LESS);
+    /* background geometry at several depths (window depth 0.25 .. 0.75; one quad exactly at depth 0) */
+    glBegin(GL_QUADS);
+    for (int k = 0; k < 6; k++) {
+        float x0 = (float)w * 0.05f + (float)k * (float)w * 0.15f, z = (k == 3) ? 1.0f : 0.5f - 0.2f * (float)k;
+        glColor4f(0.2f + 0.12f * (float)k, 0.8f - 0.1f * (float)k, 0.3f + 0.1f * (float)(k % 3), 0.6f);
+        glVertex3f(x0, (float)h * 0.1f, z); glVertex3f(x0 + (float)w * 0.2f, (float)h * 0.1f, z);
+        glVertex3f(x0 + (float)w * 0.2f, (float)h * 0.8f, z); glVertex3f(x0, (float)h * 0.8f, z);
+    }
+    glEnd();
+
+    enum { RW = 40, RH = 24 };
+    static uint8_t rgba[RW * RH * 4], rgb[RW * RH * 3], lum[RW * RH], la[RW * RH * 2];
+    for (int y = 0; y < RH; y++)
+        for (int x = 0; x < RW; x++) {
+            int i = y * RW + x;
+            rgba[i * 4] = (uint8_t)(x * 6); rgba[i * 4 + 1] = (uint8_t)(y * 10); rgba[i * 4 + 2] = (uint8_t)(255 - x * 5);
+            rgba[i * 4 + 3] = (uint8_t)((x + y) * 4);
+            rgb[i * 3] = (uint8_t)(255 - y * 9); rgb[i * 3 + 1] = (uint8_t)(x * 3 + y * 2); rgb[i * 3 + 2] = (uint8_t)(x ^ y) * 4;
+            lum[i] = (uint8_t)((x * y) & 0xFF);
+            la[i * 2] = (uint8_t)(x * 5 + 20); la[i * 2 + 1] = (uint8_t)(((x / 4 + y / 4) & 1) ? 230 : 40);
+        }
+
+    if (variant & 4) {                               /* raster position through a perspective transform */
+        glMatrixMode(GL_PROJECTION);
+        glLoadIdentity();
+        glFrustum(-0.1 * (double)w / (double)h, 0.1 * (double)w / (double)h, -0.1, 0.1, 0.1, 100.0);
+        glMatrixMode(GL_MODELVIEW);
+        glRasterPos3f(0.4f, 0.2f, 3.0f);              /* behind the eye: invalid */
+        glDrawPixels(RW, RH, GL_RGB, GL_UNSIGNED_BYTE, rgb);
+        glRasterPos3f(-1.1f, -0.6f, -2.5f);
+        glDrawPixels(RW, RH, GL_RGB, GL_UNSIGNED_BYTE, rgb);
+        glMatrixMode(GL_PROJECTION);
+        glLoadIdentity();
+        glOrtho(0.0, (double)w, 0.0, (double)h, -1.0, 1.0);
+        glMatrixMode(GL_MODELVIEW);
+    }
+
+    /* RGBA: depth test against depth 0 (passes everywhere but over the quad at depth 0 under GL_LESS), optional blend */
+    if (variant & 1) { glEnable(GL_BLEND); glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA); }
+    glRasterPos2i(w / 2 - 10, h / 3);
+    glDrawPixels(RW, RH, GL_RGBA, GL_UNSIGNED_BYTE, rgba);
+    glEnable(GL_ALPHA_TEST);
+    glAlphaFunc(GL_GREATER, 0.3f);
+    glRasterPos2i(w / 8, h / 2);
+    glDrawPixels(RW, RH, GL_RGBA, GL_UNSIGNED_BYTE, rgba);
+    glDisable(GL_BLEND);
+    /* luminance + alpha, alpha test on, no depth test: partly off the left / bottom edge */
+    glDisable(GL_DEPTH_TEST);
+    glRasterPos2i(5, 3);
+    glDrawPixels(RW, RH, GL_LUMINANCE_ALPHA, GL_UNSIGNED_BYTE, la);
+    glDisable(GL_ALPHA_TEST);
+    /* RGB opaque across the right / top edge */
+    glRasterPos2f((float)w - 17.5f, (float)h - 10.25f);
+    glDrawPixels(RW, RH, GL_RGB, GL_UNSIGNED_BYTE, rgb);
+    /* luminance with depth test and depth write off, blended additively */
+    glEnable(GL_DEPTH_TEST);
+    glDepthMask(GL_FALSE);
+    glEnable(GL_BLEND);
+    glBlendFunc(GL_ONE, GL_ONE);
+    glRasterPos2i(w / 2 + 40, h / 2 + 10);
+    glDrawPixels(RW, RH, GL_LUMINANCE, GL_UNSIGNED_BYTE, lum);
+    glDisable(GL_BLEND);
+    glDepthMask(GL_TRUE);
+
+    /* geometry after the rectangles: hidden where a rectangle wrote depth 0 */
+    glBegin(GL_TRIANGLES);
+    glColor3f(0.9f, 0.9f, 0.2f);
+    glVertex3f((float)w * 0.1f, (float)h * 0.25f, -0.9f); glVertex3f((float)w * 0.9f, (float)h * 0.3f, -0.9f);
+    glVertex3f((float)w * 0.5f, (float)h * 0.75f, -0.9f);
+    glEnd();
+
+    /* read two rectangles back (one hanging over the left / top edges) and draw them again */
+    static uint8_t back4[48 * 32 * 4], back3[48 * 32 * 3];
+    glReadPixels(w / 2 - 24, h / 3 - 4, 48, 32, GL_RGBA, GL_UNSIGNED_BYTE, back4);
+    glReadPixels(-9, h - 20, 48, 32, GL_RGB, GL_UNSIGNED_BYTE, back3);
+    glDisable(GL_DEPTH_TEST);
+    glRasterPos2i(w - 60, 8);
+    glDrawPixels(48, 32, GL_RGBA, GL_UNSIGNED_BYTE, back4);
+    glRasterPos2i(w / 3, h - 40);
+    glDrawPixels(48, 32, GL_RGB, GL_UNSIGNED_BYTE, back3);
+    glEnable(GL_DEPTH_TEST);
+    glBegin(GL_TRIANGLES);                            /* and something on top of it all */
+    glColor3f(0.2f, 0.3f, 0.95f);
+    glVertex3f((float)w * 0.6f, 4.0f, -0.95f); glVertex3f((float)w - 4.0f, 6.0f, -0.95f); glVertex3f((float)w * 0.8f, (float)h * 0.3f, -0.95f);
+    glEnd();
+}
+
 /* ---------------------------------------------------------------- registry */
 typedef void (*scene_fn)(int, int, int);
 static const struct { const char *name; scene_fn fn; } g_scenes[] = {
@@ -1180,6 +1284,7 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "depth_order", scene_depth_order },
     { "cull", scene_cull },
     { "vbo_large", scene_vbo_large },
+    { "pixels", scene_pixels },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }
