@@ -92,11 +92,12 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
             const uint32_t tile = (uint32_t)(ty0 * fb.tiles_x + tx0);
             const uint32_t peers = __match_any_sync(single, tile);
             const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
+            uint32_t base = 0, off = 0;
+            if (PASS == 1) off = __ldg(&b.tile_offset[tile]);       /* written by k_bin_scan: in flight together with the atomic */
             if ((int)lane == leader) base = atomicAdd(PASS == 0 ? &b.tile_count[tile] : &b.tile_cursor[tile], (uint32_t)__popc(peers));
             if (PASS == 0 && tflags) atomicOr(&b.tile_flags[tile], tflags);
             base = __shfl_sync(peers, base, leader);
-            if (PASS == 1) b.tile_list[b.tile_offset[tile] + base + __popc(peers & lt_mask)] = r;
+            if (PASS == 1) b.tile_list[off + base + __popc(peers & lt_mask)] = r;
         } else if (ntiles > 1) {
             for (int ty = ty0; ty <= ty1; ty++)
                 for (int tx = tx0; tx <= tx1; tx++) {
@@ -105,8 +106,9 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
                         atomicAdd(&b.tile_count[tile], 1u);
                         if (tflags) atomicOr(&b.tile_flags[tile], tflags);
                     } else {
+                        const uint32_t off = __ldg(&b.tile_offset[tile]);
                         uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);
-                        b.tile_list[b.tile_offset[tile] + at] = r;
+                        b.tile_list[off + at] = r;
                     }
                 }
         }

@@ -49,6 +49,7 @@ struct BufObj {
 struct BoundsEntry {
     uint32_t buffer = 0; uint64_t gen = 0, offset = 0; uint32_t stride = 0, size = 0; int32_t first = 0; uint32_t nverts = 0;
     DevBuf boxes; uint64_t last_use = 0;
+    uint64_t batch = 0;             /* serial of the last batch that refers to these boxes: not evictable while it is being built */
 };
 constexpr size_t kBoundsEntries = 8;
 constexpr uint32_t kBoundsMinTriangles = 4 * SETUP_THREADS;    /* smaller draws are not worth a culling pass */
@@ -70,6 +71,7 @@ struct mtgl_dev {
     DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane, chunk_cull, pixel_stage;
     BoundsEntry bounds[kBoundsEntries];
     uint64_t bounds_clock = 0;
+    uint64_t batch_serial = 0;
     DevCounters *counters = nullptr;
     DevCounters *h_counters = nullptr;      /* pinned */
 
@@ -267,16 +269,18 @@ int chunk_bounds_for(mtgl_dev *d, const mtgl_draw &s, const float4 **out)
     const uint64_t last = a.offset + (uint64_t)((uint32_t)s.first + nverts - 1u) * a.stride + (uint64_t)std::min<uint32_t>(a.size, 3u) * 4u;
     if (last > bo.size) return MTGL_OK;
     const bool band = d->band_y0 > 0 || d->band_y1 < d->height;
-    BoundsEntry *hit = nullptr, *lru = &d->bounds[0];
+    /* boxes an earlier draw of the batch being built refers to are neither evicted nor recomputed: its culling pass has
+     * not run yet */
+    BoundsEntry *hit = nullptr, *lru = nullptr;
     for (BoundsEntry &e : d->bounds) {
         if (e.buffer == a.buffer && e.gen == bo.gen && e.offset == a.offset && e.stride == a.stride && e.size == a.size &&
-            e.first == s.first && e.nverts == nverts && e.boxes.ptr && !bo.exposed) hit = &e;
-        if (e.last_use < lru->last_use) lru = &e;
+            e.first == s.first && e.nverts == nverts && e.boxes.ptr && (!bo.exposed || e.batch == d->batch_serial)) hit = &e;
+        if (e.batch != d->batch_serial && (!lru || e.last_use < lru->last_use)) lru = &e;
     }
     const bool is_static = bo.draws_since_write >= 1 && !bo.exposed;
     bo.draws_since_write++;
     if (!hit) {
-        if (!band && !is_static) return MTGL_OK;
+        if ((!band && !is_static) || !lru) return MTGL_OK;
         const uint32_t nchunks = (ntris + SETUP_THREADS - 1) / SETUP_THREADS;
         int rc = reserve(d, lru->boxes, (size_t)nchunks * 32);
         if (rc != MTGL_OK) return rc;
@@ -286,6 +290,7 @@ int chunk_bounds_for(mtgl_dev *d, const mtgl_draw &s, const float4 **out)
         hit = lru;
     }
     hit->last_use = ++d->bounds_clock;
+    hit->batch = d->batch_serial;
     *out = (const float4 *)hit->boxes.ptr;
     return MTGL_OK;
 }
@@ -514,6 +519,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     const FrameTargets fb = frame_targets(d);
     const uint32_t ntiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
 
+    d->batch_serial++;
     /* ---- validate + per-draw prefix tables ---- */
     std::vector<DevDraw> draws;
     draws.reserve(bt->n_draws);
