@@ -57,7 +57,7 @@ class Stats(ctypes.Structure):
                 ("tile_refs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("last_batch_ms", ctypes.c_float),
                 ("stage_ms", ctypes.c_float * 5), ("raster_ms", ctypes.c_float * 3),
                 ("batches", ctypes.c_uint64), ("cum_batch_ms", ctypes.c_double), ("cum_stage_ms", ctypes.c_double * 5),
-                ("cum_raster_ms", ctypes.c_double * 3)]
+                ("cum_raster_ms", ctypes.c_double * 3), ("chunks_culled", ctypes.c_uint64)]
 
 
 def counts_for(key):
@@ -497,6 +497,7 @@ def run_b200(args, workload):
         "stages_ms": {k: float(v / args.steps) for k, v in zip(["vertex", "setup", "bin_count_scan", "bin_fill", "raster"], stage)},
         "raster_ms": {k: float(v / args.steps) for k, v in zip(["visibility", "shade", "general"], rstage)},
         "batch_ms": batch_ms / args.steps, "wall_ms_per_step": wall_s * 1e3 / args.steps,
+        "chunks_culled_rank0": int(st.chunks_culled), "chunks": (cnt["vertices"] // 3 + 255) // 256,
         "cpu_baseline": cpu,
     }
     return out

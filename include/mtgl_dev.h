@@ -227,6 +227,7 @@ typedef struct mtgl_dev_stats {
     double   cum_batch_ms;
     double   cum_stage_ms[5];
     double   cum_raster_ms[3];
+    uint64_t chunks_culled;     /* 256-triangle chunks the culling pass dropped, last batch (k_cull.cu) */
 } mtgl_dev_stats;
 
 typedef struct mtgl_dev mtgl_dev;

@@ -158,7 +158,8 @@ struct DevCounters {
     unsigned int tile_refs;      /* total (record, tile) references = list length */
     unsigned int triangles_in;
     unsigned int overflow;
-    unsigned int pad_[3];
+    unsigned int culled_chunks;  /* 256-triangle chunks dropped by the culling pass (k_cull.cu) */
+    unsigned int pad_[2];
 };
 
 struct Color4 { float r, g, b, a; };

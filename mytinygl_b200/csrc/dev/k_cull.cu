@@ -138,9 +138,12 @@ __global__ void __launch_bounds__(256) k_chunk_cull(BatchDev b, FrameTargets fb,
         sx_min = fminf(sx_min, __shfl_xor_sync(0xFFFFFFFFu, sx_min, o)); sx_max = fmaxf(sx_max, __shfl_xor_sync(0xFFFFFFFFu, sx_max, o));
         sy_min = fminf(sy_min, __shfl_xor_sync(0xFFFFFFFFu, sy_min, o)); sy_max = fmaxf(sy_max, __shfl_xor_sync(0xFFFFFFFFu, sy_max, o));
     }
-    if (k == 0 && c < nchunks)
-        b.chunk_cull[c] = (all_ok && (sy_max < (float)fb.band_y0 || sy_min > (float)(fb.band_y1 - 1) ||
-                                      sx_max < 0.0f || sx_min > (float)(fb.width - 1))) ? 1 : 0;
+    if (k == 0 && c < nchunks) {
+        const bool cull = all_ok && (sy_max < (float)fb.band_y0 || sy_min > (float)(fb.band_y1 - 1) ||
+                                     sx_max < 0.0f || sx_min > (float)(fb.width - 1));
+        b.chunk_cull[c] = cull ? 1 : 0;
+        if (cull) atomicAdd(&b.counters->culled_chunks, 1u);        /* statistics only */
+    }
 }
 
 void launch_chunk_bounds(const uint8_t *pos, uint32_t stride, uint32_t size, int32_t first, uint32_t nverts, float4 *out, cudaStream_t s)

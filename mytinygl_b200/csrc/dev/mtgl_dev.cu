@@ -671,7 +671,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     CU(cudaEventRecord(es.start, d->stream));
     es.pending = true;
     d->timed = true;
-    uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0;
+    uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0, tot_culled = 0;
     while (es.stage.size() < passes.size() * 8) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
@@ -815,11 +815,13 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
                 }
             }
             tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs;
+            tot_culled += d->h_counters->culled_chunks;
         }
     }
     CU(cudaEventRecord(es.stop, d->stream));
     CU(cudaGetLastError());
     d->stats.vertices = tot_v; d->stats.triangles_in = tot_t; d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs;
+    d->stats.chunks_culled = tot_culled;
     return MTGL_OK;
 }
 

@@ -32,7 +32,7 @@ CASES = (
     + [("wireframe", 400, 300, v) for v in (0, 1, 2, 3, 4, 5, 8)]
     + [("depth_order", 320, 240, v) for v in (0, 1, 2, 3, 5, 6, 8, 9, 10, 11, 12, 16, 31)]
     + [("depth_order", 517, 389, 1), ("depth_order", 1280, 720, 8)]
-    + [("cull", 480, 270, v) for v in range(5)]
+    + [("cull", 480, 270, v) for v in range(6)]
     + [("vbo_large", 480, 270, 0)]
     + [("pixels", 320, 240, v) for v in (0, 1, 2, 5, 7)] + [("pixels", 517, 389, 3)]
 )

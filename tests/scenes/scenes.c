@@ -423,12 +423,14 @@ static void scene_c4(int w, int h, int variant)
  *         1: + rotated about Y so that part of the grid is behind the eye (w <= 0: chunks must not be dropped blindly)
  *         2: + viewport smaller than and offset inside the framebuffer, scissor on
  *         3: GL_LINE polygon mode with wide lines (a triangle then touches pixels outside its vertex box: no culling)
- *         4: position-only array (size 2: z = 0), unlit, flat colour */
+ *         4: position-only array (size 2: z = 0), unlit, flat colour
+ *         5: camera close to the grid plane: two or three Suzannes fill the view, the rest is off screen but in front */
 static void scene_cull(int w, int h, int variant)
 {
     scene_c4_setup(w, h, 8 | (6 << 8));
     glLoadIdentity();
     if (variant == 1) { glTranslatef(0.4f, -0.2f, -1.5f); glRotatef(50.0f, 0.0f, 1.0f, 0.0f); }
+    else if (variant == 5) glTranslatef(0.9f, 0.4f, -1.6f);
     else glTranslatef(0.7f, -0.3f, -4.5f);
     if (variant == 2) {
         glViewport(w / 8, h / 6, w / 2, h / 2);

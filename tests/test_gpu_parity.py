@@ -76,6 +76,32 @@ def test_list_guess_miss_requeues(b200, front_oracle, case, monkeypatch):
     assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
 
 
+def test_chunk_culling_engages(b200):
+    """The culling pass in front of set-up (k_cull.cu) must actually drop chunks: on a band from the first frame, on a
+    whole frame from the second draw of an unchanged buffer (the `cull` scene draws twice; in variant 5 most of its grid is
+    off screen).
+    That the result does not depend on it is what test_cuda_matches_oracle / test_cuda_bands_stitch check."""
+    import ctypes
+
+    class Stats(ctypes.Structure):
+        _fields_ = [("u64", ctypes.c_uint64 * 5), ("f", ctypes.c_float * 9), ("batches", ctypes.c_uint64), ("d", ctypes.c_double * 9),
+                    ("chunks_culled", ctypes.c_uint64)]
+    L = b200.lib
+    L.mtgl_dev_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+    L.mtgl_dev_set_band.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    st = Stats()
+    for band, variant in ((None, 5), ((0, 64), 0)):
+        b200.create(480, 270)
+        if band:
+            assert L.mtgl_dev_set_band(b200.device(), *band) == 0
+        assert L.scene_render(b"cull", 480, 270, variant) == 0
+        L.glFinish()
+        assert L.mtgl_dev_get_stats(b200.device(), ctypes.byref(st)) == 0
+        b200.destroy()
+        # 8x6 Suzannes = 46464 triangles = 182 chunks; the stats are those of the last batch (the second frame)
+        assert st.chunks_culled > 40, (band, st.chunks_culled)
+
+
 @pytest.mark.parametrize("shape", ["small", "large"])
 @pytest.mark.parametrize("case", [("c1_suzanne", 800, 600, 0), ("c4_grid", 960, 540, 6 | (4 << 8)), ("c4_grid", 480, 270, 3 | (2 << 8) | (1 << 16)),
                                   ("depth_order", 517, 389, 1), ("cull", 480, 270, 1), ("c2_cube", 1920, 1080, 0)], ids=case_id)
