@@ -159,6 +159,29 @@ def band_rows(height, rank, world):
     return min(lo * 64, height), min(hi * 64, height)
 
 
+def rebalanced(bounds, times, height, quantum=16):
+    """New band boundaries from the ranks' last frame times: cost density taken as uniform inside each current band,
+    boundaries moved (half way, for stability) to where the cumulative cost reaches k/N of the total, snapped to
+    `quantum` rows.  Every rank computes the same result from the same gathered times."""
+    n = len(times)
+    dens = [t / max(b1 - b0, 1) for t, b0, b1 in zip(times, bounds[:-1], bounds[1:])]
+    total = sum(times)
+    out = [0]
+    r, acc = 0, 0.0
+    for k in range(1, n):
+        want = total * k / n
+        while r < n - 1 and acc + times[r] < want:
+            acc += times[r]
+            r += 1
+        row = bounds[r] + (want - acc) / max(dens[r], 1e-12)
+        row = 0.5 * (row + bounds[k])                       # damped
+        row = int(round(row / quantum)) * quantum
+        row = max(out[-1] + quantum, min(row, height - (n - k) * quantum))
+        out.append(row)
+    out.append(height)
+    return out
+
+
 class DevTensor:
     """Zero-copy torch view of a device allocation owned by the C library."""
 
@@ -196,7 +219,8 @@ def run_b200(args, workload):
     L.scene_c4_host_data.restype = ctypes.c_void_p
     L.scene_c4_vbo.restype = ctypes.c_uint
 
-    y0, y1 = band_rows(h, rank, world)
+    bounds = [band_rows(h, r, world)[0] for r in range(world)] + [h]     # band r = rows [bounds[r], bounds[r + 1])
+    y0, y1 = bounds[rank], bounds[rank + 1]
     if world > 1:
         assert L.mtgl_dev_set_band(dev, y0, y1) == 0
     elif os.environ.get("MTGL_BENCH_BAND"):      # diagnostics: one GPU plays rank r of n ("r/n"); the line is not a bench value
@@ -252,7 +276,7 @@ def run_b200(args, workload):
         ops = []
         if rank == 0:
             for r in range(1, world):
-                a, b = band_rows(h, r, world)
+                a, b = bounds[r], bounds[r + 1]
                 if b > a:
                     ops.append(dist.P2POp(dist.irecv, color_dev[a * w * 4:b * w * 4], r))
         elif y1 > y0:
@@ -277,6 +301,34 @@ def run_b200(args, workload):
     sync_all()
 
     st = Stats()
+    # Load-balanced bands (N > 1, frames that start with a full clear -- depth and stencil of rows that change owner are
+    # not exchanged): the uniform split gives the ranks in the middle of C4's grid ~35 % more work than the ones that own
+    # the margins.  Ten untimed feedback rounds move the boundaries (16-row quantum) towards equal device time per rank;
+    # the best split seen is kept.  The assembled frame is checked against a single-GPU render after the timed loops.
+    balance_log = None
+    if world > 1 and not is_c3 and not args.uniform_bands:
+        best = (float("inf"), list(bounds))
+        balance_log = []
+        for it in range(10):
+            if it:
+                frame(); gather()
+                sync_all()
+            frame(); gather()
+            sync_all()
+            L.mtgl_dev_get_stats(dev, ctypes.byref(st))
+            tt = torch.tensor([float(st.last_batch_ms)], device=f"cuda:{local}")
+            allt = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(allt, tt)
+            times = [float(x.item()) for x in allt]
+            balance_log.append({"bounds": list(bounds), "max_ms": max(times)})
+            if max(times) < best[0]:
+                best = (max(times), list(bounds))
+            bounds = rebalanced(bounds, times, h) if it < 9 else best[1]
+            y0, y1 = bounds[rank], bounds[rank + 1]
+            assert L.mtgl_dev_set_band(dev, y0, y1) == 0
+        frame(); gather()
+        sync_all()
+
     L.mtgl_dev_get_stats(dev, ctypes.byref(st))
     launches0 = st.kernel_launches
     sampler = ClockSampler(local)
@@ -483,6 +535,7 @@ def run_b200(args, workload):
         "config": {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3,
                    "covered_fragments": cnt["covered"], "depth_passing_fragments": cnt["tested"], "shaded_fragments": cnt["shaded"],
                    "partition": f"sort-first bands x{world}" + ("" if world == 1 else (", fused NVLink peer-store gather" if peer else ", NCCL send/recv gather")),
+                   "band_rows": bounds if world > 1 else None, "band_balance": balance_log,
                    "gather_check": gather_check,
                    "l2": "flushed between frames (256 MiB fill)" if is_c3 else "inputs larger than L2 (>330 MB streamed per frame)"},
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -511,6 +564,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--uniform-bands", action="store_true", help="N > 1: keep the uniform split of tile rows (no load balancing)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'nccl' = send/recv after the frame")
     args = ap.parse_args()
