@@ -17,7 +17,7 @@ namespace mtgl_dev_impl {
 struct LevelTaps {
     uint32_t t00, t10, t01, t11;
     float fx, fy;
-    uint32_t mode;          /* 0 = single texel in t00, 1 = bilinear, 2 = opaque white (missing level 1) */
+    uint32_t mode;          /* 0 = single texel in t00, 1 = bilinear, 2 = opaque white (missing level 1), 3 = not sampled (weight 0) */
 };
 
 struct TexTaps {
@@ -85,7 +85,10 @@ __device__ __forceinline__ void tex_taps(TexTaps &T, const RasterCfg *c, float u
         if (lod > 0.0f) {
             T.cl = (lod > 1.0f) ? 1.0f : lod;
             T.tri = true;
-            level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter != G_NEAREST_MIPMAP_LINEAR);
+            /* lod >= 1: the blend of textures.c:512-515 is c0 * (1 - 1) + c1 * 1 with c0 in [0, 1]: c0 * 0 is +0 and
+             * +0 + c1 is c1, bit for bit -- level 0 does not have to be fetched or filtered at all */
+            if (T.cl == 1.0f) T.a.mode = 3;
+            else level_taps(T.a, c->tex_l0, c->tex_w, c->tex_h, rep_s, rep_t, u, v, filter != G_NEAREST_MIPMAP_LINEAR);
             mip1_taps(T.b, c, u, v, filter);
             return;
         }
@@ -103,6 +106,7 @@ __device__ __forceinline__ uint32_t level_channel(const LevelTaps &L, int sh, co
 {   /* bilinear_filter, textures.c:294-307: lerp horizontally, then vertically, truncate to 8 bits */
     if (L.mode == 0) return (L.t00 >> sh) & 0xFFu;
     if (L.mode == 2) return 0xFFu;
+    if (L.mode == 3) return 0u;         /* not sampled: its weight in the trilinear blend is exactly 0 (tex_taps), any finite value does */
     float c00 = un[(L.t00 >> sh) & 0xFFu], c10 = un[(L.t10 >> sh) & 0xFFu];
     float c01 = un[(L.t01 >> sh) & 0xFFu], c11 = un[(L.t11 >> sh) & 0xFFu];
     float sx = 1.0f - L.fx, sy = 1.0f - L.fy;
