@@ -61,14 +61,13 @@ __device__ __forceinline__ TileRange tile_range(const TriRecord *r, const FrameT
 
 /* pass = 0: count references per tile; pass = 1: write them through the per-tile cursors */
 template <int PASS>
-__global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
+__device__ __forceinline__ void bin_small(const BatchDev &b, const FrameTargets &fb, uint32_t block, uint32_t nblocks)
 {
-    if (PASS == 1 && !lists_fit(b)) return;
     const uint32_t n = b.counters->records;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     /* whole warps iterate together so that the warp-level aggregation below sees a full mask */
-    for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; r0 < n; r0 += gridDim.x * blockDim.x) {
+    for (uint32_t r0 = (block * blockDim.x + threadIdx.x) & ~31u; r0 < n; r0 += nblocks * blockDim.x) {
         const uint32_t r = r0 + lane;
         int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1, ntiles = 0;
         uint32_t tflags = 0;      /* bit 0: needs in-order shading, bit 1: not in the unordered class */
@@ -116,11 +115,10 @@ __global__ void __launch_bounds__(256) k_bin_small(BatchDev b, FrameTargets fb)
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
+__device__ __forceinline__ void bin_large(const BatchDev &b, const FrameTargets &fb, uint32_t block, uint32_t nblocks)
 {
-    if (PASS == 1 && !lists_fit(b)) return;
     const uint32_t n = b.counters->large_count;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (uint32_t i = block; i < n; i += nblocks) {
         const uint32_t r = b.large_list[i];
         const TriRecord *rec = b.records + r;
         TileRange tr = tile_range(rec, fb);
@@ -144,6 +142,23 @@ __global__ void __launch_bounds__(128) k_bin_large(BatchDev b, FrameTargets fb)
             }
         }
     }
+}
+
+constexpr uint32_t BIN_SMALL_BLOCKS = 148 * 8, BIN_LARGE_BLOCKS = 148 * 4;
+
+/* pass 0 for the cooperative binner alone (the count pass of the small records is fused into k_setup) */
+__global__ void __launch_bounds__(128) k_bin_large_count(BatchDev b, FrameTargets fb)
+{
+    bin_large<0>(b, fb, blockIdx.x, gridDim.x);
+}
+
+/* pass 1, one launch: the first BIN_SMALL_BLOCKS CTAs fill in the records that touch at most LARGE_TILES tiles, the
+ * rest go through the list of large records together */
+__global__ void __launch_bounds__(256) k_bin_fill(BatchDev b, FrameTargets fb)
+{
+    if (!lists_fit(b)) return;
+    if (blockIdx.x < BIN_SMALL_BLOCKS) bin_small<1>(b, fb, blockIdx.x, BIN_SMALL_BLOCKS);
+    else bin_large<1>(b, fb, blockIdx.x - BIN_SMALL_BLOCKS, BIN_LARGE_BLOCKS);
 }
 
 /* exclusive scan of the per-tile counts (one CTA; at most 256x256 tiles for a 16384^2 framebuffer) */
@@ -261,12 +276,9 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
     }
 }
 
-static int bin_grid() { return 148 * 8; }
-
 void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 {
-    /* the count pass of the small records is fused into k_setup; only the cooperative binner remains */
-    k_bin_large<0><<<148 * 4, 128, 0, s>>>(b, fb);
+    k_bin_large_count<<<BIN_LARGE_BLOCKS, 128, 0, s>>>(b, fb);
     note_launch();
 }
 
@@ -278,9 +290,8 @@ void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 
 void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 {
-    k_bin_small<1><<<bin_grid(), 256, 0, s>>>(b, fb);
-    k_bin_large<1><<<148 * 4, 128, 0, s>>>(b, fb);
-    note_launch(); note_launch();
+    k_bin_fill<<<BIN_SMALL_BLOCKS + BIN_LARGE_BLOCKS, 256, 0, s>>>(b, fb);
+    note_launch();
 }
 
 } // namespace mtgl_dev_impl
