@@ -199,6 +199,7 @@ def run_b200(args, workload):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     key, w, h, variant = WORKLOADS[workload]
