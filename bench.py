@@ -199,7 +199,6 @@ def run_b200(args, workload):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     key, w, h, variant = WORKLOADS[workload]
@@ -574,7 +573,17 @@ def main():
         if rank == 0:
             print(json.dumps(run_reference(args, args.workload)), flush=True)
         return
-    out = run_b200(args, args.workload)
+    # stdout carries the one JSON line and nothing else: whatever the libraries underneath print there while the bench
+    # runs (NCCL's version banner, for one) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_b200(args, args.workload)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if out is not None:
         print(json.dumps(out), flush=True)
 
