@@ -46,6 +46,10 @@ const mtgl_framebuffer *mtgl_map_framebuffer(GLState *ctx, unsigned planes);
  * plane pointers, band ownership or timing counters. */
 struct mtgl_dev *mtgl_context_device(GLState *ctx);
 
+/* Display-list geometry drawn as compiled array draws so far (glBegin ... glEnd stretches of a list that were queued as
+ * one draw record instead of being replayed call by call) -- for tools and tests. */
+uint64_t mtgl_context_list_runs_drawn(GLState *ctx);
+
 /* Select the CUDA ordinal used by contexts created afterwards on this thread (-1 = current). */
 void mtgl_set_device(int ordinal);
 

@@ -243,6 +243,11 @@ void mtgl_dev_destroy(mtgl_dev *dev);
  * rows [y0, y1).  Default is the whole framebuffer.  (No reference counterpart.) */
 int mtgl_dev_set_band(mtgl_dev *dev, int32_t y0, int32_t y1);
 
+/* Buffer ids: 1..256 are glGenBuffers names (vbo.h:17); ids MTGL_LIST_BUFFER_BASE + list (1..1024) belong to the front
+ * end, which keeps the vertices of compiled display-list geometry there. */
+#define MTGL_LIST_BUFFER_BASE 256u
+#define MTGL_MAX_BUFFER_IDS   (257u + 1024u)
+
 /* buffer_data / buffer_sub_data / buffer_delete (vbo.c:120-158, 96-110): device mirror of a
  * buffer object so that array draws fetch attributes on the device. */
 int mtgl_dev_buffer_data(mtgl_dev *dev, uint32_t id, uint64_t size, const void *data);

@@ -29,7 +29,8 @@ using namespace mtgl_dev_impl;
 
 namespace {
 
-constexpr uint32_t kMaxObjects = 257;
+constexpr uint32_t kMaxObjects = 257;               /* textures */
+constexpr uint32_t kMaxBuffers = MTGL_MAX_BUFFER_IDS; /* glGenBuffers names + the front end's display-list buffers */
 constexpr uint32_t kMaxTrisPerPass = 4u << 20;
 constexpr size_t kKernelUploadMax = 1u << 20;   /* batch arenas up to this size are uploaded by k_upload (k_misc.cu) */
 
@@ -64,7 +65,7 @@ struct mtgl_dev {
     float *depth = nullptr;
     uint8_t *stencil = nullptr;
     TexObj tex[kMaxObjects];
-    BufObj buf[kMaxObjects];
+    BufObj buf[kMaxBuffers];
     float *unorm8 = nullptr;
 
     DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list, bin_rows;
@@ -199,7 +200,7 @@ void describe(const mtgl_dev *d, const mtgl_attrib &a, DevAttrib &o)
     o.enabled = a.enabled;
     if (!a.enabled) return;
     o.stride = a.stride; o.size = a.size; o.type = a.type;
-    if (a.buffer != 0 && a.buffer < kMaxObjects && d->buf[a.buffer].ptr && a.offset <= d->buf[a.buffer].size) {
+    if (a.buffer != 0 && a.buffer < kMaxBuffers && d->buf[a.buffer].ptr && a.offset <= d->buf[a.buffer].size) {
         o.ptr = d->buf[a.buffer].ptr + a.offset;
         o.avail = d->buf[a.buffer].size - a.offset;
     }
@@ -262,7 +263,7 @@ int chunk_bounds_for(mtgl_dev *d, const mtgl_draw &s, const float4 **out)
     if (disabled) return MTGL_OK;
     const mtgl_attrib &a = s.position;
     if (s.mode != G_TRIANGLES || s.source != MTGL_SRC_ARRAYS || s.index_type || !a.enabled || a.type != MTGL_TYPE_F32) return MTGL_OK;
-    if (a.buffer == 0 || a.buffer >= kMaxObjects || a.size < 2 || (a.stride & 3u) || (a.offset & 3u) || s.first < 0) return MTGL_OK;
+    if (a.buffer == 0 || a.buffer >= kMaxBuffers || a.size < 2 || (a.stride & 3u) || (a.offset & 3u) || s.first < 0) return MTGL_OK;
     BufObj &bo = d->buf[a.buffer];
     const uint32_t ntris = s.count / 3u, nverts = ntris * 3u;
     if (!bo.ptr || ntris < kBoundsMinTriangles || (((uintptr_t)bo.ptr) & 3u)) return MTGL_OK;
@@ -353,8 +354,9 @@ void mtgl_dev_destroy(mtgl_dev *d)
     for (uint32_t i = 0; i < kMaxObjects; i++) {
         if (d->tex[i].l0) cudaFree(d->tex[i].l0);
         if (d->tex[i].l1) cudaFree(d->tex[i].l1);
-        if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     }
+    for (uint32_t i = 0; i < kMaxBuffers; i++)
+        if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
                        &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane, &d->chunk_cull, &d->pixel_stage };
     for (DevBuf *b : bufs) release(*b);
@@ -390,7 +392,7 @@ int mtgl_dev_set_band(mtgl_dev *d, int32_t y0, int32_t y1)
 
 int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *data)
 {
-    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
     BufObj &b = d->buf[id];
     b.gen++; b.draws_since_write = 0;
@@ -413,7 +415,7 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
 
 int mtgl_dev_buffer_pointer(mtgl_dev *d, uint32_t id, void **ptr, uint64_t *size)
 {
-    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
     if (ptr) *ptr = d->buf[id].ptr;
     if (size) *size = d->buf[id].size;
     d->buf[id].exposed = true;          /* the caller may write the storage directly (NCCL all-gather of a sharded upload) */
@@ -423,7 +425,7 @@ int mtgl_dev_buffer_pointer(mtgl_dev *d, uint32_t id, void **ptr, uint64_t *size
 
 int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, const void *data)
 {
-    if (!d || id == 0 || id >= kMaxObjects || !data) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= kMaxBuffers || !data) return MTGL_E_INVALID;
     BufObj &b = d->buf[id];
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
@@ -437,7 +439,7 @@ int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t
 
 int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
 {
-    if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
     BufObj &b = d->buf[id];
     if (b.ptr) {
@@ -451,7 +453,7 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
 
 int mtgl_dev_buffer_read(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, void *out)
 {
-    if (!d || id == 0 || id >= kMaxObjects || !out) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= kMaxBuffers || !out) return MTGL_E_INVALID;
     BufObj &b = d->buf[id];
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
@@ -636,7 +638,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             const mtgl_draw &s = bt->draws[q.draw];
             if (o.index_type) {
                 if (s.index_buffer) {
-                    if (s.index_buffer < kMaxObjects && d->buf[s.index_buffer].ptr && s.index_offset <= d->buf[s.index_buffer].size) {
+                    if (s.index_buffer < kMaxBuffers && d->buf[s.index_buffer].ptr && s.index_offset <= d->buf[s.index_buffer].size) {
                         o.index_ptr = d->buf[s.index_buffer].ptr + s.index_offset;
                         o.index_avail = d->buf[s.index_buffer].size - s.index_offset;
                     }

@@ -32,6 +32,8 @@ GLint *current_depth(GLState *c);
 Texture *get_texture(GLState *c, GLuint id);
 Buffer *get_buffer(GLState *c, GLuint id);
 DisplayList *get_list(GLState *c, GLuint id);
+/* compiled display-list geometry (gl_front.cpp): queue run r of list 'id' as one array draw; false = replay it instead */
+bool draw_list_run(GLState *c, GLuint id, const ListRun &r);
 /* host view of a buffer object: materialises the mirror of an HBM-only buffer on demand */
 const uint8_t *buffer_host_data(GLState *c, GLuint id);
 /* copy n bytes at 'offset' out of a buffer object (small device read-back when there is no host mirror) */

@@ -8,6 +8,7 @@
 #include "front_internal.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 using namespace mtgl;
@@ -952,13 +953,23 @@ GLuint glGenLists(GLsizei range)
     return (GLuint)start + 1;
 }
 
+/* drop a list's compiled geometry (queued draws may still read the buffer: they go first) */
+static void release_list_buffer(GLState *c, GLuint id, DisplayList *l)
+{
+    l->runs.clear();
+    if (!l->has_buffer) return;
+    flush_batch(c);
+    mtgl_dev_buffer_data(c->dev, MTGL_LIST_BUFFER_BASE + id, 0, nullptr);
+    l->has_buffer = false;
+}
+
 void glDeleteLists(GLuint list, GLsizei range)
 {
     MTGL_CTX();
     if (range < 0) { set_error(c, GL_INVALID_VALUE); return; }
     for (GLsizei i = 0; i < range; i++) {
         DisplayList *l = get_list(c, list + i);
-        if (l) *l = DisplayList();
+        if (l) { release_list_buffer(c, list + i, l); *l = DisplayList(); }
     }
 }
 
@@ -969,27 +980,92 @@ void glNewList(GLuint list, GLenum mode)
     if (mode != GL_COMPILE && mode != GL_COMPILE_AND_EXECUTE) { set_error(c, GL_INVALID_ENUM); return; }
     DisplayList *l = get_list(c, list);
     if (!l) { set_error(c, GL_INVALID_VALUE); return; }
+    release_list_buffer(c, list, l);
     l->cmds.clear();
     l->valid = false;
     c->list_index = list;
     c->list_mode = mode;
 }
 
+/* Find the glBegin ... glEnd stretches made of nothing but vertices and attribute calls and move their vertices into
+ * a device buffer.  A stretch qualifies when every attribute it sets is set before its first
+ * vertex -- then each vertex's colour / texture coordinate / normal is known at compile time; an attribute it never
+ * sets is the current value at call time.  Everything else keeps being replayed call by call. */
+static void compile_list_runs(GLState *c, GLuint id, DisplayList *l)
+{
+    static const bool disabled = std::getenv("MTGL_NO_LIST_RUNS") != nullptr;      /* A/B switch for measurements */
+    if (disabled) return;
+    std::vector<float> verts;                   /* 12 floats per vertex: position 3, colour 4, texture coordinate 2, normal 3 */
+    const std::vector<ListCmd> &cm = l->cmds;
+    for (size_t i = 0; i < cm.size(); i++) {
+        if (cm[i].op != OP_BEGIN || cm[i].e[0] > GL_POLYGON) continue;
+        ListRun r;
+        r.begin_cmd = i; r.mode = cm[i].e[0]; r.first = (uint32_t)(verts.size() / 12);
+        float col[4] = { 0, 0, 0, 1 }, tex[2] = { 0, 0 }, nrm[3] = { 0, 0, 1 };
+        bool ok = true, seen_vertex = false, closed = false;
+        size_t j = i + 1;
+        const size_t rollback = verts.size();
+        for (; j < cm.size(); j++) {
+            const ListCmd &k = cm[j];
+            if (k.op == OP_END) { closed = true; break; }
+            if (k.op == OP_VERTEX) {
+                seen_vertex = true;
+                const float v[12] = { k.f[0], k.f[1], k.f[2], col[0], col[1], col[2], col[3], tex[0], tex[1], nrm[0], nrm[1], nrm[2] };
+                verts.insert(verts.end(), v, v + 12);
+            } else if (k.op == OP_COLOR) {
+                if (seen_vertex && !r.has_color) ok = false;    /* the first vertices would need the caller's colour */
+                r.has_color = true; std::memcpy(col, k.f, sizeof col);
+            } else if (k.op == OP_TEXCOORD) {
+                if (seen_vertex && !r.has_texcoord) ok = false;
+                r.has_texcoord = true; std::memcpy(tex, k.f, sizeof tex);
+            } else if (k.op == OP_NORMAL) {
+                if (seen_vertex && !r.has_normal) ok = false;
+                r.has_normal = true; std::memcpy(nrm, k.f, sizeof nrm);
+            } else { ok = false; break; }                       /* a state change, a nested list ...: not pure geometry */
+        }
+        r.count = (uint32_t)((verts.size() - rollback) / 12);
+        if (!ok || !closed || r.count < kListRunMinVertices) {
+            verts.resize(rollback);
+            if (closed) i = j;                                  /* resume behind the glEnd */
+            continue;
+        }
+        r.end_cmd = j;
+        std::memcpy(r.last_color, col, sizeof col); std::memcpy(r.last_texcoord, tex, sizeof tex); std::memcpy(r.last_normal, nrm, sizeof nrm);
+        l->runs.push_back(r);
+        i = j;
+    }
+    if (l->runs.empty()) return;
+    if (mtgl_dev_buffer_data(c->dev, MTGL_LIST_BUFFER_BASE + id, (uint64_t)verts.size() * 4, verts.data()) == MTGL_OK) l->has_buffer = true;
+    else l->runs.clear();                                       /* no room: replay as before */
+}
+
 void glEndList(void)
 {
     MTGL_CTX();
     if (c->list_index == 0) { set_error(c, GL_INVALID_OPERATION); return; }
-    DisplayList *l = get_list(c, c->list_index);
-    if (l) l->valid = true;
+    const GLuint id = c->list_index;
+    DisplayList *l = get_list(c, id);
     c->list_index = 0;
     c->list_mode = 0;
+    if (l) {
+        l->valid = true;
+        if (id <= 1024) compile_list_runs(c, id, l);
+    }
 }
 
 static void replay(GLState *c, GLuint id) /* execute_list, gl_api.c:2331-2439: replays through the public API */
 {
     DisplayList *l = get_list(c, id);
     if (!l || !l->valid) return;
+    size_t next_run = 0;
     for (size_t i = 0; i < l->cmds.size(); i++) {
+        /* compiled geometry: one array draw instead of the calls between glBegin and glEnd */
+        l = get_list(c, id);
+        while (next_run < l->runs.size() && l->runs[next_run].begin_cmd < i) next_run++;
+        if (next_run < l->runs.size() && l->runs[next_run].begin_cmd == i && l->has_buffer) {
+            const ListRun r = l->runs[next_run++];
+            if (draw_list_run(c, id, r)) { i = r.end_cmd; continue; }
+        }
         /* copy: a replayed call may append to this very list (COMPILE_AND_EXECUTE recursion) */
         ListCmd cmd = get_list(c, id)->cmds[i];
         switch (cmd.op) {

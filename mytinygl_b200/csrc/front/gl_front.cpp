@@ -460,6 +460,7 @@ void gl_destroy_context(GLState *c)
 void gl_make_current(GLState *c) { g_ctx = c; }
 GLState *gl_get_current_context(void) { return g_ctx; }
 struct mtgl_dev *mtgl_context_device(GLState *c) { return c ? c->dev : nullptr; }
+uint64_t mtgl_context_list_runs_drawn(GLState *c) { return c ? c->list_runs_drawn : 0; }
 
 const mtgl_framebuffer *mtgl_map_framebuffer(GLState *c, unsigned planes)
 {
@@ -788,6 +789,57 @@ static void draw_arrays_common(GLState *c, GLenum mode, GLsizei count, GLint fir
     c->draws.push_back(d);
     if (c->draws.size() > kMaxBatchDraws) flush_batch(c);
 }
+
+} // extern "C"
+
+namespace mtgl {
+
+/* One compiled run of a display list as an array draw from the list's device buffer.  The
+ * reference replays the list call by call (execute_list, gl_api.c:2331-2439): glBegin, then per vertex glColor4f /
+ * glTexCoord2f / glNormal3f + emit_vertex, then glEnd -- exactly the sequence glDrawArrays runs per element
+ * (1826-1849), so the array path produces the same vertices.  Attributes the run never sets come from the current
+ * values at call time (disabled arrays); the ones it sets stay current afterwards. */
+bool draw_list_run(GLState *c, GLuint id, const ListRun &r)
+{
+    if (compiling(c) || c->inside_begin_end || c->staged.size() != c->prim_first || r.count == 0) return false;
+    /* the colour of every vertex also drives the material while GL_COLOR_MATERIAL is on (gl_api.c:285-312): that walk
+     * is left to the per-call path */
+    if (r.has_color && (c->caps & MTGL_CAP_LIGHTING) && (c->caps & MTGL_CAP_COLOR_MATERIAL)) return false;
+    c->primitive_mode = r.mode;
+    mtgl_draw d;
+    std::memset(&d, 0, sizeof d);
+    d.mode = r.mode;
+    d.count = r.count;
+    d.source = MTGL_SRC_ARRAYS;
+    d.first = (int32_t)r.first;
+    auto attrib = [&](mtgl_attrib &a, bool on, uint32_t offset, uint16_t size) {
+        a.enabled = on ? 1u : 0u;
+        if (!on) return;
+        a.buffer = MTGL_LIST_BUFFER_BASE + id; a.offset = offset; a.stride = 48; a.size = size; a.type = MTGL_TYPE_F32;
+    };
+    attrib(d.position, true, 0, 3);
+    attrib(d.color, r.has_color, 12, 4);
+    attrib(d.texcoord, r.has_texcoord, 28, 2);
+    attrib(d.normal, r.has_normal, 36, 3);
+    d.cur_color[0] = c->current_color.r; d.cur_color[1] = c->current_color.g;
+    d.cur_color[2] = c->current_color.b; d.cur_color[3] = c->current_color.a;
+    d.cur_texcoord[0] = c->current_texcoord[0]; d.cur_texcoord[1] = c->current_texcoord[1];
+    d.cur_normal[0] = c->current_normal[0]; d.cur_normal[1] = c->current_normal[1]; d.cur_normal[2] = c->current_normal[2];
+    d.vertex_state = current_state_block(c);
+    if (r.has_color) c->current_color = rgba(r.last_color[0], r.last_color[1], r.last_color[2], r.last_color[3]);
+    if (r.has_texcoord) { c->current_texcoord[0] = r.last_texcoord[0]; c->current_texcoord[1] = r.last_texcoord[1]; }
+    if (r.has_normal) { c->current_normal[0] = r.last_normal[0]; c->current_normal[1] = r.last_normal[1]; c->current_normal[2] = r.last_normal[2]; }
+    apply_color_material(c, c->current_color);      /* as after an array draw (draw_arrays_common) */
+    d.raster_state = raster_state_block(c);
+    c->draws.push_back(d);
+    c->list_runs_drawn++;
+    if (c->draws.size() > kMaxBatchDraws) flush_batch(c);
+    return true;
+}
+
+} // namespace mtgl
+
+extern "C" {
 
 void glDrawArrays(GLenum mode, GLint first, GLsizei count) /* gl_api.c:1799-1852 */
 {

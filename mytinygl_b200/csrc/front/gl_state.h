@@ -89,11 +89,26 @@ struct ListCmd {
     };
 };
 
+/* A glBegin ... glEnd stretch of a display list that holds nothing but vertices and their attributes, compiled at
+ * glEndList into one array draw from a device buffer the list owns (12 floats per vertex: position, colour, texture
+ * coordinate, normal): glCallList then queues one draw record instead of replaying every glVertex / glNormal call. */
+struct ListRun {
+    size_t begin_cmd = 0, end_cmd = 0;      /* indices of OP_BEGIN and OP_END in cmds */
+    GLenum mode = 0;
+    uint32_t first = 0, count = 0;          /* vertices in the list's buffer */
+    bool has_color = false, has_texcoord = false, has_normal = false;   /* set inside the run, before its first vertex */
+    float last_color[4], last_texcoord[2], last_normal[3];              /* what the run leaves as current values */
+};
+
 struct DisplayList {
     bool allocated = false;
     bool valid = false;
     std::vector<ListCmd> cmds;
+    std::vector<ListRun> runs;              /* sorted by begin_cmd */
+    bool has_buffer = false;                /* device buffer MTGL_LIST_BUFFER_BASE + list id holds the runs' vertices */
 };
+
+constexpr uint32_t kListRunMinVertices = 24;    /* shorter runs are replayed: a draw record costs more than they do */
 
 } // namespace mtgl
 
@@ -168,6 +183,7 @@ struct GLState {
     GLuint list_base, list_index;
     GLenum list_mode;
     GLuint list_call_depth;
+    uint64_t list_runs_drawn = 0;           /* compiled ListRuns queued as array draws (statistics) */
 
     GLenum error;
 

@@ -71,6 +71,7 @@ typedef struct {
 } obuf;
 
 #define O_MAX_OBJECTS 257
+#define O_MAX_BUFFERS MTGL_MAX_BUFFER_IDS
 
 struct mtgl_dev {
     int32_t width, height;
@@ -79,7 +80,7 @@ struct mtgl_dev {
     float *depth;
     uint8_t *stencil;
     otex tex[O_MAX_OBJECTS];
-    obuf buf[O_MAX_OBJECTS];
+    obuf buf[O_MAX_BUFFERS];
     mtgl_dev_stats stats;
     uint64_t frag_covered, frag_tested, frag_shaded;   /* cumulative: inside test / past stencil+depth / colour write */
     double t_mark[2];
@@ -293,7 +294,7 @@ static col4 sanitize_color(const float *c)
 /* get_array_element (gl_api.c:1758-1797) against a buffer-object mirror */
 static void fetch_attrib(const mtgl_dev *dev, const mtgl_attrib *a, int32_t index, float *out, int want)
 {
-    const obuf *b = (a->buffer < O_MAX_OBJECTS) ? &dev->buf[a->buffer] : NULL;
+    const obuf *b = (a->buffer < O_MAX_BUFFERS) ? &dev->buf[a->buffer] : NULL;
     if (!b || !b->data || index < 0) {
         for (int i = 0; i < want; i++) out[i] = (i < 3) ? 0.0f : 1.0f;
         return;
@@ -1073,7 +1074,8 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
 void mtgl_dev_destroy(mtgl_dev *d)
 {
     if (!d) return;
-    for (int i = 0; i < O_MAX_OBJECTS; i++) { free(d->tex[i].px); free(d->tex[i].px1); free(d->buf[i].data); }
+    for (int i = 0; i < O_MAX_OBJECTS; i++) { free(d->tex[i].px); free(d->tex[i].px1); }
+    for (unsigned i = 0; i < O_MAX_BUFFERS; i++) free(d->buf[i].data);
     free(d->color); free(d->depth); free(d->stencil);
     free(d);
 }
@@ -1087,7 +1089,7 @@ int mtgl_dev_set_band(mtgl_dev *d, int32_t y0, int32_t y1)
 
 int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *data)
 {
-    if (!d || id == 0 || id >= O_MAX_OBJECTS) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= O_MAX_BUFFERS) return MTGL_E_INVALID;
     free(d->buf[id].data);
     d->buf[id].data = NULL; d->buf[id].size = 0;
     if (size == 0) return MTGL_OK;
@@ -1100,7 +1102,7 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
 
 int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, const void *data)
 {
-    if (!d || id == 0 || id >= O_MAX_OBJECTS || !d->buf[id].data || !data) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= O_MAX_BUFFERS || !d->buf[id].data || !data) return MTGL_E_INVALID;
     if (offset + size > d->buf[id].size) return MTGL_E_INVALID;
     memcpy(d->buf[id].data + offset, data, size);
     return MTGL_OK;
@@ -1108,7 +1110,7 @@ int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t
 
 int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
 {
-    if (!d || id == 0 || id >= O_MAX_OBJECTS) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= O_MAX_BUFFERS) return MTGL_E_INVALID;
     free(d->buf[id].data);
     d->buf[id].data = NULL; d->buf[id].size = 0;
     return MTGL_OK;
@@ -1116,7 +1118,7 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
 
 int mtgl_dev_buffer_read(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t size, void *out)
 {
-    if (!d || id == 0 || id >= O_MAX_OBJECTS || !d->buf[id].data || !out) return MTGL_E_INVALID;
+    if (!d || id == 0 || id >= O_MAX_BUFFERS || !d->buf[id].data || !out) return MTGL_E_INVALID;
     if (offset + size > d->buf[id].size) return MTGL_E_INVALID;
     memcpy(out, d->buf[id].data + offset, size);
     return MTGL_OK;

@@ -35,6 +35,7 @@ CASES = (
     + [("cull", 480, 270, v) for v in range(6)]
     + [("vbo_large", 480, 270, 0)]
     + [("pixels", 320, 240, v) for v in (0, 1, 2, 5, 7)] + [("pixels", 517, 389, 3)]
+    + [("displaylist_runs", 480, 270, v) for v in range(4)]
 )
 
 

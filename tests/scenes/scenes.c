@@ -1259,6 +1259,120 @@ static void scene_pixels(int w, int h, int variant)
     glEnd();
 }
 
+/* Display lists whose glBegin ... glEnd stretches are long enough to be compiled into array draws (the front end's
+ * ListRun path): the result must be what the reference's call-by-call replay gives.
+ * variant 0: lit Suzanne (normals set before every vertex) called four times under different transforms, with the
+ *            current colour / material changed between calls; the list also holds state changes around the geometry
+ *         1: a strip whose colour is set inside the run before the first vertex, texture coordinates never (they come
+ *            from the caller), and a second run whose colour is first set AFTER its first vertex (must be replayed)
+ *         2: GL_COLOR_MATERIAL with per-vertex colours inside the run (left to the per-call path), two-sided lighting
+ *         3: a list redefined after it was drawn from, nested lists, glCallLists with a list base, COMPILE_AND_EXECUTE */
+static void scene_displaylist_runs(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.05f, 0.05f, 0.1f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    GLuint base = glGenLists(4);
+    if (variant == 0 || variant == 3) {
+        suzanne_lights_and_material();
+        glNewList(base, variant == 3 ? GL_COMPILE_AND_EXECUTE : GL_COMPILE);
+        glPushMatrix();
+        glRotatef(25.0f, 0.0f, 1.0f, 0.0f);
+        suzanne_immediate();
+        glPopMatrix();
+        glShadeModel(GL_FLAT);
+        glBegin(GL_QUADS);                      /* a short run: replayed */
+        glNormal3f(0.0f, 0.0f, 1.0f);
+        glVertex3f(-1.2f, -1.1f, 0.2f); glVertex3f(1.2f, -1.1f, 0.2f); glVertex3f(1.2f, -0.9f, 0.2f); glVertex3f(-1.2f, -0.9f, 0.2f);
+        glEnd();
+        glShadeModel(GL_SMOOTH);
+        glEndList();
+        for (int k = 0; k < 4; k++) {
+            GLfloat md[4] = { 0.3f + 0.2f * (float)k, 0.8f - 0.15f * (float)k, 0.4f, 1.0f };
+            glMaterialfv(GL_FRONT, GL_DIFFUSE, md);
+            glLoadIdentity();
+            glTranslatef(-2.7f + 1.8f * (float)k, (k & 1) ? 0.5f : -0.4f, -6.0f - 0.5f * (float)k);
+            if (variant == 3 && k == 2) {       /* redefine the list the queued draws were made from */
+                glNewList(base, GL_COMPILE);
+                glScalef(0.6f, 1.3f, 0.6f);
+                suzanne_immediate();
+                glEndList();
+            }
+            if (variant == 3 && k == 3) {
+                glNewList(base + 1, GL_COMPILE);
+                glCallList(base);
+                glTranslatef(0.0f, -1.6f, 0.0f);
+                glCallList(base);
+                glEndList();
+                GLubyte which[2] = { 1, 0 };
+                glListBase(base);
+                glCallLists(2, GL_UNSIGNED_BYTE, which);
+                glListBase(0);
+            } else glCallList(base);
+        }
+    } else if (variant == 1) {
+        GLuint tex = make_checker_rgb(32, 4, 0);
+        (void)tex;
+        glEnable(GL_TEXTURE_2D);
+        glNewList(base, GL_COMPILE);
+        glBegin(GL_TRIANGLE_STRIP);
+        glColor4f(0.9f, 0.7f, 0.3f, 1.0f);      /* before the first vertex: compiled */
+        for (int k = 0; k < 40; k++) {
+            float a = 0.16f * (float)k;
+            if (k == 20) glColor4f(0.3f, 0.6f, 0.95f, 1.0f);
+            glVertex3f(-2.5f + 0.125f * (float)k, 0.9f + 0.5f * sinf(a), 0.0f);
+            glVertex3f(-2.5f + 0.125f * (float)k, 0.2f + 0.3f * cosf(a), 0.3f);
+        }
+        glEnd();
+        glBegin(GL_TRIANGLE_FAN);
+        glVertex3f(0.0f, -1.0f, 0.0f);          /* this vertex uses the caller's colour: the run is replayed */
+        for (int k = 0; k <= 30; k++) {
+            glColor3f(0.03f * (float)k, 1.0f - 0.03f * (float)k, 0.5f);
+            glTexCoord2f(0.1f * (float)k, 0.5f);
+            glVertex3f(1.4f * cosf(0.2094f * (float)k), -1.0f + 0.8f * sinf(0.2094f * (float)k), 0.0f);
+        }
+        glEnd();
+        glEndList();
+        for (int k = 0; k < 3; k++) {
+            glLoadIdentity();
+            glTranslatef(-1.0f + 1.0f * (float)k, 0.2f * (float)k, -5.0f - (float)k);
+            glTexCoord2f(0.25f * (float)k, 0.6f);               /* the compiled strip takes these */
+            glColor3f(1.0f, 0.2f * (float)k, 1.0f);
+            glCallList(base);
+        }
+        glDisable(GL_TEXTURE_2D);
+    } else {
+        suzanne_lights_and_material();
+        glLightModeli(GL_LIGHT_MODEL_TWO_SIDE, 1);
+        glEnable(GL_COLOR_MATERIAL);
+        glColorMaterial(GL_FRONT_AND_BACK, GL_DIFFUSE);
+        glNewList(base, GL_COMPILE);
+        glBegin(GL_TRIANGLES);
+        for (int i = 0; i < g_mesh_nf && i < 400; i++)
+            for (int j = 0; j < 3; j++) {
+                int vi = g_mesh_faces[i * 3 + j];
+                glColor3f(0.5f + 0.5f * g_mesh_nrm[vi * 3], 0.5f + 0.5f * g_mesh_nrm[vi * 3 + 1], 0.6f);
+                glNormal3f(g_mesh_nrm[vi * 3], g_mesh_nrm[vi * 3 + 1], g_mesh_nrm[vi * 3 + 2]);
+                glVertex3f(g_mesh_pos[vi * 3], g_mesh_pos[vi * 3 + 1], g_mesh_pos[vi * 3 + 2]);
+            }
+        glEnd();
+        glEndList();
+        for (int k = 0; k < 2; k++) {
+            glLoadIdentity();
+            glTranslatef(-1.2f + 2.4f * (float)k, 0.0f, -4.5f);
+            glRotatef(160.0f * (float)k, 0.0f, 1.0f, 0.0f);
+            glCallList(base);
+        }
+        glDisable(GL_COLOR_MATERIAL);
+        glBegin(GL_TRIANGLES);                   /* the material the list left behind */
+        glNormal3f(0.0f, 0.0f, 1.0f);
+        glVertex3f(-0.5f, -1.6f, -4.0f); glVertex3f(0.5f, -1.6f, -4.0f); glVertex3f(0.0f, -1.0f, -4.0f);
+        glEnd();
+    }
+    glDeleteLists(base, 4);
+}
+
 /* ---------------------------------------------------------------- registry */
 typedef void (*scene_fn)(int, int, int);
 static const struct { const char *name; scene_fn fn; } g_scenes[] = {
@@ -1287,6 +1401,7 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "cull", scene_cull },
     { "vbo_large", scene_vbo_large },
     { "pixels", scene_pixels },
+    { "displaylist_runs", scene_displaylist_runs },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }
