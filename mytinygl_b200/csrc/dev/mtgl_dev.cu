@@ -671,7 +671,6 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     d->ev_next = (d->ev_next + 1) % mtgl_dev::kEvSets;
     if (es.pending && (rc = fold_timing(d, es))) return rc;     /* four batches ago: long finished */
     CU(cudaEventRecord(es.start, d->stream));
-    es.pending = true;
     d->timed = true;
     uint64_t tot_v = 0, tot_t = 0, tot_r = 0, tot_refs = 0, tot_culled = 0;
     while (es.stage.size() < passes.size() * 8) {
@@ -821,6 +820,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         }
     }
     CU(cudaEventRecord(es.stop, d->stream));
+    es.pending = true;      /* only a batch that was queued completely is folded into the statistics */
     CU(cudaGetLastError());
     d->stats.vertices = tot_v; d->stats.triangles_in = tot_t; d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs;
     d->stats.chunks_culled = tot_culled;
