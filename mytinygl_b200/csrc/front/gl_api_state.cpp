@@ -555,9 +555,31 @@ void glTexCoordPointer(GLint size, GLenum type, GLsizei stride, const GLvoid *p)
 void glNormalPointer(GLenum type, GLsizei stride, const GLvoid *p) { MTGL_CTX(); set_pointer(c, &c->normal_pointer, 3, 3, 3, type, stride, p); }
 
 /* ================================================================ lighting (gl_api.c:1945-2262) */
-void glLightfv(GLenum light, GLenum pname, const GLfloat *p)
+/* floats a light / material parameter is made of: only those are read from the caller's array (a 3-float spot
+ * direction or a 1-float shininess must not be read as four) */
+static int light_param_count(GLenum pname)
+{
+    switch (pname) {
+    case GL_AMBIENT: case GL_DIFFUSE: case GL_SPECULAR: case GL_POSITION: return 4;
+    case GL_SPOT_DIRECTION: return 3;
+    default: return 1;
+    }
+}
+
+static int material_param_count(GLenum pname)
+{
+    switch (pname) {
+    case GL_AMBIENT: case GL_DIFFUSE: case GL_SPECULAR: case GL_EMISSION: case GL_AMBIENT_AND_DIFFUSE: return 4;
+    default: return 1;
+    }
+}
+
+void glLightfv(GLenum light, GLenum pname, const GLfloat *params)
 {
     MTGL_CTX();
+    if (!params) return;
+    GLfloat p[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    std::memcpy(p, params, sizeof(GLfloat) * (size_t)light_param_count(pname));
     ListCmd cmd = make_cmd(OP_LIGHTFV, light, pname);
     std::memcpy(cmd.f, p, 16);
     if (record(c, cmd)) return;
@@ -602,9 +624,12 @@ void glLightiv(GLenum light, GLenum pname, const GLint *p)
     glLightfv(light, pname, f);
 }
 
-void glMaterialfv(GLenum face, GLenum pname, const GLfloat *p)
+void glMaterialfv(GLenum face, GLenum pname, const GLfloat *params)
 {
     MTGL_CTX();
+    if (!params) return;
+    GLfloat p[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    std::memcpy(p, params, sizeof(GLfloat) * (size_t)material_param_count(pname));
     ListCmd cmd = make_cmd(OP_MATERIALFV, face, pname);
     std::memcpy(cmd.f, p, 16);
     if (record(c, cmd)) return;
