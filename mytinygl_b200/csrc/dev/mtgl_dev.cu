@@ -51,7 +51,11 @@ struct BoundsEntry {
     uint32_t buffer = 0; uint64_t gen = 0, offset = 0; uint32_t stride = 0, size = 0; int32_t first = 0; uint32_t nverts = 0;
     DevBuf boxes; uint64_t last_use = 0;
     uint64_t batch = 0;             /* serial of the last batch that refers to these boxes: not evictable while it is being built */
+    /* whole-frame rendering of geometry that is entirely on screen: the pass drops nothing, so after a few such batches
+     * it is left out for a while and probed again later (a band-limited device always runs it) */
+    uint32_t zero_streak = 0, skip_left = 0;
 };
+constexpr uint32_t kCullZeroStreak = 4, kCullSkipBatches = 60;
 constexpr size_t kBoundsEntries = 8;
 constexpr uint32_t kBoundsMinTriangles = 4 * SETUP_THREADS;    /* smaller draws are not worth a culling pass */
 
@@ -291,6 +295,7 @@ int chunk_bounds_for(mtgl_dev *d, const mtgl_draw &s, const float4 **out)
         hit = lru;
     }
     hit->last_use = ++d->bounds_clock;
+    if (!band && hit->skip_left > 0) { hit->skip_left--; return MTGL_OK; }      /* recently useless: not this time */
     hit->batch = d->batch_serial;
     *out = (const float4 *)hit->boxes.ptr;
     return MTGL_OK;
@@ -824,6 +829,11 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     CU(cudaGetLastError());
     d->stats.vertices = tot_v; d->stats.triangles_in = tot_t; d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs;
     d->stats.chunks_culled = tot_culled;
+    for (BoundsEntry &e : d->bounds) {          /* did the culling pass pay for the boxes this batch used? */
+        if (e.batch != d->batch_serial) continue;
+        if (tot_culled != 0) e.zero_streak = 0;
+        else if (++e.zero_streak >= kCullZeroStreak) { e.zero_streak = 0; e.skip_left = kCullSkipBatches; }
+    }
     return MTGL_OK;
 }
 
