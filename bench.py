@@ -49,6 +49,8 @@ WORKLOADS = {
     "c4": ("c4_grid_3840x2160", 3840, 2160, 0),
     "c5": ("c5_grid_7680x4320", 7680, 4320, 0),
     "c3": ("c3_fill_3840x2160", 3840, 2160, 64),
+    # SURVEY.md 8(d) secondary layout: ONE Suzanne in the VBO, 1064 glDrawArrays under glPushMatrix / glTranslatef
+    "c4i": ("c4_instanced_3840x2160", 3840, 2160, 1 << 17),
 }
 
 
@@ -415,7 +417,8 @@ def run_b200(args, workload):
     pinned_out = torch.empty((ry1 - ry0) * w, dtype=torch.int32).pin_memory() if ry1 > ry0 else None
     vbo_dev = None
     if not is_c3:
-        nbytes = cnt["vertices"] * 32
+        L.scene_c4_vertex_count.restype = ctypes.c_int
+        nbytes = int(L.scene_c4_vertex_count()) * 32          # what the VBO holds (c4i: one mesh, not the whole grid)
         pinned_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         ctypes.memmove(pinned_in.data_ptr(), L.scene_c4_host_data(), nbytes)
         vbo = L.scene_c4_vbo()

@@ -36,6 +36,7 @@ CASES = (
     + [("vbo_large", 480, 270, 0)]
     + [("pixels", 320, 240, v) for v in (0, 1, 2, 5, 7)] + [("pixels", 517, 389, 3)]
     + [("displaylist_runs", 480, 270, v) for v in range(4)]
+    + [("c4_grid", 480, 270, C4_SMALL | (1 << 17)), ("c4_grid", 960, 540, 6 | (4 << 8) | (1 << 17))]     # one mesh, many draws
 )
 
 

@@ -317,6 +317,8 @@ static void scene_c3(int w, int h, int variant)
 static struct {
     GLuint vbo, tex;
     int gx, gy, nverts;
+    int instanced;  /* variant bit 17: one Suzanne in the VBO, drawn gx * gy times under glPushMatrix / glTranslatef */
+    float cz;
     float *host;    /* retained so the end-to-end benchmark can re-upload it every frame */
 } g_c4;
 
@@ -349,13 +351,17 @@ void scene_c4_upload(void) /* the per-frame host->device part of the end-to-end 
     glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr)((size_t)g_c4.nverts * 32), g_c4.host, GL_STATIC_DRAW);
 }
 
-/* variant: bits 0-7 grid columns (0 -> 38), bits 8-15 grid rows (0 -> 28), bit 16 GL_PHONG */
+/* variant: bits 0-7 grid columns (0 -> 38), bits 8-15 grid rows (0 -> 28), bit 16 GL_PHONG, bit 17 the secondary layout of
+ * ONE Suzanne in the VBO (2904 vertices), drawn gx * gy times under glPushMatrix / glTranslatef -- the
+ * same picture up to the rounding of "translate, then transform" against "transform the translated vertex" */
 void scene_c4_setup(int w, int h, int variant)
 {
     int gx = variant & 0xFF, gy = (variant >> 8) & 0xFF;
     if (gx == 0) gx = 38;
     if (gy == 0) gy = 28;
-    c4_build(gx, gy);
+    g_c4.instanced = (variant >> 17) & 1;
+    if (g_c4.instanced) { c4_build(1, 1); g_c4.gx = gx; g_c4.gy = gy; }
+    else c4_build(gx, gy);
     glGenBuffers(1, &g_c4.vbo);
     scene_c4_upload();
     g_c4.tex = make_checker_rgb(64, 4, 1);
@@ -401,13 +407,21 @@ void scene_c4_setup(int w, int h, int variant)
      * so that the per-triangle footprint stays comparable */
     float cz = 24.0f * (float)(gx > gy * 38 / 28 ? gx : gy * 38 / 28) / 38.0f;
     if (cz < 2.5f) cz = 2.5f;
+    g_c4.cz = cz;
     glTranslatef(0.0f, 0.0f, -cz);
 }
 
 void scene_c4_draw(void)
 {
     glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
-    glDrawArrays(GL_TRIANGLES, 0, g_c4.nverts);
+    if (!g_c4.instanced) { glDrawArrays(GL_TRIANGLES, 0, g_c4.nverts); return; }
+    for (int iy = 0; iy < g_c4.gy; iy++)
+        for (int ix = 0; ix < g_c4.gx; ix++) {
+            glPushMatrix();
+            glTranslatef(((float)ix - (float)(g_c4.gx - 1) * 0.5f) * 2.1f, ((float)iy - (float)(g_c4.gy - 1) * 0.5f) * 1.5f, 0.0f);
+            glDrawArrays(GL_TRIANGLES, 0, g_c4.nverts);
+            glPopMatrix();
+        }
 }
 
 static void scene_c4(int w, int h, int variant)

@@ -23,6 +23,7 @@ WORKLOADS = {
     "c4_grid_3840x2160": ("c4_grid", 3840, 2160, 0),
     "c4_grid_phong_3840x2160": ("c4_grid", 3840, 2160, 1 << 16),
     "c5_grid_7680x4320": ("c4_grid", 7680, 4320, 0),
+    "c4_instanced_3840x2160": ("c4_grid", 3840, 2160, 1 << 17),    # one 2904-vertex VBO drawn 1064 times under glTranslatef
 }
 
 
@@ -42,6 +43,8 @@ def main():
         counts = (ctypes.c_uint64 * 3)()
         lib.lib.mtgl_oracle_fragment_counts(lib.device(), counts)
         verts = lib.lib.scene_c4_vertex_count() if name == "c4_grid" else 0
+        if variant & (1 << 17):
+            verts *= 38 * 28        # vertices through the vertex stage: the one mesh, once per draw
         lib.destroy()
         out[key] = {"scene": name, "width": w, "height": h, "variant": variant, "covered": int(counts[0]),
                     "tested": int(counts[1]), "shaded": int(counts[2]), "vertices": int(verts)}
