@@ -12,7 +12,8 @@ extern thread_local GLState *g_ctx;     /* current context (gl_api.c:14-23 keeps
 void set_error(GLState *c, GLenum e);
 
 /* batching */
-void mark_state_dirty(GLState *c);
+void mark_state_dirty(GLState *c);      /* any state the device reads has changed */
+void mark_matrix_dirty(GLState *c);     /* only one of the three current matrices has changed */
 void flush_batch(GLState *c);                 /* submit queued clear + draws to the device */
 void sync_device(GLState *c);                 /* flush + wait */
 void emit_vertex(GLState *c, float x, float y, float z);

@@ -53,7 +53,7 @@ static void post_multiply(GLState *c, const float *m)
 {
     float *cur = current_matrix(c);
     mat_mul(cur, m, cur);
-    mark_state_dirty(c);
+    mark_matrix_dirty(c);
 }
 
 static bool is_compare_func(GLenum f) { return f >= GL_NEVER && f <= GL_ALWAYS; }
@@ -136,7 +136,7 @@ void glLoadIdentity(void)
     MTGL_CTX();
     if (record(c, make_cmd(OP_LOAD_IDENTITY))) return;
     mat_identity(current_matrix(c));
-    mark_state_dirty(c);
+    mark_matrix_dirty(c);
 }
 
 void glPushMatrix(void)
@@ -157,7 +157,7 @@ void glPopMatrix(void)
     GLint *depth = current_depth(c);
     if (*depth <= 0) { set_error(c, GL_STACK_UNDERFLOW); return; }
     (*depth)--;
-    mark_state_dirty(c);
+    mark_matrix_dirty(c);
 }
 
 void glLoadMatrixf(const GLfloat *m)
@@ -167,7 +167,7 @@ void glLoadMatrixf(const GLfloat *m)
     std::memcpy(cmd.f, m, 64);
     if (record(c, cmd)) return;
     std::memcpy(current_matrix(c), m, 64);
-    mark_state_dirty(c);
+    mark_matrix_dirty(c);
 }
 
 void glMultMatrixf(const GLfloat *m)

@@ -238,14 +238,27 @@ static void snapshot_state(const GLState *c, mtgl_state *s)
     s->depth_near = c->depth_near; s->depth_far = c->depth_far;
 }
 
-void mark_state_dirty(GLState *c) { c->vstate_dirty = true; }
+void mark_state_dirty(GLState *c) { c->vstate_dirty = true; c->vstate_full_dirty = true; }
+void mark_matrix_dirty(GLState *c) { c->vstate_dirty = true; }
 
 /* index of a state block equal to the live state, appending one when the last block differs */
 static uint32_t current_state_block(GLState *c)
 {
     if (!c->vstate_dirty && !c->states.empty()) return c->vstate_index;
-    mtgl_state s;
-    snapshot_state(c, &s);
+    /* A render loop changes matrices far more often than anything else (glPushMatrix / glTranslatef / draw /
+     * glPopMatrix per object): then the previous snapshot is patched -- three matrices and the normal matrix -- instead
+     * of being rebuilt (eight lights with two normalisations and a cosf each, materials, ~60 scalar fields). */
+    mtgl_state &s = c->last_snapshot;
+    if (c->vstate_full_dirty || !c->have_snapshot) {
+        snapshot_state(c, &s);
+        c->have_snapshot = true;
+        c->vstate_full_dirty = false;
+    } else {
+        std::memcpy(s.modelview, c->modelview[c->modelview_depth], 64);
+        std::memcpy(s.projection, c->projection[c->projection_depth], 64);
+        std::memcpy(s.texture, c->texture[c->texture_depth], 64);
+        normal_matrix(s.modelview, s.normal);
+    }
     if (c->states.empty() || std::memcmp(&c->states.back(), &s, sizeof s) != 0) c->states.push_back(s);
     c->vstate_index = (uint32_t)c->states.size() - 1;
     c->vstate_dirty = false;
@@ -328,7 +341,7 @@ void emit_vertex(GLState *c, float x, float y, float z)
 static uint32_t raster_state_block(GLState *c)
 {
     if (c->material_touched) {
-        c->vstate_dirty = true;
+        mark_state_dirty(c);
         c->material_touched = false;
     }
     return current_state_block(c);
@@ -440,6 +453,8 @@ GLState *gl_create_context(int32_t width, int32_t height)
 
     c->prim_first = 0;
     c->vstate_dirty = true;
+    c->vstate_full_dirty = true;
+    c->have_snapshot = false;
     c->vstate_index = 0;
     c->material_touched = false;
     c->pending_clear_mask = 0;

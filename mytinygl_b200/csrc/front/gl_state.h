@@ -201,6 +201,9 @@ struct GLState {
     std::vector<uint8_t> blob;
     uint32_t prim_first;                /* first staged vertex of the primitive being assembled */
     bool vstate_dirty;                  /* a state-changing call happened since the last snapshot */
+    bool vstate_full_dirty;             /* ... and it was not just a matrix call: the snapshot has to be rebuilt from scratch */
+    bool have_snapshot;                 /* last_snapshot mirrors the live state up to the current matrices */
+    mtgl_state last_snapshot;
     bool material_touched;              /* COLOR_MATERIAL rewrote ctx materials since the last snapshot */
     uint32_t vstate_index;              /* state block of the most recent vertex */
     uint32_t pending_clear_mask;
