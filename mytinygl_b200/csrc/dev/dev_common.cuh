@@ -126,6 +126,13 @@ constexpr uint32_t KIND_TRIANGLE = 0u, KIND_LINE = 1u, KIND_POINT = 2u;
 constexpr uint32_t STATE_DEFER_BIT = 1u << 30;
 constexpr uint32_t STATE_BACK_BIT = 1u << 31;
 
+/* what a record contributes to the flags of every tile it is binned into */
+__device__ __forceinline__ uint32_t tile_flag_bits(uint32_t state_flags)
+{
+    return ((state_flags & STATE_DEFER_BIT) ? 0u : 1u) | ((state_flags & STATE_UNORD_BIT) ? 0u : 2u) |
+           ((state_flags & STATE_KIND_MASK) ? 4u : 0u);
+}
+
 /* One set-up primitive: 10 x 16 B.  For a sub-triangle the fields mean what their names say.  A LINE record
  * (draw_line_full, raster.c:107-241) stores its end points in (x0,y0)-(x1,y1), the line width in x2, NDC z in z0/z1,
  * end colours in c0/c1, texture coordinates in (u0,v0)/(u1,v1) and eye z in ez0/ez1.  A POINT record (flush_points
@@ -416,7 +423,8 @@ struct BatchDev {
     /* binning */
     uint32_t *tile_count, *tile_offset, *tile_cursor;
     uint32_t *tile_flags;           /* bit 0: the tile references a record whose colour work cannot be deferred (general kernel);
-                                     * bit 1: it references a record outside the unordered class (sorted visibility kernel) */
+                                     * bit 1: it references a record outside the unordered class (sorted visibility kernel);
+                                     * bit 2: it references a line or a point (tile_flag_bits) */
     uint32_t *tile_order;           /* launch order of the tile kernels: blockIdx -> tile, heaviest lists first (k_bin_scan); NULL = identity */
     uint32_t *tile_list; uint32_t list_capacity;
     uint32_t guard;                 /* 1: the list buffer was sized by guess -- fill and raster kernels must check lists_fit() */
@@ -446,10 +454,14 @@ struct RasterPlan {
     bool plain_in_order;        /* ... and the pass holds nothing but in-order filled triangles */
     uint32_t unordered_func;    /* depth function (0..7) of the unordered class, 0 when the class is empty */
     bool unordered_range01;     /* every unordered state has depth range [0,1] */
+    uint32_t fill_mode;         /* FILL_* (dev_fill.cuh): may the pixel-owner kernel (k_fill.cu) take in-order tiles of large triangles */
+    uint32_t in_order_all, in_order_any;    /* AND / OR of the RasterCfg flags of the pass's in-order states */
 };
 /* ev_vis / ev_shade are recorded after the visibility kernels and after the shade kernel (stage timing) */
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
+void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
+                 cudaStream_t s);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
 void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);

@@ -1,0 +1,44 @@
+/*
+ * dev_fill.cuh -- which in-order tiles the pixel-owner kernel (k_fill.cu) takes over from the general tile kernel
+ * (k_raster.cu).  Both kernels are launched over the same grid of tiles and evaluate this one deterministic predicate
+ * on the same data, so exactly one of them renders a tile.
+ */
+#ifndef MTGL_DEV_FILL_CUH
+#define MTGL_DEV_FILL_CUH
+
+#include "dev_common.cuh"
+
+namespace mtgl_dev_impl {
+
+constexpr uint32_t FILL_MAX_LIST = 1024;        /* longest tile list k_fill sorts in shared memory */
+constexpr uint32_t FILL_MIN_AVG_AREA = 1024;    /* mean clamped box area (pixels of the 64x64 tile) per list entry from which
+                                                 * one-thread-per-pixel beats one-warp-per-8x4-block: a quarter of the tile */
+enum : uint32_t { FILL_OFF = 0u, FILL_AUTO = 1u, FILL_ALWAYS = 2u };
+
+/* Called by every thread of the CTA (blockDim.x threads; *acc is a shared word nobody else uses).  The answer is uniform.
+ * tflags: bit 0 = the tile holds a record that needs in-order shading, bit 2 = it holds a line or a point. */
+__device__ __forceinline__ bool fill_owns_tile(const BatchDev &b, uint32_t fill_mode, uint32_t L, uint32_t tflags, const uint32_t *list,
+                                               int px0, int py0, int vh, uint32_t *acc)
+{
+    if (fill_mode == FILL_OFF || L == 0u || L > FILL_MAX_LIST || (tflags & 5u) != 1u) return false;
+    if (fill_mode == FILL_ALWAYS) return true;
+    if (threadIdx.x == 0) *acc = 0u;
+    __syncthreads();
+    uint32_t area = 0;
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+        const uint4 row = __ldg(b.bin_rows + list[i]);          /* bbox_min, bbox_max, state_flags, id */
+        const int x0 = max((int)(row.x & 0xFFFFu) - px0, 0), y0 = max((int)(row.x >> 16) - py0, 0);
+        const int x1 = min((int)(row.y & 0xFFFFu) - px0, TILE_W - 1), y1 = min((int)(row.y >> 16) - py0, vh - 1);
+        if (x1 >= x0 && y1 >= y0) area += (uint32_t)((x1 - x0 + 1) * (y1 - y0 + 1));
+    }
+    area = __reduce_add_sync(0xFFFFFFFFu, area);
+    if ((threadIdx.x & 31) == 0 && area) atomicAdd(acc, area);
+    __syncthreads();
+    const bool owns = *acc >= L * FILL_MIN_AVG_AREA;
+    __syncthreads();        /* *acc may be reused by the caller */
+    return owns;
+}
+
+} // namespace mtgl_dev_impl
+
+#endif

@@ -76,7 +76,7 @@ __device__ __forceinline__ void bin_small(const BatchDev &b, const FrameTargets 
             tx0 = (int)(box.x & 0xFFFFu) >> TILE_LOG; tx1 = (int)(box.y & 0xFFFFu) >> TILE_LOG;
             ty0 = ((int)(box.x >> 16) >> TILE_LOG) - fb.tile_y0; ty1 = ((int)(box.y >> 16) >> TILE_LOG) - fb.tile_y0;
             ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-            tflags = ((box.z & STATE_DEFER_BIT) ? 0u : 1u) | ((box.z & STATE_UNORD_BIT) ? 0u : 2u);
+            tflags = tile_flag_bits(box.z);
         }
         if (ntiles > LARGE_TILES) {
             if (PASS == 0) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void bin_large(const BatchDev &b, const FrameTargets 
             uint32_t tile = (uint32_t)(ty * fb.tiles_x + tx);
             if (PASS == 0) {
                 atomicAdd(&b.tile_count[tile], 1u);
-                const uint32_t tflags = ((rec->state_flags & STATE_DEFER_BIT) ? 0u : 1u) | ((rec->state_flags & STATE_UNORD_BIT) ? 0u : 2u);
+                const uint32_t tflags = tile_flag_bits(rec->state_flags);
                 if (tflags) atomicOr(&b.tile_flags[tile], tflags);
             } else {
                 uint32_t at = atomicAdd(&b.tile_cursor[tile], 1u);

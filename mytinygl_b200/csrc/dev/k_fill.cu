@@ -1,0 +1,667 @@
+/*
+ * k_fill.cu -- K4d: the in-order tile kernel for LARGE triangles (the fill-rate case, BASELINE config C3: 64 full-screen
+ * quads with texture, alpha test, stencil and blending).
+ *
+ * Replaces, for the tiles it owns, the scan loop and the per-fragment block of rasterize_triangle_smooth
+ * (src/raster.c:532-724) with edge_function (299-302), depth / alpha / stencil tests and ops (344-448), blending
+ * (360-387), write_pixel_masked (20-45), texture_sample_lod (src/textures.c:457-557) and glClear (src/gl_api.c:409-457)
+ * -- the same functions as k_raster<false> (k_raster.cu), with the work turned inside out:
+ *
+ *   k_raster<false>: a warp owns a 16x16 region, walks the sorted list and visits every 8x4 block of every triangle's
+ *                    box; the tile's planes live in shared memory and every fragment reads its triangle's 160-byte
+ *                    record from global memory (128 registers, ~580 instructions per fragment on C3).
+ *   k_fill:          a THREAD owns pixels.  Colour, depth and stencil of its pixels stay in registers while it walks the
+ *                    sorted list; what a triangle contributes to every pixel -- edge coefficients relative to the tile,
+ *                    u/w, v/w, colours, the resolved sampler plan -- is prepared once per (triangle, tile) by one thread
+ *                    and broadcast from shared memory; the texture is staged in shared memory as float4 texels, i.e.
+ *                    already divided by 255, so a bilinear tap is one 16-byte LDS; the two 8-bit conversions that follow
+ *                    every filter stage are done with two FP32 adds / an FMA pair (dev_fragment.cuh) instead of F2I and
+ *                    a bank-conflicting table look-up.
+ *
+ * Work decomposition: one CTA (8 warps) per 64x64 tile; in pass g warp w owns row 8 g + w of the tile and lane l the
+ * pixels x = l and x = l + 32 of that row: two independent fragments per thread for instruction-level parallelism,
+ * 128-byte coalesced plane accesses per warp, and a triangle's rows are spread evenly over the warps.  The list is sorted
+ * by submission id (shared memory rank sort), then handled in windows of 64 prepared triangles.
+ *
+ * Edge functions: when every product and every edge value over the tile is an integer below 2^24 (always for a
+ * 3840x2160 full-screen triangle), the reference's float expression is exact, so e = A x + B y + C with tile-relative
+ * integer x, y evaluated with FMAs gives the same bits; a triangle too large for that (7680x4320) uses the reference's
+ * expression operation for operation.
+ *
+ * A tile goes to this kernel when its list is in-order, holds only triangles and its mean clamped box covers at
+ * least a quarter of the tile (dev_fill.cuh); everything else stays with k_raster<false>.  States with per-fragment
+ * lighting are not handled here (the host does not launch the kernel for such batches).
+ *
+ * Roofline: algorithmically HBM-bound (stencil 2 B, depth 4 (+4) B, blend read 4 B, colour write 4 B per
+ * fragment in the reference's immediate-mode formulation); here the planes are read and written once per tile and
+ * window, and the kernel is bound by FP32 issue.
+ */
+#include "dev_common.cuh"
+#include "dev_texture.cuh"
+#include "dev_fragment.cuh"
+#include "dev_fill.cuh"
+
+namespace mtgl_dev_impl {
+
+void note_launch();
+
+constexpr int FILL_THREADS = 256;
+constexpr int FILL_WINDOW = 64;                         /* prepared triangles per window */
+constexpr int FILL_TEX_TEXELS = 64 * 64 + 32 * 32;      /* float4 texels staged per tile: a 64x64 texture with its level 1 */
+constexpr int FILL_PX = 2;                              /* pixels per thread: x = lane and x = lane + 32 of one row */
+
+/* bits 27..31 of PrepTri::eb.w (bits 0..26 = state / cfg index) */
+constexpr uint32_t PT_EXACT = 1u << 27;         /* e = A x + B y + C is exact over the tile */
+constexpr uint32_t PT_NEG = 1u << 28;           /* (inexact form only) negative area: edge values are negated */
+constexpr uint32_t PT_FASTTEX = 1u << 29;       /* textured from the staged texture, attributes finite and bounded */
+
+/* sampler plan (PrepTri::p1.z): what texture_sample_lod (textures.c:457-557) decides from the per-triangle LOD */
+constexpr uint32_t TP_A_KIND = 3u;              /* level sampled first: 0 level 0, 1 level 1, 2 opaque white (missing level 1), 3 none (weight 0) */
+constexpr uint32_t TP_A_LINEAR = 1u << 2;
+constexpr uint32_t TP_TRI = 1u << 3;            /* blend with a second level, weight cl */
+constexpr uint32_t TP_B_SHIFT = 4;              /* second level: kind in bits 4-5 */
+constexpr uint32_t TP_B_LINEAR = 1u << 6;
+constexpr uint32_t TP_REP_S = 1u << 7, TP_REP_T = 1u << 8;
+
+/* what one triangle contributes to every pixel of the tile: 12 x 16 B, read as broadcasts */
+struct __align__(16) PrepTri {
+    float4 ea;      /* A0 A1 A2 | 1/area            (all negated for clockwise triangles: one inclusive test e >= 0) */
+    float4 eb;      /* B0 B1 B2 | cfg index + PT_*  */
+    float4 ec;      /* C0 C1 C2 | box x0 | y0 << 8 | x1 << 16 | y1 << 24 (tile-relative, inclusive) */
+    float4 zz;      /* z0 z1 z2 | lod */
+    float4 c0, c1, c2;
+    float4 tu;      /* u0 u1 u2 (times 1/w when perspective-correct, raster.c:501-503) | 1/w0 */
+    float4 tv;      /* v0 v1 v2 (likewise) | 1/w1 */
+    float4 te;      /* eye z0 z1 z2 | 1/w2 */
+    float4 p0;      /* x0 y0 x1 y1 as floats: the reference form of the edge functions */
+    float4 p1;      /* x2 y2 | sampler plan | trilinear weight */
+};
+static_assert(sizeof(PrepTri) == 192, "PrepTri layout");
+
+struct FillSmem {
+    float4 tex[FILL_TEX_TEXELS];
+    PrepTri tri[FILL_WINDOW];
+    uint32_t key[FILL_MAX_LIST];
+    uint32_t rec[FILL_MAX_LIST];
+    uint32_t sorted[FILL_MAX_LIST];
+    float un[256];
+    uint32_t acc;               /* scratch of fill_owns_tile */
+    uint32_t tex_cfg;           /* state index whose texture is staged (lowest textured state of the list), ~0 = none */
+    const uint32_t *tex_l0;     /* identity of the staged texture */
+    int tw, th, tw1, th1, n0;   /* its dimensions; level 1 starts at tex[n0] */
+    uint32_t tex_ok;
+};
+/* two CTAs per SM */
+static_assert(2 * (sizeof(FillSmem) + 1024) <= 227 * 1024, "k_fill: two tiles per SM");
+
+/* ---------------------------------------------------------------- per-tile preparation */
+__device__ __forceinline__ uint32_t tile_box(uint32_t bbox_min, uint32_t bbox_max, int px0, int py0)
+{
+    const int x0 = max((int)(bbox_min & 0xFFFFu) - px0, 0), y0 = max((int)(bbox_min >> 16) - py0, 0);
+    const int x1 = min((int)(bbox_max & 0xFFFFu) - px0, TILE_W - 1), y1 = min((int)(bbox_max >> 16) - py0, TILE_H - 1);
+    return (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+}
+
+__device__ __forceinline__ bool bounded(float v, float lim) { return fabsf(v) <= lim; }   /* false for NaN */
+
+/* filter decision of texture_sample_lod (textures.c:457-523), which depends on the per-triangle LOD and the state only */
+__device__ __forceinline__ uint32_t sampler_plan(const RasterCfg *c, float lod, float &cl)
+{
+    uint32_t plan = (c->tex_wrap_s == G_REPEAT ? TP_REP_S : 0u) | (c->tex_wrap_t == G_REPEAT ? TP_REP_T : 0u);
+    cl = 0.0f;
+    uint32_t filter = (lod > 0.0f) ? c->tex_min : c->tex_mag;
+    const uint32_t l1_kind = c->tex_l1 ? 1u : 2u;           /* textures.c:413-419: a level that cannot exist samples as white */
+    if (filter == G_NEAREST_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_NEAREST) {
+        if (lod >= 0.5f) return plan | l1_kind | (filter == G_LINEAR_MIPMAP_NEAREST ? TP_A_LINEAR : 0u);
+        filter = (filter == G_NEAREST_MIPMAP_NEAREST) ? G_NEAREST : G_LINEAR;
+    } else if (filter == G_NEAREST_MIPMAP_LINEAR || filter == G_LINEAR_MIPMAP_LINEAR) {
+        if (lod > 0.0f) {
+            cl = (lod > 1.0f) ? 1.0f : lod;
+            plan |= TP_TRI | (l1_kind << TP_B_SHIFT) | (filter == G_LINEAR_MIPMAP_LINEAR ? TP_B_LINEAR : 0u);
+            if (cl == 1.0f) return plan | 3u;               /* weight of level 0 is exactly 0 (dev_texture.cuh, tex_taps) */
+            return plan | 0u | (filter != G_NEAREST_MIPMAP_LINEAR ? TP_A_LINEAR : 0u);
+        }
+        filter = (filter == G_NEAREST_MIPMAP_LINEAR) ? G_NEAREST : G_LINEAR;
+    }
+    return plan | 0u | (filter == G_LINEAR ? TP_A_LINEAR : 0u);
+}
+
+__device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm, uint32_t r, int px0, int py0)
+{
+    const TriRecord *rec = b.records + r;
+    const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
+    const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+    const uint4 row2 = __ldg(reinterpret_cast<const uint4 *>(rec) + 2);
+    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
+    const float4 row4 = __ldg(reinterpret_cast<const float4 *>(rec) + 4);
+    const float4 row8 = __ldg(reinterpret_cast<const float4 *>(rec) + 8);
+    const float4 row9 = __ldg(reinterpret_cast<const float4 *>(rec) + 9);
+    P.c0 = __ldg(reinterpret_cast<const float4 *>(rec) + 5);
+    P.c1 = __ldg(reinterpret_cast<const float4 *>(rec) + 6);
+    P.c2 = __ldg(reinterpret_cast<const float4 *>(rec) + 7);
+
+    const uint32_t cfg_index = row2.z & STATE_INDEX_MASK;
+    const RasterCfg *cfg = b.cfgs + cfg_index;
+    const uint32_t cflags = cfg->flags;
+    const float area = __int_as_float(row1.z), inv_area = __int_as_float(row1.w);
+    const bool pos = area > 0;
+    uint32_t word = cfg_index;
+
+    /* raster.c:536-538: w0 = edge(v1, v2, p), w1 = edge(v2, v0, p), w2 = edge(v0, v1, p) */
+    const int vx[3] = { row0.x, row0.z, row1.x }, vy[3] = { row0.y, row0.w, row1.y };
+    float A[3] = { 0.0f, 0.0f, 0.0f }, B[3] = { 0.0f, 0.0f, 0.0f }, C[3] = { 0.0f, 0.0f, 0.0f };
+    bool exact = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) exact = exact && abs((long long)vx[k]) < (1ll << 24) && abs((long long)vy[k]) < (1ll << 24);
+    if (exact) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const long long ax = vx[(k + 1) % 3], ay = vy[(k + 1) % 3], bx = vx[(k + 2) % 3], by = vy[(k + 2) % 3];
+            const long long dx = bx - ax, dy = by - ay;
+            /* over the tile's pixels: |px - ax| <= mx, |py - ay| <= my; both products and their difference must stay
+             * below 2^24 for the float expression of raster.c:299-302 to be exact */
+            const long long mx = max(abs((long long)px0 - ax), abs((long long)px0 + TILE_W - 1 - ax));
+            const long long my = max(abs((long long)py0 - ay), abs((long long)py0 + TILE_H - 1 - ay));
+            if (mx * abs(dy) + my * abs(dx) >= (1ll << 24)) exact = false;
+            const long long c = ((long long)px0 - ax) * dy - ((long long)py0 - ay) * dx;       /* the edge value at the tile's origin */
+            A[k] = (float)dy; B[k] = (float)-dx; C[k] = (float)c;
+        }
+    }
+    if (exact) {
+        word |= PT_EXACT;
+        if (!pos) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { A[k] = -A[k]; B[k] = -B[k]; C[k] = -C[k]; }
+        }
+    } else if (!pos) word |= PT_NEG;
+    P.ea = make_float4(A[0], A[1], A[2], pos ? inv_area : -inv_area);
+    P.ec = make_float4(C[0], C[1], C[2], __uint_as_float(tile_box(row2.x, row2.y, px0, py0)));
+    P.zz = row3;
+    P.p0 = make_float4((float)row0.x, (float)row0.y, (float)row0.z, (float)row0.w);
+
+    /* u/w, v/w per vertex (raster.c:501-503) */
+    float u[3] = { row8.x, row8.z, row9.x }, v[3] = { row8.y, row8.w, row9.y };
+    const float w[3] = { row4.x, row4.y, row4.z };
+    bool fast = (cflags & RC_TEXTURED) && sm.tex_ok && cfg->tex_l0 == sm.tex_l0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) fast = fast && bounded(u[k], 1048576.0f) && bounded(v[k], 1048576.0f) && w[k] >= 9.094947e-13f && w[k] <= 1.0995116e12f;
+    if (cflags & RC_PERSPECTIVE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { u[k] = u[k] * w[k]; v[k] = v[k] * w[k]; }
+    }
+    if (fast) word |= PT_FASTTEX;
+    P.tu = make_float4(u[0], u[1], u[2], w[0]);
+    P.tv = make_float4(v[0], v[1], v[2], w[1]);
+    P.te = make_float4(row4.w, row9.z, row9.w, w[2]);
+    float cl = 0.0f;
+    const uint32_t plan = (cflags & RC_TEXTURED) ? sampler_plan(cfg, row3.w, cl) : 0u;
+    P.p1 = make_float4((float)row1.x, (float)row1.y, __uint_as_float(plan), cl);
+    P.eb = make_float4(B[0], B[1], B[2], __uint_as_float(word));
+}
+
+/* ---------------------------------------------------------------- texture sampling from the staged float4 texels */
+struct FTaps { float4 t00, t10, t01, t11; float fx, fy; };
+
+/* bilinear taps of one level (texture_sample_base / _mip1, textures.c:379-451).  floor(t) for |t| < 2^22 by a
+ * round-down add of 1.5 * 2^23: the sum is 2^23 + 2^22 + floor(t) exactly, its low mantissa bits are the integer. */
+__device__ __forceinline__ void fast_taps(FTaps &T, const float4 *px, int w, int h, bool rep_s, bool rep_t, float u, float v)
+{
+    const float tx = u * (float)w - 0.5f, ty = v * (float)h - 0.5f;
+    const float M = 12582912.0f;
+    const float mx = __fadd_rd(tx, M), my = __fadd_rd(ty, M);
+    const int x0 = __float_as_int(mx) - 0x4B400000, y0 = __float_as_int(my) - 0x4B400000;
+    T.fx = tx - (mx - M); T.fy = ty - (my - M);
+    const int xa = wrap_coord(x0, w, rep_s), xb = wrap_coord(x0 + 1, w, rep_s);
+    const int ya = wrap_coord(y0, h, rep_t) * w, yb = wrap_coord(y0 + 1, h, rep_t) * w;
+    T.t00 = px[ya + xa]; T.t10 = px[ya + xb]; T.t01 = px[yb + xa]; T.t11 = px[yb + xb];
+}
+
+/* bilinear_filter (textures.c:294-307) of one channel, truncated to 8 bits, as the float n / 255 */
+__device__ __forceinline__ float fast_channel(float c00, float c10, float c01, float c11, float fx, float fy, float sx, float sy)
+{
+    const float top = c00 * sx + c10 * fx;
+    const float bot = c01 * sx + c11 * fx;
+    return unorm_of(byte_of(top * sy + bot * fy));
+}
+
+/* all four channels of one mip level as n / 255 floats */
+__device__ __forceinline__ float4 fast_level(const FillSmem &sm, uint32_t kind, bool linear, bool rep_s, bool rep_t, float u, float v)
+{
+    if (kind == 2u) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (kind == 3u) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float4 *px = kind ? sm.tex + sm.n0 : sm.tex;
+    const int w = kind ? sm.tw1 : sm.tw, h = kind ? sm.th1 : sm.th;
+    if (!linear) {          /* nearest: floor(u w), clamped, never wrapped (textures.c:394-403) */
+        int x = f2i_x86(floorf(u * (float)w - 0.5f + 0.5f)), y = f2i_x86(floorf(v * (float)h - 0.5f + 0.5f));
+        x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
+        return px[y * w + x];
+    }
+    FTaps T;
+    fast_taps(T, px, w, h, rep_s, rep_t, u, v);
+    const float sx = 1.0f - T.fx, sy = 1.0f - T.fy;
+    return make_float4(fast_channel(T.t00.x, T.t10.x, T.t01.x, T.t11.x, T.fx, T.fy, sx, sy),
+                       fast_channel(T.t00.y, T.t10.y, T.t01.y, T.t11.y, T.fx, T.fy, sx, sy),
+                       fast_channel(T.t00.z, T.t10.z, T.t01.z, T.t11.z, T.fx, T.fy, sx, sy),
+                       fast_channel(T.t00.w, T.t10.w, T.t01.w, T.t11.w, T.fx, T.fy, sx, sy));
+}
+
+/* the general sampler (any texture size, any attribute values) from global memory: dev_texture.cuh, out of line */
+__device__ __noinline__ bool slow_texel(const RasterCfg *cfg, const float *un, float u, float v, float lod, float4 *out)
+{
+    TexTaps T;
+    tex_taps(T, cfg, u, v, lod);
+    const float a = tex_channel(T, 24, un);
+    if ((cfg->flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, a, cfg->alpha_ref)) return false;
+    *out = make_float4(tex_channel(T, 0, un), tex_channel(T, 8, un), tex_channel(T, 16, un), a);
+    return true;
+}
+
+/* ---------------------------------------------------------------- one triangle over this thread's pixels */
+/* Pixel state of a thread: colour channels as integral floats 0..255 (the byte the plane holds), depth, stencil. */
+struct PixelState {
+    float r[FILL_PX], g[FILL_PX], b[FILL_PX], a[FILL_PX];
+    float depth[FILL_PX];
+    uint32_t stencil[FILL_PX];
+};
+
+template <uint32_t ON, uint32_t OFF>
+__device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem &sm, const PrepTri &T, int px0, int py0, int Y,
+                                              const int (&X)[FILL_PX], const bool (&inb)[FILL_PX], PixelState &S)
+{
+    constexpr int P = FILL_PX;
+    const uint32_t box = __float_as_uint(T.ec.w);
+    if (Y < (int)((box >> 8) & 0xFFu) || Y > (int)(box >> 24)) return;          /* warp-uniform */
+    const int bx0 = (int)(box & 0xFFu), bx1 = (int)((box >> 16) & 0xFFu);
+    const uint32_t word = __float_as_uint(T.eb.w);
+    const RasterCfg *cfg = b.cfgs + (word & STATE_INDEX_MASK);
+    const uint32_t fl = __ldg(&cfg->flags);
+    auto has = [&](uint32_t bit) -> bool { return (ON & bit) ? true : ((OFF & bit) ? false : (fl & bit) != 0u); };
+
+    /* ---- coverage: inclusive on all three edges, no fill rule (raster.c:539-540) ---- */
+    float e0[P], e1[P], e2[P];
+    if (word & PT_EXACT) {
+        const float4 ea = T.ea, eb = T.eb, ec = T.ec;
+        const float fy = (float)Y;
+        const float t0 = __fmaf_rn(eb.x, fy, ec.x), t1 = __fmaf_rn(eb.y, fy, ec.y), t2 = __fmaf_rn(eb.z, fy, ec.z);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const float fx = (float)X[p];
+            e0[p] = __fmaf_rn(ea.x, fx, t0); e1[p] = __fmaf_rn(ea.y, fx, t1); e2[p] = __fmaf_rn(ea.z, fx, t2);
+        }
+    } else {
+        const float4 p0 = T.p0, p1 = T.p1;
+        const float py = (float)(py0 + Y);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const float px = (float)(px0 + X[p]);
+            e0[p] = edge_at(p0.z, p0.w, p1.x, p1.y, px, py);
+            e1[p] = edge_at(p1.x, p1.y, p0.x, p0.y, px, py);
+            e2[p] = edge_at(p0.x, p0.y, p0.z, p0.w, px, py);
+            if (word & PT_NEG) { e0[p] = -e0[p]; e1[p] = -e1[p]; e2[p] = -e2[p]; }
+        }
+    }
+    bool act[P];
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        act[p] = inb[p] && X[p] >= bx0 && X[p] <= bx1 && fminf(fminf(e0[p], e1[p]), e2[p]) >= 0.0f;
+        any = any || act[p];
+    }
+    if (!any) return;
+
+    const float inv_area = T.ea.w;
+    float b0[P], b1[P], b2[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) { b0[p] = e0[p] * inv_area; b1[p] = e1[p] * inv_area; b2[p] = e2[p] * inv_area; }
+
+    /* ---- depth value, stencil test + ops, depth test (raster.c:546-587) ---- */
+    float depth[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) depth[p] = 0.0f;
+    const bool depth_test = has(RC_DEPTH_TEST);
+    uint32_t depth_func = 7u;
+    if (depth_test) {
+        const float4 zz = T.zz;
+        depth_func = __ldg(&cfg->depth_func);
+        const bool r01 = has(RC_DEPTH_RANGE_01);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const float z = b0[p] * zz.x + b1[p] * zz.y + b2[p] * zz.z;
+            if (r01) depth[p] = (z + 1.0f) * 0.5f;
+            else depth[p] = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
+        }
+    }
+    if (has(RC_STENCIL)) {
+        const uint32_t sfunc = __ldg(&cfg->stencil_func), smask = __ldg(&cfg->stencil_mask), swm = __ldg(&cfg->stencil_writemask) & 0xFFu;
+        const int32_t sref = __ldg(&cfg->stencil_ref);
+        const uint32_t op_fail = __ldg(&cfg->stencil_fail), op_zfail = __ldg(&cfg->stencil_zfail), op_zpass = __ldg(&cfg->stencil_zpass);
+        const int32_t mref = (int32_t)((uint32_t)sref & smask);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            if (!act[p]) continue;
+            const uint8_t sval = (uint8_t)S.stencil[p];
+            const int32_t mval = (int32_t)((uint32_t)sval & smask);
+            uint32_t op;
+            if (!compare_i(sfunc, mref, mval)) { op = op_fail; act[p] = false; }
+            else if (depth_test && !compare_f(depth_func, depth[p], S.depth[p])) { op = op_zfail; act[p] = false; }
+            else op = op_zpass;
+            const uint8_t nv = stencil_apply(op, sval, sref);
+            S.stencil[p] = (uint32_t)((sval & ~swm) | (nv & swm));
+        }
+    } else if (depth_test) {
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            if (act[p] && !compare_f(depth_func, depth[p], S.depth[p])) act[p] = false;
+    }
+    any = false;
+#pragma unroll
+    for (int p = 0; p < P; p++) any = any || act[p];
+    if (!any) return;
+    const bool depth_write = depth_test && has(RC_DEPTH_WRITE);
+
+    /* ---- texture first: the alpha test only looks at the texel's alpha (raster.c:640-643), so the fragments it
+     * discards never need their interpolated colour ---- */
+    float tr[P], tg[P], tb[P], ta[P];
+    const bool textured = has(RC_TEXTURED);
+    if (textured) {
+        const float4 tu = T.tu, tv = T.tv;
+        const float w2 = T.te.w;
+        float u[P], v[P];
+        if (has(RC_PERSPECTIVE)) {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float uw = b0[p] * tu.x + b1[p] * tu.y + b2[p] * tu.z;
+                const float vw = b0[p] * tv.x + b1[p] * tv.y + b2[p] * tv.z;
+                const float ow = b0[p] * tu.w + b1[p] * tv.w + b2[p] * w2;
+                const float w = 1.0f / ow;
+                u[p] = uw * w; v[p] = vw * w;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                u[p] = b0[p] * tu.x + b1[p] * tu.y + b2[p] * tu.z;
+                v[p] = b0[p] * tv.x + b1[p] * tv.y + b2[p] * tv.z;
+            }
+        }
+        const bool alpha_test = has(RC_ALPHA_TEST);
+        uint32_t afunc = 7u;
+        float aref = 0.0f;
+        if (alpha_test) { afunc = __ldg(&cfg->alpha_func); aref = __ldg(&cfg->alpha_ref); }
+        if (word & PT_FASTTEX) {
+            const uint32_t plan = __float_as_uint(T.p1.z);
+            const bool rep_s = (plan & TP_REP_S) != 0u, rep_t = (plan & TP_REP_T) != 0u;
+            /* wrap (textures.c:463-486) */
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (rep_s) { u[p] = u[p] - truncf(u[p]); if (u[p] < 0) u[p] += 1.0f; }
+                else { if (u[p] < 0.0f) u[p] = 0.0f; if (u[p] > 1.0f) u[p] = 1.0f; }
+                if (rep_t) { v[p] = v[p] - truncf(v[p]); if (v[p] < 0) v[p] += 1.0f; }
+                else { if (v[p] < 0.0f) v[p] = 0.0f; if (v[p] > 1.0f) v[p] = 1.0f; }
+            }
+            const uint32_t kind_a = plan & TP_A_KIND;
+            if (!(plan & TP_TRI) && (plan & TP_A_LINEAR) && kind_a <= 1u) {
+                /* one bilinear level (the magnified / non-mipmapped case): alpha first, colour channels only for survivors */
+                const float4 *px = kind_a ? sm.tex + sm.n0 : sm.tex;
+                const int w = kind_a ? sm.tw1 : sm.tw, h = kind_a ? sm.th1 : sm.th;
+                FTaps F[P];
+                float sx[P], sy[P];
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    fast_taps(F[p], px, w, h, rep_s, rep_t, u[p], v[p]);
+                    sx[p] = 1.0f - F[p].fx; sy[p] = 1.0f - F[p].fy;
+                    ta[p] = fast_channel(F[p].t00.w, F[p].t10.w, F[p].t01.w, F[p].t11.w, F[p].fx, F[p].fy, sx[p], sy[p]);
+                }
+                if (alpha_test) {
+                    any = false;
+#pragma unroll
+                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f(afunc, ta[p], aref); any = any || act[p]; }
+                    if (!any) return;
+                }
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    tr[p] = fast_channel(F[p].t00.x, F[p].t10.x, F[p].t01.x, F[p].t11.x, F[p].fx, F[p].fy, sx[p], sy[p]);
+                    tg[p] = fast_channel(F[p].t00.y, F[p].t10.y, F[p].t01.y, F[p].t11.y, F[p].fx, F[p].fy, sx[p], sy[p]);
+                    tb[p] = fast_channel(F[p].t00.z, F[p].t10.z, F[p].t01.z, F[p].t11.z, F[p].fx, F[p].fy, sx[p], sy[p]);
+                }
+            } else {
+                const float cl = T.p1.w, s = 1.0f - cl;
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    float4 t = fast_level(sm, kind_a, (plan & TP_A_LINEAR) != 0u, rep_s, rep_t, u[p], v[p]);
+                    if (plan & TP_TRI) {        /* textures.c:512-515: per channel, truncated to 8 bits once more */
+                        const float4 t1 = fast_level(sm, (plan >> TP_B_SHIFT) & 3u, (plan & TP_B_LINEAR) != 0u, rep_s, rep_t, u[p], v[p]);
+                        t.x = unorm_of(byte_of(t.x * s + t1.x * cl)); t.y = unorm_of(byte_of(t.y * s + t1.y * cl));
+                        t.z = unorm_of(byte_of(t.z * s + t1.z * cl)); t.w = unorm_of(byte_of(t.w * s + t1.w * cl));
+                    }
+                    tr[p] = t.x; tg[p] = t.y; tb[p] = t.z; ta[p] = t.w;
+                }
+                if (alpha_test) {
+                    any = false;
+#pragma unroll
+                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f(afunc, ta[p], aref); any = any || act[p]; }
+                    if (!any) return;
+                }
+            }
+        } else {
+            const float lod = T.zz.w;
+            any = false;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (!act[p]) continue;
+                float4 t;
+                if (slow_texel(cfg, sm.un, u[p], v[p], lod, &t)) { tr[p] = t.x; tg[p] = t.y; tb[p] = t.z; ta[p] = t.w; any = true; }
+                else act[p] = false;
+            }
+            if (!any) return;
+        }
+    }
+
+    /* ---- colour (raster.c:581-591), texenv (645-669), fog (672-705) ---- */
+    float cr[P], cg[P], cb[P], ca[P];
+    {
+        const float4 c2 = T.c2;
+        if (has(RC_FLAT)) {
+#pragma unroll
+            for (int p = 0; p < P; p++) { cr[p] = c2.x; cg[p] = c2.y; cb[p] = c2.z; ca[p] = c2.w; }
+        } else {
+            const float4 c0 = T.c0, c1 = T.c1;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                cr[p] = c0.x * b0[p] + c1.x * b1[p] + c2.x * b2[p];
+                cg[p] = c0.y * b0[p] + c1.y * b1[p] + c2.y * b2[p];
+                cb[p] = c0.z * b0[p] + c1.z * b1[p] + c2.z * b2[p];
+                ca[p] = c0.w * b0[p] + c1.w * b1[p] + c2.w * b2[p];
+            }
+        }
+    }
+    if (textured) {
+        const uint32_t env = __ldg(&cfg->tex_env_mode);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            switch (env) {
+            case G_REPLACE: cr[p] = tr[p]; cg[p] = tg[p]; cb[p] = tb[p]; ca[p] = ta[p]; break;
+            case G_DECAL:
+                cr[p] = cr[p] + (tr[p] - cr[p]) * ta[p]; cg[p] = cg[p] + (tg[p] - cg[p]) * ta[p]; cb[p] = cb[p] + (tb[p] - cb[p]) * ta[p];
+                break;
+            case G_BLEND: {
+                const float *ec = cfg->tex_env_color;
+                cr[p] = cr[p] * (1.0f - tr[p]) + ec[0] * tr[p]; cg[p] = cg[p] * (1.0f - tg[p]) + ec[1] * tg[p];
+                cb[p] = cb[p] * (1.0f - tb[p]) + ec[2] * tb[p]; ca[p] = ca[p] * ta[p];
+                break;
+            }
+            case G_ADD: cr[p] = cr[p] + tr[p]; cg[p] = cg[p] + tg[p]; cb[p] = cb[p] + tb[p]; ca[p] = ca[p] * ta[p]; break;
+            default: cr[p] = cr[p] * tr[p]; cg[p] = cg[p] * tg[p]; cb[p] = cb[p] * tb[p]; ca[p] = ca[p] * ta[p]; break;
+            }
+        }
+    }
+    if (has(RC_FOG)) {
+        const float4 te = T.te;
+        const float fr = cfg->fog_color[0], fg = cfg->fog_color[1], fbl = cfg->fog_color[2], fa = cfg->fog_color[3];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const float f = fog_factor(cfg, b0[p] * te.x + b1[p] * te.y + b2[p] * te.z);
+            cr[p] = fr + (cr[p] - fr) * f; cg[p] = fg + (cg[p] - fg) * f; cb[p] = fbl + (cb[p] - fbl) * f; ca[p] = fa;   /* color_lerp_rgb(fog, c, f) */
+        }
+    }
+
+    /* ---- late depth write (707-710), blending (712-717), masked write (719-721, 20-45) ---- */
+    const bool blend = has(RC_BLEND);
+    uint32_t bsrc = G_ONE, bdst = G_ZERO;
+    if (blend) { bsrc = __ldg(&cfg->blend_src); bdst = __ldg(&cfg->blend_dst); }
+    const uint32_t cm = __ldg(&cfg->color_mask);
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        if (!act[p]) continue;
+        if (depth_write) S.depth[p] = depth[p];
+        Color4 c = { cr[p], cg[p], cb[p], ca[p] };
+        if (blend) {
+            const Color4 d = { unorm_of(S.r[p]), unorm_of(S.g[p]), unorm_of(S.b[p]), unorm_of(S.a[p]) };
+            const Color4 sf = blend_factor(bsrc, c, d), df = blend_factor(bdst, c, d);
+            /* blend_colors clamps, raster.c:719 clamps again, color_to_rgba32 clamps a third time: byte_of saturates once */
+            c = { c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a };
+        }
+        if (cm == 0xFu) { S.r[p] = byte_of(c.r); S.g[p] = byte_of(c.g); S.b[p] = byte_of(c.b); S.a[p] = byte_of(c.a); }
+        else if (cm != 0u) {
+            /* partial mask: the reference unpacks the pixel, replaces the enabled channels and packs ALL of them again */
+            S.r[p] = byte_of((cm & 1u) ? c.r : unorm_of(S.r[p]));
+            S.g[p] = byte_of((cm & 2u) ? c.g : unorm_of(S.g[p]));
+            S.b[p] = byte_of((cm & 4u) ? c.b : unorm_of(S.b[p]));
+            S.a[p] = byte_of((cm & 8u) ? c.a : unorm_of(S.a[p]));
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- the kernel */
+template <uint32_t ON, uint32_t OFF>
+__global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t fill_mode)
+{
+    extern __shared__ __align__(16) unsigned char fill_smem_raw[];
+    FillSmem &sm = *reinterpret_cast<FillSmem *>(fill_smem_raw);
+    if (!lists_fit(b) || !b.tile_count) return;
+
+    const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
+    const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
+    const int px0 = tx << TILE_LOG, py0t = ty << TILE_LOG;
+    const int py0 = max(py0t, fb.band_y0);          /* row 0 of the tile's coordinate system: its first row inside the band */
+    const int vw = min(TILE_W, fb.width - px0);
+    const int vh = min(py0t + TILE_H, fb.band_y1) - py0;
+    if (vw <= 0 || vh <= 0) return;
+    const uint32_t L = b.tile_count[tile];
+    if (L == 0u) return;
+    const uint32_t *list = b.tile_list + b.tile_offset[tile];
+    if (!fill_owns_tile(b, fill_mode, L, b.tile_flags[tile], list, px0, py0, vh, &sm.acc)) return;
+
+    /* ---- list -> shared memory, sorted by submission id; the texture to stage ---- */
+    sm.un[threadIdx.x] = b.unorm8[threadIdx.x];
+    if (threadIdx.x == 0) { sm.tex_cfg = 0xFFFFFFFFu; sm.tex_ok = 0u; sm.tex_l0 = nullptr; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < L; i += FILL_THREADS) {
+        const uint32_t r = list[i];
+        const uint4 row = __ldg(b.bin_rows + r);
+        sm.key[i] = row.w;
+        sm.rec[i] = r;
+        const uint32_t ci = row.z & STATE_INDEX_MASK;
+        if (b.cfgs[ci].flags & RC_TEXTURED) atomicMin(&sm.tex_cfg, ci);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < L; i += FILL_THREADS) {      /* ids are unique: the rank is the sorted position */
+        const uint32_t mine = sm.key[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < L; j++) rank += (sm.key[j] < mine) ? 1u : 0u;
+        sm.sorted[rank] = sm.rec[i];
+    }
+    if (sm.tex_cfg != 0xFFFFFFFFu) {
+        const RasterCfg *tc = b.cfgs + sm.tex_cfg;
+        const int n0 = tc->tex_w * tc->tex_h, n1 = tc->tex_l1 ? tc->tex_w1 * tc->tex_h1 : 0;
+        if (n0 + n1 <= FILL_TEX_TEXELS) {
+            for (int i = threadIdx.x; i < n0 + n1; i += FILL_THREADS) {
+                const uint32_t t = (i < n0) ? __ldg(tc->tex_l0 + i) : __ldg(tc->tex_l1 + (i - n0));
+                sm.tex[i] = make_float4(sm.un[t & 0xFFu], sm.un[(t >> 8) & 0xFFu], sm.un[(t >> 16) & 0xFFu], sm.un[t >> 24]);
+            }
+            if (threadIdx.x == 0) {
+                sm.tex_l0 = tc->tex_l0; sm.tw = tc->tex_w; sm.th = tc->tex_h; sm.tw1 = tc->tex_w1; sm.th1 = tc->tex_h1; sm.n0 = n0;
+                sm.tex_ok = 1u;
+            }
+        }
+    }
+
+    /* ---- clear rectangle relative to the tile (gl_api.c:409-457) ---- */
+    const int cx0 = max(clr.x0 - px0, 0), cy0 = max(clr.y0 - py0, 0);
+    const int cx1 = min(clr.x1 - px0, vw), cy1 = min(clr.y1 - py0, vh);
+    const bool clr_any = clr.mask && cx0 < cx1 && cy0 < cy1;
+
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    int X[FILL_PX];
+#pragma unroll
+    for (int p = 0; p < FILL_PX; p++) X[p] = lane + 32 * p;
+
+    for (uint32_t w0 = 0; w0 < L; w0 += FILL_WINDOW) {
+        const uint32_t n = min((uint32_t)FILL_WINDOW, L - w0);
+        __syncthreads();                /* sorted list + staged texture complete; the previous window is no longer read */
+        if (threadIdx.x < n) prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], px0, py0);
+        __syncthreads();
+
+        for (int g = 0; g < TILE_H / 8; g++) {
+            const int Y = g * 8 + warp;
+            if (Y >= vh) break;
+            const size_t rowp = (size_t)(py0 + Y) * fb.width + px0;
+            bool inb[FILL_PX];
+            PixelState S;
+            const bool first = (w0 == 0u);
+#pragma unroll
+            for (int p = 0; p < FILL_PX; p++) {
+                inb[p] = X[p] < vw;
+                const bool in_clr = first && clr_any && X[p] >= cx0 && X[p] < cx1 && Y >= cy0 && Y < cy1;
+                uint32_t c = 0;
+                S.depth[p] = 0.0f; S.stencil[p] = 0u;
+                if (inb[p]) {
+                    if (planes & 1u) c = (in_clr && (clr.mask & G_COLOR_BUFFER_BIT)) ? clr.color : fb.color[rowp + X[p]];
+                    if (planes & 2u) S.depth[p] = (in_clr && (clr.mask & G_DEPTH_BUFFER_BIT)) ? clr.depth : fb.depth[rowp + X[p]];
+                    if (planes & 4u) S.stencil[p] = (in_clr && (clr.mask & G_STENCIL_BUFFER_BIT)) ? (clr.stencil & 0xFFu) : (uint32_t)fb.stencil[rowp + X[p]];
+                }
+                S.r[p] = (float)(c & 0xFFu); S.g[p] = (float)((c >> 8) & 0xFFu); S.b[p] = (float)((c >> 16) & 0xFFu); S.a[p] = (float)(c >> 24);
+            }
+#pragma unroll 1
+            for (uint32_t t = 0; t < n; t++) fill_triangle<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, S);
+#pragma unroll
+            for (int p = 0; p < FILL_PX; p++) {
+                if (!inb[p]) continue;
+                if (planes & 1u) {
+                    const uint32_t c = __float2uint_rz(S.r[p]) | (__float2uint_rz(S.g[p]) << 8) | (__float2uint_rz(S.b[p]) << 16) | (__float2uint_rz(S.a[p]) << 24);
+                    fb.color[rowp + X[p]] = c;
+                    if (fb.present && w0 + FILL_WINDOW >= L) fb.present[rowp + X[p]] = c;       /* fused gather: the finished row goes to the presenting GPU */
+                }
+                if (planes & 2u) fb.depth[rowp + X[p]] = S.depth[p];
+                if (planes & 4u) fb.stencil[rowp + X[p]] = (uint8_t)S.stencil[p];
+            }
+        }
+    }
+}
+
+/* The fill-rate state mix (C3): textured, no depth test, no fog, smooth shading -- the dead tests and their registers
+ * leave the kernel.  Everything else runs the fully dynamic instance. */
+constexpr uint32_t FILL_FAST_ON = RC_TEXTURED;
+constexpr uint32_t FILL_FAST_OFF = RC_DEPTH_TEST | RC_FOG | RC_FLAT;
+
+void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
+                 cudaStream_t s)
+{
+    static bool configured[64] = { false };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(k_fill<0u, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
+        cudaFuncSetAttribute(k_fill<FILL_FAST_ON, FILL_FAST_OFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
+        configured[dev] = true;
+    }
+    const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
+    if (tiles == 0 || fill_mode == FILL_OFF) return;
+    /* all_on / any_on: AND / OR of the RasterCfg flags of the pass's in-order states */
+    if ((all_on & FILL_FAST_ON) == FILL_FAST_ON && (any_on & FILL_FAST_OFF) == 0u)
+        k_fill<FILL_FAST_ON, FILL_FAST_OFF><<<tiles, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode);
+    else
+        k_fill<0u, 0u><<<tiles, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode);
+    note_launch();
+}
+
+} // namespace mtgl_dev_impl

@@ -30,6 +30,8 @@
  */
 #include "dev_common.cuh"
 #include "dev_texture.cuh"
+#include "dev_fragment.cuh"
+#include "dev_fill.cuh"
 
 namespace mtgl_dev_impl {
 
@@ -61,41 +63,6 @@ struct RasterSmem {
 };
 static_assert(sizeof(uint16_t) * (RASTER_THREADS / 32) * REGION_W * REGION_H <= sizeof(uint32_t) * LIST_WINDOW, "pending lists must fit in the key array");
 static_assert((LIST_WINDOW & (LIST_WINDOW - 1)) == 0, "the bitonic sort pads to a power of two");
-
-/* ---------------------------------------------------------------- per-fragment helpers */
-__device__ __forceinline__ uint8_t stencil_apply(uint32_t op, uint8_t v, int32_t ref)   /* raster.c:425-438 */
-{
-    switch (op) {
-    case G_KEEP: return v;
-    case G_ZERO: return 0;
-    case G_REPLACE: return (uint8_t)(ref & 0xFF);
-    case G_INCR: return v < 255 ? (uint8_t)(v + 1) : (uint8_t)255;
-    case G_INCR_WRAP: return (uint8_t)(v + 1);
-    case G_DECR: return v > 0 ? (uint8_t)(v - 1) : (uint8_t)0;
-    case G_DECR_WRAP: return (uint8_t)(v - 1);
-    case G_INVERT: return (uint8_t)~v;
-    default: return v;
-    }
-}
-
-__device__ __forceinline__ float fog_factor(const RasterCfg *c, float coord)   /* raster.c:677-701 */
-{
-    float f;
-    switch (c->fog_mode) {
-    case G_LINEAR: f = (c->fog_end != c->fog_start) ? (c->fog_end - coord) / (c->fog_end - c->fog_start) : 1.0f; break;
-    case G_EXP: f = expf(-c->fog_density * coord); break;
-    case G_EXP2: { float d = c->fog_density * coord; f = expf(-d * d); break; }
-    default: f = 1.0f; break;
-    }
-    if (f < 0.0f) f = 0.0f;
-    if (f > 1.0f) f = 1.0f;
-    return f;
-}
-
-__device__ __forceinline__ float edge_at(float ax, float ay, float bx, float by, float px, float py)   /* raster.c:299-302 */
-{
-    return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
-}
 
 /* the interpolants of one record (rows 3-9), loaded uniformly per triangle or per lane when shading is deferred */
 struct TriAttr {
@@ -806,7 +773,7 @@ __device__ void process_window(const BatchDev &b, RasterSmem &sm, uint32_t n, in
  * general tile, no lines, no points -- so the deferred-shading bookkeeping and the kind dispatch are compiled out
  * (the fill-rate case C3: fewer live registers in the block loop). */
 template <bool VIS, bool PLAIN>
-__global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t only_flagged)
+__global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t only_flagged, uint32_t fill_mode)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem &sm = *reinterpret_cast<RasterSmem *>(smem_raw);
@@ -828,6 +795,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
     if (VIS ? (flagged != 2u) : (only_flagged && !(flagged & 1u))) return;
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;
     if (L == 0 && !clr_here) return;
+    /* in-order tiles of large triangles belong to the pixel-owner kernel (k_fill.cu), which is launched over the same grid */
+    if (!VIS && L && fill_owns_tile(b, fill_mode, L, flagged, b.tile_list + b.tile_offset[tile], px0, py0, vh, &sm.count)) return;
 
     for (int i = threadIdx.x; i < 256; i += RASTER_THREADS) sm.unorm8[i] = b.unorm8[i];
     if (threadIdx.x < NUM_REGIONS) sm.region_work[threadIdx.x] = 0;
@@ -1051,7 +1020,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         /* tiles whose records are all order-independent (and the tiles that only need clearing) */
         launch_vis_unordered(b, fb, clear, planes, plan.unordered_func ? plan.unordered_func : 1u, plan.unordered_range01, s);
         if (plan.any_ordered_vis) {
-            k_raster<true, false><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u);
+            k_raster<true, false><<<tiles, RASTER_THREADS, smem_vis, s>>>(b, fb, clear, planes, 0u, 0u);
             note_launch();
         }
         cudaEventRecord(ev_vis, s);
@@ -1062,15 +1031,17 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         }
         cudaEventRecord(ev_shade, s);
         if (any_in_order) {
-            k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u);
+            k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u, plan.fill_mode);
             note_launch();
+            launch_fill(b, fb, clear, planes, plan.fill_mode, plan.in_order_all, plan.in_order_any, s);
         }
     } else {
         cudaEventRecord(ev_vis, s);
         cudaEventRecord(ev_shade, s);
-        if (plan.plain_in_order) k_raster<false, true><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
-        else k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u);
+        if (plan.plain_in_order) k_raster<false, true><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u, plan.fill_mode);
+        else k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u, plan.fill_mode);
         note_launch();
+        if (b.tile_count) launch_fill(b, fb, clear, planes, plan.fill_mode, plan.in_order_all, plan.in_order_any, s);
     }
 }
 

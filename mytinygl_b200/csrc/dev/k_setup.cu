@@ -142,7 +142,7 @@ __device__ __forceinline__ void count_tiles_single(const BinOut &bo, uint32_t r,
         bo.large_list[atomicAdd(&bo.counters->large_count, 1u)] = r;
         return;
     }
-    const uint32_t tflags = ((state_flags & STATE_DEFER_BIT) ? 0u : 1u) | ((state_flags & STATE_UNORD_BIT) ? 0u : 2u);
+    const uint32_t tflags = tile_flag_bits(state_flags);
     for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) {
             const uint32_t tile = (uint32_t)(ty * bo.tiles_x + tx);
@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     const uint32_t single = __ballot_sync(0xFFFFFFFFu, ntiles == 1);
     if (ntiles == 1) {
         const uint32_t tile = (uint32_t)(ty0 * fb.tiles_x + tx0);
-        const uint32_t tflags = ((row.z & STATE_DEFER_BIT) ? 0u : 1u) | ((row.z & STATE_UNORD_BIT) ? 0u : 2u);
+        const uint32_t tflags = tile_flag_bits(row.z);
         const uint32_t peers = __match_any_sync(single, tile);
         if ((int)lane == __ffs(peers) - 1) atomicAdd(&b.tile_count[tile], (uint32_t)__popc(peers));
         if (tflags) atomicOr(&b.tile_flags[tile], tflags);

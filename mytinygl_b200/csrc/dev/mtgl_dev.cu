@@ -16,6 +16,7 @@
  * There is no CPU path in this file: every entry point either runs CUDA work or fails.
  */
 #include "dev_common.cuh"
+#include "dev_fill.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -784,6 +785,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         }
         CU(cudaEventRecord(sev[4], d->stream));
         bool any_defer = false, any_in_order = false, any_ordered_vis = false, any_not_plain = false;
+        uint32_t flags_all = 0xFFFFFFFFu, flags_any = 0u;
         for (const PassDraw &q : passes[pidx]) {
             const mtgl_draw &dq = bt->draws[q.draw];
             const mtgl_state &sq = bt->states[dq.raster_state];
@@ -793,6 +795,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if ((cf & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */
             if ((cf & RC_DEFER) && !(cf & RC_UNORDERED) && dq.mode >= G_TRIANGLES) any_ordered_vis = true;
             if ((cf & RC_DEFER) || !filled) any_not_plain = true;
+            flags_all &= cf; flags_any |= cf;
         }
         RasterPlan plan;
         plan.any_deferrable = any_defer && pi.n_triangles > 0;
@@ -801,6 +804,12 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         plan.plain_in_order = any_in_order && !any_not_plain;
         plan.unordered_func = unordered_func;
         plan.unordered_range01 = unordered_range01;
+        /* the pixel-owner kernel for in-order tiles of large triangles (k_fill.cu); it has no per-fragment lighting.
+         * MTGL_FILL=never|always: A/B switch for profiling and tests (always: every eligible in-order tile, whatever its triangles' size) */
+        uint32_t fill_env = FILL_AUTO;       /* read per batch (not cached): the tests switch it between frames */
+        if (const char *e = std::getenv("MTGL_FILL")) fill_env = !std::strcmp(e, "never") ? FILL_OFF : (!std::strcmp(e, "always") ? FILL_ALWAYS : FILL_AUTO);
+        plan.fill_mode = (need_eye || !had_triangles) ? FILL_OFF : fill_env;
+        plan.in_order_all = flags_all; plan.in_order_any = flags_any;
         launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
         CU(cudaEventRecord(sev[5], d->stream));
         t_launched = std::chrono::steady_clock::now();

@@ -39,6 +39,16 @@ CASES = (
     + [("c4_grid", 480, 270, C4_SMALL | (1 << 17)), ("c4_grid", 960, 540, 6 | (4 << 8) | (1 << 17))]     # one mesh, many draws
 )
 
+# Above 4096 pixels the float edge functions of large triangles round (products beyond 2^24, raster.c:299-302): the
+# cases the CUDA path must reproduce with the reference's own expression instead of its exact integer forms.
+LARGE_CASES = [
+    ("c3_fill", 7680, 4320, 2),          # full-screen quads: in-order tiles, k_fill's inexact edge form
+    ("c2_cube", 7680, 4320, 0),          # large deferred triangles: k_vis phase 2 / raster_blocks
+    ("clipping", 7680, 4320, 0),         # clipped fans, ordered visibility
+    ("blend", 7680, 4320, 3),
+    ("c3_fill", 4100, 4100, 1),          # just above 4096, width not a multiple of the tile
+]
+
 
 def case_id(c):
     return f"{c[0]}-{c[1]}x{c[2]}-v{c[3]}"

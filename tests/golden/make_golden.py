@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-from cases import CASES, case_id  # noqa: E402
+from cases import CASES, LARGE_CASES, case_id  # noqa: E402
 from mytinygl_b200 import load_reference  # noqa: E402
 
 
@@ -25,7 +25,7 @@ def digest(a):
 def main():
     ref = load_reference("strict")
     out = {}
-    for c in CASES:
+    for c in CASES + LARGE_CASES:
         col, dep, sten, err = ref.render(*c)
         out[case_id(c)] = {
             "color": digest(col), "depth": digest(dep), "stencil": digest(sten), "gl_error": int(err),

@@ -6,7 +6,7 @@ import json
 import numpy as np
 import pytest
 
-from cases import CASES, case_id
+from cases import CASES, LARGE_CASES, case_id
 from mytinygl_b200 import REPO_ROOT
 from parity import assert_gate, compare_planes
 
@@ -18,15 +18,37 @@ def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("case", CASES, ids=case_id)
+@pytest.mark.parametrize("case", CASES + LARGE_CASES, ids=case_id)
 def test_cuda_matches_oracle(b200, front_oracle, case):
     got = b200.render(*case)
     ref = front_oracle.render(*case)
     stats = compare_planes(ref, got)
     assert_gate(stats, case_id(case))
     assert got[3] == ref[3]                      # sticky GL error code
-    # integer-domain results must also match the reference's committed hashes exactly
+    # integer-domain results must also match the reference's committed hashes exactly; so must depth, which is a function
+    # of the positions alone (no libm on the device between a vertex and its depth)
     assert digest(got[2]) == GOLDEN[case_id(case)]["stencil"]
+    assert digest(got[1]) == GOLDEN[case_id(case)]["depth"]
+
+
+# scenes with in-order states (blending, textured alpha test, colour masks, stencil + blend ...) on triangles of any size
+FILL_SCENES = {"c3_fill", "c2_texenv", "blend", "stencil", "fog", "texture_misc", "state_churn", "scissor", "zbuffer", "depth_order",
+               "clipping", "primitives", "pixels", "validation", "c2_floor", "c2_cube"}
+
+
+@pytest.mark.parametrize("mode", ["always", "never"])
+@pytest.mark.parametrize("case", [c for c in CASES + LARGE_CASES if c[0] in FILL_SCENES], ids=case_id)
+def test_in_order_tile_kernels(b200, front_oracle, case, mode, monkeypatch):
+    """In-order tiles have two kernels: k_fill (a thread owns pixels; takes the tiles of large triangles) and
+    k_raster<false> (a warp owns a region; small triangles, lines, points).  MTGL_FILL=always sends every eligible tile
+    through the first, never through the second: both must reproduce the reference on every in-order case, whatever the
+    triangle size."""
+    monkeypatch.setenv("MTGL_FILL", mode)
+    got = b200.render(*case)
+    ref = front_oracle.render(*case)
+    assert_gate(compare_planes(ref, got), case_id(case))
+    assert digest(got[2]) == GOLDEN[case_id(case)]["stencil"]
+    assert digest(got[1]) == GOLDEN[case_id(case)]["depth"]
 
 
 def test_exactness_report(b200, front_oracle):
