@@ -1,26 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native MyTinyGL back end.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c3|c5|c4i]
+                    [--no-secondary] [--no-parity] [--no-cpu-baseline]
 
 A "step" is one frame of the workload: glClear + the draw calls + whatever makes the result observable.
-Default workload: C4 of BASELINE.json -- 38x28 Suzannes (1 029 952 triangles, 3 089 856 vertices), 8 lights,
+Headline workload: C4 of BASELINE.json -- 38x28 Suzannes (1 029 952 triangles, 3 089 856 vertices), 8 lights,
 trilinear 64x64 texture, one glDrawArrays from a VBO, 3840x2160.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   value        covered fragments/s with the VBO and texture resident in HBM (device-timed, K frames)
-  e2e          the same metric with the per-frame host->device upload of the 98.9 MB vertex buffer from pinned
-               host memory and the device->host read-back of the colour plane inside the timed region,
-               through the public gl* API + the C ABI
-  roofline     the tile raster kernel (K4/K5): algorithmic framebuffer bytes per launch (SURVEY.md 8d:
-               4 B per covered + 8 B per depth-passing fragment + cleared bytes) / its CUDA-event duration,
-               against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  e2e          the same metric with the per-frame host->device upload of the 98.9 MB vertex buffer from pinned host
+               memory and the device->host read-back of the colour plane inside the timed region, through the public
+               gl* API + the C ABI
+  roofline     the step's dominant kernel (whichever the live per-group CUDA-event times say): its algorithmic bytes
+               per launch / its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline the unmodified reference (as-shipped flags, 1 thread) on this box's host CPU
   stages_ms    CUDA-event time per pipeline stage, mean over the timed steps
+  parity       the headline frame rendered once more by the unmodified reference (strict IEEE build,
+               oracle/_ref/libref_strict.so) on this box and compared with the CUDA frame: the checker leg
+  secondary    the other two BASELINE workloads measured the same way in the same run, at every N:
+               c3_fill_3840x2160 (64 full-screen quads, alpha + stencil + blend) and c5_grid_7680x4320 (C4 at 8K),
+               each with ms_per_step, value, roofline, parity and -- for N > 1 -- gather_check
 
-Multi-GPU (torchrun, one rank per GPU): sort-first bands of framebuffer rows; every rank runs the vertex and
-set-up stages on the whole scene and bins / rasterises only its band; the colour bands are gathered into
-rank 0's framebuffer with NCCL point-to-point over NVLink.  Total work is fixed: "scaling": "strong".
+Multi-GPU (torchrun, one rank per GPU): sort-first bands of framebuffer rows.  Every rank receives the whole command
+stream; a culling pass drops the 256-triangle chunks that cannot reach its band before set-up touches them, and it
+bins / rasterises only its band.  The raster kernels store every finished tile both locally and -- over NVLink peer
+memory -- into rank 0's colour plane (fused gather); a frame-barrier kernel per rank ends the frame.  NCCL bootstraps
+the group (and all-gathers the sharded vertex-buffer upload of the end-to-end step).  Total work is fixed:
+"scaling": "strong".
 """
 from __future__ import annotations
 
@@ -38,8 +46,9 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
 
-from mytinygl_b200 import load_b200, load_reference  # noqa: E402
+from mytinygl_b200 import load_b200  # noqa: E402
 
 GL_ARRAY_BUFFER = 0x8892
 GL_STATIC_DRAW = 0x88E4
@@ -52,6 +61,7 @@ WORKLOADS = {
     # SURVEY.md 8(d) secondary layout: ONE Suzanne in the VBO, 1064 glDrawArrays under glPushMatrix / glTranslatef
     "c4i": ("c4_instanced_3840x2160", 3840, 2160, 1 << 17),
 }
+SCENE_OF = {"c4": "c4_grid", "c5": "c4_grid", "c4i": "c4_grid", "c3": "c3_fill"}
 
 
 class Stats(ctypes.Structure):
@@ -71,6 +81,16 @@ def peaks():
     if p.exists():
         return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(workload, world):
+    """The `config` object: what the workload is.  Both arms (this back end and --impl reference) print exactly this."""
+    key, w, h, _ = WORKLOADS[workload]
+    cnt = counts_for(key)
+    return {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3 if cnt["vertices"] else (128 if workload == "c3" else 0),
+            "covered_fragments": cnt["covered"], "depth_passing_fragments": cnt["tested"], "shaded_fragments": cnt["shaded"],
+            "partition": f"sort-first bands x{world}",
+            "l2": "flushed between frames (256 MiB fill)" if workload == "c3" else "inputs larger than L2 (>330 MB streamed per frame)"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -112,22 +132,33 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, workload):
+def load_reference(kind):
+    """The unmodified reference compiled by `make ref` (oracle/_ref/).  Only the reference arm, the cpu_baseline leg and
+    the parity leg of this file come here; the loader lives with the tests, not in the product package."""
+    from oracle_loader import load_reference as _load
+    return _load(kind)
+
+
+def run_reference(args, workload, steps=None, warmup=None):
     """The reference's own CPU implementation, unmodified, as-shipped flags, one thread (it has no threading)."""
     key, w, h, variant = WORKLOADS[workload]
     cnt = counts_for(key)
     lib = load_reference("shipped")
     lib.create(w, h)
-    steps = max(1, min(args.steps, 3))           # a C4 frame takes ~3 s on one host core
-    warm = 1 if args.warmup > 0 else 0
+    steps = max(1, args.steps if steps is None else steps)
+    warm = max(0, args.warmup if warmup is None else warmup)
     times = []
     if workload == "c3":
-        for i in range(warm + 1):                # ~40 s per frame: a single timed frame is the bounded sample
+        # one C3 frame takes ~40 s on a host core: a step is a bounded sample -- the first 8 of the 64 quads (the state
+        # mix and the per-fragment work are the same for every quad), scaled to the frame by fragment count
+        sample_quads = 8
+        frac = sample_quads / 64.0
+        for i in range(min(warm, 1) + min(steps, 3)):
             t0 = time.perf_counter()
-            lib.lib.scene_render(b"c3_fill", w, h, variant)
-            times.append(time.perf_counter() - t0)
-        times = times[-1:]
-        sample = "1 full C3 frame (64 full-screen quads)"
+            lib.lib.scene_render(b"c3_fill", w, h, sample_quads)
+            if i >= min(warm, 1):
+                times.append((time.perf_counter() - t0) / frac)
+        sample = f"{len(times)} steps of {sample_quads} of the 64 full-screen quads each, time scaled by 64/{sample_quads}"
     else:
         lib.lib.scene_c4_setup(w, h, variant)
         for i in range(warm + steps):
@@ -142,10 +173,10 @@ def run_reference(args, workload):
     value = cnt["covered"] / t
     return {
         "impl": "reference", "metric": "covered_fragments_per_s", "value": value, "unit": "fragments/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": 1.0 / t,
-        "config": {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3},
+        "config": workload_config(workload, args.gpus),
         "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": 1, "kind": "reference", "sample": sample,
                          "build": lib.kind, "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -191,35 +222,98 @@ class DevTensor:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
 
 
-def run_b200(args, workload):
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+class Session:
+    """One process = one GPU: rank bookkeeping, the process group, the product library."""
 
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_mod
+            self.dist = dist_mod
+            self.dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.lib = load_b200()
+        L = self.lib.lib
+        L.mtgl_set_device(self.local)
+        L.mtgl_dev_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+        L.mtgl_dev_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.mtgl_dev_timer_elapsed_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        L.mtgl_dev_set_band.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.mtgl_dev_plane_pointers.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 3
+        L.mtgl_dev_read_framebuffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+        L.mtgl_dev_export_color_plane.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.mtgl_dev_set_present_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        L.mtgl_dev_buffer_pointer.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
+        L.mtgl_dev_stream.restype = ctypes.c_void_p
+        L.mtgl_dev_stream.argtypes = [ctypes.c_void_p]
+        L.glBindBuffer.argtypes = [ctypes.c_uint, ctypes.c_uint]
+        L.glBufferData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
+        L.glBufferSubData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_long, ctypes.c_void_p]
+        L.scene_c4_host_data.restype = ctypes.c_void_p
+        L.scene_c4_vbo.restype = ctypes.c_uint
+        L.scene_c4_vertex_count.restype = ctypes.c_int
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def parity_block(sess, workload, assembled_color=None):
+    """The checker leg (rank 0): the workload's frame rendered by the unmodified reference (strict IEEE build) on this
+    box's host CPU, compared with the CUDA frame -- all three planes of a fresh single-GPU render, and for N > 1 also the
+    colour plane assembled from the bands in rank 0's framebuffer."""
+    from parity import compare_planes
+    key, w, h, variant = WORKLOADS[workload]
+    scene = SCENE_OF[workload]
+    cnt = counts_for(key)
+    t0 = time.perf_counter()
+    ref = load_reference("strict").render(scene, w, h, variant)
+    t_ref = time.perf_counter() - t0
+    if os.environ.get("MTGL_BENCH_BAND"):
+        return {"skipped": "band emulation"}
+    got = sess.lib.render(scene, w, h, variant)
+    s = compare_planes(ref, got)
+    out = {"reference": "oracle/_ref/libref_strict.so (unmodified reference, -O2 -fno-fast-math -ffp-contract=off)",
+           "reference_frame_s": round(t_ref, 2),
+           "stencil_diff": s["stencil_diff_pixels"], "depth_max_ulp": s["depth_max_ulp"], "depth_diff_pixels": s["depth_diff_pixels"],
+           "color_max_abs": s["color_max_abs"], "color_diff_pixels": s["color_diff_pixels"], "color_identical_frac": s["color_identical_frac"],
+           "gl_error": [int(ref[3]), int(got[3])]}
+    if workload == "c3":      # stencil INCR_WRAP on every covered fragment (<= 128 per pixel): the plane sums to the covered-fragment count
+        out["covered_fragments"] = int(got[2].astype(np.int64).sum())
+        out["covered_fragments_expected"] = cnt["covered"]
+    else:                      # pixels some fragment passed the depth test on
+        out["covered_pixels"] = int((got[1] != np.float32(1.0)).sum())
+        out["covered_pixels_reference"] = int((ref[1] != np.float32(1.0)).sum())
+    if assembled_color is not None:
+        a = assembled_color.reshape(h, w)
+        ch = np.abs(a.view(np.uint8).reshape(h, w, 4).astype(np.int16) - ref[0].view(np.uint8).reshape(h, w, 4).astype(np.int16))
+        out["assembled_color_max_abs"] = int(ch.max())
+        out["assembled_color_identical_frac"] = float((a == ref[0]).mean())
+    ok = (s["stencil_diff_pixels"] == 0 and s["depth_max_ulp"] <= 1 and s["color_max_abs"] <= 1 and s["color_identical_frac"] >= 0.999
+          and out.get("covered_fragments", 0) == out.get("covered_fragments_expected", 0)
+          and out.get("covered_pixels", 0) == out.get("covered_pixels_reference", 0)
+          and out.get("assembled_color_max_abs", 0) <= 1)
+    out["gate"] = "green" if ok else "RED"
+    return out
+
+
+def measure(sess, workload, primary):
+    """One workload on this rank's GPU: device-timed frames, end-to-end frames, roofline of the dominant kernel."""
+    torch, dist, args = sess.torch, sess.dist, sess.args
+    rank, world, local = sess.rank, sess.world, sess.local
+    lib = sess.lib
+    L = lib.lib
     key, w, h, variant = WORKLOADS[workload]
     cnt = counts_for(key)
-    lib = load_b200()
-    L = lib.lib
-    L.mtgl_set_device(local)
     lib.create(w, h)
     dev = lib.device()
-    L.mtgl_dev_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
-    L.mtgl_dev_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    L.mtgl_dev_timer_elapsed_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
-    L.mtgl_dev_set_band.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-    L.mtgl_dev_plane_pointers.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 3
-    L.mtgl_dev_read_framebuffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
-    L.glBindBuffer.argtypes = [ctypes.c_uint, ctypes.c_uint]
-    L.glBufferData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
-    L.scene_c4_host_data.restype = ctypes.c_void_p
-    L.scene_c4_vbo.restype = ctypes.c_uint
 
     bounds = [band_rows(h, r, world)[0] for r in range(world)] + [h]     # band r = rows [bounds[r], bounds[r + 1])
     y0, y1 = bounds[rank], bounds[rank + 1]
@@ -240,19 +334,16 @@ def run_b200(args, workload):
         else:
             L.scene_c4_draw()
 
-    # colour plane as a torch tensor for the band gather
+    # colour plane as a torch tensor for the unfused gather variant
     cptr = ctypes.c_void_p()
     L.mtgl_dev_plane_pointers(dev, ctypes.byref(cptr), None, None)
     color_dev = torch.as_tensor(DevTensor(cptr.value, w * h * 4), device=f"cuda:{local}") if world > 1 else None
 
     # Fused gather (default for N > 1): rank 0 exports its colour plane over CUDA IPC, the other ranks map it and their
     # raster kernels store every colour of their band straight into it over NVLink (mtgl_dev_set_present_target);
-    # what is left of the gather is one tiny all-reduce as the "all bands have landed" barrier.
+    # what is left of the gather is the frame-barrier kernel.
     peer = world > 1 and args.gather == "peer"
-    token = torch.zeros(1, device=f"cuda:{local}") if world > 1 else None
     if peer:
-        L.mtgl_dev_export_color_plane.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-        L.mtgl_dev_set_present_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         hbuf = (ctypes.c_ubyte * 64)()
         if rank == 0:
             assert L.mtgl_dev_export_color_plane(dev, hbuf) == 0
@@ -262,7 +353,6 @@ def run_b200(args, workload):
             hb = (ctypes.c_ubyte * 64)(*ht.cpu().tolist())
             rc = L.mtgl_dev_set_present_target(dev, hb)
             assert rc == 0, f"mtgl_dev_set_present_target failed ({rc})"
-        L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
         dist.barrier()          # every rank has mapped the plane (and its barrier counter) before the first frame
 
     def gather():
@@ -294,11 +384,12 @@ def run_b200(args, workload):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # L2 hygiene: C4/C5 stream > 126 MB per frame (98.9 MB of vertices, 165 MB of triangle records, 74 MB of planes),
+    # L2 hygiene: C4/C5 stream > 126 MB per frame (98.9 MB of vertices, > 100 MB of triangle records, 74-300 MB of planes),
     # i.e. inputs larger than L2; the C3 working set is small, so flush L2 between its frames.
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if is_c3 else None
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         frame(); gather()
     sync_all()
 
@@ -334,7 +425,7 @@ def run_b200(args, workload):
     L.mtgl_dev_get_stats(dev, ctypes.byref(st))
     launches0 = st.kernel_launches
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and primary:
         sampler.start()
 
     # ---- timed region 1: inputs resident in HBM ----
@@ -345,12 +436,6 @@ def run_b200(args, workload):
     # over NVLink): frame i+1 starts on no rank before every band of frame i has landed in rank 0's plane, and there is
     # no host synchronisation and no NCCL call inside the loop.  C3 flushes L2 between frames and therefore synchronises
     # every step.
-    stage = np.zeros(5)
-    rstage = np.zeros(3)
-    batch_ms = 0.0
-    L.mtgl_dev_stream.restype = ctypes.c_void_p
-    L.mtgl_dev_stream.argtypes = [ctypes.c_void_p]
-    lib_stream = torch.cuda.ExternalStream(L.mtgl_dev_stream(dev), device=torch.device("cuda", local))
     pipelined = flush is None and (world == 1 or peer)
     sync_all()
     L.mtgl_dev_get_stats(dev, ctypes.byref(st))
@@ -375,6 +460,8 @@ def run_b200(args, workload):
         for _ in range(args.steps):
             if flush is not None:
                 flush.fill_(1); torch.cuda.synchronize()
+                if dist:
+                    dist.barrier(); torch.cuda.synchronize()     # the ranks start the frame together
             L.mtgl_dev_timer_mark(dev, 0)
             frame()
             gather()
@@ -388,7 +475,7 @@ def run_b200(args, workload):
     wall_s = time.perf_counter() - t_wall0
     # device time of the K steps: CUDA events on the library's stream (C3: around each step, flushes excluded); the
     # unfused NCCL gather runs on torch's stream, so the bracketing torch events are used for it instead
-    elapsed_ms = dev_ms_total if (world == 1 or pipelined) else ev0.elapsed_time(ev1)
+    elapsed_ms = dev_ms_total if (world == 1 or peer) else ev0.elapsed_time(ev1)
     if dist:
         tt = torch.tensor([elapsed_ms], device=f"cuda:{local}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -399,14 +486,12 @@ def run_b200(args, workload):
     stage = np.array(list(st.cum_stage_ms)) - cum0[2]
     rstage = np.array(list(st.cum_raster_ms)) - cum0[3]
     batch_ms = st.cum_batch_ms - cum0[1]
-    L.mtgl_dev_get_stats(dev, ctypes.byref(st))
     if os.environ.get("MTGL_BENCH_DEBUG"):
-        print(f"[rank {rank}] stages {np.round(stage / args.steps, 4).tolist()} raster {np.round(rstage / args.steps, 4).tolist()} dev_ms {dev_ms_total / args.steps:.4f}", file=sys.stderr, flush=True)
+        print(f"[rank {rank}] {workload} stages {np.round(stage / args.steps, 4).tolist()} raster {np.round(rstage / args.steps, 4).tolist()} dev_ms {dev_ms_total / args.steps:.4f}", file=sys.stderr, flush=True)
     launches = int(st.kernel_launches - launches0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and primary) else None
 
     # ---- timed region 2: end to end through the public API with host buffers (C4/C5: VBO re-upload + read-back) ----
-    e2e = None
     h2d = d2h = 0
     # N = 1: this rank uploads the whole VBO and reads the whole colour plane back.
     # N > 1 (peer gather): every rank uploads 1/N of the VBO from its pinned copy, an NCCL all-gather over NVLink
@@ -417,14 +502,11 @@ def run_b200(args, workload):
     pinned_out = torch.empty((ry1 - ry0) * w, dtype=torch.int32).pin_memory() if ry1 > ry0 else None
     vbo_dev = None
     if not is_c3:
-        L.scene_c4_vertex_count.restype = ctypes.c_int
         nbytes = int(L.scene_c4_vertex_count()) * 32          # what the VBO holds (c4i: one mesh, not the whole grid)
         pinned_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         ctypes.memmove(pinned_in.data_ptr(), L.scene_c4_host_data(), nbytes)
         vbo = L.scene_c4_vbo()
         if peer and nbytes % world == 0:
-            L.mtgl_dev_buffer_pointer.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
-            L.glBufferSubData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_long, ctypes.c_void_p]
             bp, bs = ctypes.c_void_p(), ctypes.c_uint64()
             assert L.mtgl_dev_buffer_pointer(dev, vbo, ctypes.byref(bp), ctypes.byref(bs)) == 0 and bs.value == nbytes
             vbo_dev = torch.as_tensor(DevTensor(bp.value, nbytes), device=f"cuda:{local}")
@@ -466,6 +548,7 @@ def run_b200(args, workload):
 
     # ---- N > 1: the frame assembled in rank 0's plane must be bit-identical to a single-GPU render ----
     gather_check = None
+    assembled = None
     if world > 1:
         frame(); gather(); sync_all()
         if rank == 0:
@@ -476,20 +559,28 @@ def run_b200(args, workload):
             want = np.empty(h * w, dtype=np.uint32)
             assert L.mtgl_dev_read_framebuffer(dev, 0, h, want.ctypes.data, None, None) == 0
             gather_check = "bit-identical to a single-GPU render" if np.array_equal(got, want) else f"MISMATCH in {int((got != want).sum())} pixels"
+            assembled = got
         sync_all()
 
-    # ---- CPU baseline on this box (rank 0, N = 1 only) ----
+    lib.destroy()
+
+    # ---- checker legs on this box's host CPU (rank 0): the reference as timing baseline and as parity oracle ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and primary and not args.no_cpu_baseline:
         try:
-            a2 = argparse.Namespace(**vars(args)); a2.steps = 2 if not is_c3 else 1; a2.warmup = 1 if not is_c3 else 0
-            cpu = run_reference(a2, workload)["cpu_baseline"]
+            cpu = run_reference(args, workload, steps=2 if not is_c3 else 1, warmup=1 if not is_c3 else 0)["cpu_baseline"]
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "fragments/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
-
-    lib.destroy()
+    parity = None
+    if rank == 0 and not args.no_parity and not (is_c3 and world > 1):    # the 64-quad reference frame takes ~50 s: at N = 1 only
+        try:
+            parity = parity_block(sess, workload, assembled)
+        except Exception as e:  # pragma: no cover
+            parity = {"gate": "unavailable", "error": repr(e)}
+    elif is_c3 and world > 1:
+        parity = {"gate": "see N=1", "note": "the 64-quad reference frame takes ~50 s of host time; checked in the N=1 run, gather_check covers N>1"}
     if dist:
-        dist.destroy_process_group()
+        dist.barrier()
     if rank != 0:
         return None
 
@@ -506,11 +597,11 @@ def run_b200(args, workload):
         clear_bytes = px * (4 + 4)
         vertex_bytes = cnt["vertices"] * 32
     # the dominant kernel of the step, whichever the live per-group CUDA-event times say: the fused vertex + set-up
-    # kernel (K1+K2), K4a (visibility: coverage + depth), K4b (shade) or the general in-order kernel.  Its algorithmic
-    # bytes are SURVEY.md 8(d)'s figures restricted to what that kernel owns (DESIGN.md "Rooflines"): the enabled
-    # attribute arrays per input vertex for set-up, the reference's per-fragment framebuffer traffic for the planes a
-    # raster kernel owns.
-    groups = ["k_setup (K1+K2 vertex + set-up)", "k_vis (K4a visibility)", "k_shade (K4b)", "k_raster<false> (general)"]
+    # kernel (K1+K2), K4a (visibility: coverage + depth), K4b (shade) or the in-order kernels (k_fill / k_raster<false>).
+    # Its algorithmic bytes are SURVEY.md 8(d)'s figures restricted to what that kernel owns (DESIGN.md "Rooflines"): the
+    # enabled attribute arrays per input vertex for set-up, the reference's per-fragment framebuffer traffic for the
+    # planes a raster kernel owns.
+    groups = ["k_setup (K1+K2 vertex + set-up)", "k_vis (K4a visibility)", "k_shade (K4b)", "k_fill + k_raster<false> (in-order)"]
     group_ms = [stage[1] / args.steps] + [float(x) / args.steps for x in rstage]
     gi = int(np.argmax(group_ms))
     raster_ms = group_ms[gi]
@@ -518,45 +609,66 @@ def run_b200(args, workload):
         group_bytes = [0, 0, 0, frag_bytes + clear_bytes]
     else:
         group_bytes = [vertex_bytes, cnt["covered"] * 4 + cnt["tested"] * 4 + px * 4, cnt["tested"] * 4 + px * 4, 0]
-        if group_bytes[gi] == 0:        # a state mix that sends C4/C5 through the general kernel
+        if group_bytes[gi] == 0:        # a state mix that sends C4/C5 through the in-order kernels
             group_bytes[gi] = frag_bytes + clear_bytes
     raster_bytes = group_bytes[gi] / world          # one launch per rank covers 1/N of the frame (set-up: the chunks that reach its band)
     achieved = raster_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text()).get(workload, {}).get(groups[gi].split(" ")[0])
+        tfile = ROOT / "profiles" / "r02_ncu_traffic.json"
+        tj = json.loads(tfile.read_text()).get(workload, {}).get(groups[gi].split(" ")[0])
         if tj and world == 1:
             traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+            traffic_src = f"profiles/r02_ncu_traffic.json ({tj.get('capture', 'ncu --set full')}, per launch)"
     except Exception:
         traffic = None
     frame_bytes = frag_bytes + clear_bytes + vertex_bytes
     out = {
         "metric": "covered_fragments_per_s", "value": value, "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": 1e3 / ms_per_step, "triangles_per_s": cnt["vertices"] / 3 * 1e3 / ms_per_step,
-        "config": {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3,
-                   "covered_fragments": cnt["covered"], "depth_passing_fragments": cnt["tested"], "shaded_fragments": cnt["shaded"],
-                   "partition": f"sort-first bands x{world}" + ("" if world == 1 else (", fused NVLink peer-store gather" if peer else ", NCCL send/recv gather")),
-                   "band_rows": bounds if world > 1 else None, "band_balance": balance_log,
-                   "gather_check": gather_check,
-                   "l2": "flushed between frames (256 MiB fill)" if is_c3 else "inputs larger than L2 (>330 MB streamed per frame)"},
+        "config": workload_config(workload, world),
+        "multi_gpu": None if world == 1 else {"gather": "fused NVLink peer-store gather + frame-barrier kernel" if peer else "NCCL send/recv gather",
+                                              "band_rows": bounds, "band_balance": balance_log, "gather_check": gather_check},
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3 / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": groups[gi], "bound": "hbm", "achieved": achieved, "peak": bw, "unit": "GB/s",
-                     "frac": achieved / bw, "traffic": traffic, "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, per launch)" if traffic else None,
+                     "frac": achieved / bw, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": bw_src,
                      "algorithmic_bytes_per_launch": raster_bytes, "kernel_ms": raster_ms,
                      "frame_bytes": frame_bytes, "frame_frac": frame_bytes / (bw * 1e9) / (ms_per_step * 1e-3)},
         "stages_ms": {k: float(v / args.steps) for k, v in zip(["vertex", "setup", "bin_count_scan", "bin_fill", "raster"], stage)},
-        "raster_ms": {k: float(v / args.steps) for k, v in zip(["visibility", "shade", "general"], rstage)},
+        "raster_ms": {k: float(v / args.steps) for k, v in zip(["visibility", "shade", "in_order"], rstage)},
         "batch_ms": batch_ms / args.steps, "wall_ms_per_step": wall_s * 1e3 / args.steps,
         "chunks_culled_rank0": int(st.chunks_culled), "chunks": (cnt["vertices"] // 3 + 255) // 256,
         "cpu_baseline": cpu,
+        "parity": parity,
     }
     return out
+
+
+SECONDARY_KEYS = ("value", "unit", "ms_per_step", "frames_per_s", "config", "multi_gpu", "e2e", "gpu_launches", "roofline",
+                  "stages_ms", "raster_ms", "parity")
+
+
+def run_b200(args):
+    sess = Session(args)
+    try:
+        out = measure(sess, args.workload, primary=True)
+        secondary = {}
+        if not args.no_secondary and args.workload == "c4":
+            for wl in ("c3", "c5"):
+                r = measure(sess, wl, primary=False)
+                if r is not None:
+                    secondary[WORKLOADS[wl][0]] = {k: r[k] for k in SECONDARY_KEYS}
+        if out is not None:
+            out["secondary"] = secondary or None
+        return out
+    finally:
+        sess.close()
 
 
 def main():
@@ -567,6 +679,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 and C5 lines of the default (C4) run")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference-rendered parity check of each workload")
     ap.add_argument("--uniform-bands", action="store_true", help="N > 1: keep the uniform split of tile rows (no load balancing)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'nccl' = send/recv after the frame")
@@ -582,7 +696,7 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
-        out = run_b200(args, args.workload)
+        out = run_b200(args)
     finally:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -11,8 +11,6 @@ from .loader import (  # noqa: F401
     SceneLibrary,
     build,
     load_b200,
-    load_front_oracle,
-    load_reference,
     load_suzanne,
 )
 
@@ -22,7 +20,5 @@ __all__ = [
     "SceneLibrary",
     "build",
     "load_b200",
-    "load_front_oracle",
-    "load_reference",
     "load_suzanne",
 ]

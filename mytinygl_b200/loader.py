@@ -1,13 +1,12 @@
-"""ctypes loader for the three scene libraries that share one entry-point set.
+"""ctypes loader of the product library.
 
-* ``load_b200()``          tests/scenes/_build/libscenes_b200.so -> mytinygl_b200/lib/libMyTinyGL_b200.so
-                           (the product: CUDA back end; raises LibraryMissing when it was not built)
-* ``load_front_oracle()``  oracle/_build/libfront_oracle.so (front end + CPU restatement; tests only)
-* ``load_reference(kind)`` oracle/_ref/libref_{strict,shipped,shipped_v3}.so (the unmodified reference
-                           compiled from /root/reference; tests and the CPU baseline only)
+``load_b200()`` loads tests/scenes/_build/libscenes_b200.so -> mytinygl_b200/lib/libMyTinyGL_b200.so (the CUDA back
+end behind the gl* API; raises LibraryMissing when it was not built -- there is no fallback).
 
-All of them export scene_set_mesh / scene_render / scene_c4_* (tests/scenes/scenes.c), the four
-mtgl_harness_* functions and the public gl* API.
+``SceneLibrary`` is the generic wrapper around any library that exports scene_set_mesh / scene_render / scene_c4_*
+(tests/scenes/scenes.c), the four mtgl_harness_* functions and the public gl* API.  The checkers -- the CPU oracle and
+the unmodified reference -- are loaded with the same class by tests/oracle_loader.py; nothing in this package knows
+where they live.
 """
 from __future__ import annotations
 
@@ -125,30 +124,3 @@ class SceneLibrary:
 
 def load_b200() -> SceneLibrary:
     return SceneLibrary(REPO_ROOT / "tests" / "scenes" / "_build" / "libscenes_b200.so", "b200")
-
-
-def load_front_oracle() -> SceneLibrary:
-    return SceneLibrary(REPO_ROOT / "oracle" / "_build" / "libfront_oracle.so", "front+oracle")
-
-
-def _runs_here(path: Path) -> bool:
-    """True if the library executes on this host (a -march=native build may not)."""
-    code = ("import ctypes,sys; l=ctypes.CDLL(sys.argv[1]); l.mtgl_harness_create.restype=ctypes.c_void_p;"
-            "c=l.mtgl_harness_create(64,64); l.scene_render.argtypes=[ctypes.c_char_p]+[ctypes.c_int]*3;"
-            "l.scene_render(b'c2_cube',64,64,0)")
-    try:
-        return subprocess.run([sys.executable, "-c", code, str(path)], timeout=120,
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
-    except Exception:
-        return False
-
-
-def load_reference(kind: str = "strict") -> SceneLibrary:
-    """kind: 'strict' (parity oracle) or 'shipped' (timing baseline: the reference's own flags)."""
-    base = REPO_ROOT / "oracle" / "_ref"
-    if kind == "strict":
-        return SceneLibrary(base / "libref_strict.so", "ref-strict")
-    native = base / "libref_shipped.so"
-    if native.exists() and os.environ.get("MTGL_REF_PORTABLE") != "1" and _runs_here(native):
-        return SceneLibrary(native, "ref-shipped(-march=native)")
-    return SceneLibrary(base / "libref_shipped_v3.so", "ref-shipped(-march=x86-64-v3)")

@@ -14,13 +14,13 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def front_oracle():
-    from mytinygl_b200 import load_front_oracle
+    from oracle_loader import load_front_oracle
     return load_front_oracle()
 
 
 @pytest.fixture(scope="session")
 def ref_strict():
-    from mytinygl_b200 import load_reference
+    from oracle_loader import load_reference
     return load_reference("strict")
 
 

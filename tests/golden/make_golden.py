@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 from cases import CASES, LARGE_CASES, case_id  # noqa: E402
-from mytinygl_b200 import load_reference  # noqa: E402
+from oracle_loader import load_reference  # noqa: E402
 
 
 def digest(a):

@@ -31,7 +31,7 @@ def _worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from cases import case_id
-    from mytinygl_b200 import load_front_oracle
+    from oracle_loader import load_front_oracle
     lib = load_front_oracle()
     lib.lib.mtgl_dev_set_band.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     digests = {}

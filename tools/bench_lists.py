@@ -13,8 +13,9 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT))
-from mytinygl_b200 import load_b200, load_reference  # noqa: E402
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from mytinygl_b200 import load_b200  # noqa: E402
+from oracle_loader import load_reference  # noqa: E402
 
 GL_COMPILE, GL_TRIANGLES, GL_DEPTH_TEST, GL_LIGHTING, GL_LIGHT0 = 0x1300, 4, 0x0B71, 0x0B50, 0x4000
 

@@ -17,8 +17,9 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT))
-from mytinygl_b200 import load_b200, load_reference  # noqa: E402
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from mytinygl_b200 import load_b200  # noqa: E402
+from oracle_loader import load_reference  # noqa: E402
 
 GL_RGBA, GL_UNSIGNED_BYTE = 0x1908, 0x1401
 GL_DEPTH_TEST, GL_BLEND, GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA, GL_ALWAYS = 0x0B71, 0x0BE2, 0x0302, 0x0303, 0x0207

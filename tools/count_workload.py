@@ -13,8 +13,8 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT))
-from mytinygl_b200 import load_front_oracle  # noqa: E402
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from oracle_loader import load_front_oracle  # noqa: E402
 
 WORKLOADS = {
     "c1_suzanne_800x600": ("c1_suzanne", 800, 600, 0),

@@ -7,7 +7,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
-from mytinygl_b200 import load_b200, load_front_oracle  # noqa: E402
+from mytinygl_b200 import load_b200  # noqa: E402
+from oracle_loader import load_front_oracle  # noqa: E402
 from parity import compare_planes  # noqa: E402
 
 CASES = {"c4": ("c4_grid", 3840, 2160, 0), "c4_phong": ("c4_grid", 3840, 2160, 1 << 16), "c3_8quads": ("c3_fill", 3840, 2160, 8),
