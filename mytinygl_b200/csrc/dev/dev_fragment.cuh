@@ -26,6 +26,49 @@ __device__ __forceinline__ uint8_t stencil_apply(uint32_t op, uint8_t v, int32_t
     }
 }
 
+/* The eight comparison functions GL_NEVER .. GL_ALWAYS (0x200 + f) as a mask: bit 0 = true when a < b, bit 1 when a == b,
+ * bit 2 when a > b -- which is how the tokens are numbered -- and bit 3 when the operands are unordered (a NaN): the C
+ * operators of depth_test / alpha_test / stencil_test (raster.c:344-357, 391-422) are all false then, except != and
+ * "always".  One mask per triangle, then every test is branch-free. */
+__device__ __forceinline__ uint32_t compare_mask(uint32_t f) { return (f & 7u) | (((f & 7u) == 5u || (f & 7u) == 7u) ? 8u : 0u); }
+
+__device__ __forceinline__ bool compare_f_mask(uint32_t m, float a, float b)
+{
+    const uint32_t code = (a < b) ? 1u : ((a == b) ? 2u : ((a > b) ? 4u : 8u));
+    return (m & code) != 0u;
+}
+
+__device__ __forceinline__ bool compare_i_mask(uint32_t m, int32_t a, int32_t b)
+{
+    const uint32_t code = (a < b) ? 1u : ((a == b) ? 2u : 4u);
+    return (m & code) != 0u;
+}
+
+/* A stencil operation (raster.c:425-438) as data: nv = clamp(((v & A) ^ X) + D, lo, hi) & 0xFF with
+ * A = bits 0-7, X = bits 8-15, D = bits 16-17 (0, +1, 3 = -1), bit 18: lo = 0 (else none), bit 19: hi = 255 (else none). */
+__device__ __forceinline__ uint32_t stencil_op_encode(uint32_t op, int32_t ref)
+{
+    switch (op) {
+    case G_ZERO: return 0u;
+    case G_REPLACE: return ((uint32_t)ref & 0xFFu) << 8;
+    case G_INCR: return 0xFFu | (1u << 16) | (1u << 19);
+    case G_INCR_WRAP: return 0xFFu | (1u << 16);
+    case G_DECR: return 0xFFu | (3u << 16) | (1u << 18);
+    case G_DECR_WRAP: return 0xFFu | (3u << 16);
+    case G_INVERT: return 0xFFu | (0xFFu << 8);
+    default: return 0xFFu;          /* GL_KEEP */
+    }
+}
+
+__device__ __forceinline__ uint32_t stencil_op_apply(uint32_t enc, uint32_t v)
+{
+    const int d = (int)((enc >> 16) & 1u) - (int)((enc >> 16) & 2u);           /* 0, +1, -1 */
+    int r = (int)((v & enc) ^ ((enc >> 8) & 0xFFu)) + d;        /* v <= 255: v & enc == v & A */
+    r = max(r, (enc & (1u << 18)) ? 0 : -256);
+    r = min(r, (enc & (1u << 19)) ? 255 : 511);
+    return (uint32_t)r & 0xFFu;
+}
+
 __device__ __forceinline__ float fog_factor(const RasterCfg *c, float coord)   /* raster.c:677-701 */
 {
     float f;

@@ -33,7 +33,7 @@ __device__ __forceinline__ int wrap_coord(int x, int n, bool repeat)
         if ((unsigned)(x + n) < (unsigned)(3 * n)) {            /* x in [-n, 2n): one conditional add == the euclidean modulo */
             if (x < 0) x += n; else if (x >= n) x -= n;
         } else x = ((x % n) + n) % n;
-    } else { if (x < 0) x = 0; else if (x >= n) x = n - 1; }
+    } else x = min(max(x, 0), n - 1);      /* n >= 1 */
     return x;
 }
 

@@ -63,7 +63,7 @@ constexpr uint32_t TP_B_SHIFT = 4;              /* second level: kind in bits 4-
 constexpr uint32_t TP_B_LINEAR = 1u << 6;
 constexpr uint32_t TP_REP_S = 1u << 7, TP_REP_T = 1u << 8;
 
-/* what one triangle contributes to every pixel of the tile: 12 x 16 B, read as broadcasts */
+/* what one triangle contributes to every pixel of the tile: 14 x 16 B, read as broadcasts */
 struct __align__(16) PrepTri {
     float4 ea;      /* A0 A1 A2 | 1/area            (all negated for clockwise triangles: one inclusive test e >= 0) */
     float4 eb;      /* B0 B1 B2 | cfg index + PT_*  */
@@ -75,8 +75,15 @@ struct __align__(16) PrepTri {
     float4 te;      /* eye z0 z1 z2 | 1/w2 */
     float4 p0;      /* x0 y0 x1 y1 as floats: the reference form of the edge functions */
     float4 p1;      /* x2 y2 | sampler plan | trilinear weight */
+    uint4 s0;       /* state, decoded once per (triangle, tile): RasterCfg flags | PS_* word | masked stencil reference | stencil zpass op */
+    uint4 s1;       /* stencil fail op | stencil zfail op | alpha reference (float bits) | blend_src << 16 | blend_dst */
 };
-static_assert(sizeof(PrepTri) == 192, "PrepTri layout");
+static_assert(sizeof(PrepTri) == 224, "PrepTri layout");
+
+/* PrepTri::s0.y: comparison masks (dev_fragment.cuh, compare_mask) and small enums */
+constexpr uint32_t PS_STENCIL_CMP_SHIFT = 0, PS_DEPTH_CMP_SHIFT = 4, PS_ALPHA_CMP_SHIFT = 8;     /* 4 bits each */
+constexpr uint32_t PS_STENCIL_MASK_SHIFT = 12, PS_STENCIL_WMASK_SHIFT = 20;                       /* 8 bits each */
+constexpr uint32_t PS_COLOR_MASK_SHIFT = 28;                                                      /* 4 bits */
 
 struct FillSmem {
     float4 tex[FILL_TEX_TEXELS];
@@ -197,6 +204,13 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
     const uint32_t plan = (cflags & RC_TEXTURED) ? sampler_plan(cfg, row3.w, cl) : 0u;
     P.p1 = make_float4((float)row1.x, (float)row1.y, __uint_as_float(plan), cl);
     P.eb = make_float4(B[0], B[1], B[2], __uint_as_float(word));
+    const uint32_t ps = (compare_mask(cfg->stencil_func) << PS_STENCIL_CMP_SHIFT) | (compare_mask(cfg->depth_func) << PS_DEPTH_CMP_SHIFT) |
+                        (compare_mask(cfg->alpha_func) << PS_ALPHA_CMP_SHIFT) | ((cfg->stencil_mask & 0xFFu) << PS_STENCIL_MASK_SHIFT) |
+                        ((cfg->stencil_writemask & 0xFFu) << PS_STENCIL_WMASK_SHIFT) | ((cfg->color_mask & 0xFu) << PS_COLOR_MASK_SHIFT);
+    /* raster.c:407-422 compares (ref & mask) with (value & mask); the value has 8 bits, the reference and the mask need not */
+    P.s0 = make_uint4(cflags, ps, (uint32_t)cfg->stencil_ref & cfg->stencil_mask, stencil_op_encode(cfg->stencil_zpass, cfg->stencil_ref));
+    P.s1 = make_uint4(stencil_op_encode(cfg->stencil_fail, cfg->stencil_ref), stencil_op_encode(cfg->stencil_zfail, cfg->stencil_ref),
+                      __float_as_uint(cfg->alpha_ref), (cfg->blend_src << 16) | (cfg->blend_dst & 0xFFFFu));
 }
 
 /* ---------------------------------------------------------------- texture sampling from the staged float4 texels */
@@ -273,8 +287,9 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
     if (Y < (int)((box >> 8) & 0xFFu) || Y > (int)(box >> 24)) return;          /* warp-uniform */
     const int bx0 = (int)(box & 0xFFu), bx1 = (int)((box >> 16) & 0xFFu);
     const uint32_t word = __float_as_uint(T.eb.w);
-    const RasterCfg *cfg = b.cfgs + (word & STATE_INDEX_MASK);
-    const uint32_t fl = __ldg(&cfg->flags);
+    const RasterCfg *cfg = b.cfgs + (word & STATE_INDEX_MASK);      /* only the rarely used fields are read from it */
+    const uint4 s0 = T.s0;
+    const uint32_t fl = s0.x, ps = s0.y;
     auto has = [&](uint32_t bit) -> bool { return (ON & bit) ? true : ((OFF & bit) ? false : (fl & bit) != 0u); };
 
     /* ---- coverage: inclusive on all three edges, no fill rule (raster.c:539-540) ---- */
@@ -319,10 +334,9 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
 #pragma unroll
     for (int p = 0; p < P; p++) depth[p] = 0.0f;
     const bool depth_test = has(RC_DEPTH_TEST);
-    uint32_t depth_func = 7u;
+    const uint32_t depth_cmp = (ps >> PS_DEPTH_CMP_SHIFT) & 15u;
     if (depth_test) {
         const float4 zz = T.zz;
-        depth_func = __ldg(&cfg->depth_func);
         const bool r01 = has(RC_DEPTH_RANGE_01);
 #pragma unroll
         for (int p = 0; p < P; p++) {
@@ -332,26 +346,22 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
         }
     }
     if (has(RC_STENCIL)) {
-        const uint32_t sfunc = __ldg(&cfg->stencil_func), smask = __ldg(&cfg->stencil_mask), swm = __ldg(&cfg->stencil_writemask) & 0xFFu;
-        const int32_t sref = __ldg(&cfg->stencil_ref);
-        const uint32_t op_fail = __ldg(&cfg->stencil_fail), op_zfail = __ldg(&cfg->stencil_zfail), op_zpass = __ldg(&cfg->stencil_zpass);
-        const int32_t mref = (int32_t)((uint32_t)sref & smask);
+        const uint4 s1 = T.s1;
+        const uint32_t scmp = (ps >> PS_STENCIL_CMP_SHIFT) & 15u, smask = (ps >> PS_STENCIL_MASK_SHIFT) & 0xFFu, swm = (ps >> PS_STENCIL_WMASK_SHIFT) & 0xFFu;
+        const int32_t mref = (int32_t)s0.z;
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            if (!act[p]) continue;
-            const uint8_t sval = (uint8_t)S.stencil[p];
-            const int32_t mval = (int32_t)((uint32_t)sval & smask);
-            uint32_t op;
-            if (!compare_i(sfunc, mref, mval)) { op = op_fail; act[p] = false; }
-            else if (depth_test && !compare_f(depth_func, depth[p], S.depth[p])) { op = op_zfail; act[p] = false; }
-            else op = op_zpass;
-            const uint8_t nv = stencil_apply(op, sval, sref);
-            S.stencil[p] = (uint32_t)((sval & ~swm) | (nv & swm));
+            const uint32_t sval = S.stencil[p];
+            const bool spass = compare_i_mask(scmp, mref, (int32_t)(sval & smask));
+            const bool zpass = !depth_test || compare_f_mask(depth_cmp, depth[p], S.depth[p]);
+            const uint32_t op = !spass ? s1.x : (!zpass ? s1.y : s0.w);
+            const uint32_t nv = stencil_op_apply(op, sval);
+            if (act[p]) S.stencil[p] = (sval & ~swm) | (nv & swm);
+            act[p] = act[p] && spass && zpass;
         }
     } else if (depth_test) {
 #pragma unroll
-        for (int p = 0; p < P; p++)
-            if (act[p] && !compare_f(depth_func, depth[p], S.depth[p])) act[p] = false;
+        for (int p = 0; p < P; p++) act[p] = act[p] && compare_f_mask(depth_cmp, depth[p], S.depth[p]);
     }
     any = false;
 #pragma unroll
@@ -384,19 +394,17 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
             }
         }
         const bool alpha_test = has(RC_ALPHA_TEST);
-        uint32_t afunc = 7u;
-        float aref = 0.0f;
-        if (alpha_test) { afunc = __ldg(&cfg->alpha_func); aref = __ldg(&cfg->alpha_ref); }
+        const uint32_t acmp = (ps >> PS_ALPHA_CMP_SHIFT) & 15u;
+        const float aref = __uint_as_float(T.s1.z);
         if (word & PT_FASTTEX) {
             const uint32_t plan = __float_as_uint(T.p1.z);
             const bool rep_s = (plan & TP_REP_S) != 0u, rep_t = (plan & TP_REP_T) != 0u;
             /* wrap (textures.c:463-486) */
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                if (rep_s) { u[p] = u[p] - truncf(u[p]); if (u[p] < 0) u[p] += 1.0f; }
-                else { if (u[p] < 0.0f) u[p] = 0.0f; if (u[p] > 1.0f) u[p] = 1.0f; }
-                if (rep_t) { v[p] = v[p] - truncf(v[p]); if (v[p] < 0) v[p] += 1.0f; }
-                else { if (v[p] < 0.0f) v[p] = 0.0f; if (v[p] > 1.0f) v[p] = 1.0f; }
+                /* (PT_FASTTEX: u and v are finite, so the saturate is the reference's pair of ternaries) */
+                if (rep_s) { u[p] = u[p] - truncf(u[p]); if (u[p] < 0) u[p] += 1.0f; } else u[p] = __saturatef(u[p]);
+                if (rep_t) { v[p] = v[p] - truncf(v[p]); if (v[p] < 0) v[p] += 1.0f; } else v[p] = __saturatef(v[p]);
             }
             const uint32_t kind_a = plan & TP_A_KIND;
             if (!(plan & TP_TRI) && (plan & TP_A_LINEAR) && kind_a <= 1u) {
@@ -414,7 +422,7 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
                 if (alpha_test) {
                     any = false;
 #pragma unroll
-                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f(afunc, ta[p], aref); any = any || act[p]; }
+                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f_mask(acmp, ta[p], aref); any = any || act[p]; }
                     if (!any) return;
                 }
 #pragma unroll
@@ -438,7 +446,7 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
                 if (alpha_test) {
                     any = false;
 #pragma unroll
-                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f(afunc, ta[p], aref); any = any || act[p]; }
+                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f_mask(acmp, ta[p], aref); any = any || act[p]; }
                     if (!any) return;
                 }
             }
@@ -475,7 +483,7 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
         }
     }
     if (textured) {
-        const uint32_t env = __ldg(&cfg->tex_env_mode);
+        const uint32_t env = cfg->tex_env_mode;
 #pragma unroll
         for (int p = 0; p < P; p++) {
             switch (env) {
@@ -506,9 +514,9 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
 
     /* ---- late depth write (707-710), blending (712-717), masked write (719-721, 20-45) ---- */
     const bool blend = has(RC_BLEND);
-    uint32_t bsrc = G_ONE, bdst = G_ZERO;
-    if (blend) { bsrc = __ldg(&cfg->blend_src); bdst = __ldg(&cfg->blend_dst); }
-    const uint32_t cm = __ldg(&cfg->color_mask);
+    const uint32_t bfunc = T.s1.w, bsrc = bfunc >> 16, bdst = bfunc & 0xFFFFu;
+    const bool blend_alpha = bfunc == ((G_SRC_ALPHA << 16) | G_ONE_MINUS_SRC_ALPHA);       /* the usual transparency blend, without the switches */
+    const uint32_t cm = ps >> PS_COLOR_MASK_SHIFT;
 #pragma unroll
     for (int p = 0; p < P; p++) {
         if (!act[p]) continue;
@@ -516,9 +524,14 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
         Color4 c = { cr[p], cg[p], cb[p], ca[p] };
         if (blend) {
             const Color4 d = { unorm_of(S.r[p]), unorm_of(S.g[p]), unorm_of(S.b[p]), unorm_of(S.a[p]) };
-            const Color4 sf = blend_factor(bsrc, c, d), df = blend_factor(bdst, c, d);
             /* blend_colors clamps, raster.c:719 clamps again, color_to_rgba32 clamps a third time: byte_of saturates once */
-            c = { c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a };
+            if (blend_alpha) {
+                const float sa = c.a, da = 1 - c.a;
+                c = { c.r * sa + d.r * da, c.g * sa + d.g * da, c.b * sa + d.b * da, c.a * sa + d.a * da };
+            } else {
+                const Color4 sf = blend_factor(bsrc, c, d), df = blend_factor(bdst, c, d);
+                c = { c.r * sf.r + d.r * df.r, c.g * sf.g + d.g * df.g, c.b * sf.b + d.b * df.b, c.a * sf.a + d.a * df.a };
+            }
         }
         if (cm == 0xFu) { S.r[p] = byte_of(c.r); S.g[p] = byte_of(c.g); S.b[p] = byte_of(c.b); S.a[p] = byte_of(c.a); }
         else if (cm != 0u) {

@@ -74,3 +74,41 @@ def test_exact_edge_form_matches_the_float_expression():
         ref = (px - f32(ax)) * (f32(by) - f32(ay)) - (py - f32(ay)) * (f32(bx) - f32(ax))
         c = (px0 - ax) * dy - (py0 - ay) * dx
         assert float(ref) == float(dy * X - dx * Y + c)
+
+
+def test_stencil_ops_as_data():
+    """dev_fragment.cuh stencil_op_encode / stencil_op_apply against stencil_op (raster.c:425-438) for every op, value, ref."""
+    KEEP, ZERO, REPLACE, INCR, DECR, INVERT, INCR_WRAP, DECR_WRAP = 0x1E00, 0, 0x1E01, 0x1E02, 0x1E03, 0x150A, 0x8507, 0x8508
+
+    def reference(op, v, ref):
+        return {KEEP: v, ZERO: 0, REPLACE: ref & 0xFF, INCR: min(v + 1, 255), INCR_WRAP: (v + 1) & 0xFF, DECR: max(v - 1, 0),
+                DECR_WRAP: (v - 1) & 0xFF, INVERT: (~v) & 0xFF}[op]
+
+    def encode(op, ref):
+        return {ZERO: 0, REPLACE: (ref & 0xFF) << 8, INCR: 0xFF | (1 << 16) | (1 << 19), INCR_WRAP: 0xFF | (1 << 16),
+                DECR: 0xFF | (3 << 16) | (1 << 18), DECR_WRAP: 0xFF | (3 << 16), INVERT: 0xFF | (0xFF << 8)}.get(op, 0xFF)
+
+    def apply(enc, v):
+        d = ((enc >> 16) & 1) - ((enc >> 16) & 2)
+        r = ((v & enc & 0xFF) ^ ((enc >> 8) & 0xFF)) + d
+        r = max(r, 0 if enc & (1 << 18) else -256)
+        r = min(r, 255 if enc & (1 << 19) else 511)
+        return r & 0xFF
+
+    for op in (KEEP, ZERO, REPLACE, INCR, DECR, INVERT, INCR_WRAP, DECR_WRAP):
+        for ref in (0, 1, 0x7F, 0xFF, 0x1234):
+            for v in range(256):
+                assert apply(encode(op, ref), v) == reference(op, v, ref), (hex(op), ref, v)
+
+
+def test_comparison_masks():
+    """compare_mask / compare_*_mask: GL_NEVER .. GL_ALWAYS are numbered lt = 1, eq = 2, gt = 4; unordered operands pass != and always."""
+    import operator
+    ops = [lambda a, b: False, operator.lt, operator.eq, operator.le, operator.gt, operator.ne, operator.ge, lambda a, b: True]
+    vals = [-1.0, 0.0, 0.5, 1.0, float("inf"), float("nan")]
+    for f in range(8):
+        m = (f & 7) | (8 if f in (5, 7) else 0)
+        for a in vals:
+            for b in vals:
+                code = 1 if a < b else 2 if a == b else 4 if a > b else 8
+                assert bool(m & code) == bool(ops[f](a, b)), (f, a, b)
