@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native MyTinyGL back end.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c3|c5|c4i]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c3|c5|c4i|c3s]
                     [--no-secondary] [--no-parity] [--no-cpu-baseline]
 
 A "step" is one frame of the workload: glClear + the draw calls + whatever makes the result observable.
@@ -58,10 +58,13 @@ WORKLOADS = {
     "c4": ("c4_grid_3840x2160", 3840, 2160, 0),
     "c5": ("c5_grid_7680x4320", 7680, 4320, 0),
     "c3": ("c3_fill_3840x2160", 3840, 2160, 64),
+    # diagnostic: C3 with per-quad texture coordinates (no two layers sample the same texels: k_fill's coincident-run reuse
+    # covers coverage and barycentrics only)
+    "c3s": ("c3_shifted_3840x2160", 3840, 2160, 64 | 256),
     # SURVEY.md 8(d) secondary layout: ONE Suzanne in the VBO, 1064 glDrawArrays under glPushMatrix / glTranslatef
     "c4i": ("c4_instanced_3840x2160", 3840, 2160, 1 << 17),
 }
-SCENE_OF = {"c4": "c4_grid", "c5": "c4_grid", "c4i": "c4_grid", "c3": "c3_fill"}
+SCENE_OF = {"c4": "c4_grid", "c5": "c4_grid", "c4i": "c4_grid", "c3": "c3_fill", "c3s": "c3_fill"}
 
 
 class Stats(ctypes.Structure):
@@ -87,10 +90,10 @@ def workload_config(workload, world):
     """The `config` object: what the workload is.  Both arms (this back end and --impl reference) print exactly this."""
     key, w, h, _ = WORKLOADS[workload]
     cnt = counts_for(key)
-    return {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3 if cnt["vertices"] else (128 if workload == "c3" else 0),
+    return {"workload": key, "width": w, "height": h, "triangles": cnt["vertices"] // 3 if cnt["vertices"] else (128 if workload in ("c3", "c3s") else 0),
             "covered_fragments": cnt["covered"], "depth_passing_fragments": cnt["tested"], "shaded_fragments": cnt["shaded"],
             "partition": f"sort-first bands x{world}",
-            "l2": "flushed between frames (256 MiB fill)" if workload == "c3" else "inputs larger than L2 (>330 MB streamed per frame)"}
+            "l2": "flushed between frames (256 MiB fill)" if workload in ("c3", "c3s") else "inputs larger than L2 (>330 MB streamed per frame)"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -148,14 +151,14 @@ def run_reference(args, workload, steps=None, warmup=None):
     steps = max(1, args.steps if steps is None else steps)
     warm = max(0, args.warmup if warmup is None else warmup)
     times = []
-    if workload == "c3":
+    if workload in ("c3", "c3s"):
         # one C3 frame takes ~40 s on a host core: a step is a bounded sample -- the first 8 of the 64 quads (the state
         # mix and the per-fragment work are the same for every quad), scaled to the frame by fragment count
         sample_quads = 8
         frac = sample_quads / 64.0
         for i in range(min(warm, 1) + min(steps, 3)):
             t0 = time.perf_counter()
-            lib.lib.scene_render(b"c3_fill", w, h, sample_quads)
+            lib.lib.scene_render(b"c3_fill", w, h, sample_quads | (variant & 256))
             if i >= min(warm, 1):
                 times.append((time.perf_counter() - t0) / frac)
         sample = f"{len(times)} steps of {sample_quads} of the 64 full-screen quads each, time scaled by 64/{sample_quads}"
@@ -285,7 +288,7 @@ def parity_block(sess, workload, assembled_color=None):
            "stencil_diff": s["stencil_diff_pixels"], "depth_max_ulp": s["depth_max_ulp"], "depth_diff_pixels": s["depth_diff_pixels"],
            "color_max_abs": s["color_max_abs"], "color_diff_pixels": s["color_diff_pixels"], "color_identical_frac": s["color_identical_frac"],
            "gl_error": [int(ref[3]), int(got[3])]}
-    if workload == "c3":      # stencil INCR_WRAP on every covered fragment (<= 128 per pixel): the plane sums to the covered-fragment count
+    if workload in ("c3", "c3s"):      # stencil INCR_WRAP on every covered fragment (<= 128 per pixel): the plane sums to the covered-fragment count
         out["covered_fragments"] = int(got[2].astype(np.int64).sum())
         out["covered_fragments_expected"] = cnt["covered"]
     else:                      # pixels some fragment passed the depth test on
@@ -324,7 +327,7 @@ def measure(sess, workload, primary):
         y0, y1 = band_rows(h, er, en)
         assert L.mtgl_dev_set_band(dev, y0, y1) == 0
 
-    is_c3 = workload == "c3"
+    is_c3 = workload in ("c3", "c3s")
     if not is_c3:
         L.scene_c4_setup(w, h, variant)
 

@@ -39,6 +39,7 @@
 #include "dev_common.cuh"
 #include "dev_texture.cuh"
 #include "dev_fragment.cuh"
+#include "dev_fasttex.cuh"
 #include "dev_fill.cuh"
 
 namespace mtgl_dev_impl {
@@ -47,21 +48,13 @@ void note_launch();
 
 constexpr int FILL_THREADS = 256;
 constexpr int FILL_WINDOW = 64;                         /* prepared triangles per window */
-constexpr int FILL_TEX_TEXELS = 64 * 64 + 32 * 32;      /* float4 texels staged per tile: a 64x64 texture with its level 1 */
 constexpr int FILL_PX = 2;                              /* pixels per thread: x = lane and x = lane + 32 of one row */
 
 /* bits 27..31 of PrepTri::eb.w (bits 0..26 = state / cfg index) */
 constexpr uint32_t PT_EXACT = 1u << 27;         /* e = A x + B y + C is exact over the tile */
 constexpr uint32_t PT_NEG = 1u << 28;           /* (inexact form only) negative area: edge values are negated */
-constexpr uint32_t PT_FASTTEX = 1u << 29;       /* textured from the staged texture, attributes finite and bounded */
-
-/* sampler plan (PrepTri::p1.z): what texture_sample_lod (textures.c:457-557) decides from the per-triangle LOD */
-constexpr uint32_t TP_A_KIND = 3u;              /* level sampled first: 0 level 0, 1 level 1, 2 opaque white (missing level 1), 3 none (weight 0) */
-constexpr uint32_t TP_A_LINEAR = 1u << 2;
-constexpr uint32_t TP_TRI = 1u << 3;            /* blend with a second level, weight cl */
-constexpr uint32_t TP_B_SHIFT = 4;              /* second level: kind in bits 4-5 */
-constexpr uint32_t TP_B_LINEAR = 1u << 6;
-constexpr uint32_t TP_REP_S = 1u << 7, TP_REP_T = 1u << 8;
+constexpr uint32_t PT_FASTTEX = 1u << 29;       /* textured from the staged texture (dev_fasttex.cuh) */
+constexpr uint32_t PT_COINCIDENT = 1u << 30;    /* same geometry, texture coordinates and sampler as the previous triangle of the window */
 
 /* what one triangle contributes to every pixel of the tile: 14 x 16 B, read as broadcasts */
 struct __align__(16) PrepTri {
@@ -86,7 +79,7 @@ constexpr uint32_t PS_STENCIL_MASK_SHIFT = 12, PS_STENCIL_WMASK_SHIFT = 20;     
 constexpr uint32_t PS_COLOR_MASK_SHIFT = 28;                                                      /* 4 bits */
 
 struct FillSmem {
-    float4 tex[FILL_TEX_TEXELS];
+    float4 tex[STAGED_TEXELS];
     PrepTri tri[FILL_WINDOW];
     uint32_t key[FILL_MAX_LIST];
     uint32_t rec[FILL_MAX_LIST];
@@ -94,9 +87,7 @@ struct FillSmem {
     float un[256];
     uint32_t acc;               /* scratch of fill_owns_tile */
     uint32_t tex_cfg;           /* state index whose texture is staged (lowest textured state of the list), ~0 = none */
-    const uint32_t *tex_l0;     /* identity of the staged texture */
-    int tw, th, tw1, th1, n0;   /* its dimensions; level 1 starts at tex[n0] */
-    uint32_t tex_ok;
+    StagedTex st;
 };
 /* two CTAs per SM */
 static_assert(2 * (sizeof(FillSmem) + 1024) <= 227 * 1024, "k_fill: two tiles per SM");
@@ -109,31 +100,31 @@ __device__ __forceinline__ uint32_t tile_box(uint32_t bbox_min, uint32_t bbox_ma
     return (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
 }
 
-__device__ __forceinline__ bool bounded(float v, float lim) { return fabsf(v) <= lim; }   /* false for NaN */
+__device__ __forceinline__ bool same16(const uint4 &a, const uint4 &b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
 
-/* filter decision of texture_sample_lod (textures.c:457-523), which depends on the per-triangle LOD and the state only */
-__device__ __forceinline__ uint32_t sampler_plan(const RasterCfg *c, float lod, float &cl)
+/* Everything a triangle hands to the per-pixel stages BEFORE its own colours, depth and per-fragment state come into play
+ * -- coverage, barycentrics, texture coordinates, the sampled texel -- is a pure function of its snapped vertices, its
+ * clamped box, its per-vertex (u, v, 1/w), its LOD and its sampler state.  Multi-pass rendering draws the same geometry
+ * again and again (C3: 64 coincident quads); a triangle that repeats all of those inputs of its predecessor in the
+ * sorted list is marked PT_COINCIDENT and reuses the predecessor's per-pixel intermediates (fill_shared). */
+__device__ __forceinline__ bool coincident(const BatchDev &b, const TriRecord *rec, const TriRecord *prev, const RasterCfg *cfg)
 {
-    uint32_t plan = (c->tex_wrap_s == G_REPEAT ? TP_REP_S : 0u) | (c->tex_wrap_t == G_REPEAT ? TP_REP_T : 0u);
-    cl = 0.0f;
-    uint32_t filter = (lod > 0.0f) ? c->tex_min : c->tex_mag;
-    const uint32_t l1_kind = c->tex_l1 ? 1u : 2u;           /* textures.c:413-419: a level that cannot exist samples as white */
-    if (filter == G_NEAREST_MIPMAP_NEAREST || filter == G_LINEAR_MIPMAP_NEAREST) {
-        if (lod >= 0.5f) return plan | l1_kind | (filter == G_LINEAR_MIPMAP_NEAREST ? TP_A_LINEAR : 0u);
-        filter = (filter == G_NEAREST_MIPMAP_NEAREST) ? G_NEAREST : G_LINEAR;
-    } else if (filter == G_NEAREST_MIPMAP_LINEAR || filter == G_LINEAR_MIPMAP_LINEAR) {
-        if (lod > 0.0f) {
-            cl = (lod > 1.0f) ? 1.0f : lod;
-            plan |= TP_TRI | (l1_kind << TP_B_SHIFT) | (filter == G_LINEAR_MIPMAP_LINEAR ? TP_B_LINEAR : 0u);
-            if (cl == 1.0f) return plan | 3u;               /* weight of level 0 is exactly 0 (dev_texture.cuh, tex_taps) */
-            return plan | 0u | (filter != G_NEAREST_MIPMAP_LINEAR ? TP_A_LINEAR : 0u);
-        }
-        filter = (filter == G_NEAREST_MIPMAP_LINEAR) ? G_NEAREST : G_LINEAR;
-    }
-    return plan | 0u | (filter == G_LINEAR ? TP_A_LINEAR : 0u);
+    const uint4 *a = reinterpret_cast<const uint4 *>(rec), *p = reinterpret_cast<const uint4 *>(prev);
+    const uint4 a0 = __ldg(a + 0), p0 = __ldg(p + 0), a1 = __ldg(a + 1), p1 = __ldg(p + 1), a2 = __ldg(a + 2), p2 = __ldg(p + 2);
+    if (!same16(a0, p0) || !same16(a1, p1) || a2.x != p2.x || a2.y != p2.y) return false;         /* vertices, area, box */
+    if ((a2.z & STATE_KIND_MASK) != (p2.z & STATE_KIND_MASK)) return false;
+    const RasterCfg *pc = b.cfgs + (p2.z & STATE_INDEX_MASK);
+    const uint32_t tf = RC_TEXTURED | RC_PERSPECTIVE;
+    if ((cfg->flags & tf) != (pc->flags & tf)) return false;
+    if (!(cfg->flags & RC_TEXTURED)) return true;
+    if (cfg->tex_l0 != pc->tex_l0 || cfg->tex_l1 != pc->tex_l1 || cfg->tex_min != pc->tex_min || cfg->tex_mag != pc->tex_mag ||
+        cfg->tex_wrap_s != pc->tex_wrap_s || cfg->tex_wrap_t != pc->tex_wrap_t) return false;
+    const uint4 a4 = __ldg(a + 4), p4 = __ldg(p + 4), a8 = __ldg(a + 8), p8 = __ldg(p + 8), a9 = __ldg(a + 9), p9 = __ldg(p + 9);
+    const uint32_t alod = __ldg(&reinterpret_cast<const uint32_t *>(rec)[15]), plod = __ldg(&reinterpret_cast<const uint32_t *>(prev)[15]);
+    return a4.x == p4.x && a4.y == p4.y && a4.z == p4.z && same16(a8, p8) && a9.x == p9.x && a9.y == p9.y && alod == plod;   /* 1/w, u, v, lod (bitwise) */
 }
 
-__device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm, uint32_t r, int px0, int py0)
+__device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm, uint32_t r, uint32_t r_prev, int px0, int py0)
 {
     const TriRecord *rec = b.records + r;
     const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
@@ -153,6 +144,7 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
     const float area = __int_as_float(row1.z), inv_area = __int_as_float(row1.w);
     const bool pos = area > 0;
     uint32_t word = cfg_index;
+    if (r_prev != 0xFFFFFFFFu && coincident(b, rec, b.records + r_prev, cfg)) word |= PT_COINCIDENT;
 
     /* raster.c:536-538: w0 = edge(v1, v2, p), w1 = edge(v2, v0, p), w2 = edge(v0, v1, p) */
     const int vx[3] = { row0.x, row0.z, row1.x }, vy[3] = { row0.y, row0.w, row1.y };
@@ -189,14 +181,11 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
     /* u/w, v/w per vertex (raster.c:501-503) */
     float u[3] = { row8.x, row8.z, row9.x }, v[3] = { row8.y, row8.w, row9.y };
     const float w[3] = { row4.x, row4.y, row4.z };
-    bool fast = (cflags & RC_TEXTURED) && sm.tex_ok && cfg->tex_l0 == sm.tex_l0;
-#pragma unroll
-    for (int k = 0; k < 3; k++) fast = fast && bounded(u[k], 1048576.0f) && bounded(v[k], 1048576.0f) && w[k] >= 9.094947e-13f && w[k] <= 1.0995116e12f;
+    if (fast_texture_ok(sm.st, cfg, u, v, w)) word |= PT_FASTTEX;
     if (cflags & RC_PERSPECTIVE) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { u[k] = u[k] * w[k]; v[k] = v[k] * w[k]; }
     }
-    if (fast) word |= PT_FASTTEX;
     P.tu = make_float4(u[0], u[1], u[2], w[0]);
     P.tv = make_float4(v[0], v[1], v[2], w[1]);
     P.te = make_float4(row4.w, row9.z, row9.w, w[2]);
@@ -213,64 +202,15 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
                       __float_as_uint(cfg->alpha_ref), (cfg->blend_src << 16) | (cfg->blend_dst & 0xFFFFu));
 }
 
-/* ---------------------------------------------------------------- texture sampling from the staged float4 texels */
-struct FTaps { float4 t00, t10, t01, t11; float fx, fy; };
-
-/* bilinear taps of one level (texture_sample_base / _mip1, textures.c:379-451).  floor(t) for |t| < 2^22 by a
- * round-down add of 1.5 * 2^23: the sum is 2^23 + 2^22 + floor(t) exactly, its low mantissa bits are the integer. */
-__device__ __forceinline__ void fast_taps(FTaps &T, const float4 *px, int w, int h, bool rep_s, bool rep_t, float u, float v)
-{
-    const float tx = u * (float)w - 0.5f, ty = v * (float)h - 0.5f;
-    const float M = 12582912.0f;
-    const float mx = __fadd_rd(tx, M), my = __fadd_rd(ty, M);
-    const int x0 = __float_as_int(mx) - 0x4B400000, y0 = __float_as_int(my) - 0x4B400000;
-    T.fx = tx - (mx - M); T.fy = ty - (my - M);
-    const int xa = wrap_coord(x0, w, rep_s), xb = wrap_coord(x0 + 1, w, rep_s);
-    const int ya = wrap_coord(y0, h, rep_t) * w, yb = wrap_coord(y0 + 1, h, rep_t) * w;
-    T.t00 = px[ya + xa]; T.t10 = px[ya + xb]; T.t01 = px[yb + xa]; T.t11 = px[yb + xb];
-}
-
-/* bilinear_filter (textures.c:294-307) of one channel, truncated to 8 bits, as the float n / 255 */
-__device__ __forceinline__ float fast_channel(float c00, float c10, float c01, float c11, float fx, float fy, float sx, float sy)
-{
-    const float top = c00 * sx + c10 * fx;
-    const float bot = c01 * sx + c11 * fx;
-    return unorm_of(byte_of(top * sy + bot * fy));
-}
-
-/* all four channels of one mip level as n / 255 floats */
-__device__ __forceinline__ float4 fast_level(const FillSmem &sm, uint32_t kind, bool linear, bool rep_s, bool rep_t, float u, float v)
-{
-    if (kind == 2u) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-    if (kind == 3u) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    const float4 *px = kind ? sm.tex + sm.n0 : sm.tex;
-    const int w = kind ? sm.tw1 : sm.tw, h = kind ? sm.th1 : sm.th;
-    if (!linear) {          /* nearest: floor(u w), clamped, never wrapped (textures.c:394-403) */
-        int x = f2i_x86(floorf(u * (float)w - 0.5f + 0.5f)), y = f2i_x86(floorf(v * (float)h - 0.5f + 0.5f));
-        x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
-        return px[y * w + x];
-    }
-    FTaps T;
-    fast_taps(T, px, w, h, rep_s, rep_t, u, v);
-    const float sx = 1.0f - T.fx, sy = 1.0f - T.fy;
-    return make_float4(fast_channel(T.t00.x, T.t10.x, T.t01.x, T.t11.x, T.fx, T.fy, sx, sy),
-                       fast_channel(T.t00.y, T.t10.y, T.t01.y, T.t11.y, T.fx, T.fy, sx, sy),
-                       fast_channel(T.t00.z, T.t10.z, T.t01.z, T.t11.z, T.fx, T.fy, sx, sy),
-                       fast_channel(T.t00.w, T.t10.w, T.t01.w, T.t11.w, T.fx, T.fy, sx, sy));
-}
-
 /* the general sampler (any texture size, any attribute values) from global memory: dev_texture.cuh, out of line */
-__device__ __noinline__ bool slow_texel(const RasterCfg *cfg, const float *un, float u, float v, float lod, float4 *out)
+__device__ __noinline__ void slow_texel(const RasterCfg *cfg, const float *un, float u, float v, float lod, float4 *out)
 {
     TexTaps T;
     tex_taps(T, cfg, u, v, lod);
-    const float a = tex_channel(T, 24, un);
-    if ((cfg->flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, a, cfg->alpha_ref)) return false;
-    *out = make_float4(tex_channel(T, 0, un), tex_channel(T, 8, un), tex_channel(T, 16, un), a);
-    return true;
+    *out = make_float4(tex_channel(T, 0, un), tex_channel(T, 8, un), tex_channel(T, 16, un), tex_channel(T, 24, un));
 }
 
-/* ---------------------------------------------------------------- one triangle over this thread's pixels */
+/* ---------------------------------------------------------------- one run of coincident triangles over this thread's pixels */
 /* Pixel state of a thread: colour channels as integral floats 0..255 (the byte the plane holds), depth, stencil. */
 struct PixelState {
     float r[FILL_PX], g[FILL_PX], b[FILL_PX], a[FILL_PX];
@@ -278,21 +218,28 @@ struct PixelState {
     uint32_t stencil[FILL_PX];
 };
 
+/* what the triangles of a run share, per pixel */
+struct Shared {
+    bool cov[FILL_PX];                                  /* inside the triangle, its box and the framebuffer */
+    float b0[FILL_PX], b1[FILL_PX], b2[FILL_PX];        /* barycentrics (raster.c:541-543) */
+    float tr[FILL_PX], tg[FILL_PX], tb[FILL_PX], ta[FILL_PX];   /* the sampled texel */
+};
+
+/* coverage (raster.c:536-540), barycentrics, texture coordinates (618-637) and the texel of the run's first triangle.
+ * `single`: the run has one member, so its alpha test may discard before the colour channels are filtered.
+ * Returns false when this thread has nothing to do for the whole run. */
 template <uint32_t ON, uint32_t OFF>
-__device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem &sm, const PrepTri &T, int px0, int py0, int Y,
-                                              const int (&X)[FILL_PX], const bool (&inb)[FILL_PX], PixelState &S)
+__device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &sm, const PrepTri &T, int px0, int py0, int Y,
+                                            const int (&X)[FILL_PX], const bool (&inb)[FILL_PX], bool single, Shared &H)
 {
     constexpr int P = FILL_PX;
     const uint32_t box = __float_as_uint(T.ec.w);
-    if (Y < (int)((box >> 8) & 0xFFu) || Y > (int)(box >> 24)) return;          /* warp-uniform */
+    if (Y < (int)((box >> 8) & 0xFFu) || Y > (int)(box >> 24)) return false;          /* warp-uniform */
     const int bx0 = (int)(box & 0xFFu), bx1 = (int)((box >> 16) & 0xFFu);
     const uint32_t word = __float_as_uint(T.eb.w);
-    const RasterCfg *cfg = b.cfgs + (word & STATE_INDEX_MASK);      /* only the rarely used fields are read from it */
-    const uint4 s0 = T.s0;
-    const uint32_t fl = s0.x, ps = s0.y;
+    const uint32_t fl = T.s0.x;
     auto has = [&](uint32_t bit) -> bool { return (ON & bit) ? true : ((OFF & bit) ? false : (fl & bit) != 0u); };
 
-    /* ---- coverage: inclusive on all three edges, no fill rule (raster.c:539-540) ---- */
     float e0[P], e1[P], e2[P];
     if (word & PT_EXACT) {
         const float4 ea = T.ea, eb = T.eb, ec = T.ec;
@@ -315,21 +262,109 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
             if (word & PT_NEG) { e0[p] = -e0[p]; e1[p] = -e1[p]; e2[p] = -e2[p]; }
         }
     }
-    bool act[P];
     bool any = false;
 #pragma unroll
     for (int p = 0; p < P; p++) {
-        act[p] = inb[p] && X[p] >= bx0 && X[p] <= bx1 && fminf(fminf(e0[p], e1[p]), e2[p]) >= 0.0f;
-        any = any || act[p];
+        H.cov[p] = inb[p] && X[p] >= bx0 && X[p] <= bx1 && fminf(fminf(e0[p], e1[p]), e2[p]) >= 0.0f;
+        any = any || H.cov[p];
     }
-    if (!any) return;
-
+    if (!any) return false;
     const float inv_area = T.ea.w;
-    float b0[P], b1[P], b2[P];
 #pragma unroll
-    for (int p = 0; p < P; p++) { b0[p] = e0[p] * inv_area; b1[p] = e1[p] * inv_area; b2[p] = e2[p] * inv_area; }
+    for (int p = 0; p < P; p++) { H.b0[p] = e0[p] * inv_area; H.b1[p] = e1[p] * inv_area; H.b2[p] = e2[p] * inv_area; }
+    if (!has(RC_TEXTURED)) return true;
 
-    /* ---- depth value, stencil test + ops, depth test (raster.c:546-587) ---- */
+    const float4 tu = T.tu, tv = T.tv;
+    const float w2 = T.te.w;
+    float u[P], v[P];
+    if (has(RC_PERSPECTIVE)) {
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const float uw = H.b0[p] * tu.x + H.b1[p] * tu.y + H.b2[p] * tu.z;
+            const float vw = H.b0[p] * tv.x + H.b1[p] * tv.y + H.b2[p] * tv.z;
+            const float ow = H.b0[p] * tu.w + H.b1[p] * tv.w + H.b2[p] * w2;
+            const float w = 1.0f / ow;
+            u[p] = uw * w; v[p] = vw * w;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            u[p] = H.b0[p] * tu.x + H.b1[p] * tu.y + H.b2[p] * tu.z;
+            v[p] = H.b0[p] * tv.x + H.b1[p] * tv.y + H.b2[p] * tv.z;
+        }
+    }
+    if (word & PT_FASTTEX) {
+        const uint32_t plan = __float_as_uint(T.p1.z);
+        const uint32_t kind_a = plan & TP_A_KIND;
+        if (!(plan & TP_TRI) && (plan & TP_A_LINEAR) && kind_a <= 1u) {
+            /* one bilinear level (the magnified / non-mipmapped case): alpha first; a lone triangle whose alpha test
+             * (raster.c:640-643: on the texel's alpha) discards both fragments never filters the colour channels */
+            const bool rep_s = (plan & TP_REP_S) != 0u, rep_t = (plan & TP_REP_T) != 0u;
+            const float4 *px = kind_a ? sm.tex + sm.st.n0 : sm.tex;
+            const int w = kind_a ? sm.st.w1 : sm.st.w, h = kind_a ? sm.st.h1 : sm.st.h;
+            FTaps F[P];
+            float sx[P], sy[P];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                fast_taps(F[p], px, w, h, rep_s, rep_t, fast_wrap(u[p], rep_s), fast_wrap(v[p], rep_t));
+                sx[p] = 1.0f - F[p].fx; sy[p] = 1.0f - F[p].fy;
+                H.ta[p] = fast_channel(F[p].t00.w, F[p].t10.w, F[p].t01.w, F[p].t11.w, F[p].fx, F[p].fy, sx[p], sy[p]);
+            }
+            if (single && has(RC_ALPHA_TEST)) {
+                const uint32_t acmp = (T.s0.y >> PS_ALPHA_CMP_SHIFT) & 15u;
+                const float aref = __uint_as_float(T.s1.z);
+                any = false;
+#pragma unroll
+                for (int p = 0; p < P; p++) any = any || (H.cov[p] && compare_f_mask(acmp, H.ta[p], aref));
+                if (!any) {         /* the stencil / depth stages of the triangle still run (fill_one), the colour stages cannot be reached */
+#pragma unroll
+                    for (int p = 0; p < P; p++) { H.tr[p] = 0.0f; H.tg[p] = 0.0f; H.tb[p] = 0.0f; }
+                    return true;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                H.tr[p] = fast_channel(F[p].t00.x, F[p].t10.x, F[p].t01.x, F[p].t11.x, F[p].fx, F[p].fy, sx[p], sy[p]);
+                H.tg[p] = fast_channel(F[p].t00.y, F[p].t10.y, F[p].t01.y, F[p].t11.y, F[p].fx, F[p].fy, sx[p], sy[p]);
+                H.tb[p] = fast_channel(F[p].t00.z, F[p].t10.z, F[p].t01.z, F[p].t11.z, F[p].fx, F[p].fy, sx[p], sy[p]);
+            }
+        } else {
+            const float cl = T.p1.w;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float4 t = fast_sample(sm.tex, sm.st, plan, cl, u[p], v[p]);
+                H.tr[p] = t.x; H.tg[p] = t.y; H.tb[p] = t.z; H.ta[p] = t.w;
+            }
+        }
+    } else {
+        const RasterCfg *cfg = b.cfgs + (word & STATE_INDEX_MASK);
+        const float lod = T.zz.w;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            H.tr[p] = H.tg[p] = H.tb[p] = H.ta[p] = 0.0f;
+            if (!H.cov[p]) continue;
+            float4 t;
+            slow_texel(cfg, sm.un, u[p], v[p], lod, &t);
+            H.tr[p] = t.x; H.tg[p] = t.y; H.tb[p] = t.z; H.ta[p] = t.w;
+        }
+    }
+    return true;
+}
+
+/* One triangle of the run: depth value, stencil test + ops, depth test (raster.c:546-587), colour (581-591), alpha test
+ * (640-643), texenv (645-669), fog (672-705), late depth write (707-710), blending (712-717), masked write (719-721, 20-45). */
+template <uint32_t ON, uint32_t OFF>
+__device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, const Shared &H, PixelState &S)
+{
+    constexpr int P = FILL_PX;
+    const uint4 s0 = T.s0;
+    const uint32_t fl = s0.x, ps = s0.y;
+    auto has = [&](uint32_t bit) -> bool { return (ON & bit) ? true : ((OFF & bit) ? false : (fl & bit) != 0u); };
+    const RasterCfg *cfg = b.cfgs + (__float_as_uint(T.eb.w) & STATE_INDEX_MASK);      /* only the rarely used fields are read from it */
+
+    bool act[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) act[p] = H.cov[p];
     float depth[P];
 #pragma unroll
     for (int p = 0; p < P; p++) depth[p] = 0.0f;
@@ -340,7 +375,7 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
         const bool r01 = has(RC_DEPTH_RANGE_01);
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            const float z = b0[p] * zz.x + b1[p] * zz.y + b2[p] * zz.z;
+            const float z = H.b0[p] * zz.x + H.b1[p] * zz.y + H.b2[p] * zz.z;
             if (r01) depth[p] = (z + 1.0f) * 0.5f;
             else depth[p] = (float)((double)((z + 1.0f) * 0.5f) * (cfg->depth_far - cfg->depth_near) + cfg->depth_near);   /* raster.c:548 */
         }
@@ -363,108 +398,19 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
 #pragma unroll
         for (int p = 0; p < P; p++) act[p] = act[p] && compare_f_mask(depth_cmp, depth[p], S.depth[p]);
     }
-    any = false;
+    const bool textured = has(RC_TEXTURED);
+    if (textured && has(RC_ALPHA_TEST)) {       /* on the texel's alpha, and only when textured (raster.c:640-643) */
+        const uint32_t acmp = (ps >> PS_ALPHA_CMP_SHIFT) & 15u;
+        const float aref = __uint_as_float(T.s1.z);
+#pragma unroll
+        for (int p = 0; p < P; p++) act[p] = act[p] && compare_f_mask(acmp, H.ta[p], aref);
+    }
+    bool any = false;
 #pragma unroll
     for (int p = 0; p < P; p++) any = any || act[p];
     if (!any) return;
     const bool depth_write = depth_test && has(RC_DEPTH_WRITE);
 
-    /* ---- texture first: the alpha test only looks at the texel's alpha (raster.c:640-643), so the fragments it
-     * discards never need their interpolated colour ---- */
-    float tr[P], tg[P], tb[P], ta[P];
-    const bool textured = has(RC_TEXTURED);
-    if (textured) {
-        const float4 tu = T.tu, tv = T.tv;
-        const float w2 = T.te.w;
-        float u[P], v[P];
-        if (has(RC_PERSPECTIVE)) {
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-                const float uw = b0[p] * tu.x + b1[p] * tu.y + b2[p] * tu.z;
-                const float vw = b0[p] * tv.x + b1[p] * tv.y + b2[p] * tv.z;
-                const float ow = b0[p] * tu.w + b1[p] * tv.w + b2[p] * w2;
-                const float w = 1.0f / ow;
-                u[p] = uw * w; v[p] = vw * w;
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-                u[p] = b0[p] * tu.x + b1[p] * tu.y + b2[p] * tu.z;
-                v[p] = b0[p] * tv.x + b1[p] * tv.y + b2[p] * tv.z;
-            }
-        }
-        const bool alpha_test = has(RC_ALPHA_TEST);
-        const uint32_t acmp = (ps >> PS_ALPHA_CMP_SHIFT) & 15u;
-        const float aref = __uint_as_float(T.s1.z);
-        if (word & PT_FASTTEX) {
-            const uint32_t plan = __float_as_uint(T.p1.z);
-            const bool rep_s = (plan & TP_REP_S) != 0u, rep_t = (plan & TP_REP_T) != 0u;
-            /* wrap (textures.c:463-486) */
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-                /* (PT_FASTTEX: u and v are finite, so the saturate is the reference's pair of ternaries) */
-                if (rep_s) { u[p] = u[p] - truncf(u[p]); if (u[p] < 0) u[p] += 1.0f; } else u[p] = __saturatef(u[p]);
-                if (rep_t) { v[p] = v[p] - truncf(v[p]); if (v[p] < 0) v[p] += 1.0f; } else v[p] = __saturatef(v[p]);
-            }
-            const uint32_t kind_a = plan & TP_A_KIND;
-            if (!(plan & TP_TRI) && (plan & TP_A_LINEAR) && kind_a <= 1u) {
-                /* one bilinear level (the magnified / non-mipmapped case): alpha first, colour channels only for survivors */
-                const float4 *px = kind_a ? sm.tex + sm.n0 : sm.tex;
-                const int w = kind_a ? sm.tw1 : sm.tw, h = kind_a ? sm.th1 : sm.th;
-                FTaps F[P];
-                float sx[P], sy[P];
-#pragma unroll
-                for (int p = 0; p < P; p++) {
-                    fast_taps(F[p], px, w, h, rep_s, rep_t, u[p], v[p]);
-                    sx[p] = 1.0f - F[p].fx; sy[p] = 1.0f - F[p].fy;
-                    ta[p] = fast_channel(F[p].t00.w, F[p].t10.w, F[p].t01.w, F[p].t11.w, F[p].fx, F[p].fy, sx[p], sy[p]);
-                }
-                if (alpha_test) {
-                    any = false;
-#pragma unroll
-                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f_mask(acmp, ta[p], aref); any = any || act[p]; }
-                    if (!any) return;
-                }
-#pragma unroll
-                for (int p = 0; p < P; p++) {
-                    tr[p] = fast_channel(F[p].t00.x, F[p].t10.x, F[p].t01.x, F[p].t11.x, F[p].fx, F[p].fy, sx[p], sy[p]);
-                    tg[p] = fast_channel(F[p].t00.y, F[p].t10.y, F[p].t01.y, F[p].t11.y, F[p].fx, F[p].fy, sx[p], sy[p]);
-                    tb[p] = fast_channel(F[p].t00.z, F[p].t10.z, F[p].t01.z, F[p].t11.z, F[p].fx, F[p].fy, sx[p], sy[p]);
-                }
-            } else {
-                const float cl = T.p1.w, s = 1.0f - cl;
-#pragma unroll
-                for (int p = 0; p < P; p++) {
-                    float4 t = fast_level(sm, kind_a, (plan & TP_A_LINEAR) != 0u, rep_s, rep_t, u[p], v[p]);
-                    if (plan & TP_TRI) {        /* textures.c:512-515: per channel, truncated to 8 bits once more */
-                        const float4 t1 = fast_level(sm, (plan >> TP_B_SHIFT) & 3u, (plan & TP_B_LINEAR) != 0u, rep_s, rep_t, u[p], v[p]);
-                        t.x = unorm_of(byte_of(t.x * s + t1.x * cl)); t.y = unorm_of(byte_of(t.y * s + t1.y * cl));
-                        t.z = unorm_of(byte_of(t.z * s + t1.z * cl)); t.w = unorm_of(byte_of(t.w * s + t1.w * cl));
-                    }
-                    tr[p] = t.x; tg[p] = t.y; tb[p] = t.z; ta[p] = t.w;
-                }
-                if (alpha_test) {
-                    any = false;
-#pragma unroll
-                    for (int p = 0; p < P; p++) { act[p] = act[p] && compare_f_mask(acmp, ta[p], aref); any = any || act[p]; }
-                    if (!any) return;
-                }
-            }
-        } else {
-            const float lod = T.zz.w;
-            any = false;
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-                if (!act[p]) continue;
-                float4 t;
-                if (slow_texel(cfg, sm.un, u[p], v[p], lod, &t)) { tr[p] = t.x; tg[p] = t.y; tb[p] = t.z; ta[p] = t.w; any = true; }
-                else act[p] = false;
-            }
-            if (!any) return;
-        }
-    }
-
-    /* ---- colour (raster.c:581-591), texenv (645-669), fog (672-705) ---- */
     float cr[P], cg[P], cb[P], ca[P];
     {
         const float4 c2 = T.c2;
@@ -475,30 +421,34 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
             const float4 c0 = T.c0, c1 = T.c1;
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                cr[p] = c0.x * b0[p] + c1.x * b1[p] + c2.x * b2[p];
-                cg[p] = c0.y * b0[p] + c1.y * b1[p] + c2.y * b2[p];
-                cb[p] = c0.z * b0[p] + c1.z * b1[p] + c2.z * b2[p];
-                ca[p] = c0.w * b0[p] + c1.w * b1[p] + c2.w * b2[p];
+                cr[p] = c0.x * H.b0[p] + c1.x * H.b1[p] + c2.x * H.b2[p];
+                cg[p] = c0.y * H.b0[p] + c1.y * H.b1[p] + c2.y * H.b2[p];
+                cb[p] = c0.z * H.b0[p] + c1.z * H.b1[p] + c2.z * H.b2[p];
+                ca[p] = c0.w * H.b0[p] + c1.w * H.b1[p] + c2.w * H.b2[p];
             }
         }
     }
     if (textured) {
         const uint32_t env = cfg->tex_env_mode;
+        if (env == G_MODULATE) {
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            switch (env) {
-            case G_REPLACE: cr[p] = tr[p]; cg[p] = tg[p]; cb[p] = tb[p]; ca[p] = ta[p]; break;
-            case G_DECAL:
-                cr[p] = cr[p] + (tr[p] - cr[p]) * ta[p]; cg[p] = cg[p] + (tg[p] - cg[p]) * ta[p]; cb[p] = cb[p] + (tb[p] - cb[p]) * ta[p];
-                break;
-            case G_BLEND: {
-                const float *ec = cfg->tex_env_color;
-                cr[p] = cr[p] * (1.0f - tr[p]) + ec[0] * tr[p]; cg[p] = cg[p] * (1.0f - tg[p]) + ec[1] * tg[p];
-                cb[p] = cb[p] * (1.0f - tb[p]) + ec[2] * tb[p]; ca[p] = ca[p] * ta[p];
-                break;
-            }
-            case G_ADD: cr[p] = cr[p] + tr[p]; cg[p] = cg[p] + tg[p]; cb[p] = cb[p] + tb[p]; ca[p] = ca[p] * ta[p]; break;
-            default: cr[p] = cr[p] * tr[p]; cg[p] = cg[p] * tg[p]; cb[p] = cb[p] * tb[p]; ca[p] = ca[p] * ta[p]; break;
+            for (int p = 0; p < P; p++) { cr[p] = cr[p] * H.tr[p]; cg[p] = cg[p] * H.tg[p]; cb[p] = cb[p] * H.tb[p]; ca[p] = ca[p] * H.ta[p]; }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float tr = H.tr[p], tg = H.tg[p], tb = H.tb[p], ta = H.ta[p];
+                switch (env) {
+                case G_REPLACE: cr[p] = tr; cg[p] = tg; cb[p] = tb; ca[p] = ta; break;
+                case G_DECAL: cr[p] = cr[p] + (tr - cr[p]) * ta; cg[p] = cg[p] + (tg - cg[p]) * ta; cb[p] = cb[p] + (tb - cb[p]) * ta; break;
+                case G_BLEND: {
+                    const float *ec = cfg->tex_env_color;
+                    cr[p] = cr[p] * (1.0f - tr) + ec[0] * tr; cg[p] = cg[p] * (1.0f - tg) + ec[1] * tg;
+                    cb[p] = cb[p] * (1.0f - tb) + ec[2] * tb; ca[p] = ca[p] * ta;
+                    break;
+                }
+                case G_ADD: cr[p] = cr[p] + tr; cg[p] = cg[p] + tg; cb[p] = cb[p] + tb; ca[p] = ca[p] * ta; break;
+                default: cr[p] = cr[p] * tr; cg[p] = cg[p] * tg; cb[p] = cb[p] * tb; ca[p] = ca[p] * ta; break;
+                }
             }
         }
     }
@@ -507,12 +457,11 @@ __device__ __forceinline__ void fill_triangle(const BatchDev &b, const FillSmem 
         const float fr = cfg->fog_color[0], fg = cfg->fog_color[1], fbl = cfg->fog_color[2], fa = cfg->fog_color[3];
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            const float f = fog_factor(cfg, b0[p] * te.x + b1[p] * te.y + b2[p] * te.z);
+            const float f = fog_factor(cfg, H.b0[p] * te.x + H.b1[p] * te.y + H.b2[p] * te.z);
             cr[p] = fr + (cr[p] - fr) * f; cg[p] = fg + (cg[p] - fg) * f; cb[p] = fbl + (cb[p] - fbl) * f; ca[p] = fa;   /* color_lerp_rgb(fog, c, f) */
         }
     }
 
-    /* ---- late depth write (707-710), blending (712-717), masked write (719-721, 20-45) ---- */
     const bool blend = has(RC_BLEND);
     const uint32_t bfunc = T.s1.w, bsrc = bfunc >> 16, bdst = bfunc & 0xFFFFu;
     const bool blend_alpha = bfunc == ((G_SRC_ALPHA << 16) | G_ONE_MINUS_SRC_ALPHA);       /* the usual transparency blend, without the switches */
@@ -566,7 +515,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
 
     /* ---- list -> shared memory, sorted by submission id; the texture to stage ---- */
     sm.un[threadIdx.x] = b.unorm8[threadIdx.x];
-    if (threadIdx.x == 0) { sm.tex_cfg = 0xFFFFFFFFu; sm.tex_ok = 0u; sm.tex_l0 = nullptr; }
+    if (threadIdx.x == 0) { sm.tex_cfg = 0xFFFFFFFFu; sm.st.id = nullptr; }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < L; i += FILL_THREADS) {
         const uint32_t r = list[i];
@@ -583,20 +532,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
         for (uint32_t j = 0; j < L; j++) rank += (sm.key[j] < mine) ? 1u : 0u;
         sm.sorted[rank] = sm.rec[i];
     }
-    if (sm.tex_cfg != 0xFFFFFFFFu) {
-        const RasterCfg *tc = b.cfgs + sm.tex_cfg;
-        const int n0 = tc->tex_w * tc->tex_h, n1 = tc->tex_l1 ? tc->tex_w1 * tc->tex_h1 : 0;
-        if (n0 + n1 <= FILL_TEX_TEXELS) {
-            for (int i = threadIdx.x; i < n0 + n1; i += FILL_THREADS) {
-                const uint32_t t = (i < n0) ? __ldg(tc->tex_l0 + i) : __ldg(tc->tex_l1 + (i - n0));
-                sm.tex[i] = make_float4(sm.un[t & 0xFFu], sm.un[(t >> 8) & 0xFFu], sm.un[(t >> 16) & 0xFFu], sm.un[t >> 24]);
-            }
-            if (threadIdx.x == 0) {
-                sm.tex_l0 = tc->tex_l0; sm.tw = tc->tex_w; sm.th = tc->tex_h; sm.tw1 = tc->tex_w1; sm.th1 = tc->tex_h1; sm.n0 = n0;
-                sm.tex_ok = 1u;
-            }
-        }
-    }
+    if (sm.tex_cfg != 0xFFFFFFFFu) stage_texture(sm.tex, sm.st, b.cfgs + sm.tex_cfg, sm.un, FILL_THREADS);
 
     /* ---- clear rectangle relative to the tile (gl_api.c:409-457) ---- */
     const int cx0 = max(clr.x0 - px0, 0), cy0 = max(clr.y0 - py0, 0);
@@ -611,7 +547,8 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
     for (uint32_t w0 = 0; w0 < L; w0 += FILL_WINDOW) {
         const uint32_t n = min((uint32_t)FILL_WINDOW, L - w0);
         __syncthreads();                /* sorted list + staged texture complete; the previous window is no longer read */
-        if (threadIdx.x < n) prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], px0, py0);
+        if (threadIdx.x < n)        /* (a run of coincident triangles does not continue across windows) */
+            prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu, px0, py0);
         __syncthreads();
 
         for (int g = 0; g < TILE_H / 8; g++) {
@@ -635,7 +572,17 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
                 S.r[p] = (float)(c & 0xFFu); S.g[p] = (float)((c >> 8) & 0xFFu); S.b[p] = (float)((c >> 16) & 0xFFu); S.a[p] = (float)(c >> 24);
             }
 #pragma unroll 1
-            for (uint32_t t = 0; t < n; t++) fill_triangle<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, S);
+            for (uint32_t t = 0; t < n;) {
+                /* the run of coincident triangles that starts at t: coverage, barycentrics and texel once, then each member */
+                uint32_t e = t + 1;
+                while (e < n && (__float_as_uint(sm.tri[e].eb.w) & PT_COINCIDENT)) e++;
+                Shared H;
+                if (fill_shared<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, e == t + 1, H)) {
+#pragma unroll 1
+                    for (; t < e; t++) fill_one<ON, OFF>(b, sm.tri[t], H, S);
+                }
+                t = e;
+            }
 #pragma unroll
             for (int p = 0; p < FILL_PX; p++) {
                 if (!inb[p]) continue;

@@ -13,7 +13,7 @@ CASES = (
     + [("c2_cube", 480, 270, 0), ("c2_cube", 1920, 1080, 0)]
     + [("c2_floor", 400, 300, v) for v in range(6)]
     + [("c2_texenv", 320, 240, v) for v in range(5)]
-    + [("c3_fill", 256, 144, 4), ("c3_fill", 640, 360, 9)]
+    + [("c3_fill", 256, 144, 4), ("c3_fill", 640, 360, 9), ("c3_fill", 320, 200, 6 | 256)]    # | 256: per-quad texture coordinates
     + [("c4_grid", 480, 270, C4_SMALL), ("c4_grid", 480, 270, C4_SMALL_PHONG), ("c4_grid", 960, 540, 6 | (4 << 8))]
     + [("clipping", 320, 240, v) for v in range(2)]
     + [("primitives", 320, 240, v) for v in (0, 1, 3, 5, 7, 8)]

@@ -274,10 +274,13 @@ static void scene_c2_texenv(int w, int h, int variant)
     glEnd();
 }
 
-/* C3: fill-rate stress.  variant = number of full-screen quads (0 -> 64). */
+/* C3: fill-rate stress.  variant bits 0-7 = number of full-screen quads (0 -> 64); bit 8: every quad gets its own texture
+ * coordinates (shifted by q / 512), so that no two quads sample the same texels -- the layers are then no longer
+ * coincident for the texture stage (a diagnostic variant, not a BASELINE configuration). */
 static void scene_c3(int w, int h, int variant)
 {
-    int nq = variant > 0 ? variant : 64;
+    int nq = (variant & 0xFF) > 0 ? (variant & 0xFF) : 64;
+    int shifted = (variant >> 8) & 1;
     glViewport(0, 0, w, h);
     glMatrixMode(GL_PROJECTION);
     glLoadIdentity();
@@ -304,10 +307,11 @@ static void scene_c3(int w, int h, int variant)
     for (int q = 0; q < nq; q++) {
         glColor4f((float)((q * 37) % 64) / 63.0f, (float)((q * 11) % 64) / 63.0f, (float)((q * 5) % 64) / 63.0f,
                   (q & 1) ? 0.75f : 0.25f);
-        glTexCoord2f(0.0f, 0.0f); glVertex2f(-1.0f, -1.0f);
-        glTexCoord2f(1.0f, 0.0f); glVertex2f(1.0f, -1.0f);
-        glTexCoord2f(1.0f, 1.0f); glVertex2f(1.0f, 1.0f);
-        glTexCoord2f(0.0f, 1.0f); glVertex2f(-1.0f, 1.0f);
+        float o = shifted ? (float)q / 512.0f : 0.0f;
+        glTexCoord2f(0.0f + o, 0.0f); glVertex2f(-1.0f, -1.0f);
+        glTexCoord2f(1.0f + o, 0.0f); glVertex2f(1.0f, -1.0f);
+        glTexCoord2f(1.0f + o, 1.0f); glVertex2f(1.0f, 1.0f);
+        glTexCoord2f(0.0f + o, 1.0f); glVertex2f(-1.0f, 1.0f);
     }
     glEnd();
 }

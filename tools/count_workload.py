@@ -20,6 +20,7 @@ WORKLOADS = {
     "c1_suzanne_800x600": ("c1_suzanne", 800, 600, 0),
     "c2_cube_1920x1080": ("c2_cube", 1920, 1080, 0),
     "c3_fill_3840x2160": ("c3_fill", 3840, 2160, 64),
+    "c3_shifted_3840x2160": ("c3_fill", 3840, 2160, 64 | 256),      # diagnostic: every quad with its own texture coordinates
     "c4_grid_3840x2160": ("c4_grid", 3840, 2160, 0),
     "c4_grid_phong_3840x2160": ("c4_grid", 3840, 2160, 1 << 16),
     "c5_grid_7680x4320": ("c4_grid", 7680, 4320, 0),
