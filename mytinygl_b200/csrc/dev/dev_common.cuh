@@ -456,12 +456,14 @@ struct RasterPlan {
     bool unordered_range01;     /* every unordered state has depth range [0,1] */
     uint32_t fill_mode;         /* FILL_* (dev_fill.cuh): may the pixel-owner kernel (k_fill.cu) take in-order tiles of large triangles */
     uint32_t in_order_all, in_order_any;    /* AND / OR of the RasterCfg flags of the pass's in-order states */
+    uint32_t stage_cfg;         /* state whose texture the shade pass stages in shared memory (first textured deferrable state), ~0 = none */
 };
 /* ev_vis / ev_shade are recorded after the visibility kernels and after the shade kernel (stage timing) */
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
                  cudaStream_t s);
+void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t stage_cfg, cudaStream_t s);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
 void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);

@@ -32,16 +32,24 @@ __device__ __forceinline__ uint8_t stencil_apply(uint32_t op, uint8_t v, int32_t
  * "always".  One mask per triangle, then every test is branch-free. */
 __device__ __forceinline__ uint32_t compare_mask(uint32_t f) { return (f & 7u) | (((f & 7u) == 5u || (f & 7u) == 7u) ? 8u : 0u); }
 
+/* (the mask is the same for every fragment of a triangle: the tests on it are loop-invariant and the usual functions
+ * -- always, greater, less, lequal -- cost one comparison per fragment) */
 __device__ __forceinline__ bool compare_f_mask(uint32_t m, float a, float b)
 {
-    const uint32_t code = (a < b) ? 1u : ((a == b) ? 2u : ((a > b) ? 4u : 8u));
-    return (m & code) != 0u;
+    if (m == 15u) return true;
+    if (m == 4u) return a > b;
+    if (m == 1u) return a < b;
+    if (m == 3u) return a <= b;
+    const uint32_t idx = (a != a || b != b) ? 3u : ((a > b) ? 2u : ((a == b) ? 1u : 0u));
+    return ((m >> idx) & 1u) != 0u;
 }
 
 __device__ __forceinline__ bool compare_i_mask(uint32_t m, int32_t a, int32_t b)
 {
-    const uint32_t code = (a < b) ? 1u : ((a == b) ? 2u : 4u);
-    return (m & code) != 0u;
+    if ((m & 7u) == 7u) return true;
+    if ((m & 7u) == 2u) return a == b;
+    const uint32_t idx = (a > b) ? 2u : ((a == b) ? 1u : 0u);
+    return ((m >> idx) & 1u) != 0u;
 }
 
 /* A stencil operation (raster.c:425-438) as data: nv = clamp(((v & A) ^ X) + D, lo, hi) & 0xFF with
@@ -60,13 +68,21 @@ __device__ __forceinline__ uint32_t stencil_op_encode(uint32_t op, int32_t ref)
     }
 }
 
-__device__ __forceinline__ uint32_t stencil_op_apply(uint32_t enc, uint32_t v)
+struct StencilOp { uint32_t amask, xmask; int add, lo, hi; };
+
+__device__ __forceinline__ StencilOp stencil_op_decode(uint32_t enc)
 {
-    const int d = (int)((enc >> 16) & 1u) - (int)((enc >> 16) & 2u);           /* 0, +1, -1 */
-    int r = (int)((v & enc) ^ ((enc >> 8) & 0xFFu)) + d;        /* v <= 255: v & enc == v & A */
-    r = max(r, (enc & (1u << 18)) ? 0 : -256);
-    r = min(r, (enc & (1u << 19)) ? 255 : 511);
-    return (uint32_t)r & 0xFFu;
+    StencilOp o;
+    o.amask = enc & 0xFFu; o.xmask = (enc >> 8) & 0xFFu;
+    o.add = (int)((enc >> 16) & 1u) - (int)((enc >> 16) & 2u);          /* 0, +1, -1 */
+    o.lo = (enc & (1u << 18)) ? 0 : -256;
+    o.hi = (enc & (1u << 19)) ? 255 : 511;
+    return o;
+}
+
+__device__ __forceinline__ uint32_t stencil_op_apply(const StencilOp &o, uint32_t v)
+{
+    return (uint32_t)min(max((int)((v & o.amask) ^ o.xmask) + o.add, o.lo), o.hi) & 0xFFu;
 }
 
 __device__ __forceinline__ float fog_factor(const RasterCfg *c, float coord)   /* raster.c:677-701 */

@@ -384,15 +384,24 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
         const uint4 s1 = T.s1;
         const uint32_t scmp = (ps >> PS_STENCIL_CMP_SHIFT) & 15u, smask = (ps >> PS_STENCIL_MASK_SHIFT) & 0xFFu, swm = (ps >> PS_STENCIL_WMASK_SHIFT) & 0xFFu;
         const int32_t mref = (int32_t)s0.z;
+        const StencilOp zpass_op = stencil_op_decode(s0.w);
+        if ((scmp & 7u) == 7u && !depth_test) {      /* GL_ALWAYS without a depth test: every covered fragment takes the zpass op */
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            const uint32_t sval = S.stencil[p];
-            const bool spass = compare_i_mask(scmp, mref, (int32_t)(sval & smask));
-            const bool zpass = !depth_test || compare_f_mask(depth_cmp, depth[p], S.depth[p]);
-            const uint32_t op = !spass ? s1.x : (!zpass ? s1.y : s0.w);
-            const uint32_t nv = stencil_op_apply(op, sval);
-            if (act[p]) S.stencil[p] = (sval & ~swm) | (nv & swm);
-            act[p] = act[p] && spass && zpass;
+            for (int p = 0; p < P; p++) {
+                const uint32_t sval = S.stencil[p];
+                if (act[p]) S.stencil[p] = (sval & ~swm) | (stencil_op_apply(zpass_op, sval) & swm);
+            }
+        } else {
+            const StencilOp fail_op = stencil_op_decode(s1.x), zfail_op = stencil_op_decode(s1.y);
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const uint32_t sval = S.stencil[p];
+                const bool spass = compare_i_mask(scmp, mref, (int32_t)(sval & smask));
+                const bool zpass = !depth_test || compare_f_mask(depth_cmp, depth[p], S.depth[p]);
+                const uint32_t nv = !spass ? stencil_op_apply(fail_op, sval) : (!zpass ? stencil_op_apply(zfail_op, sval) : stencil_op_apply(zpass_op, sval));
+                if (act[p]) S.stencil[p] = (sval & ~swm) | (nv & swm);
+                act[p] = act[p] && spass && zpass;
+            }
         }
     } else if (depth_test) {
 #pragma unroll

@@ -32,6 +32,7 @@
 #include "dev_texture.cuh"
 #include "dev_fragment.cuh"
 #include "dev_fill.cuh"
+#include "dev_shade.cuh"
 
 namespace mtgl_dev_impl {
 
@@ -63,108 +64,6 @@ struct RasterSmem {
 };
 static_assert(sizeof(uint16_t) * (RASTER_THREADS / 32) * REGION_W * REGION_H <= sizeof(uint32_t) * LIST_WINDOW, "pending lists must fit in the key array");
 static_assert((LIST_WINDOW & (LIST_WINDOW - 1)) == 0, "the bitonic sort pads to a power of two");
-
-/* the interpolants of one record (rows 3-9), loaded uniformly per triangle or per lane when shading is deferred */
-struct TriAttr {
-    float4 col0, col1, col2;
-    float u0, v0, u1, v1, u2, v2;
-    float w0, w1, w2;
-    float ez0, ez1, ez2;
-    float lod;
-};
-
-__device__ __forceinline__ void load_attr(TriAttr &A, const TriRecord *rec)
-{
-    const float4 row3 = __ldg(reinterpret_cast<const float4 *>(rec) + 3);
-    const float4 row4 = __ldg(reinterpret_cast<const float4 *>(rec) + 4);
-    A.col0 = __ldg(reinterpret_cast<const float4 *>(rec) + 5);
-    A.col1 = __ldg(reinterpret_cast<const float4 *>(rec) + 6);
-    A.col2 = __ldg(reinterpret_cast<const float4 *>(rec) + 7);
-    const float4 row8 = __ldg(reinterpret_cast<const float4 *>(rec) + 8);
-    const float4 row9 = __ldg(reinterpret_cast<const float4 *>(rec) + 9);
-    A.lod = row3.w;
-    A.w0 = row4.x; A.w1 = row4.y; A.w2 = row4.z; A.ez0 = row4.w;
-    A.u0 = row8.x; A.v0 = row8.y; A.u1 = row8.z; A.v1 = row8.w;
-    A.u2 = row9.x; A.v2 = row9.y; A.ez1 = row9.z; A.ez2 = row9.w;
-}
-
-/* Colour of one fragment: interpolation, per-fragment lighting, texturing, alpha test, texenv, fog
- * (raster.c:581-705).  Returns false when the alpha test discards the fragment. */
-__device__ __forceinline__ bool shade_color(const BatchDev &b, const float *un, uint32_t r, uint32_t state_flags,
-                                            const TriAttr &A, const RasterCfg *cfg, float b0, float b1, float b2, Color4 &c)
-{
-    const uint32_t flags = cfg->flags;
-    if (flags & RC_FLAT) c = { A.col2.x, A.col2.y, A.col2.z, A.col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
-    else {
-        c.r = A.col0.x * b0 + A.col1.x * b1 + A.col2.x * b2;
-        c.g = A.col0.y * b0 + A.col1.y * b1 + A.col2.y * b2;
-        c.b = A.col0.z * b0 + A.col1.z * b1 + A.col2.z * b2;
-        c.a = A.col0.w * b0 + A.col1.w * b1 + A.col2.w * b2;
-    }
-
-    if (flags & RC_LIGHTING) {                              /* raster.c:592-615 */
-        const bool back_facing = (state_flags >> 31) != 0;
-        const bool flip = back_facing && (flags & RC_TWO_SIDE);
-        if ((flags & RC_PHONG) || flip) {
-            const TriEye *eye = b.rec_eye + r;
-            float ep[3], en[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                ep[k] = eye->ep0[k] * b0 + eye->ep1[k] * b1 + eye->ep2[k] * b2;
-                en[k] = eye->en0[k] * b0 + eye->en1[k] * b1 + eye->en2[k] * b2;
-            }
-            const mtgl_state *st = b.states + (state_flags & STATE_INDEX_MASK);
-            MaterialRegs mat;
-            if (flip) {
-                en[0] *= -1.0f; en[1] *= -1.0f; en[2] *= -1.0f;
-                load_material(mat, &st->material_back);
-            } else load_material(mat, &st->material_front);
-            c = compute_lighting(st, ep[0], ep[1], ep[2], en[0], en[1], en[2], mat);
-        }
-    }
-
-    if (flags & RC_TEXTURED) {                              /* raster.c:618-669 */
-        float u, v;
-        if (flags & RC_PERSPECTIVE) {
-            /* u/w, v/w per vertex (raster.c:501-503) */
-            const float u0w = A.u0 * A.w0, v0w = A.v0 * A.w0, u1w = A.u1 * A.w1, v1w = A.v1 * A.w1, u2w = A.u2 * A.w2, v2w = A.v2 * A.w2;
-            float uw = b0 * u0w + b1 * u1w + b2 * u2w;
-            float vw = b0 * v0w + b1 * v1w + b2 * v2w;
-            float ow = b0 * A.w0 + b1 * A.w1 + b2 * A.w2;
-            float w = 1.0f / ow;
-            u = uw * w;
-            v = vw * w;
-        } else {
-            u = b0 * A.u0 + b1 * A.u1 + b2 * A.u2;
-            v = b0 * A.v0 + b1 * A.v1 + b2 * A.v2;
-        }
-        TexTaps T;
-        tex_taps(T, cfg, u, v, A.lod);
-        Color4 t;
-        t.a = tex_channel(T, 24, un);
-        /* alpha test exists only here and tests the TEXEL alpha (raster.c:640-643) */
-        if ((flags & RC_ALPHA_TEST) && !compare_f(cfg->alpha_func, t.a, cfg->alpha_ref)) return false;
-        t.r = tex_channel(T, 0, un); t.g = tex_channel(T, 8, un); t.b = tex_channel(T, 16, un);
-        switch (cfg->tex_env_mode) {
-        case G_REPLACE: c = t; break;
-        case G_DECAL: c = color_lerp_rgb(c, t, t.a); break;
-        case G_BLEND: {
-            const float *e = cfg->tex_env_color;
-            c = { c.r * (1.0f - t.r) + e[0] * t.r, c.g * (1.0f - t.g) + e[1] * t.g, c.b * (1.0f - t.b) + e[2] * t.b, c.a * t.a };
-            break;
-        }
-        case G_ADD: c = { c.r + t.r, c.g + t.g, c.b + t.b, c.a * t.a }; break;
-        default: c = { c.r * t.r, c.g * t.g, c.b * t.b, c.a * t.a }; break;
-        }
-    }
-
-    if (flags & RC_FOG) {                                   /* raster.c:672-705; result alpha = fog colour alpha */
-        float fc = b0 * A.ez0 + b1 * A.ez1 + b2 * A.ez2;
-        Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
-        c = color_lerp_rgb(fogc, c, fog_factor(cfg, fc));
-    }
-    return true;
-}
 
 /* Deferred shading of one 16x16 region: every pixel whose visibility entry is set gets the colour of that
  * (last, in submission order) fragment.  Only fragments of states that neither blend nor alpha-test nor mask
@@ -872,130 +771,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, VIS ? 3 : 2) k_raster(BatchDev
     tile_store<VIS>(sm, fb, planes, px0, py0, vw, vh, b.vis_plane);
 }
 
-/* K4b, the shade pass: one CTA per tile handled by K4a.  The tile's pixels that carry a visibility entry are
- * first compacted into a list (ballot + prefix), then shaded 256 at a time with every lane busy -- same colour
- * code as resolve_region.  The colour part of the batch's leading clear is applied here as well.  Full occupancy,
- * coalesced plane accesses, no ordering constraints left. */
-/* SPLIT = 1: one CTA per tile.  SPLIT = 4: four CTAs per tile, 16 rows each -- for grids of at most about one wave
- * (small_grid(): the band of a multi-GPU frame), where the finer granularity spreads the uneven tiles over the SMs. */
-template <int SPLIT>
-__global__ void __launch_bounds__(256, 3) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
-{
-    constexpr int ROWS = TILE_H / SPLIT;        /* rows of the tile this CTA owns */
-    constexpr int PX = 16 / SPLIT;              /* consecutive pixels per thread in pass 1 */
-    constexpr int TPR = TILE_W / PX;            /* threads per row */
-    __shared__ float un[256];
-    __shared__ uint16_t list[TILE_W * ROWS];
-    __shared__ uint32_t rlist[TILE_W * ROWS];               /* record index of the compacted pixel: pass 2 does not re-read the plane */
-    __shared__ uint32_t warp_total[8];
-    if (!lists_fit(b)) return;
-    un[threadIdx.x] = b.unorm8[threadIdx.x];
-
-    const uint32_t slot = blockIdx.x / SPLIT, sub = blockIdx.x % SPLIT;
-    const uint32_t tile = b.tile_order ? b.tile_order[slot] : slot;
-    const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
-    const int row0 = (ty << TILE_LOG) + (int)sub * ROWS;
-    const int px0 = tx << TILE_LOG, py0 = max(row0, fb.band_y0);
-    const int vw = min(TILE_W, fb.width - px0), vh = min(row0 + ROWS, fb.band_y1) - py0;
-    if (vw <= 0 || vh <= 0) return;
-    const uint32_t L = b.tile_count ? b.tile_count[tile] : 0u;
-    if (L && (b.tile_flags[tile] & 1u)) return;             /* the general kernel owns this tile */
-    const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
-    if (L == 0 && !clr_here) return;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    /* pass 1: colour clear + compaction of the pixels to shade.  A thread owns PX consecutive pixels of one row, so
-     * its visibility loads are 16-byte loads issued back to back and thread order is row-major pixel order: the
-     * compacted list keeps neighbouring pixels next to each other for pass 2. */
-    const int y = (int)threadIdx.x / TPR, xq = ((int)threadIdx.x % TPR) * PX;
-    uint32_t has_mask = 0;
-    uint32_t v[PX];
-    if (y < vh) {
-        const size_t p0 = (size_t)(py0 + y) * fb.width + px0 + xq;
-        if (!L) {
-#pragma unroll
-            for (int k = 0; k < PX; k++) v[k] = VIS_NONE;
-        } else if (vw == TILE_W && (fb.width & 3) == 0) {
-#pragma unroll
-            for (int q = 0; q < PX / 4; q++) {
-                const uint4 t = *reinterpret_cast<const uint4 *>(b.vis_plane + p0 + q * 4);
-                v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < PX; k++) v[k] = (xq + k < vw) ? b.vis_plane[p0 + k] : VIS_NONE;
-        }
-        const bool clr_row = (clr.mask & G_COLOR_BUFFER_BIT) && py0 + y >= clr.y0 && py0 + y < clr.y1;
-#pragma unroll
-        for (int k = 0; k < PX; k++) {
-            if (v[k] != VIS_NONE) has_mask |= 1u << k;
-            else if (clr_row && xq + k < vw && px0 + xq + k >= clr.x0 && px0 + xq + k < clr.x1) fb.color[p0 + k] = clr.color;
-        }
-    }
-    const uint32_t mine = (uint32_t)__popc(has_mask);
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (uint32_t)o) incl += up;
-    }
-    if (lane == 31) warp_total[warp] = incl;
-    __syncthreads();
-    uint32_t at = incl - mine, n = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < 8; w++) {
-        const uint32_t wt = warp_total[w];
-        if (w < warp) at += wt;
-        n += wt;
-    }
-#pragma unroll
-    for (int k = 0; k < PX; k++)
-        if (has_mask & (1u << k)) { list[at] = (uint16_t)(y * TILE_W + xq + k); rlist[at] = v[k]; at++; }
-    __syncthreads();
-
-    /* pass 2: shade the compacted pixels */
-    for (uint32_t i = threadIdx.x; i < n; i += 256) {
-        const int lx = list[i] % TILE_W, ly = list[i] / TILE_W;
-        const int x = px0 + lx, y = py0 + ly;
-        const size_t p = (size_t)y * fb.width + x;
-        const uint32_t r = rlist[i];
-        const TriRecord *rec = b.records + r;
-        const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
-        const int4 row1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
-        const uint32_t state_flags = __ldg(&rec->state_flags);
-        const float fx0 = (float)row0.x, fy0 = (float)row0.y, fx1 = (float)row0.z, fy1 = (float)row0.w;
-        const float fx2 = (float)row1.x, fy2 = (float)row1.y;
-        const float inv_area = __int_as_float(row1.w);
-        const float px = (float)x, py = (float)y;
-        const float b0 = edge_at(fx1, fy1, fx2, fy2, px, py) * inv_area;
-        const float b1 = edge_at(fx2, fy2, fx0, fy0, px, py) * inv_area;
-        const float b2 = edge_at(fx0, fy0, fx1, fy1, px, py) * inv_area;
-        const RasterCfg *cfg = b.cfgs + (state_flags & STATE_INDEX_MASK);
-        TriAttr A;
-        load_attr(A, rec);
-        Color4 c;
-        shade_color(b, un, r, state_flags, A, cfg, b0, b1, b2, c);
-        fb.color[p] = color_pack(c);       /* raster.c:719-721: color_pack clamps */
-    }
-
-    /* Fused gather: the finished tile also goes to the presenting GPU's plane over NVLink, as whole rows in 16-byte
-     * stores (per-pixel peer stores cost twice the kernel); other CTAs keep the SMs busy meanwhile. */
-    if (fb.present) {
-        __threadfence();
-        __syncthreads();
-        if (vw == TILE_W && (fb.width & 3) == 0) {
-            for (int i = threadIdx.x; i < vh * 16; i += 256) {
-                const size_t p = (size_t)(py0 + (i >> 4)) * fb.width + px0 + (i & 15) * 4;
-                *reinterpret_cast<uint4 *>(fb.present + p) = __ldcg(reinterpret_cast<const uint4 *>(fb.color + p));
-            }
-        } else {
-            for (int i = threadIdx.x; i < vh * TILE_W; i += 256) {
-                const size_t p = (size_t)(py0 + (i >> 6)) * fb.width + px0 + (i & 63);
-                if ((i & 63) < vw) fb.present[p] = __ldcg(fb.color + p);
-            }
-        }
-    }
-}
-
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes,
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade)
 {
@@ -1024,11 +799,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
             note_launch();
         }
         cudaEventRecord(ev_vis, s);
-        if (planes & 1u) {
-            if (small_grid(tiles)) k_shade<4><<<tiles * 4u, 256, 0, s>>>(b, fb, clear);
-            else k_shade<1><<<tiles, 256, 0, s>>>(b, fb, clear);
-            note_launch();
-        }
+        if (planes & 1u) launch_shade(b, fb, clear, plan.stage_cfg, s);
         cudaEventRecord(ev_shade, s);
         if (any_in_order) {
             k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u, plan.fill_mode);

@@ -810,6 +810,12 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         if (const char *e = std::getenv("MTGL_FILL")) fill_env = !std::strcmp(e, "never") ? FILL_OFF : (!std::strcmp(e, "always") ? FILL_ALWAYS : FILL_AUTO);
         plan.fill_mode = (need_eye || !had_triangles) ? FILL_OFF : fill_env;
         plan.in_order_all = flags_all; plan.in_order_any = flags_any;
+        plan.stage_cfg = 0xFFFFFFFFu;
+        for (const PassDraw &q : passes[pidx]) {
+            const uint32_t ci = bt->draws[q.draw].raster_state;
+            const uint32_t need = RC_TEXTURED | RC_DEFER;
+            if ((cfgs[ci].flags & need) == need) { plan.stage_cfg = ci; break; }
+        }
         launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
         CU(cudaEventRecord(sev[5], d->stream));
         t_launched = std::chrono::steady_clock::now();
