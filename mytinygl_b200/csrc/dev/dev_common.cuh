@@ -100,6 +100,9 @@ struct RasterCfg {
     uint32_t tex_min, tex_mag, tex_wrap_s, tex_wrap_t;
     int32_t tex_w, tex_h, tex_w1, tex_h1;
     const uint32_t *tex_l0, *tex_l1;
+    const float4 *tex_f4;           /* the same texels as n / 255 floats, level 0 then level 1 (small textures only, else NULL): dev_fasttex.cuh */
+    uint32_t fast_tex;              /* 1: the float4 copy exists and every REPEAT axis has a power-of-two size */
+    uint32_t pad_;
     float alpha_ref;
     float fog_density, fog_start, fog_end;
     float fog_color[4];
@@ -117,14 +120,24 @@ enum : uint32_t {
                                      * function: the surviving fragment of a pixel does not depend on submission order (k_vis.cu) */
 };
 
-/* TriRecord.state_flags: state block index | unordered << 27 | record kind << 28 | deferrable << 30 | back-facing << 31 */
-constexpr uint32_t STATE_INDEX_MASK = 0x07FFFFFFu;
+/* TriRecord.state_flags: state block index | bounded << 26 | unordered << 27 | record kind << 28 | deferrable << 30 | back-facing << 31 */
+constexpr uint32_t STATE_INDEX_MASK = 0x03FFFFFFu;
+constexpr uint32_t STATE_BOUNDED_BIT = 1u << 26;        /* filled triangle whose texture coordinates and 1/w are finite and bounded (attr_bounded) */
 constexpr uint32_t STATE_UNORD_BIT = 1u << 27;
 constexpr uint32_t STATE_KIND_SHIFT = 28;
 constexpr uint32_t STATE_KIND_MASK = 3u << STATE_KIND_SHIFT;
 constexpr uint32_t KIND_TRIANGLE = 0u, KIND_LINE = 1u, KIND_POINT = 2u;
 constexpr uint32_t STATE_DEFER_BIT = 1u << 30;
 constexpr uint32_t STATE_BACK_BIT = 1u << 31;
+
+/* |u|, |v| <= 2^20 and 2^-40 <= 1/w <= 2^40 at all three vertices: no NaN or infinity can then arise in the interpolated
+ * texture coordinates, which is what the staged / float4 texture path (dev_fasttex.cuh) relies on */
+__device__ __forceinline__ bool attr_bounded(float u0, float v0, float w0, float u1, float v1, float w1, float u2, float v2, float w2)
+{
+    const float lim = 1048576.0f, wlo = 9.094947e-13f, whi = 1.0995116e12f;
+    return fabsf(u0) <= lim && fabsf(v0) <= lim && fabsf(u1) <= lim && fabsf(v1) <= lim && fabsf(u2) <= lim && fabsf(v2) <= lim &&
+           w0 >= wlo && w0 <= whi && w1 >= wlo && w1 <= whi && w2 >= wlo && w2 <= whi;
+}
 
 /* what a record contributes to the flags of every tile it is binned into */
 __device__ __forceinline__ uint32_t tile_flag_bits(uint32_t state_flags)
@@ -456,14 +469,13 @@ struct RasterPlan {
     bool unordered_range01;     /* every unordered state has depth range [0,1] */
     uint32_t fill_mode;         /* FILL_* (dev_fill.cuh): may the pixel-owner kernel (k_fill.cu) take in-order tiles of large triangles */
     uint32_t in_order_all, in_order_any;    /* AND / OR of the RasterCfg flags of the pass's in-order states */
-    uint32_t stage_cfg;         /* state whose texture the shade pass stages in shared memory (first textured deferrable state), ~0 = none */
 };
 /* ev_vis / ev_shade are recorded after the visibility kernels and after the shade kernel (stage timing) */
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
                  cudaStream_t s);
-void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t stage_cfg, cudaStream_t s);
+void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, cudaStream_t s);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
 void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);
@@ -471,6 +483,7 @@ void launch_read_pixels(const FrameTargets &fb, int32_t x, int32_t y, int32_t w,
 void launch_frame_barrier(unsigned long long *counter, unsigned long long target, cudaStream_t s);
 void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
+void launch_tex_f4(const uint32_t *l0, int n0, const uint32_t *l1, int n1, float4 *out, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);
 uint64_t kernel_launch_count();
 /* A tile grid well below one wave of 8-warp CTAs (148 SMs x 4 = 592): the band of a multi-GPU frame (measured: the

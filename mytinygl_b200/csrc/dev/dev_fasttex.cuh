@@ -1,16 +1,19 @@
 /*
- * dev_fasttex.cuh -- texture_sample_lod (src/textures.c:457-557) from a texture STAGED IN SHARED MEMORY, shared by the
- * tile kernels that shade many fragments against one small texture (k_fill.cu, k_shade.cu).
+ * dev_fasttex.cuh -- texture_sample_lod (src/textures.c:457-557) from FLOAT4 TEXELS, shared by the tile kernels that shade
+ * many fragments (k_fill.cu, k_shade.cu).
  *
- * The tile's CTA converts the texture once into float4 texels n / 255 (level 0, then level 1): a bilinear tap is then one
- * 16-byte LDS with no per-channel conversion, where the general sampler (dev_texture.cuh) does a global load plus four
- * shift / mask / table look-ups per tap.  The filter decision, which depends only on the state and the PER-TRIANGLE lod
- * (raster.c:505-529), is made once per triangle (sampler_plan) instead of once per fragment; the 8-bit truncation
- * after every filter stage uses the arithmetic forms of dev_fragment.cuh.  Values are the reference's, bit for bit.
+ * Small textures keep, next to their RGBA8 words, a float4 copy in HBM in which every texel already is what
+ * color_from_rgba32 returns (n / 255, built once at glTexImage2D time: k_tex_f4).  A bilinear tap is then one 16-byte load
+ * with no per-channel conversion, where the general sampler (dev_texture.cuh) does a 4-byte load plus four shift / mask /
+ * table look-ups per tap.  k_shade reads the copy through L1 (GLOBAL = true); k_fill stages it in shared memory with one
+ * bulk-asynchronous copy (cp.async.bulk + mbarrier, below) because it samples it tens of thousands of times per tile.
+ * The filter decision, which depends only on the state and the PER-TRIANGLE lod (raster.c:505-529), is made once per
+ * triangle (sampler_plan); the 8-bit truncation after every filter stage uses the arithmetic forms of dev_fragment.cuh.
+ * Values are the reference's, bit for bit.
  *
- * Preconditions of the fast path (checked once per triangle by fast_texture_ok, everything else takes the general
- * sampler): the triangle's texture is the staged one; REPEAT only with power-of-two sizes (a mask); u, v, 1/w finite and
- * bounded, so that no NaN can reach the wrap or the floor.
+ * Preconditions of the fast path (everything else takes the general sampler): the state's texture has a float4 copy and
+ * every REPEAT axis a power-of-two size (RasterCfg::fast_tex); u, v, 1/w of the triangle are finite and bounded
+ * (STATE_BOUNDED_BIT, attr_bounded), so that no NaN can reach the wrap or the floor.
  */
 #ifndef MTGL_DEV_FASTTEX_CUH
 #define MTGL_DEV_FASTTEX_CUH
@@ -30,9 +33,15 @@ constexpr uint32_t TP_B_SHIFT = 4;              /* second level: kind in bits 4-
 constexpr uint32_t TP_B_LINEAR = 1u << 6;
 constexpr uint32_t TP_REP_S = 1u << 7, TP_REP_T = 1u << 8;
 
-struct StagedTex {              /* in shared memory, next to the texels */
-    const uint32_t *id;         /* level-0 pointer of the staged texture = its identity; NULL: nothing staged */
-    int w, h, w1, h1, n0;       /* level 1 starts at texel n0 */
+/* where the float4 texels are: the float4 copy in HBM (RasterCfg::tex_f4, read through L1) or its image in shared memory */
+struct TexView {
+    const float4 *tex;          /* level 0, level 1 right behind it */
+    int w, h, w1, h1, n0;       /* level 1 starts at texel n0 = w * h */
+};
+
+struct StagedTex {              /* in shared memory, next to the staged texels */
+    const float4 *id;           /* the float4 copy that was staged = its identity; NULL: nothing staged */
+    int w, h, w1, h1, n0;
 };
 
 __device__ __forceinline__ uint32_t sampler_plan(const RasterCfg *c, float lod, float &cl)
@@ -56,31 +65,56 @@ __device__ __forceinline__ uint32_t sampler_plan(const RasterCfg *c, float lod, 
     return plan | 0u | (filter == G_LINEAR ? TP_A_LINEAR : 0u);
 }
 
-__device__ __forceinline__ bool bounded_abs(float v, float lim) { return fabsf(v) <= lim; }   /* false for NaN */
-
-/* may a triangle with these per-vertex texture coordinates and 1/w values take the fast path? */
-__device__ __forceinline__ bool fast_texture_ok(const StagedTex &st, const RasterCfg *cfg, const float (&u)[3], const float (&v)[3], const float (&w)[3])
+template <bool GLOBAL>
+__device__ __forceinline__ float4 texel_at(const float4 *px, int i)
 {
-    if (!(cfg->flags & RC_TEXTURED) || st.id == nullptr || cfg->tex_l0 != st.id) return false;
-    if (cfg->tex_wrap_s == G_REPEAT && (st.w & (st.w - 1))) return false;
-    if (cfg->tex_wrap_t == G_REPEAT && (st.h & (st.h - 1))) return false;
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-        ok = ok && bounded_abs(u[k], 1048576.0f) && bounded_abs(v[k], 1048576.0f) && w[k] >= 9.094947e-13f && w[k] <= 1.0995116e12f;   /* 2^-40 .. 2^40 */
-    return ok;
+    if (GLOBAL) return __ldg(px + i);
+    return px[i];
 }
 
-/* all threads of the CTA: texture of state `tc` -> float4 texels (the caller synchronises before use) */
-__device__ __forceinline__ void stage_texture(float4 *tex, StagedTex &st, const RasterCfg *tc, const float *un, int nthreads)
+/* ---- bulk-asynchronous copy global -> shared (sm_90+: cp.async.bulk, SASS UBLKCP) completing on an mbarrier ---- */
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      /* visible to the asynchronous proxy */
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+/* dst, src 16-byte aligned, bytes a multiple of 16 */
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+/* every consumer thread: wait for phase `parity` of the barrier; a copy that never lands traps instead of hanging the GPU */
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t done;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
+
+/* one thread: queue the float4 copy of state `tc`'s texture into `tex` (at most STAGED_TEXELS texels) */
+__device__ __forceinline__ void stage_texture_async(float4 *tex, StagedTex &st, const RasterCfg *tc, unsigned long long *bar)
 {
     const int n0 = tc->tex_w * tc->tex_h, n1 = tc->tex_l1 ? tc->tex_w1 * tc->tex_h1 : 0;
-    if (!tc->tex_l0 || n0 + n1 > STAGED_TEXELS) return;
-    for (int i = threadIdx.x; i < n0 + n1; i += nthreads) {
-        const uint32_t t = (i < n0) ? __ldg(tc->tex_l0 + i) : __ldg(tc->tex_l1 + (i - n0));
-        tex[i] = make_float4(un[t & 0xFFu], un[(t >> 8) & 0xFFu], un[(t >> 16) & 0xFFu], un[t >> 24]);
-    }
-    if (threadIdx.x == 0) { st.id = tc->tex_l0; st.w = tc->tex_w; st.h = tc->tex_h; st.w1 = tc->tex_w1; st.h1 = tc->tex_h1; st.n0 = n0; }
+    if (!tc->tex_f4 || n0 + n1 > STAGED_TEXELS) return;
+    const uint32_t bytes = (uint32_t)(n0 + n1) * (uint32_t)sizeof(float4);
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 16384u)
+        bulk_copy_g2s(reinterpret_cast<unsigned char *>(tex) + off, reinterpret_cast<const unsigned char *>(tc->tex_f4) + off, min(16384u, bytes - off), bar);
+    st.id = tc->tex_f4; st.w = tc->tex_w; st.h = tc->tex_h; st.w1 = tc->tex_w1; st.h1 = tc->tex_h1; st.n0 = n0;
 }
 
 /* wrap of texture_sample_lod (textures.c:463-486) for finite coordinates */
@@ -95,6 +129,7 @@ struct FTaps { float4 t00, t10, t01, t11; float fx, fy; };
 /* bilinear taps of one level (texture_sample_base / _mip1, textures.c:379-451).  floor(t) for |t| < 2^22 by a
  * round-down add of 1.5 * 2^23: the sum is 2^23 + 2^22 + floor(t) exactly, its low mantissa bits are the integer.
  * Texel coordinates: REPEAT with a power-of-two size is a mask, CLAMP a min / max -- one branch-free form for both. */
+template <bool GLOBAL>
 __device__ __forceinline__ void fast_taps(FTaps &T, const float4 *px, int w, int h, bool rep_s, bool rep_t, float u, float v)
 {
     const float tx = u * (float)w - 0.5f, ty = v * (float)h - 0.5f;
@@ -106,7 +141,8 @@ __device__ __forceinline__ void fast_taps(FTaps &T, const float4 *px, int w, int
     const int ax = rep_s ? wm : -1, ay = rep_t ? hm : -1;
     const int xa = min(max(x0 & ax, 0), wm), xb = min(max((x0 + 1) & ax, 0), wm);
     const int ya = min(max(y0 & ay, 0), hm) * w, yb = min(max((y0 + 1) & ay, 0), hm) * w;
-    T.t00 = px[ya + xa]; T.t10 = px[ya + xb]; T.t01 = px[yb + xa]; T.t11 = px[yb + xb];
+    T.t00 = texel_at<GLOBAL>(px, ya + xa); T.t10 = texel_at<GLOBAL>(px, ya + xb);
+    T.t01 = texel_at<GLOBAL>(px, yb + xa); T.t11 = texel_at<GLOBAL>(px, yb + xb);
 }
 
 /* bilinear_filter (textures.c:294-307) of one channel, truncated to 8 bits, as the float n / 255 */
@@ -118,19 +154,20 @@ __device__ __forceinline__ float fast_channel(float c00, float c10, float c01, f
 }
 
 /* all four channels of one mip level as n / 255 floats; u, v already wrapped */
-__device__ __forceinline__ float4 fast_level(const float4 *tex, const StagedTex &st, uint32_t kind, bool linear, bool rep_s, bool rep_t, float u, float v)
+template <bool GLOBAL>
+__device__ __forceinline__ float4 fast_level(const TexView &tv, uint32_t kind, bool linear, bool rep_s, bool rep_t, float u, float v)
 {
     if (kind == 2u) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     if (kind == 3u) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    const float4 *px = kind ? tex + st.n0 : tex;
-    const int w = kind ? st.w1 : st.w, h = kind ? st.h1 : st.h;
+    const float4 *px = kind ? tv.tex + tv.n0 : tv.tex;
+    const int w = kind ? tv.w1 : tv.w, h = kind ? tv.h1 : tv.h;
     if (!linear) {          /* nearest: floor(u w), clamped, never wrapped (textures.c:394-403) */
         int x = f2i_x86(floorf(u * (float)w - 0.5f + 0.5f)), y = f2i_x86(floorf(v * (float)h - 0.5f + 0.5f));
         x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
-        return px[y * w + x];
+        return texel_at<GLOBAL>(px, y * w + x);
     }
     FTaps T;
-    fast_taps(T, px, w, h, rep_s, rep_t, u, v);
+    fast_taps<GLOBAL>(T, px, w, h, rep_s, rep_t, u, v);
     const float sx = 1.0f - T.fx, sy = 1.0f - T.fy;
     return make_float4(fast_channel(T.t00.x, T.t10.x, T.t01.x, T.t11.x, T.fx, T.fy, sx, sy),
                        fast_channel(T.t00.y, T.t10.y, T.t01.y, T.t11.y, T.fx, T.fy, sx, sy),
@@ -139,13 +176,14 @@ __device__ __forceinline__ float4 fast_level(const float4 *tex, const StagedTex 
 }
 
 /* texture_sample_lod for one fragment with the triangle's plan: the texel as four n / 255 floats.  u, v unwrapped. */
-__device__ __forceinline__ float4 fast_sample(const float4 *tex, const StagedTex &st, uint32_t plan, float cl, float u, float v)
+template <bool GLOBAL>
+__device__ __forceinline__ float4 fast_sample(const TexView &tv, uint32_t plan, float cl, float u, float v)
 {
     const bool rep_s = (plan & TP_REP_S) != 0u, rep_t = (plan & TP_REP_T) != 0u;
     u = fast_wrap(u, rep_s); v = fast_wrap(v, rep_t);
-    float4 t = fast_level(tex, st, plan & TP_A_KIND, (plan & TP_A_LINEAR) != 0u, rep_s, rep_t, u, v);
+    float4 t = fast_level<GLOBAL>(tv, plan & TP_A_KIND, (plan & TP_A_LINEAR) != 0u, rep_s, rep_t, u, v);
     if (plan & TP_TRI) {        /* textures.c:512-515: per channel, truncated to 8 bits once more */
-        const float4 t1 = fast_level(tex, st, (plan >> TP_B_SHIFT) & 3u, (plan & TP_B_LINEAR) != 0u, rep_s, rep_t, u, v);
+        const float4 t1 = fast_level<GLOBAL>(tv, (plan >> TP_B_SHIFT) & 3u, (plan & TP_B_LINEAR) != 0u, rep_s, rep_t, u, v);
         const float s = 1.0f - cl;
         t.x = unorm_of(byte_of(t.x * s + t1.x * cl)); t.y = unorm_of(byte_of(t.y * s + t1.y * cl));
         t.z = unorm_of(byte_of(t.z * s + t1.z * cl)); t.w = unorm_of(byte_of(t.w * s + t1.w * cl));

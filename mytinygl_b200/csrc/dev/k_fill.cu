@@ -88,6 +88,7 @@ struct FillSmem {
     uint32_t acc;               /* scratch of fill_owns_tile */
     uint32_t tex_cfg;           /* state index whose texture is staged (lowest textured state of the list), ~0 = none */
     StagedTex st;
+    __align__(8) unsigned long long tex_bar;    /* mbarrier the bulk copy of the texture completes on */
 };
 /* two CTAs per SM */
 static_assert(2 * (sizeof(FillSmem) + 1024) <= 227 * 1024, "k_fill: two tiles per SM");
@@ -181,7 +182,7 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
     /* u/w, v/w per vertex (raster.c:501-503) */
     float u[3] = { row8.x, row8.z, row9.x }, v[3] = { row8.y, row8.w, row9.y };
     const float w[3] = { row4.x, row4.y, row4.z };
-    if (fast_texture_ok(sm.st, cfg, u, v, w)) word |= PT_FASTTEX;
+    if ((cflags & RC_TEXTURED) && cfg->fast_tex && sm.st.id != nullptr && cfg->tex_f4 == sm.st.id && (row2.z & STATE_BOUNDED_BIT)) word |= PT_FASTTEX;
     if (cflags & RC_PERSPECTIVE) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { u[k] = u[k] * w[k]; v[k] = v[k] * w[k]; }
@@ -301,12 +302,12 @@ __device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &s
              * (raster.c:640-643: on the texel's alpha) discards both fragments never filters the colour channels */
             const bool rep_s = (plan & TP_REP_S) != 0u, rep_t = (plan & TP_REP_T) != 0u;
             const float4 *px = kind_a ? sm.tex + sm.st.n0 : sm.tex;
-            const int w = kind_a ? sm.st.w1 : sm.st.w, h = kind_a ? sm.st.h1 : sm.st.h;
+            const int w = kind_a ? sm.st.w1 : sm.st.w, h = kind_a ? sm.st.h1 : sm.st.h;      /* (the staged copy: shared-memory loads) */
             FTaps F[P];
             float sx[P], sy[P];
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                fast_taps(F[p], px, w, h, rep_s, rep_t, fast_wrap(u[p], rep_s), fast_wrap(v[p], rep_t));
+                fast_taps<false>(F[p], px, w, h, rep_s, rep_t, fast_wrap(u[p], rep_s), fast_wrap(v[p], rep_t));
                 sx[p] = 1.0f - F[p].fx; sy[p] = 1.0f - F[p].fy;
                 H.ta[p] = fast_channel(F[p].t00.w, F[p].t10.w, F[p].t01.w, F[p].t11.w, F[p].fx, F[p].fy, sx[p], sy[p]);
             }
@@ -330,9 +331,10 @@ __device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &s
             }
         } else {
             const float cl = T.p1.w;
+            const TexView tv = { sm.tex, sm.st.w, sm.st.h, sm.st.w1, sm.st.h1, sm.st.n0 };
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                const float4 t = fast_sample(sm.tex, sm.st, plan, cl, u[p], v[p]);
+                const float4 t = fast_sample<false>(tv, plan, cl, u[p], v[p]);
                 H.tr[p] = t.x; H.tg[p] = t.y; H.tb[p] = t.z; H.ta[p] = t.w;
             }
         }
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
 
     /* ---- list -> shared memory, sorted by submission id; the texture to stage ---- */
     sm.un[threadIdx.x] = b.unorm8[threadIdx.x];
-    if (threadIdx.x == 0) { sm.tex_cfg = 0xFFFFFFFFu; sm.st.id = nullptr; }
+    if (threadIdx.x == 0) { sm.tex_cfg = 0xFFFFFFFFu; sm.st.id = nullptr; mbar_init(&sm.tex_bar, 1u); }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < L; i += FILL_THREADS) {
         const uint32_t r = list[i];
@@ -535,13 +537,14 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
         if (b.cfgs[ci].flags & RC_TEXTURED) atomicMin(&sm.tex_cfg, ci);
     }
     __syncthreads();
+    /* the texture goes to shared memory as one bulk-asynchronous copy of its float4 image while the list is being sorted */
+    if (threadIdx.x == 0 && sm.tex_cfg != 0xFFFFFFFFu) stage_texture_async(sm.tex, sm.st, b.cfgs + sm.tex_cfg, &sm.tex_bar);
     for (uint32_t i = threadIdx.x; i < L; i += FILL_THREADS) {      /* ids are unique: the rank is the sorted position */
         const uint32_t mine = sm.key[i];
         uint32_t rank = 0;
         for (uint32_t j = 0; j < L; j++) rank += (sm.key[j] < mine) ? 1u : 0u;
         sm.sorted[rank] = sm.rec[i];
     }
-    if (sm.tex_cfg != 0xFFFFFFFFu) stage_texture(sm.tex, sm.st, b.cfgs + sm.tex_cfg, sm.un, FILL_THREADS);
 
     /* ---- clear rectangle relative to the tile (gl_api.c:409-457) ---- */
     const int cx0 = max(clr.x0 - px0, 0), cy0 = max(clr.y0 - py0, 0);
@@ -555,7 +558,8 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
 
     for (uint32_t w0 = 0; w0 < L; w0 += FILL_WINDOW) {
         const uint32_t n = min((uint32_t)FILL_WINDOW, L - w0);
-        __syncthreads();                /* sorted list + staged texture complete; the previous window is no longer read */
+        __syncthreads();                /* sorted list complete, texture queued; the previous window is no longer read */
+        if (w0 == 0u && sm.st.id != nullptr) mbar_wait(&sm.tex_bar, 0u);        /* the staged texels have landed */
         if (threadIdx.x < n)        /* (a run of coincident triangles does not continue across windows) */
             prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu, px0, py0);
         __syncthreads();

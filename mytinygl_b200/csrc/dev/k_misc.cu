@@ -34,6 +34,23 @@ __global__ void __launch_bounds__(256) k_mip1(const uint32_t *l0, int w, int h, 
     l1[i] = color_pack(s);
 }
 
+/* float4 copy of a small texture (level 0, then level 1): every texel as color_from_rgba32 (src/graphics.h:350-357) returns
+ * it, so that a tap of the tile kernels' samplers (dev_fasttex.cuh) is one 16-byte load with no conversion */
+__global__ void __launch_bounds__(256) k_tex_f4(const uint32_t *l0, int n0, const uint32_t *l1, int n1, float4 *out, const float *unorm8)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + n1) return;
+    const Color4 c = color_unpack(i < n0 ? l0[i] : l1[i - n0], unorm8);
+    out[i] = make_float4(c.r, c.g, c.b, c.a);
+}
+
+void launch_tex_f4(const uint32_t *l0, int n0, const uint32_t *l1, int n1, float4 *out, const float *unorm8, cudaStream_t s)
+{
+    if (n0 + n1 <= 0) return;
+    k_tex_f4<<<(n0 + n1 + 255) / 256, 256, 0, s>>>(l0, n0, l1, n1, out, unorm8);
+    note_launch();
+}
+
 /* Small batch arenas (state blocks, draw records: a few KB) are pulled over PCIe by a kernel reading the pinned,
  * device-mapped staging buffer instead of a DMA: a host-to-device memcpy between two frames' kernels costs a
  * compute -> copy-engine -> compute round trip, several times the transfer itself. */

@@ -799,7 +799,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
             note_launch();
         }
         cudaEventRecord(ev_vis, s);
-        if (planes & 1u) launch_shade(b, fb, clear, plan.stage_cfg, s);
+        if (planes & 1u) launch_shade(b, fb, clear, s);
         cudaEventRecord(ev_shade, s);
         if (any_in_order) {
             k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u, plan.fill_mode);

@@ -381,7 +381,8 @@ __device__ __forceinline__ uint4 write_fill(TriRecord *dst, TriEye *eye_dst, uin
     rec.x0 = s.x0; rec.y0 = s.y0; rec.x1 = s.x1; rec.y1 = s.y1; rec.x2 = s.x2; rec.y2 = s.y2;
     const uint32_t cflags = cfg->flags;
     rec.state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
-                      ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
+                      ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u) |
+                      (attr_bounded(a.u, a.v, a.w, b.u, b.v, b.w, c.u, c.v, c.w) ? STATE_BOUNDED_BIT : 0u);
     rec.id = id;
     rec.bbox_min = s.bbox_min;
     rec.bbox_max = s.bbox_max;
@@ -585,11 +586,11 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
 {
     float4 *out = reinterpret_cast<float4 *>(dst);
     const uint32_t cflags = cfg->flags;
-    const uint32_t state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
-                                 ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
+    uint32_t state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
+                           ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
     reinterpret_cast<int4 *>(dst)[0] = make_int4(s.x0, s.y0, s.x1, s.y1);
     reinterpret_cast<int4 *>(dst)[1] = make_int4(s.x2, s.y2, __float_as_int(s.area), __float_as_int(1.0f / s.area));
-    reinterpret_cast<uint4 *>(dst)[2] = make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
+    float bu[3], bv[3];
     {   /* rows 5-7: colours are copied */
         const float4 c0 = __ldg(src.color + i0), c1 = __ldg(src.color + i1), c2 = __ldg(src.color + i2);
         out[5] = c0; out[6] = c1; out[7] = c2;
@@ -614,6 +615,7 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
         out[8] = make_float4(t0.x, t0.y, t1.x, t1.y);
         out[9] = make_float4(t2.x, t2.y, t1.z, t2.z);
         ez0 = t0.z;
+        bu[0] = t0.x; bu[1] = t1.x; bu[2] = t2.x; bv[0] = t0.y; bv[1] = t1.y; bv[2] = t2.y;
     }
     {   /* rows 3-4: z / w after the divide (raster.c:729-746) */
         const float4 p0 = __ldg(src.clip + i0), p1 = __ldg(src.clip + i1), p2 = __ldg(src.clip + i2);
@@ -623,7 +625,9 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
         if (fabsf(p2.w) < 1e-6f) { z2 = 0.0f; w2 = 1.0f; } else { w2 = 1.0f / p2.w; z2 = p2.z * w2; }
         out[3] = make_float4(z0, z1, z2, lod);
         out[4] = make_float4(w0, w1, w2, ez0);
+        if (attr_bounded(bu[0], bv[0], w0, bu[1], bv[1], w1, bu[2], bv[2], w2)) state_flags |= STATE_BOUNDED_BIT;
     }
+    reinterpret_cast<uint4 *>(dst)[2] = make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
     if (eye_dst) {
         float4 *eo = reinterpret_cast<float4 *>(eye_dst);
         float4 e0 = __ldg(src.epos + i0), e1 = __ldg(src.epos + i1), e2 = __ldg(src.epos + i2);
@@ -645,11 +649,10 @@ __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, u
 {
     float4 *out = reinterpret_cast<float4 *>(dst);
     const uint32_t cflags = cfg->flags;
-    const uint32_t state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
-                                 ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
+    uint32_t state_flags = state_index | (s.back ? STATE_BACK_BIT : 0u) | ((cflags & RC_DEFER) ? STATE_DEFER_BIT : 0u) |
+                           ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
     reinterpret_cast<int4 *>(dst)[0] = make_int4(s.x0, s.y0, s.x1, s.y1);
     reinterpret_cast<int4 *>(dst)[1] = make_int4(s.x2, s.y2, __float_as_int(s.area), __float_as_int(1.0f / s.area));
-    reinterpret_cast<uint4 *>(dst)[2] = make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
     float z[3], w[3], nez[3], tu[3], tv[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -675,6 +678,8 @@ __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, u
             }
         }
     }
+    if (attr_bounded(tu[0], tv[0], w[0], tu[1], tv[1], w[1], tu[2], tv[2], w[2])) state_flags |= STATE_BOUNDED_BIT;
+    reinterpret_cast<uint4 *>(dst)[2] = make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
     out[3] = make_float4(z[0], z[1], z[2], lod);
     out[4] = make_float4(w[0], w[1], w[2], nez[0]);
     out[8] = make_float4(tu[0], tv[0], tu[1], tv[1]);

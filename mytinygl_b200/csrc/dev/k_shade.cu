@@ -10,14 +10,14 @@
  *   pass 1  the tile's visibility entries -> a colour tile in shared memory: the record index for visible pixels, the
  *           clear colour / the plane's colour for the others; visible pixels are compacted into a row-major list (one
  *           block scan), so that pass 2 runs with every lane busy and neighbouring lanes on neighbouring pixels;
- *   stage   the texture of the batch's deferrable textured state goes to shared memory as float4 texels n / 255
- *           (dev_fasttex.cuh): a bilinear tap is one 16-byte LDS, the trilinear sample of a C4 fragment 8 of them,
- *           instead of 8 global loads and 32 table look-ups;
+ *   texels  small textures have a float4 copy in HBM (n / 255 per channel, built at glTexImage2D time; dev_fasttex.cuh):
+ *           a bilinear tap is one 16-byte load through L1, the trilinear sample of a C4 fragment 8 of them, instead of 8
+ *           4-byte loads and 32 shift / mask / table look-ups;
  *   pass 2  TWO pixels per thread and iteration (independent instruction streams): record -> barycentrics with the
  *           reference's expressions (raster.c:534-544) -> colour, texel (sampler plan from the record's LOD), texenv, fog
- *           -> packed colour into the tile.  Fragments that cannot take the staged-texture path -- per-fragment
- *           lighting, another or a larger texture, non-finite attributes -- go through the general code of
- *           dev_shade.cuh, out of line;
+ *           -> packed colour into the tile.  Fragments that cannot take the float4 path -- per-fragment lighting, a large
+ *           texture, REPEAT with a size that is no power of two, non-finite attributes -- go through the general code
+ *           of dev_shade.cuh, out of line;
  *   pass 3  the tile leaves as whole rows in 16-byte stores: to the colour plane and, for a band of a multi-GPU frame,
  *           straight into the presenting GPU's plane over NVLink (fused gather).
  *
@@ -28,6 +28,8 @@
 #include "dev_shade.cuh"
 #include "dev_fasttex.cuh"
 
+#include <cstdlib>
+
 namespace mtgl_dev_impl {
 
 void note_launch();
@@ -37,14 +39,11 @@ constexpr int SHADE_THREADS = 256;
 
 template <int SPLIT>
 struct ShadeSmem {
-    float4 tex[STAGED_TEXELS];
     uint32_t tile[TILE_W * (TILE_H / SPLIT)];       /* record index of a visible pixel until it is shaded, packed colour otherwise */
     uint16_t list[TILE_W * (TILE_H / SPLIT)];
     float un[256];
     uint32_t warp_total[SHADE_THREADS / 32];
-    StagedTex st;
 };
-static_assert(2 * (sizeof(ShadeSmem<1>) + 1024) <= 227 * 1024, "k_shade: two tiles per SM");
 
 /* the general path (dev_shade.cuh), out of line so that its registers do not count against the fast path */
 __device__ __noinline__ uint32_t shade_general(const BatchDev &b, const float *un, uint32_t r, float b0, float b1, float b2)
@@ -58,14 +57,14 @@ __device__ __noinline__ uint32_t shade_general(const BatchDev &b, const float *u
     return color_pack(c);      /* raster.c:719-721: color_pack clamps */
 }
 
-template <int SPLIT>
-__global__ void __launch_bounds__(SHADE_THREADS, 2) k_shade(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t stage_cfg)
+/* P: pixels per thread and iteration of pass 2; CTAS: CTAs per SM the register budget is set for */
+template <int SPLIT, int P, int CTAS>
+__global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
 {
     constexpr int ROWS = TILE_H / SPLIT;        /* rows of the tile this CTA owns */
     constexpr int PX = 16 / SPLIT;              /* consecutive pixels per thread in pass 1 */
     constexpr int TPR = TILE_W / PX;            /* threads per row */
-    extern __shared__ __align__(16) unsigned char shade_smem_raw[];
-    ShadeSmem<SPLIT> &sm = *reinterpret_cast<ShadeSmem<SPLIT> *>(shade_smem_raw);
+    __shared__ __align__(16) ShadeSmem<SPLIT> sm;
     if (!lists_fit(b)) return;
 
     const uint32_t slot = blockIdx.x / SPLIT, sub = blockIdx.x % SPLIT;
@@ -80,7 +79,6 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2) k_shade(BatchDev b, FrameTar
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
     sm.un[threadIdx.x] = b.unorm8[threadIdx.x];
-    if (threadIdx.x == 0) sm.st.id = nullptr;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
 
@@ -134,12 +132,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2) k_shade(BatchDev b, FrameTar
     for (int k = 0; k < PX; k++)
         if (has_mask & (1u << k)) sm.list[at++] = (uint16_t)(y * TILE_W + xq + k);
 
-    /* ---- the texture the fast path samples ---- */
-    if (n != 0u && stage_cfg != 0xFFFFFFFFu) stage_texture(sm.tex, sm.st, b.cfgs + stage_cfg, sm.un, SHADE_THREADS);
     __syncthreads();
 
     /* ---- pass 2: shade the compacted pixels, two per thread and iteration ---- */
-    constexpr int P = 2;
     for (uint32_t i0 = threadIdx.x; i0 < n; i0 += P * SHADE_THREADS) {
         int ci[P];
         uint32_t r[P], out[P];
@@ -171,12 +166,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2) k_shade(BatchDev b, FrameTar
             const uint32_t flags = cfg->flags;
             TriAttr A;
             load_attr(A, rec);
-            /* per-fragment lighting (raster.c:592-615) and textures outside the staged one take the general path */
+            /* per-fragment lighting (raster.c:592-615) and textures without a usable float4 copy take the general path */
             general[p] = (flags & RC_LIGHTING) && ((flags & RC_PHONG) || ((sflags[p] >> 31) && (flags & RC_TWO_SIDE)));
-            if (flags & RC_TEXTURED) {
-                const float u[3] = { A.u0, A.u1, A.u2 }, v3[3] = { A.v0, A.v1, A.v2 }, w[3] = { A.w0, A.w1, A.w2 };
-                general[p] = general[p] || !fast_texture_ok(sm.st, cfg, u, v3, w);
-            }
+            if (flags & RC_TEXTURED) general[p] = general[p] || !cfg->fast_tex || !(sflags[p] & STATE_BOUNDED_BIT);
             Color4 c;
             if (flags & RC_FLAT) c = { A.col2.x, A.col2.y, A.col2.z, A.col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
             else {
@@ -200,7 +192,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2) k_shade(BatchDev b, FrameTar
                 }
                 float cl;
                 const uint32_t plan = sampler_plan(cfg, A.lod, cl);
-                const float4 t = fast_sample(sm.tex, sm.st, plan, cl, u, v2);
+                const TexView tv = { cfg->tex_f4, cfg->tex_w, cfg->tex_h, cfg->tex_w1, cfg->tex_h1, cfg->tex_w * cfg->tex_h };
+                const float4 t = fast_sample<true>(tv, plan, cl, u, v2);
                 switch (cfg->tex_env_mode) {
                 case G_REPLACE: c = { t.x, t.y, t.z, t.w }; break;
                 case G_DECAL: c = color_lerp_rgb(c, { t.x, t.y, t.z, t.w }, t.w); break;
@@ -250,20 +243,22 @@ __global__ void __launch_bounds__(SHADE_THREADS, 2) k_shade(BatchDev b, FrameTar
     }
 }
 
-void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t stage_cfg, cudaStream_t s)
+void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, cudaStream_t s)
 {
-    static bool configured[64] = { false };
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeSmem<1>));
-        cudaFuncSetAttribute(k_shade<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeSmem<4>));
-        configured[dev] = true;
-    }
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0) return;
-    if (small_grid(tiles)) k_shade<4><<<tiles * 4u, SHADE_THREADS, sizeof(ShadeSmem<4>), s>>>(b, fb, clear, stage_cfg);
-    else k_shade<1><<<tiles, SHADE_THREADS, sizeof(ShadeSmem<1>), s>>>(b, fb, clear, stage_cfg);
+    /* MTGL_SHADE_VARIANT: A/B switch for profiling -- 0: two pixels per thread at 2 CTAs / SM, 1: one pixel at 3 CTAs / SM,
+     * 2: two pixels at 3 CTAs / SM (a few spilled registers) */
+    static const int variant = [] { const char *e = std::getenv("MTGL_SHADE_VARIANT"); return e ? std::atoi(e) : 0; }();
+    if (small_grid(tiles)) {
+        if (variant == 1) k_shade<4, 1, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else if (variant == 2) k_shade<4, 2, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else k_shade<4, 2, 2><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+    } else {
+        if (variant == 1) k_shade<1, 1, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else if (variant == 2) k_shade<1, 2, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else k_shade<1, 2, 2><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+    }
     note_launch();
 }
 

@@ -40,7 +40,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-struct TexObj { uint32_t *l0 = nullptr, *l1 = nullptr; int w = 0, h = 0, w1 = 0, h1 = 0; };
+struct TexObj { uint32_t *l0 = nullptr, *l1 = nullptr; float4 *f4 = nullptr; int w = 0, h = 0, w1 = 0, h1 = 0; };
+constexpr int kFloatTexelsMax = 256 * 256;      /* textures up to this size also keep a float4 copy (16 B / texel + level 1) */
 struct BufObj {
     uint8_t *ptr = nullptr; uint64_t size = 0;
     uint64_t gen = 0;               /* bumped by every write through the API */
@@ -179,6 +180,9 @@ void build_cfg(const mtgl_dev *d, const mtgl_state &s, RasterCfg &c)
         f |= RC_TEXTURED;
         textured = true;
         c.tex_l0 = t.l0; c.tex_l1 = t.l1;
+        c.tex_f4 = t.f4;
+        const bool pow2_w = (t.w & (t.w - 1)) == 0, pow2_h = (t.h & (t.h - 1)) == 0;
+        c.fast_tex = (t.f4 && (s.tex_wrap_s != G_REPEAT || pow2_w) && (s.tex_wrap_t != G_REPEAT || pow2_h)) ? 1u : 0u;
         c.tex_w = t.w; c.tex_h = t.h; c.tex_w1 = t.w1; c.tex_h1 = t.h1;
         c.tex_min = s.tex_min_filter; c.tex_mag = s.tex_mag_filter;
         c.tex_wrap_s = s.tex_wrap_s; c.tex_wrap_t = s.tex_wrap_t;
@@ -360,6 +364,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
     for (uint32_t i = 0; i < kMaxObjects; i++) {
         if (d->tex[i].l0) cudaFree(d->tex[i].l0);
         if (d->tex[i].l1) cudaFree(d->tex[i].l1);
+        if (d->tex[i].f4) cudaFree(d->tex[i].f4);
     }
     for (uint32_t i = 0; i < kMaxBuffers; i++)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
@@ -478,6 +483,7 @@ int mtgl_dev_texture_image(mtgl_dev *d, uint32_t id, int32_t w, int32_t h, const
     CU(cudaStreamSynchronize(d->stream));
     if (t.l0) CU(cudaFree(t.l0));
     if (t.l1) CU(cudaFree(t.l1));
+    if (t.f4) CU(cudaFree(t.f4));
     t = TexObj();
     size_t n = (size_t)w * (size_t)h;
     CU(cudaMalloc(&t.l0, n * 4));
@@ -487,6 +493,11 @@ int mtgl_dev_texture_image(mtgl_dev *d, uint32_t id, int32_t w, int32_t h, const
         t.w1 = w / 2; t.h1 = h / 2;
         CU(cudaMalloc(&t.l1, (size_t)t.w1 * t.h1 * 4));
         launch_mip1(t.l0, w, h, t.l1, d->unorm8, d->stream);
+    }
+    if (n <= (size_t)kFloatTexelsMax) {
+        const int n1 = t.l1 ? t.w1 * t.h1 : 0;
+        CU(cudaMalloc(&t.f4, (n + (size_t)n1) * sizeof(float4)));
+        launch_tex_f4(t.l0, (int)n, t.l1, n1, t.f4, d->unorm8, d->stream);
     }
     CU(cudaStreamSynchronize(d->stream));
     return MTGL_OK;
@@ -500,6 +511,7 @@ int mtgl_dev_texture_delete(mtgl_dev *d, uint32_t id)
     if (t.l0 || t.l1) CU(cudaStreamSynchronize(d->stream));
     if (t.l0) CU(cudaFree(t.l0));
     if (t.l1) CU(cudaFree(t.l1));
+    if (t.f4) CU(cudaFree(t.f4));
     t = TexObj();
     return MTGL_OK;
 }
@@ -810,12 +822,6 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         if (const char *e = std::getenv("MTGL_FILL")) fill_env = !std::strcmp(e, "never") ? FILL_OFF : (!std::strcmp(e, "always") ? FILL_ALWAYS : FILL_AUTO);
         plan.fill_mode = (need_eye || !had_triangles) ? FILL_OFF : fill_env;
         plan.in_order_all = flags_all; plan.in_order_any = flags_any;
-        plan.stage_cfg = 0xFFFFFFFFu;
-        for (const PassDraw &q : passes[pidx]) {
-            const uint32_t ci = bt->draws[q.draw].raster_state;
-            const uint32_t need = RC_TEXTURED | RC_DEFER;
-            if ((cfgs[ci].flags & need) == need) { plan.stage_cfg = ci; break; }
-        }
         launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
         CU(cudaEventRecord(sev[5], d->stream));
         t_launched = std::chrono::steady_clock::now();
