@@ -262,6 +262,8 @@ class Session:
         L.scene_c4_host_data.restype = ctypes.c_void_p
         L.scene_c4_vbo.restype = ctypes.c_uint
         L.scene_c4_vertex_count.restype = ctypes.c_int
+        L.mtglBufferDataPinned.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
+        L.mtglReadColorAsync.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 
     def close(self):
         if self.dist:
@@ -536,13 +538,43 @@ def measure(sess, workload, primary):
             base = pinned_out.data_ptr() - ry0 * w * 4
             assert L.mtgl_dev_read_framebuffer(dev, ry0, ry1, base, None, None) == 0
 
-    e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    # N = 1: the pipelined form of the same step (include/mtgl_context.h): the upload is queued from pinned memory into
+    # fresh storage (mtglBufferDataPinned), the frame is queued behind it, the read-back of its colour plane is queued
+    # behind the frame (mtglReadColorAsync, two pinned targets in turn) -- so frame i+1's upload crosses PCIe while frame
+    # i is rasterised and read back.  Every step still uploads its whole VBO and reads its whole frame back, and the timed
+    # region ends when the last read-back has landed (glFinish).
+    pipelined_e2e = world == 1 and not args.serial_e2e
+    if pipelined_e2e:
+        outs = [pinned_out, torch.empty_like(pinned_out).pin_memory()]
+
+        def e2e_step(k=0):
+            if not is_c3:
+                L.glBindBuffer(GL_ARRAY_BUFFER, vbo)
+                L.mtglBufferDataPinned(GL_ARRAY_BUFFER, nbytes, pinned_in.data_ptr(), GL_STATIC_DRAW)
+            frame()
+            L.mtglReadColorAsync(0, h, outs[k & 1].data_ptr())
+
+        e2e_step(); e2e_step(1)
+        sync_all()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_step(k)
+        L.glFinish()
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        if not is_c3 and os.environ.get("MTGL_BENCH_BAND") is None:      # the frames that came back are the frame
+            want = np.empty(h * w, dtype=np.uint32)
+            assert L.mtgl_dev_read_framebuffer(dev, 0, h, want.ctypes.data, None, None) == 0
+            for o in outs:
+                assert np.array_equal(o.numpy().view(np.uint32), want), "pipelined read-back differs from the plane"
+    else:
         e2e_step()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        sync_all()
+        e2e_s = time.perf_counter() - t0
     if dist:
         tt = torch.tensor([e2e_s], device=f"cuda:{local}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -635,7 +667,8 @@ def measure(sess, workload, primary):
         "multi_gpu": None if world == 1 else {"gather": "fused NVLink peer-store gather + frame-barrier kernel" if peer else "NCCL send/recv gather",
                                               "band_rows": bounds, "band_balance": balance_log, "gather_check": gather_check},
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_s * 1e3 / args.steps},
+                "ms_per_step": e2e_s * 1e3 / args.steps,
+                "mode": "pipelined across frames (mtglBufferDataPinned / mtglReadColorAsync)" if (world == 1 and not args.serial_e2e) else "upload, render, read-back in sequence"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": groups[gi], "bound": "hbm", "achieved": achieved, "peak": bw, "unit": "GB/s",
@@ -684,6 +717,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 and C5 lines of the default (C4) run")
     ap.add_argument("--no-parity", action="store_true", help="skip the reference-rendered parity check of each workload")
+    ap.add_argument("--serial-e2e", action="store_true", help="N = 1: upload, render and read back strictly in sequence (no pipelining across frames)")
     ap.add_argument("--uniform-bands", action="store_true", help="N > 1: keep the uniform split of tile rows (no load balancing)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'nccl' = send/recv after the frame")

@@ -42,6 +42,14 @@ typedef struct mtgl_framebuffer {
  * mirror; returns the mirror (valid until the next gl* call on the context) or NULL on error. */
 const mtgl_framebuffer *mtgl_map_framebuffer(GLState *ctx, unsigned planes);
 
+/* Pipelined transfers for render loops that stream geometry in and frames out (extensions; include/mtgl_dev.h explains
+ * the mechanics).  mtglBufferDataPinned is glBufferData (src/gl_api.c -> src/vbo.c:120-145) for a source in page-locked
+ * host memory that stays unchanged until glFinish(): the call returns once the copy is queued.  mtglReadColorAsync hands
+ * the queued work to the device and queues a copy of colour rows [y0, y1) (row 0 = top, as ctx->framebuffer.color) into
+ * page-locked host memory; glFinish() waits for it. */
+void mtglBufferDataPinned(unsigned target, long size, const void *pinned_data, unsigned usage);
+void mtglReadColorAsync(int32_t y0, int32_t y1, uint32_t *pinned_color);
+
 /* Back-end handle of a context (struct mtgl_dev*, include/mtgl_dev.h) for tools that need device
  * plane pointers, band ownership or timing counters. */
 struct mtgl_dev *mtgl_context_device(GLState *ctx);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MTGL_DEV_ABI_VERSION 4
+#define MTGL_DEV_ABI_VERSION 5
 
 /* error codes */
 #define MTGL_OK            0
@@ -258,6 +258,20 @@ int mtgl_dev_buffer_delete(mtgl_dev *dev, uint32_t id);
  * the buffer with a collective (each rank uploads a slice, NCCL all-gather over NVLink) instead of N full uploads */
 int mtgl_dev_buffer_pointer(mtgl_dev *dev, uint32_t id, void **ptr, uint64_t *size);
 int mtgl_dev_buffer_read(mtgl_dev *dev, uint32_t id, uint64_t offset, uint64_t size, void *out);
+
+/* Pipelined transfers (no reference counterpart: the reference's buffers and framebuffer ARE host memory).
+ *
+ * mtgl_dev_buffer_data_pinned is mtgl_dev_buffer_data for a source in PAGE-LOCKED host memory that the caller leaves
+ * unchanged until mtgl_dev_finish: the copy is queued on an upload stream and the call returns at once.  The buffer name
+ * gets fresh storage (the storage that batches submitted earlier still read is orphaned and recycled once they have
+ * finished -- what a GL driver does for glBufferData on a buffer in flight), so the upload of frame i+1 overlaps the
+ * rasterisation and the read-back of frame i; batches submitted afterwards wait for the copy on the device.
+ *
+ * mtgl_dev_read_color_async queues a copy of colour rows [y0, y1) into page-locked host memory (`color` addresses row 0,
+ * pitch = width) behind every batch submitted so far, on a read-back stream, and returns; batches submitted afterwards
+ * do not touch the plane before the copy has left it.  mtgl_dev_finish waits for uploads, batches and read-backs. */
+int mtgl_dev_buffer_data_pinned(mtgl_dev *dev, uint32_t id, uint64_t size, const void *pinned_data);
+int mtgl_dev_read_color_async(mtgl_dev *dev, int32_t y0, int32_t y1, uint32_t *pinned_color);
 
 /* texture_upload_* (textures.c:141-269) after conversion to RGBA8 words (a<<24|b<<16|g<<8|r);
  * also builds mip level 1 the way texture_generate_mip1 does (textures.c:311-354). */

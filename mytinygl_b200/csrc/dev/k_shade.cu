@@ -107,8 +107,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
 #pragma unroll
         for (int k = 0; k < PX; k++) {
             uint32_t word = v[k];
-            if (v[k] != VIS_NONE) has_mask |= 1u << k;
-            else if (xq + k < vw) word = (clr_row && px0 + xq + k >= clr.x0 && px0 + xq + k < clr.x1) ? clr.color : fb.color[p0 + k];
+            if (v[k] != VIS_NONE) {
+                has_mask |= 1u << k;
+                /* pass 2 starts two barriers from here: its records (160 B, two 128-byte lines at most) travel L2 -> L1 meanwhile */
+                const char *rp = reinterpret_cast<const char *>(b.records + v[k]);
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(rp));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(rp + 128));
+            } else if (xq + k < vw) word = (clr_row && px0 + xq + k >= clr.x0 && px0 + xq + k < clr.x1) ? clr.color : fb.color[p0 + k];
             sm.tile[y * TILE_W + xq + k] = word;
         }
     }
@@ -248,14 +253,16 @@ void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clea
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0) return;
     /* MTGL_SHADE_VARIANT: A/B switch for profiling -- 0: two pixels per thread at 2 CTAs / SM, 1: one pixel at 3 CTAs / SM,
-     * 2: two pixels at 3 CTAs / SM (a few spilled registers) */
-    static const int variant = [] { const char *e = std::getenv("MTGL_SHADE_VARIANT"); return e ? std::atoi(e) : 0; }();
+     * 2: two pixels at 3 CTAs / SM (a few spilled registers), 3: one pixel at 4 CTAs / SM (64 registers, ~100 B spilled) */
+    static const int variant = [] { const char *e = std::getenv("MTGL_SHADE_VARIANT"); return e ? std::atoi(e) : 1; }();
     if (small_grid(tiles)) {
-        if (variant == 1) k_shade<4, 1, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        if (variant == 3) k_shade<4, 1, 4><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else if (variant == 1) k_shade<4, 1, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
         else if (variant == 2) k_shade<4, 2, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
         else k_shade<4, 2, 2><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
     } else {
-        if (variant == 1) k_shade<1, 1, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        if (variant == 3) k_shade<1, 1, 4><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else if (variant == 1) k_shade<1, 1, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
         else if (variant == 2) k_shade<1, 2, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
         else k_shade<1, 2, 2><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
     }

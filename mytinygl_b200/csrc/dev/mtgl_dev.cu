@@ -104,6 +104,13 @@ struct mtgl_dev {
     unsigned long long barrier_epoch = 0;   /* frame barriers this context has taken part in since the plane was exported / mapped */
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
+    /* pipelined transfers (mtgl_dev_buffer_data_pinned / mtgl_dev_read_color_async) */
+    cudaStream_t upload_stream = nullptr, readback_stream = nullptr;
+    cudaEvent_t upload_ev = nullptr, readback_ev = nullptr, render_ev = nullptr;
+    bool upload_pending = false, readback_pending = false;
+    struct Orphan { uint8_t *ptr; uint64_t size; cudaEvent_t ev; };     /* storage whose last readers are batches before `ev` */
+    std::vector<Orphan> orphans;
+
     mtgl_dev_stats stats{};
     char err[256] = { 0 };
 };
@@ -121,6 +128,24 @@ int fail(mtgl_dev *d, int code, const char *what, cudaError_t ce = cudaSuccess)
         cudaError_t ce_ = (call);                                                            \
         if (ce_ != cudaSuccess) return fail(d, ce_ == cudaErrorMemoryAllocation ? MTGL_E_OOM : MTGL_E_CUDA, #call, ce_); \
     } while (0)
+
+/* work queued on the main stream from here on runs after the queued uploads have landed and after the queued read-backs
+ * have left the colour plane */
+int order_after_transfers(mtgl_dev *d)
+{
+    if (d->upload_pending) { CU(cudaStreamWaitEvent(d->stream, d->upload_ev, 0)); d->upload_pending = false; }
+    if (d->readback_pending) { CU(cudaStreamWaitEvent(d->stream, d->readback_ev, 0)); d->readback_pending = false; }
+    return MTGL_OK;
+}
+
+int sync_all_streams(mtgl_dev *d)
+{
+    if (d->upload_stream) CU(cudaStreamSynchronize(d->upload_stream));
+    CU(cudaStreamSynchronize(d->stream));
+    if (d->readback_stream) CU(cudaStreamSynchronize(d->readback_stream));
+    d->upload_pending = false; d->readback_pending = false;
+    return MTGL_OK;
+}
 
 int reserve(mtgl_dev *d, DevBuf &b, size_t bytes)
 {
@@ -346,6 +371,11 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
         if (ce == cudaSuccess) ce = cudaEventCreate(&es.stop);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->counters_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->upload_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->readback_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->upload_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->readback_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->render_ev, cudaEventDisableTiming);
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreate(&d->mark_ev[i]);
     if (ce != cudaSuccess) {
         mtgl_dev_destroy(d);
@@ -360,7 +390,15 @@ void mtgl_dev_destroy(mtgl_dev *d)
 {
     if (!d) return;
     cudaSetDevice(d->device);
+    if (d->upload_stream) cudaStreamSynchronize(d->upload_stream);
     if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->readback_stream) cudaStreamSynchronize(d->readback_stream);
+    for (mtgl_dev::Orphan &o : d->orphans) { if (o.ptr) cudaFree(o.ptr); if (o.ev) cudaEventDestroy(o.ev); }
+    if (d->upload_stream) cudaStreamDestroy(d->upload_stream);
+    if (d->readback_stream) cudaStreamDestroy(d->readback_stream);
+    if (d->upload_ev) cudaEventDestroy(d->upload_ev);
+    if (d->readback_ev) cudaEventDestroy(d->readback_ev);
+    if (d->render_ev) cudaEventDestroy(d->render_ev);
     for (uint32_t i = 0; i < kMaxObjects; i++) {
         if (d->tex[i].l0) cudaFree(d->tex[i].l0);
         if (d->tex[i].l1) cudaFree(d->tex[i].l1);
@@ -407,6 +445,7 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
     CU(cudaSetDevice(d->device));
     BufObj &b = d->buf[id];
     b.gen++; b.draws_since_write = 0;
+    if (d->upload_pending) CU(cudaStreamSynchronize(d->upload_stream));     /* a queued pinned upload may target this storage */
     if (b.size != size || !b.ptr) {
         b.exposed = false;
         CU(cudaStreamSynchronize(d->stream));
@@ -421,6 +460,61 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
         /* the caller may reuse 'data' immediately (glBufferData copies at call time, vbo.c:120-145) */
         CU(cudaStreamSynchronize(d->stream));
     }
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_data_pinned(mtgl_dev *d, uint32_t id, uint64_t size, const void *data)
+{
+    if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
+    if (size == 0 || !data) return mtgl_dev_buffer_data(d, id, size, data);
+    CU(cudaSetDevice(d->device));
+    BufObj &b = d->buf[id];
+    /* the storage the name has now may still be read by batches already submitted: orphan it behind an event on the main
+     * stream (recycled by a later call once the event has passed), and give the name storage nobody reads */
+    if (b.ptr) {
+        mtgl_dev::Orphan o{ b.ptr, b.size, nullptr };
+        for (mtgl_dev::Orphan &f : d->orphans) if (!f.ptr && f.ev) { o.ev = f.ev; f.ev = nullptr; break; }
+        if (!o.ev) CU(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(o.ev, d->stream));
+        bool placed = false;
+        for (mtgl_dev::Orphan &f : d->orphans) if (!f.ptr && !f.ev) { f = o; placed = true; break; }
+        if (!placed) d->orphans.push_back(o);
+        b.ptr = nullptr; b.size = 0;
+    }
+    uint8_t *fresh = nullptr;
+    for (mtgl_dev::Orphan &f : d->orphans) {
+        if (!f.ptr || f.size != size || cudaEventQuery(f.ev) != cudaSuccess) continue;
+        fresh = f.ptr; f.ptr = nullptr;         /* (its event stays in the slot for reuse) */
+        break;
+    }
+    cudaGetLastError();                         /* cudaEventQuery reports "not ready" as an error code: not an error here */
+    if (!fresh) {
+        /* nothing to recycle yet (the first frames of a loop): a plain allocation; orphans of other sizes whose readers
+         * have finished are released on the way */
+        for (mtgl_dev::Orphan &f : d->orphans)
+            if (f.ptr && f.size != size && cudaEventQuery(f.ev) == cudaSuccess) { CU(cudaFree(f.ptr)); f.ptr = nullptr; }
+        cudaGetLastError();
+        CU(cudaMalloc(&fresh, size));
+    }
+    b.ptr = fresh; b.size = size;
+    b.gen++; b.draws_since_write = 0; b.exposed = false;
+    CU(cudaMemcpyAsync(b.ptr, data, size, cudaMemcpyHostToDevice, d->upload_stream));
+    CU(cudaEventRecord(d->upload_ev, d->upload_stream));
+    d->upload_pending = true;
+    return MTGL_OK;
+}
+
+int mtgl_dev_read_color_async(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *color)
+{
+    if (!d || !color || y0 < 0 || y1 > d->height || y0 > y1) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    const size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
+    if (n == 0) return MTGL_OK;
+    CU(cudaEventRecord(d->render_ev, d->stream));
+    CU(cudaStreamWaitEvent(d->readback_stream, d->render_ev, 0));
+    CU(cudaMemcpyAsync(color + o, d->color + o, n * 4, cudaMemcpyDeviceToHost, d->readback_stream));
+    CU(cudaEventRecord(d->readback_ev, d->readback_stream));
+    d->readback_pending = true;
     return MTGL_OK;
 }
 
@@ -441,6 +535,7 @@ int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
     b.gen++; b.draws_since_write = 0;
+    if (int orc = order_after_transfers(d)) return orc;
     if (size) {
         CU(cudaMemcpyAsync(b.ptr + offset, data, size, cudaMemcpyHostToDevice, d->stream));
         CU(cudaStreamSynchronize(d->stream));
@@ -452,6 +547,7 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
 {
     if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int orc = order_after_transfers(d)) return orc;
     BufObj &b = d->buf[id];
     if (b.ptr) {
         CU(cudaStreamSynchronize(d->stream));
@@ -468,6 +564,7 @@ int mtgl_dev_buffer_read(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t siz
     BufObj &b = d->buf[id];
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int orc = order_after_transfers(d)) return orc;
     if (size) {
         CU(cudaMemcpyAsync(out, b.ptr + offset, size, cudaMemcpyDeviceToHost, d->stream));
         CU(cudaStreamSynchronize(d->stream));
@@ -536,6 +633,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         }
     } trace_out{ trace, t_in, t_copy, t_launched };
     CU(cudaSetDevice(d->device));
+    if (int orc = order_after_transfers(d)) return orc;
     const FrameTargets fb = frame_targets(d);
     const uint32_t ntiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
 
@@ -862,8 +960,7 @@ int mtgl_dev_finish(mtgl_dev *d)
 {
     if (!d) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
-    CU(cudaStreamSynchronize(d->stream));
-    return MTGL_OK;
+    return sync_all_streams(d);
 }
 
 int mtgl_dev_read_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *color, float *depth, uint8_t *stencil)
@@ -885,6 +982,7 @@ int mtgl_dev_write_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, const uint32
     CU(cudaSetDevice(d->device));
     size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
+    if (int orc = order_after_transfers(d)) return orc;
     if (color) CU(cudaMemcpyAsync(d->color + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
     if (color && d->present) CU(cudaMemcpyAsync(d->present + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
     if (depth) CU(cudaMemcpyAsync(d->depth + o, depth + o, n * 4, cudaMemcpyHostToDevice, d->stream));
@@ -950,6 +1048,7 @@ int mtgl_dev_draw_pixels(mtgl_dev *d, const mtgl_pixel_rect *rect, const void *p
     const uint32_t bpp = pixel_bpp(rect->format);
     if (bpp == 0 || rect->width <= 0 || rect->height <= 0) return MTGL_OK;       /* gl_api.c:1336-1338: unknown formats draw nothing */
     CU(cudaSetDevice(d->device));
+    if (int orc = order_after_transfers(d)) return orc;
     const size_t bytes = (size_t)rect->width * rect->height * bpp;
     /* the staging buffer is reused in stream order (copy, kernel, next copy); growing it waits for the stream */
     int rc = reserve(d, d->pixel_stage, bytes);

@@ -443,7 +443,20 @@ static GLuint buffer_for_target(GLState *c, GLenum target, bool *ok)
     return 0;
 }
 
+static void buffer_data_common(GLenum target, GLsizeiptr size, const GLvoid *data, GLenum usage, bool pinned_async);
+
 void glBufferData(GLenum target, GLsizeiptr size, const GLvoid *data, GLenum usage)
+{
+    buffer_data_common(target, size, data, usage, false);
+}
+
+/* include/mtgl_context.h: the source is page-locked and stays unchanged until glFinish() -- the copy is only queued */
+void mtglBufferDataPinned(unsigned target, long size, const void *pinned_data, unsigned usage)
+{
+    buffer_data_common((GLenum)target, (GLsizeiptr)size, pinned_data, (GLenum)usage, pinned_data != nullptr);
+}
+
+static void buffer_data_common(GLenum target, GLsizeiptr size, const GLvoid *data, GLenum usage, bool pinned_async)
 {
     MTGL_CTX();
     if (size < 0) { set_error(c, GL_INVALID_VALUE); return; }
@@ -483,7 +496,8 @@ void glBufferData(GLenum target, GLsizeiptr size, const GLvoid *data, GLenum usa
         b->data.clear(); b->data.shrink_to_fit();
         b->host_valid = false;
     }
-    if (mtgl_dev_buffer_data(c->dev, id, (uint64_t)size, data) != MTGL_OK) {
+    const int rc = pinned_async ? mtgl_dev_buffer_data_pinned(c->dev, id, (uint64_t)size, data) : mtgl_dev_buffer_data(c->dev, id, (uint64_t)size, data);
+    if (rc != MTGL_OK) {
         set_error(c, GL_OUT_OF_MEMORY);
         b->has_data = false; b->host_valid = false; b->size = 0;
     }

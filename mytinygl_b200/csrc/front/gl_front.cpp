@@ -496,6 +496,15 @@ const mtgl_framebuffer *mtgl_map_framebuffer(GLState *c, unsigned planes)
     return &c->mirror;
 }
 
+/* include/mtgl_context.h: queue the frame, then a copy of its colour rows into page-locked host memory; glFinish() waits */
+void mtglReadColorAsync(int32_t y0, int32_t y1, uint32_t *pinned_color)
+{
+    MTGL_CTX();
+    if (!pinned_color) { set_error(c, GL_INVALID_VALUE); return; }
+    flush_batch(c);
+    if (mtgl_dev_read_color_async(c->dev, y0, y1, pinned_color) != MTGL_OK) set_error(c, GL_INVALID_OPERATION);
+}
+
 /* ================================================================ clears and synchronisation */
 void glClear(GLbitfield mask) /* gl_api.c:409-457 */
 {

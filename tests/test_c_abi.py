@@ -28,7 +28,7 @@ def test_exports_device_abi(lib):
     for n in names:
         assert hasattr(lib, n), n
     lib.mtgl_dev_abi_version.restype = ctypes.c_int
-    assert lib.mtgl_dev_abi_version() == 4
+    assert lib.mtgl_dev_abi_version() == 5
 
 
 def test_exports_gl_api(lib):
@@ -36,7 +36,7 @@ def test_exports_gl_api(lib):
     assert len(names) == 111          # the reference's public entry points (include/GL/gl.h:531-669)
     for n in names:
         assert hasattr(lib, n), n
-    for n in declared("mtgl_context.h", r"\b((?:gl_|mtgl_)[a-z_]+)\s*\("):
+    for n in declared("mtgl_context.h", r"\b((?:gl_|mtgl_)[a-z_]+|mtgl[A-Z][A-Za-z]+)\s*\("):
         assert hasattr(lib, n), n
 
 

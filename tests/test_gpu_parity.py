@@ -199,3 +199,47 @@ def test_present_target_mirrors_color(b200, case):
         parent.send("done")
         proc.join(60)
         b200.destroy()
+
+
+def test_pipelined_transfers_match_the_synchronous_path(b200):
+    """mtglBufferDataPinned / mtglReadColorAsync (include/mtgl_context.h): frames queued back to back, each with its own
+    vertex data uploaded into orphaned storage and its colour plane read back asynchronously, give the same pixels as
+    glBufferData + draw + synchronous read -- including while earlier frames are still in flight."""
+    import ctypes
+    L = b200.lib
+    w, h, variant = 480, 270, 3 | (2 << 8)
+    L.scene_c4_host_data.restype = ctypes.c_void_p
+    L.scene_c4_vbo.restype = ctypes.c_uint
+    L.glBindBuffer.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    L.glBufferData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
+    L.mtglBufferDataPinned.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
+    L.mtglReadColorAsync.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    b200.create(w, h)
+    L.scene_c4_setup(w, h, variant)
+    nv = L.scene_c4_vertex_count()
+    base = np.ctypeslib.as_array(ctypes.cast(L.scene_c4_host_data(), ctypes.POINTER(ctypes.c_float)), shape=(nv, 8)).copy()
+    frames = []
+    for k in range(5):                       # a different mesh every frame: shifted and squeezed
+        f = base.copy()
+        f[:, 0] = f[:, 0] * (1.0 - 0.07 * k) + 0.11 * k
+        f[:, 1] += 0.05 * k
+        frames.append(np.ascontiguousarray(f))
+    vbo = L.scene_c4_vbo()
+    want = []
+    for f in frames:                         # synchronous path
+        L.glBindBuffer(0x8892, vbo)
+        L.glBufferData(0x8892, f.nbytes, f.ctypes.data, 0x88E4)
+        L.scene_c4_draw()
+        want.append(b200.read()[0].copy())
+    outs = [np.zeros((h, w), np.uint32) for _ in frames]
+    for f, o in zip(frames, outs):           # pipelined path: nothing waits until glFinish
+        L.glBindBuffer(0x8892, vbo)
+        L.mtglBufferDataPinned(0x8892, f.nbytes, f.ctypes.data, 0x88E4)
+        L.scene_c4_draw()
+        L.mtglReadColorAsync(0, h, o.ctypes.data)
+    L.glFinish()
+    assert L.glGetError() == 0
+    for k, (a, o) in enumerate(zip(want, outs)):
+        assert np.array_equal(a, o), f"frame {k}"
+    assert not np.array_equal(want[0], want[4])
+    b200.destroy()
