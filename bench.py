@@ -253,7 +253,8 @@ class Session:
         L.mtgl_dev_export_color_plane.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mtgl_dev_set_present_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
-        L.mtgl_dev_buffer_pointer.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
+        L.mtgl_context_buffer_pointer.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
+        L.gl_get_current_context.restype = ctypes.c_void_p
         L.mtgl_dev_stream.restype = ctypes.c_void_p
         L.mtgl_dev_stream.argtypes = [ctypes.c_void_p]
         L.glBindBuffer.argtypes = [ctypes.c_uint, ctypes.c_uint]
@@ -513,7 +514,7 @@ def measure(sess, workload, primary):
         vbo = L.scene_c4_vbo()
         if peer and nbytes % world == 0:
             bp, bs = ctypes.c_void_p(), ctypes.c_uint64()
-            assert L.mtgl_dev_buffer_pointer(dev, vbo, ctypes.byref(bp), ctypes.byref(bs)) == 0 and bs.value == nbytes
+            assert L.mtgl_context_buffer_pointer(L.gl_get_current_context(), vbo, ctypes.byref(bp), ctypes.byref(bs)) == 0 and bs.value == nbytes
             vbo_dev = torch.as_tensor(DevTensor(bp.value, nbytes), device=f"cuda:{local}")
         h2d = nbytes if (world == 1 or vbo_dev is not None) else nbytes * world      # bytes per step, summed over ranks
     d2h = h * w * 4

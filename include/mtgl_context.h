@@ -54,6 +54,11 @@ void mtglReadColorAsync(int32_t y0, int32_t y1, uint32_t *pinned_color);
  * plane pointers, band ownership or timing counters. */
 struct mtgl_dev *mtgl_context_device(GLState *ctx);
 
+/* Device address and size of a buffer object's storage, for applications that fill it behind the API (each rank of a
+ * multi-GPU application uploads a slice, an NCCL all-gather over NVLink completes the buffer).  The front end forgets what
+ * it knew about the contents; glBufferData makes them known again.  Returns 0 on success. */
+int mtgl_context_buffer_pointer(GLState *ctx, unsigned id, void **ptr, uint64_t *size);
+
 /* Display-list geometry drawn as compiled array draws so far (glBegin ... glEnd stretches of a list that were queued as
  * one draw record instead of being replayed call by call) -- for tools and tests. */
 uint64_t mtgl_context_list_runs_drawn(GLState *ctx);

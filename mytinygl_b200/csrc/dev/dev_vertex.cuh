@@ -78,7 +78,7 @@ __device__ __forceinline__ void fetch_position(const mtgl_in_vertex *staged, con
     if (dr.source == MTGL_SRC_STAGED) {
         const mtgl_in_vertex *iv = staged + dr.first_staged + i;
         px = iv->position[0]; py = iv->position[1]; pz = iv->position[2];
-        st = states + iv->state;
+        st = states + min(iv->state, dr.state_max);
     } else {
         float p[4];
         fetch_attrib(dr.position, element_index(dr, i), p, 4);
@@ -121,7 +121,7 @@ __device__ __forceinline__ void fetch_vertex(const mtgl_in_vertex *staged, const
         v.cur = { iv->color[0], iv->color[1], iv->color[2], iv->color[3] };
         v.s = iv->texcoord[0]; v.t = iv->texcoord[1];
         v.nx = iv->normal[0]; v.ny = iv->normal[1]; v.nz = iv->normal[2];
-        v.st = states + iv->state;
+        v.st = states + min(iv->state, dr.state_max);
     } else {
         const int32_t idx = element_index(dr, i);
         float p[4], c[4], tc[2], n[3];

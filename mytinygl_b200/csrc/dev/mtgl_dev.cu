@@ -322,6 +322,7 @@ int chunk_bounds_for(mtgl_dev *d, const mtgl_draw &s, const float4 **out)
         launch_chunk_bounds(bo.ptr + a.offset, a.stride, a.size, s.first, nverts, (float4 *)lru->boxes.ptr, d->stream);
         lru->buffer = a.buffer; lru->gen = bo.gen; lru->offset = a.offset; lru->stride = a.stride; lru->size = a.size;
         lru->first = s.first; lru->nverts = nverts;
+        lru->zero_streak = 0; lru->skip_left = 0;          /* a new occupant does not inherit the previous one's skip window */
         hit = lru;
     }
     hit->last_use = ++d->bounds_clock;
@@ -643,6 +644,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     draws.reserve(bt->n_draws);
     uint32_t planes = 0;
     bool need_eye = false;
+    if (bt->n_states > STATE_INDEX_MASK) return fail(d, MTGL_E_INVALID, "too many state blocks in one batch");
     for (uint32_t i = 0; i < bt->n_draws; i++) {
         const mtgl_draw &s = bt->draws[i];
         if (s.raster_state >= bt->n_states) return fail(d, MTGL_E_INVALID, "draw refers to a missing state block");
@@ -656,6 +658,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         describe(d, s.position, o.position); describe(d, s.color, o.color);
         describe(d, s.texcoord, o.texcoord); describe(d, s.normal, o.normal);
         o.ntris = triangles_of(s.mode, s.count);
+        o.state_max = bt->n_states ? bt->n_states - 1u : 0u;
         if (int brc = chunk_bounds_for(d, s, &o.bounds)) return brc;
         draws.push_back(o);
         const mtgl_state &rs = bt->states[s.raster_state];
@@ -1049,13 +1052,25 @@ int mtgl_dev_draw_pixels(mtgl_dev *d, const mtgl_pixel_rect *rect, const void *p
     if (bpp == 0 || rect->width <= 0 || rect->height <= 0) return MTGL_OK;       /* gl_api.c:1336-1338: unknown formats draw nothing */
     CU(cudaSetDevice(d->device));
     if (int orc = order_after_transfers(d)) return orc;
-    const size_t bytes = (size_t)rect->width * rect->height * bpp;
+    /* Only the part of the rectangle that lands on this device's rows and inside the framebuffer's columns is staged and
+     * launched (the reference skips the other pixels one by one, gl_api.c:1304-1312): rectangle row r lands on
+     * framebuffer row height - 1 - (y + r), column c on x + c. */
+    const int64_t fy_lo = std::max<int64_t>(d->band_y0, 0), fy_hi = std::min<int64_t>(d->band_y1, d->height);     /* [lo, hi) */
+    const int64_t r_lo = std::max<int64_t>(0, (int64_t)d->height - 1 - rect->y - (fy_hi - 1));
+    const int64_t r_hi = std::min<int64_t>(rect->height, (int64_t)d->height - 1 - rect->y - fy_lo + 1);
+    const int64_t c_lo = std::max<int64_t>(0, -(int64_t)rect->x), c_hi = std::min<int64_t>(rect->width, (int64_t)d->width - rect->x);
+    if (r_lo >= r_hi || c_lo >= c_hi) return MTGL_OK;
+    mtgl_pixel_rect part = *rect;
+    part.x = (int32_t)(rect->x + c_lo); part.y = (int32_t)(rect->y + r_lo);
+    part.width = (int32_t)(c_hi - c_lo); part.height = (int32_t)(r_hi - r_lo);
+    const size_t row_bytes = (size_t)part.width * bpp, bytes = row_bytes * (size_t)part.height;
     /* the staging buffer is reused in stream order (copy, kernel, next copy); growing it waits for the stream */
     int rc = reserve(d, d->pixel_stage, bytes);
     if (rc != MTGL_OK) return rc;
     /* from pageable memory this returns once the driver has taken its copy: the caller may reuse 'pixels' */
-    CU(cudaMemcpyAsync(d->pixel_stage.ptr, pixels, bytes, cudaMemcpyHostToDevice, d->stream));
-    launch_draw_pixels(*rect, (const uint8_t *)d->pixel_stage.ptr, frame_targets(d), d->unorm8, d->stream);
+    const uint8_t *src = (const uint8_t *)pixels + ((size_t)r_lo * (size_t)rect->width + (size_t)c_lo) * bpp;
+    CU(cudaMemcpy2DAsync(d->pixel_stage.ptr, row_bytes, src, (size_t)rect->width * bpp, row_bytes, (size_t)part.height, cudaMemcpyHostToDevice, d->stream));
+    launch_draw_pixels(part, (const uint8_t *)d->pixel_stage.ptr, frame_targets(d), d->unorm8, d->stream);
     CU(cudaGetLastError());
     return MTGL_OK;
 }
@@ -1066,11 +1081,29 @@ int mtgl_dev_read_pixels(mtgl_dev *d, int32_t x, int32_t y, int32_t width, int32
     const uint32_t bpp = (format == 0x1908) ? 4u : (format == 0x1907 ? 3u : 0u);
     if (bpp == 0 || width <= 0 || height <= 0) return MTGL_OK;                   /* other formats leave 'out' untouched */
     CU(cudaSetDevice(d->device));
-    const size_t bytes = (size_t)width * height * bpp;
+    /* rows outside the framebuffer read as zeros, columns outside it as (0, 0, 0, 255) (gl_api.c:1193-1214): filled on
+     * the host; only the visible part of the rectangle is gathered on the device and crosses PCIe */
+    const int64_t r_lo = std::max<int64_t>(0, -(int64_t)y), r_hi = std::min<int64_t>(height, (int64_t)d->height - y);
+    const int64_t c_lo = std::max<int64_t>(0, -(int64_t)x), c_hi = std::min<int64_t>(width, (int64_t)d->width - x);
+    const bool any = r_lo < r_hi && c_lo < c_hi;
+    uint8_t *o = (uint8_t *)out;
+    const size_t out_row = (size_t)width * bpp;
+    for (int64_t r = 0; r < height; r++) {
+        uint8_t *row = o + (size_t)r * out_row;
+        if (r < r_lo || r >= r_hi) { std::memset(row, 0, out_row); continue; }
+        if (!any || c_lo > 0 || c_hi < width) {
+            std::memset(row, 0, out_row);
+            if (bpp == 4) for (int64_t c = 0; c < width; c++) if (c < c_lo || c >= c_hi) row[(size_t)c * 4 + 3] = 255;
+        }
+    }
+    if (!any) { CU(cudaStreamSynchronize(d->stream)); return MTGL_OK; }
+    const int32_t pw = (int32_t)(c_hi - c_lo), ph = (int32_t)(r_hi - r_lo);
+    const size_t row_bytes = (size_t)pw * bpp, bytes = row_bytes * (size_t)ph;
     int rc = reserve(d, d->pixel_stage, bytes);
     if (rc != MTGL_OK) return rc;
-    launch_read_pixels(frame_targets(d), x, y, width, height, bpp, (uint8_t *)d->pixel_stage.ptr, d->stream);
-    CU(cudaMemcpyAsync(out, d->pixel_stage.ptr, bytes, cudaMemcpyDeviceToHost, d->stream));
+    launch_read_pixels(frame_targets(d), (int32_t)(x + c_lo), (int32_t)(y + r_lo), pw, ph, bpp, (uint8_t *)d->pixel_stage.ptr, d->stream);
+    CU(cudaMemcpy2DAsync(o + ((size_t)r_lo * (size_t)width + (size_t)c_lo) * bpp, out_row, d->pixel_stage.ptr, row_bytes, row_bytes, (size_t)ph,
+                         cudaMemcpyDeviceToHost, d->stream));
     CU(cudaStreamSynchronize(d->stream));
     return MTGL_OK;
 }

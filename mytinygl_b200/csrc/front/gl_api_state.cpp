@@ -467,6 +467,7 @@ static void buffer_data_common(GLenum target, GLsizeiptr size, const GLvoid *dat
     if (!b) return;
     flush_batch(c);                           /* queued draws read the previous contents */
     b->usage = usage;
+    b->peeks_frozen = false;                  /* the contents are known again */
     if (size <= 0) {                          /* vbo.c:126-134 */
         b->data.clear(); b->data.shrink_to_fit();
         b->has_data = false; b->host_valid = false; b->size = 0;

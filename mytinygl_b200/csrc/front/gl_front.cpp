@@ -145,12 +145,12 @@ bool buffer_read(GLState *c, GLuint id, uint64_t offset, uint64_t n, void *out)
     Buffer *b = get_buffer(c, id);
     if (!b || !b->has_data || offset + n > b->size) return false;
     if (b->host_valid) { std::memcpy(out, b->data.data() + offset, (size_t)n); return true; }
-    if (n <= sizeof(Buffer::Peek::raw)) {
+    if (n <= sizeof(Buffer::Peek::raw) && !b->peeks_frozen) {
         for (const Buffer::Peek &p : b->peeks)
             if (p.off == offset && p.n == n) { std::memcpy(out, p.raw, (size_t)n); return true; }
     }
     if (mtgl_dev_buffer_read(c->dev, id, offset, n, out) != MTGL_OK) return false;      /* waits for the queued frames */
-    if (n <= sizeof(Buffer::Peek::raw)) {
+    if (n <= sizeof(Buffer::Peek::raw) && !b->peeks_frozen) {
         if (b->peeks.size() >= 16) b->peeks.erase(b->peeks.begin());
         Buffer::Peek p; p.off = offset; p.n = (uint32_t)n;
         std::memcpy(p.raw, out, (size_t)n);
@@ -477,6 +477,22 @@ GLState *gl_get_current_context(void) { return g_ctx; }
 struct mtgl_dev *mtgl_context_device(GLState *c) { return c ? c->dev : nullptr; }
 uint64_t mtgl_context_list_runs_drawn(GLState *c) { return c ? c->list_runs_drawn : 0; }
 
+/* Device address of a buffer object's storage for applications that fill it behind the API (a sharded upload completed
+ * by an NCCL all-gather): from here on the front end cannot know the contents, so what it remembers of them is dropped
+ * and the bytes it needs (the last element of an array draw, gl_api.c:1826-1842) are read from the device when asked for. */
+int mtgl_context_buffer_pointer(GLState *c, unsigned id, void **ptr, uint64_t *size)
+{
+    if (!c) return MTGL_E_INVALID;
+    Buffer *b = get_buffer(c, id);
+    if (!b) return MTGL_E_INVALID;
+    flush_batch(c);
+    b->peeks.clear();
+    b->peeks_frozen = true;
+    b->host_valid = false;
+    b->data.clear();
+    return mtgl_dev_buffer_pointer(c->dev, id, ptr, size);
+}
+
 const mtgl_framebuffer *mtgl_map_framebuffer(GLState *c, unsigned planes)
 {
     if (!c) return nullptr;
@@ -721,7 +737,10 @@ static void describe_attrib(GLState *c, const ArrayPointer &a, bool enabled, mtg
 static bool host_element(GLState *c, GLuint buffer, const ArrayPointer &a, GLint idx, float *out, int want)
 {
     GLsizei stride = resolved_stride(a);
-    if (idx < 0 || stride <= 0) return false;
+    if (idx < 0 || stride <= 0) {           /* get_array_element (gl_api.c:1761-1782): the defaults, which then become current */
+        for (int i = 0; i < want; i++) out[i] = (i < 3) ? 0.0f : 1.0f;
+        return true;
+    }
     size_t comp = (a.type == GL_FLOAT) ? 4 : 1;
     uint64_t off = (uint64_t)(size_t)a.pointer + (uint64_t)idx * (uint64_t)stride;
     uint8_t raw[16];

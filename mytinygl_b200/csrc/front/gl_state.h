@@ -68,6 +68,8 @@ struct Buffer {                         /* buffer_t, vbo.h */
      * glBufferData / glBufferSubData, so a frame loop never waits for the device to learn them again. */
     struct Peek { uint64_t off; uint32_t n; uint8_t raw[16]; };
     std::vector<Peek> peeks;
+    bool peeks_frozen = false;          /* the storage's address was handed out (mtgl_context_buffer_pointer): nothing about its
+                                         * contents may be remembered until the next glBufferData */
 };
 
 constexpr uint64_t kHostMirrorLimit = 8u << 20;   /* buffers above this keep no host copy */
