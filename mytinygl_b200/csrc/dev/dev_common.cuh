@@ -82,6 +82,9 @@ struct DevDraw {
     uint32_t tbase;          /* index of this draw's first assembled primitive (triangle, line segment or point) */
     uint32_t ntris;          /* primitives of this draw in the pass */
     uint32_t fused;          /* independent triangles: no vertex-stage launch, k_setup shades the survivors' vertices */
+    uint32_t shared_verts;   /* indexed draw whose buffer ELEMENTS 0 .. shared_verts-1 go through the vertex stage once (plus one slot of
+                              * default attributes for out-of-range indices): k_setup looks a vertex up by its index.  0 = off */
+    uint32_t pad3_;
     uint32_t state_max;      /* n_states - 1 of the batch: a staged vertex's state index is clamped to it (a stale index from a broken
                               * binding must not become an out-of-bounds read) */
     const float4 *bounds;    /* object-space boxes of the draw's 256-triangle chunks (k_cull.cu), or NULL */

@@ -113,7 +113,15 @@ __device__ __forceinline__ void tex_transform(const mtgl_state *st, float s, flo
     if (tq != 0.0f && tq != 1.0f) { tu = tu / tq; tv = tv / tq; }
 }
 
-__device__ __forceinline__ void fetch_vertex(const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw &dr, uint32_t i, VertexIn &v)
+/* slot of element index e of a shared-vertex draw (DevDraw::shared_verts): the element itself, or the default slot */
+__device__ __forceinline__ uint32_t shared_slot(const DevDraw &dr, int32_t e)
+{
+    return (e >= 0 && (uint32_t)e < dr.shared_verts) ? (uint32_t)e : dr.shared_verts;
+}
+
+/* i: position in the draw's vertex sequence -- or, with by_element, the buffer element itself (negative: the defaults) */
+__device__ __forceinline__ void fetch_vertex(const mtgl_in_vertex *staged, const mtgl_state *states, const DevDraw &dr, uint32_t i, VertexIn &v,
+                                             bool by_element = false)
 {
     if (dr.source == MTGL_SRC_STAGED) {
         const mtgl_in_vertex *iv = staged + dr.first_staged + i;
@@ -123,7 +131,7 @@ __device__ __forceinline__ void fetch_vertex(const mtgl_in_vertex *staged, const
         v.nx = iv->normal[0]; v.ny = iv->normal[1]; v.nz = iv->normal[2];
         v.st = states + min(iv->state, dr.state_max);
     } else {
-        const int32_t idx = element_index(dr, i);
+        const int32_t idx = by_element ? (int32_t)i : element_index(dr, i);
         float p[4], c[4], tc[2], n[3];
         fetch_attrib(dr.position, idx, p, 4);
         v.px = p[0]; v.py = p[1]; v.pz = (dr.position.size == 2) ? 0.0f : p[2];

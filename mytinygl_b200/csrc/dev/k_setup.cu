@@ -840,6 +840,9 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         case G_QUAD_STRIP: { uint32_t q = 2 * (k >> 1); i0 = q; if (k & 1) { i1 = q + 3; i2 = q + 2; } else { i1 = q + 1; i2 = q + 3; } shape = 1; break; }
         default: i0 = 0; i1 = k + 1; i2 = k + 2; shape = 1; break;     /* fan, polygon */
         }
+        if (dr.shared_verts) {          /* the vertex stage ran once per buffer element: look the three up by index (gl_api.c:1898-1939) */
+            i0 = shared_slot(dr, element_index(dr, i0)); i1 = shared_slot(dr, element_index(dr, i1)); i2 = shared_slot(dr, element_index(dr, i2));
+        }
         i0 += dr.vbase; i1 += dr.vbase; i2 += dr.vbase;
         if (shape == 1) {
             float4 p0, p1, p2;

@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) k_vertex(BatchDev b)
     const DevDraw &dr = b.draws[d];
     if (dr.fused) return;               /* independent triangles: k_setup shades the vertices of the survivors itself */
     VertexIn in;
-    fetch_vertex(b.staged, b.states, dr, g - dr.vbase, in);
+    if (dr.shared_verts) {              /* one vertex per buffer element (glDrawElements reuses them); the last slot holds the defaults */
+        const uint32_t e = g - dr.vbase;
+        fetch_vertex(b.staged, b.states, dr, e < dr.shared_verts ? e : 0xFFFFFFFFu, in, true);
+    } else fetch_vertex(b.staged, b.states, dr, g - dr.vbase, in);
     VertexOut o;
     shade_vertex(in, o);
     b.v_clip[g] = o.clip;

@@ -742,6 +742,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
 
     struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles, n_unfused; bool any_bounds; };
     static const bool fuse_triangles = std::getenv("MTGL_NO_FUSE") == nullptr;     /* A/B switch for profiling */
+    const bool share_indexed = std::getenv("MTGL_NO_SHARED_VERTS") == nullptr;      /* A/B switch (read per batch: the tests flip it) */
     std::vector<PassInfo> infos;
     for (auto &p : passes) {
         PassInfo pi{};
@@ -768,12 +769,25 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             }
             o.vbase = v;
             o.fused = (fuse_triangles && o.mode == G_TRIANGLES) ? 1u : 0u;
+            /* glDrawElements re-emits a vertex for every index (gl_api.c:1898-1939); the vertex stage is a pure function of
+             * the element, so when the arrays hold fewer elements than the draw has indices, every ELEMENT is transformed
+             * and lit once and set-up looks vertices up by index (a post-transform cache that cannot miss).  Elements
+             * = the longest enabled array; indices beyond it read as the defaults, like fetch_attrib does per attribute. */
+            if (o.index_type && o.index_ptr && s.source == MTGL_SRC_ARRAYS && share_indexed) {
+                uint64_t elems = 0;
+                for (const DevAttrib *a : { &o.position, &o.color, &o.texcoord, &o.normal }) {
+                    if (!a->enabled || !a->ptr || !a->stride) continue;
+                    const uint64_t bytes = (uint64_t)a->size * (a->type == MTGL_TYPE_F32 ? 4u : 1u);
+                    if (a->avail >= bytes) elems = std::max<uint64_t>(elems, (a->avail - bytes) / a->stride + 1u);
+                }
+                if (elems > 0 && elems + 1 <= (uint64_t)o.count && elems < (1u << 24)) { o.shared_verts = (uint32_t)elems; o.fused = 0u; }
+            }
             if (!o.fused) unfused++;
             o.tbase = t - q.tri_first;      /* triangle k of the draw has global index tbase + k */
             o.ntris = q.tri_count;
             vb[k] = v; tb[k] = t;
             pd[k++] = o;
-            v += o.count; t += q.tri_count;
+            v += o.shared_verts ? o.shared_verts + 1u : o.count; t += q.tri_count;
         }
         vb[k] = v; tb[k] = t;
         pi.n_draws = k; pi.n_vertices = v; pi.n_triangles = t; pi.n_unfused = unfused;

@@ -36,6 +36,8 @@ CASES = (
     + [("vbo_large", 480, 270, 0)]
     + [("pixels", 320, 240, v) for v in (0, 1, 2, 5, 7)] + [("pixels", 517, 389, 3)]
     + [("displaylist_runs", 480, 270, v) for v in range(4)]
+    + [("indexed", 480, 360, v) for v in range(7)]          # Suzanne through glDrawElements: u16 / u32 / client indices / strips with u8
+    + [("lifetime", 400, 300, v) for v in range(3)]         # objects deleted / redefined while draws that use them are queued
     + [("c4_grid", 480, 270, C4_SMALL | (1 << 17)), ("c4_grid", 960, 540, 6 | (4 << 8) | (1 << 17))]     # one mesh, many draws
 )
 

@@ -1391,6 +1391,198 @@ static void scene_displaylist_runs(int w, int h, int variant)
     glDeleteLists(base, 4);
 }
 
+/* Suzanne as an INDEXED mesh -- 507 vertices (position + normal, texture coordinates derived from
+ * the position) in one buffer, 968 x 3 indices drawn with glDrawElements (gl_api.c:1854-1941): every vertex is referenced
+ * 5.7 times.  variant 0: GL_UNSIGNED_SHORT indices in an element buffer; 1: GL_UNSIGNED_INT in an element buffer;
+ * 2: GL_UNSIGNED_SHORT indices in client memory; 3: GL_UNSIGNED_INT, three draws of the mesh under different modelview
+ * matrices, two-sided lighting; 4: a 5x5 grid of vertices with ubyte colours under GL_COLOR_MATERIAL drawn as indexed
+ * GL_TRIANGLE_STRIPs with GL_UNSIGNED_BYTE indices; 5: variant 0 with GL_PHONG shading (per-fragment lighting);
+ * 6: GL_UNSIGNED_SHORT, textured + fog, polygon mode GL_LINE for back faces. */
+static void scene_indexed(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 100.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.15f, 0.15f, 0.2f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    GLuint buf[2];
+    glGenBuffers(2, buf);
+    if (variant == 4) {
+        struct { float x, y, z; uint8_t c[4]; } grid[25];
+        for (int j = 0; j < 5; j++)
+            for (int i = 0; i < 5; i++) {
+                int k = j * 5 + i;
+                grid[k].x = (float)i * 0.5f - 1.0f; grid[k].y = (float)j * 0.5f - 1.0f; grid[k].z = 0.15f * (float)((i * 7 + j * 3) % 5);
+                grid[k].c[0] = (uint8_t)(40 + 50 * i); grid[k].c[1] = (uint8_t)(30 + 45 * j); grid[k].c[2] = (uint8_t)(255 - 30 * i - 20 * j); grid[k].c[3] = 255;
+            }
+        uint8_t strip[4][10];
+        for (int j = 0; j < 4; j++)
+            for (int i = 0; i < 5; i++) { strip[j][2 * i] = (uint8_t)(j * 5 + i); strip[j][2 * i + 1] = (uint8_t)((j + 1) * 5 + i); }
+        glBindBuffer(GL_ARRAY_BUFFER, buf[0]);
+        glBufferData(GL_ARRAY_BUFFER, sizeof grid, grid, GL_STATIC_DRAW);
+        glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, buf[1]);
+        glBufferData(GL_ELEMENT_ARRAY_BUFFER, sizeof strip, strip, GL_STATIC_DRAW);
+        glEnableClientState(GL_VERTEX_ARRAY);
+        glEnableClientState(GL_COLOR_ARRAY);
+        glVertexPointer(3, GL_FLOAT, 16, (const void *)0);
+        glColorPointer(4, GL_UNSIGNED_BYTE, 16, (const void *)12);
+        suzanne_lights_and_material();
+        glEnable(GL_COLOR_MATERIAL);
+        glColorMaterial(GL_FRONT_AND_BACK, GL_AMBIENT_AND_DIFFUSE);
+        glNormal3f(0.0f, 0.0f, 1.0f);
+        glLoadIdentity();
+        glTranslatef(0.0f, 0.0f, -3.2f);
+        glRotatef(-25.0f, 1.0f, 0.0f, 0.0f);
+        for (int j = 0; j < 4; j++) glDrawElements(GL_TRIANGLE_STRIP, 10, GL_UNSIGNED_BYTE, (const void *)(size_t)(j * 10));
+        glDisableClientState(GL_COLOR_ARRAY);
+        glDisableClientState(GL_VERTEX_ARRAY);
+        glDeleteBuffers(2, buf);
+        return;
+    }
+    /* 507 vertices, interleaved position3 + normal3 + uv2 */
+    float *vb = (float *)malloc((size_t)g_mesh_nv * 8 * sizeof(float));
+    for (int i = 0; i < g_mesh_nv; i++) {
+        memcpy(vb + i * 8, g_mesh_pos + i * 3, 12);
+        memcpy(vb + i * 8 + 3, g_mesh_nrm + i * 3, 12);
+        vb[i * 8 + 6] = (g_mesh_pos[i * 3] + 0.7f) * 4.0f; vb[i * 8 + 7] = (g_mesh_pos[i * 3 + 1] + 0.5f) * 4.0f;
+    }
+    int ni = g_mesh_nf * 3;
+    uint16_t *i16 = (uint16_t *)malloc((size_t)ni * 2);
+    uint32_t *i32 = (uint32_t *)malloc((size_t)ni * 4);
+    for (int i = 0; i < ni; i++) { i16[i] = (uint16_t)g_mesh_faces[i]; i32[i] = (uint32_t)g_mesh_faces[i]; }
+    glBindBuffer(GL_ARRAY_BUFFER, buf[0]);
+    glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr)((size_t)g_mesh_nv * 32), vb, GL_STATIC_DRAW);
+    const int wide = (variant == 1 || variant == 3);
+    const void *indices = (const void *)0;
+    if (variant == 2) indices = i16;
+    else {
+        glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, buf[1]);
+        if (wide) glBufferData(GL_ELEMENT_ARRAY_BUFFER, (GLsizeiptr)((size_t)ni * 4), i32, GL_STATIC_DRAW);
+        else glBufferData(GL_ELEMENT_ARRAY_BUFFER, (GLsizeiptr)((size_t)ni * 2), i16, GL_STATIC_DRAW);
+    }
+    glEnableClientState(GL_VERTEX_ARRAY);
+    glEnableClientState(GL_NORMAL_ARRAY);
+    glVertexPointer(3, GL_FLOAT, 32, (const void *)0);
+    glNormalPointer(GL_FLOAT, 32, (const void *)12);
+    suzanne_lights_and_material();
+    if (variant == 5) glShadeModel(GL_PHONG);
+    if (variant == 3) {
+        GLfloat bd[] = { 0.1f, 0.6f, 0.9f, 1.0f };
+        glMaterialfv(GL_BACK, GL_DIFFUSE, bd);
+        glLightModeli(GL_LIGHT_MODEL_TWO_SIDE, 1);
+    }
+    if (variant == 6) {
+        glEnableClientState(GL_TEXTURE_COORD_ARRAY);
+        glTexCoordPointer(2, GL_FLOAT, 32, (const void *)24);
+        glEnable(GL_TEXTURE_2D);
+        make_checker_rgb(64, 4, 1);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_REPEAT);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_REPEAT);
+        GLfloat fog[] = { 0.15f, 0.15f, 0.2f, 1.0f };
+        glEnable(GL_FOG); glFogi(GL_FOG_MODE, GL_EXP2); glFogf(GL_FOG_DENSITY, 0.25f); glFogfv(GL_FOG_COLOR, fog);
+        glPolygonMode(GL_BACK, GL_LINE);
+    }
+    const int draws = (variant == 3) ? 3 : 1;
+    for (int k = 0; k < draws; k++) {
+        glLoadIdentity();
+        glTranslatef(draws == 1 ? 0.0f : (float)(k - 1) * 1.6f, 0.0f, draws == 1 ? -2.2f : -4.0f);
+        glRotatef(20.0f + 70.0f * (float)k, 1.0f, 0.0f, 0.0f);
+        glRotatef(30.0f, 0.0f, 1.0f, 0.0f);
+        glDrawElements(GL_TRIANGLES, ni, wide ? GL_UNSIGNED_INT : GL_UNSIGNED_SHORT, indices);
+    }
+    i16[0] = 1; /* client-memory indices are consumed at the call: must not affect the draw above */
+    glDisableClientState(GL_TEXTURE_COORD_ARRAY);
+    glDisableClientState(GL_NORMAL_ARRAY);
+    glDisableClientState(GL_VERTEX_ARRAY);
+    glDeleteBuffers(2, buf);
+    free(vb); free(i16); free(i32);
+}
+
+/* Object lifetime ("observationally synchronous"): the reference executes every draw at the call, so an
+ * object may be deleted, redefined or have its name reused right after the draw that used it.  A back end that queues
+ * draws must behave the same.  variant 0: glDeleteTextures / glDeleteBuffers / glDeleteLists directly behind the draws
+ * that use them, then the names are generated again, filled with different contents and drawn; 1: glTexImage2D /
+ * glBufferData / glBufferSubData / glNewList on objects that queued draws still use; 2: as 0 inside a display list that
+ * is deleted while it ... has just been called. */
+static void scene_lifetime(int w, int h, int variant)
+{
+    frustum_like_testbed(w, h, 50.0);
+    glEnable(GL_DEPTH_TEST);
+    glClearColor(0.05f, 0.1f, 0.1f, 1.0f);
+    glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+    static const float quad[4][5] = { { -1, -1, 0, 0, 0 }, { 1, -1, 0, 2, 0 }, { 1, 1, 0, 2, 2 }, { -1, 1, 0, 0, 2 } };
+    static const float small[4][5] = { { -0.5f, -0.5f, 0, 0, 0 }, { 0.5f, -0.5f, 0, 1, 0 }, { 0.5f, 0.5f, 0, 1, 1 }, { -0.5f, 0.5f, 0, 0, 1 } };
+    glEnableClientState(GL_VERTEX_ARRAY);
+    glEnableClientState(GL_TEXTURE_COORD_ARRAY);
+    glEnable(GL_TEXTURE_2D);
+    glTexEnvi(GL_TEXTURE_ENV, GL_TEXTURE_ENV_MODE, GL_REPLACE);
+    for (int round = 0; round < 3; round++) {
+        GLuint tex = round & 1 ? make_radial_rgba(32) : make_checker_rgb(64, 4 << round, round & 1);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, round == 2 ? GL_NEAREST : GL_LINEAR);
+        GLuint vbo;
+        glGenBuffers(1, &vbo);
+        glBindBuffer(GL_ARRAY_BUFFER, vbo);
+        glBufferData(GL_ARRAY_BUFFER, sizeof quad, quad, GL_STATIC_DRAW);
+        glVertexPointer(3, GL_FLOAT, 20, (const void *)0);
+        glTexCoordPointer(2, GL_FLOAT, 20, (const void *)12);
+        glLoadIdentity();
+        glTranslatef((float)(round - 1) * 1.7f, 0.4f, -5.0f - (float)round * 0.3f);
+        glRotatef(15.0f * (float)round, 0.0f, 0.0f, 1.0f);
+        glDrawArrays(GL_QUADS, 0, 4);
+        GLuint list = glGenLists(1);
+        glNewList(list, GL_COMPILE);
+        glBegin(GL_TRIANGLES);
+        for (int k = 0; k < 30; k++) {      /* long enough to become a compiled run */
+            float a = (float)k * 0.2094395f;
+            glTexCoord2f(0.5f, 0.5f); glVertex3f(0.0f, -1.6f, 0.0f);
+            glTexCoord2f(0.5f + 0.5f * cosf(a), 0.5f + 0.5f * sinf(a)); glVertex3f(0.6f * cosf(a), -1.6f + 0.6f * sinf(a), 0.0f);
+            glTexCoord2f(0.5f + 0.5f * cosf(a + 0.2094395f), 0.5f + 0.5f * sinf(a + 0.2094395f));
+            glVertex3f(0.6f * cosf(a + 0.2094395f), -1.6f + 0.6f * sinf(a + 0.2094395f), 0.0f);
+        }
+        glEnd();
+        glEndList();
+        glCallList(list);
+        if (variant == 1) {
+            /* redefinition while the draws above are still queued */
+            uint8_t px[16 * 16 * 3];
+            for (int i = 0; i < 16 * 16; i++) { px[i * 3] = (uint8_t)(i * 7); px[i * 3 + 1] = (uint8_t)(255 - i); px[i * 3 + 2] = (uint8_t)(round * 90); }
+            glTexImage2D(GL_TEXTURE_2D, 0, GL_RGB, 16, 16, 0, GL_RGB, GL_UNSIGNED_BYTE, px);
+            glBufferData(GL_ARRAY_BUFFER, sizeof small, small, GL_STATIC_DRAW);
+            glLoadIdentity();
+            glTranslatef((float)(round - 1) * 1.7f, 0.4f, -4.0f);
+            glDrawArrays(GL_QUADS, 0, 4);
+            float moved[5] = { -0.9f, -0.9f, 0.2f, 0, 0 };
+            glBufferSubData(GL_ARRAY_BUFFER, 0, sizeof moved, moved);
+            glTranslatef(0.0f, 1.3f, 0.0f);
+            glDrawArrays(GL_QUADS, 0, 4);
+            glNewList(list, GL_COMPILE);
+            glBegin(GL_QUADS);
+            glTexCoord2f(0, 0); glVertex3f(-0.3f, -2.0f, 0.5f); glTexCoord2f(1, 0); glVertex3f(0.3f, -2.0f, 0.5f);
+            glTexCoord2f(1, 1); glVertex3f(0.3f, -1.4f, 0.5f); glTexCoord2f(0, 1); glVertex3f(-0.3f, -1.4f, 0.5f);
+            glEnd();
+            glEndList();
+            glCallList(list);
+        }
+        /* the objects go away while everything above may still be queued; their names are reused by the next round */
+        glDeleteTextures(1, &tex);
+        glDeleteBuffers(1, &vbo);
+        glDeleteLists(list, 1);
+        if (variant == 2 && round == 1) {    /* drawing with the deleted names bound: no texture, no buffer -> nothing / untextured */
+            glBindTexture(GL_TEXTURE_2D, tex);
+            glBegin(GL_TRIANGLES);
+            glColor3f(0.9f, 0.3f, 0.1f);
+            glVertex3f(-0.4f, 1.2f, 0.3f); glVertex3f(0.4f, 1.2f, 0.3f); glVertex3f(0.0f, 1.8f, 0.3f);
+            glEnd();
+            glCallList(list);
+            glColor3f(1.0f, 1.0f, 1.0f);
+        }
+    }
+    glDisableClientState(GL_TEXTURE_COORD_ARRAY);
+    glDisableClientState(GL_VERTEX_ARRAY);
+}
+
 /* ---------------------------------------------------------------- registry */
 typedef void (*scene_fn)(int, int, int);
 static const struct { const char *name; scene_fn fn; } g_scenes[] = {
@@ -1420,6 +1612,8 @@ static const struct { const char *name; scene_fn fn; } g_scenes[] = {
     { "vbo_large", scene_vbo_large },
     { "pixels", scene_pixels },
     { "displaylist_runs", scene_displaylist_runs },
+    { "indexed", scene_indexed },
+    { "lifetime", scene_lifetime },
 };
 
 int scene_count(void) { return (int)(sizeof g_scenes / sizeof g_scenes[0]); }

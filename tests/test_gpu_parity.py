@@ -243,3 +243,35 @@ def test_pipelined_transfers_match_the_synchronous_path(b200):
         assert np.array_equal(a, o), f"frame {k}"
     assert not np.array_equal(want[0], want[4])
     b200.destroy()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 6])
+def test_indexed_draws_share_vertices(b200, front_oracle, variant, monkeypatch):
+    """glDrawElements (gl_api.c:1854-1941) re-emits a vertex per index; the back end runs the vertex stage once per buffer
+    ELEMENT when the arrays hold fewer elements than the draw has indices (Suzanne: 507 + 1 default slot instead of 2904)
+    and set-up looks vertices up by index.  Same frame as the per-index path, and the shared path must actually engage."""
+    import ctypes
+
+    class Stats(ctypes.Structure):
+        _fields_ = [("vertices", ctypes.c_uint64), ("rest", ctypes.c_uint64 * 40)]
+    L = b200.lib
+    L.mtgl_dev_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+    case = ("indexed", 480, 360, variant)
+    seen = {}
+    for mode in ("shared", "per-index"):
+        if mode == "per-index":
+            monkeypatch.setenv("MTGL_NO_SHARED_VERTS", "1")
+        b200.create(480, 360)
+        L.glClearColor(ctypes.c_float(0.25), ctypes.c_float(0.5), ctypes.c_float(0.75), ctypes.c_float(1.0))
+        L.glClear(0x4000 | 0x0100 | 0x0400)
+        assert L.scene_render(b"indexed", 480, 360, variant) == 0
+        planes = b200.read()
+        st = Stats()
+        assert L.mtgl_dev_get_stats(b200.device(), ctypes.byref(st)) == 0
+        b200.destroy()
+        seen[mode] = (planes, int(st.vertices))
+    for a, b in zip(seen["shared"][0], seen["per-index"][0]):
+        assert np.array_equal(a, b)
+    draws = 3 if variant == 3 else 1
+    assert seen["shared"][1] == draws * 508 and seen["per-index"][1] == draws * 2904, (seen["shared"][1], seen["per-index"][1])
+    assert_gate(compare_planes(front_oracle.render(*case), b200.render(*case)), case_id(case))
