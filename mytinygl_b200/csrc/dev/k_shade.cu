@@ -254,7 +254,7 @@ void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clea
     if (tiles == 0) return;
     /* MTGL_SHADE_VARIANT: A/B switch for profiling -- 0: two pixels per thread at 2 CTAs / SM, 1: one pixel at 3 CTAs / SM,
      * 2: two pixels at 3 CTAs / SM (a few spilled registers), 3: one pixel at 4 CTAs / SM (64 registers, ~100 B spilled) */
-    static const int variant = [] { const char *e = std::getenv("MTGL_SHADE_VARIANT"); return e ? std::atoi(e) : 1; }();
+    static const int variant = [] { const char *e = std::getenv("MTGL_SHADE_VARIANT"); return e ? std::atoi(e) : 3; }();
     if (small_grid(tiles)) {
         if (variant == 3) k_shade<4, 1, 4><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
         else if (variant == 1) k_shade<4, 1, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
