@@ -545,7 +545,63 @@ def measure(sess, workload, primary):
     # i is rasterised and read back.  Every step still uploads its whole VBO and reads its whole frame back, and the timed
     # region ends when the last read-back has landed (glFinish).
     pipelined_e2e = world == 1 and not args.serial_e2e
-    if pipelined_e2e:
+    host_gather = peer and not args.serial_e2e
+    host_gather_check = None
+    if host_gather:
+        # N > 1: the frame is assembled in HOST memory.  Rank 0 creates a page-locked frame that all ranks map (POSIX shared
+        # memory registered with CUDA); every rank queues the read-back of its own band into it behind its frame
+        # (mtglReadColorAsync) -- N PCIe links in parallel instead of rank 0 reading all 33 MB -- and goes on to the next
+        # step: the sharded upload + NCCL all-gather of step i+1 overlaps the read-back of step i.  Two frames in turn.
+        from multiprocessing import resource_tracker, shared_memory
+        names = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=2 * h * w * 4)
+            names = [shm.name]
+        dist.broadcast_object_list(names, 0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=names[0])
+            try:
+                resource_tracker.unregister(shm._name, "shared_memory")      # rank 0 owns the segment
+            except Exception:
+                pass
+        host = np.ndarray((2, h * w), dtype=np.uint32, buffer=shm.buf)
+        rc = torch.cuda.cudart().cudaHostRegister(host.ctypes.data, 2 * h * w * 4, 0)
+        assert int(rc) == 0, f"cudaHostRegister failed ({rc})"
+
+        def e2e_step(k=0):
+            if not is_c3:
+                L.glBindBuffer(GL_ARRAY_BUFFER, vbo)
+                if vbo_dev is not None:
+                    part = nbytes // world
+                    L.glBufferSubData(GL_ARRAY_BUFFER, rank * part, part, pinned_in.data_ptr() + rank * part)
+                    dist.all_gather_into_tensor(vbo_dev, vbo_dev[rank * part:(rank + 1) * part])
+                    torch.cuda.current_stream().synchronize()
+                else:
+                    L.glBufferData(GL_ARRAY_BUFFER, nbytes, pinned_in.data_ptr(), GL_STATIC_DRAW)
+            frame()
+            if y1 > y0:
+                L.mtglReadColorAsync(y0, y1, host[k & 1].ctypes.data)
+
+        e2e_step(); e2e_step(1)
+        sync_all()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_step(k)
+        L.glFinish()
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        host[0].fill(0)                                         # the check below must see this frame, not an earlier one
+        sync_all()
+        e2e_step(0); L.glFinish(); sync_all()
+        if rank == 0:
+            host_frame = host[0].copy()
+        sync_all()
+        torch.cuda.cudart().cudaHostUnregister(host.ctypes.data)
+        del host
+        shm.close()
+        if rank == 0:
+            shm.unlink()
+    elif pipelined_e2e:
         outs = [pinned_out, torch.empty_like(pinned_out).pin_memory()]
 
         def e2e_step(k=0):
@@ -595,6 +651,8 @@ def measure(sess, workload, primary):
             want = np.empty(h * w, dtype=np.uint32)
             assert L.mtgl_dev_read_framebuffer(dev, 0, h, want.ctypes.data, None, None) == 0
             gather_check = "bit-identical to a single-GPU render" if np.array_equal(got, want) else f"MISMATCH in {int((got != want).sum())} pixels"
+            if host_gather:
+                host_gather_check = "bit-identical to a single-GPU render" if np.array_equal(host_frame, want) else f"MISMATCH in {int((host_frame != want).sum())} pixels"
             assembled = got
         sync_all()
 
@@ -666,10 +724,13 @@ def measure(sess, workload, primary):
         "frames_per_s": 1e3 / ms_per_step, "triangles_per_s": cnt["vertices"] / 3 * 1e3 / ms_per_step,
         "config": workload_config(workload, world),
         "multi_gpu": None if world == 1 else {"gather": "fused NVLink peer-store gather + frame-barrier kernel" if peer else "NCCL send/recv gather",
-                                              "band_rows": bounds, "band_balance": balance_log, "gather_check": gather_check},
+                                              "band_rows": bounds, "band_balance": balance_log, "gather_check": gather_check,
+                                              "host_gather_check": host_gather_check},
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3 / args.steps,
-                "mode": "pipelined across frames (mtglBufferDataPinned / mtglReadColorAsync)" if (world == 1 and not args.serial_e2e) else "upload, render, read-back in sequence"},
+                "mode": ("pipelined across frames (mtglBufferDataPinned / mtglReadColorAsync)" if (world == 1 and not args.serial_e2e) else
+                         "sharded upload + NCCL all-gather, every rank reads its band back into one shared page-locked frame (mtglReadColorAsync)" if host_gather else
+                         "upload, render, read-back in sequence")},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": groups[gi], "bound": "hbm", "achieved": achieved, "peak": bw, "unit": "GB/s",

@@ -183,7 +183,8 @@ struct DevCounters {
     unsigned int triangles_in;
     unsigned int overflow;
     unsigned int culled_chunks;  /* 256-triangle chunks dropped by the culling pass (k_cull.cu) */
-    unsigned int pad_[2];
+    unsigned int scan_ticket;    /* CTAs of k_bin_scan that have finished counting: the last one scans */
+    unsigned int pad_[1];
 };
 
 struct Color4 { float r, g, b, a; };
@@ -460,7 +461,6 @@ void launch_vertex_stage(const BatchDev &b, cudaStream_t s);
 void launch_setup(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_chunk_bounds(const uint8_t *pos, uint32_t stride, uint32_t size, int32_t first, uint32_t nverts, float4 *out, cudaStream_t s);
 void launch_chunk_cull(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
-void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s);
 /* which raster kernels a pass needs, decided on the host from the raster states its draws use */
@@ -485,7 +485,7 @@ void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const Clear
 void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);
 void launch_read_pixels(const FrameTargets &fb, int32_t x, int32_t y, int32_t w, int32_t h, uint32_t bpp, uint8_t *dst, cudaStream_t s);
 void launch_frame_barrier(unsigned long long *counter, unsigned long long target, cudaStream_t s);
-void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s);
+void launch_upload(const void *host_mapped, void *dst, size_t bytes, void *zero, size_t zero_bytes, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_tex_f4(const uint32_t *l0, int n0, const uint32_t *l1, int n1, float4 *out, const float *unorm8, cudaStream_t s);
 void launch_fill_unorm8(float *table, cudaStream_t s);

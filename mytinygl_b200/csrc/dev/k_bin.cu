@@ -146,11 +146,6 @@ __device__ __forceinline__ void bin_large(const BatchDev &b, const FrameTargets 
 
 constexpr uint32_t BIN_SMALL_BLOCKS = 148 * 8, BIN_LARGE_BLOCKS = 148 * 4;
 
-/* pass 0 for the cooperative binner alone (the count pass of the small records is fused into k_setup) */
-__global__ void __launch_bounds__(128) k_bin_large_count(BatchDev b, FrameTargets fb)
-{
-    bin_large<0>(b, fb, blockIdx.x, gridDim.x);
-}
 
 /* pass 1, one launch: the first BIN_SMALL_BLOCKS CTAs fill in the records that touch at most LARGE_TILES tiles, the
  * rest go through the list of large records together */
@@ -161,17 +156,28 @@ __global__ void __launch_bounds__(256) k_bin_fill(BatchDev b, FrameTargets fb)
     else bin_large<1>(b, fb, blockIdx.x - BIN_SMALL_BLOCKS, BIN_LARGE_BLOCKS);
 }
 
-/* exclusive scan of the per-tile counts (one CTA; at most 256x256 tiles for a 16384^2 framebuffer) */
-__global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
+/* One launch for the two steps between set-up and the fill pass:
+ *   count  references of the LARGE records per tile (the cooperative binner's pass 0; the count pass of the small records
+ *          is fused into k_setup), all CTAs;
+ *   scan   exclusive scan of the per-tile counts + the launch order of the tile kernels, by the CTA that finishes its
+ *          share of the counting last (ticket in DevCounters: no second launch, no idle GPU in between).
+ * At most 256x256 tiles for a 16384^2 framebuffer. */
+__global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, FrameTargets fb, uint32_t ntiles)
 {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ uint32_t ticket;
+    bin_large<0>(b, fb, blockIdx.x, gridDim.x);
+    __threadfence();                    /* this CTA's counts are visible before its ticket is */
     __syncthreads();
+    if (threadIdx.x == 0) { ticket = atomicAdd(&b.counters->scan_ticket, 1u); carry = 0; }
+    __syncthreads();
+    if (ticket != gridDim.x - 1u) return;
+    __threadfence();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
         uint32_t i = base + threadIdx.x;
-        uint32_t v = (i < ntiles) ? b.tile_count[i] : 0u;
+        uint32_t v = (i < ntiles) ? __ldcg(&b.tile_count[i]) : 0u;
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -201,7 +207,10 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
         /* the host sizes the reference lists from these: written straight into its pinned, device-mapped copy (a
          * device-to-host memcpy here costs a compute -> copy-engine -> compute round trip of ~17 us in mid-frame) */
         if (b.host_counters) {
-            DevCounters c = *b.counters;
+            DevCounters c;
+            c.records = __ldcg(&b.counters->records); c.large_count = __ldcg(&b.counters->large_count);
+            c.triangles_in = __ldcg(&b.counters->triangles_in); c.overflow = __ldcg(&b.counters->overflow);
+            c.culled_chunks = __ldcg(&b.counters->culled_chunks); c.scan_ticket = 0u; c.pad_[0] = 0u;
             c.tile_refs = carry;
             *b.host_counters = c;
             __threadfence_system();
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
     if (threadIdx.x == 0) maxc = 0;
     __syncthreads();
     uint32_t m = 0;
-    for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) m = max(m, b.tile_count[i]);
+    for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) m = max(m, __ldcg(&b.tile_count[i]));
     m = __reduce_max_sync(0xFFFFFFFFu, m);
     if (lane == 0 && m) atomicMax(&maxc, m);
     __syncthreads();
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
     const uint32_t w_begin = min(warp * per_warp, ntiles), w_end = min(w_begin + per_warp, ntiles);
     for (uint32_t i0 = w_begin; i0 < w_end; i0 += 32) {
         const uint32_t i = i0 + lane;
-        if (i < w_end) atomicAdd(&hist[(63u - (uint32_t)(((unsigned long long)b.tile_count[i] * 64ull) / span)) * 32u + warp], 1u);
+        if (i < w_end) atomicAdd(&hist[(63u - (uint32_t)(((unsigned long long)__ldcg(&b.tile_count[i]) * 64ull) / span)) * 32u + warp], 1u);
     }
     __syncthreads();
     {   /* exclusive scan of the 2048 counters, two per thread */
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
         const bool on = i < w_end;
         const uint32_t act = __ballot_sync(0xFFFFFFFFu, on);
         if (on) {
-            const uint32_t bucket = 63u - (uint32_t)(((unsigned long long)b.tile_count[i] * 64ull) / span);
+            const uint32_t bucket = 63u - (uint32_t)(((unsigned long long)__ldcg(&b.tile_count[i]) * 64ull) / span);
             const uint32_t peers = __match_any_sync(act, bucket);
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
@@ -276,15 +285,9 @@ __global__ void __launch_bounds__(1024) k_bin_scan(BatchDev b, uint32_t ntiles)
     }
 }
 
-void launch_bin_count(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
-{
-    k_bin_large_count<<<BIN_LARGE_BLOCKS, 128, 0, s>>>(b, fb);
-    note_launch();
-}
-
 void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 {
-    k_bin_scan<<<1, 1024, 0, s>>>(b, (uint32_t)(fb.tiles_x * fb.tile_rows));
+    k_bin_scan<<<148, 1024, 0, s>>>(b, fb, (uint32_t)(fb.tiles_x * fb.tile_rows));      /* one CTA per SM counts; the last one scans */
     note_launch();
 }
 

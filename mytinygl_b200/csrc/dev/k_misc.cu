@@ -54,16 +54,20 @@ void launch_tex_f4(const uint32_t *l0, int n0, const uint32_t *l1, int n1, float
 /* Small batch arenas (state blocks, draw records: a few KB) are pulled over PCIe by a kernel reading the pinned,
  * device-mapped staging buffer instead of a DMA: a host-to-device memcpy between two frames' kernels costs a
  * compute -> copy-engine -> compute round trip, several times the transfer itself. */
-__global__ void __launch_bounds__(256) k_upload(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint32_t n16)
+__global__ void __launch_bounds__(256) k_upload(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint32_t n16, uint4 *__restrict__ zero, uint32_t z16)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    /* the tables a pass starts from zero (counters, per-tile counts and flags), in the same launch */
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < z16; i += gridDim.x * blockDim.x) zero[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-void launch_upload(const void *host_mapped, void *dst, size_t bytes, cudaStream_t s)
+/* zero / zero_bytes (a multiple of 16, may be 0): cleared by the same kernel */
+void launch_upload(const void *host_mapped, void *dst, size_t bytes, void *zero, size_t zero_bytes, cudaStream_t s)
 {
-    const uint32_t n16 = (uint32_t)((bytes + 15) / 16);
-    if (!n16) return;
-    k_upload<<<min((n16 + 255u) / 256u, 148u * 4u), 256, 0, s>>>(static_cast<const uint4 *>(host_mapped), static_cast<uint4 *>(dst), n16);
+    const uint32_t n16 = (uint32_t)((bytes + 15) / 16), z16 = (uint32_t)(zero_bytes / 16);
+    if (!n16 && !z16) return;
+    k_upload<<<min((max(n16, z16) + 255u) / 256u, 148u * 4u), 256, 0, s>>>(static_cast<const uint4 *>(host_mapped), static_cast<uint4 *>(dst), n16,
+                                                                           static_cast<uint4 *>(zero), z16);
     note_launch();
 }
 

@@ -795,8 +795,18 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     }
     /* the pinned staging buffer is device-mapped (unified addressing): small arenas are read by a kernel, large ones
      * (immediate-mode batches with millions of staged vertices) go through the copy engine.  Sizes are multiples of 256. */
-    if (arena_total <= kKernelUploadMax) launch_upload(hp, dp, arena_total, d->stream);
-    else CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
+    /* the tables the (first) pass starts from zero are cleared by the same kernel: one launch less per frame */
+    bool zeroed_by_upload = false;
+    if (arena_total <= kKernelUploadMax) {
+        void *zero = nullptr;
+        size_t zero_bytes = 0;
+        if (!infos.empty() && infos[0].n_triangles > 0 && ntiles > 0) {
+            if ((rc = reserve(d, d->tile_count, 256 + (size_t)ntiles * 8))) return rc;
+            zero = d->tile_count.ptr; zero_bytes = align_up(256 + (size_t)ntiles * 8, 16);
+            zeroed_by_upload = true;
+        }
+        launch_upload(hp, dp, arena_total, zero, zero_bytes, d->stream);
+    } else CU(cudaMemcpyAsync(dp, hp, arena_total, cudaMemcpyHostToDevice, d->stream));
     CU(cudaEventRecord(d->pinned_ev[slot], d->stream));
     t_copy = std::chrono::steady_clock::now();
 
@@ -873,13 +883,12 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.tile_order = (uint32_t *)d->tile_order.ptr;
             b.vis_plane = (uint32_t *)d->vis_plane.ptr;
 
-            CU(cudaMemsetAsync(d->tile_count.ptr, 0, 256 + (size_t)ntiles * 8, d->stream));
+            if (!(pidx == 0 && zeroed_by_upload)) CU(cudaMemsetAsync(d->tile_count.ptr, 0, 256 + (size_t)ntiles * 8, d->stream));
             launch_vertex_stage(b, d->stream);
             launch_chunk_cull(b, fb, d->stream);
             CU(cudaEventRecord(sev[1], d->stream));
             launch_setup(b, fb, d->stream);
             CU(cudaEventRecord(sev[2], d->stream));
-            launch_bin_count(b, fb, d->stream);
             launch_bin_scan(b, fb, d->stream);
             CU(cudaEventRecord(sev[3], d->stream));
             /* The list length is only known on the device.  Single-pass batches (the normal frame) run optimistically:
