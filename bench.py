@@ -405,7 +405,7 @@ def measure(sess, workload, primary):
     # the margins.  Ten untimed feedback rounds move the boundaries (16-row quantum) towards equal device time per rank;
     # the best split seen is kept.  The assembled frame is checked against a single-GPU render after the timed loops.
     balance_log = None
-    if world > 1 and not is_c3 and not args.uniform_bands:
+    if world > 1 and not args.uniform_bands:
         best = (float("inf"), list(bounds))
         balance_log = []
         for it in range(10):

@@ -506,13 +506,16 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
 
 /* ---------------------------------------------------------------- the kernel */
 template <uint32_t ON, uint32_t OFF>
-__global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t fill_mode)
+__global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t fill_mode, uint32_t split)
 {
     extern __shared__ __align__(16) unsigned char fill_smem_raw[];
     FillSmem &sm = *reinterpret_cast<FillSmem *>(fill_smem_raw);
     if (!lists_fit(b) || !b.tile_count) return;
 
-    const uint32_t tile = b.tile_order ? b.tile_order[blockIdx.x] : blockIdx.x;
+    /* split CTAs per tile, TILE_H / split rows each: a grid below one wave (the band of a multi-GPU frame) lasts as long
+     * as its heaviest tile, so there the tile is cut into up to eight slices that sort and prepare the same list */
+    const uint32_t slot = blockIdx.x / split, sub = blockIdx.x % split;
+    const uint32_t tile = b.tile_order ? b.tile_order[slot] : slot;
     const int tx = (int)(tile % (uint32_t)fb.tiles_x), ty = (int)(tile / (uint32_t)fb.tiles_x) + fb.tile_y0;
     const int px0 = tx << TILE_LOG, py0t = ty << TILE_LOG;
     const int py0 = max(py0t, fb.band_y0);          /* row 0 of the tile's coordinate system: its first row inside the band */
@@ -564,7 +567,8 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
             prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu, px0, py0);
         __syncthreads();
 
-        for (int g = 0; g < TILE_H / 8; g++) {
+        const int g_per = (TILE_H / 8) / (int)split;
+        for (int g = (int)sub * g_per; g < ((int)sub + 1) * g_per; g++) {
             const int Y = g * 8 + warp;
             if (Y >= vh) break;
             const size_t rowp = (size_t)(py0 + Y) * fb.width + px0;
@@ -629,11 +633,12 @@ void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear
     }
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0 || fill_mode == FILL_OFF) return;
+    const uint32_t split = small_grid(tiles) ? 4u : 1u;     /* (1, 2, 4 or 8: the tile is walked in eight passes of eight rows) */
     /* all_on / any_on: AND / OR of the RasterCfg flags of the pass's in-order states */
     if ((all_on & FILL_FAST_ON) == FILL_FAST_ON && (any_on & FILL_FAST_OFF) == 0u)
-        k_fill<FILL_FAST_ON, FILL_FAST_OFF><<<tiles, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode);
+        k_fill<FILL_FAST_ON, FILL_FAST_OFF><<<tiles * split, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode, split);
     else
-        k_fill<0u, 0u><<<tiles, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode);
+        k_fill<0u, 0u><<<tiles * split, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode, split);
     note_launch();
 }
 

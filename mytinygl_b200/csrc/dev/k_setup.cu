@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         fastd.valid = 0;
         if (t0 < b.n_triangles) {
             const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
-            fast_draw_init(fastd, b.states, b.draws[d0], d0, b.draw_tbase[d0], b.draw_tbase[d0 + 1]);
+            fast_draw_init(fastd, b.states, b.draws[d0], d0, b.draw_tbase[d0], b.draw_tbase[d0] + b.draws[d0].ntris);
         }
     }
     for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) sm.vcache[i] = 0xFFFFFFFFu;
@@ -820,8 +820,14 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     VertexSrc src = { b.v_clip, b.v_color, b.v_tex, b.v_epos, b.v_enrm, b.unorm8, b.need_eye ? 1 : 0, b.staged, b.states, nullptr, 0u };
     const BinOut bin = { b.records, b.bin_rows, b.tile_count, b.tile_flags, b.large_list, b.counters, fb.tiles_x, fb.tile_y0 };
 
+    uint32_t d = 0;
     if (valid) {
-        uint32_t d = (b.n_draws == 1) ? 0u : (fast_t ? fastd.draw : find_draw_tri(b.draw_tbase, b.n_draws, t));
+        d = (b.n_draws == 1) ? 0u : (fast_t ? fastd.draw : find_draw_tri(b.draw_tbase, b.n_draws, t));
+        /* large draws start on a chunk boundary (mtgl_dev.cu): the slots between a draw's last triangle and the next
+         * boundary hold nothing */
+        if (t - __ldg(b.draw_tbase + d) >= b.draws[d].ntris) d = 0xFFFFFFFFu;
+    }
+    if (d != 0xFFFFFFFFu && valid) {
         const DevDraw &dr = b.draws[d];
         const uint32_t k = t - dr.tbase, n = dr.count;
         state_index = dr.raster_state;

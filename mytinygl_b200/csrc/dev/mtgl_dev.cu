@@ -59,7 +59,7 @@ struct BoundsEntry {
 };
 constexpr uint32_t kCullZeroStreak = 4, kCullSkipBatches = 60;
 constexpr size_t kBoundsEntries = 8;
-constexpr uint32_t kBoundsMinTriangles = 4 * SETUP_THREADS;    /* smaller draws are not worth a culling pass */
+constexpr uint32_t kBoundsMinTriangles = 2 * SETUP_THREADS;    /* smaller draws are not worth a culling pass (and do not own their chunks) */
 
 } // namespace
 
@@ -740,7 +740,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
     const size_t o_staged = off; if (bt->n_vertices) std::memcpy(hp + off, bt->vertices, (size_t)bt->n_vertices * sizeof(mtgl_in_vertex)); off += sz_staged;
     const size_t o_blob = off; if (bt->blob_size) std::memcpy(hp + off, bt->blob, (size_t)bt->blob_size); off += sz_blob;
 
-    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles, n_unfused; bool any_bounds; };
+    struct PassInfo { size_t o_draws, o_vbase, o_tbase; uint32_t n_draws, n_vertices, n_triangles, n_unfused, real_triangles; bool any_bounds; };
     static const bool fuse_triangles = std::getenv("MTGL_NO_FUSE") == nullptr;     /* A/B switch for profiling */
     const bool share_indexed = std::getenv("MTGL_NO_SHARED_VERTS") == nullptr;      /* A/B switch (read per batch: the tests flip it) */
     std::vector<PassInfo> infos;
@@ -753,6 +753,11 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         uint32_t *vb = reinterpret_cast<uint32_t *>(hp + pi.o_vbase), *tb = reinterpret_cast<uint32_t *>(hp + pi.o_tbase);
         uint32_t v = 0, t = 0, k = 0, unfused = 0;
         for (const PassDraw &q : p) {
+            /* a draw of several chunks starts on a chunk boundary and leaves the rest of its last chunk empty, so that no
+             * 256-triangle chunk of k_setup mixes two such draws (one fast attribute path, one state block, one set of chunk
+             * boxes per CTA): many draws of one mesh under changing matrices cost a few idle slots instead of the slow path */
+            const bool own_chunks = q.tri_count >= 2u * SETUP_THREADS;
+            if (own_chunks) t = (uint32_t)align_up(t, SETUP_THREADS);
             if (draws[q.draw].bounds) pi.any_bounds = true;
             DevDraw o = draws[q.draw];
             const mtgl_draw &s = bt->draws[q.draw];
@@ -788,6 +793,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             vb[k] = v; tb[k] = t;
             pd[k++] = o;
             v += o.shared_verts ? o.shared_verts + 1u : o.count; t += q.tri_count;
+            pi.real_triangles += q.tri_count;
+            if (own_chunks) t = (uint32_t)align_up(t, SETUP_THREADS);
         }
         vb[k] = v; tb[k] = t;
         pi.n_draws = k; pi.n_vertices = v; pi.n_triangles = t; pi.n_unfused = unfused;
@@ -965,7 +972,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
                     CU(cudaEventRecord(sev[5], d->stream));
                 }
             }
-            tot_v += pi.n_vertices; tot_t += pi.n_triangles; tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs;
+            tot_v += pi.n_vertices; tot_t += pi.real_triangles; tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs;
             tot_culled += d->h_counters->culled_chunks;
         }
     }

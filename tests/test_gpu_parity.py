@@ -126,10 +126,12 @@ def test_chunk_culling_engages(b200):
 
 @pytest.mark.parametrize("shape", ["small", "large"])
 @pytest.mark.parametrize("case", [("c1_suzanne", 800, 600, 0), ("c4_grid", 960, 540, 6 | (4 << 8)), ("c4_grid", 480, 270, 3 | (2 << 8) | (1 << 16)),
-                                  ("depth_order", 517, 389, 1), ("cull", 480, 270, 1), ("c2_cube", 1920, 1080, 0)], ids=case_id)
+                                  ("depth_order", 517, 389, 1), ("cull", 480, 270, 1), ("c2_cube", 1920, 1080, 0),
+                                  ("c3_fill", 640, 360, 9), ("blend", 320, 240, 3), ("stencil", 300, 200, 1), ("c2_texenv", 320, 240, 3)], ids=case_id)
 def test_tile_kernel_shapes(b200, front_oracle, case, shape, monkeypatch):
-    """The deferred tile kernels come in a throughput shape (k_vis<256>, k_shade<1>: grids of several waves) and a latency
-    shape (k_vis<512>, k_shade<4>: the band of a multi-GPU frame).  Both must give the same frame at any grid size."""
+    """The tile kernels come in a throughput shape (k_vis<256>, one k_shade / k_fill CTA per tile: grids of several waves)
+    and a latency shape (k_vis<512>, four k_shade / k_fill CTAs per tile: the band of a multi-GPU frame).  Both must give
+    the same frame at any grid size."""
     monkeypatch.setenv("MTGL_GRID_SHAPE", shape)
     got = b200.render(*case)
     assert_gate(compare_planes(front_oracle.render(*case), got), case_id(case))
