@@ -348,7 +348,10 @@ def measure(sess, workload, primary):
     # Fused gather (default for N > 1): rank 0 exports its colour plane over CUDA IPC, the other ranks map it and their
     # raster kernels store every colour of their band straight into it over NVLink (mtgl_dev_set_present_target);
     # what is left of the gather is the frame-barrier kernel.
-    peer = world > 1 and args.gather == "peer"
+    peer = world > 1 and args.gather in ("peer", "copy")
+    if world > 1 and args.gather == "copy":     # bands pushed by an asynchronous peer-to-peer copy behind each frame (MTGL_PRESENT_COPY)
+        L.mtgl_dev_set_present_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        assert L.mtgl_dev_set_present_mode(dev, 1) == 0
     if peer:
         hbuf = (ctypes.c_ubyte * 64)()
         if rank == 0:
@@ -723,7 +726,8 @@ def measure(sess, workload, primary):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": 1e3 / ms_per_step, "triangles_per_s": cnt["vertices"] / 3 * 1e3 / ms_per_step,
         "config": workload_config(workload, world),
-        "multi_gpu": None if world == 1 else {"gather": "fused NVLink peer-store gather + frame-barrier kernel" if peer else "NCCL send/recv gather",
+        "multi_gpu": None if world == 1 else {"gather": ("asynchronous NVLink peer copy per band + frame-barrier kernel on a side stream" if args.gather == "copy" else
+                                                         "fused NVLink peer-store gather + frame-barrier kernel") if peer else "NCCL send/recv gather",
                                               "band_rows": bounds, "band_balance": balance_log, "gather_check": gather_check,
                                               "host_gather_check": host_gather_check},
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -781,8 +785,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the reference-rendered parity check of each workload")
     ap.add_argument("--serial-e2e", action="store_true", help="N = 1: upload, render and read back strictly in sequence (no pipelining across frames)")
     ap.add_argument("--uniform-bands", action="store_true", help="N > 1: keep the uniform split of tile rows (no load balancing)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'nccl' = send/recv after the frame")
+    ap.add_argument("--gather", default="peer", choices=["peer", "copy", "nccl"],
+                    help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'copy' = one asynchronous "
+                         "peer-to-peer copy per band behind the frame, overlapped with the next frame's geometry, 'nccl' = send/recv after the frame")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

@@ -306,6 +306,16 @@ int mtgl_dev_plane_pointers(mtgl_dev *dev, void **color, void **depth, void **st
 #define MTGL_IPC_HANDLE_BYTES 64
 int mtgl_dev_export_color_plane(mtgl_dev *dev, void *handle_out);
 int mtgl_dev_set_present_target(mtgl_dev *dev, const void *handle);
+/* How a band reaches the presenting GPU's plane.
+ *   MTGL_PRESENT_STORES (default): fused -- every raster kernel stores its finished tiles locally AND into the mapped plane.
+ *   MTGL_PRESENT_COPY: the kernels store locally only; mtgl_dev_frame_barrier pushes the band with one asynchronous
+ *     peer-to-peer copy over NVLink on a side stream, followed there by the barrier.  The next frame's geometry and
+ *     visibility stages (which do not touch the colour plane) run meanwhile; only its colour-writing kernels wait.  This is
+ *     the better choice when the presenting GPU's NVLink ingest is the bottleneck (8 GPUs sending an 8K frame: 116 MB per
+ *     frame into one GPU), where fused stores stall the SMs that issue them. */
+#define MTGL_PRESENT_STORES 0
+#define MTGL_PRESENT_COPY   1
+int mtgl_dev_set_present_mode(mtgl_dev *dev, int mode);
 
 /* Pixel rectangles.  mtgl_dev_draw_pixels replaces the loop of glDrawPixels (gl_api.c:1286-1373):
  * the rectangle is copied at call time and drawn in stream order behind every batch submitted so far -- no host

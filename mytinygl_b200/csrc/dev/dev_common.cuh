@@ -473,6 +473,8 @@ struct RasterPlan {
     bool unordered_range01;     /* every unordered state has depth range [0,1] */
     uint32_t fill_mode;         /* FILL_* (dev_fill.cuh): may the pixel-owner kernel (k_fill.cu) take in-order tiles of large triangles */
     uint32_t in_order_all, in_order_any;    /* AND / OR of the RasterCfg flags of the pass's in-order states */
+    cudaEvent_t color_gate;     /* the kernels that write the colour plane wait for this event first (MTGL_PRESENT_COPY: the previous
+                                 * frame's band is still being copied out of the plane), or NULL */
 };
 /* ev_vis / ev_shade are recorded after the visibility kernels and after the shade kernel (stage timing) */
 void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t plane_rw_mask,

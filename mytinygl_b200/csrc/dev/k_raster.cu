@@ -799,6 +799,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
             note_launch();
         }
         cudaEventRecord(ev_vis, s);
+        if (plan.color_gate) cudaStreamWaitEvent(s, plan.color_gate, 0);       /* visibility above ran ahead; colour waits */
         if (planes & 1u) launch_shade(b, fb, clear, s);
         cudaEventRecord(ev_shade, s);
         if (any_in_order) {
@@ -807,6 +808,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
             launch_fill(b, fb, clear, planes, plan.fill_mode, plan.in_order_all, plan.in_order_any, s);
         }
     } else {
+        if (plan.color_gate) cudaStreamWaitEvent(s, plan.color_gate, 0);
         cudaEventRecord(ev_vis, s);
         cudaEventRecord(ev_shade, s);
         if (plan.plain_in_order) k_raster<false, true><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 0u, plan.fill_mode);

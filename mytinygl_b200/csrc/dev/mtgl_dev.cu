@@ -104,6 +104,12 @@ struct mtgl_dev {
     unsigned long long barrier_epoch = 0;   /* frame barriers this context has taken part in since the plane was exported / mapped */
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
+    /* MTGL_PRESENT_COPY: band pushed to the presenting GPU by an asynchronous copy + barrier on a side stream */
+    int present_mode = MTGL_PRESENT_STORES;
+    cudaStream_t present_stream = nullptr;
+    cudaEvent_t present_ev = nullptr, raster_ev = nullptr;
+    bool present_busy = false;          /* a push is in flight: colour writers and readers wait for present_ev */
+
     /* pipelined transfers (mtgl_dev_buffer_data_pinned / mtgl_dev_read_color_async) */
     cudaStream_t upload_stream = nullptr, readback_stream = nullptr;
     cudaEvent_t upload_ev = nullptr, readback_ev = nullptr, render_ev = nullptr;
@@ -138,8 +144,17 @@ int order_after_transfers(mtgl_dev *d)
     return MTGL_OK;
 }
 
+/* work queued on the main stream from here on sees the plane after the band push / frame barrier in flight on the side stream */
+int order_after_present(mtgl_dev *d)
+{
+    if (d->present_busy) { CU(cudaStreamWaitEvent(d->stream, d->present_ev, 0)); d->present_busy = false; }
+    return MTGL_OK;
+}
+
 int sync_all_streams(mtgl_dev *d)
 {
+    if (d->present_stream) CU(cudaStreamSynchronize(d->present_stream));
+    d->present_busy = false;
     if (d->upload_stream) CU(cudaStreamSynchronize(d->upload_stream));
     CU(cudaStreamSynchronize(d->stream));
     if (d->readback_stream) CU(cudaStreamSynchronize(d->readback_stream));
@@ -247,7 +262,7 @@ FrameTargets frame_targets(const mtgl_dev *d)
 {
     FrameTargets fb;
     fb.color = d->color; fb.depth = d->depth; fb.stencil = d->stencil;
-    fb.present = d->present;
+    fb.present = d->present_mode == MTGL_PRESENT_STORES ? d->present : nullptr;
     fb.width = d->width; fb.height = d->height;
     fb.band_y0 = d->band_y0; fb.band_y1 = d->band_y1;
     fb.tiles_x = (d->width + TILE_W - 1) / TILE_W;
@@ -372,6 +387,9 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
         if (ce == cudaSuccess) ce = cudaEventCreate(&es.stop);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->counters_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->present_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->present_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->raster_ev, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->upload_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->readback_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&d->upload_ev, cudaEventDisableTiming);
@@ -394,6 +412,9 @@ void mtgl_dev_destroy(mtgl_dev *d)
     if (d->upload_stream) cudaStreamSynchronize(d->upload_stream);
     if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->readback_stream) cudaStreamSynchronize(d->readback_stream);
+    if (d->present_stream) { cudaStreamSynchronize(d->present_stream); cudaStreamDestroy(d->present_stream); }
+    if (d->present_ev) cudaEventDestroy(d->present_ev);
+    if (d->raster_ev) cudaEventDestroy(d->raster_ev);
     for (mtgl_dev::Orphan &o : d->orphans) { if (o.ptr) cudaFree(o.ptr); if (o.ev) cudaEventDestroy(o.ev); }
     if (d->upload_stream) cudaStreamDestroy(d->upload_stream);
     if (d->readback_stream) cudaStreamDestroy(d->readback_stream);
@@ -511,6 +532,7 @@ int mtgl_dev_read_color_async(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *col
     CU(cudaSetDevice(d->device));
     const size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
+    if (int prc = order_after_present(d)) return prc;
     CU(cudaEventRecord(d->render_ev, d->stream));
     CU(cudaStreamWaitEvent(d->readback_stream, d->render_ev, 0));
     CU(cudaMemcpyAsync(color + o, d->color + o, n * 4, cudaMemcpyDeviceToHost, d->readback_stream));
@@ -947,6 +969,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         plan.plain_in_order = any_in_order && !any_not_plain;
         plan.unordered_func = unordered_func;
         plan.unordered_range01 = unordered_range01;
+        plan.color_gate = nullptr;
+        if (d->present_busy) { plan.color_gate = d->present_ev; d->present_busy = false; }      /* (the stream waits inside launch_raster) */
         /* the pixel-owner kernel for in-order tiles of large triangles (k_fill.cu); it has no per-fragment lighting.
          * MTGL_FILL=never|always: A/B switch for profiling and tests (always: every eligible in-order tile, whatever its triangles' size) */
         uint32_t fill_env = FILL_AUTO;       /* read per batch (not cached): the tests switch it between frames */
@@ -1002,6 +1026,7 @@ int mtgl_dev_read_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *col
     CU(cudaSetDevice(d->device));
     size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
+    if (int prc = order_after_present(d)) return prc;
     if (color) CU(cudaMemcpyAsync(color + o, d->color + o, n * 4, cudaMemcpyDeviceToHost, d->stream));
     if (depth) CU(cudaMemcpyAsync(depth + o, d->depth + o, n * 4, cudaMemcpyDeviceToHost, d->stream));
     if (stencil) CU(cudaMemcpyAsync(stencil + o, d->stencil + o, n, cudaMemcpyDeviceToHost, d->stream));
@@ -1016,6 +1041,7 @@ int mtgl_dev_write_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, const uint32
     size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
     if (int orc = order_after_transfers(d)) return orc;
+    if (int prc = order_after_present(d)) return prc;
     if (color) CU(cudaMemcpyAsync(d->color + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
     if (color && d->present) CU(cudaMemcpyAsync(d->present + o, color + o, n * 4, cudaMemcpyHostToDevice, d->stream));
     if (depth) CU(cudaMemcpyAsync(d->depth + o, depth + o, n * 4, cudaMemcpyHostToDevice, d->stream));
@@ -1064,6 +1090,15 @@ int mtgl_dev_set_present_target(mtgl_dev *d, const void *handle)
     return MTGL_OK;
 }
 
+int mtgl_dev_set_present_mode(mtgl_dev *d, int mode)
+{
+    if (!d || (mode != MTGL_PRESENT_STORES && mode != MTGL_PRESENT_COPY)) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    if (int rc = sync_all_streams(d)) return rc;
+    d->present_mode = mode;
+    return MTGL_OK;
+}
+
 static uint32_t pixel_bpp(uint32_t format)
 {
     switch (format) {
@@ -1082,6 +1117,7 @@ int mtgl_dev_draw_pixels(mtgl_dev *d, const mtgl_pixel_rect *rect, const void *p
     if (bpp == 0 || rect->width <= 0 || rect->height <= 0) return MTGL_OK;       /* gl_api.c:1336-1338: unknown formats draw nothing */
     CU(cudaSetDevice(d->device));
     if (int orc = order_after_transfers(d)) return orc;
+    if (int prc = order_after_present(d)) return prc;
     /* Only the part of the rectangle that lands on this device's rows and inside the framebuffer's columns is staged and
      * launched (the reference skips the other pixels one by one, gl_api.c:1304-1312): rectangle row r lands on
      * framebuffer row height - 1 - (y + r), column c on x + c. */
@@ -1111,6 +1147,7 @@ int mtgl_dev_read_pixels(mtgl_dev *d, int32_t x, int32_t y, int32_t width, int32
     const uint32_t bpp = (format == 0x1908) ? 4u : (format == 0x1907 ? 3u : 0u);
     if (bpp == 0 || width <= 0 || height <= 0) return MTGL_OK;                   /* other formats leave 'out' untouched */
     CU(cudaSetDevice(d->device));
+    if (int prc = order_after_present(d)) return prc;
     /* rows outside the framebuffer read as zeros, columns outside it as (0, 0, 0, 255) (gl_api.c:1193-1214): filled on
      * the host; only the visible part of the rectangle is gathered on the device and crosses PCIe */
     const int64_t r_lo = std::max<int64_t>(0, -(int64_t)y), r_hi = std::min<int64_t>(height, (int64_t)d->height - y);
@@ -1147,7 +1184,20 @@ int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants)
     uint32_t *plane = d->present ? d->present : d->color;
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>((uint8_t *)plane + barrier_offset((size_t)d->width * d->height));
     d->barrier_epoch++;
-    launch_frame_barrier(ctr, d->barrier_epoch * participants, d->stream);
+    if (d->present_mode == MTGL_PRESENT_COPY) {
+        /* behind this frame's raster kernels, on the side stream: push the band (peer-to-peer copy over NVLink), then the
+         * barrier.  The main stream goes on with the next frame's geometry and visibility; its colour writers wait. */
+        if (int orc = order_after_present(d)) return orc;       /* (two barriers without a frame in between) */
+        CU(cudaEventRecord(d->raster_ev, d->stream));
+        CU(cudaStreamWaitEvent(d->present_stream, d->raster_ev, 0));
+        if (d->present && d->band_y1 > d->band_y0) {
+            const size_t o = (size_t)d->band_y0 * d->width, n = (size_t)(d->band_y1 - d->band_y0) * d->width;
+            CU(cudaMemcpyAsync(d->present + o, d->color + o, n * 4, cudaMemcpyDeviceToDevice, d->present_stream));
+        }
+        launch_frame_barrier(ctr, d->barrier_epoch * participants, d->present_stream);
+        CU(cudaEventRecord(d->present_ev, d->present_stream));
+        d->present_busy = true;
+    } else launch_frame_barrier(ctr, d->barrier_epoch * participants, d->stream);
     CU(cudaGetLastError());
     return MTGL_OK;
 }
@@ -1171,6 +1221,7 @@ int mtgl_dev_timer_mark(mtgl_dev *d, int which)
 {
     if (!d || which < 0 || which > 1) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc = order_after_present(d)) return prc;           /* a band push in flight belongs to the time before the mark */
     CU(cudaEventRecord(d->mark_ev[which], d->stream));
     return MTGL_OK;
 }

@@ -1342,6 +1342,7 @@ int mtgl_dev_read_pixels(mtgl_dev *d, int32_t x, int32_t y, int32_t width, int32
 }
 
 void *mtgl_dev_stream(mtgl_dev *d) { (void)d; return NULL; }
+int mtgl_dev_set_present_mode(mtgl_dev *d, int mode) { (void)mode; return d ? MTGL_OK : MTGL_E_INVALID; }
 int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants) { (void)d; return participants == 1 ? MTGL_OK : MTGL_E_INVALID; }   /* no device, no stream */
 
 int mtgl_dev_timer_mark(mtgl_dev *d, int which)

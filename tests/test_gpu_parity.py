@@ -141,15 +141,17 @@ def test_tile_kernel_shapes(b200, front_oracle, case, shape, monkeypatch):
         assert np.array_equal(a, b)
 
 
-def _present_child(conn, case):
+def _present_child(conn, case, mode=0):
     """second process: renders `case` with its colour stores mirrored into the parent's plane"""
     import ctypes
     from mytinygl_b200 import load_b200
     lib = load_b200()
     L = lib.lib
     L.mtgl_dev_set_present_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.mtgl_dev_set_present_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
     name, w, h, variant = case
     lib.create(w, h)
+    assert L.mtgl_dev_set_present_mode(lib.device(), mode) == 0
     handle = (ctypes.c_ubyte * 64)(*conn.recv())
     rc = L.mtgl_dev_set_present_target(lib.device(), handle)
     if rc == 0:
@@ -168,8 +170,9 @@ def _present_child(conn, case):
     lib.destroy()
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["stores", "copy"])
 @pytest.mark.parametrize("case", [("c4_grid", 517, 389, 3 | (2 << 8)), ("state_churn", 517, 389, 0), ("lines", 320, 240, 19)], ids=case_id)
-def test_present_target_mirrors_color(b200, case):
+def test_present_target_mirrors_color(b200, case, mode):
     """mtgl_dev_export_color_plane / mtgl_dev_set_present_target: every colour store of a context also lands in the
     plane it was given.  Two processes on one GPU here (CUDA IPC needs two processes); bench.py --gpus N uses the same
     calls across GPUs over NVLink and checks the assembled frame against a single-GPU render."""
@@ -179,6 +182,8 @@ def test_present_target_mirrors_color(b200, case):
     L.mtgl_dev_export_color_plane.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     name, w, h, variant = case
     b200.create(w, h)
+    L.mtgl_dev_set_present_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    assert L.mtgl_dev_set_present_mode(b200.device(), mode) == 0       # 0: fused peer stores, 1: asynchronous band copy at the barrier
     L.glClearColor(ctypes.c_float(1), ctypes.c_float(0), ctypes.c_float(1), ctypes.c_float(0))
     L.glClear(0x4000)
     L.glFinish()
@@ -186,7 +191,7 @@ def test_present_target_mirrors_color(b200, case):
     assert L.mtgl_dev_export_color_plane(b200.device(), handle) == 0
     ctx = mp.get_context("spawn")
     parent, child = ctx.Pipe()
-    proc = ctx.Process(target=_present_child, args=(child, case))
+    proc = ctx.Process(target=_present_child, args=(child, case, mode))
     proc.start()
     try:
         parent.send(list(handle))
