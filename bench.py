@@ -348,8 +348,13 @@ def measure(sess, workload, primary):
     # Fused gather (default for N > 1): rank 0 exports its colour plane over CUDA IPC, the other ranks map it and their
     # raster kernels store every colour of their band straight into it over NVLink (mtgl_dev_set_present_target);
     # what is left of the gather is the frame-barrier kernel.
-    peer = world > 1 and args.gather in ("peer", "copy")
-    if world > 1 and args.gather == "copy":     # bands pushed by an asynchronous peer-to-peer copy behind each frame (MTGL_PRESENT_COPY)
+    # "auto": the fused peer stores, unless the bands entering the presenting GPU exceed 64 MB per frame (8K frames on many
+    # GPUs) -- its NVLink ingest is then the bottleneck and fused stores stall the SMs that issue them
+    gather_mode = args.gather
+    if gather_mode == "auto":
+        gather_mode = "copy" if w * h * 4 * (world - 1) / max(world, 1) > 64e6 else "peer"
+    peer = world > 1 and gather_mode in ("peer", "copy")
+    if world > 1 and gather_mode == "copy":     # bands pushed by an asynchronous peer-to-peer copy behind each frame (MTGL_PRESENT_COPY)
         L.mtgl_dev_set_present_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
         assert L.mtgl_dev_set_present_mode(dev, 1) == 0
     if peer:
@@ -726,7 +731,7 @@ def measure(sess, workload, primary):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": 1e3 / ms_per_step, "triangles_per_s": cnt["vertices"] / 3 * 1e3 / ms_per_step,
         "config": workload_config(workload, world),
-        "multi_gpu": None if world == 1 else {"gather": ("asynchronous NVLink peer copy per band + frame-barrier kernel on a side stream" if args.gather == "copy" else
+        "multi_gpu": None if world == 1 else {"gather": ("asynchronous NVLink peer copy per band + frame-barrier kernel on a side stream" if gather_mode == "copy" else
                                                          "fused NVLink peer-store gather + frame-barrier kernel") if peer else "NCCL send/recv gather",
                                               "band_rows": bounds, "band_balance": balance_log, "gather_check": gather_check,
                                               "host_gather_check": host_gather_check},
@@ -785,7 +790,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the reference-rendered parity check of each workload")
     ap.add_argument("--serial-e2e", action="store_true", help="N = 1: upload, render and read back strictly in sequence (no pipelining across frames)")
     ap.add_argument("--uniform-bands", action="store_true", help="N > 1: keep the uniform split of tile rows (no load balancing)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "copy", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "copy", "nccl"],
                     help="N > 1: 'peer' = raster kernels store into rank 0's plane over NVLink (fused), 'copy' = one asynchronous "
                          "peer-to-peer copy per band behind the frame, overlapped with the next frame's geometry, 'nccl' = send/recv after the frame")
     args = ap.parse_args()

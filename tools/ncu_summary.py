@@ -18,7 +18,8 @@ METRICS = [
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "threads/inst"),
     ("dram__bytes_read.sum", "dram_read"),
     ("dram__bytes_write.sum", "dram_write"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_%peak"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_%peak"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_%peak"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_%"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_%"),
 ]
