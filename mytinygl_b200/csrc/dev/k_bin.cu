@@ -97,6 +97,19 @@ __device__ __forceinline__ void bin_small(const BatchDev &b, const FrameTargets 
             if (PASS == 0 && tflags) atomicOr(&b.tile_flags[tile], tflags);
             base = __shfl_sync(peers, base, leader);
             if (PASS == 1) b.tile_list[off + base + __popc(peers & lt_mask)] = r;
+        } else if (PASS == 1 && ntiles > 1 && ntiles <= 4) {
+            /* the usual multi-tile record (a triangle across a tile edge or corner): all its cursor atomics are issued
+             * before the first result is needed -- one memory round trip instead of one per tile */
+            uint32_t tl[4], off[4], at[4];
+            int n = 0;
+            for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++) tl[n++] = (uint32_t)(ty * fb.tiles_x + tx);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < n) { off[k] = __ldg(&b.tile_offset[tl[k]]); at[k] = atomicAdd(&b.tile_cursor[tl[k]], 1u); }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < n) b.tile_list[off[k] + at[k]] = r;
         } else if (ntiles > 1) {
             for (int ty = ty0; ty <= ty1; ty++)
                 for (int tx = tx0; tx <= tx1; tx++) {
@@ -144,16 +157,16 @@ __device__ __forceinline__ void bin_large(const BatchDev &b, const FrameTargets 
     }
 }
 
-constexpr uint32_t BIN_SMALL_BLOCKS = 148 * 8, BIN_LARGE_BLOCKS = 148 * 4;
+constexpr uint32_t BIN_SMALL_BLOCKS_MIN = 148 * 8, BIN_SMALL_BLOCKS_MAX = 148 * 64, BIN_LARGE_BLOCKS = 148 * 4;
 
 
 /* pass 1, one launch: the first BIN_SMALL_BLOCKS CTAs fill in the records that touch at most LARGE_TILES tiles, the
  * rest go through the list of large records together */
-__global__ void __launch_bounds__(256) k_bin_fill(BatchDev b, FrameTargets fb)
+__global__ void __launch_bounds__(256) k_bin_fill(BatchDev b, FrameTargets fb, uint32_t small_blocks)
 {
     if (!lists_fit(b)) return;
-    if (blockIdx.x < BIN_SMALL_BLOCKS) bin_small<1>(b, fb, blockIdx.x, BIN_SMALL_BLOCKS);
-    else bin_large<1>(b, fb, blockIdx.x - BIN_SMALL_BLOCKS, BIN_LARGE_BLOCKS);
+    if (blockIdx.x < small_blocks) bin_small<1>(b, fb, blockIdx.x, small_blocks);
+    else bin_large<1>(b, fb, blockIdx.x - small_blocks, BIN_LARGE_BLOCKS);
 }
 
 /* One launch for the two steps between set-up and the fill pass:
@@ -293,7 +306,11 @@ void launch_bin_scan(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 
 void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 {
-    k_bin_fill<<<BIN_SMALL_BLOCKS + BIN_LARGE_BLOCKS, 256, 0, s>>>(b, fb);
+    /* the pass is bound by the latency of its dependent memory operations (row -> cursor atomic -> store), not by
+     * throughput: enough CTAs that a thread rarely takes a second record (records ~ input triangles for meshes) */
+    const uint32_t want = (b.n_triangles + 255u) / 256u;
+    const uint32_t small_blocks = want < BIN_SMALL_BLOCKS_MIN ? BIN_SMALL_BLOCKS_MIN : (want > BIN_SMALL_BLOCKS_MAX ? BIN_SMALL_BLOCKS_MAX : want);
+    k_bin_fill<<<small_blocks + BIN_LARGE_BLOCKS, 256, 0, s>>>(b, fb, small_blocks);
     note_launch();
 }
 
