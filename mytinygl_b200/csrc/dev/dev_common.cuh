@@ -67,6 +67,22 @@ struct DevAttrib {
     uint32_t pad_;
 };
 
+/* Fast attribute path.  For a non-indexed array draw whose enabled arrays are 4-byte aligned floats and whose whole
+ * element range lies inside the buffers (checked once, attrib_range_ok), element e of an attribute is base + e * stride:
+ * no per-vertex bounds / type / alignment logic.  The values are the same loads fetch_attrib would do. */
+struct FastDraw {
+    const uint8_t *pos, *nrm, *tex;     /* element 0 of each array (NULL: array disabled) */
+    uint32_t pos_stride, nrm_stride, tex_stride;
+    uint32_t pos_size;
+    int32_t first;
+    uint32_t tri_begin, tri_end;        /* global indices of the draw's triangles in this pass */
+    uint32_t tbase;
+    uint32_t draw;                      /* index into BatchDev::draws */
+    uint32_t valid;
+    float cur_color[4], cur_normal[3], cur_texcoord[2];
+    const mtgl_state *st;
+};
+
 struct DevDraw {
     uint32_t mode, count, raster_state, source;
     uint32_t first_staged, vertex_state;
@@ -88,6 +104,7 @@ struct DevDraw {
     uint32_t state_max;      /* n_states - 1 of the batch: a staged vertex's state index is clamped to it (a stale index from a broken
                               * binding must not become an out-of-bounds read) */
     const float4 *bounds;    /* object-space boxes of the draw's 256-triangle chunks (k_cull.cu), or NULL */
+    FastDraw fast;           /* the fast attribute path of this draw in this pass, decided on the host (dev_vertex.cuh: fast_draw_init) */
 };
 
 /* Raster-stage view of one mtgl_state: enums folded to small integers, texture resolved to

@@ -153,31 +153,15 @@ __device__ __forceinline__ void fetch_vertex(const mtgl_in_vertex *staged, const
     }
 }
 
-/* Fast attribute path.  For a non-indexed array draw whose enabled arrays are 4-byte aligned floats and whose whole
- * element range lies inside the buffers (checked once, attrib_range_ok), element e of an attribute is base + e * stride:
- * no per-vertex bounds / type / alignment logic.  The values are the same loads fetch_attrib would do. */
-struct FastDraw {
-    const uint8_t *pos, *nrm, *tex;     /* element 0 of each array (NULL: array disabled) */
-    uint32_t pos_stride, nrm_stride, tex_stride;
-    uint32_t pos_size;
-    int32_t first;
-    uint32_t tri_begin, tri_end;        /* global indices of the draw's triangles in this pass */
-    uint32_t tbase;
-    uint32_t draw;                      /* index into BatchDev::draws */
-    uint32_t valid;
-    float cur_color[4], cur_normal[3], cur_texcoord[2];
-    const mtgl_state *st;
-};
-
-__device__ __forceinline__ bool attrib_range_ok(const DevAttrib &a, int32_t first, uint32_t count)
+__host__ __device__ __forceinline__ bool attrib_range_ok(const DevAttrib &a, int32_t first, uint32_t count)
 {
     if (!a.ptr || a.type != MTGL_TYPE_F32 || (((uintptr_t)a.ptr) & 3u) || (a.stride & 3u) || first < 0 || count == 0) return false;
     const uint64_t last = (uint64_t)((uint32_t)first + count - 1u) * a.stride + (uint64_t)a.size * 4u;
     return last <= a.avail;
 }
 
-/* one thread fills the descriptor for draw d; valid = 0 when the draw does not qualify */
-__device__ __forceinline__ void fast_draw_init(FastDraw &f, const mtgl_state *states, const DevDraw &dr, uint32_t d, uint32_t tri_begin, uint32_t tri_end)
+/* the descriptor of draw d (filled on the host once per draw and pass, DevDraw::fast); valid = 0 when the draw does not qualify */
+__host__ __device__ __forceinline__ void fast_draw_init(FastDraw &f, const mtgl_state *states, const DevDraw &dr, uint32_t d, uint32_t tri_begin, uint32_t tri_end)
 {
     f.valid = 0;
     f.draw = d; f.tri_begin = tri_begin; f.tri_end = tri_end; f.tbase = dr.tbase;

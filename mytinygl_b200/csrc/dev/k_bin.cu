@@ -16,6 +16,8 @@
  */
 #include "dev_common.cuh"
 
+#include <cstdlib>
+
 namespace mtgl_dev_impl {
 
 void note_launch();
@@ -101,15 +103,16 @@ __device__ __forceinline__ void bin_small(const BatchDev &b, const FrameTargets 
             /* the usual multi-tile record (a triangle across a tile edge or corner): all its cursor atomics are issued
              * before the first result is needed -- one memory round trip instead of one per tile */
             uint32_t tl[4], off[4], at[4];
-            int n = 0;
-            for (int ty = ty0; ty <= ty1; ty++)
-                for (int tx = tx0; tx <= tx1; tx++) tl[n++] = (uint32_t)(ty * fb.tiles_x + tx);
+            const int w = tx1 - tx0 + 1;            /* 1 or 2 columns when 2 <= ntiles <= 4 spans more than one row; up to 4 in one row */
+#pragma unroll
+            for (int k = 0; k < 4; k++) {           /* (static indices: the arrays stay in registers) */
+                const int row = (w == 1) ? k : ((w == 2) ? (k >> 1) : 0), col = (w == 1) ? 0 : ((w == 2) ? (k & 1) : k);
+                tl[k] = (uint32_t)((ty0 + row) * fb.tiles_x + tx0 + col);
+                if (k < ntiles) { off[k] = __ldg(&b.tile_offset[tl[k]]); at[k] = atomicAdd(&b.tile_cursor[tl[k]], 1u); }
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (k < n) { off[k] = __ldg(&b.tile_offset[tl[k]]); at[k] = atomicAdd(&b.tile_cursor[tl[k]], 1u); }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (k < n) b.tile_list[off[k] + at[k]] = r;
+                if (k < ntiles) b.tile_list[off[k] + at[k]] = r;
         } else if (ntiles > 1) {
             for (int ty = ty0; ty <= ty1; ty++)
                 for (int tx = tx0; tx <= tx1; tx++) {
@@ -308,7 +311,8 @@ void launch_bin_fill(const BatchDev &b, const FrameTargets &fb, cudaStream_t s)
 {
     /* the pass is bound by the latency of its dependent memory operations (row -> cursor atomic -> store), not by
      * throughput: enough CTAs that a thread rarely takes a second record (records ~ input triangles for meshes) */
-    const uint32_t want = (b.n_triangles + 255u) / 256u;
+    static const bool fixed_grid = std::getenv("MTGL_BIN_GRID") != nullptr;        /* A/B switch for profiling: the minimum grid */
+    const uint32_t want = fixed_grid ? 0u : (b.n_triangles + 255u) / 256u;
     const uint32_t small_blocks = want < BIN_SMALL_BLOCKS_MIN ? BIN_SMALL_BLOCKS_MIN : (want > BIN_SMALL_BLOCKS_MAX ? BIN_SMALL_BLOCKS_MAX : want);
     k_bin_fill<<<small_blocks + BIN_LARGE_BLOCKS, 256, 0, s>>>(b, fb, small_blocks);
     note_launch();

@@ -774,15 +774,14 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         return;
     }
     const uint32_t t0 = chunk * SETUP_THREADS;
-    if (threadIdx.x == 0) {
-        sm.fused_n = 0;
-        sm.shade_n = 0;
-        fastd.valid = 0;
-        if (t0 < b.n_triangles) {
-            const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
-            fast_draw_init(fastd, b.states, b.draws[d0], d0, b.draw_tbase[d0], b.draw_tbase[d0] + b.draws[d0].ntris);
-        }
-    }
+    if (threadIdx.x == 0) { sm.fused_n = 0; sm.shade_n = 0; }
+    /* the fast attribute path of the draw this chunk starts in: decided per draw on the host, copied by 28 threads (one
+     * thread walking the draw record while 255 wait cost 5 % of the kernel) */
+    if (t0 < b.n_triangles) {
+        const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
+        if (threadIdx.x < sizeof(FastDraw) / 4u)
+            reinterpret_cast<uint32_t *>(&fastd)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t *>(&b.draws[d0].fast) + threadIdx.x);
+    } else if (threadIdx.x == 0) fastd.valid = 0;
     for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) sm.vcache[i] = 0xFFFFFFFFu;
     __syncthreads();
 

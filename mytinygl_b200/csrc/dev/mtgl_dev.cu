@@ -17,6 +17,7 @@
  */
 #include "dev_common.cuh"
 #include "dev_fill.cuh"
+#include "dev_vertex.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -813,6 +814,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             o.tbase = t - q.tri_first;      /* triangle k of the draw has global index tbase + k */
             o.ntris = q.tri_count;
             vb[k] = v; tb[k] = t;
+            fast_draw_init(o.fast, reinterpret_cast<const mtgl_state *>(dp + o_states), o, k, t, t + q.tri_count);
             pd[k++] = o;
             v += o.shared_verts ? o.shared_verts + 1u : o.count; t += q.tri_count;
             pi.real_triangles += q.tri_count;
