@@ -105,6 +105,17 @@ struct mtgl_dev {
     unsigned long long barrier_epoch = 0;   /* frame barriers this context has taken part in since the plane was exported / mapped */
     cudaEvent_t mark_ev[2] = { nullptr, nullptr };
 
+    /* The optimistic check of the last single-pass batch (tile-list guess, record overflow), deferred: the host does not
+     * wait for the scan of frame i before it goes on to queue the upload of frame i+1 (resolve_pending) */
+    struct Pending {
+        bool active = false;
+        BatchDev b; FrameTargets fb; ClearOp clr; uint32_t planes = 0; RasterPlan plan;
+        cudaEvent_t sev3 = nullptr, sev4 = nullptr, sev5 = nullptr, sev6 = nullptr, sev7 = nullptr, stop = nullptr;
+        uint64_t serial = 0;
+        struct Readback { int32_t y0, y1; uint32_t *dst; };
+        std::vector<Readback> readbacks;        /* asynchronous read-backs queued behind the batch: re-issued if it has to be redone */
+    } pending;
+
     /* MTGL_PRESENT_COPY: band pushed to the presenting GPU by an asynchronous copy + barrier on a side stream */
     int present_mode = MTGL_PRESENT_STORES;
     cudaStream_t present_stream = nullptr;
@@ -174,6 +185,48 @@ int reserve(mtgl_dev *d, DevBuf &b, size_t bytes)
     b.ptr = nullptr; b.cap = 0;
     CU(cudaMalloc(&b.ptr, want));
     b.cap = want;
+    return MTGL_OK;
+}
+
+/* Settle the deferred check of the last optimistic batch.  Must run before anything else is queued on the main stream
+ * (every entry point that queues work or waits calls it): when the guessed tile-list capacity was too small the batch's
+ * fill and raster kernels have left everything untouched, and they are queued again here, in order. */
+int resolve_pending(mtgl_dev *d)
+{
+    mtgl_dev::Pending &p = d->pending;
+    if (!p.active) return MTGL_OK;
+    p.active = false;
+    CU(cudaEventSynchronize(d->counters_ev));
+    const DevCounters hc = *d->h_counters;
+    d->stats.triangles_setup = hc.records; d->stats.tile_refs = hc.tile_refs; d->stats.chunks_culled = hc.culled_chunks;
+    for (BoundsEntry &e : d->bounds) {          /* did the culling pass pay for the boxes this batch used? */
+        if (e.batch != p.serial) continue;
+        if (hc.culled_chunks != 0) e.zero_streak = 0;
+        else if (++e.zero_streak >= kCullZeroStreak) { e.zero_streak = 0; e.skip_left = kCullSkipBatches; }
+    }
+    if (hc.overflow) { p.readbacks.clear(); return fail(d, MTGL_E_OOM, "triangle record storage overflow"); }
+    if (hc.tile_refs > p.b.list_capacity) {     /* the guess was too small: nothing ran; size exactly and redo */
+        CU(cudaStreamSynchronize(d->stream));
+        int rc = reserve(d, d->tile_list, (size_t)hc.tile_refs * 4);
+        if (rc != MTGL_OK) return rc;
+        p.b.tile_list = (uint32_t *)d->tile_list.ptr;
+        p.b.list_capacity = (uint32_t)(d->tile_list.cap / 4);
+        CU(cudaEventRecord(p.sev3, d->stream));
+        launch_bin_fill(p.b, p.fb, d->stream);
+        CU(cudaEventRecord(p.sev4, d->stream));
+        launch_raster(p.b, p.fb, p.clr, p.planes, p.plan, d->stream, p.sev6, p.sev7);
+        CU(cudaEventRecord(p.sev5, d->stream));
+        CU(cudaEventRecord(p.stop, d->stream));
+        for (const mtgl_dev::Pending::Readback &rb : p.readbacks) {     /* what was copied out before is not the frame */
+            const size_t o = (size_t)rb.y0 * d->width, n = (size_t)(rb.y1 - rb.y0) * d->width;
+            CU(cudaEventRecord(d->render_ev, d->stream));
+            CU(cudaStreamWaitEvent(d->readback_stream, d->render_ev, 0));
+            CU(cudaMemcpyAsync(rb.dst + o, d->color + o, n * 4, cudaMemcpyDeviceToHost, d->readback_stream));
+            CU(cudaEventRecord(d->readback_ev, d->readback_stream));
+            d->readback_pending = true;
+        }
+    }
+    p.readbacks.clear();
     return MTGL_OK;
 }
 
@@ -410,6 +463,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
 {
     if (!d) return;
     cudaSetDevice(d->device);
+    if (d->stream) resolve_pending(d);
     if (d->upload_stream) cudaStreamSynchronize(d->upload_stream);
     if (d->stream) cudaStreamSynchronize(d->stream);
     if (d->readback_stream) cudaStreamSynchronize(d->readback_stream);
@@ -466,6 +520,7 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
 {
     if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     BufObj &b = d->buf[id];
     b.gen++; b.draws_since_write = 0;
     if (d->upload_pending) CU(cudaStreamSynchronize(d->upload_stream));     /* a queued pinned upload may target this storage */
@@ -539,6 +594,7 @@ int mtgl_dev_read_color_async(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *col
     CU(cudaMemcpyAsync(color + o, d->color + o, n * 4, cudaMemcpyDeviceToHost, d->readback_stream));
     CU(cudaEventRecord(d->readback_ev, d->readback_stream));
     d->readback_pending = true;
+    if (d->pending.active) d->pending.readbacks.push_back({ y0, y1, color });     /* re-issued should the batch have to be redone */
     return MTGL_OK;
 }
 
@@ -558,6 +614,7 @@ int mtgl_dev_buffer_sub_data(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t
     BufObj &b = d->buf[id];
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     b.gen++; b.draws_since_write = 0;
     if (int orc = order_after_transfers(d)) return orc;
     if (size) {
@@ -571,6 +628,7 @@ int mtgl_dev_buffer_delete(mtgl_dev *d, uint32_t id)
 {
     if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int orc = order_after_transfers(d)) return orc;
     BufObj &b = d->buf[id];
     if (b.ptr) {
@@ -588,6 +646,7 @@ int mtgl_dev_buffer_read(mtgl_dev *d, uint32_t id, uint64_t offset, uint64_t siz
     BufObj &b = d->buf[id];
     if (!b.ptr || offset + size > b.size) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int orc = order_after_transfers(d)) return orc;
     if (size) {
         CU(cudaMemcpyAsync(out, b.ptr + offset, size, cudaMemcpyDeviceToHost, d->stream));
@@ -600,6 +659,7 @@ int mtgl_dev_texture_image(mtgl_dev *d, uint32_t id, int32_t w, int32_t h, const
 {
     if (!d || id == 0 || id >= kMaxObjects || w <= 0 || h <= 0 || w > 2048 || h > 2048 || !rgba8) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     TexObj &t = d->tex[id];
     CU(cudaStreamSynchronize(d->stream));
     if (t.l0) CU(cudaFree(t.l0));
@@ -628,6 +688,7 @@ int mtgl_dev_texture_delete(mtgl_dev *d, uint32_t id)
 {
     if (!d || id == 0 || id >= kMaxObjects) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     TexObj &t = d->tex[id];
     if (t.l0 || t.l1) CU(cudaStreamSynchronize(d->stream));
     if (t.l0) CU(cudaFree(t.l0));
@@ -657,6 +718,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         }
     } trace_out{ trace, t_in, t_copy, t_launched };
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int orc = order_after_transfers(d)) return orc;
     const FrameTargets fb = frame_targets(d);
     const uint32_t ntiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
@@ -983,34 +1045,31 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         CU(cudaEventRecord(sev[5], d->stream));
         t_launched = std::chrono::steady_clock::now();
         if (had_triangles) {
+            tot_v += pi.n_vertices; tot_t += pi.real_triangles;
             if (optimistic) {
-                CU(cudaEventSynchronize(d->counters_ev));       /* the scan finished long ago; the raster kernels are running */
-                if (d->h_counters->overflow) return fail(d, MTGL_E_OOM, "triangle record storage overflow");
-                if (d->h_counters->tile_refs > b.list_capacity) {      /* the guess was too small: nothing ran; size exactly and redo */
-                    CU(cudaStreamSynchronize(d->stream));
-                    if ((rc = reserve(d, d->tile_list, (size_t)d->h_counters->tile_refs * 4))) return rc;
-                    b.tile_list = (uint32_t *)d->tile_list.ptr;
-                    b.list_capacity = (uint32_t)(d->tile_list.cap / 4);
-                    CU(cudaEventRecord(sev[3], d->stream));
-                    launch_bin_fill(b, fb, d->stream);
-                    CU(cudaEventRecord(sev[4], d->stream));
-                    launch_raster(b, fb, clr, planes, plan, d->stream, sev[6], sev[7]);
-                    CU(cudaEventRecord(sev[5], d->stream));
-                }
+                /* The scan's counters are looked at later (resolve_pending): at the next call that queues work or waits.
+                 * The host is free to queue the next frame's upload in the meantime. */
+                mtgl_dev::Pending &pd = d->pending;
+                pd.active = true; pd.b = b; pd.fb = fb; pd.clr = clr; pd.planes = planes; pd.plan = plan; pd.plan.color_gate = nullptr;
+                pd.sev3 = sev[3]; pd.sev4 = sev[4]; pd.sev5 = sev[5]; pd.sev6 = sev[6]; pd.sev7 = sev[7]; pd.stop = es.stop;
+                pd.serial = d->batch_serial;
+                pd.readbacks.clear();
+            } else {
+                tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs; tot_culled += d->h_counters->culled_chunks;
             }
-            tot_v += pi.n_vertices; tot_t += pi.real_triangles; tot_r += d->h_counters->records; tot_refs += d->h_counters->tile_refs;
-            tot_culled += d->h_counters->culled_chunks;
         }
     }
     CU(cudaEventRecord(es.stop, d->stream));
     es.pending = true;      /* only a batch that was queued completely is folded into the statistics */
     CU(cudaGetLastError());
-    d->stats.vertices = tot_v; d->stats.triangles_in = tot_t; d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs;
-    d->stats.chunks_culled = tot_culled;
-    for (BoundsEntry &e : d->bounds) {          /* did the culling pass pay for the boxes this batch used? */
-        if (e.batch != d->batch_serial) continue;
-        if (tot_culled != 0) e.zero_streak = 0;
-        else if (++e.zero_streak >= kCullZeroStreak) { e.zero_streak = 0; e.skip_left = kCullSkipBatches; }
+    d->stats.vertices = tot_v; d->stats.triangles_in = tot_t;
+    if (!d->pending.active) {
+        d->stats.triangles_setup = tot_r; d->stats.tile_refs = tot_refs; d->stats.chunks_culled = tot_culled;
+        for (BoundsEntry &e : d->bounds) {          /* did the culling pass pay for the boxes this batch used? */
+            if (e.batch != d->batch_serial) continue;
+            if (tot_culled != 0) e.zero_streak = 0;
+            else if (++e.zero_streak >= kCullZeroStreak) { e.zero_streak = 0; e.skip_left = kCullSkipBatches; }
+        }
     }
     return MTGL_OK;
 }
@@ -1019,6 +1078,7 @@ int mtgl_dev_finish(mtgl_dev *d)
 {
     if (!d) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     return sync_all_streams(d);
 }
 
@@ -1026,6 +1086,7 @@ int mtgl_dev_read_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *col
 {
     if (!d || y0 < 0 || y1 > d->height || y0 > y1) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
     if (int prc = order_after_present(d)) return prc;
@@ -1040,6 +1101,7 @@ int mtgl_dev_write_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, const uint32
 {
     if (!d || y0 < 0 || y1 > d->height || y0 > y1) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     size_t o = (size_t)y0 * d->width, n = (size_t)(y1 - y0) * d->width;
     if (n == 0) return MTGL_OK;
     if (int orc = order_after_transfers(d)) return orc;
@@ -1066,6 +1128,7 @@ int mtgl_dev_export_color_plane(mtgl_dev *d, void *handle_out)
     static_assert(sizeof(cudaIpcMemHandle_t) <= MTGL_IPC_HANDLE_BYTES, "IPC handle size");
     if (!d || !handle_out) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, d->color));
     CU(cudaStreamSynchronize(d->stream));
@@ -1080,6 +1143,7 @@ int mtgl_dev_set_present_target(mtgl_dev *d, const void *handle)
 {
     if (!d) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     CU(cudaStreamSynchronize(d->stream));
     if (d->present) { CU(cudaIpcCloseMemHandle(d->present)); d->present = nullptr; }
     d->barrier_epoch = 0;
@@ -1096,6 +1160,7 @@ int mtgl_dev_set_present_mode(mtgl_dev *d, int mode)
 {
     if (!d || (mode != MTGL_PRESENT_STORES && mode != MTGL_PRESENT_COPY)) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int rc = sync_all_streams(d)) return rc;
     d->present_mode = mode;
     return MTGL_OK;
@@ -1118,6 +1183,7 @@ int mtgl_dev_draw_pixels(mtgl_dev *d, const mtgl_pixel_rect *rect, const void *p
     const uint32_t bpp = pixel_bpp(rect->format);
     if (bpp == 0 || rect->width <= 0 || rect->height <= 0) return MTGL_OK;       /* gl_api.c:1336-1338: unknown formats draw nothing */
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int orc = order_after_transfers(d)) return orc;
     if (int prc = order_after_present(d)) return prc;
     /* Only the part of the rectangle that lands on this device's rows and inside the framebuffer's columns is staged and
@@ -1149,6 +1215,7 @@ int mtgl_dev_read_pixels(mtgl_dev *d, int32_t x, int32_t y, int32_t width, int32
     const uint32_t bpp = (format == 0x1908) ? 4u : (format == 0x1907 ? 3u : 0u);
     if (bpp == 0 || width <= 0 || height <= 0) return MTGL_OK;                   /* other formats leave 'out' untouched */
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int prc = order_after_present(d)) return prc;
     /* rows outside the framebuffer read as zeros, columns outside it as (0, 0, 0, 255) (gl_api.c:1193-1214): filled on
      * the host; only the visible part of the rectangle is gathered on the device and crosses PCIe */
@@ -1182,6 +1249,7 @@ int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants)
     if (!d || participants == 0) return MTGL_E_INVALID;
     if (participants == 1) return MTGL_OK;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     /* the counter lives behind the presenting GPU's colour plane: local for the presenter, NVLink-mapped for the others */
     uint32_t *plane = d->present ? d->present : d->color;
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>((uint8_t *)plane + barrier_offset((size_t)d->width * d->height));
@@ -1208,6 +1276,7 @@ int mtgl_dev_get_stats(mtgl_dev *d, mtgl_dev_stats *out)
 {
     if (!d || !out) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     for (int i = 0; i < mtgl_dev::kEvSets; i++) {           /* oldest first: the last one folded is the last batch */
         mtgl_dev::EvSet &es = d->evset[(d->ev_next + i) % mtgl_dev::kEvSets];
         if (es.pending) { int rc = fold_timing(d, es); if (rc != MTGL_OK) return rc; }
@@ -1223,6 +1292,7 @@ int mtgl_dev_timer_mark(mtgl_dev *d, int which)
 {
     if (!d || which < 0 || which > 1) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
+    if (int prc_ = resolve_pending(d)) return prc_;
     if (int prc = order_after_present(d)) return prc;           /* a band push in flight belongs to the time before the mark */
     CU(cudaEventRecord(d->mark_ev[which], d->stream));
     return MTGL_OK;
