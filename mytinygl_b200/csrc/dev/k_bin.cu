@@ -87,45 +87,51 @@ __device__ __forceinline__ void bin_small_fill(const BatchDev &b, const FrameTar
             ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
             if (ntiles > LARGE_TILES) ntiles = 0;       /* the cooperative binner's */
         }
-        /* ---- single-tile records: warp group -> table slot -> (after the barrier) one atomic per slot ---- */
-        const uint32_t single = __ballot_sync(0xFFFFFFFFu, ntiles == 1);
-        uint32_t tile = 0, slot = FILL_SLOTS, rank = 0, off = 0;
-        if (ntiles == 1) {
-            tile = (uint32_t)(ty0 * fb.tiles_x + tx0);
-            off = __ldg(&b.tile_offset[tile]);
-            const uint32_t peers = __match_any_sync(single, tile);
-            const int leader = __ffs(peers) - 1;
-            if ((int)lane == leader) {
-                uint32_t h = (tile * 2654435761u) >> 26;
-                for (uint32_t probe = 0; probe < FILL_SLOTS; probe++, h = (h + 1u) & (FILL_SLOTS - 1u)) {
-                    const uint32_t prev = atomicCAS(&s_tile[h], 0xFFFFFFFFu, tile);
-                    if (prev == 0xFFFFFFFFu || prev == tile) { slot = h; break; }
-                }
-                if (slot < FILL_SLOTS) rank = atomicAdd(&s_count[slot], (uint32_t)__popc(peers));
-                else rank = atomicAdd(&b.tile_cursor[tile], (uint32_t)__popc(peers));       /* table full: this group goes straight to L2 */
+        /* ---- every (record, tile) reference takes a rank in its tile's table slot; single-tile records, the bulk, as
+         * warp groups (match.any), the two to four references of a record across a tile edge or corner one by one ---- */
+        auto table_slot = [&](uint32_t tile) -> uint32_t {
+            uint32_t h = (tile * 2654435761u) >> 26;
+            for (uint32_t probe = 0; probe < FILL_SLOTS; probe++, h = (h + 1u) & (FILL_SLOTS - 1u)) {
+                const uint32_t prev = atomicCAS(&s_tile[h], 0xFFFFFFFFu, tile);
+                if (prev == 0xFFFFFFFFu || prev == tile) return h;
             }
-            slot = __shfl_sync(peers, slot, leader);
-            rank = __shfl_sync(peers, rank, leader) + (uint32_t)__popc(peers & lt_mask);
+            return FILL_SLOTS;      /* table full: the reference goes straight to L2 */
+        };
+        const uint32_t single = __ballot_sync(0xFFFFFFFFu, ntiles == 1);
+        uint32_t tl[4] = { 0u, 0u, 0u, 0u }, slot[4] = { FILL_SLOTS, FILL_SLOTS, FILL_SLOTS, FILL_SLOTS }, rank[4] = { 0u, 0u, 0u, 0u }, off[4] = { 0u, 0u, 0u, 0u };
+        const int nref = (ntiles >= 1 && ntiles <= 4) ? ntiles : 0;
+        if (ntiles == 1) {
+            tl[0] = (uint32_t)(ty0 * fb.tiles_x + tx0);
+            off[0] = __ldg(&b.tile_offset[tl[0]]);
+            const uint32_t peers = __match_any_sync(single, tl[0]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t sl = FILL_SLOTS, rk = 0;
+            if ((int)lane == leader) {
+                sl = table_slot(tl[0]);
+                rk = (sl < FILL_SLOTS) ? atomicAdd(&s_count[sl], (uint32_t)__popc(peers)) : atomicAdd(&b.tile_cursor[tl[0]], (uint32_t)__popc(peers));
+            }
+            slot[0] = __shfl_sync(peers, sl, leader);
+            rank[0] = __shfl_sync(peers, rk, leader) + (uint32_t)__popc(peers & lt_mask);
+        } else if (nref > 1) {
+            const int w = tx1 - tx0 + 1;            /* 1 or 2 columns when the record spans more than one row; up to 4 in one row */
+#pragma unroll
+            for (int k = 0; k < 4; k++) {           /* (static indices: the arrays stay in registers) */
+                const int row = (w == 1) ? k : ((w == 2) ? (k >> 1) : 0), col = (w == 1) ? 0 : ((w == 2) ? (k & 1) : k);
+                if (k < nref) {
+                    tl[k] = (uint32_t)((ty0 + row) * fb.tiles_x + tx0 + col);
+                    off[k] = __ldg(&b.tile_offset[tl[k]]);
+                    slot[k] = table_slot(tl[k]);
+                    rank[k] = (slot[k] < FILL_SLOTS) ? atomicAdd(&s_count[slot[k]], 1u) : atomicAdd(&b.tile_cursor[tl[k]], 1u);
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x < FILL_SLOTS && s_count[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&b.tile_cursor[s_tile[threadIdx.x]], s_count[threadIdx.x]);
         __syncthreads();
-        if (ntiles == 1) b.tile_list[off + (slot < FILL_SLOTS ? s_base[slot] : 0u) + rank] = r;
-        else if (ntiles > 1 && ntiles <= 4) {
-            /* the usual multi-tile record (a triangle across a tile edge or corner): all its cursor atomics are issued
-             * before the first result is needed -- one memory round trip instead of one per tile */
-            uint32_t tl[4], of[4], at[4];
-            const int w = tx1 - tx0 + 1;            /* 1 or 2 columns when 2 <= ntiles <= 4 spans more than one row; up to 4 in one row */
 #pragma unroll
-            for (int k = 0; k < 4; k++) {           /* (static indices: the arrays stay in registers) */
-                const int row = (w == 1) ? k : ((w == 2) ? (k >> 1) : 0), col = (w == 1) ? 0 : ((w == 2) ? (k & 1) : k);
-                tl[k] = (uint32_t)((ty0 + row) * fb.tiles_x + tx0 + col);
-                if (k < ntiles) { of[k] = __ldg(&b.tile_offset[tl[k]]); at[k] = atomicAdd(&b.tile_cursor[tl[k]], 1u); }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (k < ntiles) b.tile_list[of[k] + at[k]] = r;
-        } else if (ntiles > 1) {
+        for (int k = 0; k < 4; k++)
+            if (k < nref) b.tile_list[off[k] + (slot[k] < FILL_SLOTS ? s_base[slot[k]] : 0u) + rank[k]] = r;
+        if (ntiles > 4) {
             for (int ty = ty0; ty <= ty1; ty++)
                 for (int tx = tx0; tx <= tx1; tx++) {
                     const uint32_t t2 = (uint32_t)(ty * fb.tiles_x + tx);
