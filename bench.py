@@ -448,15 +448,34 @@ def measure(sess, workload, primary):
     # time is taken between two CUDA events on the library's stream.  For N > 1 every frame ends with the library's frame
     # barrier (mtgl_dev_frame_barrier: one tiny kernel per rank on the same stream, counter in the presenting GPU's HBM
     # over NVLink): frame i+1 starts on no rank before every band of frame i has landed in rank 0's plane, and there is
-    # no host synchronisation and no NCCL call inside the loop.  C3 flushes L2 between frames and therefore synchronises
-    # every step.
-    pipelined = flush is None and (world == 1 or peer)
+    # no host synchronisation and no NCCL call inside the loop.  C3 flushes L2 between frames (on the same stream,
+    # outside the per-frame event pairs).
+    pipelined = world == 1 or peer
     sync_all()
     L.mtgl_dev_get_stats(dev, ctypes.byref(st))
     cum0 = (st.batches, st.cum_batch_ms, np.array(list(st.cum_stage_ms)), np.array(list(st.cum_raster_ms)))
     dev_ms_total = 0.0
     t_wall0 = time.perf_counter()
-    if pipelined:
+    if pipelined and flush is not None and not (world > 1 and gather_mode == "copy"):
+        # C3: the L2 flush runs on the library's own stream between the frames and every frame sits between its own pair
+        # of CUDA events on that stream, so the host queues ahead of the device and no host time (Python, a page fault,
+        # a descheduled thread) lands between the events; the flushes are outside the pairs.
+        lib_stream = torch.cuda.ExternalStream(L.mtgl_dev_stream(dev), device=f"cuda:{local}")
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in pairs:
+            L.glFlush()                 # whatever the previous step left queued is on the stream before the flush
+            with torch.cuda.stream(lib_stream):
+                flush.fill_(1)
+            e0.record(lib_stream)
+            frame()
+            L.glFlush()
+            if world > 1:
+                L.mtgl_dev_frame_barrier(dev, world)
+            e1.record(lib_stream)
+        L.glFinish()
+        sync_all()
+        dev_ms_total = float(sum(e0.elapsed_time(e1) for e0, e1 in pairs))
+    elif pipelined and flush is None:
         L.mtgl_dev_timer_mark(dev, 0)
         for _ in range(args.steps):
             frame()

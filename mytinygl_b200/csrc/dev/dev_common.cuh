@@ -54,7 +54,8 @@ constexpr int COLOR_PITCH = 72;               /* words per tile row in shared me
 constexpr int STENCIL_PITCH = 80;             /* (the fragment quantum) hits 32 distinct banks            */
 constexpr int LIST_WINDOW = 2048;             /* triangle references sorted + staged per pass             */
 constexpr int SETUP_THREADS = 256;            /* one chunk = 256 input triangles                          */
-constexpr int CHUNK_SHIFT = 13;               /* record id = chunk << 13 | index-in-chunk (<= 21*256)     */
+constexpr int GROUP_SHIFT = 10;               /* record id = group << 10 | index-in-group; a group is 32   */
+                                              /* consecutive input triangles (one warp of k_setup, <= 21*32 records) */
 constexpr int LARGE_TILES = 16;               /* records overlapping more tiles are binned cooperatively  */
 
 /* ---- device views of objects ---- */
@@ -443,13 +444,14 @@ struct BatchDev {
     const uint32_t *draw_vbase;     /* n_draws + 1 */
     const uint32_t *draw_tbase;     /* n_draws + 1 */
     uint32_t n_draws, n_vertices, n_triangles;
+    uint32_t n_states;              /* entries of states[] / cfgs[] */
     uint32_t need_eye;
     uint32_t n_unfused_draws;       /* draws whose vertices go through k_vertex */
     /* post-transform vertices */
     float4 *v_clip, *v_color, *v_tex, *v_epos, *v_enrm;
     /* set-up output */
     TriRecord *records; TriEye *rec_eye; uint32_t record_capacity;
-    uint32_t *chunk_base;           /* first record slot of every 256-triangle chunk */
+    uint32_t *group_base;           /* first record slot of every group of 32 input triangles (one warp of k_setup) */
     uint8_t *chunk_cull;            /* 1 = the chunk cannot produce a record on this device (k_cull.cu); NULL = no culling pass */
     uint32_t *large_list;
     uint4 *bin_rows;                /* copy of every record's row 2 (bbox_min, bbox_max, state_flags, id): all the binner reads */

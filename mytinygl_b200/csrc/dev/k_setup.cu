@@ -7,12 +7,12 @@
  * (src/clipping.h:27-126), perspective_divide (raster.c:729-746), ndc_to_screen (59-63),
  * should_cull (751-774) and the set-up half of rasterize_triangle_smooth (458-529).
  *
- * Work decomposition: a CTA owns a chunk of 256 consecutive input triangles.  Every thread first
- * counts how many sub-triangles of its triangle survive (0 or 1 without clipping, up to 7 with),
- * a block scan turns the counts into dense, submission-ordered slots inside the chunk, one
- * atomicAdd per CTA reserves the chunk's slots in the record array, and a second evaluation
- * writes the 160-byte records.  A record's id = chunk << 11 | slot-in-chunk is therefore ordered
- * exactly like the reference's sequential loop; the tile kernel sorts by it.
+ * Work decomposition: a CTA owns a chunk of 256 consecutive input triangles, a warp a group of 32.
+ * Every thread first counts how many sub-triangles of its triangle survive (0 or 1 without clipping,
+ * up to 7 with), a warp scan turns the counts into submission-ordered indices inside the group, one
+ * atomicAdd per warp reserves the group's slots in the record array, and the thread writes its
+ * 160-byte records.  A record's id = group << 10 | index-in-group is ordered exactly like the
+ * reference's sequential loop; the tile kernels sort and compare by it.
  *
  * Algorithmic bytes per input triangle: 3 x 48 B gathered (+ 3 x 32 B for per-fragment lighting),
  * 160 B written per surviving sub-triangle.
@@ -640,12 +640,12 @@ __device__ __forceinline__ uint4 write_fill_stream(TriRecord *__restrict__ dst, 
     return make_uint4(s.bbox_min, s.bbox_max, state_flags, id);
 }
 
-/* Fused path, triangle part: rows 0-4 and 8-9 of the record (geometry, z / w, texture coordinates, eye z, LOD) from
- * the attribute arrays.  The colour rows (and the eye-space side record) are filled afterwards by the whole CTA, one
- * thread per vertex of the survivors (k_setup, phase B). */
+/* Fused path, triangle part: rows 0-4 and 8-9 of the record (geometry, z / w, texture coordinates, eye z, LOD).  z, w
+ * (after the divide, raster.c:729-746) and -eye z come from the decision, which already transformed the three positions;
+ * the colour rows (and the eye-space side record) are filled afterwards by the whole CTA (k_setup, phase B). */
 __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, uint32_t id, const RasterCfg *cfg, uint32_t state_index,
-                                                  const ScreenTri &s, const mtgl_state *vs, const float (&px)[3], const float (&py)[3],
-                                                  const float (&pz)[3], const float (&ts)[3], const float (&tt)[3])
+                                                  const ScreenTri &s, const mtgl_state *vs, const float (&z)[3], const float (&w)[3],
+                                                  const float (&nez)[3], const float (&ts)[3], const float (&tt)[3])
 {
     float4 *out = reinterpret_cast<float4 *>(dst);
     const uint32_t cflags = cfg->flags;
@@ -653,16 +653,9 @@ __device__ __forceinline__ uint4 write_fused_head(TriRecord *__restrict__ dst, u
                            ((cflags & RC_UNORDERED) ? STATE_UNORD_BIT : 0u);
     reinterpret_cast<int4 *>(dst)[0] = make_int4(s.x0, s.y0, s.x1, s.y1);
     reinterpret_cast<int4 *>(dst)[1] = make_int4(s.x2, s.y2, __float_as_int(s.area), __float_as_int(1.0f / s.area));
-    float z[3], w[3], nez[3], tu[3], tv[3];
+    float tu[3], tv[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        float ex, ey, ez, ew;
-        to_eye(vs, px[j], py[j], pz[j], ex, ey, ez, ew);
-        const float4 c = to_clip(vs, ex, ey, ez, ew);
-        if (fabsf(c.w) < 1e-6f) { z[j] = 0.0f; w[j] = 1.0f; } else { w[j] = 1.0f / c.w; z[j] = c.z * w[j]; }   /* raster.c:729-746 */
-        nez[j] = -ez;
-        tex_transform(vs, ts[j], tt[j], tu[j], tv[j]);
-    }
+    for (int j = 0; j < 3; j++) tex_transform(vs, ts[j], tt[j], tu[j], tv[j]);
     float lod = 0.0f;       /* one LOD per triangle from non-perspective UV deltas (raster.c:505-529) */
     if (cflags & RC_TEXTURED) {
         float screen_area = fabsf(s.area) * 0.5f;
@@ -724,39 +717,44 @@ __device__ __forceinline__ bool inside_all(const float4 &v)
     return (v.z + v.w) >= 0 && (v.w - v.z) >= 0 && (v.x + v.w) >= 0 && (v.w - v.x) >= 0 && (v.y + v.w) >= 0 && (v.w - v.y) >= 0;
 }
 
-__device__ __forceinline__ void persp_divide_xy(const float4 &v, float &x, float &y)   /* the x, y half of persp_divide */
+/* persp_divide (raster.c:729-746) on a clip-space position: x, y, z over w, and w becomes 1/w */
+__device__ __forceinline__ void persp_divide4(const float4 &v, float &x, float &y, float &z, float &w)
 {
-    if (fabsf(v.w) < 1e-6f) { x = 0.0f; y = 0.0f; return; }
-    float iw = 1.0f / v.w;
-    x = v.x * iw; y = v.y * iw;
+    if (fabsf(v.w) < 1e-6f) { x = 0.0f; y = 0.0f; z = 0.0f; w = 1.0f; return; }
+    w = 1.0f / v.w;
+    x = v.x * w; y = v.y * w; z = v.z * w;
 }
 
 /*
  * The common case -- a triangle with all three vertices inside the frustum and polygon mode GL_FILL -- is decided
  * from the three clip-space positions alone (48 B); colours, texture coordinates and eye-space attributes are only
- * fetched for survivors, after the scan, so culled triangles cost a third of the traffic and nothing but the
- * screen-space result (10 registers) lives across the barrier.
+ * fetched for survivors, so culled triangles cost a third of the traffic.
  *
  * Fused draws on the fast attribute path (FastDraw) stage the chunk's 768 raw vertices (position, normal, texture
- * coordinate) in shared memory once, structure-of-arrays, with every load of the chunk in flight at the same time;
- * the decision, the record heads, the vertex-cache hashing and the vertex stage all read them from there, so each
- * CTA pays one global-memory round trip for its attributes instead of one per phase.
+ * coordinate) in shared memory once, structure-of-arrays, every warp the 96 vertices of its own 32 triangles with all
+ * loads in flight at the same time; the decision, the record heads, the vertex-cache hashing and the vertex stage all
+ * read them from there, so each CTA pays one global-memory round trip for its attributes instead of one per phase.
+ *
+ * Record slots are reserved per WARP: a shuffle scan of the survivor counts and one atomicAdd per warp.  Storage order
+ * therefore is not submission order -- the record's id is: id = group << GROUP_SHIFT | index-in-group, the group being
+ * the warp's 32 consecutive input triangles, is ordered exactly like the reference's sequential loop, the tile kernels
+ * sort and compare by it, and K4a turns an id back into a slot through group_base[].  Up to the vertex stage the CTA
+ * meets at ONE barrier (the prologue's); the earlier form -- block-wide scan, dense slots per chunk -- had four, and
+ * evaluated the three transforms twice because nothing but the screen-space result could live across them.
  */
 constexpr uint32_t SETUP_VERTS = 3 * SETUP_THREADS;
 constexpr uint32_t VCACHE_SLOTS = 2048;
+static_assert(32 * 21 <= (1 << GROUP_SHIFT), "a group's records (32 primitives, up to 21 records each) fit its id field");
 
 struct SetupSmem {
     /* raw attributes of local vertex lv = 3 * (triangle - first triangle of the chunk) + corner; after phase B2 the first
      * four arrays of an OWNER vertex hold its shaded colour (r, g, b, a) instead */
     float a_px[SETUP_VERTS], a_py[SETUP_VERTS], a_pz[SETUP_VERTS], a_nx[SETUP_VERTS];
     float a_ny[SETUP_VERTS], a_nz[SETUP_VERTS], a_s[SETUP_VERTS], a_t[SETUP_VERTS];
-    uint32_t vcache[VCACHE_SLOTS];              /* phase B: hash slot -> first vertex reference that claimed it */
-    uint2 fused_list[SETUP_THREADS];            /* (record index, input triangle) of the chunk's fused survivors */
-    uint16_t vsame[SETUP_VERTS];                /* vertex reference -> the reference it duplicates (itself if none) */
-    uint16_t shade_list[SETUP_VERTS];           /* references to shade */
-    uint32_t warp_sums[SETUP_THREADS / 32];
-    uint32_t chunk_slot0;
-    uint32_t fused_n;                           /* survivors of this chunk whose colour rows phase B fills */
+    uint32_t vcache[VCACHE_SLOTS];              /* phase B: hash slot -> first local vertex that claimed it */
+    uint32_t rec_of[SETUP_THREADS];             /* record of the thread's fused survivor (eye-space rows of duplicates, need_eye) */
+    uint16_t vsame[SETUP_VERTS];                /* local vertex -> the local vertex it duplicates (itself if none) */
+    uint16_t shade_list[SETUP_VERTS];           /* local vertices to shade */
     uint32_t shade_n;
     FastDraw fastd;                             /* fast attribute path of the draw this chunk starts in */
     mtgl_state vstate;                          /* ... and a copy of its vertex-stage state block: matrices, lights and materials
@@ -769,40 +767,42 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     __shared__ SetupSmem sm;
     FastDraw &fastd = sm.fastd;
     const uint32_t chunk = blockIdx.x;
-    if (b.chunk_cull && b.chunk_cull[chunk]) {              /* k_cull.cu: nothing of this chunk reaches the device's rows */
-        if (threadIdx.x == 0) b.chunk_base[chunk] = 0u;
-        return;
-    }
+    if (b.chunk_cull && b.chunk_cull[chunk]) return;        /* k_cull.cu: nothing of this chunk reaches the device's rows */
     const uint32_t t0 = chunk * SETUP_THREADS;
-    if (threadIdx.x == 0) { sm.fused_n = 0; sm.shade_n = 0; }
-    /* the fast attribute path of the draw this chunk starts in: decided per draw on the host, copied by 28 threads (one
-     * thread walking the draw record while 255 wait cost 5 % of the kernel) */
-    if (t0 < b.n_triangles) {
-        const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
-        if (threadIdx.x < sizeof(FastDraw) / 4u)
-            reinterpret_cast<uint32_t *>(&fastd)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t *>(&b.draws[d0].fast) + threadIdx.x);
-    } else if (threadIdx.x == 0) fastd.valid = 0;
-    for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) sm.vcache[i] = 0xFFFFFFFFu;
-    __syncthreads();
-
-    /* ---- phase A0: stage the raw attributes of the chunk's fast-path triangles ---- */
-    const bool any_fast = fastd.valid != 0u;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const mtgl_state *const fst = &sm.vstate;
-    if (any_fast) {
-        {
-            const uint32_t *srcw = reinterpret_cast<const uint32_t *>(fastd.st);
+    if (threadIdx.x == 0) sm.shade_n = 0;
+    /* the fast attribute path of the draw this chunk starts in: decided per draw on the host; the descriptor and the
+     * vertex-stage state block it names are copied to shared memory */
+    bool any_fast = false;
+    {
+        const uint32_t d0 = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, t0);
+        const FastDraw *const gf = &b.draws[d0].fast;
+        any_fast = __ldg(&gf->valid) != 0u;
+        if (threadIdx.x < sizeof(FastDraw) / 4u)
+            reinterpret_cast<uint32_t *>(&fastd)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t *>(gf) + threadIdx.x);
+        if (any_fast) {
+            const uint32_t *srcw = reinterpret_cast<const uint32_t *>(
+                (const void *)__ldg(reinterpret_cast<const unsigned long long *>(&gf->st)));
             uint32_t *dstw = reinterpret_cast<uint32_t *>(&sm.vstate);
             for (uint32_t i = threadIdx.x; i < sizeof(mtgl_state) / 4u; i += SETUP_THREADS) dstw[i] = __ldg(srcw + i);
         }
+    }
+    for (uint32_t i = threadIdx.x; i < VCACHE_SLOTS; i += SETUP_THREADS) sm.vcache[i] = 0xFFFFFFFFu;
+    __syncthreads();
+
+    /* ---- phase A0: every warp stages the raw attributes of its own fast-path triangles ---- */
+    if (any_fast) {
         const uint32_t tb = max(fastd.tri_begin, t0), te = min(min(fastd.tri_end, t0 + SETUP_THREADS), b.n_triangles);
-        for (uint32_t lv = threadIdx.x + 3u * (tb - t0); lv < 3u * (te - t0); lv += SETUP_THREADS) {
+        const uint32_t lo = max(96u * warp, 3u * (tb - t0)), hi = min(96u * warp + 96u, 3u * (te - t0));
+        for (uint32_t lv = lo + lane; lv < hi; lv += 32u) {
             VertexIn in;
             fast_vertex(fastd, 3u * (t0 - fastd.tbase) + lv, in);
             sm.a_px[lv] = in.px; sm.a_py[lv] = in.py; sm.a_pz[lv] = in.pz;
             sm.a_nx[lv] = in.nx; sm.a_ny[lv] = in.ny; sm.a_nz[lv] = in.nz;
             sm.a_s[lv] = in.s; sm.a_t[lv] = in.t;
         }
-        __syncthreads();
+        __syncwarp();
     }
 
     const uint32_t t = t0 + threadIdx.x;
@@ -816,6 +816,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
     uint32_t i0 = 0, i1 = 0, i2 = 0;
     uint32_t count = 0;
     ScreenTri s;
+    float zd[3] = { 0.0f, 0.0f, 0.0f }, wd[3] = { 1.0f, 1.0f, 1.0f }, nez[3] = { 0.0f, 0.0f, 0.0f };   /* fused: z / w after the divide, -eye z */
+    const mtgl_state *vs = nullptr;                         /* fused: the vertex-stage state of the triangle's vertices */
     VertexSrc src = { b.v_clip, b.v_color, b.v_tex, b.v_epos, b.v_enrm, b.unorm8, b.need_eye ? 1 : 0, b.staged, b.states, nullptr, 0u };
     const BinOut bin = { b.records, b.bin_rows, b.tile_count, b.tile_flags, b.large_list, b.counters, fb.tiles_x, fb.tile_y0 };
 
@@ -854,23 +856,22 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
             if (src.fused) {            /* positions straight from the attribute arrays: MV, then P */
                 const uint32_t l0 = i0 - dr.vbase;
                 float x, y, z, ex, ey, ez, ew;
-                const mtgl_state *vs;
                 if (fast_t) {
                     vs = fst;
                     const uint32_t lv = 3u * threadIdx.x;
-                    to_eye(vs, sm.a_px[lv], sm.a_py[lv], sm.a_pz[lv], ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
-                    to_eye(vs, sm.a_px[lv + 1], sm.a_py[lv + 1], sm.a_pz[lv + 1], ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
-                    to_eye(vs, sm.a_px[lv + 2], sm.a_py[lv + 2], sm.a_pz[lv + 2], ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+                    to_eye(vs, sm.a_px[lv], sm.a_py[lv], sm.a_pz[lv], ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew); nez[0] = -ez;
+                    to_eye(vs, sm.a_px[lv + 1], sm.a_py[lv + 1], sm.a_pz[lv + 1], ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew); nez[1] = -ez;
+                    to_eye(vs, sm.a_px[lv + 2], sm.a_py[lv + 2], sm.a_pz[lv + 2], ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew); nez[2] = -ez;
                 } else {
-                    fetch_position(b.staged, b.states, dr, l0, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew);
-                    fetch_position(b.staged, b.states, dr, l0 + 1, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew);
-                    fetch_position(b.staged, b.states, dr, l0 + 2, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew);
+                    fetch_position(b.staged, b.states, dr, l0, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p0 = to_clip(vs, ex, ey, ez, ew); nez[0] = -ez;
+                    fetch_position(b.staged, b.states, dr, l0 + 1, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p1 = to_clip(vs, ex, ey, ez, ew); nez[1] = -ez;
+                    fetch_position(b.staged, b.states, dr, l0 + 2, x, y, z, vs); to_eye(vs, x, y, z, ex, ey, ez, ew); p2 = to_clip(vs, ex, ey, ez, ew); nez[2] = -ez;
                 }
             } else { p0 = src.clip[i0]; p1 = src.clip[i1]; p2 = src.clip[i2]; }
             if (inside_all(p0) && inside_all(p1) && inside_all(p2)) {
                 /* Sutherland-Hodgman returns its input unchanged when every vertex passes every plane */
                 float ax, ay, bx, by, cx, cy;
-                persp_divide_xy(p0, ax, ay); persp_divide_xy(p1, bx, by); persp_divide_xy(p2, cx, cy);
+                persp_divide4(p0, ax, ay, zd[0], wd[0]); persp_divide4(p1, bx, by, zd[1], wd[1]); persp_divide4(p2, cx, cy, zd[2], wd[2]);
                 const int kind = screen_setup(st, fb, ax, ay, bx, by, cx, cy, s);
                 if (kind == TRI_OUTLINE) shape = 5; else count = (uint32_t)kind;
             } else shape = 2;
@@ -878,65 +879,46 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
         if (shape > 1) count = setup_rare(false, nullptr, nullptr, 0u, bin, src, st, cfg, fb, state_index, shape, i0, i1, i2);
     }
 
-    /* block-wide exclusive scan of the survivor counts -> submission-ordered slots */
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    /* ---- slots: exclusive scan of the warp's survivor counts, one atomicAdd per warp ---- */
     uint32_t incl = count;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= (uint32_t)o) incl += n;
     }
-    if (lane == 31) sm.warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = (lane < SETUP_THREADS / 32) ? sm.warp_sums[lane] : 0u;
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < SETUP_THREADS / 32; o <<= 1) {
-            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-            if (lane >= (uint32_t)o) wi += n;
-        }
-        if (lane < SETUP_THREADS / 32) sm.warp_sums[lane] = wi - w;
-        if (lane == SETUP_THREADS / 32 - 1) {
-            uint32_t total = wi;
-            uint32_t base = total ? atomicAdd(&b.counters->records, total) : 0u;
-            if (base + total > b.record_capacity) { atomicExch(&b.counters->overflow, 1u); base = 0xFFFFFFFFu; }
-            sm.chunk_slot0 = base;
-            b.chunk_base[chunk] = base;
-        }
+    uint32_t group_slot0 = 0u;
+    const uint32_t group = (t0 >> 5) + warp;
+    if (lane == 31) {
+        group_slot0 = incl ? atomicAdd(&b.counters->records, incl) : 0u;
+        if (group_slot0 + incl > b.record_capacity) { atomicExch(&b.counters->overflow, 1u); group_slot0 = 0xFFFFFFFFu; }
+        b.group_base[group] = group_slot0;
     }
-    __syncthreads();
+    group_slot0 = __shfl_sync(0xFFFFFFFFu, group_slot0, 31);
+
     /* no early exit: the whole warp stays for the aggregated tile counting below */
-    bool counted = false;
+    bool counted = false, fused_mine = false;
     uint32_t r = 0;
     uint4 row = make_uint4(0u, 0u, 0u, 0u);
-    if (count != 0 && sm.chunk_slot0 != 0xFFFFFFFFu) {
-        const uint32_t slot = sm.warp_sums[warp] + incl - count;       /* index inside the chunk */
-        r = sm.chunk_slot0 + slot;
+    if (count != 0 && group_slot0 != 0xFFFFFFFFu) {
+        const uint32_t slot = incl - count;                 /* index inside the group */
+        r = group_slot0 + slot;
         TriRecord *const dst = b.records + r;
         TriEye *const eye_dst = b.need_eye ? b.rec_eye + r : nullptr;
-        const uint32_t id0 = (chunk << CHUNK_SHIFT) | slot;
+        const uint32_t id0 = (group << GROUP_SHIFT) | slot;
         if (shape == 1) {
             if (src.fused) {
-                float px[3], py[3], pz[3], ts[3], tt[3];
-                const mtgl_state *vs;
+                float ts[3], tt[3];
                 if (fast_t) {
-                    vs = fst;
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        const uint32_t lv = 3u * threadIdx.x + j;
-                        px[j] = sm.a_px[lv]; py[j] = sm.a_py[lv]; pz[j] = sm.a_pz[lv]; ts[j] = sm.a_s[lv]; tt[j] = sm.a_t[lv];
-                    }
+                    for (int j = 0; j < 3; j++) { ts[j] = sm.a_s[3u * threadIdx.x + j]; tt[j] = sm.a_t[3u * threadIdx.x + j]; }
                 } else {
                     const uint32_t l0 = i0 - src.draw->vbase;
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        fetch_position(b.staged, b.states, *src.draw, l0 + j, px[j], py[j], pz[j], vs);
-                        fetch_texcoord(b.staged, *src.draw, l0 + j, ts[j], tt[j]);
-                    }
+                    for (int j = 0; j < 3; j++) fetch_texcoord(b.staged, *src.draw, l0 + j, ts[j], tt[j]);
                 }
-                row = write_fused_head(dst, id0, cfg, state_index, s, vs, px, py, pz, ts, tt);
-                sm.fused_list[atomicAdd(&sm.fused_n, 1u)] = make_uint2(r, t);
+                row = write_fused_head(dst, id0, cfg, state_index, s, vs, zd, wd, nez, ts, tt);
+                sm.rec_of[threadIdx.x] = r;
+                fused_mine = true;
             } else row = write_fill_stream(dst, eye_dst, id0, cfg, state_index, s, src, i0, i1, i2);
             b.bin_rows[r] = row;
             counted = true;
@@ -967,18 +949,16 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
      *
      * Independent triangles of a mesh repeat their vertices (C4: 4.3 references per distinct vertex inside a chunk of
      * 256 triangles).  The vertex stage is a pure function of (attributes, state block), so it runs once per DISTINCT
-     * input of the chunk -- a post-transform vertex cache: B1 every vertex reference hashes its raw attributes and
-     * claims a table slot; a loser compares bit for bit with the slot's owner and, if equal, becomes its duplicate;
-     * B2 the owners (and hash collisions) are shaded, one thread each, and leave their colour in shared memory;
-     * B3 every reference stores its owner's colour into its record row. ---- */
-    __syncthreads();
-    const uint32_t nv = sm.fused_n * 3u;
-    if (nv == 0) return;                                    /* uniform: fused_n is shared */
-    auto local_vertex = [&](uint32_t v) { return 3u * (sm.fused_list[v / 3u].y - t0) + v % 3u; };
-    auto vertex_in = [&](uint32_t v, VertexIn &in, uint32_t &state_id) {
-        const uint2 e = sm.fused_list[v / 3u];
-        if (any_fast && e.y >= fastd.tri_begin && e.y < fastd.tri_end) {
-            const uint32_t lv = 3u * (e.y - t0) + v % 3u;
+     * input of the chunk -- a post-transform vertex cache: B1 every survivor hashes the raw attributes of its three
+     * vertices and claims a table slot for each; a loser compares bit for bit with the slot's owner and, if equal,
+     * becomes its duplicate; B2 the owners (and hash collisions) are shaded, one thread each, and leave their colour in
+     * shared memory; B3 every survivor stores its vertices' owners' colours into its record rows. ---- */
+    if (!__syncthreads_or(fused_mine ? 1 : 0)) return;
+    /* every triangle of the chunk is staged: its vertices share the state block and the current colour */
+    const bool chunk_fast = any_fast && fastd.tri_begin <= t0 && fastd.tri_end >= min(t0 + SETUP_THREADS, b.n_triangles);
+    auto vertex_in = [&](uint32_t lv, VertexIn &in, uint32_t &state_id) {
+        const uint32_t tt = t0 + lv / 3u;
+        if (any_fast && tt >= fastd.tri_begin && tt < fastd.tri_end) {
             in.px = sm.a_px[lv]; in.py = sm.a_py[lv]; in.pz = sm.a_pz[lv];
             in.nx = sm.a_nx[lv]; in.ny = sm.a_ny[lv]; in.nz = sm.a_nz[lv];
             in.s = sm.a_s[lv]; in.t = sm.a_t[lv];
@@ -987,69 +967,93 @@ __global__ void __launch_bounds__(SETUP_THREADS, 4) k_setup(BatchDev b, FrameTar
             state_id = (uint32_t)(fastd.st - b.states);
             return;
         }
-        const uint32_t dd = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, e.y);
+        const uint32_t dd = (b.n_draws == 1) ? 0u : find_draw_tri(b.draw_tbase, b.n_draws, tt);
         const DevDraw &dr = b.draws[dd];
-        fetch_vertex(b.staged, b.states, dr, 3u * (e.y - dr.tbase) + v % 3u, in);
+        fetch_vertex(b.staged, b.states, dr, 3u * (tt - dr.tbase) + lv % 3u, in);
         state_id = (uint32_t)(in.st - b.states);
     };
-    for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {            /* B1 */
-        VertexIn in;
-        uint32_t sid;
-        vertex_in(v, in, sid);
-        const uint32_t w[13] = { __float_as_uint(in.px), __float_as_uint(in.py), __float_as_uint(in.pz), __float_as_uint(in.nx),
-                                 __float_as_uint(in.ny), __float_as_uint(in.nz), __float_as_uint(in.s), __float_as_uint(in.t),
-                                 __float_as_uint(in.cur.r), __float_as_uint(in.cur.g), __float_as_uint(in.cur.b), __float_as_uint(in.cur.a),
-                                 sid };
-        uint32_t hsh = 0x811C9DC5u;
+    if (fused_mine) {                                                       /* B1 */
+        for (uint32_t j = 0; j < 3u; j++) {
+            const uint32_t lv = 3u * threadIdx.x + j;
+            uint32_t w[13];
+            if (chunk_fast) {
+                w[0] = __float_as_uint(sm.a_px[lv]); w[1] = __float_as_uint(sm.a_py[lv]); w[2] = __float_as_uint(sm.a_pz[lv]);
+                w[3] = __float_as_uint(sm.a_nx[lv]); w[4] = __float_as_uint(sm.a_ny[lv]); w[5] = __float_as_uint(sm.a_nz[lv]);
+                w[6] = __float_as_uint(sm.a_s[lv]); w[7] = __float_as_uint(sm.a_t[lv]);
+                w[8] = w[9] = w[10] = w[11] = w[12] = 0u;
+            } else {
+                VertexIn in;
+                uint32_t sid;
+                vertex_in(lv, in, sid);
+                w[0] = __float_as_uint(in.px); w[1] = __float_as_uint(in.py); w[2] = __float_as_uint(in.pz); w[3] = __float_as_uint(in.nx);
+                w[4] = __float_as_uint(in.ny); w[5] = __float_as_uint(in.nz); w[6] = __float_as_uint(in.s); w[7] = __float_as_uint(in.t);
+                w[8] = __float_as_uint(in.cur.r); w[9] = __float_as_uint(in.cur.g); w[10] = __float_as_uint(in.cur.b);
+                w[11] = __float_as_uint(in.cur.a); w[12] = sid;
+            }
+            uint32_t hsh = 0x811C9DC5u;
 #pragma unroll
-        for (int k = 0; k < 13; k++) hsh = (hsh ^ w[k]) * 0x9E3779B1u;
-        hsh ^= hsh >> 15;
-        const uint32_t owner = atomicCAS(&sm.vcache[hsh & (VCACHE_SLOTS - 1)], 0xFFFFFFFFu, v);
-        uint32_t same_as = v;
-        if (owner != 0xFFFFFFFFu) {
-            VertexIn o;
-            uint32_t osid;
-            vertex_in(owner, o, osid);
-            const bool equal = __float_as_uint(o.px) == w[0] && __float_as_uint(o.py) == w[1] && __float_as_uint(o.pz) == w[2] &&
-                               __float_as_uint(o.nx) == w[3] && __float_as_uint(o.ny) == w[4] && __float_as_uint(o.nz) == w[5] &&
-                               __float_as_uint(o.s) == w[6] && __float_as_uint(o.t) == w[7] && __float_as_uint(o.cur.r) == w[8] &&
-                               __float_as_uint(o.cur.g) == w[9] && __float_as_uint(o.cur.b) == w[10] && __float_as_uint(o.cur.a) == w[11] &&
-                               osid == w[12];
-            if (equal) same_as = owner;
+            for (int k = 0; k < 8; k++) hsh = (hsh ^ w[k]) * 0x9E3779B1u;
+            if (!chunk_fast) {
+#pragma unroll
+                for (int k = 8; k < 13; k++) hsh = (hsh ^ w[k]) * 0x9E3779B1u;
+            }
+            hsh ^= hsh >> 15;
+            const uint32_t owner = atomicCAS(&sm.vcache[hsh & (VCACHE_SLOTS - 1)], 0xFFFFFFFFu, lv);
+            uint32_t same_as = lv;
+            if (owner != 0xFFFFFFFFu) {
+                bool equal;
+                if (chunk_fast) {
+                    equal = __float_as_uint(sm.a_px[owner]) == w[0] && __float_as_uint(sm.a_py[owner]) == w[1] &&
+                            __float_as_uint(sm.a_pz[owner]) == w[2] && __float_as_uint(sm.a_nx[owner]) == w[3] &&
+                            __float_as_uint(sm.a_ny[owner]) == w[4] && __float_as_uint(sm.a_nz[owner]) == w[5] &&
+                            __float_as_uint(sm.a_s[owner]) == w[6] && __float_as_uint(sm.a_t[owner]) == w[7];
+                } else {
+                    VertexIn o;
+                    uint32_t osid;
+                    vertex_in(owner, o, osid);
+                    equal = __float_as_uint(o.px) == w[0] && __float_as_uint(o.py) == w[1] && __float_as_uint(o.pz) == w[2] &&
+                            __float_as_uint(o.nx) == w[3] && __float_as_uint(o.ny) == w[4] && __float_as_uint(o.nz) == w[5] &&
+                            __float_as_uint(o.s) == w[6] && __float_as_uint(o.t) == w[7] && __float_as_uint(o.cur.r) == w[8] &&
+                            __float_as_uint(o.cur.g) == w[9] && __float_as_uint(o.cur.b) == w[10] && __float_as_uint(o.cur.a) == w[11] &&
+                            osid == w[12];
+                }
+                if (equal) same_as = owner;
+            }
+            sm.vsame[lv] = (uint16_t)same_as;
+            if (same_as == lv) sm.shade_list[atomicAdd(&sm.shade_n, 1u)] = (uint16_t)lv;
         }
-        sm.vsame[v] = (uint16_t)same_as;
-        if (same_as == v) sm.shade_list[atomicAdd(&sm.shade_n, 1u)] = (uint16_t)v;
     }
     __syncthreads();
     const uint32_t ns = sm.shade_n;
     for (uint32_t i = threadIdx.x; i < ns; i += SETUP_THREADS) {            /* B2 */
-        const uint32_t v = sm.shade_list[i];
+        const uint32_t lv = sm.shade_list[i];
         VertexIn in;
         uint32_t sid;
-        vertex_in(v, in, sid);
+        vertex_in(lv, in, sid);
         VertexOut o;
         shade_vertex(in, o);
         /* the owner's raw position / normal.x are dead from here on (only this thread read them): its colour takes their place */
-        const uint32_t lv = local_vertex(v);
         sm.a_px[lv] = o.color.x; sm.a_py[lv] = o.color.y; sm.a_pz[lv] = o.color.z; sm.a_nx[lv] = o.color.w;
         if (b.need_eye) {
-            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + sm.fused_list[v / 3u].x);
-            eo[v % 3u] = o.epos;
-            eo[3 + v % 3u] = o.enrm;
+            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + sm.rec_of[lv / 3u]);
+            eo[lv % 3u] = o.epos;
+            eo[3 + lv % 3u] = o.enrm;
         }
     }
     __syncthreads();                                        /* the owners' colours are visible to the whole CTA */
-    for (uint32_t v = threadIdx.x; v < nv; v += SETUP_THREADS) {            /* B3 */
-        const uint32_t o = sm.vsame[v];
-        const uint32_t lo = local_vertex(o);
-        const uint32_t rr = sm.fused_list[v / 3u].x, j = v % 3u;
-        reinterpret_cast<float4 *>(b.records + rr)[5 + j] = make_float4(sm.a_px[lo], sm.a_py[lo], sm.a_pz[lo], sm.a_nx[lo]);
-        if (b.need_eye && o != v) {
-            const uint32_t ro = sm.fused_list[o / 3u].x, jo = o % 3u;
-            float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + rr);
-            const float4 *es = reinterpret_cast<const float4 *>(b.rec_eye + ro);
-            eo[j] = __ldcg(es + jo);
-            eo[3 + j] = __ldcg(es + 3 + jo);
+    if (fused_mine) {                                                       /* B3 */
+#pragma unroll
+        for (uint32_t j = 0; j < 3u; j++) {
+            const uint32_t lv = 3u * threadIdx.x + j;
+            const uint32_t o = sm.vsame[lv];
+            reinterpret_cast<float4 *>(b.records + r)[5 + j] = make_float4(sm.a_px[o], sm.a_py[o], sm.a_pz[o], sm.a_nx[o]);
+            if (b.need_eye && o != lv) {
+                const uint32_t ro = sm.rec_of[o / 3u], jo = o % 3u;
+                float4 *eo = reinterpret_cast<float4 *>(b.rec_eye + r);
+                const float4 *es = reinterpret_cast<const float4 *>(b.rec_eye + ro);
+                eo[j] = __ldcg(es + jo);
+                eo[3 + j] = __ldcg(es + 3 + jo);
+            }
         }
     }
 }

@@ -43,6 +43,7 @@ struct ShadeSmem {
     uint16_t list[TILE_W * (TILE_H / SPLIT)];
     float un[256];
     uint32_t warp_total[SHADE_THREADS / 32];
+    RasterCfg cfg0;                                 /* the batch's only configuration block, if it has just one */
 };
 
 /* the general path (dev_shade.cuh), out of line so that its registers do not count against the fast path */
@@ -79,6 +80,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
     const bool clr_here = clr.mask && clr.x0 < px0 + vw && clr.x1 > px0 && clr.y0 < py0 + vh && clr.y1 > py0;   /* as in k_raster */
     if (L == 0 && !clr_here) return;
     sm.un[threadIdx.x] = b.unorm8[threadIdx.x];
+    /* a batch with one state block (C4, C5): its configuration is read from shared memory, so a pixel's chain of dependent
+     * loads is list -> record and not list -> record -> configuration */
+    const bool one_cfg = b.n_states == 1u;
+    if (one_cfg && threadIdx.x < sizeof(RasterCfg) / 4u)
+        reinterpret_cast<uint32_t *>(&sm.cfg0)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t *>(b.cfgs) + threadIdx.x);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
 
@@ -109,10 +115,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
             uint32_t word = v[k];
             if (v[k] != VIS_NONE) {
                 has_mask |= 1u << k;
-                /* pass 2 starts two barriers from here: its records (160 B, two 128-byte lines at most) travel L2 -> L1 meanwhile */
-                const char *rp = reinterpret_cast<const char *>(b.records + v[k]);
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(rp));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(rp + 128));
+                /* pass 2 starts two barriers from here: its records (160 B, two 128-byte lines at most) travel L2 -> L1
+                 * meanwhile; a run of pixels of one triangle asks once */
+                if (k == 0 || v[k] != v[k > 0 ? k - 1 : 0]) {
+                    const char *rp = reinterpret_cast<const char *>(b.records + v[k]);
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rp));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(rp + 128));
+                }
             } else if (xq + k < vw) word = (clr_row && px0 + xq + k >= clr.x0 && px0 + xq + k < clr.x1) ? clr.color : fb.color[p0 + k];
             sm.tile[y * TILE_W + xq + k] = word;
         }
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const TriRecord *rec = b.records + r[p];
-            const RasterCfg *cfg = b.cfgs + (sflags[p] & STATE_INDEX_MASK);
+            const RasterCfg *cfg = one_cfg ? &sm.cfg0 : b.cfgs + (sflags[p] & STATE_INDEX_MASK);
             const uint32_t flags = cfg->flags;
             TriAttr A;
             load_attr(A, rec);

@@ -440,7 +440,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
     __syncthreads();
 
     /* ---- write-back: depth plane + visibility plane (record index of the surviving fragment) ---- */
-    const uint32_t slot_mask = (1u << CHUNK_SHIFT) - 1u;
+    const uint32_t slot_mask = (1u << GROUP_SHIFT) - 1u;
     const bool vec = (vw == TILE_W) && ((fb.width & 3) == 0);
     if (vec) {
         for (int i = threadIdx.x; i < vh * 16; i += THREADS) {
@@ -455,7 +455,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
                 if (lo == none_lo) rv[k] = VIS_NONE;
                 else {
                     const uint32_t id = mode.first_wins ? lo - 1u : 0xFFFFFFFEu - lo;
-                    rv[k] = __ldg(&b.chunk_base[id >> CHUNK_SHIFT]) + (id & slot_mask);
+                    rv[k] = __ldg(&b.group_base[id >> GROUP_SHIFT]) + (id & slot_mask);
                 }
             }
             const size_t p = (size_t)(py0 + y) * fb.width + px0 + q4;
@@ -471,7 +471,7 @@ k_vis(BatchDev b, FrameTargets fb, ClearOp clr, uint32_t planes, uint32_t depth_
             uint32_t rv = VIS_NONE;
             if (lo != none_lo) {
                 const uint32_t id = mode.first_wins ? lo - 1u : 0xFFFFFFFEu - lo;
-                rv = __ldg(&b.chunk_base[id >> CHUNK_SHIFT]) + (id & slot_mask);
+                rv = __ldg(&b.group_base[id >> GROUP_SHIFT]) + (id & slot_mask);
             }
             const size_t p = (size_t)(py0 + y) * fb.width + px0 + x;
             if (planes & 2u) fb.depth[p] = ord_float((uint32_t)(key >> 32) ^ mode.inv);

@@ -75,7 +75,7 @@ struct mtgl_dev {
     BufObj buf[kMaxBuffers];
     float *unorm8 = nullptr;
 
-    DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, chunk_base, large_list, bin_rows;
+    DevBuf arena, v_clip, v_color, v_tex, v_epos, v_enrm, records, rec_eye, group_base, large_list, bin_rows;
     DevBuf tile_count, tile_offset, tile_cursor, tile_flags, tile_order, tile_list, vis_plane, chunk_cull, pixel_stage;
     BoundsEntry bounds[kBoundsEntries];
     uint64_t bounds_clock = 0;
@@ -484,7 +484,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
     for (uint32_t i = 0; i < kMaxBuffers; i++)
         if (d->buf[i].ptr) cudaFree(d->buf[i].ptr);
     DevBuf *bufs[] = { &d->arena, &d->v_clip, &d->v_color, &d->v_tex, &d->v_epos, &d->v_enrm, &d->records, &d->rec_eye,
-                       &d->chunk_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane, &d->chunk_cull, &d->pixel_stage };
+                       &d->group_base, &d->large_list, &d->bin_rows, &d->tile_count, &d->tile_offset, &d->tile_cursor, &d->tile_flags, &d->tile_order, &d->tile_list, &d->vis_plane, &d->chunk_cull, &d->pixel_stage };
     for (DevBuf *b : bufs) release(*b);
     for (BoundsEntry &e : d->bounds) release(e.boxes);
     if (d->color) cudaFree(d->color);
@@ -922,6 +922,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         std::memset(&b, 0, sizeof b);
         b.states = reinterpret_cast<const mtgl_state *>(dp + o_states);
         b.cfgs = reinterpret_cast<const RasterCfg *>(dp + o_cfgs);
+        b.n_states = bt->n_states;
         b.staged = reinterpret_cast<const mtgl_in_vertex *>(dp + o_staged);
         b.draws = reinterpret_cast<const DevDraw *>(dp + pi.o_draws);
         b.draw_vbase = reinterpret_cast<const uint32_t *>(dp + pi.o_vbase);
@@ -952,7 +953,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             if (need_eye && ((rc = reserve(d, d->v_epos, nv * 16)) || (rc = reserve(d, d->v_enrm, nv * 16)))) return rc;
             if ((rc = reserve(d, d->records, rec_cap * sizeof(TriRecord)))) return rc;
             if (need_eye && (rc = reserve(d, d->rec_eye, rec_cap * sizeof(TriEye)))) return rc;
-            if ((rc = reserve(d, d->chunk_base, (size_t)chunks * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4)) ||
+            if ((rc = reserve(d, d->group_base, (size_t)chunks * (SETUP_THREADS / 32) * 4)) || (rc = reserve(d, d->large_list, rec_cap * 4)) ||
                 (rc = reserve(d, d->bin_rows, rec_cap * 16))) return rc;
             /* everything a pass starts from zero lives in one allocation (one memset per frame, not three):
              * counters (256 B) | tile_count | tile_flags */
@@ -966,7 +967,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             b.v_epos = (float4 *)d->v_epos.ptr; b.v_enrm = (float4 *)d->v_enrm.ptr;
             b.records = (TriRecord *)d->records.ptr; b.rec_eye = (TriEye *)d->rec_eye.ptr;
             b.record_capacity = (uint32_t)std::min<size_t>(rec_cap, 0xFFFFFFFFu);
-            b.chunk_base = (uint32_t *)d->chunk_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
+            b.group_base = (uint32_t *)d->group_base.ptr; b.large_list = (uint32_t *)d->large_list.ptr;
             b.bin_rows = (uint4 *)d->bin_rows.ptr;
             b.counters = (DevCounters *)d->tile_count.ptr;
             b.host_counters = d->h_counters;
