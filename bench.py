@@ -12,7 +12,9 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   value        covered fragments/s with the VBO and texture resident in HBM (device-timed, K frames)
   e2e          the same metric with the per-frame host->device upload of the 98.9 MB vertex buffer from pinned host
                memory and the device->host read-back of the colour plane inside the timed region, through the public
-               gl* API + the C ABI
+               gl* API + the C ABI, pipelined across frames (mtglBufferDataPinned / mtglReadColorAsync at N = 1; at
+               N > 1 a sharded upload + NCCL all-gather into orphaned storage on a side stream and every rank's band
+               read back into one shared page-locked frame); --serial-e2e keeps the strictly sequential form
   roofline     the step's dominant kernel (whichever the live per-group CUDA-event times say): its algorithmic bytes
                per launch / its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline the unmodified reference (as-shipped flags, 1 thread) on this box's host CPU
@@ -26,9 +28,10 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
 Multi-GPU (torchrun, one rank per GPU): sort-first bands of framebuffer rows.  Every rank receives the whole command
 stream; a culling pass drops the 256-triangle chunks that cannot reach its band before set-up touches them, and it
 bins / rasterises only its band.  The raster kernels store every finished tile both locally and -- over NVLink peer
-memory -- into rank 0's colour plane (fused gather); a frame-barrier kernel per rank ends the frame.  NCCL bootstraps
-the group (and all-gathers the sharded vertex-buffer upload of the end-to-end step).  Total work is fixed:
-"scaling": "strong".
+memory -- into rank 0's colour plane (fused gather), or the band follows the frame as one asynchronous peer copy on a
+side stream (--gather copy; 'auto' picks it when more than 64 MB per frame converge on the presenting GPU); a
+frame-barrier kernel per rank ends the frame.  NCCL bootstraps the group (and all-gathers the sharded vertex-buffer
+upload of the end-to-end step).  Total work is fixed: "scaling": "strong".
 """
 from __future__ import annotations
 
@@ -595,15 +598,29 @@ def measure(sess, workload, primary):
         rc = torch.cuda.cudart().cudaHostRegister(host.ctypes.data, 2 * h * w * 4, 0)
         assert int(rc) == 0, f"cudaHostRegister failed ({rc})"
 
+        # The upload is pipelined too: every step the VBO name gets fresh storage (mtgl_context_buffer_orphan), this rank's
+        # slice goes up from pinned memory and the NCCL all-gather completes the buffer on a side stream, and the library's
+        # stream waits for that with an event -- so the fill of step i+1 overlaps the frame of step i on every GPU.
+        L.mtgl_context_buffer_orphan.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
+        fill_stream = torch.cuda.Stream(device=f"cuda:{local}")
+        lib_stream = torch.cuda.ExternalStream(L.mtgl_dev_stream(dev), device=f"cuda:{local}")
+        ctx = L.gl_get_current_context()
+
         def e2e_step(k=0):
             if not is_c3:
-                L.glBindBuffer(GL_ARRAY_BUFFER, vbo)
                 if vbo_dev is not None:
                     part = nbytes // world
-                    L.glBufferSubData(GL_ARRAY_BUFFER, rank * part, part, pinned_in.data_ptr() + rank * part)
-                    dist.all_gather_into_tensor(vbo_dev, vbo_dev[rank * part:(rank + 1) * part])
-                    torch.cuda.current_stream().synchronize()
+                    bp, bs = ctypes.c_void_p(), ctypes.c_uint64()
+                    assert L.mtgl_context_buffer_orphan(ctx, vbo, pinned_in.data_ptr(), ctypes.byref(bp), ctypes.byref(bs)) == 0 and bs.value == nbytes
+                    fresh = torch.as_tensor(DevTensor(bp.value, nbytes), device=f"cuda:{local}")
+                    landed = torch.cuda.Event()
+                    with torch.cuda.stream(fill_stream):
+                        fresh[rank * part:(rank + 1) * part].copy_(pinned_in[rank * part:(rank + 1) * part], non_blocking=True)
+                        dist.all_gather_into_tensor(fresh, fresh[rank * part:(rank + 1) * part])
+                        landed.record(fill_stream)
+                    lib_stream.wait_event(landed)
                 else:
+                    L.glBindBuffer(GL_ARRAY_BUFFER, vbo)
                     L.glBufferData(GL_ARRAY_BUFFER, nbytes, pinned_in.data_ptr(), GL_STATIC_DRAW)
             frame()
             if y1 > y0:
@@ -757,7 +774,7 @@ def measure(sess, workload, primary):
         "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3 / args.steps,
                 "mode": ("pipelined across frames (mtglBufferDataPinned / mtglReadColorAsync)" if (world == 1 and not args.serial_e2e) else
-                         "sharded upload + NCCL all-gather, every rank reads its band back into one shared page-locked frame (mtglReadColorAsync)" if host_gather else
+                         "pipelined: sharded upload + NCCL all-gather into orphaned storage on a side stream, every rank reads its band back into one shared page-locked frame (mtglReadColorAsync)" if host_gather else
                          "upload, render, read-back in sequence")},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -58,6 +58,14 @@ struct mtgl_dev *mtgl_context_device(GLState *ctx);
  * multi-GPU application uploads a slice, an NCCL all-gather over NVLink completes the buffer).  The front end forgets what
  * it knew about the contents; glBufferData makes them known again.  Returns 0 on success. */
 int mtgl_context_buffer_pointer(GLState *ctx, unsigned id, void **ptr, uint64_t *size);
+/* The same for a buffer whose previous contents queued frames may still be reading: the name gets FRESH storage of its
+ * current size (contents undefined; mtgl_dev_buffer_orphan) and *ptr its address.  Fill it on your own stream, then make
+ * the context's stream (mtgl_dev_stream(mtgl_context_device(ctx))) wait for that work before the draws that read it.
+ * `contents`: NULL, or host memory holding the bytes the buffer WILL contain once the fill has landed -- the front end
+ * then takes the few bytes it needs for host-visible side effects (the last element of an array draw becomes the current
+ * normal / colour / texture coordinate, gl_api.c:1826-1842) from there, as glBufferData does, instead of reading them
+ * back from the device at every draw (which waits for everything queued). */
+int mtgl_context_buffer_orphan(GLState *ctx, unsigned id, const void *contents, void **ptr, uint64_t *size);
 
 /* Display-list geometry drawn as compiled array draws so far (glBegin ... glEnd stretches of a list that were queued as
  * one draw record instead of being replayed call by call) -- for tools and tests. */

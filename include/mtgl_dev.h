@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MTGL_DEV_ABI_VERSION 5
+#define MTGL_DEV_ABI_VERSION 6
 
 /* error codes */
 #define MTGL_OK            0
@@ -272,6 +272,12 @@ int mtgl_dev_buffer_read(mtgl_dev *dev, uint32_t id, uint64_t offset, uint64_t s
  * do not touch the plane before the copy has left it.  mtgl_dev_finish waits for uploads, batches and read-backs. */
 int mtgl_dev_buffer_data_pinned(mtgl_dev *dev, uint32_t id, uint64_t size, const void *pinned_data);
 int mtgl_dev_read_color_async(mtgl_dev *dev, int32_t y0, int32_t y1, uint32_t *pinned_color);
+/* mtgl_dev_buffer_orphan is the first half of mtgl_dev_buffer_data_pinned alone: the buffer name gets fresh storage of
+ * `size` bytes that no submitted batch reads (contents undefined) and *ptr receives its device address.  The caller fills
+ * it on a stream of its own -- a slice from host memory plus an NCCL all-gather over NVLink, say -- and orders the
+ * context's stream (mtgl_dev_stream) behind that work with an event before it issues draws that read the buffer.  The
+ * fill of frame i+1 then overlaps the rasterisation of frame i. */
+int mtgl_dev_buffer_orphan(mtgl_dev *dev, uint32_t id, uint64_t size, void **ptr);
 
 /* texture_upload_* (textures.c:141-269) after conversion to RGBA8 words (a<<24|b<<16|g<<8|r);
  * also builds mip level 1 the way texture_generate_mip1 does (textures.c:311-354). */

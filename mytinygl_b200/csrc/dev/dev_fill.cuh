@@ -14,6 +14,9 @@ constexpr uint32_t FILL_MAX_LIST = 1024;        /* longest tile list k_fill sort
 constexpr uint32_t FILL_MIN_AVG_AREA = 1024;    /* mean clamped box area (pixels of the 64x64 tile) per list entry from which
                                                  * one-thread-per-pixel beats one-warp-per-8x4-block: a quarter of the tile */
 enum : uint32_t { FILL_OFF = 0u, FILL_AUTO = 1u, FILL_ALWAYS = 2u };
+/* pseudo-flag next to the RC_* bits in RasterPlan::in_order_all: every alpha test of the pass is GL_GREATER (C3's, and the
+ * usual cut-out test) -- the kernel instance for it compares instead of decoding the function per fragment */
+constexpr uint32_t FILL_ALPHA_GREATER = 1u << 30;
 
 /* Called by every thread of the CTA (blockDim.x threads; *acc is a shared word nobody else uses).  The answer is uniform.
  * tflags: bit 0 = the tile holds a record that needs in-order shading, bit 2 = it holds a line or a point. */

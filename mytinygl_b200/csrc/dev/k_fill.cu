@@ -316,7 +316,7 @@ __device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &s
                 const float aref = __uint_as_float(T.s1.z);
                 any = false;
 #pragma unroll
-                for (int p = 0; p < P; p++) any = any || (H.cov[p] && compare_f_mask(acmp, H.ta[p], aref));
+                for (int p = 0; p < P; p++) any = any || (H.cov[p] && ((ON & FILL_ALPHA_GREATER) ? (H.ta[p] > aref) : compare_f_mask(acmp, H.ta[p], aref)));
                 if (!any) {         /* the stencil / depth stages of the triangle still run (fill_one), the colour stages cannot be reached */
 #pragma unroll
                     for (int p = 0; p < P; p++) { H.tr[p] = 0.0f; H.tg[p] = 0.0f; H.tb[p] = 0.0f; }
@@ -414,7 +414,7 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
         const uint32_t acmp = (ps >> PS_ALPHA_CMP_SHIFT) & 15u;
         const float aref = __uint_as_float(T.s1.z);
 #pragma unroll
-        for (int p = 0; p < P; p++) act[p] = act[p] && compare_f_mask(acmp, H.ta[p], aref);
+        for (int p = 0; p < P; p++) act[p] = act[p] && ((ON & FILL_ALPHA_GREATER) ? (H.ta[p] > aref) : compare_f_mask(acmp, H.ta[p], aref));
     }
     bool any = false;
 #pragma unroll
@@ -619,6 +619,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
  * leave the kernel.  Everything else runs the fully dynamic instance. */
 constexpr uint32_t FILL_FAST_ON = RC_TEXTURED;
 constexpr uint32_t FILL_FAST_OFF = RC_DEPTH_TEST | RC_FOG | RC_FLAT;
+constexpr uint32_t FILL_FASTER_ON = RC_TEXTURED | FILL_ALPHA_GREATER;     /* ... and every alpha test is GL_GREATER */
 
 void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
                  cudaStream_t s)
@@ -629,13 +630,16 @@ void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaFuncSetAttribute(k_fill<0u, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
         cudaFuncSetAttribute(k_fill<FILL_FAST_ON, FILL_FAST_OFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
+        cudaFuncSetAttribute(k_fill<FILL_FASTER_ON, FILL_FAST_OFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FillSmem));
         configured[dev] = true;
     }
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0 || fill_mode == FILL_OFF) return;
     const uint32_t split = small_grid(tiles) ? 4u : 1u;     /* (1, 2, 4 or 8: the tile is walked in eight passes of eight rows) */
     /* all_on / any_on: AND / OR of the RasterCfg flags of the pass's in-order states */
-    if ((all_on & FILL_FAST_ON) == FILL_FAST_ON && (any_on & FILL_FAST_OFF) == 0u)
+    if ((all_on & FILL_FASTER_ON) == FILL_FASTER_ON && (any_on & FILL_FAST_OFF) == 0u)
+        k_fill<FILL_FASTER_ON, FILL_FAST_OFF><<<tiles * split, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode, split);
+    else if ((all_on & FILL_FAST_ON) == FILL_FAST_ON && (any_on & FILL_FAST_OFF) == 0u)
         k_fill<FILL_FAST_ON, FILL_FAST_OFF><<<tiles * split, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode, split);
     else
         k_fill<0u, 0u><<<tiles * split, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode, split);

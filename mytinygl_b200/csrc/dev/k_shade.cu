@@ -13,7 +13,8 @@
  *   texels  small textures have a float4 copy in HBM (n / 255 per channel, built at glTexImage2D time; dev_fasttex.cuh):
  *           a bilinear tap is one 16-byte load through L1, the trilinear sample of a C4 fragment 8 of them, instead of 8
  *           4-byte loads and 32 shift / mask / table look-ups;
- *   pass 2  TWO pixels per thread and iteration (independent instruction streams): record -> barycentrics with the
+ *   pass 2  P pixels per thread and iteration (shipped: one, at 64 registers and 4 CTAs per SM; two independent streams
+ *           per thread at 2-3 CTAs per SM measured slower): record -> barycentrics with the
  *           reference's expressions (raster.c:534-544) -> colour, texel (sampler plan from the record's LOD), texenv, fog
  *           -> packed colour into the tile.  Fragments that cannot take the float4 path -- per-fragment lighting, a large
  *           texture, REPEAT with a size that is no power of two, non-finite attributes -- go through the general code
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
 
     __syncthreads();
 
-    /* ---- pass 2: shade the compacted pixels, two per thread and iteration ---- */
+    /* ---- pass 2: shade the compacted pixels, P per thread and iteration ---- */
     for (uint32_t i0 = threadIdx.x; i0 < n; i0 += P * SHADE_THREADS) {
         int ci[P];
         uint32_t r[P], out[P];

@@ -541,14 +541,11 @@ int mtgl_dev_buffer_data(mtgl_dev *d, uint32_t id, uint64_t size, const void *da
     return MTGL_OK;
 }
 
-int mtgl_dev_buffer_data_pinned(mtgl_dev *d, uint32_t id, uint64_t size, const void *data)
+/* the buffer name gets storage of `size` bytes that nobody reads.  The storage it has now may still be read by batches
+ * already submitted: it is orphaned behind an event on the main stream (recycled by a later call once the event has
+ * passed) */
+static int fresh_storage(mtgl_dev *d, BufObj &b, uint64_t size)
 {
-    if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
-    if (size == 0 || !data) return mtgl_dev_buffer_data(d, id, size, data);
-    CU(cudaSetDevice(d->device));
-    BufObj &b = d->buf[id];
-    /* the storage the name has now may still be read by batches already submitted: orphan it behind an event on the main
-     * stream (recycled by a later call once the event has passed), and give the name storage nobody reads */
     if (b.ptr) {
         mtgl_dev::Orphan o{ b.ptr, b.size, nullptr };
         for (mtgl_dev::Orphan &f : d->orphans) if (!f.ptr && f.ev) { o.ev = f.ev; f.ev = nullptr; break; }
@@ -576,9 +573,31 @@ int mtgl_dev_buffer_data_pinned(mtgl_dev *d, uint32_t id, uint64_t size, const v
     }
     b.ptr = fresh; b.size = size;
     b.gen++; b.draws_since_write = 0; b.exposed = false;
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_data_pinned(mtgl_dev *d, uint32_t id, uint64_t size, const void *data)
+{
+    if (!d || id == 0 || id >= kMaxBuffers) return MTGL_E_INVALID;
+    if (size == 0 || !data) return mtgl_dev_buffer_data(d, id, size, data);
+    CU(cudaSetDevice(d->device));
+    BufObj &b = d->buf[id];
+    if (int rc = fresh_storage(d, b, size)) return rc;
     CU(cudaMemcpyAsync(b.ptr, data, size, cudaMemcpyHostToDevice, d->upload_stream));
     CU(cudaEventRecord(d->upload_ev, d->upload_stream));
     d->upload_pending = true;
+    return MTGL_OK;
+}
+
+int mtgl_dev_buffer_orphan(mtgl_dev *d, uint32_t id, uint64_t size, void **ptr)
+{
+    if (!d || id == 0 || id >= kMaxBuffers || size == 0 || !ptr) return MTGL_E_INVALID;
+    CU(cudaSetDevice(d->device));
+    BufObj &b = d->buf[id];
+    if (d->upload_pending) CU(cudaStreamSynchronize(d->upload_stream));     /* a queued pinned upload may target the storage being orphaned */
+    if (int rc = fresh_storage(d, b, size)) return rc;
+    b.exposed = true;                   /* the caller writes the storage directly */
+    *ptr = b.ptr;
     return MTGL_OK;
 }
 
@@ -1019,7 +1038,8 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
         for (const PassDraw &q : passes[pidx]) {
             const mtgl_draw &dq = bt->draws[q.draw];
             const mtgl_state &sq = bt->states[dq.raster_state];
-            const uint32_t cf = cfgs[dq.raster_state].flags;
+            uint32_t cf = cfgs[dq.raster_state].flags;
+            if (!(cf & RC_ALPHA_TEST) || cfgs[dq.raster_state].alpha_func == 4u) cf |= FILL_ALPHA_GREATER;    /* (pseudo-flag for launch_fill) */
             const bool filled = dq.mode >= G_TRIANGLES && sq.polygon_mode_front == G_FILL && sq.polygon_mode_back == G_FILL;
             if ((cf & RC_DEFER) && filled) any_defer = true; else any_in_order = true;
             if ((cf & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */

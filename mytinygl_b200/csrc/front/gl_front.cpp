@@ -493,6 +493,29 @@ int mtgl_context_buffer_pointer(GLState *c, unsigned id, void **ptr, uint64_t *s
     return mtgl_dev_buffer_pointer(c->dev, id, ptr, size);
 }
 
+int mtgl_context_buffer_orphan(GLState *c, unsigned id, const void *contents, void **ptr, uint64_t *size)
+{
+    if (!c || !ptr) return MTGL_E_INVALID;
+    Buffer *b = get_buffer(c, id);
+    if (!b || !b->has_data || b->size == 0) return MTGL_E_INVALID;
+    flush_batch(c);                             /* queued draws read the storage the name has now */
+    if (contents) {                             /* what the host has looked at before, from the contents to come (as glBufferData) */
+        for (Buffer::Peek &p : b->peeks) std::memcpy(p.raw, (const uint8_t *)contents + p.off, p.n);
+        b->peeks_frozen = false;
+        if (b->size <= kHostMirrorLimit) {
+            b->data.assign((const uint8_t *)contents, (const uint8_t *)contents + b->size);
+            b->host_valid = true;
+        }
+    } else {
+        b->peeks.clear();
+        b->peeks_frozen = true;
+        b->host_valid = false;
+        b->data.clear();
+    }
+    if (size) *size = b->size;
+    return mtgl_dev_buffer_orphan(c->dev, id, b->size, ptr);
+}
+
 const mtgl_framebuffer *mtgl_map_framebuffer(GLState *c, unsigned planes)
 {
     if (!c) return nullptr;

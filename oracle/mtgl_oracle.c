@@ -1108,6 +1108,14 @@ int mtgl_dev_buffer_pointer(mtgl_dev *d, uint32_t id, void **ptr, uint64_t *size
     return MTGL_OK;
 }
 
+int mtgl_dev_buffer_orphan(mtgl_dev *d, uint32_t id, uint64_t size, void **ptr)     /* nothing is in flight here: same storage, resized */
+{
+    if (!d || id == 0 || id >= O_MAX_BUFFERS || size == 0 || !ptr) return MTGL_E_INVALID;
+    if (d->buf[id].size != size) { int rc = mtgl_dev_buffer_data(d, id, size, NULL); if (rc) return rc; }
+    *ptr = d->buf[id].data;
+    return MTGL_OK;
+}
+
 /* the pipelined forms (include/mtgl_dev.h) are the synchronous ones here: the oracle executes every call at once */
 int mtgl_dev_buffer_data_pinned(mtgl_dev *d, uint32_t id, uint64_t size, const void *data) { return mtgl_dev_buffer_data(d, id, size, data); }
 int mtgl_dev_read_color_async(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *color) { return mtgl_dev_read_framebuffer(d, y0, y1, color, NULL, NULL); }

@@ -28,7 +28,7 @@ def test_exports_device_abi(lib):
     for n in names:
         assert hasattr(lib, n), n
     lib.mtgl_dev_abi_version.restype = ctypes.c_int
-    assert lib.mtgl_dev_abi_version() == 5
+    assert lib.mtgl_dev_abi_version() == 6
 
 
 def test_exports_gl_api(lib):

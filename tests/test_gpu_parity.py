@@ -252,6 +252,72 @@ def test_pipelined_transfers_match_the_synchronous_path(b200):
     b200.destroy()
 
 
+def test_orphaned_buffer_filled_on_a_side_stream(b200):
+    """mtgl_context_buffer_orphan (include/mtgl_context.h): the buffer name gets fresh storage every frame, the application
+    fills it on a stream of its own (here: a device-to-device copy, in bench.py a host slice + NCCL all-gather) while earlier
+    frames are still in flight, and orders the context's stream behind the fill with an event.  Same pixels as glBufferData."""
+    import ctypes
+    import torch
+    L = b200.lib
+    w, h, variant = 480, 270, 3 | (2 << 8)
+    L.scene_c4_host_data.restype = ctypes.c_void_p
+    L.scene_c4_vbo.restype = ctypes.c_uint
+    L.glBindBuffer.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    L.glBufferData.argtypes = [ctypes.c_uint, ctypes.c_long, ctypes.c_void_p, ctypes.c_uint]
+    L.mtglReadColorAsync.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.gl_get_current_context.restype = ctypes.c_void_p
+    L.mtgl_context_buffer_orphan.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
+    L.mtgl_dev_stream.restype = ctypes.c_void_p
+    L.mtgl_dev_stream.argtypes = [ctypes.c_void_p]
+    b200.create(w, h)
+    L.scene_c4_setup(w, h, variant)
+    nv = L.scene_c4_vertex_count()
+    base = np.ctypeslib.as_array(ctypes.cast(L.scene_c4_host_data(), ctypes.POINTER(ctypes.c_float)), shape=(nv, 8)).copy()
+    frames = []
+    for k in range(5):
+        f = base.copy()
+        f[:, 0] = f[:, 0] * (1.0 - 0.06 * k) + 0.09 * k
+        f[:, 1] -= 0.04 * k
+        frames.append(np.ascontiguousarray(f))
+    vbo = L.scene_c4_vbo()
+    want = []
+    for f in frames:
+        L.glBindBuffer(0x8892, vbo)
+        L.glBufferData(0x8892, f.nbytes, f.ctypes.data, 0x88E4)
+        L.scene_c4_draw()
+        want.append(b200.read()[0].copy())
+
+    class DevTensor:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    staged = [torch.from_numpy(f.view(np.uint8).reshape(-1)).cuda() for f in frames]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    lib_stream = torch.cuda.ExternalStream(L.mtgl_dev_stream(b200.device()))
+    ctx = L.gl_get_current_context()
+    outs = [np.zeros((h, w), np.uint32) for _ in frames]
+    seen = set()
+    for k, (f, src, o) in enumerate(zip(frames, staged, outs)):
+        ptr, size = ctypes.c_void_p(), ctypes.c_uint64()
+        hint = f.ctypes.data if k % 2 == 0 else None        # with and without the host copy of the contents to come
+        assert L.mtgl_context_buffer_orphan(ctx, vbo, hint, ctypes.byref(ptr), ctypes.byref(size)) == 0 and size.value == f.nbytes
+        seen.add(ptr.value)
+        dst = torch.as_tensor(DevTensor(ptr.value, f.nbytes), device="cuda")
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            dst.copy_(src, non_blocking=True)
+            ev.record(side)
+        lib_stream.wait_event(ev)
+        L.scene_c4_draw()
+        L.mtglReadColorAsync(0, h, o.ctypes.data)
+    L.glFinish()
+    assert L.glGetError() == 0
+    assert len(seen) >= 1
+    for k, (a, o) in enumerate(zip(want, outs)):
+        assert np.array_equal(a, o), f"frame {k}"
+    b200.destroy()
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 6])
 def test_indexed_draws_share_vertices(b200, front_oracle, variant, monkeypatch):
     """glDrawElements (gl_api.c:1854-1941) re-emits a vertex per index; the back end runs the vertex stage once per buffer
