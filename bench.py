@@ -159,9 +159,11 @@ def run_reference(args, workload, steps=None, warmup=None):
         # mix and the per-fragment work are the same for every quad), scaled to the frame by fragment count
         sample_quads = 8
         frac = sample_quads / 64.0
+        lib.lib.scene_c3_setup(w, h, sample_quads | (variant & 256))
         for i in range(min(warm, 1) + min(steps, 3)):
             t0 = time.perf_counter()
-            lib.lib.scene_render(b"c3_fill", w, h, sample_quads | (variant & 256))
+            lib.lib.scene_c3_draw()
+            lib.lib.glFinish()
             if i >= min(warm, 1):
                 times.append((time.perf_counter() - t0) / frac)
         sample = f"{len(times)} steps of {sample_quads} of the 64 full-screen quads each, time scaled by 64/{sample_quads}"
@@ -334,12 +336,14 @@ def measure(sess, workload, primary):
         assert L.mtgl_dev_set_band(dev, y0, y1) == 0
 
     is_c3 = workload in ("c3", "c3s")
-    if not is_c3:
+    if is_c3:
+        L.scene_c3_setup(w, h, variant)     # state + texture once; the frame is the clear and the 64 quads
+    else:
         L.scene_c4_setup(w, h, variant)
 
     def frame():
         if is_c3:
-            L.scene_render(b"c3_fill", w, h, variant)
+            L.scene_c3_draw()
         else:
             L.scene_c4_draw()
 

@@ -387,7 +387,7 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
         const uint32_t scmp = (ps >> PS_STENCIL_CMP_SHIFT) & 15u, smask = (ps >> PS_STENCIL_MASK_SHIFT) & 0xFFu, swm = (ps >> PS_STENCIL_WMASK_SHIFT) & 0xFFu;
         const int32_t mref = (int32_t)s0.z;
         const StencilOp zpass_op = stencil_op_decode(s0.w);
-        if ((scmp & 7u) == 7u && !depth_test) {      /* GL_ALWAYS without a depth test: every covered fragment takes the zpass op */
+        if (((ON & FILL_STENCIL_ALWAYS) || (scmp & 7u) == 7u) && !depth_test) {      /* GL_ALWAYS without a depth test: every covered fragment takes the zpass op */
 #pragma unroll
             for (int p = 0; p < P; p++) {
                 const uint32_t sval = S.stencil[p];
@@ -440,7 +440,7 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
         }
     }
     if (textured) {
-        const uint32_t env = cfg->tex_env_mode;
+        const uint32_t env = (ON & FILL_MODULATE) ? (uint32_t)G_MODULATE : cfg->tex_env_mode;
         if (env == G_MODULATE) {
 #pragma unroll
             for (int p = 0; p < P; p++) { cr[p] = cr[p] * H.tr[p]; cg[p] = cg[p] * H.tg[p]; cb[p] = cb[p] * H.tb[p]; ca[p] = ca[p] * H.ta[p]; }
@@ -475,8 +475,8 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
 
     const bool blend = has(RC_BLEND);
     const uint32_t bfunc = T.s1.w, bsrc = bfunc >> 16, bdst = bfunc & 0xFFFFu;
-    const bool blend_alpha = bfunc == ((G_SRC_ALPHA << 16) | G_ONE_MINUS_SRC_ALPHA);       /* the usual transparency blend, without the switches */
-    const uint32_t cm = ps >> PS_COLOR_MASK_SHIFT;
+    const bool blend_alpha = (ON & FILL_BLEND_ALPHA) || bfunc == ((G_SRC_ALPHA << 16) | G_ONE_MINUS_SRC_ALPHA);       /* the usual transparency blend, without the switches */
+    const uint32_t cm = (ON & FILL_FULL_MASK) ? 0xFu : ps >> PS_COLOR_MASK_SHIFT;
 #pragma unroll
     for (int p = 0; p < P; p++) {
         if (!act[p]) continue;
@@ -595,7 +595,8 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
                 while (e < n && (__float_as_uint(sm.tri[e].eb.w) & PT_COINCIDENT)) e++;
                 Shared H;
                 if (fill_shared<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, e == t + 1, H)) {
-#pragma unroll 1
+                    constexpr int UNROLL = ((ON & FILL_PSEUDO) == FILL_PSEUDO) ? 2 : 1;     /* the small instance: two members in flight */
+#pragma unroll UNROLL
                     for (; t < e; t++) fill_one<ON, OFF>(b, sm.tri[t], H, S);
                 }
                 t = e;
@@ -619,7 +620,9 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
  * leave the kernel.  Everything else runs the fully dynamic instance. */
 constexpr uint32_t FILL_FAST_ON = RC_TEXTURED;
 constexpr uint32_t FILL_FAST_OFF = RC_DEPTH_TEST | RC_FOG | RC_FLAT;
-constexpr uint32_t FILL_FASTER_ON = RC_TEXTURED | FILL_ALPHA_GREATER;     /* ... and every alpha test is GL_GREATER */
+/* ... and the mix itself: textured, alpha-tested (GREATER), stencil (ALWAYS), blended (SRC_ALPHA, ONE_MINUS_SRC_ALPHA),
+ * MODULATE, full colour mask */
+constexpr uint32_t FILL_FASTER_ON = RC_TEXTURED | RC_ALPHA_TEST | RC_STENCIL | RC_BLEND | FILL_PSEUDO;
 
 void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
                  cudaStream_t s)

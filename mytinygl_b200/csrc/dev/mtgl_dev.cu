@@ -1039,7 +1039,7 @@ int mtgl_dev_submit(mtgl_dev *d, const mtgl_batch *bt)
             const mtgl_draw &dq = bt->draws[q.draw];
             const mtgl_state &sq = bt->states[dq.raster_state];
             uint32_t cf = cfgs[dq.raster_state].flags;
-            if (!(cf & RC_ALPHA_TEST) || cfgs[dq.raster_state].alpha_func == 4u) cf |= FILL_ALPHA_GREATER;    /* (pseudo-flag for launch_fill) */
+            cf |= fill_pseudo_flags(cfgs[dq.raster_state]);         /* (for launch_fill's choice of kernel instance) */
             const bool filled = dq.mode >= G_TRIANGLES && sq.polygon_mode_front == G_FILL && sq.polygon_mode_back == G_FILL;
             if ((cf & RC_DEFER) && filled) any_defer = true; else any_in_order = true;
             if ((cf & RC_DEFER) && !filled && dq.mode >= G_TRIANGLES) any_defer = true;   /* mixed fill/outline faces */

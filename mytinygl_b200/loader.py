@@ -58,6 +58,7 @@ class SceneLibrary:
         L.scene_render.restype = ctypes.c_int
         L.scene_render.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.scene_c4_setup.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.scene_c3_setup.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.scene_c4_vertex_count.restype = ctypes.c_int
         L.scene_count.restype = ctypes.c_int
         L.scene_name.restype = ctypes.c_char_p

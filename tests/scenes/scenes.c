@@ -277,10 +277,14 @@ static void scene_c2_texenv(int w, int h, int variant)
 /* C3: fill-rate stress.  variant bits 0-7 = number of full-screen quads (0 -> 64); bit 8: every quad gets its own texture
  * coordinates (shifted by q / 512), so that no two quads sample the same texels -- the layers are then no longer
  * coincident for the texture stage (a diagnostic variant, not a BASELINE configuration). */
-static void scene_c3(int w, int h, int variant)
+static struct { int nq, shifted; } c3;
+
+/* the state and the texture are set up once per context (scene_c3_setup), scene_c3_draw issues the frame: the clear and
+ * the quads -- what bench.py times as a step, like scene_c4_setup / scene_c4_draw */
+void scene_c3_setup(int w, int h, int variant)
 {
-    int nq = (variant & 0xFF) > 0 ? (variant & 0xFF) : 64;
-    int shifted = (variant >> 8) & 1;
+    c3.nq = (variant & 0xFF) > 0 ? (variant & 0xFF) : 64;
+    c3.shifted = (variant >> 8) & 1;
     glViewport(0, 0, w, h);
     glMatrixMode(GL_PROJECTION);
     glLoadIdentity();
@@ -302,18 +306,28 @@ static void scene_c3(int w, int h, int variant)
     glStencilOp(GL_KEEP, GL_KEEP, GL_INCR_WRAP);
     glEnable(GL_BLEND);
     glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA);
+}
+
+void scene_c3_draw(void)
+{
     glClear(GL_COLOR_BUFFER_BIT | GL_STENCIL_BUFFER_BIT);
     glBegin(GL_QUADS);
-    for (int q = 0; q < nq; q++) {
+    for (int q = 0; q < c3.nq; q++) {
         glColor4f((float)((q * 37) % 64) / 63.0f, (float)((q * 11) % 64) / 63.0f, (float)((q * 5) % 64) / 63.0f,
                   (q & 1) ? 0.75f : 0.25f);
-        float o = shifted ? (float)q / 512.0f : 0.0f;
+        float o = c3.shifted ? (float)q / 512.0f : 0.0f;
         glTexCoord2f(0.0f + o, 0.0f); glVertex2f(-1.0f, -1.0f);
         glTexCoord2f(1.0f + o, 0.0f); glVertex2f(1.0f, -1.0f);
         glTexCoord2f(1.0f + o, 1.0f); glVertex2f(1.0f, 1.0f);
         glTexCoord2f(0.0f + o, 1.0f); glVertex2f(-1.0f, 1.0f);
     }
     glEnd();
+}
+
+static void scene_c3(int w, int h, int variant)
+{
+    scene_c3_setup(w, h, variant);
+    scene_c3_draw();
 }
 
 /* C4 / C5: grid of Suzannes through one interleaved VBO (pos3 normal3 uv2 = 32 B / vertex).
