@@ -200,6 +200,11 @@ def band_rows(height, rank, world):
     return min(lo * 64, height), min(hi * 64, height)
 
 
+def nbytes_ok(nbytes, parts):
+    """True when a buffer of nbytes splits into `parts` equal 16-byte-aligned pieces."""
+    return nbytes > 0 and nbytes % (parts * 16) == 0
+
+
 def rebalanced(bounds, times, height, quantum=16):
     """New band boundaries from the ranks' last frame times: cost density taken as uniform inside each current band,
     boundaries moved (half way, for stability) to where the cumulative cost reaches k/N of the total, snapped to
@@ -606,22 +611,37 @@ def measure(sess, workload, primary):
         # slice goes up from pinned memory and the NCCL all-gather completes the buffer on a side stream, and the library's
         # stream waits for that with an event -- so the fill of step i+1 overlaps the frame of step i on every GPU.
         L.mtgl_context_buffer_orphan.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
-        fill_stream = torch.cuda.Stream(device=f"cuda:{local}")
+        # The buffer goes up in `pieces` chunks, each cut into one slice per rank: while the all-gather of chunk c runs over
+        # NVLink (gather stream), this rank's slice of chunk c + 1 crosses PCIe (upload stream).
+        up_stream = torch.cuda.Stream(device=f"cuda:{local}")
+        gather_stream = torch.cuda.Stream(device=f"cuda:{local}")
         lib_stream = torch.cuda.ExternalStream(L.mtgl_dev_stream(dev), device=f"cuda:{local}")
         ctx = L.gl_get_current_context()
+        pieces = int(os.environ.get("MTGL_BENCH_PIECES", "4"))
+        if not nbytes_ok(nbytes if not is_c3 else 0, pieces * world):
+            pieces = 1
 
         def e2e_step(k=0):
             if not is_c3:
                 if vbo_dev is not None:
-                    part = nbytes // world
                     bp, bs = ctypes.c_void_p(), ctypes.c_uint64()
                     assert L.mtgl_context_buffer_orphan(ctx, vbo, pinned_in.data_ptr(), ctypes.byref(bp), ctypes.byref(bs)) == 0 and bs.value == nbytes
                     fresh = torch.as_tensor(DevTensor(bp.value, nbytes), device=f"cuda:{local}")
+                    chunk = nbytes // pieces
+                    sub = chunk // world
+                    up_done = [torch.cuda.Event() for _ in range(pieces)]
                     landed = torch.cuda.Event()
-                    with torch.cuda.stream(fill_stream):
-                        fresh[rank * part:(rank + 1) * part].copy_(pinned_in[rank * part:(rank + 1) * part], non_blocking=True)
-                        dist.all_gather_into_tensor(fresh, fresh[rank * part:(rank + 1) * part])
-                        landed.record(fill_stream)
+                    with torch.cuda.stream(up_stream):
+                        for c in range(pieces):
+                            o = c * chunk + rank * sub
+                            fresh[o:o + sub].copy_(pinned_in[o:o + sub], non_blocking=True)
+                            up_done[c].record(up_stream)
+                    with torch.cuda.stream(gather_stream):
+                        for c in range(pieces):
+                            o = c * chunk + rank * sub
+                            gather_stream.wait_event(up_done[c])
+                            dist.all_gather_into_tensor(fresh[c * chunk:(c + 1) * chunk], fresh[o:o + sub])
+                        landed.record(gather_stream)
                     lib_stream.wait_event(landed)
                 else:
                     L.glBindBuffer(GL_ARRAY_BUFFER, vbo)

@@ -68,10 +68,11 @@ struct __align__(16) PrepTri {
     float4 te;      /* eye z0 z1 z2 | 1/w2 */
     float4 p0;      /* x0 y0 x1 y1 as floats: the reference form of the edge functions */
     float4 p1;      /* x2 y2 | sampler plan | trilinear weight */
-    uint4 s0;       /* state, decoded once per (triangle, tile): RasterCfg flags | PS_* word | masked stencil reference | stencil zpass op */
+    uint4 s0;       /* state, decoded once per (triangle, tile): RasterCfg flags | PS_* word | masked stencil reference | zpass op: hi */
     uint4 s1;       /* stencil fail op | stencil zfail op | alpha reference (float bits) | blend_src << 16 | blend_dst */
+    int4 so;        /* the stencil zpass op, decoded (dev_fragment.cuh StencilOp): and-mask | xor-mask | add | lo */
 };
-static_assert(sizeof(PrepTri) == 224, "PrepTri layout");
+static_assert(sizeof(PrepTri) == 240, "PrepTri layout");
 
 /* PrepTri::s0.y: comparison masks (dev_fragment.cuh, compare_mask) and small enums */
 constexpr uint32_t PS_STENCIL_CMP_SHIFT = 0, PS_DEPTH_CMP_SHIFT = 4, PS_ALPHA_CMP_SHIFT = 8;     /* 4 bits each */
@@ -85,6 +86,7 @@ struct FillSmem {
     uint32_t rec[FILL_MAX_LIST];
     uint32_t sorted[FILL_MAX_LIST];
     float un[256];
+    uint8_t run_end[FILL_WINDOW];   /* for the first triangle of a run of coincident triangles: index behind the run's last */
     uint32_t acc;               /* scratch of fill_owns_tile */
     uint32_t tex_cfg;           /* state index whose texture is staged (lowest textured state of the list), ~0 = none */
     StagedTex st;
@@ -198,7 +200,9 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
                         (compare_mask(cfg->alpha_func) << PS_ALPHA_CMP_SHIFT) | ((cfg->stencil_mask & 0xFFu) << PS_STENCIL_MASK_SHIFT) |
                         ((cfg->stencil_writemask & 0xFFu) << PS_STENCIL_WMASK_SHIFT) | ((cfg->color_mask & 0xFu) << PS_COLOR_MASK_SHIFT);
     /* raster.c:407-422 compares (ref & mask) with (value & mask); the value has 8 bits, the reference and the mask need not */
-    P.s0 = make_uint4(cflags, ps, (uint32_t)cfg->stencil_ref & cfg->stencil_mask, stencil_op_encode(cfg->stencil_zpass, cfg->stencil_ref));
+    const StencilOp zp = stencil_op_decode(stencil_op_encode(cfg->stencil_zpass, cfg->stencil_ref));
+    P.s0 = make_uint4(cflags, ps, (uint32_t)cfg->stencil_ref & cfg->stencil_mask, (uint32_t)zp.hi);
+    P.so = make_int4((int)zp.amask, (int)zp.xmask, zp.add, zp.lo);
     P.s1 = make_uint4(stencil_op_encode(cfg->stencil_fail, cfg->stencil_ref), stencil_op_encode(cfg->stencil_zfail, cfg->stencil_ref),
                       __float_as_uint(cfg->alpha_ref), (cfg->blend_src << 16) | (cfg->blend_dst & 0xFFFFu));
 }
@@ -386,7 +390,8 @@ __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, co
         const uint4 s1 = T.s1;
         const uint32_t scmp = (ps >> PS_STENCIL_CMP_SHIFT) & 15u, smask = (ps >> PS_STENCIL_MASK_SHIFT) & 0xFFu, swm = (ps >> PS_STENCIL_WMASK_SHIFT) & 0xFFu;
         const int32_t mref = (int32_t)s0.z;
-        const StencilOp zpass_op = stencil_op_decode(s0.w);
+        const int4 so = T.so;
+        const StencilOp zpass_op = { (uint32_t)so.x, (uint32_t)so.y, so.z, so.w, (int)s0.w };
         if (((ON & FILL_STENCIL_ALWAYS) || (scmp & 7u) == 7u) && !depth_test) {      /* GL_ALWAYS without a depth test: every covered fragment takes the zpass op */
 #pragma unroll
             for (int p = 0; p < P; p++) {
@@ -566,6 +571,12 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
         if (threadIdx.x < n)        /* (a run of coincident triangles does not continue across windows) */
             prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu, px0, py0);
         __syncthreads();
+        if (threadIdx.x < n) {      /* where the run of coincident triangles that starts here ends (every pixel row walks the runs) */
+            uint32_t e = threadIdx.x + 1u;
+            while (e < n && (__float_as_uint(sm.tri[e].eb.w) & PT_COINCIDENT)) e++;
+            sm.run_end[threadIdx.x] = (uint8_t)e;
+        }
+        __syncthreads();
 
         const int g_per = (TILE_H / 8) / (int)split;
         for (int g = (int)sub * g_per; g < ((int)sub + 1) * g_per; g++) {
@@ -591,8 +602,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
 #pragma unroll 1
             for (uint32_t t = 0; t < n;) {
                 /* the run of coincident triangles that starts at t: coverage, barycentrics and texel once, then each member */
-                uint32_t e = t + 1;
-                while (e < n && (__float_as_uint(sm.tri[e].eb.w) & PT_COINCIDENT)) e++;
+                const uint32_t e = sm.run_end[t];
                 Shared H;
                 if (fill_shared<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, e == t + 1, H)) {
                     constexpr int UNROLL = ((ON & FILL_PSEUDO) == FILL_PSEUDO) ? 2 : 1;     /* the small instance: two members in flight */
