@@ -532,7 +532,7 @@ def measure(sess, workload, primary):
     rstage = np.array(list(st.cum_raster_ms)) - cum0[3]
     batch_ms = st.cum_batch_ms - cum0[1]
     if os.environ.get("MTGL_BENCH_DEBUG"):
-        print(f"[rank {rank}] {workload} stages {np.round(stage / args.steps, 4).tolist()} raster {np.round(rstage / args.steps, 4).tolist()} dev_ms {dev_ms_total / args.steps:.4f}", file=sys.stderr, flush=True)
+        print(f"[rank {rank}] {workload} stages {np.round(stage / args.steps, 4).tolist()} raster {np.round(rstage / args.steps, 4).tolist()} dev_ms {dev_ms_total / args.steps:.4f} records {int(st.triangles_setup)} tile_refs {int(st.tile_refs)}", file=sys.stderr, flush=True)
     launches = int(st.kernel_launches - launches0)
     clocks = sampler.stop() if (rank == 0 and primary) else None
 

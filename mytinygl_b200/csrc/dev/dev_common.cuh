@@ -505,7 +505,7 @@ void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const Clear
                           bool all_range01, cudaStream_t s);
 void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);
 void launch_read_pixels(const FrameTargets &fb, int32_t x, int32_t y, int32_t w, int32_t h, uint32_t bpp, uint8_t *dst, cudaStream_t s);
-void launch_frame_barrier(unsigned long long *counter, unsigned long long target, cudaStream_t s);
+void launch_frame_barrier(unsigned long long *counter, unsigned long long target, unsigned long long timeout_ns, uint32_t *timed_out, cudaStream_t s);
 void launch_upload(const void *host_mapped, void *dst, size_t bytes, void *zero, size_t zero_bytes, cudaStream_t s);
 void launch_mip1(const uint32_t *l0, int w, int h, uint32_t *l1, const float *unorm8, cudaStream_t s);
 void launch_tex_f4(const uint32_t *l0, int n0, const uint32_t *l1, int n1, float4 *out, const float *unorm8, cudaStream_t s);

@@ -55,6 +55,7 @@ constexpr uint32_t PT_EXACT = 1u << 27;         /* e = A x + B y + C is exact ov
 constexpr uint32_t PT_NEG = 1u << 28;           /* (inexact form only) negative area: edge values are negated */
 constexpr uint32_t PT_FASTTEX = 1u << 29;       /* textured from the staged texture (dev_fasttex.cuh) */
 constexpr uint32_t PT_COINCIDENT = 1u << 30;    /* same geometry, texture coordinates and sampler as the previous triangle of the window */
+constexpr uint32_t PT_COINCIDENT2 = 1u << 31;   /* ... as the triangle before the previous one (the two halves of stacked quads alternate) */
 
 /* what one triangle contributes to every pixel of the tile: 14 x 16 B, read as broadcasts */
 struct __align__(16) PrepTri {
@@ -86,7 +87,8 @@ struct FillSmem {
     uint32_t rec[FILL_MAX_LIST];
     uint32_t sorted[FILL_MAX_LIST];
     float un[256];
-    uint8_t run_end[FILL_WINDOW];   /* for the first triangle of a run of coincident triangles: index behind the run's last */
+    uint8_t cls[FILL_WINDOW];       /* bits 0-5: the triangle's geometry class = index of the first triangle of the window it coincides
+                                     * with (through the chain of PT_COINCIDENT / PT_COINCIDENT2 links); bit 7: the class has one member */
     uint32_t acc;               /* scratch of fill_owns_tile */
     uint32_t tex_cfg;           /* state index whose texture is staged (lowest textured state of the list), ~0 = none */
     StagedTex st;
@@ -127,7 +129,7 @@ __device__ __forceinline__ bool coincident(const BatchDev &b, const TriRecord *r
     return a4.x == p4.x && a4.y == p4.y && a4.z == p4.z && same16(a8, p8) && a9.x == p9.x && a9.y == p9.y && alod == plod;   /* 1/w, u, v, lod (bitwise) */
 }
 
-__device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm, uint32_t r, uint32_t r_prev, int px0, int py0)
+__device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm, uint32_t r, uint32_t r_prev, uint32_t r_prev2, int px0, int py0)
 {
     const TriRecord *rec = b.records + r;
     const int4 row0 = __ldg(reinterpret_cast<const int4 *>(rec) + 0);
@@ -148,6 +150,7 @@ __device__ void prep_triangle(PrepTri &P, const BatchDev &b, const FillSmem &sm,
     const bool pos = area > 0;
     uint32_t word = cfg_index;
     if (r_prev != 0xFFFFFFFFu && coincident(b, rec, b.records + r_prev, cfg)) word |= PT_COINCIDENT;
+    else if (r_prev2 != 0xFFFFFFFFu && coincident(b, rec, b.records + r_prev2, cfg)) word |= PT_COINCIDENT2;
 
     /* raster.c:536-538: w0 = edge(v1, v2, p), w1 = edge(v2, v0, p), w2 = edge(v0, v1, p) */
     const int vx[3] = { row0.x, row0.z, row1.x }, vy[3] = { row0.y, row0.w, row1.y };
@@ -267,13 +270,15 @@ __device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &s
             if (word & PT_NEG) { e0[p] = -e0[p]; e1[p] = -e1[p]; e2[p] = -e2[p]; }
         }
     }
-    bool any = false;
+    bool any = false, cov[P];
 #pragma unroll
     for (int p = 0; p < P; p++) {
-        H.cov[p] = inb[p] && X[p] >= bx0 && X[p] <= bx1 && fminf(fminf(e0[p], e1[p]), e2[p]) >= 0.0f;
-        any = any || H.cov[p];
+        cov[p] = inb[p] && X[p] >= bx0 && X[p] <= bx1 && fminf(fminf(e0[p], e1[p]), e2[p]) >= 0.0f;
+        any = any || cov[p];
     }
-    if (!any) return false;
+    if (!any) return false;             /* H still holds what it held: the intermediates of another class stay usable */
+#pragma unroll
+    for (int p = 0; p < P; p++) H.cov[p] = cov[p];
     const float inv_area = T.ea.w;
 #pragma unroll
     for (int p = 0; p < P; p++) { H.b0[p] = e0[p] * inv_area; H.b1[p] = e1[p] * inv_area; H.b2[p] = e2[p] * inv_area; }
@@ -569,12 +574,16 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
         __syncthreads();                /* sorted list complete, texture queued; the previous window is no longer read */
         if (w0 == 0u && sm.st.id != nullptr) mbar_wait(&sm.tex_bar, 0u);        /* the staged texels have landed */
         if (threadIdx.x < n)        /* (a run of coincident triangles does not continue across windows) */
-            prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu, px0, py0);
+            prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu,
+                          threadIdx.x > 1u ? sm.sorted[w0 + threadIdx.x - 2] : 0xFFFFFFFFu, px0, py0);
         __syncthreads();
-        if (threadIdx.x < n) {      /* where the run of coincident triangles that starts here ends (every pixel row walks the runs) */
-            uint32_t e = threadIdx.x + 1u;
-            while (e < n && (__float_as_uint(sm.tri[e].eb.w) & PT_COINCIDENT)) e++;
-            sm.run_end[threadIdx.x] = (uint8_t)e;
+        if (threadIdx.x < n) {      /* geometry classes: follow the links back to the first triangle of the chain */
+            auto link = [&](uint32_t t) -> uint32_t { const uint32_t wd = __float_as_uint(sm.tri[t].eb.w); return (wd & PT_COINCIDENT) ? 1u : ((wd & PT_COINCIDENT2) ? 2u : 0u); };
+            const uint32_t t = threadIdx.x;
+            uint32_t c = t;
+            for (uint32_t l = link(c); l; l = link(c)) c -= l;
+            const bool followed = (t + 1u < n && link(t + 1u) == 1u) || (t + 2u < n && link(t + 2u) == 2u);
+            sm.cls[t] = (uint8_t)(c | ((c == t && !followed) ? 0x80u : 0u));
         }
         __syncthreads();
 
@@ -599,17 +608,23 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
                 }
                 S.r[p] = (float)(c & 0xFFu); S.g[p] = (float)((c >> 8) & 0xFFu); S.b[p] = (float)((c >> 16) & 0xFFu); S.a[p] = (float)(c >> 24);
             }
-#pragma unroll 1
-            for (uint32_t t = 0; t < n;) {
-                /* the run of coincident triangles that starts at t: coverage, barycentrics and texel once, then each member */
-                const uint32_t e = sm.run_end[t];
-                Shared H;
-                if (fill_shared<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, e == t + 1, H)) {
-                    constexpr int UNROLL = ((ON & FILL_PSEUDO) == FILL_PSEUDO) ? 2 : 1;     /* the small instance: two members in flight */
+            /* The intermediates H belong to a geometry class; a triangle of the class H holds skips straight to its own
+             * stages, a triangle of a class that covered none of this thread's pixels is skipped altogether.  Stacked
+             * quads (C3) give runs of one class where a tile lies inside one half of the quad, and two alternating
+             * classes in the tiles on the diagonal -- there a thread's pixels belong to one half (the other half misses
+             * and leaves H alone), except for the pixels ON the diagonal, which recompute. */
+            Shared H;
+            uint32_t held = 0xFFFFFFFFu, missed = 0xFFFFFFFFu;
+            constexpr int UNROLL = ((ON & FILL_PSEUDO) == FILL_PSEUDO) ? 2 : 1;     /* the small instance: two triangles in flight */
 #pragma unroll UNROLL
-                    for (; t < e; t++) fill_one<ON, OFF>(b, sm.tri[t], H, S);
+            for (uint32_t t = 0; t < n; t++) {
+                const uint32_t ce = sm.cls[t], c = ce & 63u;
+                if (c == missed) continue;
+                if (c != held) {
+                    if (!fill_shared<ON, OFF>(b, sm, sm.tri[t], px0, py0, Y, X, inb, (ce & 0x80u) != 0u, H)) { missed = c; continue; }
+                    held = c;
                 }
-                t = e;
+                fill_one<ON, OFF>(b, sm.tri[t], H, S);
             }
 #pragma unroll
             for (int p = 0; p < FILL_PX; p++) {

@@ -77,9 +77,10 @@ void launch_upload(const void *host_mapped, void *dst, size_t bytes, void *zero,
  * replaces an NCCL all-reduce used as a barrier (launch + protocol + two cross-stream event waits: 50-100 us per
  * frame on 8 GPUs) by one tiny kernel on the stream that is busy anyway.  The colour stores of the preceding kernels
  * are complete when this kernel starts (stream order); the fence orders them before the arrival for good measure.
- * A participant that never arrives would make the others spin for ever: after 10 s the kernel traps instead, which
- * surfaces as a CUDA error on the host. */
-__global__ void k_frame_barrier(unsigned long long *counter, unsigned long long target)
+ * A participant that never arrives would make the others spin for ever: after timeout_ns (MTGL_BARRIER_TIMEOUT_S, default
+ * 10 s, 0 = wait for ever) the kernel gives up, says so in mapped host memory and ends normally -- the host reports
+ * MTGL_E_CUDA from the next mtgl_dev_finish, the context stays usable (a trap would poison it on every rank). */
+__global__ void k_frame_barrier(unsigned long long *counter, unsigned long long target, unsigned long long timeout_ns, uint32_t *timed_out)
 {
     __threadfence_system();
     atomicAdd_system(counter, 1ull);
@@ -89,14 +90,14 @@ __global__ void k_frame_barrier(unsigned long long *counter, unsigned long long 
         __nanosleep(200);
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 10000000000ull) __trap();
+        if (timeout_ns && t - t0 > timeout_ns) { *timed_out = 1u; break; }
     }
     __threadfence_system();
 }
 
-void launch_frame_barrier(unsigned long long *counter, unsigned long long target, cudaStream_t s)
+void launch_frame_barrier(unsigned long long *counter, unsigned long long target, unsigned long long timeout_ns, uint32_t *timed_out, cudaStream_t s)
 {
-    k_frame_barrier<<<1, 1, 0, s>>>(counter, target);
+    k_frame_barrier<<<1, 1, 0, s>>>(counter, target, timeout_ns, timed_out);
     note_launch();
 }
 

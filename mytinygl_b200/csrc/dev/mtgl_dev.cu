@@ -82,6 +82,8 @@ struct mtgl_dev {
     uint64_t batch_serial = 0;
     DevCounters *counters = nullptr;
     DevCounters *h_counters = nullptr;      /* pinned */
+    uint32_t *h_barrier_timed_out = nullptr; /* pinned, mapped: set by k_frame_barrier when a participant never arrived */
+    unsigned long long barrier_timeout_ns = 10000000000ull;
 
     uint8_t *pinned[2] = { nullptr, nullptr };
     size_t pinned_cap[2] = { 0, 0 };
@@ -435,6 +437,9 @@ int mtgl_dev_create(int32_t width, int32_t height, int32_t device, mtgl_dev **ou
     if (ce == cudaSuccess) ce = cudaMalloc(&d->unorm8, 256 * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&d->counters, sizeof(DevCounters));
     if (ce == cudaSuccess) ce = cudaMallocHost(&d->h_counters, sizeof(DevCounters));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&d->h_barrier_timed_out, sizeof(uint32_t));
+    if (ce == cudaSuccess) *d->h_barrier_timed_out = 0u;
+    if (const char *e = std::getenv("MTGL_BARRIER_TIMEOUT_S")) d->barrier_timeout_ns = (unsigned long long)(std::atof(e) * 1e9);
     for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&d->pinned_ev[i], cudaEventDisableTiming);
     for (mtgl_dev::EvSet &es : d->evset) {
         if (ce == cudaSuccess) ce = cudaEventCreate(&es.start);
@@ -493,6 +498,7 @@ void mtgl_dev_destroy(mtgl_dev *d)
     if (d->unorm8) cudaFree(d->unorm8);
     if (d->counters) cudaFree(d->counters);
     if (d->h_counters) cudaFreeHost(d->h_counters);
+    if (d->h_barrier_timed_out) cudaFreeHost(d->h_barrier_timed_out);
     for (int i = 0; i < 2; i++) {
         if (d->pinned[i]) cudaFreeHost(d->pinned[i]);
         if (d->pinned_ev[i]) cudaEventDestroy(d->pinned_ev[i]);
@@ -1100,7 +1106,12 @@ int mtgl_dev_finish(mtgl_dev *d)
     if (!d) return MTGL_E_INVALID;
     CU(cudaSetDevice(d->device));
     if (int prc_ = resolve_pending(d)) return prc_;
-    return sync_all_streams(d);
+    if (int rc = sync_all_streams(d)) return rc;
+    if (*d->h_barrier_timed_out) {
+        *d->h_barrier_timed_out = 0u;
+        return fail(d, MTGL_E_CUDA, "frame barrier timed out: a participant of the frame never arrived (MTGL_BARRIER_TIMEOUT_S)");
+    }
+    return MTGL_OK;
 }
 
 int mtgl_dev_read_framebuffer(mtgl_dev *d, int32_t y0, int32_t y1, uint32_t *color, float *depth, uint8_t *stencil)
@@ -1285,10 +1296,10 @@ int mtgl_dev_frame_barrier(mtgl_dev *d, uint32_t participants)
             const size_t o = (size_t)d->band_y0 * d->width, n = (size_t)(d->band_y1 - d->band_y0) * d->width;
             CU(cudaMemcpyAsync(d->present + o, d->color + o, n * 4, cudaMemcpyDeviceToDevice, d->present_stream));
         }
-        launch_frame_barrier(ctr, d->barrier_epoch * participants, d->present_stream);
+        launch_frame_barrier(ctr, d->barrier_epoch * participants, d->barrier_timeout_ns, d->h_barrier_timed_out, d->present_stream);
         CU(cudaEventRecord(d->present_ev, d->present_stream));
         d->present_busy = true;
-    } else launch_frame_barrier(ctr, d->barrier_epoch * participants, d->stream);
+    } else launch_frame_barrier(ctr, d->barrier_epoch * participants, d->barrier_timeout_ns, d->h_barrier_timed_out, d->stream);
     CU(cudaGetLastError());
     return MTGL_OK;
 }
