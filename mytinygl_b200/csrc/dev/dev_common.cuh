@@ -500,7 +500,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
                    const RasterPlan &plan, cudaStream_t s, cudaEvent_t ev_vis, cudaEvent_t ev_shade);
 void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t fill_mode, uint32_t all_on, uint32_t any_on,
                  cudaStream_t s);
-void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, cudaStream_t s);
+void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t all_on, uint32_t any_on, cudaStream_t s);
 void launch_vis_unordered(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t planes, uint32_t depth_func,
                           bool all_range01, cudaStream_t s);
 void launch_draw_pixels(const ::mtgl_pixel_rect &rect, const uint8_t *src, const FrameTargets &fb, const float *unorm8, cudaStream_t s);

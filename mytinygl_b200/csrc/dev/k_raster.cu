@@ -800,7 +800,7 @@ void launch_raster(const BatchDev &b, const FrameTargets &fb, const ClearOp &cle
         }
         cudaEventRecord(ev_vis, s);
         if (plan.color_gate) cudaStreamWaitEvent(s, plan.color_gate, 0);       /* visibility above ran ahead; colour waits */
-        if (planes & 1u) launch_shade(b, fb, clear, s);
+        if (planes & 1u) launch_shade(b, fb, clear, plan.in_order_all, plan.in_order_any, s);
         cudaEventRecord(ev_shade, s);
         if (any_in_order) {
             k_raster<false, false><<<tiles, RASTER_THREADS, sizeof(RasterSmem), s>>>(b, fb, clear, planes, 1u, plan.fill_mode);

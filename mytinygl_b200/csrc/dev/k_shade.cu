@@ -28,8 +28,8 @@
 #include "dev_common.cuh"
 #include "dev_shade.cuh"
 #include "dev_fasttex.cuh"
+#include "dev_fill.cuh"
 
-#include <cstdlib>
 
 namespace mtgl_dev_impl {
 
@@ -59,8 +59,11 @@ __device__ __noinline__ uint32_t shade_general(const BatchDev &b, const float *u
     return color_pack(c);      /* raster.c:719-721: color_pack clamps */
 }
 
-/* P: pixels per thread and iteration of pass 2; CTAS: CTAs per SM the register budget is set for */
-template <int SPLIT, int P, int CTAS>
+/* P: pixels per thread and iteration of pass 2; CTAS: CTAs per SM the register budget is set for.
+ * ON / OFF: RasterCfg flags (and dev_fill.cuh pseudo-flags) that every state of the pass has / that none has -- decided at
+ * compile time instead of per pixel (the instance for the plain textured mix: smooth shading, GL_MODULATE, no fog, no
+ * per-fragment lighting; everything else runs <0, 0>). */
+template <int SPLIT, int P, int CTAS, uint32_t ON, uint32_t OFF>
 __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, FrameTargets fb, ClearOp clr)
 {
     constexpr int ROWS = TILE_H / SPLIT;        /* rows of the tile this CTA owns */
@@ -179,22 +182,23 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
             const TriRecord *rec = b.records + r[p];
             const RasterCfg *cfg = one_cfg ? &sm.cfg0 : b.cfgs + (sflags[p] & STATE_INDEX_MASK);
             const uint32_t flags = cfg->flags;
+            auto has = [&](uint32_t bit) -> bool { return (ON & bit) ? true : ((OFF & bit) ? false : (flags & bit) != 0u); };
             TriAttr A;
             load_attr(A, rec);
             /* per-fragment lighting (raster.c:592-615) and textures without a usable float4 copy take the general path */
-            general[p] = (flags & RC_LIGHTING) && ((flags & RC_PHONG) || ((sflags[p] >> 31) && (flags & RC_TWO_SIDE)));
-            if (flags & RC_TEXTURED) general[p] = general[p] || !cfg->fast_tex || !(sflags[p] & STATE_BOUNDED_BIT);
+            general[p] = has(RC_LIGHTING) && (has(RC_PHONG) || ((sflags[p] >> 31) && has(RC_TWO_SIDE)));
+            if (has(RC_TEXTURED)) general[p] = general[p] || !cfg->fast_tex || !(sflags[p] & STATE_BOUNDED_BIT);
             Color4 c;
-            if (flags & RC_FLAT) c = { A.col2.x, A.col2.y, A.col2.z, A.col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
+            if (has(RC_FLAT)) c = { A.col2.x, A.col2.y, A.col2.z, A.col2.w };        /* third vertex of the sub-triangle (raster.c:583-585) */
             else {
                 c.r = A.col0.x * b0[p] + A.col1.x * b1[p] + A.col2.x * b2[p];
                 c.g = A.col0.y * b0[p] + A.col1.y * b1[p] + A.col2.y * b2[p];
                 c.b = A.col0.z * b0[p] + A.col1.z * b1[p] + A.col2.z * b2[p];
                 c.a = A.col0.w * b0[p] + A.col1.w * b1[p] + A.col2.w * b2[p];
             }
-            if ((flags & RC_TEXTURED) && !general[p]) {          /* raster.c:618-669 */
+            if (has(RC_TEXTURED) && !general[p]) {          /* raster.c:618-669 */
                 float u, v2;
-                if (flags & RC_PERSPECTIVE) {
+                if (has(RC_PERSPECTIVE)) {
                     const float u0w = A.u0 * A.w0, v0w = A.v0 * A.w0, u1w = A.u1 * A.w1, v1w = A.v1 * A.w1, u2w = A.u2 * A.w2, v2w = A.v2 * A.w2;
                     const float uw = b0[p] * u0w + b1[p] * u1w + b2[p] * u2w;
                     const float vw_ = b0[p] * v0w + b1[p] * v1w + b2[p] * v2w;
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
                 const uint32_t plan = sampler_plan(cfg, A.lod, cl);
                 const TexView tv = { cfg->tex_f4, cfg->tex_w, cfg->tex_h, cfg->tex_w1, cfg->tex_h1, cfg->tex_w * cfg->tex_h };
                 const float4 t = fast_sample<true>(tv, plan, cl, u, v2);
-                switch (cfg->tex_env_mode) {
+                switch ((ON & FILL_MODULATE) ? (uint32_t)G_MODULATE : cfg->tex_env_mode) {
                 case G_REPLACE: c = { t.x, t.y, t.z, t.w }; break;
                 case G_DECAL: c = color_lerp_rgb(c, { t.x, t.y, t.z, t.w }, t.w); break;
                 case G_BLEND: {
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
                 default: c = { c.r * t.x, c.g * t.y, c.b * t.z, c.a * t.w }; break;
                 }
             }
-            if (flags & RC_FOG) {                                   /* raster.c:672-705; result alpha = fog colour alpha */
+            if (has(RC_FOG)) {                                   /* raster.c:672-705; result alpha = fog colour alpha */
                 const float fc = b0[p] * A.ez0 + b1[p] * A.ez1 + b2[p] * A.ez2;
                 const Color4 fogc = { cfg->fog_color[0], cfg->fog_color[1], cfg->fog_color[2], cfg->fog_color[3] };
                 c = color_lerp_rgb(fogc, c, fog_factor(cfg, fc));
@@ -258,23 +262,24 @@ __global__ void __launch_bounds__(SHADE_THREADS, CTAS) k_shade(BatchDev b, Frame
     }
 }
 
-void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, cudaStream_t s)
+/* the plain textured mix (C4 / C5): every state textured with GL_MODULATE, smooth-shaded, no fog, no per-fragment lighting */
+constexpr uint32_t SHADE_PLAIN_ON = RC_TEXTURED | FILL_MODULATE;
+constexpr uint32_t SHADE_PLAIN_OFF = RC_FLAT | RC_FOG | RC_PHONG | RC_TWO_SIDE;
+
+/* all_on / any_on: AND / OR of the RasterCfg flags (+ pseudo-flags, dev_fill.cuh) of the pass's states.
+ * One pixel per thread at 64 registers and 4 CTAs per SM; measured slower on C4: two pixels at 2 CTAs (0.168 ms against
+ * 0.148), one pixel at 3 CTAs (0.153), two pixels at 3 CTAs with a few spilled registers (0.157). */
+void launch_shade(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear, uint32_t all_on, uint32_t any_on, cudaStream_t s)
 {
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0) return;
-    /* MTGL_SHADE_VARIANT: A/B switch for profiling -- 0: two pixels per thread at 2 CTAs / SM, 1: one pixel at 3 CTAs / SM,
-     * 2: two pixels at 3 CTAs / SM (a few spilled registers), 3: one pixel at 4 CTAs / SM (64 registers, ~100 B spilled) */
-    static const int variant = [] { const char *e = std::getenv("MTGL_SHADE_VARIANT"); return e ? std::atoi(e) : 3; }();
+    const bool plain = (all_on & SHADE_PLAIN_ON) == SHADE_PLAIN_ON && (any_on & SHADE_PLAIN_OFF) == 0u;
     if (small_grid(tiles)) {
-        if (variant == 3) k_shade<4, 1, 4><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
-        else if (variant == 1) k_shade<4, 1, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
-        else if (variant == 2) k_shade<4, 2, 3><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
-        else k_shade<4, 2, 2><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        if (plain) k_shade<4, 1, 4, SHADE_PLAIN_ON, SHADE_PLAIN_OFF><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else k_shade<4, 1, 4, 0u, 0u><<<tiles * 4u, SHADE_THREADS, 0, s>>>(b, fb, clear);
     } else {
-        if (variant == 3) k_shade<1, 1, 4><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
-        else if (variant == 1) k_shade<1, 1, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
-        else if (variant == 2) k_shade<1, 2, 3><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
-        else k_shade<1, 2, 2><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        if (plain) k_shade<1, 1, 4, SHADE_PLAIN_ON, SHADE_PLAIN_OFF><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
+        else k_shade<1, 1, 4, 0u, 0u><<<tiles, SHADE_THREADS, 0, s>>>(b, fb, clear);
     }
     note_launch();
 }

@@ -252,6 +252,42 @@ def test_pipelined_transfers_match_the_synchronous_path(b200):
     b200.destroy()
 
 
+def test_frame_barrier_times_out_without_poisoning_the_context(b200, front_oracle, monkeypatch):
+    """mtgl_dev_frame_barrier with a participant that never arrives: after MTGL_BARRIER_TIMEOUT_S the barrier kernel gives
+    up, mtgl_dev_finish reports it (glFinish: GL_INVALID_OPERATION) and the context keeps rendering correctly -- the
+    kernel used to trap, which left a sticky CUDA error behind on every rank."""
+    import ctypes
+    monkeypatch.setenv("MTGL_BARRIER_TIMEOUT_S", "0.2")
+    L = b200.lib
+    L.mtgl_dev_frame_barrier.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+    name, w, h, variant = "c1_suzanne", 320, 240, 0
+
+    def twice(lib, between):
+        """the scene, `between`, then the planes cleared and the scene again in the SAME context"""
+        lib.create(w, h)
+        assert lib.lib.scene_render(name.encode(), w, h, variant) == 0
+        between(lib)
+        lib.lib.glClearColor(ctypes.c_float(0.25), ctypes.c_float(0.5), ctypes.c_float(0.75), ctypes.c_float(1.0))
+        lib.lib.glClearStencil(0)
+        lib.lib.glClear(0x4000 | 0x0100 | 0x0400)
+        assert lib.lib.scene_render(name.encode(), w, h, variant) == 0
+        out = lib.read()
+        assert lib.lib.glGetError() == 0
+        lib.destroy()
+        return out
+
+    def stuck_barrier(lib):
+        assert L.mtgl_dev_frame_barrier(lib.device(), 2) == 0     # two participants, one process: nobody else will come
+        L.glFinish()
+        assert L.glGetError() == 0x0502                           # GL_INVALID_OPERATION: the finish saw the timeout
+        assert L.glGetError() == 0
+
+    got = twice(b200, stuck_barrier)                              # the context is alive and exact afterwards
+    want = twice(front_oracle, lambda lib: lib.lib.glFinish())
+    for a, b, plane in zip(got[:3], want[:3], ("color", "depth", "stencil")):
+        assert np.array_equal(a, b), plane
+
+
 def test_orphaned_buffer_filled_on_a_side_stream(b200):
     """mtgl_context_buffer_orphan (include/mtgl_context.h): the buffer name gets fresh storage every frame, the application
     fills it on a stream of its own (here: a device-to-device copy, in bench.py a host slice + NCCL all-gather) while earlier
