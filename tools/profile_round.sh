@@ -25,7 +25,7 @@ if [ "$WHAT" = capture ]; then
       -o $O/${TAG}_prof_c3 -f $B --workload c3 --steps 2 --warmup 3 > $O/${TAG}_ncu_c3.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:'k_setup|k_vis|k_shade|k_bin' -s 15 -c 5 \
       -o $O/${TAG}_prof_c5 -f $B --workload c5 --steps 2 --warmup 3 > $O/${TAG}_ncu_c5.log 2>&1
-  tail -1 $O/${TAG}_ncu_c4.log $O/${TAG}_ncu_c3.log $O/${TAG}_ncu_c5.log
+  for wl in c4 c3 c5; do tail -n 1 $O/${TAG}_ncu_$wl.log; done
   du -sh $O; ls -la $O/*.ncu-rep
   exit 0
 fi
