@@ -514,7 +514,7 @@ uint64_t kernel_launch_count();
 /* A tile grid well below one wave of 8-warp CTAs (148 SMs x 4 = 592): the band of a multi-GPU frame (measured: the
  * latency shapes win at 240-300 tiles, lose at 540).  The tile kernels
  * then run in their latency shapes -- more warps per tile (k_vis<512>), sub-tile CTAs (k_shade<4>). */
-bool small_grid(uint32_t tiles);      /* tiles <= 400, or what MTGL_GRID_SHAPE=small|large forces (tests cover both shapes at any size) */
+bool small_grid(uint32_t tiles, uint32_t limit = 400u);      /* tiles <= limit, or what MTGL_GRID_SHAPE=small|large forces (tests cover both shapes at any size) */
 
 } // namespace mtgl_dev_impl
 

@@ -663,7 +663,13 @@ void launch_fill(const BatchDev &b, const FrameTargets &fb, const ClearOp &clear
     }
     const uint32_t tiles = (uint32_t)(fb.tiles_x * fb.tile_rows);
     if (tiles == 0 || fill_mode == FILL_OFF) return;
-    const uint32_t split = small_grid(tiles) ? 4u : 1u;     /* (1, 2, 4 or 8: the tile is walked in eight passes of eight rows) */
+    /* (1, 2, 4 or 8: the tile is walked in eight passes of eight rows.)  Tiles differ in cost by up to 4x -- layers whose
+     * alpha test passes, lists that hold both halves of stacked quads -- so on the band of a multi-GPU frame a few
+     * whole-tile CTAs outlast everything else: up to FILL_SPLIT_TILES tiles they are cut in four.  Measured on C3
+     * (emulated bands): 1020 tiles 0.82 -> 0.71 ms, 540 tiles 0.79 -> 0.45; the full frame (2040 tiles) 1.18 -> 1.34, hence
+     * the bound. */
+    constexpr uint32_t FILL_SPLIT_TILES = 1100u;
+    const uint32_t split = small_grid(tiles, FILL_SPLIT_TILES) ? 4u : 1u;
     /* all_on / any_on: AND / OR of the RasterCfg flags of the pass's in-order states */
     if ((all_on & FILL_FASTER_ON) == FILL_FASTER_ON && (any_on & FILL_FAST_OFF) == 0u)
         k_fill<FILL_FASTER_ON, FILL_FAST_OFF><<<tiles * split, FILL_THREADS, sizeof(FillSmem), s>>>(b, fb, clear, planes, fill_mode, split);

@@ -28,13 +28,13 @@ static unsigned long long g_launches = 0;
 uint64_t kernel_launch_count() { return g_launches; }
 void note_launch() { g_launches++; }
 
-bool small_grid(uint32_t tiles)
+bool small_grid(uint32_t tiles, uint32_t limit)
 {
     if (const char *e = std::getenv("MTGL_GRID_SHAPE")) {
         if (e[0] == 's') return true;
         if (e[0] == 'l') return false;
     }
-    return tiles <= 400u;
+    return tiles <= limit;
 }
 
 __device__ __forceinline__ uint32_t find_draw(const uint32_t *base, uint32_t n, uint32_t g)
