@@ -218,7 +218,7 @@ __device__ __noinline__ void slow_texel(const RasterCfg *cfg, const float *un, f
     *out = make_float4(tex_channel(T, 0, un), tex_channel(T, 8, un), tex_channel(T, 16, un), tex_channel(T, 24, un));
 }
 
-/* ---------------------------------------------------------------- one run of coincident triangles over this thread's pixels */
+/* ---------------------------------------------------------------- one class of coincident triangles over this thread's pixels */
 /* Pixel state of a thread: colour channels as integral floats 0..255 (the byte the plane holds), depth, stencil. */
 struct PixelState {
     float r[FILL_PX], g[FILL_PX], b[FILL_PX], a[FILL_PX];
@@ -226,16 +226,16 @@ struct PixelState {
     uint32_t stencil[FILL_PX];
 };
 
-/* what the triangles of a run share, per pixel */
+/* what the triangles of a geometry class share, per pixel */
 struct Shared {
     bool cov[FILL_PX];                                  /* inside the triangle, its box and the framebuffer */
     float b0[FILL_PX], b1[FILL_PX], b2[FILL_PX];        /* barycentrics (raster.c:541-543) */
     float tr[FILL_PX], tg[FILL_PX], tb[FILL_PX], ta[FILL_PX];   /* the sampled texel */
 };
 
-/* coverage (raster.c:536-540), barycentrics, texture coordinates (618-637) and the texel of the run's first triangle.
- * `single`: the run has one member, so its alpha test may discard before the colour channels are filtered.
- * Returns false when this thread has nothing to do for the whole run. */
+/* coverage (raster.c:536-540), barycentrics, texture coordinates (618-637) and the texel of a class, from its first
+ * triangle that reaches this thread.  `single`: the class has one member, so its alpha test may discard before the colour
+ * channels are filtered.  Returns false -- and leaves H alone -- when none of this thread's pixels is covered. */
 template <uint32_t ON, uint32_t OFF>
 __device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &sm, const PrepTri &T, int px0, int py0, int Y,
                                             const int (&X)[FILL_PX], const bool (&inb)[FILL_PX], bool single, Shared &H)
@@ -362,7 +362,7 @@ __device__ __forceinline__ bool fill_shared(const BatchDev &b, const FillSmem &s
     return true;
 }
 
-/* One triangle of the run: depth value, stencil test + ops, depth test (raster.c:546-587), colour (581-591), alpha test
+/* One triangle of the class H holds: depth value, stencil test + ops, depth test (raster.c:546-587), colour (581-591), alpha test
  * (640-643), texenv (645-669), fog (672-705), late depth write (707-710), blending (712-717), masked write (719-721, 20-45). */
 template <uint32_t ON, uint32_t OFF>
 __device__ __forceinline__ void fill_one(const BatchDev &b, const PrepTri &T, const Shared &H, PixelState &S)
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) k_fill(BatchDev b, FrameTarge
         const uint32_t n = min((uint32_t)FILL_WINDOW, L - w0);
         __syncthreads();                /* sorted list complete, texture queued; the previous window is no longer read */
         if (w0 == 0u && sm.st.id != nullptr) mbar_wait(&sm.tex_bar, 0u);        /* the staged texels have landed */
-        if (threadIdx.x < n)        /* (a run of coincident triangles does not continue across windows) */
+        if (threadIdx.x < n)        /* (a class of coincident triangles does not continue across windows) */
             prep_triangle(sm.tri[threadIdx.x], b, sm, sm.sorted[w0 + threadIdx.x], threadIdx.x ? sm.sorted[w0 + threadIdx.x - 1] : 0xFFFFFFFFu,
                           threadIdx.x > 1u ? sm.sorted[w0 + threadIdx.x - 2] : 0xFFFFFFFFu, px0, py0);
         __syncthreads();
