@@ -43,3 +43,35 @@ def test_rebalanced_moves_rows_towards_the_slow_ranks_and_keeps_a_partition():
     # a rank that is far too slow cannot squeeze its neighbours below the quantum
     tight = b.rebalanced([0, 16, 32, 2160], [1.0, 1.0, 100.0], 2160)
     assert all(y1 - y0 >= 16 for y0, y1 in zip(tight, tight[1:])) and tight[-1] == 2160
+
+
+def test_upload_chunking_rule():
+    b = _bench()
+    nbytes = 3089856 * 32                      # C4's vertex buffer
+    for world in (2, 4, 8):
+        assert b.nbytes_ok(nbytes, 4 * world)  # four chunks of one slice per rank, 16-byte aligned
+    assert not b.nbytes_ok(0, 8)
+    assert not b.nbytes_ok(1000, 8)            # would leave unaligned slices: the caller falls back to one piece
+
+
+def test_timed_e2e_reports_the_median_run():
+    b = _bench()
+    calls = {"steps": 0, "finishes": 0}
+    clock = {"t": 0.0}
+    cost = iter([0.0] * 4 + [1.0] * 5 + [9.0] * 5 + [2.0] * 5)       # warm-up, then three runs of five steps: one hiccup run
+
+    def step(k):
+        calls["steps"] += 1
+        clock["t"] += next(cost)
+
+    def finish():
+        calls["finishes"] += 1
+
+    real = b.time.perf_counter
+    b.time.perf_counter = lambda: clock["t"]
+    try:
+        median, runs = b.timed_e2e(step, finish, 5, None, None, 0)
+    finally:
+        b.time.perf_counter = real
+    assert calls == {"steps": 4 + 15, "finishes": 1 + 3}
+    assert runs == [5.0, 45.0, 10.0] and median == 10.0
